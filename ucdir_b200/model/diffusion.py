@@ -1,0 +1,198 @@
+"""Sampler mirror: GaussianDiffusion / ResiGaussianGuideDY with the reference's surface
+(model/diffusion.py:73-211, 296-304, 436-478 in the reference).
+
+Same constructor arguments, buffers (the 12 fp32 schedule vectors + the float64
+numpy attribute `sqrt_alphas_cumprod_prev`), attributes (`denoise_fn`, `predictor`,
+`pre_initx`, `num_timesteps`, `betas`) and methods (`set_loss`,
+`set_new_noise_schedule`, `p_sample`, `p_sample_loop`, `super_resolution`, `sample`).
+The per-step arithmetic (UNet forward over the tile batch, tile stitch and posterior
+update) runs in the CUDA engine; with torch.distributed initialised and
+UCDIR_SHARD=tiles the tiles of one step are sharded over ranks with one all-gather
+per step.  Training losses are out of scope and raise.
+"""
+from __future__ import annotations
+
+import math
+import os
+from functools import partial
+
+import numpy as np
+import torch
+from torch import nn
+
+from .ucdir import UNetSeeInDark
+
+
+def _warmup_beta(linear_start, linear_end, n_timestep, warmup_frac):
+    betas = linear_end * np.ones(n_timestep, dtype=np.float64)
+    warmup_time = int(n_timestep * warmup_frac)
+    betas[:warmup_time] = np.linspace(linear_start, linear_end, warmup_time, dtype=np.float64)
+    return betas
+
+
+def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):
+    """float64 beta vector; follows model/diffusion.py:23-54."""
+    if schedule == "quad":
+        return np.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=np.float64) ** 2
+    if schedule == "linear":
+        return np.linspace(linear_start, linear_end, n_timestep, dtype=np.float64)
+    if schedule == "warmup10":
+        return _warmup_beta(linear_start, linear_end, n_timestep, 0.1)
+    if schedule == "warmup50":
+        return _warmup_beta(linear_start, linear_end, n_timestep, 0.5)
+    if schedule == "const":
+        return linear_end * np.ones(n_timestep, dtype=np.float64)
+    if schedule == "jsd":
+        return 1.0 / np.linspace(n_timestep, 1, n_timestep, dtype=np.float64)
+    if schedule == "cosine":
+        ts = torch.arange(n_timestep + 1, dtype=torch.float64) / n_timestep + cosine_s
+        alphas = torch.cos(ts / (1 + cosine_s) * math.pi / 2).pow(2)
+        alphas = alphas / alphas[0]
+        return (1 - alphas[1:] / alphas[:-1]).clamp(max=0.999).numpy()
+    raise NotImplementedError(schedule)
+
+
+class GaussianDiffusion(nn.Module):
+    def __init__(self, denoise_fn, image_size, channels=3, loss_type="l1", conditional=True, schedule_opt=None):
+        super().__init__()
+        self.channels = channels
+        self.image_size = image_size
+        self.denoise_fn = denoise_fn
+        self.loss_type = loss_type
+        self.conditional = conditional
+        self._noise_source = None      # test hook: callable(shape) -> tensor, replaces torch.randn
+        self._sched_host = None
+
+    # ---- reference surface --------------------------------------------------------------
+    def set_loss(self, device):
+        """model/diffusion.py:93-99.  Kept so DDPM.__init__ (model/model.py:59) works; inference never uses it."""
+        if self.loss_type == "l1":
+            self.loss_func = nn.L1Loss(reduction="sum").to(device)
+        elif self.loss_type == "l2":
+            self.loss_func = nn.MSELoss(reduction="sum").to(device)
+        else:
+            raise NotImplementedError()
+
+    def set_new_noise_schedule(self, schedule_opt, device):
+        """model/diffusion.py:101-148: float64 derivations, fp32 buffers, same names; callable repeatedly."""
+        to_torch = partial(torch.tensor, dtype=torch.float32, device=device)
+        betas = make_beta_schedule(schedule=schedule_opt["schedule"], n_timestep=schedule_opt["n_timestep"],
+                                   linear_start=schedule_opt["linear_start"], linear_end=schedule_opt["linear_end"])
+        alphas = 1.0 - betas
+        alphas_cumprod = np.cumprod(alphas, axis=0)
+        alphas_cumprod_prev = np.append(1.0, alphas_cumprod[:-1])
+        self.sqrt_alphas_cumprod_prev = np.sqrt(np.append(1.0, alphas_cumprod))
+        self.num_timesteps = int(betas.shape[0])
+        posterior_variance = betas * (1.0 - alphas_cumprod_prev) / (1.0 - alphas_cumprod)
+        host = {
+            "betas": betas,
+            "alphas_cumprod": alphas_cumprod,
+            "alphas_cumprod_prev": alphas_cumprod_prev,
+            "sqrt_alphas_cumprod": np.sqrt(alphas_cumprod),
+            "sqrt_one_minus_alphas_cumprod": np.sqrt(1.0 - alphas_cumprod),
+            "log_one_minus_alphas_cumprod": np.log(1.0 - alphas_cumprod),
+            "sqrt_recip_alphas_cumprod": np.sqrt(1.0 / (alphas_cumprod + 1e-10)),
+            "sqrt_recipm1_alphas_cumprod": np.sqrt(1.0 / (alphas_cumprod + 1e-10) - 1),
+            "posterior_variance": posterior_variance,
+            "posterior_log_variance_clipped": np.log(np.maximum(posterior_variance, 1e-20)),
+            "posterior_mean_coef1": betas * np.sqrt(alphas_cumprod_prev) / (1.0 - alphas_cumprod),
+            "posterior_mean_coef2": (1.0 - alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - alphas_cumprod),
+        }
+        for name, val in host.items():
+            self.register_buffer(name, to_torch(val))
+        # host-side fp32 copies: the per-step scalars are kernel arguments, no per-step H2D
+        self._sched_host = {k: np.asarray(v, dtype=np.float64).astype(np.float32) for k, v in host.items()}
+        if hasattr(self.denoise_fn, "engine") and getattr(self.denoise_fn, "_engine", None) is not None:
+            self.denoise_fn._engine.invalidate_schedule()
+
+    # ---- sampler -------------------------------------------------------------------------
+    def _randn(self, shape, device):
+        if self._noise_source is not None:
+            return self._noise_source(tuple(shape)).to(device=device, dtype=torch.float32)
+        return torch.randn(shape, device=device)
+
+    def _step_scalars(self, t):
+        """The five per-step scalars of model/diffusion.py:150-158,183 as fp32 values."""
+        s = self._sched_host
+        if s is None:  # schedule buffers arrived through load_state_dict only
+            s = self._sched_host = {k: getattr(self, k).detach().float().cpu().numpy() for k in (
+                "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                "posterior_mean_coef2", "posterior_log_variance_clipped")}
+        sigma = np.exp(np.float32(0.5) * s["posterior_log_variance_clipped"][t], dtype=np.float32)
+        return (float(s["sqrt_recip_alphas_cumprod"][t]), float(s["sqrt_recipm1_alphas_cumprod"][t]),
+                float(s["posterior_mean_coef1"][t]), float(s["posterior_mean_coef2"][t]), float(sigma))
+
+    def noise_level(self, t):
+        """fp32 value of sqrt_alphas_cumprod_prev[t+1] (model/diffusion.py:162-163)."""
+        return float(np.float32(self.sqrt_alphas_cumprod_prev[t + 1]))
+
+    @torch.no_grad()
+    def p_sample(self, x, t, clip_denoised=True, condition_x=None, kwargs={}):
+        """model/diffusion.py:160-183 for one step on explicit tensors (generic entry; the loop below
+        uses a resident session instead)."""
+        if condition_x is None:
+            raise NotImplementedError("ucdir_b200: unconditional sampling is not on the hot path")
+        sess = self.denoise_fn.engine().session(condition_x, kwargs["guide"])
+        noise = self._randn(x.shape, x.device) if t > 0 else None
+        out = torch.empty_like(x)
+        sess.step(x.contiguous(), out, self.noise_level(t), self._step_scalars(t), noise, clip_denoised)
+        return out
+
+    @torch.no_grad()
+    def p_sample_loop(self, x_in, continous=False, kwargs={}):
+        """model/diffusion.py:185-211 (conditional branch): ancestral sampling, snapshots every
+        1|(T//10) steps.  The reference grows ret_img with torch.cat per snapshot; here the rows are
+        preallocated and written in place."""
+        if not self.conditional:
+            raise NotImplementedError("ucdir_b200: unconditional sampling is not on the hot path")
+        T = self.num_timesteps
+        sample_inter = 1 | (T // 10)
+        x = x_in.contiguous().float()
+        b = x.shape[0]
+        device = x.device
+        n_snap = sum(1 for i in range(T) if i % sample_inter == 0)
+        ret = torch.empty((b * (1 + n_snap),) + tuple(x.shape[1:]), device=device, dtype=torch.float32)
+        ret[:b] = x
+        sess = self.denoise_fn.engine().session(x, kwargs["guide"], levels=[self.noise_level(t) for t in range(T)])
+        img = self._randn(x.shape, device).contiguous()
+        nxt = torch.empty_like(img)
+        row = 1
+        for i in reversed(range(T)):
+            noise = self._randn(x.shape, device) if i > 0 else None
+            sess.step(img, nxt, self.noise_level(i), self._step_scalars(i), noise, True, level_index=i)
+            img, nxt = nxt, img
+            if i % sample_inter == 0:
+                ret[row * b:(row + 1) * b] = img
+                row += 1
+        return ret if continous else ret[-1]
+
+    @torch.no_grad()
+    def sample(self, batch_size=1, continous=False):
+        raise NotImplementedError("ucdir_b200: unconditional sample() is not on the hot path")
+
+    @torch.no_grad()
+    def super_resolution(self, x_in, continous=False):
+        """model/diffusion.py:302-304."""
+        return self.p_sample_loop(x_in, continous)
+
+    def p_losses(self, x_in, noise=None):
+        raise NotImplementedError("ucdir_b200 is the inference hot path; training losses stay in the reference")
+
+    def forward(self, x, *args, **kwargs):
+        return self.p_losses(x, *args, **kwargs)
+
+
+class ResiGaussianGuideDY(GaussianDiffusion):
+    """model/diffusion.py:436-478: residual diffusion guided by the initial predictor."""
+
+    def __init__(self, denoise_fn, image_size, channels=3, loss_type="l1", conditional=True, schedule_opt=None):
+        super().__init__(denoise_fn, image_size, channels, loss_type, conditional, schedule_opt)
+        self.predictor = UNetSeeInDark()
+
+    @torch.no_grad()
+    def super_resolution(self, x_in, continous=False):
+        """model/diffusion.py:473-478.  Like the reference, `+ initx` broadcasts over the snapshot rows,
+        which is only shape-valid for batch 1 when continous."""
+        initx = self.predictor(x_in)
+        self.pre_initx = initx
+        return self.p_sample_loop(x_in, continous, kwargs={"guide": initx}) + initx
