@@ -1,0 +1,189 @@
+/* ucdir_b200.h -- C ABI of libucdir_b200.so (hand-written sm_100a CUDA for UCDIR's denoising hot path).
+ *
+ * The reference (zhangyi-3/UCDIR) is pure Python/PyTorch and has no FFI of its own; every arithmetic
+ * step of its hot path is a library call issued from model/ucdir.py, model/diffusion.py and
+ * utils/util.py.  This ABI is what a binding for that path binds instead: plain
+ * pointers and sizes, no torch types, no allocation, no implicit synchronisation, stream ordered,
+ * int return codes (0 = ok, <0 = error, text via ucdir_last_error()).
+ *
+ * The unit of work is an "op": one kernel launch described by a POD record.  A whole UNet forward, a
+ * whole denoising step, or a single op for a unit test are all arrays of ops handed to
+ * ucdir_run_ops() in one call (host code builds the array once per shape -- see ucdir_b200/engine.py).
+ *
+ * Which reference code each op kind replaces (paths relative to the reference root):
+ *   UCDIR_OP_CONV_F32      nn.Conv2d / GroupNorm(1,C) / Swish / grouped spdyconv + per-pixel mix + residual
+ *                          model/ucdir.py:57,66,109-140,162-163,180-182,223,266-268 ; predictor convs :360-403
+ *   UCDIR_OP_SGEMM_F32     the two attention einsums                    model/ucdir.py:174,179
+ *   UCDIR_OP_SOFTMAX_F32   torch.softmax over keys                      model/ucdir.py:176
+ *   UCDIR_OP_GUIDANCE      F.interpolate(bilinear) + conv2 branch       model/ucdir.py:133-135,113-114
+ *   UCDIR_OP_TIME_EMBED    PositionalEncoding + noise_level_mlp + per-block noise_func
+ *                                                                      model/ucdir.py:24-29,212-214,106,125
+ *   UCDIR_OP_GATHER_TILES  F.pad(reflect) + window slicing + torch.cat([cond, x])
+ *                          utils/util.py:117-137 ; model/ucdir.py:303-306 ; model/diffusion.py:166
+ *   UCDIR_OP_SCATTER       interior write-back + crop (+ fused posterior step)
+ *                          utils/util.py:144-146 ; model/diffusion.py:150-158,171-172,182-183
+ *   UCDIR_OP_MAXPOOL2      nn.MaxPool2d(2)                              model/ucdir.py:363-375
+ *   UCDIR_OP_TC_*          bf16 tcgen05/TMA versions of CONV / attention (same reference lines)
+ *
+ * Activation layout inside the library: NHWC ("pixel-major, channel-innermost"), fp32 or bf16.
+ * Image layout at the boundary: the reference's NCHW fp32.
+ */
+#ifndef UCDIR_B200_H
+#define UCDIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UCDIR_ABI_VERSION 3
+
+#define UCDIR_OP_NPTR 16
+#define UCDIR_OP_NINT 32
+#define UCDIR_OP_NFLT 8
+
+typedef struct ucdir_op {
+  int32_t kind;                 /* enum ucdir_op_kind */
+  int32_t flags;                /* reserved, 0 */
+  void*   p[UCDIR_OP_NPTR];     /* device pointers, meaning per kind (enums below) */
+  int32_t i[UCDIR_OP_NINT];     /* integers, meaning per kind */
+  float   f[UCDIR_OP_NFLT];     /* floats, meaning per kind */
+} ucdir_op_t;
+
+enum ucdir_op_kind {
+  UCDIR_OP_CONV_F32 = 1,
+  UCDIR_OP_SGEMM_F32 = 2,
+  UCDIR_OP_SOFTMAX_F32 = 3,
+  UCDIR_OP_GUIDANCE = 4,
+  UCDIR_OP_TIME_EMBED = 5,
+  UCDIR_OP_GATHER_TILES = 6,
+  UCDIR_OP_SCATTER = 7,
+  UCDIR_OP_MAXPOOL2 = 8,
+  UCDIR_OP_MEMSET = 9,
+  UCDIR_OP_TC_CONV = 10,
+  UCDIR_OP_TC_ATTN = 11,
+  UCDIR_OP_GN_APPLY_BF16 = 12,
+  UCDIR_OP_CAST = 13
+};
+
+/* ---- UCDIR_OP_CONV_F32: dst = epilogue( conv( prologue(concat(src0, src1)) ) ) -----------------
+ * Implicit GEMM over NHWC fp32: M = output pixels of one sample, N = COUT, K = KSIZE^2 * (C0+C1)/GROUPS.
+ * prologue PRE: 0 none | 1 GroupNorm(1,C) | 2 GroupNorm(1,C) then Swish.  Statistics come from STATS0/1
+ *   (per sample {sum, sum of squares} in double, written by the producing op's epilogue); zero padding is
+ *   applied after the prologue, as in the reference where the conv pads the normalised tensor.
+ * UP=1: the source is read through a nearest x2 upsample (model/ucdir.py:56).
+ * epilogue MODE 0 (plain): v = acc + bias[n]; ACT (0 none | 1 Swish | 2 LeakyReLU 0.2); + RES[pix, n] if RES;
+ *                          FiLM: if FILM_B: v = (1 + FILM_G[b,n]) * v + FILM_B[b,n]  (FILM_G may be NULL => v + FILM_B)
+ *                          applied before ACT/RES (model/ucdir.py:38-45).
+ * epilogue MODE 1 (mix):   grouped conv C -> 8C whose 8 adjacent outputs n = c*8+s are mixed per pixel:
+ *                          h = sum_s (acc[c*8+s] + bias) * ATT[pix, s] * ATTW[b, s]; v = Swish(h) + RES[pix, c]
+ *                          (model/ucdir.py:135-140); the 8C tensor is never written.
+ * Every epilogue also accumulates {sum v, sum v^2} per sample into DST_STATS when non-NULL (the next GN).
+ * DST_UP=1 writes to pixel (2y+DST_PY, 2x+DST_PX) of a 2H x 2W tensor (ConvTranspose2d 2x2 s2 as 4 phases).
+ */
+enum ucdir_conv_ptr {
+  UCDIR_CONV_P_SRC0 = 0, UCDIR_CONV_P_SRC1 = 1, UCDIR_CONV_P_W = 2, UCDIR_CONV_P_BIAS = 3,
+  UCDIR_CONV_P_GAMMA = 4, UCDIR_CONV_P_BETA = 5, UCDIR_CONV_P_STATS0 = 6, UCDIR_CONV_P_STATS1 = 7,
+  UCDIR_CONV_P_RES = 8, UCDIR_CONV_P_ATT = 9, UCDIR_CONV_P_ATTW = 10, UCDIR_CONV_P_DST = 11,
+  UCDIR_CONV_P_DST_STATS = 12, UCDIR_CONV_P_FILM_G = 13, UCDIR_CONV_P_FILM_B = 14
+};
+enum ucdir_conv_int {
+  UCDIR_CONV_I_B = 0, UCDIR_CONV_I_H = 1, UCDIR_CONV_I_W = 2,        /* output spatial size per sample */
+  UCDIR_CONV_I_C0 = 3, UCDIR_CONV_I_C1 = 4, UCDIR_CONV_I_COUT = 5,
+  UCDIR_CONV_I_KSIZE = 6, UCDIR_CONV_I_STRIDE = 7, UCDIR_CONV_I_UP = 8, UCDIR_CONV_I_GROUPS = 9,
+  UCDIR_CONV_I_PRE = 10, UCDIR_CONV_I_ACT = 11, UCDIR_CONV_I_MODE = 12,
+  UCDIR_CONV_I_SRC_H = 13, UCDIR_CONV_I_SRC_W = 14,                  /* stored source size (before UP) */
+  UCDIR_CONV_I_DST_C = 15, UCDIR_CONV_I_DST_COFF = 16,               /* dst channel stride / offset */
+  UCDIR_CONV_I_DST_UP = 17, UCDIR_CONV_I_DST_PY = 18, UCDIR_CONV_I_DST_PX = 19,
+  UCDIR_CONV_I_RES_C = 20, UCDIR_CONV_I_ATTW_STRIDE = 21,            /* floats between samples in ATTW */
+  UCDIR_CONV_I_GN_GROUPS = 22                                        /* 1 (default) or G for the FiLM block */
+};
+enum ucdir_conv_flt { UCDIR_CONV_F_EPS = 0 };
+
+/* ---- UCDIR_OP_SGEMM_F32: C[b] = alpha * A[b] * op(B[b]); TRANSB=1: B is N x K row-major ------------- */
+enum ucdir_sgemm_ptr { UCDIR_SGEMM_P_A = 0, UCDIR_SGEMM_P_B = 1, UCDIR_SGEMM_P_C = 2 };
+enum ucdir_sgemm_int {
+  UCDIR_SGEMM_I_BATCH = 0, UCDIR_SGEMM_I_M = 1, UCDIR_SGEMM_I_N = 2, UCDIR_SGEMM_I_K = 3,
+  UCDIR_SGEMM_I_LDA = 4, UCDIR_SGEMM_I_LDB = 5, UCDIR_SGEMM_I_LDC = 6,
+  UCDIR_SGEMM_I_SA = 7, UCDIR_SGEMM_I_SB = 8, UCDIR_SGEMM_I_SC = 9,  /* batch strides in elements */
+  UCDIR_SGEMM_I_TRANSB = 10
+};
+enum ucdir_sgemm_flt { UCDIR_SGEMM_F_ALPHA = 0 };
+
+/* ---- UCDIR_OP_SOFTMAX_F32: in-place softmax over each row of X[ROWS][COLS] --------------------------- */
+enum ucdir_softmax_ptr { UCDIR_SOFTMAX_P_X = 0 };
+enum ucdir_softmax_int { UCDIR_SOFTMAX_I_ROWS = 0, UCDIR_SOFTMAX_I_COLS = 1 };
+
+/* ---- UCDIR_OP_GUIDANCE: DST[B,H,W,8] = conv3x3(SimpleGate(conv1x1(bilinear(GUIDE[B,GH,GW,4])))) --------- */
+enum ucdir_guid_ptr {
+  UCDIR_GUID_P_GUIDE = 0, UCDIR_GUID_P_W0 = 1, UCDIR_GUID_P_B0 = 2, UCDIR_GUID_P_W2 = 3, UCDIR_GUID_P_B2 = 4,
+  UCDIR_GUID_P_DST = 5
+};
+enum ucdir_guid_int { UCDIR_GUID_I_B = 0, UCDIR_GUID_I_GH = 1, UCDIR_GUID_I_GW = 2, UCDIR_GUID_I_H = 3, UCDIR_GUID_I_W = 4 };
+
+/* ---- UCDIR_OP_TIME_EMBED: DST[L][NBLK][8] from noise levels -------------------------------------------
+ * LEVELS (float[L]) or, when NULL, the single value f[LEVEL] replicated L times.
+ * BLK = NBLK records of { W_a[8][INNER], b_a[8], W_b[8][8], b_b[8] } (noise_func.0 / noise_func.2).     */
+enum ucdir_temb_ptr {
+  UCDIR_TEMB_P_LEVELS = 0, UCDIR_TEMB_P_W1 = 1, UCDIR_TEMB_P_B1 = 2, UCDIR_TEMB_P_W2 = 3, UCDIR_TEMB_P_B2 = 4,
+  UCDIR_TEMB_P_BLK = 5, UCDIR_TEMB_P_DST = 6, UCDIR_TEMB_P_TEMB_OUT = 7 /* optional float[L][INNER] */
+};
+enum ucdir_temb_int { UCDIR_TEMB_I_L = 0, UCDIR_TEMB_I_NBLK = 1, UCDIR_TEMB_I_INNER = 2 };
+enum ucdir_temb_flt { UCDIR_TEMB_F_LEVEL = 0 };
+
+/* ---- UCDIR_OP_GATHER_TILES: DST[BT,TH,TW,CD] from NCHW fp32 images with on-the-fly reflect padding -------
+ * TAB = int32[BT][3] {image index, y0, x0}: tile origin in padded coordinates; source pixel of padded
+ * coordinate P is reflect(P - PD) (PD=0 with bottom/right overhang reproduces model/ucdir.py:303-306).
+ * Channels: CA from SRC_A, then CB from SRC_B (may be NULL/0), zero-filled up to CD.  OUT_BF16=1 writes bf16. */
+enum ucdir_gather_ptr { UCDIR_GATHER_P_SRC_A = 0, UCDIR_GATHER_P_SRC_B = 1, UCDIR_GATHER_P_TAB = 2, UCDIR_GATHER_P_DST = 3 };
+enum ucdir_gather_int {
+  UCDIR_GATHER_I_BT = 0, UCDIR_GATHER_I_TH = 1, UCDIR_GATHER_I_TW = 2, UCDIR_GATHER_I_IMG_H = 3,
+  UCDIR_GATHER_I_IMG_W = 4, UCDIR_GATHER_I_PD = 5, UCDIR_GATHER_I_CA = 6, UCDIR_GATHER_I_CB = 7,
+  UCDIR_GATHER_I_CD = 8, UCDIR_GATHER_I_OUT_BF16 = 9
+};
+
+/* ---- UCDIR_OP_SCATTER: stitch tile outputs back to NCHW images; MODE 1 fuses the posterior step ---------
+ * OWNER_Y[IMG_H] / OWNER_X[IMG_W]: index of the tile row / column whose interior owns that image row /
+ * column (the LAST window in reference order, utils/util.py:124-145), -1 = never written (zeros).
+ * Y0[NTY] / X0[NTX]: window origins in padded coordinates.  Tile index = (img*NTY + ty)*NTX + tx.
+ * MODE 0: OUT = eps.   MODE 1: x0 = clamp(A*x - B*eps); OUT = C1*x0 + C2*x + SIGMA*noise
+ * (model/diffusion.py:150-158,171-172,182-183; NOISE NULL => 0; CLIP=0 skips the clamp).                     */
+enum ucdir_scatter_ptr {
+  UCDIR_SCATTER_P_EPS = 0, UCDIR_SCATTER_P_OWNER_Y = 1, UCDIR_SCATTER_P_OWNER_X = 2, UCDIR_SCATTER_P_Y0 = 3,
+  UCDIR_SCATTER_P_X0 = 4, UCDIR_SCATTER_P_XT = 5, UCDIR_SCATTER_P_NOISE = 6, UCDIR_SCATTER_P_OUT = 7
+};
+enum ucdir_scatter_int {
+  UCDIR_SCATTER_I_BIMG = 0, UCDIR_SCATTER_I_IMG_H = 1, UCDIR_SCATTER_I_IMG_W = 2, UCDIR_SCATTER_I_NTY = 3,
+  UCDIR_SCATTER_I_NTX = 4, UCDIR_SCATTER_I_TH = 5, UCDIR_SCATTER_I_TW = 6, UCDIR_SCATTER_I_PD = 7,
+  UCDIR_SCATTER_I_CE = 8, UCDIR_SCATTER_I_MODE = 9, UCDIR_SCATTER_I_CLIP = 10, UCDIR_SCATTER_I_C = 11
+};
+enum ucdir_scatter_flt {
+  UCDIR_SCATTER_F_A = 0, UCDIR_SCATTER_F_B = 1, UCDIR_SCATTER_F_C1 = 2, UCDIR_SCATTER_F_C2 = 3, UCDIR_SCATTER_F_SIGMA = 4
+};
+
+/* ---- UCDIR_OP_MAXPOOL2: DST[B,H,W,C] = max 2x2 of SRC[B,2H,2W,C] (fp32 NHWC) -------------------------- */
+enum ucdir_pool_ptr { UCDIR_POOL_P_SRC = 0, UCDIR_POOL_P_DST = 1 };
+enum ucdir_pool_int { UCDIR_POOL_I_B = 0, UCDIR_POOL_I_H = 1, UCDIR_POOL_I_W = 2, UCDIR_POOL_I_C = 3 };
+
+/* ---- UCDIR_OP_MEMSET: cudaMemsetAsync(p[0], 0, i[0] + (i[1] << 31)) ------------------------------------ */
+
+/* Run ops[0..n) in order on `stream` (a cudaStream_t).  No synchronisation.  Returns 0 or a negative error
+ * (-1 bad argument, -2 unsupported shape, -3 CUDA launch error). */
+int ucdir_run_ops(const ucdir_op_t* ops, int n_ops, void* stream);
+
+/* Validate ops without launching (same return codes). */
+int ucdir_check_ops(const ucdir_op_t* ops, int n_ops);
+
+int ucdir_abi_version(void);
+int ucdir_op_sizeof(void);
+const char* ucdir_last_error(void);
+/* Number of kernel launches issued by this process through ucdir_run_ops since load. */
+long long ucdir_launch_count(void);
+/* Device capability probe: returns 0 iff the current device is sm_100 (B200). */
+int ucdir_device_ok(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UCDIR_B200_H */

@@ -1,0 +1,306 @@
+"""CPU interpreter of `ucdir_op_t` arrays -- TEST INFRASTRUCTURE ONLY.
+
+The build container has no GPU, so the engine's graph construction (ucdir_b200/engine.py: weight packing,
+tile tables, buffer reuse, op wiring) is checked here by executing the op array it emits with this
+interpreter (torch CPU, semantics restated from include/ucdir_b200.h) and comparing against the oracle.
+The CUDA kernels themselves are checked on the B200 by the `-m gpu` tests.  Nothing under ucdir_b200/
+imports this file; the product path has no CPU route.
+"""
+from __future__ import annotations
+
+import ctypes
+import gc
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from ucdir_b200 import _lib
+from ucdir_b200._lib import C as K
+
+
+class Memory:
+    """Resolve raw host pointers to views of live torch CPU storages."""
+
+    def __init__(self):
+        self.iv = []
+        seen = set()
+        import warnings
+        warnings.simplefilter("ignore")
+        for o in gc.get_objects():
+            try:
+                if isinstance(o, torch.Tensor) and o.device.type == "cpu" and o.numel() > 0:
+                    st = o.untyped_storage()
+                    p = st.data_ptr()
+                    if p and p not in seen:
+                        seen.add(p)
+                        self.iv.append((p, st.nbytes(), st))
+            except Exception:
+                pass
+
+    def view(self, ptr, shape, dtype=torch.float32):
+        if not ptr:
+            return None
+        n = int(np.prod(shape))
+        es = torch.empty(0, dtype=dtype).element_size()
+        for p, nb, st in self.iv:
+            if p <= ptr and ptr + n * es <= p + nb:
+                off = ptr - p
+                assert off % es == 0
+                return torch.empty(0, dtype=dtype).set_(st, off // es, tuple(shape))
+        raise KeyError("pointer %#x (+%d bytes) is not inside any live CPU tensor" % (ptr, n * es))
+
+
+def _p(op, name):
+    v = op.p[K[name]]
+    return int(v) if v else 0
+
+
+def _i(op, name):
+    return int(op.i[K[name]])
+
+
+def _f(op, name):
+    return float(op.f[K[name]])
+
+
+def swish(x):
+    return x * torch.sigmoid(x)
+
+
+def emu_conv(op, mem):
+    B, H, W = _i(op, "UCDIR_CONV_I_B"), _i(op, "UCDIR_CONV_I_H"), _i(op, "UCDIR_CONV_I_W")
+    C0, C1, Cout = _i(op, "UCDIR_CONV_I_C0"), _i(op, "UCDIR_CONV_I_C1"), _i(op, "UCDIR_CONV_I_COUT")
+    ks, stride, up, groups = (_i(op, "UCDIR_CONV_I_KSIZE"), _i(op, "UCDIR_CONV_I_STRIDE"), _i(op, "UCDIR_CONV_I_UP"),
+                              _i(op, "UCDIR_CONV_I_GROUPS"))
+    pre, act, mode = _i(op, "UCDIR_CONV_I_PRE"), _i(op, "UCDIR_CONV_I_ACT"), _i(op, "UCDIR_CONV_I_MODE")
+    sH, sW = _i(op, "UCDIR_CONV_I_SRC_H"), _i(op, "UCDIR_CONV_I_SRC_W")
+    dstC, dstCoff = _i(op, "UCDIR_CONV_I_DST_C"), _i(op, "UCDIR_CONV_I_DST_COFF")
+    dstUp, dpy, dpx = _i(op, "UCDIR_CONV_I_DST_UP"), _i(op, "UCDIR_CONV_I_DST_PY"), _i(op, "UCDIR_CONV_I_DST_PX")
+    resC, attw_stride = _i(op, "UCDIR_CONV_I_RES_C"), _i(op, "UCDIR_CONV_I_ATTW_STRIDE")
+    eps = _f(op, "UCDIR_CONV_F_EPS")
+    Cin = C0 + C1
+    x = mem.view(_p(op, "UCDIR_CONV_P_SRC0"), (B, sH, sW, C0))
+    if C1:
+        x = torch.cat([x, mem.view(_p(op, "UCDIR_CONV_P_SRC1"), (B, sH, sW, C1))], dim=-1)
+    x = x.double() if False else x.clone()
+    if pre:
+        s0 = mem.view(_p(op, "UCDIR_CONV_P_STATS0"), (B, 2), torch.float64).clone()
+        if C1:
+            s0 = s0 + mem.view(_p(op, "UCDIR_CONV_P_STATS1"), (B, 2), torch.float64)
+        cnt = float(Cin * sH * sW)
+        mean = s0[:, 0] / cnt
+        var = (s0[:, 1] / cnt - mean * mean).clamp_min(0)
+        rstd = 1.0 / torch.sqrt(var + eps)
+        gamma = mem.view(_p(op, "UCDIR_CONV_P_GAMMA"), (Cin,))
+        beta = mem.view(_p(op, "UCDIR_CONV_P_BETA"), (Cin,))
+        x = (x - mean.float().view(B, 1, 1, 1)) * rstd.float().view(B, 1, 1, 1) * gamma + beta
+        if pre == 2:
+            x = swish(x)
+    xn = x.permute(0, 3, 1, 2)
+    if up:
+        xn = F.interpolate(xn, scale_factor=2, mode="nearest")
+    Cg, Ng = Cin // groups, Cout // groups
+    ldw = (Ng + 3) & ~3
+    Kdim = ks * ks * Cg
+    wp = mem.view(_p(op, "UCDIR_CONV_P_W"), (groups, Kdim, ldw))[:, :, :Ng]
+    w = wp.view(groups, ks, ks, Cg, Ng).permute(0, 4, 3, 1, 2).reshape(Cout, Cg, ks, ks)
+    y = F.conv2d(xn, w, None, stride=stride, padding=ks // 2, groups=groups)          # B, Cout, H, W
+    assert y.shape[2] == H and y.shape[3] == W, (y.shape, H, W)
+    bias_p = _p(op, "UCDIR_CONV_P_BIAS")
+    if bias_p:
+        y = y + mem.view(bias_p, (Cout,)).view(1, Cout, 1, 1)
+    y = y.permute(0, 2, 3, 1)                                                           # B, H, W, Cout
+    if mode == 1:
+        att = mem.view(_p(op, "UCDIR_CONV_P_ATT"), (B, H, W, 8))
+        aw_base = _p(op, "UCDIR_CONV_P_ATTW")
+        aw = torch.stack([mem.view(aw_base + b * attw_stride * 4, (8,)) for b in range(B)])
+        a = att * aw.view(B, 1, 1, 8)
+        c = Cout // 8
+        h = (y.reshape(B, H, W, c, 8) * a.unsqueeze(3)).sum(-1)
+        res = mem.view(_p(op, "UCDIR_CONV_P_RES"), (B, H, W, resC))[..., :c]
+        v = swish(h) + res
+        nout = c
+    else:
+        fb = _p(op, "UCDIR_CONV_P_FILM_B")
+        if fb:
+            b_ = mem.view(fb, (B, Cout)).view(B, 1, 1, Cout)
+            fg = _p(op, "UCDIR_CONV_P_FILM_G")
+            y = (1 + mem.view(fg, (B, Cout)).view(B, 1, 1, Cout)) * y + b_ if fg else y + b_
+        if act == 1:
+            y = swish(y)
+        elif act == 2:
+            y = torch.max(0.2 * y, y)
+        rp = _p(op, "UCDIR_CONV_P_RES")
+        if rp:
+            y = y + mem.view(rp, (B, H, W, resC))[..., :Cout]
+        v = y
+        nout = Cout
+    if dstUp:
+        dst = mem.view(_p(op, "UCDIR_CONV_P_DST"), (B, 2 * H, 2 * W, dstC))
+        dst[:, dpy::2, dpx::2, dstCoff:dstCoff + nout] = v
+    else:
+        dst = mem.view(_p(op, "UCDIR_CONV_P_DST"), (B, H, W, dstC))
+        dst[..., dstCoff:dstCoff + nout] = v
+    sp = _p(op, "UCDIR_CONV_P_DST_STATS")
+    if sp:
+        st = mem.view(sp, (B, 2), torch.float64)
+        vd = v.double().reshape(B, -1)
+        st[:, 0] += vd.sum(1)
+        st[:, 1] += (vd * vd).sum(1)
+
+
+def emu_sgemm(op, mem):
+    batch, M, N, Kd = (_i(op, "UCDIR_SGEMM_I_BATCH"), _i(op, "UCDIR_SGEMM_I_M"), _i(op, "UCDIR_SGEMM_I_N"),
+                       _i(op, "UCDIR_SGEMM_I_K"))
+    lda, ldb, ldc = _i(op, "UCDIR_SGEMM_I_LDA"), _i(op, "UCDIR_SGEMM_I_LDB"), _i(op, "UCDIR_SGEMM_I_LDC")
+    sa, sb, sc = _i(op, "UCDIR_SGEMM_I_SA"), _i(op, "UCDIR_SGEMM_I_SB"), _i(op, "UCDIR_SGEMM_I_SC")
+    tb = _i(op, "UCDIR_SGEMM_I_TRANSB")
+    alpha = _f(op, "UCDIR_SGEMM_F_ALPHA")
+    for b in range(batch):
+        A = mem.view(_p(op, "UCDIR_SGEMM_P_A") + b * sa * 4, ((M - 1) * lda + Kd,))
+        A = torch.as_strided(A, (M, Kd), (lda, 1))
+        if tb:
+            Bm = mem.view(_p(op, "UCDIR_SGEMM_P_B") + b * sb * 4, ((N - 1) * ldb + Kd,))
+            Bm = torch.as_strided(Bm, (N, Kd), (ldb, 1)).t()
+        else:
+            Bm = mem.view(_p(op, "UCDIR_SGEMM_P_B") + b * sb * 4, ((Kd - 1) * ldb + N,))
+            Bm = torch.as_strided(Bm, (Kd, N), (ldb, 1))
+        Cm = mem.view(_p(op, "UCDIR_SGEMM_P_C") + b * sc * 4, ((M - 1) * ldc + N,))
+        torch.as_strided(Cm, (M, N), (ldc, 1)).copy_(alpha * (A @ Bm))
+
+
+def emu_softmax(op, mem):
+    rows, cols = _i(op, "UCDIR_SOFTMAX_I_ROWS"), _i(op, "UCDIR_SOFTMAX_I_COLS")
+    X = mem.view(_p(op, "UCDIR_SOFTMAX_P_X"), (rows, cols))
+    X.copy_(torch.softmax(X, dim=-1))
+
+
+def emu_guidance(op, mem):
+    B, GH, GW, H, W = (_i(op, "UCDIR_GUID_I_B"), _i(op, "UCDIR_GUID_I_GH"), _i(op, "UCDIR_GUID_I_GW"),
+                       _i(op, "UCDIR_GUID_I_H"), _i(op, "UCDIR_GUID_I_W"))
+    g = mem.view(_p(op, "UCDIR_GUID_P_GUIDE"), (B, GH, GW, 4))[..., :3].permute(0, 3, 1, 2)
+    r = GW // W
+    if r > 1:
+        off = r // 2 - 1
+        g = 0.25 * (g[:, :, off::r, off::r] + g[:, :, off::r, off + 1::r] + g[:, :, off + 1::r, off::r]
+                    + g[:, :, off + 1::r, off + 1::r])
+        assert g.shape[-2:] == (H, W)
+    w0 = mem.view(_p(op, "UCDIR_GUID_P_W0"), (16, 3, 1, 1)); b0 = mem.view(_p(op, "UCDIR_GUID_P_B0"), (16,))
+    w2 = mem.view(_p(op, "UCDIR_GUID_P_W2"), (8, 8, 3, 3)); b2 = mem.view(_p(op, "UCDIR_GUID_P_B2"), (8,))
+    u = F.conv2d(g, w0, b0)
+    gate = u[:, :8] * u[:, 8:]
+    out = F.conv2d(gate, w2, b2, padding=1)
+    mem.view(_p(op, "UCDIR_GUID_P_DST"), (B, H, W, 8)).copy_(out.permute(0, 2, 3, 1))
+
+
+def emu_time_embed(op, mem):
+    L, nblk, inner = _i(op, "UCDIR_TEMB_I_L"), _i(op, "UCDIR_TEMB_I_NBLK"), _i(op, "UCDIR_TEMB_I_INNER")
+    lp = _p(op, "UCDIR_TEMB_P_LEVELS")
+    levels = mem.view(lp, (L,)).clone() if lp else torch.full((L,), _f(op, "UCDIR_TEMB_F_LEVEL"), dtype=torch.float32)
+    count = inner // 2
+    step = torch.arange(count, dtype=torch.float32) / count
+    e = levels.view(L, 1) * torch.exp(-math.log(1e4) * step.view(1, -1))
+    enc = torch.cat([torch.sin(e), torch.cos(e)], dim=-1)
+    w1 = mem.view(_p(op, "UCDIR_TEMB_P_W1"), (4 * inner, inner)); b1 = mem.view(_p(op, "UCDIR_TEMB_P_B1"), (4 * inner,))
+    w2 = mem.view(_p(op, "UCDIR_TEMB_P_W2"), (inner, 4 * inner)); b2 = mem.view(_p(op, "UCDIR_TEMB_P_B2"), (inner,))
+    t = F.linear(swish(F.linear(enc, w1, b1)), w2, b2)
+    rec = 8 * inner + 8 + 64 + 8
+    blk = mem.view(_p(op, "UCDIR_TEMB_P_BLK"), (nblk, rec))
+    dst = mem.view(_p(op, "UCDIR_TEMB_P_DST"), (L, nblk, 8))
+    for k in range(nblk):
+        wa = blk[k, :8 * inner].view(8, inner); ba = blk[k, 8 * inner:8 * inner + 8]
+        wb = blk[k, 8 * inner + 8:8 * inner + 72].view(8, 8); bb = blk[k, 8 * inner + 72:]
+        dst[:, k] = F.linear(swish(F.linear(t, wa, ba)), wb, bb)
+
+
+def _reflect(q, n):
+    q = np.abs(q)
+    return np.where(q >= n, 2 * (n - 1) - q, q)
+
+
+def emu_gather(op, mem):
+    BT, TH, TW = _i(op, "UCDIR_GATHER_I_BT"), _i(op, "UCDIR_GATHER_I_TH"), _i(op, "UCDIR_GATHER_I_TW")
+    IH, IW, PD = _i(op, "UCDIR_GATHER_I_IMG_H"), _i(op, "UCDIR_GATHER_I_IMG_W"), _i(op, "UCDIR_GATHER_I_PD")
+    CA, CB, CD = _i(op, "UCDIR_GATHER_I_CA"), _i(op, "UCDIR_GATHER_I_CB"), _i(op, "UCDIR_GATHER_I_CD")
+    assert not _i(op, "UCDIR_GATHER_I_OUT_BF16")
+    tab = mem.view(_p(op, "UCDIR_GATHER_P_TAB"), (BT, 3), torch.int32).numpy()
+    nimg = int(tab[:, 0].max()) + 1
+    A = mem.view(_p(op, "UCDIR_GATHER_P_SRC_A"), (nimg, CA, IH, IW))
+    Bs = mem.view(_p(op, "UCDIR_GATHER_P_SRC_B"), (nimg, CB, IH, IW)) if CB else None
+    dst = mem.view(_p(op, "UCDIR_GATHER_P_DST"), (BT, TH, TW, CD))
+    for t in range(BT):
+        img, y0, x0 = (int(v) for v in tab[t])
+        sy = torch.from_numpy(_reflect(np.arange(TH) + y0 - PD, IH))
+        sx = torch.from_numpy(_reflect(np.arange(TW) + x0 - PD, IW))
+        dst[t].zero_()
+        dst[t, :, :, :CA] = A[img][:, sy][:, :, sx].permute(1, 2, 0)
+        if CB:
+            dst[t, :, :, CA:CA + CB] = Bs[img][:, sy][:, :, sx].permute(1, 2, 0)
+
+
+def emu_scatter(op, mem):
+    BI, IH, IW = _i(op, "UCDIR_SCATTER_I_BIMG"), _i(op, "UCDIR_SCATTER_I_IMG_H"), _i(op, "UCDIR_SCATTER_I_IMG_W")
+    NTY, NTX, TH, TW = (_i(op, "UCDIR_SCATTER_I_NTY"), _i(op, "UCDIR_SCATTER_I_NTX"), _i(op, "UCDIR_SCATTER_I_TH"),
+                        _i(op, "UCDIR_SCATTER_I_TW"))
+    PD, CE, mode, clip, Cc = (_i(op, "UCDIR_SCATTER_I_PD"), _i(op, "UCDIR_SCATTER_I_CE"), _i(op, "UCDIR_SCATTER_I_MODE"),
+                              _i(op, "UCDIR_SCATTER_I_CLIP"), _i(op, "UCDIR_SCATTER_I_C"))
+    eps_t = mem.view(_p(op, "UCDIR_SCATTER_P_EPS"), (BI * NTY * NTX, TH, TW, CE))
+    oy = mem.view(_p(op, "UCDIR_SCATTER_P_OWNER_Y"), (IH,), torch.int32).long()
+    ox = mem.view(_p(op, "UCDIR_SCATTER_P_OWNER_X"), (IW,), torch.int32).long()
+    y0 = mem.view(_p(op, "UCDIR_SCATTER_P_Y0"), (NTY,), torch.int32).long()
+    x0 = mem.view(_p(op, "UCDIR_SCATTER_P_X0"), (NTX,), torch.int32).long()
+    out = mem.view(_p(op, "UCDIR_SCATTER_P_OUT"), (BI, Cc, IH, IW))
+    yy = torch.arange(IH); xx = torch.arange(IW)
+    py = yy + PD - y0[oy.clamp_min(0)]; px = xx + PD - x0[ox.clamp_min(0)]
+    e = torch.zeros((BI, Cc, IH, IW))
+    for img in range(BI):
+        tile = (img * NTY + oy.clamp_min(0)).view(-1, 1) * NTX + ox.clamp_min(0).view(1, -1)
+        v = eps_t[tile, py.view(-1, 1), px.view(1, -1)][..., :Cc]                    # IH, IW, C
+        v = torch.where(((oy >= 0).view(-1, 1) & (ox >= 0).view(1, -1)).unsqueeze(-1), v, torch.zeros_like(v))
+        e[img] = v.permute(2, 0, 1)
+    if mode == 0:
+        out.copy_(e)
+        return
+    xt = mem.view(_p(op, "UCDIR_SCATTER_P_XT"), (BI, Cc, IH, IW))
+    f = lambda n: torch.tensor(_f(op, "UCDIR_SCATTER_F_" + n), dtype=torch.float32)
+    x0_ = f("A") * xt - f("B") * e
+    if clip:
+        x0_ = x0_.clamp(-1.0, 1.0)
+    mean = f("C1") * x0_ + f("C2") * xt
+    npz = _p(op, "UCDIR_SCATTER_P_NOISE")
+    z = mem.view(npz, (BI, Cc, IH, IW)) if npz else torch.zeros_like(xt)
+    out.copy_(mean + z * f("SIGMA"))
+
+
+def emu_maxpool(op, mem):
+    B, H, W, Cc = _i(op, "UCDIR_POOL_I_B"), _i(op, "UCDIR_POOL_I_H"), _i(op, "UCDIR_POOL_I_W"), _i(op, "UCDIR_POOL_I_C")
+    s = mem.view(_p(op, "UCDIR_POOL_P_SRC"), (B, 2 * H, 2 * W, Cc))
+    d = mem.view(_p(op, "UCDIR_POOL_P_DST"), (B, H, W, Cc))
+    d.copy_(F.max_pool2d(s.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1))
+
+
+def emu_memset(op, mem):
+    n = int(op.i[0]) + (int(op.i[1]) << 31)
+    mem.view(int(op.p[0]), (n,), torch.uint8).zero_()
+
+
+DISPATCH = {
+    K["UCDIR_OP_CONV_F32"]: emu_conv, K["UCDIR_OP_SGEMM_F32"]: emu_sgemm, K["UCDIR_OP_SOFTMAX_F32"]: emu_softmax,
+    K["UCDIR_OP_GUIDANCE"]: emu_guidance, K["UCDIR_OP_TIME_EMBED"]: emu_time_embed,
+    K["UCDIR_OP_GATHER_TILES"]: emu_gather, K["UCDIR_OP_SCATTER"]: emu_scatter, K["UCDIR_OP_MAXPOOL2"]: emu_maxpool,
+    K["UCDIR_OP_MEMSET"]: emu_memset,
+}
+
+LAUNCHED = []
+
+
+def run_ops(ops, n, stream=0):
+    """Drop-in for ucdir_b200._lib.run_ops (tests monkeypatch the engine's runner with this)."""
+    mem = Memory()
+    with torch.no_grad():
+        for k in range(n):
+            op = ops[k]
+            LAUNCHED.append(int(op.kind))
+            DISPATCH[int(op.kind)](op, mem)

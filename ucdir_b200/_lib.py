@@ -1,0 +1,110 @@
+"""ctypes binding of libucdir_b200.so (C ABI in include/ucdir_b200.h).
+
+The library is the product: if it is missing or the device is not sm_100 this module raises --
+there is no PyTorch / CPU fallback path anywhere in ucdir_b200.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(HERE, "..", "include", "ucdir_b200.h")
+LIB_PATH = os.path.join(HERE, "libucdir_b200.so")
+
+
+def _parse_header(path):
+    """Pull every `UCDIR_X = n` enumerator and `#define UCDIR_X n` out of the header so the Python side
+    can never drift from the C side."""
+    txt = open(path).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    consts = {}
+    for m in re.finditer(r"#define\s+(UCDIR_\w+)\s+(\d+)", txt):
+        consts[m.group(1)] = int(m.group(2))
+    for m in re.finditer(r"\b(UCDIR_\w+)\s*=\s*(\d+)", txt):
+        consts[m.group(1)] = int(m.group(2))
+    return consts
+
+
+C = _parse_header(HEADER)
+NPTR, NINT, NFLT = C["UCDIR_OP_NPTR"], C["UCDIR_OP_NINT"], C["UCDIR_OP_NFLT"]
+
+
+class Op(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("flags", ctypes.c_int32), ("p", ctypes.c_void_p * NPTR),
+                ("i", ctypes.c_int32 * NINT), ("f", ctypes.c_float * NFLT)]
+
+
+EXPORTS = ["ucdir_run_ops", "ucdir_check_ops", "ucdir_abi_version", "ucdir_op_sizeof", "ucdir_last_error",
+           "ucdir_launch_count", "ucdir_device_ok"]
+
+_lib = None
+
+
+class UcdirLibraryError(RuntimeError):
+    pass
+
+
+def load(require_device=True):
+    """Load the shared library (building is __graft_entry__.build()'s / ucdir_b200.build's job)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UcdirLibraryError(
+                "libucdir_b200.so is missing (%s). Build it with `python -m ucdir_b200.build`; "
+                "ucdir_b200 has no CPU / PyTorch fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.ucdir_run_ops.argtypes = [ctypes.POINTER(Op), ctypes.c_int, ctypes.c_void_p]
+        lib.ucdir_run_ops.restype = ctypes.c_int
+        lib.ucdir_check_ops.argtypes = [ctypes.POINTER(Op), ctypes.c_int]
+        lib.ucdir_check_ops.restype = ctypes.c_int
+        lib.ucdir_abi_version.restype = ctypes.c_int
+        lib.ucdir_op_sizeof.restype = ctypes.c_int
+        lib.ucdir_last_error.restype = ctypes.c_char_p
+        lib.ucdir_launch_count.restype = ctypes.c_longlong
+        lib.ucdir_device_ok.restype = ctypes.c_int
+        if lib.ucdir_abi_version() != C["UCDIR_ABI_VERSION"]:
+            raise UcdirLibraryError("libucdir_b200.so ABI %d != header ABI %d: rebuild" % (
+                lib.ucdir_abi_version(), C["UCDIR_ABI_VERSION"]))
+        if lib.ucdir_op_sizeof() != ctypes.sizeof(Op):
+            raise UcdirLibraryError("ucdir_op_t size mismatch: C %d vs ctypes %d" % (lib.ucdir_op_sizeof(), ctypes.sizeof(Op)))
+        _lib = lib
+    if require_device:
+        rc = _lib.ucdir_device_ok()
+        if rc != 0:
+            raise UcdirLibraryError("ucdir_b200 needs a B200 (sm_100) CUDA device: %s" % last_error())
+    return _lib
+
+
+def last_error():
+    return (_lib.ucdir_last_error() or b"").decode() if _lib is not None else ""
+
+
+def make_op(kind, p=None, i=None, f=None):
+    op = Op()
+    op.kind = C[kind] if isinstance(kind, str) else kind
+    for k, v in (p or {}).items():
+        op.p[C[k] if isinstance(k, str) else k] = v
+    for k, v in (i or {}).items():
+        op.i[C[k] if isinstance(k, str) else k] = int(v)
+    for k, v in (f or {}).items():
+        op.f[C[k] if isinstance(k, str) else k] = float(v)
+    return op
+
+
+def run_ops(ops, n, stream):
+    """ops: ctypes array of Op.  stream: integer cudaStream_t handle."""
+    rc = load().ucdir_run_ops(ops, n, ctypes.c_void_p(stream))
+    if rc != 0:
+        raise UcdirLibraryError("ucdir_run_ops failed (%d): %s" % (rc, last_error()))
+
+
+def check_ops(ops, n):
+    rc = load(require_device=False).ucdir_check_ops(ops, n)
+    if rc != 0:
+        raise UcdirLibraryError("ucdir_check_ops failed (%d): %s" % (rc, last_error()))
+
+
+def launch_count():
+    return int(load(require_device=False).ucdir_launch_count())

@@ -1,0 +1,53 @@
+"""Build libucdir_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libucdir_b200.so")
+SOURCES = ["c_abi.cu", "ucdir_f32.cu", "ucdir_misc.cu", "ucdir_tc.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "ucdir_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    bdir = os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        o = os.path.join(bdir, s.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    for s, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError("nvcc failed on %s" % s)
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

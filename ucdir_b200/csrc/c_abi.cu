@@ -1,0 +1,75 @@
+// C ABI of libucdir_b200.so: op dispatcher, error reporting, capability probe.  See include/ucdir_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include "common.cuh"
+
+namespace ucdir {
+static thread_local char g_err[512] = "";
+long long g_launches = 0;
+void set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+
+static int dispatch(const ucdir_op_t& op, cudaStream_t st, bool dry) {
+  switch (op.kind) {
+    case UCDIR_OP_CONV_F32: return launch_conv_f32(op, st, dry);
+    case UCDIR_OP_SGEMM_F32: return launch_sgemm_f32(op, st, dry);
+    case UCDIR_OP_SOFTMAX_F32: return launch_softmax_f32(op, st, dry);
+    case UCDIR_OP_GUIDANCE: return launch_guidance(op, st, dry);
+    case UCDIR_OP_TIME_EMBED: return launch_time_embed(op, st, dry);
+    case UCDIR_OP_GATHER_TILES: return launch_gather_tiles(op, st, dry);
+    case UCDIR_OP_SCATTER: return launch_scatter(op, st, dry);
+    case UCDIR_OP_MAXPOOL2: return launch_maxpool2(op, st, dry);
+    case UCDIR_OP_MEMSET: {
+      size_t n = (size_t)op.i[0] + ((size_t)op.i[1] << 31);
+      if (!op.p[0]) { set_error("memset: null pointer"); return -1; }
+      if (dry) return 0;
+      if (cudaMemsetAsync(op.p[0], 0, n, st) != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
+      return 0;
+    }
+    case UCDIR_OP_TC_CONV: return launch_tc_conv(op, st, dry);
+    case UCDIR_OP_TC_ATTN: return launch_tc_attn(op, st, dry);
+    case UCDIR_OP_GN_APPLY_BF16: return launch_gn_apply_bf16(op, st, dry);
+    case UCDIR_OP_CAST: return launch_cast(op, st, dry);
+    default: set_error("unknown op kind %d", op.kind); return -1;
+  }
+}
+}  // namespace ucdir
+
+extern "C" {
+
+int ucdir_run_ops(const ucdir_op_t* ops, int n_ops, void* stream) {
+  if (!ops || n_ops < 0) { ucdir::set_error("run_ops: bad arguments"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int k = 0; k < n_ops; ++k) {
+    int rc = ucdir::dispatch(ops[k], st, false);
+    if (rc) { char tmp[400]; snprintf(tmp, sizeof(tmp), "%s", ucdir::g_err); ucdir::set_error("op %d (kind %d): %s", k, ops[k].kind, tmp); return rc; }
+  }
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { ucdir::set_error("CUDA launch error: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return -3; }
+  return 0;
+}
+
+int ucdir_check_ops(const ucdir_op_t* ops, int n_ops) {
+  if (!ops || n_ops < 0) { ucdir::set_error("check_ops: bad arguments"); return -1; }
+  for (int k = 0; k < n_ops; ++k) {
+    int rc = ucdir::dispatch(ops[k], nullptr, true);
+    if (rc) { char tmp[400]; snprintf(tmp, sizeof(tmp), "%s", ucdir::g_err); ucdir::set_error("op %d (kind %d): %s", k, ops[k].kind, tmp); return rc; }
+  }
+  return 0;
+}
+
+int ucdir_abi_version(void) { return UCDIR_ABI_VERSION; }
+int ucdir_op_sizeof(void) { return (int)sizeof(ucdir_op_t); }
+const char* ucdir_last_error(void) { return ucdir::g_err; }
+long long ucdir_launch_count(void) { return ucdir::g_launches; }
+
+int ucdir_device_ok(void) {
+  int dev = 0; cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    ucdir::set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
+  if (prop.major != 10) { ucdir::set_error("device is sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor); return -2; }
+  return 0;
+}
+
+}  // extern "C"

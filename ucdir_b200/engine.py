@@ -1,0 +1,918 @@
+"""Host-side engine: turns the reference's module graph into arrays of `ucdir_op_t` records and hands
+them to libucdir_b200.so (C ABI, include/ucdir_b200.h).  One `ucdir_run_ops` call per denoising step.
+
+What is here is plumbing only: weight re-packing (OIHW fp32 -> kernel layouts, once per load), tile
+geometry (utils/util.py:108-146 and model/ucdir.py:295-307 of the reference restated as index tables),
+buffer planning, and op-list construction.  Every arithmetic step of the hot path is a CUDA kernel in
+the library; torch is used for device memory and streams.  There is no eager / CPU compute path.
+
+Data layout in HBM: activations are NHWC ("pixel-major, channel-innermost") over a *tile batch*
+[BT, TH, TW, C]; images at the boundary stay in the reference's NCHW fp32.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import C as K_
+
+F32 = torch.float32
+
+# Test seam: tests/ may swap the op runner for the CPU interpreter in tests/op_emulator.py to check graph
+# construction without a GPU.  The product never sets these; on a non-CUDA device every entry point raises.
+_RUNNER = _lib.run_ops
+_TEST_CPU_PLAN = False
+
+
+def _run_ops(arr, n, stream):
+    return _RUNNER(arr, n, stream)
+
+
+def _require_cuda(dev):
+    if _TEST_CPU_PLAN:
+        return
+    if dev.type != "cuda":
+        raise _lib.UcdirLibraryError("ucdir_b200 runs on a CUDA device only (module is on %s); there is no CPU "
+                                     "fallback" % dev)
+    _lib.load()
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0
+
+
+# ======================================================================================
+# geometry: which windows of which (reflect padded) image form the tile batch
+# ======================================================================================
+def tile_windows(length: int, skip: int, padding: int) -> List[int]:
+    """Window origins along one padded axis, reference order (utils/util.py:122-134): i in
+    arange(0, L, skip - 2*padding), a window that would overrun is shifted back to end at L."""
+    shift = skip - 2 * padding
+    if shift <= 0:
+        raise ValueError("tiler stride skip-2*padding must be positive (skip=%d padding=%d)" % (skip, padding))
+    return [min(i, length - skip) for i in range(0, length, shift)]
+
+
+@dataclass
+class Geometry:
+    """Tile batch description.  Tile index = (img * nty + ty) * ntx + tx."""
+    B: int
+    IH: int
+    IW: int
+    TH: int
+    TW: int
+    PD: int                      # reflect padding applied on every side before windowing (0: bottom/right overhang)
+    ys: List[int]                # unique window origins (padded coordinates)
+    xs: List[int]
+    owner_y: np.ndarray          # int32[IH]: window row that owns image row y (last writer wins), -1 none
+    owner_x: np.ndarray
+    kind: str = "direct"
+
+    @property
+    def nty(self): return len(self.ys)
+    @property
+    def ntx(self): return len(self.xs)
+    @property
+    def tiles_per_image(self): return self.nty * self.ntx
+    @property
+    def n_tiles(self): return self.B * self.tiles_per_image
+
+    def table(self) -> np.ndarray:
+        t = np.zeros((self.n_tiles, 3), dtype=np.int32)
+        k = 0
+        for b in range(self.B):
+            for y0 in self.ys:
+                for x0 in self.xs:
+                    t[k] = (b, y0, x0)
+                    k += 1
+        return t
+
+
+def _owners(n: int, pd: int, starts: Sequence[int], skip: int, padding: int) -> Tuple[List[int], np.ndarray]:
+    """Dedupe window origins (a shifted-back last window can coincide with its predecessor; both produce the
+    same values) and compute, for each image row, the last window in reference order whose interior
+    [s+padding, s+skip-padding) covers it (utils/util.py:144-145: later writes overwrite earlier ones)."""
+    uniq: List[int] = []
+    for s in starts:
+        if s not in uniq:
+            uniq.append(s)
+    own = np.full(n, -1, dtype=np.int32)
+    for s in starts:                       # reference order, later wins
+        lo, hi = s + padding - pd, s + skip - padding - pd
+        lo, hi = max(lo, 0), min(hi, n)
+        if hi > lo:
+            own[lo:hi] = uniq.index(s)
+    return uniq, own
+
+
+def geometry_direct(B: int, h: int, w: int, fac: int = 32) -> Geometry:
+    """model/ucdir.py:302-307: reflect-pad bottom/right to (h//32+1)*32 (always adds 1..32), run, crop."""
+    TH, TW = (h // fac + 1) * fac, (w // fac + 1) * fac
+    if TH - h >= h or TW - w >= w:
+        raise ValueError("reflect padding %dx%d -> %dx%d needs pad < dim (F.pad raises in the reference too)" % (h, w, TH, TW))
+    return Geometry(B, h, w, TH, TW, 0, [0], [0], np.zeros(h, np.int32), np.zeros(w, np.int32), "direct")
+
+
+def geometry_naive(B: int, h: int, w: int) -> Geometry:
+    """model/ucdir.py:270-293 called directly: no padding; four stride-2 stages need h, w % 16 == 0."""
+    if h % 16 or w % 16:
+        raise ValueError("naiveforward needs H, W multiples of 16 (got %dx%d): skip concat shapes would differ" % (h, w))
+    return Geometry(B, h, w, h, w, 0, [0], [0], np.zeros(h, np.int32), np.zeros(w, np.int32), "naive")
+
+
+def geometry_tiled(B: int, h: int, w: int, skip: int, padding: int) -> Geometry:
+    """utils/util.py:108-146."""
+    if skip % 16:
+        raise ValueError("tile size must be a multiple of 16")
+    m = min(h, w)
+    pd = skip - m + padding if m < skip else padding
+    if pd >= h or pd >= w:
+        raise ValueError("tiler reflect pad %d >= image dim %dx%d (F.pad raises in the reference too)" % (pd, h, w))
+    ys, oy = _owners(h, pd, tile_windows(h + 2 * pd, skip, padding), skip, padding)
+    xs, ox = _owners(w, pd, tile_windows(w + 2 * pd, skip, padding), skip, padding)
+    return Geometry(B, h, w, skip, skip, pd, ys, xs, oy, ox, "tiled")
+
+
+# ======================================================================================
+# device buffers
+# ======================================================================================
+class Pool:
+    """Size-bucketed free list over torch allocations.  Ops execute in stream order, so a buffer can be
+    handed to a later op as soon as its last reader has been *emitted*."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free: Dict[int, List[torch.Tensor]] = {}
+        self.all: List[torch.Tensor] = []
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        nbytes = (int(nbytes) + 255) & ~255
+        lst = self.free.get(nbytes)
+        if lst:
+            return lst.pop()
+        t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.all.append(t)
+        return t
+
+    def put(self, t: torch.Tensor):
+        self.free.setdefault(t.numel(), []).append(t)
+
+    def total_bytes(self):
+        return sum(t.numel() for t in self.all)
+
+
+@dataclass
+class Act:
+    """An NHWC activation of the tile batch plus its GroupNorm(1,C) statistics slot."""
+    buf: torch.Tensor
+    C: int
+    H: int
+    W: int
+    stats: int                   # device pointer to double[BT][2] or 0
+    keep: bool = False
+
+    @property
+    def ptr(self): return self.buf.data_ptr()
+
+
+# ======================================================================================
+# weight packing (runs once per load; layouts documented in include/ucdir_b200.h)
+# ======================================================================================
+def pack_conv_f32(w: torch.Tensor, groups: int = 1, pad_cin_to: Optional[int] = None) -> torch.Tensor:
+    """OIHW fp32 -> [groups][K = ks*ks*Cg (tap-major, channel-minor)][ldw = roundup4(Cout/groups)]."""
+    co, cg, kh, kw = w.shape
+    if pad_cin_to is not None and cg < pad_cin_to:
+        w = torch.cat([w, w.new_zeros(co, pad_cin_to - cg, kh, kw)], dim=1)
+        cg = pad_cin_to
+    ng = co // groups
+    ldw = (ng + 3) & ~3
+    p = w.view(groups, ng, cg, kh, kw).permute(0, 3, 4, 2, 1).reshape(groups, kh * kw * cg, ng)
+    if ldw != ng:
+        p = torch.cat([p, p.new_zeros(groups, kh * kw * cg, ldw - ng)], dim=2)
+    return p.contiguous().float()
+
+
+def pack_convT_phase_f32(w: torch.Tensor, py: int, px: int) -> torch.Tensor:
+    """ConvTranspose2d(2, stride 2) weight [Cin, Cout, 2, 2] -> the 1x1 GEMM [K=Cin][Cout] of phase (py,px)."""
+    return w[:, :, py, px].contiguous().float().unsqueeze(0)
+
+
+class WeightStore:
+    """Flat device copies of every tensor the kernels read, keyed by name."""
+
+    def __init__(self, device):
+        self.device = device
+        self.t: Dict[str, torch.Tensor] = {}
+
+    def put(self, name: str, t: torch.Tensor) -> int:
+        t = t.detach().to(device=self.device).contiguous()
+        self.t[name] = t
+        return t.data_ptr()
+
+    def ptr(self, name: str) -> int:
+        return self.t[name].data_ptr()
+
+    def has(self, name): return name in self.t
+
+
+# ======================================================================================
+# op-list builder
+# ======================================================================================
+class OpList:
+    def __init__(self):
+        self.ops: List[_lib.Op] = []
+        self._arr = None
+
+    def add(self, kind, p=None, i=None, f=None) -> int:
+        self.ops.append(_lib.make_op(kind, p, i, f))
+        self._arr = None
+        return len(self.ops) - 1
+
+    def extend(self, other: "OpList"):
+        self.ops.extend(other.ops)
+        self._arr = None
+
+    def array(self):
+        if self._arr is None:
+            arr = (_lib.Op * len(self.ops))()
+            for k, o in enumerate(self.ops):
+                ctypes.memmove(ctypes.addressof(arr[k]), ctypes.addressof(o), ctypes.sizeof(_lib.Op))
+            self._arr = arr
+        return self._arr
+
+    def __len__(self): return len(self.ops)
+
+
+def _conv_op(ol: OpList, *, src0: Act, w: int, dst: Act, cout: int, B: int, src1: Optional[Act] = None,
+             bias: int = 0, gamma: int = 0, beta: int = 0, ks: int = 3, stride: int = 1, up: int = 0,
+             groups: int = 1, pre: int = 0, act: int = 0, mode: int = 0, res: Optional[Act] = None,
+             att: int = 0, attw: int = 0, attw_stride: int = 0, dst_c: Optional[int] = None, dst_coff: int = 0,
+             dst_up: int = 0, dst_py: int = 0, dst_px: int = 0, c0: Optional[int] = None, eps: float = 1e-5):
+    """Append one UCDIR_OP_CONV_F32.  Output spatial size: dst.H x dst.W (or half of it when dst_up)."""
+    H, W = (dst.H // 2, dst.W // 2) if dst_up else (dst.H, dst.W)
+    p = {"UCDIR_CONV_P_SRC0": src0.ptr, "UCDIR_CONV_P_W": w, "UCDIR_CONV_P_DST": dst.ptr}
+    if src1 is not None:
+        p["UCDIR_CONV_P_SRC1"] = src1.ptr
+    if bias: p["UCDIR_CONV_P_BIAS"] = bias
+    if pre:
+        p["UCDIR_CONV_P_GAMMA"], p["UCDIR_CONV_P_BETA"] = gamma, beta
+        p["UCDIR_CONV_P_STATS0"] = src0.stats
+        if src1 is not None:
+            p["UCDIR_CONV_P_STATS1"] = src1.stats
+    if res is not None: p["UCDIR_CONV_P_RES"] = res.ptr
+    if att: p["UCDIR_CONV_P_ATT"] = att
+    if attw: p["UCDIR_CONV_P_ATTW"] = attw
+    if dst.stats: p["UCDIR_CONV_P_DST_STATS"] = dst.stats
+    i = {"UCDIR_CONV_I_B": B, "UCDIR_CONV_I_H": H, "UCDIR_CONV_I_W": W,
+         "UCDIR_CONV_I_C0": src0.C if c0 is None else c0, "UCDIR_CONV_I_C1": src1.C if src1 is not None else 0,
+         "UCDIR_CONV_I_COUT": cout, "UCDIR_CONV_I_KSIZE": ks, "UCDIR_CONV_I_STRIDE": stride, "UCDIR_CONV_I_UP": up,
+         "UCDIR_CONV_I_GROUPS": groups, "UCDIR_CONV_I_PRE": pre, "UCDIR_CONV_I_ACT": act, "UCDIR_CONV_I_MODE": mode,
+         "UCDIR_CONV_I_SRC_H": src0.H, "UCDIR_CONV_I_SRC_W": src0.W,
+         "UCDIR_CONV_I_DST_C": dst.C if dst_c is None else dst_c, "UCDIR_CONV_I_DST_COFF": dst_coff,
+         "UCDIR_CONV_I_DST_UP": dst_up, "UCDIR_CONV_I_DST_PY": dst_py, "UCDIR_CONV_I_DST_PX": dst_px,
+         "UCDIR_CONV_I_RES_C": res.C if res is not None else 0, "UCDIR_CONV_I_ATTW_STRIDE": attw_stride,
+         "UCDIR_CONV_I_GN_GROUPS": 1}
+    ol.add("UCDIR_OP_CONV_F32", p, i, {"UCDIR_CONV_F_EPS": eps})
+
+
+class _Builder:
+    """Shared helpers of the UNet / predictor graph builders."""
+
+    def __init__(self, pool: Pool, BT: int, stats: torch.Tensor):
+        self.pool, self.BT = pool, BT
+        self.stats = stats               # double[n_slots][BT][2]
+        self.next_slot = 0
+        self.ops = OpList()
+
+    def new(self, C, H, W, with_stats=True, keep=False, cpad: Optional[int] = None) -> Act:
+        buf = self.pool.get(self.BT * H * W * (cpad or C) * 4)
+        st = 0
+        if with_stats:
+            if self.next_slot >= self.stats.shape[0]:
+                raise RuntimeError("statistics arena exhausted")
+            st = self.stats.data_ptr() + self.next_slot * self.BT * 16
+            self.next_slot += 1
+        return Act(buf, cpad or C, H, W, st, keep)
+
+    def release(self, a: Optional[Act]):
+        if a is not None and not a.keep:
+            self.pool.put(a.buf)
+
+
+# ======================================================================================
+# UNet engine
+# ======================================================================================
+MAX_STAT_SLOTS = 192
+
+
+def _max_chunk_pixels():
+    return int(os.environ.get("UCDIR_CHUNK_PIXELS", 2 * 1024 * 1024 + 256 * 1024))
+
+
+class UNetEngine:
+    """Owns packed weights of one DY3h module and builds/runs forward plans."""
+
+    def __init__(self, module):
+        self.m = module
+        self.ws: Optional[WeightStore] = None
+        self.blocks: List[Tuple[str, object]] = []
+        self._sessions: Dict[tuple, "Session"] = {}
+
+    # ---- weights ------------------------------------------------------------------------
+    def invalidate_weights(self):
+        self.ws = None
+        self._sessions.clear()
+
+    def invalidate_schedule(self):
+        pass                            # levels are per-step kernel arguments; nothing cached per schedule
+
+    def device(self):
+        return next(self.m.parameters()).device
+
+    def _iter_blocks(self):
+        from .model import ucdir as U
+        for grp in ("downs", "mid", "ups"):
+            for k, layer in enumerate(getattr(self.m, grp)):
+                if isinstance(layer, U.ResnetBlocWithAttn):
+                    yield "%s.%d" % (grp, k), layer
+
+    def ensure_weights(self):
+        dev = self.device()
+        _require_cuda(dev)
+        if self.ws is not None and self.ws.device == dev:
+            return
+        ws = WeightStore(dev)
+        m = self.m
+        inner = m.cfg["inner_channel"]
+        ws.put("temb.w1", m.noise_level_mlp[1].weight.float()); ws.put("temb.b1", m.noise_level_mlp[1].bias.float())
+        ws.put("temb.w2", m.noise_level_mlp[3].weight.float()); ws.put("temb.b2", m.noise_level_mlp[3].bias.float())
+        recs = []
+        self.blocks = list(self._iter_blocks())
+        for name, layer in self.blocks:
+            rb = layer.res_block
+            recs.append(torch.cat([rb.noise_func[0].weight.float().reshape(-1), rb.noise_func[0].bias.float(),
+                                   rb.noise_func[2].weight.float().reshape(-1), rb.noise_func[2].bias.float()]))
+            ws.put(name + ".norm1.w", rb.norm1.weight.float()); ws.put(name + ".norm1.b", rb.norm1.bias.float())
+            ws.put(name + ".norm2.w", rb.norm2.weight.float()); ws.put(name + ".norm2.b", rb.norm2.bias.float())
+            ws.put(name + ".conv1.w", pack_conv_f32(rb.conv1.weight)); ws.put(name + ".conv1.b", rb.conv1.bias.float())
+            ws.put(name + ".spdy.w", pack_conv_f32(rb.spdyconv.weight, groups=rb.nset))
+            ws.put(name + ".spdy.b", rb.spdyconv.bias.float())
+            ws.put(name + ".g.w0", rb.conv2[0].weight.float().reshape(16, 3)); ws.put(name + ".g.b0", rb.conv2[0].bias.float())
+            ws.put(name + ".g.w2", rb.conv2[2].weight.float()); ws.put(name + ".g.b2", rb.conv2[2].bias.float())
+            if isinstance(rb.res_conv, torch.nn.Conv2d):
+                ws.put(name + ".res.w", pack_conv_f32(rb.res_conv.weight)); ws.put(name + ".res.b", rb.res_conv.bias.float())
+            if layer.with_attn:
+                at = layer.attn
+                ws.put(name + ".attn.norm.w", at.norm.weight.float()); ws.put(name + ".attn.norm.b", at.norm.bias.float())
+                ws.put(name + ".attn.qkv.w", pack_conv_f32(at.qkv.weight))
+                ws.put(name + ".attn.out.w", pack_conv_f32(at.out.weight)); ws.put(name + ".attn.out.b", at.out.bias.float())
+        ws.put("temb.blk", torch.stack(recs))
+        from .model import ucdir as U
+        for grp in ("downs", "ups"):
+            for k, layer in enumerate(getattr(m, grp)):
+                name = "%s.%d" % (grp, k)
+                if isinstance(layer, torch.nn.Conv2d):          # in-conv: 6 -> 8 zero-padded input channels
+                    ws.put(name + ".w", pack_conv_f32(layer.weight, pad_cin_to=8)); ws.put(name + ".b", layer.bias.float())
+                elif isinstance(layer, (U.Downsample, U.Upsample)):
+                    ws.put(name + ".w", pack_conv_f32(layer.conv.weight)); ws.put(name + ".b", layer.conv.bias.float())
+        fc = m.final_conv
+        ws.put("final.norm.w", fc[0].weight.float()); ws.put("final.norm.b", fc[0].bias.float())
+        ws.put("final.w", pack_conv_f32(fc[3].weight)); ws.put("final.b", fc[3].bias.float())
+        self.inner = inner
+        self.ws = ws
+
+    # ---- graph --------------------------------------------------------------------------
+    def n_blocks(self):
+        return len(self.blocks)
+
+    def build_guidance_ops(self, ol: OpList, pool: Pool, BT: int, TH: int, TW: int, guide_tiles: torch.Tensor
+                           ) -> List[torch.Tensor]:
+        """27 step-invariant guidance maps [BT, H, W, 8] (model/ucdir.py:133-135 without attw), one per block."""
+        from .model import ucdir as U
+        ws = self.ws
+        maps = []
+        res = {}                                                 # block name -> (H, W)
+        H, W = TH, TW
+        for k, layer in enumerate(self.m.downs):
+            if isinstance(layer, U.Downsample):
+                H, W = H // 2, W // 2
+            elif isinstance(layer, U.ResnetBlocWithAttn):
+                res["downs.%d" % k] = (H, W)
+        for k, _ in enumerate(self.m.mid):
+            res["mid.%d" % k] = (H, W)
+        for k, layer in enumerate(self.m.ups):
+            if isinstance(layer, U.Upsample):
+                H, W = H * 2, W * 2
+            else:
+                res["ups.%d" % k] = (H, W)
+        for name, _ in self.blocks:
+            h, w = res[name]
+            t = torch.empty(BT * h * w * 8, dtype=F32, device=pool.device)
+            maps.append(t)
+            ol.add("UCDIR_OP_GUIDANCE",
+                   {"UCDIR_GUID_P_GUIDE": guide_tiles.data_ptr(), "UCDIR_GUID_P_W0": ws.ptr(name + ".g.w0"),
+                    "UCDIR_GUID_P_B0": ws.ptr(name + ".g.b0"), "UCDIR_GUID_P_W2": ws.ptr(name + ".g.w2"),
+                    "UCDIR_GUID_P_B2": ws.ptr(name + ".g.b2"), "UCDIR_GUID_P_DST": t.data_ptr()},
+                   {"UCDIR_GUID_I_B": BT, "UCDIR_GUID_I_GH": TH, "UCDIR_GUID_I_GW": TW, "UCDIR_GUID_I_H": h,
+                    "UCDIR_GUID_I_W": w})
+        return maps
+
+    def time_embed_op(self, ol: OpList, dst: torch.Tensor, L: int, levels_ptr: int = 0, level: float = 0.0) -> int:
+        ws = self.ws
+        return ol.add("UCDIR_OP_TIME_EMBED",
+                      {"UCDIR_TEMB_P_LEVELS": levels_ptr, "UCDIR_TEMB_P_W1": ws.ptr("temb.w1"),
+                       "UCDIR_TEMB_P_B1": ws.ptr("temb.b1"), "UCDIR_TEMB_P_W2": ws.ptr("temb.w2"),
+                       "UCDIR_TEMB_P_B2": ws.ptr("temb.b2"), "UCDIR_TEMB_P_BLK": ws.ptr("temb.blk"),
+                       "UCDIR_TEMB_P_DST": dst.data_ptr()},
+                      {"UCDIR_TEMB_I_L": L, "UCDIR_TEMB_I_NBLK": len(self.blocks), "UCDIR_TEMB_I_INNER": self.inner},
+                      {"UCDIR_TEMB_F_LEVEL": level})
+
+    def build_forward_ops(self, pool: Pool, BT: int, TH: int, TW: int, x_in: torch.Tensor, gmaps: List[torch.Tensor],
+                          attw: torch.Tensor, attw_stride: int, eps_ptr: int, stats: torch.Tensor) -> OpList:
+        """DY3h.naiveforward (model/ucdir.py:270-293) over the tile batch x_in[BT,TH,TW,8] -> eps[BT,TH,TW,4]."""
+        from .model import ucdir as U
+        ws, m = self.ws, self.m
+        bld = _Builder(pool, BT, stats)
+        ol = bld.ops
+        nbytes = stats.numel() * stats.element_size()
+        ol.add("UCDIR_OP_MEMSET", {0: stats.data_ptr()}, {0: nbytes & 0x7FFFFFFF, 1: nbytes >> 31})
+        blk_index = {name: k for k, (name, _) in enumerate(self.blocks)}
+        nblk = len(self.blocks)
+
+        def block(name, layer, x: Act, skip: Optional[Act]) -> Act:
+            rb = layer.res_block
+            cout = rb.dim_out
+            k = blk_index[name]
+            h1 = bld.new(cout, x.H, x.W)
+            _conv_op(ol, src0=x, src1=skip, w=ws.ptr(name + ".conv1.w"), bias=ws.ptr(name + ".conv1.b"),
+                     gamma=ws.ptr(name + ".norm1.w"), beta=ws.ptr(name + ".norm1.b"), pre=1, act=1, dst=h1, cout=cout, B=BT)
+            if ws.has(name + ".res.w"):
+                res = bld.new(cout, x.H, x.W, with_stats=False)
+                _conv_op(ol, src0=x, src1=skip, w=ws.ptr(name + ".res.w"), bias=ws.ptr(name + ".res.b"), ks=1, dst=res,
+                         cout=cout, B=BT)
+                own_res = True
+            else:
+                if skip is not None:
+                    raise RuntimeError("identity residual with a concatenated input")
+                res, own_res = x, False
+            out = bld.new(cout, x.H, x.W)
+            _conv_op(ol, src0=h1, w=ws.ptr(name + ".spdy.w"), bias=ws.ptr(name + ".spdy.b"),
+                     gamma=ws.ptr(name + ".norm2.w"), beta=ws.ptr(name + ".norm2.b"), pre=1, groups=rb.nset, mode=1,
+                     att=gmaps[k].data_ptr(), attw=attw.data_ptr() + k * 8 * 4, attw_stride=attw_stride, res=res,
+                     dst=out, cout=cout * rb.nset, B=BT, dst_c=cout)
+            bld.release(h1)
+            if own_res:
+                bld.release(res)
+            bld.release(x)
+            bld.release(skip)
+            if layer.with_attn:
+                out = attention(name, out)
+            return out
+
+        def attention(name, x: Act) -> Act:
+            """SelfAttention.forward, model/ucdir.py:165-182 (n_head = 1, d = C)."""
+            C, N = x.C, x.H * x.W
+            qkv = bld.new(3 * C, x.H, x.W, with_stats=False)
+            _conv_op(ol, src0=x, w=ws.ptr(name + ".attn.qkv.w"), gamma=ws.ptr(name + ".attn.norm.w"),
+                     beta=ws.ptr(name + ".attn.norm.b"), pre=1, ks=1, dst=qkv, cout=3 * C, B=BT)
+            if N * N >= 2 ** 31 or N * 3 * C >= 2 ** 31:
+                raise RuntimeError("attention over %d tokens exceeds the fp32 path's 32-bit strides" % N)
+            S = pool.get(BT * N * N * 4)
+            ol.add("UCDIR_OP_SGEMM_F32",
+                   {"UCDIR_SGEMM_P_A": qkv.ptr, "UCDIR_SGEMM_P_B": qkv.ptr + C * 4, "UCDIR_SGEMM_P_C": S.data_ptr()},
+                   {"UCDIR_SGEMM_I_BATCH": BT, "UCDIR_SGEMM_I_M": N, "UCDIR_SGEMM_I_N": N, "UCDIR_SGEMM_I_K": C,
+                    "UCDIR_SGEMM_I_LDA": 3 * C, "UCDIR_SGEMM_I_LDB": 3 * C, "UCDIR_SGEMM_I_LDC": N,
+                    "UCDIR_SGEMM_I_SA": N * 3 * C, "UCDIR_SGEMM_I_SB": N * 3 * C, "UCDIR_SGEMM_I_SC": N * N,
+                    "UCDIR_SGEMM_I_TRANSB": 1},
+                   {"UCDIR_SGEMM_F_ALPHA": 1.0 / math.sqrt(C)})
+            ol.add("UCDIR_OP_SOFTMAX_F32", {"UCDIR_SOFTMAX_P_X": S.data_ptr()},
+                   {"UCDIR_SOFTMAX_I_ROWS": BT * N, "UCDIR_SOFTMAX_I_COLS": N})
+            o = bld.new(C, x.H, x.W, with_stats=False)
+            ol.add("UCDIR_OP_SGEMM_F32",
+                   {"UCDIR_SGEMM_P_A": S.data_ptr(), "UCDIR_SGEMM_P_B": qkv.ptr + 2 * C * 4, "UCDIR_SGEMM_P_C": o.ptr},
+                   {"UCDIR_SGEMM_I_BATCH": BT, "UCDIR_SGEMM_I_M": N, "UCDIR_SGEMM_I_N": C, "UCDIR_SGEMM_I_K": N,
+                    "UCDIR_SGEMM_I_LDA": N, "UCDIR_SGEMM_I_LDB": 3 * C, "UCDIR_SGEMM_I_LDC": C,
+                    "UCDIR_SGEMM_I_SA": N * N, "UCDIR_SGEMM_I_SB": N * 3 * C, "UCDIR_SGEMM_I_SC": N * C,
+                    "UCDIR_SGEMM_I_TRANSB": 0},
+                   {"UCDIR_SGEMM_F_ALPHA": 1.0})
+            pool.put(S)
+            bld.release(qkv)
+            y = bld.new(C, x.H, x.W)
+            _conv_op(ol, src0=o, w=ws.ptr(name + ".attn.out.w"), bias=ws.ptr(name + ".attn.out.b"), ks=1, res=x, dst=y,
+                     cout=C, B=BT)
+            bld.release(o)
+            bld.release(x)
+            return y
+
+        feats: List[Act] = []
+        x = Act(x_in, 8, TH, TW, 0, keep=True)
+        for k, layer in enumerate(m.downs):
+            name = "downs.%d" % k
+            if isinstance(layer, torch.nn.Conv2d):
+                y = bld.new(layer.out_channels, x.H, x.W)
+                _conv_op(ol, src0=x, w=ws.ptr(name + ".w"), bias=ws.ptr(name + ".b"), dst=y, cout=layer.out_channels, B=BT)
+                x = y
+            elif isinstance(layer, U.Downsample):
+                y = bld.new(x.C, x.H // 2, x.W // 2)
+                _conv_op(ol, src0=x, w=ws.ptr(name + ".w"), bias=ws.ptr(name + ".b"), stride=2, dst=y, cout=x.C, B=BT)
+                x = y
+            else:
+                x.keep = True                                    # the input of a down block is always a stored feature
+                x = block(name, layer, x, None)
+            x.keep = True
+            feats.append(x)
+        x = feats[-1]
+        for k, layer in enumerate(m.mid):
+            x = block("mid.%d" % k, layer, x, None)              # first input is feats[-1] (kept); later ones are released
+        for k, layer in enumerate(m.ups):
+            name = "ups.%d" % k
+            if isinstance(layer, U.Upsample):
+                y = bld.new(x.C, x.H * 2, x.W * 2)
+                _conv_op(ol, src0=x, w=ws.ptr(name + ".w"), bias=ws.ptr(name + ".b"), up=1, dst=y, cout=x.C, B=BT)
+                bld.release(x)
+                x = y
+            else:
+                skip = feats.pop()
+                skip.keep = False
+                x = block(name, layer, x, skip)                  # torch.cat((x, feats.pop())) is never materialised
+        eps_dst = Act(_PtrBuf(eps_ptr), 4, TH, TW, 0, keep=True)      # type: ignore[arg-type]
+        _conv_op(ol, src0=x, w=ws.ptr("final.w"), bias=ws.ptr("final.b"), gamma=ws.ptr("final.norm.w"),
+                 beta=ws.ptr("final.norm.b"), pre=2, dst=eps_dst, cout=m.cfg["out_channel"], B=BT)
+        bld.release(x)
+        self.last_stat_slots = bld.next_slot
+        return ol
+
+    # ---- sessions -----------------------------------------------------------------------
+    def session(self, cond: torch.Tensor, guide: torch.Tensor, levels=None, geometry: Optional[Geometry] = None,
+                cond_channels: Optional[int] = None) -> "Session":
+        """A session binds one conditioning image batch (+ guidance) to a resident plan."""
+        self.ensure_weights()
+        B, _, h, w = cond.shape
+        if geometry is None:
+            geometry = self.default_geometry(B, h, w)
+        key = (B, h, w, geometry.kind, geometry.TH, geometry.TW, geometry.PD, cond.shape[1])
+        s = self._sessions.get(key)
+        if s is None:
+            self._sessions.clear()                               # one resident plan at a time: plans hold GBs
+            s = Session(self, geometry, cond.shape[1])
+            self._sessions[key] = s
+        s.bind(cond, guide)
+        return s
+
+    def default_geometry(self, B, h, w) -> Geometry:
+        m = self.m
+        if h * w > m.tile_trigger:
+            return geometry_tiled(B, h, w, m.tile_skip, m.tile_padding)
+        return geometry_direct(B, h, w)
+
+    # ---- reference-signature entry points ------------------------------------------------
+    def forward(self, x, time, guide):
+        """DY3h.forward(x[B,6,h,w], time[B,1], guide[B,3,h,w]) -> eps[B,3,h,w]  (model/ucdir.py:295-307)."""
+        return self._forward_generic(x, time, guide, None)
+
+    def forward_plain(self, x, time, guide):
+        """DY3h.naiveforward: no padding (model/ucdir.py:270-293)."""
+        self.ensure_weights()
+        B, _, h, w = x.shape
+        return self._forward_generic(x, time, guide, geometry_naive(B, h, w))
+
+    def _forward_generic(self, x, time, guide, geometry):
+        self.ensure_weights()
+        x = x.contiguous().float()
+        sess = self.session(x, guide.contiguous().float(), geometry=geometry, cond_channels=x.shape[1])
+        out = torch.empty((x.shape[0], self.m.cfg["out_channel"], x.shape[2], x.shape[3]), device=x.device, dtype=F32)
+        sess.eps_only(time.reshape(-1).float().contiguous(), out)
+        return out
+
+
+class _PtrBuf:
+    """Adapter: a raw device pointer where an Act expects a tensor."""
+
+    def __init__(self, ptr): self._p = ptr
+    def data_ptr(self): return self._p
+
+
+# ======================================================================================
+# session: resident per-image-batch state + the per-step op array
+# ======================================================================================
+class Session:
+    """Everything that is invariant across the T denoising steps of one image batch: tile table, padded
+    guidance tiles and the 27 guidance maps per chunk, workspace, and the op array of one step:
+
+        TIME_EMBED -> per chunk [MEMSET stats, GATHER_TILES, UNet ops] -> (all-gather) -> SCATTER(+posterior)
+
+    Tile sharding: with a process group given, rank r computes tiles [r*per, (r+1)*per) and one
+    all_gather_into_tensor on the eps tile buffer reassembles the step; the posterior update runs
+    redundantly on every rank with identical noise.
+    """
+
+    def __init__(self, eng: UNetEngine, geo: Geometry, in_channels: int):
+        self.eng, self.geo = eng, geo
+        dev = eng.device()
+        self.dev = dev
+        self.in_channels = in_channels          # 3: cond only (x_t supplied per step); 6: already concatenated
+        self.group = None
+        self.rank, self.world = 0, 1
+        if os.environ.get("UCDIR_SHARD", "tiles") == "tiles" and torch.distributed.is_available() \
+                and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            self.group = torch.distributed.group.WORLD
+            self.rank, self.world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        g = geo
+        NT = g.n_tiles
+        self.per_rank = (NT + self.world - 1) // self.world
+        self.NT_pad = self.per_rank * self.world
+        lo = min(self.rank * self.per_rank, NT)
+        hi = min(lo + self.per_rank, NT)
+        self.my_tiles = (lo, hi)
+        tab = g.table()
+        self.tab = torch.from_numpy(tab).to(dev)
+        self.owner_y = torch.from_numpy(g.owner_y).to(dev)
+        self.owner_x = torch.from_numpy(g.owner_x).to(dev)
+        self.y0 = torch.tensor(g.ys, dtype=torch.int32, device=dev)
+        self.x0 = torch.tensor(g.xs, dtype=torch.int32, device=dev)
+        self.cond = torch.empty((g.B, in_channels, g.IH, g.IW), dtype=F32, device=dev)
+        self.guide = torch.empty((g.B, 3, g.IH, g.IW), dtype=F32, device=dev)
+        self.eps = torch.empty((self.NT_pad, g.TH, g.TW, 4), dtype=F32, device=dev)
+        per_chunk = max(1, _max_chunk_pixels() // (g.TH * g.TW))
+        self.chunks = [(a, min(a + per_chunk, hi)) for a in range(lo, hi, per_chunk)]
+        self.pool = Pool(dev)
+        nblk = eng.n_blocks()
+        self.levels = torch.zeros(max(NT, 1), dtype=F32, device=dev)      # per-tile noise levels (generic forward)
+        self.attw = torch.empty((max(NT, 1), nblk, 8), dtype=F32, device=dev)
+        self.static_ops = OpList()
+        self.step_ops = OpList()
+        self.idx_gather: List[int] = []
+        self.gmaps_all = []
+        self.guide_tiles_all = []
+        maxbt = max((b - a) for a, b in self.chunks) if self.chunks else 1
+        self.stats = torch.empty((MAX_STAT_SLOTS, maxbt, 2), dtype=torch.float64, device=dev)
+        self.x_tiles = torch.empty((maxbt, g.TH, g.TW, 8), dtype=F32, device=dev)
+        # step op 0: timestep embedding -> attw table
+        self.idx_temb = eng.time_embed_op(self.step_ops, self.attw, 1, 0, 0.0)
+        for (a, b) in self.chunks:
+            BT = b - a
+            tab_ptr = self.tab.data_ptr() + a * 3 * 4
+            gt = torch.empty((BT, g.TH, g.TW, 4), dtype=F32, device=dev)
+            self.guide_tiles_all.append(gt)
+            self.static_ops.add("UCDIR_OP_GATHER_TILES",
+                                {"UCDIR_GATHER_P_SRC_A": self.guide.data_ptr(), "UCDIR_GATHER_P_TAB": tab_ptr,
+                                 "UCDIR_GATHER_P_DST": gt.data_ptr()},
+                                {"UCDIR_GATHER_I_BT": BT, "UCDIR_GATHER_I_TH": g.TH, "UCDIR_GATHER_I_TW": g.TW,
+                                 "UCDIR_GATHER_I_IMG_H": g.IH, "UCDIR_GATHER_I_IMG_W": g.IW, "UCDIR_GATHER_I_PD": g.PD,
+                                 "UCDIR_GATHER_I_CA": 3, "UCDIR_GATHER_I_CB": 0, "UCDIR_GATHER_I_CD": 4})
+            gmaps = eng.build_guidance_ops(self.static_ops, self.pool, BT, g.TH, g.TW, gt)
+            self.gmaps_all.append(gmaps)
+            ca = in_channels
+            self.idx_gather.append(self.step_ops.add(
+                "UCDIR_OP_GATHER_TILES",
+                {"UCDIR_GATHER_P_SRC_A": self.cond.data_ptr(), "UCDIR_GATHER_P_TAB": tab_ptr,
+                 "UCDIR_GATHER_P_DST": self.x_tiles.data_ptr()},
+                {"UCDIR_GATHER_I_BT": BT, "UCDIR_GATHER_I_TH": g.TH, "UCDIR_GATHER_I_TW": g.TW,
+                 "UCDIR_GATHER_I_IMG_H": g.IH, "UCDIR_GATHER_I_IMG_W": g.IW, "UCDIR_GATHER_I_PD": g.PD,
+                 "UCDIR_GATHER_I_CA": ca, "UCDIR_GATHER_I_CB": 6 - ca, "UCDIR_GATHER_I_CD": 8}))
+            eps_ptr = self.eps.data_ptr() + a * g.TH * g.TW * 4 * 4
+            stats_view = self.stats.view(-1)[:MAX_STAT_SLOTS * BT * 2].view(MAX_STAT_SLOTS, BT, 2)   # same storage
+            sub = eng.build_forward_ops(self.pool, BT, g.TH, g.TW, self.x_tiles, gmaps, self.attw, 0, eps_ptr,
+                                        stats_view)
+            self._chunk_attw_fix(sub, a)
+            self.step_ops.extend(sub)
+        self.n_unet_ops = len(self.step_ops)
+        # the scatter (+ posterior) closes the step; kept as a separate one-op list so that a collective can
+        # be issued between the UNet ops and it
+        self.tail_ops = OpList()
+        self.tail_ops.add("UCDIR_OP_SCATTER",
+                          {"UCDIR_SCATTER_P_EPS": self.eps.data_ptr(), "UCDIR_SCATTER_P_OWNER_Y": self.owner_y.data_ptr(),
+                           "UCDIR_SCATTER_P_OWNER_X": self.owner_x.data_ptr(), "UCDIR_SCATTER_P_Y0": self.y0.data_ptr(),
+                           "UCDIR_SCATTER_P_X0": self.x0.data_ptr()},
+                          {"UCDIR_SCATTER_I_BIMG": g.B, "UCDIR_SCATTER_I_IMG_H": g.IH, "UCDIR_SCATTER_I_IMG_W": g.IW,
+                           "UCDIR_SCATTER_I_NTY": g.nty, "UCDIR_SCATTER_I_NTX": g.ntx, "UCDIR_SCATTER_I_TH": g.TH,
+                           "UCDIR_SCATTER_I_TW": g.TW, "UCDIR_SCATTER_I_PD": g.PD, "UCDIR_SCATTER_I_CE": 4,
+                           "UCDIR_SCATTER_I_MODE": 0, "UCDIR_SCATTER_I_CLIP": 1, "UCDIR_SCATTER_I_C": 3})
+        self._attw_stride = 0
+        self._bound = False
+
+    # per-sample attw addressing: sample b of chunk starting at tile a reads attw[(a + b) * stride]
+    def _chunk_attw_fix(self, sub: OpList, a: int):
+        self._mix_ops = getattr(self, "_mix_ops", [])
+        for o in sub.ops:
+            if o.kind == K_["UCDIR_OP_CONV_F32"] and o.i[K_["UCDIR_CONV_I_MODE"]] == 1:
+                self._mix_ops.append((o, a, int(o.p[K_["UCDIR_CONV_P_ATTW"]])))
+
+    def _set_attw_mode(self, per_tile: bool):
+        """per_tile=False: one level for the whole batch (sampler).  True: levels[tile] (generic forward)."""
+        nblk = self.eng.n_blocks()
+        stride = nblk * 8 if per_tile else 0
+        if stride == self._attw_stride and self._bound:
+            return
+        for o, a, base in self._mix_ops:
+            o.i[K_["UCDIR_CONV_I_ATTW_STRIDE"]] = stride
+            o.p[K_["UCDIR_CONV_P_ATTW"]] = base + a * stride * 4
+        self._attw_stride = stride
+        self.step_ops._arr = None
+
+    # ---- binding -------------------------------------------------------------------------
+    def stream(self) -> int:
+        return _stream(self.dev)
+
+    def bind(self, cond: torch.Tensor, guide: torch.Tensor):
+        """Copy the conditioning batch in and (re)compute the step-invariant guidance maps."""
+        self.cond.copy_(cond)
+        self.guide.copy_(guide)
+        if len(self.static_ops):
+            _run_ops(self.static_ops.array(), len(self.static_ops), self.stream())
+        self._bound = True
+
+    # ---- one UNet evaluation over all tiles, result stitched to NCHW ---------------------------
+    def _run_unet(self, x_t: Optional[torch.Tensor]):
+        ops = self.step_ops
+        if x_t is not None:
+            for k in self.idx_gather:
+                ops.ops[k].p[K_["UCDIR_GATHER_P_SRC_B"]] = x_t.data_ptr()
+            ops._arr = None
+        _run_ops(ops.array(), len(ops), self.stream())
+        if self.group is not None:
+            torch.distributed.all_gather_into_tensor(self.eps, self.eps[self.rank * self.per_rank:(self.rank + 1) * self.per_rank],
+                                                     group=self.group)
+
+    def eps_only(self, levels: torch.Tensor, out: torch.Tensor):
+        """Generic DY3h.forward: per-image noise levels from a device tensor, eps stitched into `out`."""
+        g = self.geo
+        self._set_attw_mode(True)
+        self.levels[:g.n_tiles].copy_(levels.repeat_interleave(g.tiles_per_image))
+        o = self.step_ops.ops[self.idx_temb]
+        o.p[K_["UCDIR_TEMB_P_LEVELS"]] = self.levels.data_ptr()
+        o.i[K_["UCDIR_TEMB_I_L"]] = g.n_tiles
+        self.step_ops._arr = None
+        self._run_unet(None)
+        t = self.tail_ops.ops[0]
+        t.i[K_["UCDIR_SCATTER_I_MODE"]] = 0
+        t.p[K_["UCDIR_SCATTER_P_OUT"]] = out.data_ptr()
+        self.tail_ops._arr = None
+        _run_ops(self.tail_ops.array(), 1, self.stream())
+
+    def step(self, x_t: torch.Tensor, out: torch.Tensor, level: float, scalars, noise: Optional[torch.Tensor],
+             clip: bool = True, level_index=None):
+        """One p_sample (model/diffusion.py:160-183): eps = UNet(cat[cond, x_t], level); posterior update."""
+        if self.in_channels != 3:
+            raise RuntimeError("session was bound with a pre-concatenated input; step() needs cond only")
+        self._set_attw_mode(False)
+        o = self.step_ops.ops[self.idx_temb]
+        o.p[K_["UCDIR_TEMB_P_LEVELS"]] = None
+        o.i[K_["UCDIR_TEMB_I_L"]] = 1
+        o.f[K_["UCDIR_TEMB_F_LEVEL"]] = level
+        self._run_unet(x_t)
+        a, b, c1, c2, sigma = scalars
+        t = self.tail_ops.ops[0]
+        t.i[K_["UCDIR_SCATTER_I_MODE"]] = 1
+        t.i[K_["UCDIR_SCATTER_I_CLIP"]] = 1 if clip else 0
+        t.p[K_["UCDIR_SCATTER_P_XT"]] = x_t.data_ptr()
+        t.p[K_["UCDIR_SCATTER_P_NOISE"]] = noise.data_ptr() if noise is not None else None
+        t.p[K_["UCDIR_SCATTER_P_OUT"]] = out.data_ptr()
+        for k, v in zip(("A", "B", "C1", "C2", "SIGMA"), (a, b, c1, c2, sigma)):
+            t.f[K_["UCDIR_SCATTER_F_" + k]] = v
+        self.tail_ops._arr = None
+        _run_ops(self.tail_ops.array(), 1, self.stream())
+
+    def launches_per_step(self) -> int:
+        n = 0
+        for o in self.step_ops.ops + self.tail_ops.ops:
+            n += 0 if o.kind == K_["UCDIR_OP_MEMSET"] else 1
+        return n
+
+
+# ======================================================================================
+# predictor engine (UNetSeeInDark, model/ucdir.py:310-416)
+# ======================================================================================
+class PredictorEngine:
+    def __init__(self, module):
+        self.m = module
+        self.ws: Optional[WeightStore] = None
+        self._plans: Dict[tuple, tuple] = {}
+
+    def invalidate_weights(self):
+        self.ws = None
+        self._plans.clear()
+
+    def device(self):
+        return next(self.m.parameters()).device
+
+    def ensure_weights(self):
+        dev = self.device()
+        _require_cuda(dev)
+        if self.ws is not None and self.ws.device == dev:
+            return
+        ws = WeightStore(dev)
+        for name, layer in self.m.named_children():
+            if isinstance(layer, torch.nn.ConvTranspose2d):
+                for py in range(2):
+                    for px in range(2):
+                        ws.put("%s.w%d%d" % (name, py, px), pack_convT_phase_f32(layer.weight, py, px))
+                ws.put(name + ".b", layer.bias.float())
+            elif isinstance(layer, torch.nn.Conv2d):
+                ws.put(name + ".w", pack_conv_f32(layer.weight, pad_cin_to=8 if layer.in_channels < 8 else None))
+                ws.put(name + ".b", layer.bias.float())
+        self.ws = ws
+
+    def _plan(self, B, h, w):
+        key = (B, h, w)
+        if key in self._plans:
+            return self._plans[key]
+        self._plans.clear()
+        dev = self.device()
+        ws = self.ws
+        geo = geometry_direct(B, h, w)                            # model/ucdir.py:352-358: same pad rule
+        TH, TW = geo.TH, geo.TW
+        pool = Pool(dev)
+        x_img = torch.empty((B, 3, h, w), dtype=F32, device=dev)
+        x_tiles = torch.empty((B, TH, TW, 8), dtype=F32, device=dev)
+        tab = torch.from_numpy(geo.table()).to(dev)
+        out_tiles = torch.empty((B, TH, TW, 4), dtype=F32, device=dev)
+        dummy_stats = torch.zeros((1, B, 2), dtype=torch.float64, device=dev)
+        bld = _Builder(pool, B, dummy_stats)
+        ol = bld.ops
+        ol.add("UCDIR_OP_GATHER_TILES",
+               {"UCDIR_GATHER_P_SRC_A": x_img.data_ptr(), "UCDIR_GATHER_P_TAB": tab.data_ptr(),
+                "UCDIR_GATHER_P_DST": x_tiles.data_ptr()},
+               {"UCDIR_GATHER_I_BT": B, "UCDIR_GATHER_I_TH": TH, "UCDIR_GATHER_I_TW": TW, "UCDIR_GATHER_I_IMG_H": h,
+                "UCDIR_GATHER_I_IMG_W": w, "UCDIR_GATHER_I_PD": 0, "UCDIR_GATHER_I_CA": 3, "UCDIR_GATHER_I_CB": 0,
+                "UCDIR_GATHER_I_CD": 8})
+
+        def conv(name, x: Act, cout, skip: Optional[Act] = None, ks=3, act=2, dst: Optional[Act] = None) -> Act:
+            y = dst or bld.new(cout, x.H, x.W, with_stats=False)
+            _conv_op(ol, src0=x, src1=skip, w=ws.ptr(name + ".w"), bias=ws.ptr(name + ".b"), ks=ks, act=act, dst=y,
+                     cout=cout, B=B)
+            return y
+
+        def pool2(x: Act) -> Act:
+            y = bld.new(x.C, x.H // 2, x.W // 2, with_stats=False)
+            ol.add("UCDIR_OP_MAXPOOL2", {"UCDIR_POOL_P_SRC": x.ptr, "UCDIR_POOL_P_DST": y.ptr},
+                   {"UCDIR_POOL_I_B": B, "UCDIR_POOL_I_H": y.H, "UCDIR_POOL_I_W": y.W, "UCDIR_POOL_I_C": x.C})
+            return y
+
+        def upconv(name, x: Act, cout) -> Act:
+            """ConvTranspose2d(k=2, s=2) as four 1x1 GEMMs writing interleaved output phases (ucdir.py:381-400)."""
+            y = bld.new(cout, x.H * 2, x.W * 2, with_stats=False)
+            for py in range(2):
+                for px in range(2):
+                    _conv_op(ol, src0=x, w=ws.ptr("%s.w%d%d" % (name, py, px)), bias=ws.ptr(name + ".b"), ks=1, dst=y,
+                             cout=cout, B=B, dst_up=1, dst_py=py, dst_px=px)
+            return y
+
+        x = Act(x_tiles, 8, TH, TW, 0, keep=True)
+        enc = []
+        chans = [32, 64, 128, 256, 512]
+        for lvl, c in enumerate(chans, start=1):
+            a = conv("conv%d_1" % lvl, x, c)
+            if lvl > 1:
+                bld.release(x)
+            x = conv("conv%d_2" % lvl, a, c)
+            bld.release(a)
+            if lvl < 5:
+                x.keep = True
+                enc.append(x)
+                x = pool2(x)
+        for lvl, c in zip(range(6, 10), [256, 128, 64, 32]):
+            u = upconv("upv%d" % lvl, x, c)
+            bld.release(x)
+            skip = enc.pop()
+            skip.keep = False
+            a = conv("conv%d_1" % lvl, u, c, skip=skip)           # torch.cat([up, conv_k], 1) as a dual-source K loop
+            bld.release(u); bld.release(skip)
+            x = conv("conv%d_2" % lvl, a, c)
+            bld.release(a)
+        dst = Act(out_tiles, 4, TH, TW, 0, keep=True)
+        conv("conv10_1", x, 3, ks=1, act=0, dst=dst)
+        bld.release(x)
+        owner_y = torch.from_numpy(geo.owner_y).to(dev); owner_x = torch.from_numpy(geo.owner_x).to(dev)
+        z = torch.zeros(1, dtype=torch.int32, device=dev)
+        idx_scatter = ol.add("UCDIR_OP_SCATTER",
+                             {"UCDIR_SCATTER_P_EPS": out_tiles.data_ptr(), "UCDIR_SCATTER_P_OWNER_Y": owner_y.data_ptr(),
+                              "UCDIR_SCATTER_P_OWNER_X": owner_x.data_ptr(), "UCDIR_SCATTER_P_Y0": z.data_ptr(),
+                              "UCDIR_SCATTER_P_X0": z.data_ptr()},
+                             {"UCDIR_SCATTER_I_BIMG": B, "UCDIR_SCATTER_I_IMG_H": h, "UCDIR_SCATTER_I_IMG_W": w,
+                              "UCDIR_SCATTER_I_NTY": 1, "UCDIR_SCATTER_I_NTX": 1, "UCDIR_SCATTER_I_TH": TH,
+                              "UCDIR_SCATTER_I_TW": TW, "UCDIR_SCATTER_I_PD": 0, "UCDIR_SCATTER_I_CE": 4,
+                              "UCDIR_SCATTER_I_MODE": 0, "UCDIR_SCATTER_I_C": 3})
+        plan = (ol, x_img, idx_scatter, (pool, x_tiles, tab, out_tiles, owner_y, owner_x, z, dummy_stats))
+        self._plans[key] = plan
+        return plan
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self.ensure_weights()
+        B, c, h, w = x.shape
+        if c != 3:
+            raise ValueError("predictor expects 3 input channels")
+        ol, x_img, idx_scatter, _ = self._plan(B, h, w)
+        x_img.copy_(x)
+        out = torch.empty((B, 3, h, w), dtype=F32, device=x.device)
+        ol.ops[idx_scatter].p[K_["UCDIR_SCATTER_P_OUT"]] = out.data_ptr()
+        ol._arr = None
+        _run_ops(ol.array(), len(ol), _stream(x.device))
+        return out
