@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define UCDIR_ABI_VERSION 3
+#define UCDIR_ABI_VERSION 4
 
 #define UCDIR_OP_NPTR 16
 #define UCDIR_OP_NINT 32
@@ -174,6 +174,12 @@ int ucdir_run_ops(const ucdir_op_t* ops, int n_ops, void* stream);
 
 /* Validate ops without launching (same return codes). */
 int ucdir_check_ops(const ucdir_op_t* ops, int n_ops);
+
+/* Per-op device timing for benchmarks: between begin and end every op run by ucdir_run_ops is bracketed by CUDA
+ * events on its stream.  ucdir_profile_end waits for the last event and fills up to `cap` records
+ * {milliseconds, index of the op inside its ucdir_run_ops call, op kind}; returns the record count or <0. */
+int ucdir_profile_begin(void);
+int ucdir_profile_end(float* ms, int* op_index, int* kind, int cap);
 
 int ucdir_abi_version(void);
 int ucdir_op_sizeof(void);

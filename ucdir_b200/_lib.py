@@ -37,7 +37,7 @@ class Op(ctypes.Structure):
 
 
 EXPORTS = ["ucdir_run_ops", "ucdir_check_ops", "ucdir_abi_version", "ucdir_op_sizeof", "ucdir_last_error",
-           "ucdir_launch_count", "ucdir_device_ok"]
+           "ucdir_launch_count", "ucdir_device_ok", "ucdir_profile_begin", "ucdir_profile_end"]
 
 _lib = None
 
@@ -64,6 +64,10 @@ def load(require_device=True):
         lib.ucdir_last_error.restype = ctypes.c_char_p
         lib.ucdir_launch_count.restype = ctypes.c_longlong
         lib.ucdir_device_ok.restype = ctypes.c_int
+        lib.ucdir_profile_begin.restype = ctypes.c_int
+        lib.ucdir_profile_end.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int),
+                                          ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+        lib.ucdir_profile_end.restype = ctypes.c_int
         if lib.ucdir_abi_version() != C["UCDIR_ABI_VERSION"]:
             raise UcdirLibraryError("libucdir_b200.so ABI %d != header ABI %d: rebuild" % (
                 lib.ucdir_abi_version(), C["UCDIR_ABI_VERSION"]))
@@ -108,3 +112,18 @@ def check_ops(ops, n):
 
 def launch_count():
     return int(load(require_device=False).ucdir_launch_count())
+
+
+def profile_begin():
+    load().ucdir_profile_begin()
+
+
+def profile_end(cap=1 << 20):
+    """-> list of (ms, op_index, kind) for every op run since profile_begin()."""
+    ms = (ctypes.c_float * cap)()
+    idx = (ctypes.c_int * cap)()
+    kind = (ctypes.c_int * cap)()
+    n = load().ucdir_profile_end(ms, idx, kind, cap)
+    if n < 0:
+        raise UcdirLibraryError("ucdir_profile_end failed: %s" % last_error())
+    return [(ms[k], idx[k], kind[k]) for k in range(n)]

@@ -1,11 +1,23 @@
 // C ABI of libucdir_b200.so: op dispatcher, error reporting, capability probe.  See include/ucdir_b200.h.
 #include <cstdarg>
 #include <cstdio>
+#include <vector>
 #include "common.cuh"
 
 namespace ucdir {
 static thread_local char g_err[512] = "";
 long long g_launches = 0;
+// per-op CUDA-event profiling (bench.py's live roofline measurement): one event after every op
+static bool g_prof = false;
+static std::vector<cudaEvent_t> g_ev;
+static std::vector<int> g_ev_op;      // index of the op (within its run_ops call) the event closes, -1 = call start
+static std::vector<int> g_ev_kind;
+static size_t g_ev_used = 0;
+static void prof_mark(cudaStream_t st, int op_index, int kind) {
+  if (g_ev_used == g_ev.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; g_ev.push_back(e); g_ev_op.push_back(0); g_ev_kind.push_back(0); }
+  g_ev_op[g_ev_used] = op_index; g_ev_kind[g_ev_used] = kind;
+  cudaEventRecord(g_ev[g_ev_used++], st);
+}
 void set_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
@@ -41,8 +53,10 @@ extern "C" {
 int ucdir_run_ops(const ucdir_op_t* ops, int n_ops, void* stream) {
   if (!ops || n_ops < 0) { ucdir::set_error("run_ops: bad arguments"); return -1; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (ucdir::g_prof) ucdir::prof_mark(st, -1, 0);
   for (int k = 0; k < n_ops; ++k) {
     int rc = ucdir::dispatch(ops[k], st, false);
+    if (ucdir::g_prof && !rc) ucdir::prof_mark(st, k, ops[k].kind);
     if (rc) { char tmp[400]; snprintf(tmp, sizeof(tmp), "%s", ucdir::g_err); ucdir::set_error("op %d (kind %d): %s", k, ops[k].kind, tmp); return rc; }
   }
   cudaError_t e = cudaPeekAtLastError();
@@ -57,6 +71,26 @@ int ucdir_check_ops(const ucdir_op_t* ops, int n_ops) {
     if (rc) { char tmp[400]; snprintf(tmp, sizeof(tmp), "%s", ucdir::g_err); ucdir::set_error("op %d (kind %d): %s", k, ops[k].kind, tmp); return rc; }
   }
   return 0;
+}
+
+int ucdir_profile_begin(void) { ucdir::g_prof = true; ucdir::g_ev_used = 0; return 0; }
+
+int ucdir_profile_end(float* ms, int* op_index, int* kind, int cap) {
+  ucdir::g_prof = false;
+  if (ucdir::g_ev_used == 0) return 0;
+  if (cudaEventSynchronize(ucdir::g_ev[ucdir::g_ev_used - 1]) != cudaSuccess) { ucdir::set_error("profile_end: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
+  int n = 0;
+  for (size_t k = 1; k < ucdir::g_ev_used && n < cap; ++k) {
+    if (ucdir::g_ev_op[k] < 0) continue;                       // start marker of a later call
+    float t = 0.f;
+    cudaEventElapsedTime(&t, ucdir::g_ev[k - 1], ucdir::g_ev[k]);
+    if (ms) ms[n] = t;
+    if (op_index) op_index[n] = ucdir::g_ev_op[k];
+    if (kind) kind[n] = ucdir::g_ev_kind[k];
+    ++n;
+  }
+  ucdir::g_ev_used = 0;
+  return n;
 }
 
 int ucdir_abi_version(void) { return UCDIR_ABI_VERSION; }

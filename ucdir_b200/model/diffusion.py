@@ -62,6 +62,7 @@ class GaussianDiffusion(nn.Module):
         self.conditional = conditional
         self._noise_source = None      # test hook: callable(shape) -> tensor, replaces torch.randn
         self._sched_host = None
+        self._shared_gen = None        # tile-sharded mode: every rank draws the identical noise sequence
 
     # ---- reference surface --------------------------------------------------------------
     def set_loss(self, device):
@@ -109,7 +110,20 @@ class GaussianDiffusion(nn.Module):
     def _randn(self, shape, device):
         if self._noise_source is not None:
             return self._noise_source(tuple(shape)).to(device=device, dtype=torch.float32)
+        if self._shared_gen is not None:
+            return torch.randn(shape, device=device, generator=self._shared_gen)
         return torch.randn(shape, device=device)
+
+    def _sync_noise_stream(self, sess, device):
+        """Tile sharding: the posterior update runs redundantly on every rank, so all ranks must
+        consume the same z_t.  Rank 0 draws a seed from its default generator and broadcasts it once per image."""
+        if sess.group is None:
+            self._shared_gen = None
+            return
+        seed = torch.randint(0, 2 ** 62, (1,), device=device, dtype=torch.int64)
+        torch.distributed.broadcast(seed, 0, group=sess.group)
+        self._shared_gen = torch.Generator(device=device)
+        self._shared_gen.manual_seed(int(seed.item()))
 
     def _step_scalars(self, t):
         """The five per-step scalars of model/diffusion.py:150-158,183 as fp32 values."""
@@ -153,17 +167,19 @@ class GaussianDiffusion(nn.Module):
         n_snap = sum(1 for i in range(T) if i % sample_inter == 0)
         ret = torch.empty((b * (1 + n_snap),) + tuple(x.shape[1:]), device=device, dtype=torch.float32)
         ret[:b] = x
-        sess = self.denoise_fn.engine().session(x, kwargs["guide"], levels=[self.noise_level(t) for t in range(T)])
+        sess = self.denoise_fn.engine().session(x, kwargs["guide"])
+        self._sync_noise_stream(sess, device)
         img = self._randn(x.shape, device).contiguous()
         nxt = torch.empty_like(img)
         row = 1
         for i in reversed(range(T)):
             noise = self._randn(x.shape, device) if i > 0 else None
-            sess.step(img, nxt, self.noise_level(i), self._step_scalars(i), noise, True, level_index=i)
+            sess.step(img, nxt, self.noise_level(i), self._step_scalars(i), noise, True)
             img, nxt = nxt, img
             if i % sample_inter == 0:
                 ret[row * b:(row + 1) * b] = img
                 row += 1
+        self._shared_gen = None
         return ret if continous else ret[-1]
 
     @torch.no_grad()
