@@ -48,7 +48,7 @@ def layout():
 def test_library_is_native_and_counts_launches(net):
     from ucdir_b200 import _lib
     before = _lib.launch_count()
-    net.predictor(torch.zeros(1, 3, 32, 32, device="cuda"))
+    net.predictor(torch.zeros(1, 3, 48, 48, device="cuda"))
     torch.cuda.synchronize()
     assert _lib.launch_count() - before >= 30
 
