@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define UCDIR_ABI_VERSION 4
+#define UCDIR_ABI_VERSION 5
 
 #define UCDIR_OP_NPTR 16
 #define UCDIR_OP_NINT 32
@@ -107,7 +107,8 @@ enum ucdir_sgemm_int {
   UCDIR_SGEMM_I_BATCH = 0, UCDIR_SGEMM_I_M = 1, UCDIR_SGEMM_I_N = 2, UCDIR_SGEMM_I_K = 3,
   UCDIR_SGEMM_I_LDA = 4, UCDIR_SGEMM_I_LDB = 5, UCDIR_SGEMM_I_LDC = 6,
   UCDIR_SGEMM_I_SA = 7, UCDIR_SGEMM_I_SB = 8, UCDIR_SGEMM_I_SC = 9,  /* batch strides in elements */
-  UCDIR_SGEMM_I_TRANSB = 10
+  UCDIR_SGEMM_I_TRANSB = 10,
+  UCDIR_SGEMM_I_A_BF16 = 11, UCDIR_SGEMM_I_B_BF16 = 12, UCDIR_SGEMM_I_C_BF16 = 13   /* operand element types (0 = fp32) */
 };
 enum ucdir_sgemm_flt { UCDIR_SGEMM_F_ALPHA = 0 };
 
@@ -165,6 +166,36 @@ enum ucdir_scatter_flt {
 /* ---- UCDIR_OP_MAXPOOL2: DST[B,H,W,C] = max 2x2 of SRC[B,2H,2W,C] (fp32 NHWC) -------------------------- */
 enum ucdir_pool_ptr { UCDIR_POOL_P_SRC = 0, UCDIR_POOL_P_DST = 1 };
 enum ucdir_pool_int { UCDIR_POOL_I_B = 0, UCDIR_POOL_I_H = 1, UCDIR_POOL_I_W = 2, UCDIR_POOL_I_C = 3 };
+
+/* ---- UCDIR_OP_TC_CONV: bf16 tcgen05 / TMA implicit-GEMM convolution (ucdir_tc.cu) ---------------------------
+ * Same reference lines as UCDIR_OP_CONV_F32.  Activations bf16 NHWC; weights bf16 [NTOT][K] K-major with
+ * K = (tap, channel chunk) slabs of KC channels, packed by ucdir_b200/engine.py:pack_tc_*.
+ * Source pixel of output (y, x), tap (ty, tx): (y*STRIDE + ty + OY0, x*STRIDE + tx + OX0); outside the image = 0.
+ * GN=1: GroupNorm(1,C) of the input is folded: weights carry gamma, the epilogue applies
+ *   v = rstd*acc - mean*rstd*TG[cls][n] + TB[cls][n]  (cls = 3x3 border class when NCLS = 9, else 0);
+ * GN=0: v = acc + TB[0][n] (TB = bias).  MODE / ACT / RES / DST_UP as in UCDIR_OP_CONV_F32 (RES, DST bf16;
+ * DST_F32=1 stores fp32 and only columns < NCOL_VALID).  DST_STATS as in UCDIR_OP_CONV_F32. */
+enum ucdir_tc_ptr {
+  UCDIR_TC_P_SRC0 = 0, UCDIR_TC_P_SRC1 = 1, UCDIR_TC_P_W = 2, UCDIR_TC_P_TB = 3, UCDIR_TC_P_TG = 4,
+  UCDIR_TC_P_STATS0 = 5, UCDIR_TC_P_STATS1 = 6, UCDIR_TC_P_RES = 7, UCDIR_TC_P_ATT = 8, UCDIR_TC_P_ATTW = 9,
+  UCDIR_TC_P_DST = 10, UCDIR_TC_P_DST_STATS = 11
+};
+enum ucdir_tc_int {
+  UCDIR_TC_I_B = 0, UCDIR_TC_I_H = 1, UCDIR_TC_I_W = 2, UCDIR_TC_I_SRC_H = 3, UCDIR_TC_I_SRC_W = 4,
+  UCDIR_TC_I_C0 = 5, UCDIR_TC_I_C1 = 6, UCDIR_TC_I_NTOT = 7, UCDIR_TC_I_NCOL_VALID = 8,
+  UCDIR_TC_I_NTY = 9, UCDIR_TC_I_NTX = 10, UCDIR_TC_I_OY0 = 11, UCDIR_TC_I_OX0 = 12, UCDIR_TC_I_STRIDE = 13,
+  UCDIR_TC_I_GROUPS = 14, UCDIR_TC_I_KC = 15, UCDIR_TC_I_NT = 16, UCDIR_TC_I_GN = 17, UCDIR_TC_I_NCLS = 18,
+  UCDIR_TC_I_ACT = 19, UCDIR_TC_I_MODE = 20, UCDIR_TC_I_DST_F32 = 21, UCDIR_TC_I_DST_C = 22,
+  UCDIR_TC_I_DST_COFF = 23, UCDIR_TC_I_DST_UP = 24, UCDIR_TC_I_DST_PY = 25, UCDIR_TC_I_DST_PX = 26,
+  UCDIR_TC_I_RES_C = 27, UCDIR_TC_I_ATTW_STRIDE = 28
+};
+enum ucdir_tc_flt { UCDIR_TC_F_EPS = 0 };
+
+/* ---- UCDIR_OP_GN_APPLY_BF16: DST = [Swish](GroupNorm(1,C)(SRC)) on bf16 NHWC [B][HW][C]; f[0] = eps ------------ */
+enum ucdir_gna_ptr { UCDIR_GNA_P_SRC = 0, UCDIR_GNA_P_DST = 1, UCDIR_GNA_P_GAMMA = 2, UCDIR_GNA_P_BETA = 3, UCDIR_GNA_P_STATS = 4 };
+enum ucdir_gna_int { UCDIR_GNA_I_B = 0, UCDIR_GNA_I_HW = 1, UCDIR_GNA_I_C = 2, UCDIR_GNA_I_SWISH = 3 };
+
+/* ---- UCDIR_OP_CAST: p[1][k] = cast(p[0][k]) for k < i[0] + (i[1] << 31); i[2] = 0: fp32 -> bf16, 1: bf16 -> fp32 -- */
 
 /* ---- UCDIR_OP_MEMSET: cudaMemsetAsync(p[0], 0, i[0] + (i[1] << 31)) ------------------------------------ */
 

@@ -158,17 +158,21 @@ def emu_sgemm(op, mem):
     sa, sb, sc = _i(op, "UCDIR_SGEMM_I_SA"), _i(op, "UCDIR_SGEMM_I_SB"), _i(op, "UCDIR_SGEMM_I_SC")
     tb = _i(op, "UCDIR_SGEMM_I_TRANSB")
     alpha = _f(op, "UCDIR_SGEMM_F_ALPHA")
+    ta = torch.bfloat16 if _i(op, "UCDIR_SGEMM_I_A_BF16") else torch.float32
+    tbt = torch.bfloat16 if _i(op, "UCDIR_SGEMM_I_B_BF16") else torch.float32
+    tc = torch.bfloat16 if _i(op, "UCDIR_SGEMM_I_C_BF16") else torch.float32
+    ea, eb, ec = (2 if t == torch.bfloat16 else 4 for t in (ta, tbt, tc))
     for b in range(batch):
-        A = mem.view(_p(op, "UCDIR_SGEMM_P_A") + b * sa * 4, ((M - 1) * lda + Kd,))
-        A = torch.as_strided(A, (M, Kd), (lda, 1))
+        A = mem.view(_p(op, "UCDIR_SGEMM_P_A") + b * sa * ea, ((M - 1) * lda + Kd,), ta)
+        A = torch.as_strided(A, (M, Kd), (lda, 1)).float()
         if tb:
-            Bm = mem.view(_p(op, "UCDIR_SGEMM_P_B") + b * sb * 4, ((N - 1) * ldb + Kd,))
-            Bm = torch.as_strided(Bm, (N, Kd), (ldb, 1)).t()
+            Bm = mem.view(_p(op, "UCDIR_SGEMM_P_B") + b * sb * eb, ((N - 1) * ldb + Kd,), tbt)
+            Bm = torch.as_strided(Bm, (N, Kd), (ldb, 1)).t().float()
         else:
-            Bm = mem.view(_p(op, "UCDIR_SGEMM_P_B") + b * sb * 4, ((Kd - 1) * ldb + N,))
-            Bm = torch.as_strided(Bm, (Kd, N), (ldb, 1))
-        Cm = mem.view(_p(op, "UCDIR_SGEMM_P_C") + b * sc * 4, ((M - 1) * ldc + N,))
-        torch.as_strided(Cm, (M, N), (ldc, 1)).copy_(alpha * (A @ Bm))
+            Bm = mem.view(_p(op, "UCDIR_SGEMM_P_B") + b * sb * eb, ((Kd - 1) * ldb + N,), tbt)
+            Bm = torch.as_strided(Bm, (Kd, N), (ldb, 1)).float()
+        Cm = mem.view(_p(op, "UCDIR_SGEMM_P_C") + b * sc * ec, ((M - 1) * ldc + N,), tc)
+        torch.as_strided(Cm, (M, N), (ldc, 1)).copy_((alpha * (A @ Bm)).to(tc))
 
 
 def emu_softmax(op, mem):
@@ -224,20 +228,20 @@ def emu_gather(op, mem):
     BT, TH, TW = _i(op, "UCDIR_GATHER_I_BT"), _i(op, "UCDIR_GATHER_I_TH"), _i(op, "UCDIR_GATHER_I_TW")
     IH, IW, PD = _i(op, "UCDIR_GATHER_I_IMG_H"), _i(op, "UCDIR_GATHER_I_IMG_W"), _i(op, "UCDIR_GATHER_I_PD")
     CA, CB, CD = _i(op, "UCDIR_GATHER_I_CA"), _i(op, "UCDIR_GATHER_I_CB"), _i(op, "UCDIR_GATHER_I_CD")
-    assert not _i(op, "UCDIR_GATHER_I_OUT_BF16")
+    odt = torch.bfloat16 if _i(op, "UCDIR_GATHER_I_OUT_BF16") else torch.float32
     tab = mem.view(_p(op, "UCDIR_GATHER_P_TAB"), (BT, 3), torch.int32).numpy()
     nimg = int(tab[:, 0].max()) + 1
     A = mem.view(_p(op, "UCDIR_GATHER_P_SRC_A"), (nimg, CA, IH, IW))
     Bs = mem.view(_p(op, "UCDIR_GATHER_P_SRC_B"), (nimg, CB, IH, IW)) if CB else None
-    dst = mem.view(_p(op, "UCDIR_GATHER_P_DST"), (BT, TH, TW, CD))
+    dst = mem.view(_p(op, "UCDIR_GATHER_P_DST"), (BT, TH, TW, CD), odt)
     for t in range(BT):
         img, y0, x0 = (int(v) for v in tab[t])
         sy = torch.from_numpy(_reflect(np.arange(TH) + y0 - PD, IH))
         sx = torch.from_numpy(_reflect(np.arange(TW) + x0 - PD, IW))
         dst[t].zero_()
-        dst[t, :, :, :CA] = A[img][:, sy][:, :, sx].permute(1, 2, 0)
+        dst[t, :, :, :CA] = A[img][:, sy][:, :, sx].permute(1, 2, 0).to(odt)
         if CB:
-            dst[t, :, :, CA:CA + CB] = Bs[img][:, sy][:, :, sx].permute(1, 2, 0)
+            dst[t, :, :, CA:CA + CB] = Bs[img][:, sy][:, :, sx].permute(1, 2, 0).to(odt)
 
 
 def emu_scatter(op, mem):
@@ -286,11 +290,126 @@ def emu_memset(op, mem):
     mem.view(int(op.p[0]), (n,), torch.uint8).zero_()
 
 
+def emu_tc_conv(op, mem):
+    """UCDIR_OP_TC_CONV restated: bf16 operands, fp32 accumulation, epilogue exactly as documented in the header."""
+    g = lambda n: _i(op, "UCDIR_TC_I_" + n)
+    B, H, W, sH, sW = g("B"), g("H"), g("W"), g("SRC_H"), g("SRC_W")
+    C0, C1, Ntot = g("C0"), g("C1"), g("NTOT")
+    ncv = g("NCOL_VALID") or Ntot
+    nty, ntx, oy0, ox0, stride, groups, KC, NT = g("NTY"), g("NTX"), g("OY0"), g("OX0"), g("STRIDE"), g("GROUPS"), g("KC"), g("NT")
+    gn, ncls, act, mode, dst_f32 = g("GN"), g("NCLS"), g("ACT"), g("MODE"), g("DST_F32")
+    dstC, dstCoff, dstUp, dpy, dpx, resC, aws = g("DST_C"), g("DST_COFF"), g("DST_UP"), g("DST_PY"), g("DST_PX"), g("RES_C"), g("ATTW_STRIDE")
+    eps = _f(op, "UCDIR_TC_F_EPS")
+    bf = torch.bfloat16
+    Cin = C0 + C1
+    x = mem.view(_p(op, "UCDIR_TC_P_SRC0"), (B, sH, sW, C0), bf).float()
+    if C1:
+        x = torch.cat([x, mem.view(_p(op, "UCDIR_TC_P_SRC1"), (B, sH, sW, C1), bf).float()], dim=-1)
+    if groups > 1:
+        Cg, Ng = Cin // groups, Ntot // groups
+        cg_eff = max(Cg, KC)
+    else:
+        Cg, Ng, cg_eff = Cin, Ntot, Cin
+    ktap = cg_eff
+    Ktot = nty * ntx * ktap
+    wp = mem.view(_p(op, "UCDIR_TC_P_W"), (Ntot, nty * ntx, ktap), bf).float()
+    acc = torch.zeros(B, H, W, Ntot)
+    ys = torch.arange(H) * stride
+    xs = torch.arange(W) * stride
+    for ty in range(nty):
+        for tx in range(ntx):
+            sy, sx = ys + ty + oy0, xs + tx + ox0
+            vy, vx = (sy >= 0) & (sy < sH), (sx >= 0) & (sx < sW)
+            patch = x[:, sy.clamp(0, sH - 1)][:, :, sx.clamp(0, sW - 1)]
+            patch = patch * (vy.view(1, -1, 1, 1) & vx.view(1, 1, -1, 1))
+            for gi in range(groups):
+                cb = (gi * Cg) // cg_eff * cg_eff if groups > 1 else 0
+                rows = slice(gi * Ng, (gi + 1) * Ng)
+                acc[..., rows] += patch[..., cb:cb + cg_eff] @ wp[rows, ty * ntx + tx].t()
+    tb = mem.view(_p(op, "UCDIR_TC_P_TB"), (ncls if gn else 1, Ntot))
+    if gn:
+        s0 = mem.view(_p(op, "UCDIR_TC_P_STATS0"), (B, 2), torch.float64).clone()
+        if C1:
+            s0 = s0 + mem.view(_p(op, "UCDIR_TC_P_STATS1"), (B, 2), torch.float64)
+        cnt = float(Cin * sH * sW)
+        mean = s0[:, 0] / cnt
+        var = (s0[:, 1] / cnt - mean * mean).clamp_min(0)
+        rstd = (1.0 / torch.sqrt(var + eps)).float().view(B, 1, 1, 1)
+        mr = mean.float().view(B, 1, 1, 1) * rstd
+        tg = mem.view(_p(op, "UCDIR_TC_P_TG"), (ncls, Ntot))
+        if ncls == 9:
+            cy = torch.ones(H, dtype=torch.long); cy[0] = 0; cy[-1] = 2
+            cx = torch.ones(W, dtype=torch.long); cx[0] = 0; cx[-1] = 2
+            cls = cy.view(-1, 1) * 3 + cx.view(1, -1)
+        else:
+            cls = torch.zeros(H, W, dtype=torch.long)
+        v = acc * rstd - mr * tg[cls].unsqueeze(0) + tb[cls].unsqueeze(0)
+    else:
+        v = acc + tb[0].view(1, 1, 1, -1)
+    if mode == 1:
+        att = mem.view(_p(op, "UCDIR_TC_P_ATT"), (B, H, W, 8))
+        base = _p(op, "UCDIR_TC_P_ATTW")
+        aw = torch.stack([mem.view(base + b * aws * 4, (8,)) for b in range(B)])
+        a = att * aw.view(B, 1, 1, 8)
+        c = Ntot // 8
+        h = (v.reshape(B, H, W, c, 8) * a.unsqueeze(3)).sum(-1)
+        res = mem.view(_p(op, "UCDIR_TC_P_RES"), (B, H, W, resC), bf)[..., :c].float()
+        out = swish(h) + res
+        nout = c
+    else:
+        if act == 1:
+            v = swish(v)
+        rp = _p(op, "UCDIR_TC_P_RES")
+        if rp:
+            v = v + mem.view(rp, (B, H, W, resC), bf)[..., :Ntot].float()
+        out = v[..., :ncv]
+        nout = ncv
+    odt = torch.float32 if dst_f32 else bf
+    out = out.to(odt)
+    if dstUp:
+        dst = mem.view(_p(op, "UCDIR_TC_P_DST"), (B, 2 * H, 2 * W, dstC), odt)
+        dst[:, dpy::2, dpx::2, dstCoff:dstCoff + nout] = out
+    else:
+        dst = mem.view(_p(op, "UCDIR_TC_P_DST"), (B, H, W, dstC), odt)
+        dst[..., dstCoff:dstCoff + nout] = out
+    sp = _p(op, "UCDIR_TC_P_DST_STATS")
+    if sp:
+        st = mem.view(sp, (B, 2), torch.float64)
+        vd = out.double().reshape(B, -1)
+        st[:, 0] += vd.sum(1)
+        st[:, 1] += (vd * vd).sum(1)
+
+
+def emu_gn_apply(op, mem):
+    B, HW, Cc, sw = _i(op, "UCDIR_GNA_I_B"), _i(op, "UCDIR_GNA_I_HW"), _i(op, "UCDIR_GNA_I_C"), _i(op, "UCDIR_GNA_I_SWISH")
+    bf = torch.bfloat16
+    x = mem.view(_p(op, "UCDIR_GNA_P_SRC"), (B, HW, Cc), bf).float()
+    st = mem.view(_p(op, "UCDIR_GNA_P_STATS"), (B, 2), torch.float64)
+    cnt = float(HW * Cc)
+    mean = st[:, 0] / cnt
+    var = (st[:, 1] / cnt - mean * mean).clamp_min(0)
+    rstd = (1.0 / torch.sqrt(var + float(op.f[0]))).float().view(B, 1, 1)
+    gamma = mem.view(_p(op, "UCDIR_GNA_P_GAMMA"), (Cc,)); beta = mem.view(_p(op, "UCDIR_GNA_P_BETA"), (Cc,))
+    y = (x - mean.float().view(B, 1, 1)) * rstd * gamma + beta
+    if sw:
+        y = swish(y)
+    mem.view(_p(op, "UCDIR_GNA_P_DST"), (B, HW, Cc), bf).copy_(y.to(bf))
+
+
+def emu_cast(op, mem):
+    n = int(op.i[0]) + (int(op.i[1]) << 31)
+    if int(op.i[2]) == 0:
+        mem.view(int(op.p[1]), (n,), torch.bfloat16).copy_(mem.view(int(op.p[0]), (n,)).to(torch.bfloat16))
+    else:
+        mem.view(int(op.p[1]), (n,)).copy_(mem.view(int(op.p[0]), (n,), torch.bfloat16).float())
+
+
 DISPATCH = {
     K["UCDIR_OP_CONV_F32"]: emu_conv, K["UCDIR_OP_SGEMM_F32"]: emu_sgemm, K["UCDIR_OP_SOFTMAX_F32"]: emu_softmax,
     K["UCDIR_OP_GUIDANCE"]: emu_guidance, K["UCDIR_OP_TIME_EMBED"]: emu_time_embed,
     K["UCDIR_OP_GATHER_TILES"]: emu_gather, K["UCDIR_OP_SCATTER"]: emu_scatter, K["UCDIR_OP_MAXPOOL2"]: emu_maxpool,
-    K["UCDIR_OP_MEMSET"]: emu_memset,
+    K["UCDIR_OP_MEMSET"]: emu_memset, K["UCDIR_OP_TC_CONV"]: emu_tc_conv, K["UCDIR_OP_GN_APPLY_BF16"]: emu_gn_apply,
+    K["UCDIR_OP_CAST"]: emu_cast,
 }
 
 LAUNCHED = []

@@ -99,3 +99,25 @@ def test_super_resolution_e2e(emulated, golden, sid_weights):
     # launches per step are what bench.py reports as gpu_launches
     sess = next(iter(net.denoise_fn.engine()._sessions.values()))
     assert sess.launches_per_step() > 100
+
+
+def test_bf16_graph_matches_reference_within_bf16_tolerance(emulated, golden, sid_weights):
+    """tcgen05-path graph (GroupNorm folded into weights + border-class tables, grouped K chunks with zero
+    filled foreign channels, 4-phase upsample convs, bf16 storage) executed by the CPU interpreter."""
+    net, _ = sid_weights
+    unet = net.denoise_fn
+    eng = unet.engine()
+    eng.set_precision("bf16")
+    try:
+        g = golden("unet")
+        eps = unet(T(g["x6"]), T(g["level"]), T(g["guide"]))
+        sess = next(iter(eng._sessions.values()))
+        _lib.check_ops(sess.step_ops.array(), len(sess.step_ops))          # C-side argument validation of every TC op
+        err = (eps - T(g["eps"])).abs()
+        ref = T(g["eps"]).abs().max().item()
+        assert err.max().item() < 0.03 * ref and err.mean().item() < 0.004 * ref, (err.max().item(), err.mean().item(), ref)
+        eps2 = unet.naiveforward(T(g["xs"]), T(g["lv2"]), T(g["gs"]))
+        err2 = (eps2 - T(g["eps2"])).abs()
+        assert err2.max().item() < 0.03 * ref and err2.mean().item() < 0.004 * ref, (err2.max().item(), err2.mean().item())
+    finally:
+        eng.set_precision("fp32")

@@ -1,0 +1,214 @@
+"""Per-op GPU tests of the tcgen05 / TMA kernels: the same `ucdir_op_t` record is executed by the CUDA library
+on device copies and by the CPU interpreter (tests/op_emulator.py) on host copies of identical bf16 inputs.
+Differences are then only accumulation order (fp32) and one bf16 rounding of the result."""
+import numpy as np
+import pytest
+import torch
+
+from tests import op_emulator
+from ucdir_b200 import _lib, engine as E
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+class Case:
+    """Named host tensors + a function that builds the op list from Act/pointer views on a given device."""
+
+    def __init__(self):
+        self.t = {}
+
+    def add(self, name, tensor):
+        self.t[name] = tensor.contiguous()
+        return self
+
+    def on(self, dev):
+        return {k: v.to(dev).contiguous() for k, v in self.t.items()}
+
+
+def run_both(case, build):
+    host = case.on("cpu")
+    ol = build(host)
+    op_emulator.run_ops(ol.array(), len(ol))
+    devt = case.on("cuda")
+    ol2 = build(devt)
+    _lib.run_ops(ol2.array(), len(ol2), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return host, {k: v.cpu() for k, v in devt.items()}
+
+
+def assert_close(got, want, what, rtol=2e-2, atol=2e-2):
+    got, want = got.float(), want.float()
+    err = (got - want).abs()
+    scale = want.abs().max().item() + 1e-6
+    bad = (err > atol * scale + rtol * want.abs()).float().mean().item()
+    assert bad == 0.0, f"{what}: max err {err.max().item():.4e} (scale {scale:.3e}), {bad:.3%} elements out of tolerance"
+
+
+def act(t, C, H, W, stats=None):
+    return E.Act(t, C, H, W, stats.data_ptr() if stats is not None else 0, True)
+
+
+def rnd(g, *shape, scale=1.0):
+    return torch.randn(*shape, generator=g) * scale
+
+
+def stats_of(x_bf16):
+    B = x_bf16.shape[0]
+    v = x_bf16.double().reshape(B, -1)
+    return torch.stack([v.sum(1), (v * v).sum(1)], dim=1).contiguous()
+
+
+def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1):
+    g = torch.Generator().manual_seed(seed)
+    sH, sW = H * stride, W * stride
+    c = Case()
+    c.add("x0", (rnd(g, B, sH, sW, C0) + 0.3).to(BF))
+    if C1:
+        c.add("x1", (rnd(g, B, sH, sW, C1) * 0.7 - 0.2).to(BF))
+    Cin = C0 + C1
+    w = rnd(g, Cout, Cin, ks, ks, scale=1.0 / np.sqrt(Cin * ks * ks))
+    bias = rnd(g, Cout, scale=0.1)
+    gamma = 1 + 0.3 * rnd(g, Cin) if gn else None
+    beta = 0.2 * rnd(g, Cin) if gn else None
+    nt = E._tc_nt(Cout)
+    wp, tb, tg = E.pack_tc_dense(w, bias, nt, gamma, beta)
+    c.add("w", wp).add("tb", tb)
+    if tg is not None:
+        c.add("tg", tg)
+    if gn:
+        c.add("s0", stats_of(c.t["x0"]))
+        if C1:
+            c.add("s1", stats_of(c.t["x1"]))
+    if res:
+        c.add("res", rnd(g, B, H, W, Cout).to(BF))
+    c.add("dst", torch.zeros(B, H, W, Cout, dtype=BF)).add("dstats", torch.zeros(B, 2, dtype=torch.float64))
+
+    def build(t):
+        ol = E.OpList()
+        E._tc_op(ol, src0=act(t["x0"], C0, sH, sW, t.get("s0")), src1=act(t["x1"], C1, sH, sW, t.get("s1")) if C1 else None,
+                 w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), tg=t["tg"].data_ptr() if "tg" in t else 0, gn=1 if gn else 0,
+                 ncls=9 if (gn and ks == 3) else 1, nty=ks, ntx=ks, oy0=-(ks // 2), ox0=-(ks // 2), stride=stride, act=act_,
+                 res=act(t["res"], Cout, H, W) if res else None, dst=act(t["dst"], Cout, H, W, t["dstats"]), ntot=Cout, B=B, nt=nt)
+        return ol
+    return c, build
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(seed=1, B=2, H=16, W=16, C0=64, C1=0, Cout=64, ks=1, gn=False, act_=0, res=False),
+    dict(seed=2, B=3, H=24, W=20, C0=128, C1=0, Cout=128, ks=3, gn=True, act_=1, res=False),
+    dict(seed=3, B=2, H=16, W=16, C0=128, C1=64, Cout=64, ks=3, gn=True, act_=1, res=False),
+    dict(seed=4, B=1, H=32, W=32, C0=256, C1=0, Cout=256, ks=3, gn=False, act_=0, res=True),
+    dict(seed=5, B=5, H=8, W=8, C0=512, C1=512, Cout=512, ks=3, gn=True, act_=1, res=False),
+    dict(seed=6, B=2, H=16, W=16, C0=64, C1=0, Cout=64, ks=3, gn=False, act_=0, res=False, stride=2),
+    dict(seed=7, B=2, H=18, W=18, C0=512, C1=0, Cout=1536, ks=1, gn=True, act_=0, res=False),
+    dict(seed=8, B=1, H=128, W=128, C0=64, C1=0, Cout=64, ks=3, gn=True, act_=1, res=False),
+], ids=lambda c: "C%d+%d_%d_k%d_s%d_%dx%d" % (c["C0"], c["C1"], c["Cout"], c["ks"], c.get("stride", 1), c["H"], c["W"]))
+def test_tc_dense(cfg):
+    c, build = dense_case(**cfg)
+    host, dev = run_both(c, build)
+    assert_close(dev["dst"], host["dst"], "dst")
+    assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("C,B,H,W", [(64, 2, 16, 16), (128, 1, 24, 16), (256, 3, 8, 8), (512, 3, 8, 8), (64, 1, 128, 128)])
+def test_tc_grouped_mix(C, B, H, W):
+    g = torch.Generator().manual_seed(C + H)
+    c = Case()
+    c.add("h1", (torch.nn.functional.silu(rnd(g, B, H, W, C))).to(BF))
+    w = rnd(g, 8 * C, C // 8, 3, 3, scale=1.0 / np.sqrt(C // 8 * 9))
+    bias = rnd(g, 8 * C, scale=0.1)
+    gamma, beta = 1 + 0.3 * rnd(g, C), 0.2 * rnd(g, C)
+    kc = 64 if C >= 512 else (32 if C == 256 else 16)
+    wp, tb, tg = E.pack_tc_grouped(w, bias, 8, kc, gamma, beta)
+    c.add("w", wp).add("tb", tb).add("tg", tg).add("s0", stats_of(c.t["h1"]))
+    c.add("att", rnd(g, B, H, W, 8)).add("attw", rnd(g, B, 8)).add("res", rnd(g, B, H, W, C).to(BF))
+    c.add("dst", torch.zeros(B, H, W, C, dtype=BF)).add("dstats", torch.zeros(B, 2, dtype=torch.float64))
+
+    def build(t):
+        ol = E.OpList()
+        E._tc_op(ol, src0=act(t["h1"], C, H, W, t["s0"]), w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), tg=t["tg"].data_ptr(),
+                 gn=1, ncls=9, groups=8, kc=kc, nt=min(C, 256), mode=1, att=t["att"].data_ptr(), attw=t["attw"].data_ptr(),
+                 attw_stride=8, res=act(t["res"], C, H, W), dst=act(t["dst"], C, H, W, t["dstats"]), ntot=8 * C, B=B)
+        return ol
+    host, dev = run_both(c, build)
+    assert_close(dev["dst"], host["dst"], "mix dst")
+    assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
+
+
+def test_tc_upsample_phases_equal_upsample_then_conv():
+    """Four 2x2-tap phase convolutions == nearest-2x + conv3x3 (model/ucdir.py:53-60), checked against torch."""
+    g = torch.Generator().manual_seed(9)
+    B, H, W, C = 2, 8, 12, 128
+    x = rnd(g, B, H, W, C).to(BF)
+    w = rnd(g, C, C, 3, 3, scale=1.0 / np.sqrt(9 * C))
+    bias = rnd(g, C, scale=0.1)
+    c = Case().add("x", x).add("dst", torch.zeros(B, 2 * H, 2 * W, C, dtype=BF)).add("dstats", torch.zeros(B, 2, dtype=torch.float64))
+    for py in range(2):
+        for px in range(2):
+            wp, tb = E.pack_tc_up_phase(w, bias, py, px, 128)
+            c.add("w%d%d" % (py, px), wp).add("tb%d%d" % (py, px), tb)
+
+    def build(t):
+        ol = E.OpList()
+        for py in range(2):
+            for px in range(2):
+                E._tc_op(ol, src0=act(t["x"], C, H, W), w=t["w%d%d" % (py, px)].data_ptr(), tb=t["tb%d%d" % (py, px)].data_ptr(),
+                         nty=2, ntx=2, oy0=py - 1, ox0=px - 1, dst=act(t["dst"], C, 2 * H, 2 * W, t["dstats"]), ntot=C, B=B,
+                         nt=128, dst_up=1, dst_py=py, dst_px=px)
+        return ol
+    host, dev = run_both(c, build)
+    assert_close(dev["dst"], host["dst"], "phase dst vs interpreter")
+    xn = torch.nn.functional.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    want = torch.nn.functional.conv2d(xn, w, bias, padding=1).permute(0, 2, 3, 1)
+    assert_close(dev["dst"], want, "phase dst vs upsample+conv", rtol=3e-2, atol=3e-2)
+
+
+def test_tc_final_conv_fp32_out_and_gn_apply():
+    g = torch.Generator().manual_seed(10)
+    B, H, W, C = 2, 16, 16, 64
+    x = (rnd(g, B, H, W, C) * 1.3 + 0.4).to(BF)
+    w = rnd(g, 3, C, 3, 3, scale=1.0 / np.sqrt(9 * C))
+    bias = rnd(g, 3, scale=0.1)
+    wp, tb, _ = E.pack_tc_dense(w, bias, 16)
+    c = Case().add("x", x).add("s0", stats_of(x)).add("gamma", 1 + 0.3 * rnd(g, C)).add("beta", 0.2 * rnd(g, C))
+    c.add("xn", torch.zeros(B, H, W, C, dtype=BF)).add("w", wp).add("tb", tb).add("eps", torch.zeros(B, H, W, 4))
+
+    def build(t):
+        ol = E.OpList()
+        ol.add("UCDIR_OP_GN_APPLY_BF16", {"UCDIR_GNA_P_SRC": t["x"].data_ptr(), "UCDIR_GNA_P_DST": t["xn"].data_ptr(),
+                                          "UCDIR_GNA_P_GAMMA": t["gamma"].data_ptr(), "UCDIR_GNA_P_BETA": t["beta"].data_ptr(),
+                                          "UCDIR_GNA_P_STATS": t["s0"].data_ptr()},
+               {"UCDIR_GNA_I_B": B, "UCDIR_GNA_I_HW": H * W, "UCDIR_GNA_I_C": C, "UCDIR_GNA_I_SWISH": 1}, {0: 1e-5})
+        E._tc_op(ol, src0=act(t["xn"], C, H, W), w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), dst=act(t["eps"], 4, H, W), ntot=16,
+                 B=B, nt=16, dst_f32=1, ncol_valid=3)
+        return ol
+    host, dev = run_both(c, build)
+    assert_close(dev["xn"], host["xn"], "gn_apply")
+    assert_close(dev["eps"][..., :3], host["eps"][..., :3], "final conv eps")
+
+
+def test_sgemm_bf16_operands():
+    g = torch.Generator().manual_seed(12)
+    Bt, N, C = 3, 80, 64
+    qkv = rnd(g, Bt, N, 3 * C).to(BF)
+    c = Case().add("qkv", qkv).add("S", torch.zeros(Bt, N, N)).add("O", torch.zeros(Bt, N, C, dtype=BF))
+
+    def build(t):
+        ol = E.OpList()
+        q = t["qkv"].data_ptr()
+        ol.add("UCDIR_OP_SGEMM_F32", {"UCDIR_SGEMM_P_A": q, "UCDIR_SGEMM_P_B": q + C * 2, "UCDIR_SGEMM_P_C": t["S"].data_ptr()},
+               {"UCDIR_SGEMM_I_BATCH": Bt, "UCDIR_SGEMM_I_M": N, "UCDIR_SGEMM_I_N": N, "UCDIR_SGEMM_I_K": C, "UCDIR_SGEMM_I_LDA": 3 * C,
+                "UCDIR_SGEMM_I_LDB": 3 * C, "UCDIR_SGEMM_I_LDC": N, "UCDIR_SGEMM_I_SA": N * 3 * C, "UCDIR_SGEMM_I_SB": N * 3 * C,
+                "UCDIR_SGEMM_I_SC": N * N, "UCDIR_SGEMM_I_TRANSB": 1, "UCDIR_SGEMM_I_A_BF16": 1, "UCDIR_SGEMM_I_B_BF16": 1},
+               {"UCDIR_SGEMM_F_ALPHA": 0.125})
+        ol.add("UCDIR_OP_SOFTMAX_F32", {"UCDIR_SOFTMAX_P_X": t["S"].data_ptr()}, {"UCDIR_SOFTMAX_I_ROWS": Bt * N, "UCDIR_SOFTMAX_I_COLS": N})
+        ol.add("UCDIR_OP_SGEMM_F32", {"UCDIR_SGEMM_P_A": t["S"].data_ptr(), "UCDIR_SGEMM_P_B": q + 2 * C * 2, "UCDIR_SGEMM_P_C": t["O"].data_ptr()},
+               {"UCDIR_SGEMM_I_BATCH": Bt, "UCDIR_SGEMM_I_M": N, "UCDIR_SGEMM_I_N": C, "UCDIR_SGEMM_I_K": N, "UCDIR_SGEMM_I_LDA": N,
+                "UCDIR_SGEMM_I_LDB": 3 * C, "UCDIR_SGEMM_I_LDC": C, "UCDIR_SGEMM_I_SA": N * N, "UCDIR_SGEMM_I_SB": N * 3 * C,
+                "UCDIR_SGEMM_I_SC": N * C, "UCDIR_SGEMM_I_TRANSB": 0, "UCDIR_SGEMM_I_B_BF16": 1, "UCDIR_SGEMM_I_C_BF16": 1},
+               {"UCDIR_SGEMM_F_ALPHA": 1.0})
+        return ol
+    host, dev = run_both(c, build)
+    assert_close(dev["S"], host["S"], "softmax(QK^T)", rtol=1e-3, atol=1e-4)
+    assert_close(dev["O"], host["O"], "PV")

@@ -269,9 +269,14 @@ int launch_conv_f32(const ucdir_op_t& op, cudaStream_t st, bool dry) {
 // Batched SGEMM: C[b] = alpha * A[b] (MxK, lda) * B[b]   (TRANSB: B is NxK row-major; else KxN row-major)
 // 64x64 tile, BK=16, 256 threads, 4x4 per thread.  Used by the fp32 attention path.
 // ------------------------------------------------------------------------------------------------
-template <bool TRANSB>
-__global__ void __launch_bounds__(256) sgemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
-                                                        float* __restrict__ C, int M, int N, int K, int lda, int ldb,
+__device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+template <bool TRANSB, typename TA, typename TB, typename TC>
+__global__ void __launch_bounds__(256) sgemm_f32_kernel(const TA* __restrict__ A, const TB* __restrict__ Bm,
+                                                        TC* __restrict__ C, int M, int N, int K, int lda, int ldb,
                                                         int ldc, long long sa, long long sb, long long sc, float alpha) {
   constexpr int BM = 64, BN = 64, BK = 16;
   __shared__ float As[BK][BM + 1];
@@ -283,14 +288,13 @@ __global__ void __launch_bounds__(256) sgemm_f32_kernel(const float* __restrict_
   const int tx = tid % 16, ty = tid / 16;
   float acc[4][4] = {};
   for (int k0 = 0; k0 < K; k0 += BK) {
-    // A tile: 64 x 16, thread loads 4 elements (row = tid/4, cols (tid%4)*4..+3)
     {
       int r = tid >> 2, c = (tid & 3) * 4;
       int m = m0 + r;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int k = k0 + c + j;
-        As[c + j][r] = (m < M && k < K) ? A[(size_t)m * lda + k] : 0.f;
+        As[c + j][r] = (m < M && k < K) ? ldf(A + (size_t)m * lda + k) : 0.f;
       }
     }
     if (TRANSB) {
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(256) sgemm_f32_kernel(const float* __restrict_
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int k = k0 + c + j;
-        Bs[c + j][r] = (n < N && k < K) ? Bm[(size_t)n * ldb + k] : 0.f;
+        Bs[c + j][r] = (n < N && k < K) ? ldf(Bm + (size_t)n * ldb + k) : 0.f;
       }
     } else {
       int r = tid >> 4, c = (tid & 15) * 4;   // 16 rows x 64 cols
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(256) sgemm_f32_kernel(const float* __restrict_
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int n = n0 + c + j;
-        Bs[r][c + j] = (k < K && n < N) ? Bm[(size_t)k * ldb + n] : 0.f;
+        Bs[r][c + j] = (k < K && n < N) ? ldf(Bm + (size_t)k * ldb + n) : 0.f;
       }
     }
     __syncthreads();
@@ -330,25 +334,31 @@ __global__ void __launch_bounds__(256) sgemm_f32_kernel(const float* __restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
-      if (n < N) C[(size_t)m * ldc + n] = acc[i][j] * alpha;
+      if (n < N) stf(C + (size_t)m * ldc + n, acc[i][j] * alpha);
     }
   }
 }
 
 int launch_sgemm_f32(const ucdir_op_t& op, cudaStream_t st, bool dry) {
-  const float* A = (const float*)op.p[UCDIR_SGEMM_P_A]; const float* B = (const float*)op.p[UCDIR_SGEMM_P_B];
-  float* C = (float*)op.p[UCDIR_SGEMM_P_C];
+  const void* A = op.p[UCDIR_SGEMM_P_A]; const void* B = op.p[UCDIR_SGEMM_P_B];
+  void* C = op.p[UCDIR_SGEMM_P_C];
   int batch = op.i[UCDIR_SGEMM_I_BATCH], M = op.i[UCDIR_SGEMM_I_M], N = op.i[UCDIR_SGEMM_I_N], K = op.i[UCDIR_SGEMM_I_K];
   if (!A || !B || !C || batch <= 0 || M <= 0 || N <= 0 || K <= 0) { set_error("sgemm_f32: bad args"); return -1; }
   if (batch > 65535) { set_error("sgemm_f32: batch > 65535"); return -2; }
+  const int tb = op.i[UCDIR_SGEMM_I_TRANSB] ? 1 : 0;
+  const int ty = (op.i[UCDIR_SGEMM_I_A_BF16] ? 4 : 0) | (op.i[UCDIR_SGEMM_I_B_BF16] ? 2 : 0) | (op.i[UCDIR_SGEMM_I_C_BF16] ? 1 : 0);
+  // supported operand type combinations: fp32 x fp32 -> fp32 (parity path); bf16 x bf16 -> fp32 (Q K^T);
+  // fp32 x bf16 -> bf16 (P V)
+  if (!((ty == 0) || (ty == 6 && tb) || (ty == 3 && !tb))) { set_error("sgemm_f32: unsupported operand types %d transb %d", ty, tb); return -2; }
   if (dry) return 0;
   dim3 grid((N + 63) / 64, (M + 63) / 64, batch);
-  if (op.i[UCDIR_SGEMM_I_TRANSB])
-    sgemm_f32_kernel<true><<<grid, 256, 0, st>>>(A, B, C, M, N, K, op.i[UCDIR_SGEMM_I_LDA], op.i[UCDIR_SGEMM_I_LDB],
-        op.i[UCDIR_SGEMM_I_LDC], op.i[UCDIR_SGEMM_I_SA], op.i[UCDIR_SGEMM_I_SB], op.i[UCDIR_SGEMM_I_SC], op.f[UCDIR_SGEMM_F_ALPHA]);
-  else
-    sgemm_f32_kernel<false><<<grid, 256, 0, st>>>(A, B, C, M, N, K, op.i[UCDIR_SGEMM_I_LDA], op.i[UCDIR_SGEMM_I_LDB],
-        op.i[UCDIR_SGEMM_I_LDC], op.i[UCDIR_SGEMM_I_SA], op.i[UCDIR_SGEMM_I_SB], op.i[UCDIR_SGEMM_I_SC], op.f[UCDIR_SGEMM_F_ALPHA]);
+  const int lda = op.i[UCDIR_SGEMM_I_LDA], ldb = op.i[UCDIR_SGEMM_I_LDB], ldc = op.i[UCDIR_SGEMM_I_LDC];
+  const long long sa = op.i[UCDIR_SGEMM_I_SA], sb = op.i[UCDIR_SGEMM_I_SB], sc = op.i[UCDIR_SGEMM_I_SC];
+  const float alpha = op.f[UCDIR_SGEMM_F_ALPHA];
+  if (ty == 0 && tb) sgemm_f32_kernel<true, float, float, float><<<grid, 256, 0, st>>>((const float*)A, (const float*)B, (float*)C, M, N, K, lda, ldb, ldc, sa, sb, sc, alpha);
+  else if (ty == 0) sgemm_f32_kernel<false, float, float, float><<<grid, 256, 0, st>>>((const float*)A, (const float*)B, (float*)C, M, N, K, lda, ldb, ldc, sa, sb, sc, alpha);
+  else if (ty == 6) sgemm_f32_kernel<true, __nv_bfloat16, __nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, (float*)C, M, N, K, lda, ldb, ldc, sa, sb, sc, alpha);
+  else sgemm_f32_kernel<false, float, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)A, (const __nv_bfloat16*)B, (__nv_bfloat16*)C, M, N, K, lda, ldb, ldc, sa, sb, sc, alpha);
   ++g_launches;
   return 0;
 }

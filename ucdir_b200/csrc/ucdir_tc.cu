@@ -1,8 +1,557 @@
-// tcgen05 / TMA bf16 kernels (placeholder until the tensor-core path lands; ops report "unsupported").
+// bf16 tensor-core path (sm_100a): implicit-GEMM convolution on tcgen05 with TMA-staged NHWC tiles.
+//
+//   D[128 pixels x NT channels] (fp32, TMEM)  +=  A[128 pixels x KC] (bf16, smem)  *  B[NT x KC]^T (bf16, smem)
+//
+// * M tile = a bw x bh x bn box of output pixels (x, y, image); for filter tap (ty, tx) the A slab is ONE tiled
+//   TMA box load of the NHWC activation at (x0*s + tx + ox0, y0*s + ty + oy0) -- out-of-bounds pixels are
+//   zero-filled by the TMA unit, which is exactly the convolution's zero padding.  No im2col buffer.
+// * K loop = taps x channel chunks of KC (64/32/16 channels = 128/64/32-byte swizzled rows, K-major).
+//   torch.cat((x, skip)) is a second tensor map visited by the same loop; grouped convolution picks the
+//   chunk(s) of its group; nearest-2x upsampling is four 2x2-tap phase convolutions (weights pre-summed).
+// * GroupNorm(1,C) in front of a convolution is folded: gamma is multiplied into the packed weights and the
+//   epilogue applies v = rstd*acc - mean*rstd*TG[cls][n] + TB[cls][n], where TG/TB are per-layer tables over
+//   the 9 border classes (which taps fall outside the image) -- model/ucdir.py:109-112,161 never touch HBM.
+// * warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + tcgen05.mma issuer (one lane),
+//   warps 2..5 = epilogue (tcgen05.ld 32x32b, one TMEM lane quadrant each).
+// * epilogues: plain (bias/FiLM-free) + Swish + residual, or the integration-module mix (model/ucdir.py:135-140):
+//   8 adjacent accumulator columns weighted by the per-pixel guidance map x per-step attw, Swish, + residual.
+//   Both emit the {sum, sum^2} of what they store for the next GroupNorm.
+#include <cuda.h>
+#include <cstdio>
 #include "common.cuh"
+
 namespace ucdir {
-int launch_tc_conv(const ucdir_op_t&, cudaStream_t, bool) { set_error("TC_CONV not built yet"); return -2; }
-int launch_tc_attn(const ucdir_op_t&, cudaStream_t, bool) { set_error("TC_ATTN not built yet"); return -2; }
-int launch_gn_apply_bf16(const ucdir_op_t&, cudaStream_t, bool) { set_error("GN_APPLY_BF16 not built yet"); return -2; }
-int launch_cast(const ucdir_op_t&, cudaStream_t, bool) { set_error("CAST not built yet"); return -2; }
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) { printf("ucdir tc_conv: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major swizzled smem operand descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14),
+// LBO>>4 [16,30) (ignored for swizzled K-major, 1), SBO>>4 [32,46) = 8 rows, version 1 at [46,48), layout [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)((8 * row_bytes) >> 4) << 32) | (1ull << 46) |
+         (layout << 61);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct TcParams {
+  const double* stats0; const double* stats1;
+  const float* tb; const float* tg;
+  const __nv_bfloat16* res; const float* att; const float* attw;
+  void* dst; double* dst_stats;
+  int B, H, W, srcH, srcW;
+  int Ntot, ncol_valid;
+  int bw, bh, bn, tiles_x, tiles_y;
+  int nty, ntx, oy0, ox0, stride;
+  int nchunk, c0_chunks, groups, Ng, Cg, cg_eff;
+  int gn, ncls, act, mode, dst_f32;
+  int dstC, dstCoff, dstUp, dstPy, dstPx, resC, attwStride;
+  double gn_count; float eps;
+};
+
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+
+template <int KC, int NT>
+struct TcSmem {
+  static constexpr int A_BYTES = 128 * KC * 2;
+  static constexpr int B_BYTES = NT * KC * 2;
+  static constexpr int B_PAD = (B_BYTES + 1023) & ~1023;
+  static constexpr int STAGE = A_BYTES + B_PAD;
+  static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*align slack*/ + 128 /*barriers*/;
+};
+
+template <int KC, int NT>
+__global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0,
+                                                             const __grid_constant__ CUtensorMap mapA1,
+                                                             const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  using S = TcSmem<KC, NT>;
+  constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * S::STAGE);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* tmem_full = empty + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- tile coordinates ----
+  const int m = blockIdx.x;
+  const int tx_i = m % p.tiles_x, ty_i = (m / p.tiles_x) % p.tiles_y, tn_i = m / (p.tiles_x * p.tiles_y);
+  const int x0 = tx_i * p.bw, y0 = ty_i * p.bh, n0 = tn_i * p.bn;
+  const int ncol0 = blockIdx.y * NT;
+  const int g = p.groups > 1 ? ncol0 / p.Ng : 0;
+  const int nslab = p.nty * p.ntx * p.nchunk;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
+    if (p.c0_chunks < p.nchunk && p.groups == 1) prefetch_tmap(&mapA1);
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)(p.bw * p.bh * p.bn * KC * 2 + NT * KC * 2);
+      const int cgrp0 = p.groups > 1 ? (g * p.Cg) / p.cg_eff * p.cg_eff : 0;
+      for (int i = 0; i < nslab; ++i) {
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (i / TC_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int tap = i / p.nchunk, j = i - tap * p.nchunk;
+        const int ty = tap / p.ntx, tx = tap - ty * p.ntx;
+        uint8_t* sa = smem + s * S::STAGE;
+        uint8_t* sb = sa + S::A_BYTES;
+        mbar_expect_tx(&full[s], tx_bytes);
+        const int cx = x0 * p.stride + tx + p.ox0, cy = y0 * p.stride + ty + p.oy0;
+        if (p.groups > 1 || j < p.c0_chunks) tma_load_4d(&mapA0, &full[s], sa, cgrp0 + j * KC, cx, cy, n0);
+        else tma_load_4d(&mapA1, &full[s], sa, (j - p.c0_chunks) * KC, cx, cy, n0);
+        tma_load_2d(&mapB, &full[s], sb, i * KC, ncol0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int i = 0; i < nslab; ++i) {
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (i / TC_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::STAGE), sb = sa + S::A_BYTES;
+        const uint64_t ad = make_desc(sa, KC * 2), bd = make_desc(sb, KC * 2);
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k)
+          umma_bf16(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (i | k) != 0);
+        umma_commit(&empty[s]);            // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(tmem_full);              // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may read
+    const int r = q * 32 + lane;                     // accumulator row = pixel slot of the tile
+    const int box = p.bw * p.bh;
+    const int nn = r / box, rr = r - nn * box;
+    const int yy = rr / p.bw, xx = rr - yy * p.bw;
+    const int img = n0 + nn, y = y0 + yy, x = x0 + xx;
+    const bool valid = (r < box * p.bn) && img < p.B && y < p.H && x < p.W;
+    float rstd = 1.f, mr = 0.f;
+    int cls = 0;
+    if (p.gn && valid) {
+      GnScalars sc = gn_scalars(p.stats0, p.stats1, img, p.gn_count, p.eps);
+      rstd = sc.rstd; mr = sc.mean * sc.rstd;
+      if (p.ncls == 9) cls = (y == 0 ? 0 : (y == p.H - 1 ? 2 : 1)) * 3 + (x == 0 ? 0 : (x == p.W - 1 ? 2 : 1));
+    }
+    const float* tb = p.tb + (size_t)cls * p.Ntot + ncol0;
+    const float* tg = p.tg ? p.tg + (size_t)cls * p.Ntot + ncol0 : nullptr;
+    const size_t pix_in = ((size_t)(valid ? img : 0) * p.H + (valid ? y : 0)) * p.W + (valid ? x : 0);
+    const size_t pix_out = p.dstUp ? ((size_t)(valid ? img : 0) * 2 * p.H + 2 * (valid ? y : 0) + p.dstPy) * (2 * p.W) + 2 * (valid ? x : 0) + p.dstPx
+                                   : pix_in;
+    float aw[8];
+    if (p.mode == 1) {
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.att + pix_in * 8));
+      const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.att + pix_in * 8 + 4));
+      const float* w8 = p.attw + (size_t)(valid ? img : 0) * p.attwStride;
+      aw[0] = t0.x * __ldg(w8 + 0); aw[1] = t0.y * __ldg(w8 + 1); aw[2] = t0.z * __ldg(w8 + 2); aw[3] = t0.w * __ldg(w8 + 3);
+      aw[4] = t1.x * __ldg(w8 + 4); aw[5] = t1.y * __ldg(w8 + 5); aw[6] = t1.z * __ldg(w8 + 6); aw[7] = t1.w * __ldg(w8 + 7);
+    }
+    float s1 = 0.f, s2 = 0.f;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    constexpr int CH = NT < 32 ? 16 : 32;
+#pragma unroll 1
+    for (int c0 = 0; c0 < NT; c0 += CH) {
+      uint32_t rv[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      if (CH == 32) tmem_ld32(taddr, rv); else tmem_ld16(taddr, rv);
+      tmem_ld_wait();
+      if (!valid) continue;
+      float v[CH];
+#pragma unroll
+      for (int j = 0; j < CH; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(tb + c0 + j));
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tg) g4 = __ldg(reinterpret_cast<const float4*>(tg + c0 + j));
+        v[j + 0] = fmaf(__uint_as_float(rv[j + 0]), rstd, fmaf(-mr, g4.x, b4.x));
+        v[j + 1] = fmaf(__uint_as_float(rv[j + 1]), rstd, fmaf(-mr, g4.y, b4.y));
+        v[j + 2] = fmaf(__uint_as_float(rv[j + 2]), rstd, fmaf(-mr, g4.z, b4.z));
+        v[j + 3] = fmaf(__uint_as_float(rv[j + 3]), rstd, fmaf(-mr, g4.w, b4.w));
+      }
+      if (p.mode == 1) {
+        // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
+        constexpr int NO = CH / 8;
+        const int cbase = (ncol0 + c0) >> 3;
+        __align__(8) __nv_bfloat16 o[NO];
+        const __nv_bfloat16* rp = p.res + pix_in * p.resC + cbase;
+#pragma unroll
+        for (int c = 0; c < NO; ++c) {
+          float h = 0.f;
+#pragma unroll
+          for (int s = 0; s < 8; ++s) h = fmaf(v[c * 8 + s], aw[s], h);
+          const float t = swish_f(h) + __bfloat162float(rp[c]);
+          o[c] = __float2bfloat16(t);
+          const float tr = __bfloat162float(o[c]);
+          s1 += tr; s2 += tr * tr;
+        }
+        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix_out * p.dstC + p.dstCoff + cbase;
+        if (NO == 4) *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(o);
+        else *reinterpret_cast<uint32_t*>(d) = *reinterpret_cast<const uint32_t*>(o);
+      } else {
+        const int nb = ncol0 + c0;
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = swish_f(v[j]);
+        }
+        if (p.res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix_in * p.resC + nb);
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            const uint4 u = __ldg(rp + j / 8);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(h2[e]);
+              v[j + 2 * e] += f.x; v[j + 2 * e + 1] += f.y;
+            }
+          }
+        }
+        if (p.dst_f32) {
+          float* d = reinterpret_cast<float*>(p.dst) + pix_out * p.dstC + p.dstCoff + nb;
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (nb + j < p.ncol_valid) { d[j] = v[j]; s1 += v[j]; s2 += v[j] * v[j]; }
+        } else {
+          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix_out * p.dstC + p.dstCoff + nb;
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            __align__(16) __nv_bfloat162 o2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              o2[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+              const float2 f = __bfloat1622float2(o2[e]);
+              s1 += f.x + f.y; s2 += f.x * f.x + f.y * f.y;
+            }
+            *reinterpret_cast<uint4*>(d + j) = *reinterpret_cast<const uint4*>(o2);
+          }
+        }
+      }
+    }
+    if (p.dst_stats) {
+      if (p.bn == 1) {
+        const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
+        if (lane == 0 && n0 < p.B) { atomicAdd(p.dst_stats + 2 * n0, d1); atomicAdd(p.dst_stats + 2 * n0 + 1, d2); }
+      } else if (valid) {
+        atomicAdd(p.dst_stats + 2 * img, (double)s1); atomicAdd(p.dst_stats + 2 * img + 1, (double)s2);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swz(int kc) { return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B); }
+
+static int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int B, int kc, int bw, int bh, int bn, int stride) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("tc_conv: cuTensorMapEncodeTiled unavailable"); return -3; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("tc_conv: cuTensorMapEncodeTiled(activation C=%d W=%d H=%d B=%d box %dx%dx%dx%d stride %d) failed: %d",
+                                     C, W, H, B, kc, bw, bh, bn, stride, (int)r); return -3; }
+  return 0;
+}
+static int make_w_map(CUtensorMap* m, const void* base, int Ktot, int Ntot, int kc, int nt) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("tc_conv: cuTensorMapEncodeTiled unavailable"); return -3; }
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Ntot};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)nt};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("tc_conv: cuTensorMapEncodeTiled(weights K=%d N=%d box %dx%d) failed: %d", Ktot, Ntot, kc, nt, (int)r); return -3; }
+  return 0;
+}
+
+// choose the M-tile rectangle: bw*bh*bn <= 128 maximising the useful fraction of the 128 accumulator rows
+static void choose_tile(int W, int H, int B, int stride, int* bw, int* bh, int* bn) {
+  double best = -1; int bbw = 1, bbh = 1, bbn = 1;
+  const int lim = 256 / stride;                       // TMA box dimension limit
+  for (int w = 1; w <= W && w <= 128 && w <= lim; ++w) {
+    int hmax = 128 / w; if (hmax > H) hmax = H; if (hmax > lim) hmax = lim;
+    for (int h = 1; h <= hmax; ++h) {
+      int n = 128 / (w * h); if (n > B) n = B; if (n < 1) n = 1;
+      if (h < H) n = 1;                              // only stack images when a tile covers a whole image
+      const long tiles = (long)((W + w - 1) / w) * ((H + h - 1) / h) * ((B + n - 1) / n);
+      const double eff = (double)W * H * B / (tiles * 128.0);
+      if (eff > best + 1e-9 || (eff > best - 1e-9 && w > bbw)) { best = eff; bbw = w; bbh = h; bbn = n; }
+    }
+  }
+  *bw = bbw; *bh = bbh; *bn = bbn;
+}
+
+template <int KC, int NT>
+static int launch_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t st) {
+  using S = TcSmem<KC, NT>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(tc_conv_kernel<KC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+      set_error("tc_conv: cannot opt in to %d bytes of shared memory: %s", S::TOTAL, cudaGetErrorString(cudaGetLastError())); return -3; }
+    attr = true;
+  }
+  tc_conv_kernel<KC, NT><<<grid, TC_THREADS, S::TOTAL, st>>>(a0, a1, b, p);
+  return 0;
+}
+
+int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
+  TcParams p;
+  const void* src0 = op.p[UCDIR_TC_P_SRC0]; const void* src1 = op.p[UCDIR_TC_P_SRC1]; const void* w = op.p[UCDIR_TC_P_W];
+  p.stats0 = (const double*)op.p[UCDIR_TC_P_STATS0]; p.stats1 = (const double*)op.p[UCDIR_TC_P_STATS1];
+  p.tb = (const float*)op.p[UCDIR_TC_P_TB]; p.tg = (const float*)op.p[UCDIR_TC_P_TG];
+  p.res = (const __nv_bfloat16*)op.p[UCDIR_TC_P_RES]; p.att = (const float*)op.p[UCDIR_TC_P_ATT];
+  p.attw = (const float*)op.p[UCDIR_TC_P_ATTW]; p.dst = op.p[UCDIR_TC_P_DST]; p.dst_stats = (double*)op.p[UCDIR_TC_P_DST_STATS];
+  p.B = op.i[UCDIR_TC_I_B]; p.H = op.i[UCDIR_TC_I_H]; p.W = op.i[UCDIR_TC_I_W];
+  p.srcH = op.i[UCDIR_TC_I_SRC_H]; p.srcW = op.i[UCDIR_TC_I_SRC_W];
+  const int C0 = op.i[UCDIR_TC_I_C0], C1 = op.i[UCDIR_TC_I_C1];
+  p.Ntot = op.i[UCDIR_TC_I_NTOT]; p.ncol_valid = op.i[UCDIR_TC_I_NCOL_VALID] ? op.i[UCDIR_TC_I_NCOL_VALID] : p.Ntot;
+  p.nty = op.i[UCDIR_TC_I_NTY]; p.ntx = op.i[UCDIR_TC_I_NTX]; p.oy0 = op.i[UCDIR_TC_I_OY0]; p.ox0 = op.i[UCDIR_TC_I_OX0];
+  p.stride = op.i[UCDIR_TC_I_STRIDE]; p.groups = op.i[UCDIR_TC_I_GROUPS];
+  const int KC = op.i[UCDIR_TC_I_KC], NT = op.i[UCDIR_TC_I_NT];
+  p.gn = op.i[UCDIR_TC_I_GN]; p.ncls = op.i[UCDIR_TC_I_NCLS]; p.act = op.i[UCDIR_TC_I_ACT]; p.mode = op.i[UCDIR_TC_I_MODE];
+  p.dst_f32 = op.i[UCDIR_TC_I_DST_F32];
+  p.dstC = op.i[UCDIR_TC_I_DST_C]; p.dstCoff = op.i[UCDIR_TC_I_DST_COFF]; p.dstUp = op.i[UCDIR_TC_I_DST_UP];
+  p.dstPy = op.i[UCDIR_TC_I_DST_PY]; p.dstPx = op.i[UCDIR_TC_I_DST_PX]; p.resC = op.i[UCDIR_TC_I_RES_C];
+  p.attwStride = op.i[UCDIR_TC_I_ATTW_STRIDE];
+  p.eps = op.f[UCDIR_TC_F_EPS];
+  if (!src0 || !w || !p.dst || !p.tb) { set_error("tc_conv: null src0/w/dst/tb"); return -1; }
+  if (p.B <= 0 || p.H <= 0 || p.W <= 0 || C0 <= 0 || p.Ntot <= 0 || p.groups < 1) { set_error("tc_conv: bad dims"); return -1; }
+  if (p.stride != 1 && p.stride != 2) { set_error("tc_conv: stride must be 1 or 2"); return -2; }
+  if (p.nty < 1 || p.ntx < 1 || p.nty > 3 || p.ntx > 3) { set_error("tc_conv: tap grid must be 1..3 per axis"); return -2; }
+  if (KC != 64 && KC != 32 && KC != 16) { set_error("tc_conv: KC must be 64, 32 or 16"); return -2; }
+  const int Cin = C0 + C1;
+  if (p.groups > 1) {
+    if (C1 || Cin % p.groups || p.Ntot % p.groups) { set_error("tc_conv: bad grouped config"); return -2; }
+    p.Cg = Cin / p.groups; p.Ng = p.Ntot / p.groups;
+    p.cg_eff = p.Cg > KC ? p.Cg : KC;
+    if (p.cg_eff % KC || Cin % p.cg_eff || p.Ng % NT) { set_error("tc_conv: grouped conv needs KC | max(Cg,KC) | Cin and NT | Cout/groups"); return -2; }
+    p.nchunk = p.cg_eff / KC; p.c0_chunks = p.nchunk;
+  } else {
+    if (C0 % KC || C1 % KC) { set_error("tc_conv: C0=%d / C1=%d must be multiples of KC=%d", C0, C1, KC); return -2; }
+    if (C1 > 0 && !src1) { set_error("tc_conv: null src1"); return -1; }
+    p.Cg = Cin; p.Ng = p.Ntot; p.cg_eff = Cin; p.nchunk = Cin / KC; p.c0_chunks = C0 / KC;
+  }
+  if (p.Ntot % NT) { set_error("tc_conv: Ntot=%d not a multiple of NT=%d", p.Ntot, NT); return -2; }
+  if (p.gn) {
+    if (!p.tg || !p.stats0 || (C1 > 0 && !p.stats1)) { set_error("tc_conv: GroupNorm fold needs tg and stats"); return -1; }
+    if (p.ncls != 1 && p.ncls != 9) { set_error("tc_conv: ncls must be 1 or 9"); return -2; }
+    if (p.ncls == 9 && (p.H < 2 || p.W < 2 || p.stride != 1 || p.nty != 3 || p.ntx != 3)) { set_error("tc_conv: 9-class fold needs a 3x3 stride-1 conv on >=2x2 pixels"); return -2; }
+  } else { p.ncls = 1; }
+  if (p.mode == 1 && (!p.att || !p.attw || !p.res || NT % 32 || p.dst_f32 || p.dstUp)) { set_error("tc_conv: mix epilogue needs att/attw/res, NT %% 32 == 0, bf16 dst"); return -2; }
+  if (p.mode != 1 && !p.dst_f32 && (NT % 32 || (p.dstC % 8) || (p.dstCoff % 8))) { set_error("tc_conv: bf16 dst needs NT %% 32 == 0 and 16-byte aligned rows"); return -2; }
+  if (p.res && p.mode != 1 && (p.resC % 8)) { set_error("tc_conv: residual rows must be 16-byte aligned"); return -2; }
+  if (p.stats1 == nullptr && C1 > 0 && p.gn) { set_error("tc_conv: stats1 missing"); return -1; }
+  if (C1 == 0) p.stats1 = nullptr;
+  p.gn_count = (double)Cin * p.srcH * p.srcW;
+  choose_tile(p.W, p.H, p.B, p.stride, &p.bw, &p.bh, &p.bn);
+  p.tiles_x = (p.W + p.bw - 1) / p.bw; p.tiles_y = (p.H + p.bh - 1) / p.bh;
+  const int tiles_n = (p.B + p.bn - 1) / p.bn;
+  const long mt = (long)p.tiles_x * p.tiles_y * tiles_n;
+  if (mt > 0x7fffffffL || p.Ntot / NT > 65535) { set_error("tc_conv: grid too large"); return -2; }
+  if (dry) return 0;
+  CUtensorMap a0, a1, bm;
+  int rc = make_act_map(&a0, src0, C0, p.srcW, p.srcH, p.B, KC, p.bw, p.bh, p.bn, p.stride);
+  if (rc) return rc;
+  if (C1 > 0) { rc = make_act_map(&a1, src1, C1, p.srcW, p.srcH, p.B, KC, p.bw, p.bh, p.bn, p.stride); if (rc) return rc; }
+  else a1 = a0;
+  const int Ktot = p.nty * p.ntx * p.nchunk * KC;
+  rc = make_w_map(&bm, w, Ktot, p.Ntot, KC, NT);
+  if (rc) return rc;
+  dim3 grid((unsigned)mt, p.Ntot / NT, 1);
+#define INST(kc, nt) if (KC == kc && NT == nt) { rc = launch_inst<kc, nt>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
+  INST(64, 16) INST(64, 64) INST(64, 128) INST(64, 256)
+  INST(32, 256) INST(32, 128)
+  INST(16, 64) INST(16, 128)
+#undef INST
+  set_error("tc_conv: no kernel instance for KC=%d NT=%d", KC, NT);
+  return -2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bf16 elementwise: GroupNorm(1,C) apply (+Swish) for the one place the fold does not reach
+// (final_conv: GN -> Swish -> conv, model/ucdir.py:266-268), and fp32 <-> bf16 casts.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_apply_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const double* __restrict__ stats, int C, size_t per_sample,
+                                                            double count, float eps, int swish) {
+  const int b = blockIdx.y;
+  const GnScalars sc = gn_scalars(stats, nullptr, b, count, eps);
+  const size_t n8 = per_sample / 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 8;
+    const int c = (int)(e % C);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (size_t)b * per_sample + e));
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    __align__(16) __nv_bfloat162 o2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = __bfloat1622float2(h2[k]);
+      const float a0 = sc.rstd * __ldg(gamma + c + 2 * k), a1 = sc.rstd * __ldg(gamma + c + 2 * k + 1);
+      f.x = f.x * a0 + (__ldg(beta + c + 2 * k) - a0 * sc.mean);
+      f.y = f.y * a1 + (__ldg(beta + c + 2 * k + 1) - a1 * sc.mean);
+      if (swish) { f.x = swish_f(f.x); f.y = swish_f(f.y); }
+      o2[k] = __floats2bfloat162_rn(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)b * per_sample + e) = *reinterpret_cast<const uint4*>(o2);
+  }
+}
+
+int launch_gn_apply_bf16(const ucdir_op_t& op, cudaStream_t st, bool dry) {
+  const int B = op.i[UCDIR_GNA_I_B], HW = op.i[UCDIR_GNA_I_HW], C = op.i[UCDIR_GNA_I_C];
+  for (int k = 0; k <= UCDIR_GNA_P_STATS; ++k) if (!op.p[k]) { set_error("gn_apply: null pointer %d", k); return -1; }
+  if (B <= 0 || HW <= 0 || C <= 0 || C % 8) { set_error("gn_apply: bad dims"); return -1; }
+  if (dry) return 0;
+  const size_t per = (size_t)HW * C;
+  unsigned gx = (unsigned)((per / 8 + 255) / 256); if (gx > 2368) gx = 2368;       // 16 CTAs per SM x 148
+  gn_apply_bf16_kernel<<<dim3(gx, B), 256, 0, st>>>((const __nv_bfloat16*)op.p[UCDIR_GNA_P_SRC], (__nv_bfloat16*)op.p[UCDIR_GNA_P_DST],
+      (const float*)op.p[UCDIR_GNA_P_GAMMA], (const float*)op.p[UCDIR_GNA_P_BETA], (const double*)op.p[UCDIR_GNA_P_STATS], C, per,
+      (double)per, op.f[0], op.i[UCDIR_GNA_I_SWISH]);
+  ++g_launches;
+  return 0;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = __float2bfloat16(s[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = __bfloat162float(s[i]);
+}
+int launch_cast(const ucdir_op_t& op, cudaStream_t st, bool dry) {
+  const size_t n = (size_t)op.i[0] + ((size_t)op.i[1] << 31);
+  if (!op.p[0] || !op.p[1] || n == 0) { set_error("cast: bad args"); return -1; }
+  if (dry) return 0;
+  unsigned g = (unsigned)((n + 255) / 256); if (g > 4736) g = 4736;
+  if (op.i[2] == 0) cast_f32_bf16_kernel<<<g, 256, 0, st>>>((const float*)op.p[0], (__nv_bfloat16*)op.p[1], n);
+  else cast_bf16_f32_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)op.p[0], (float*)op.p[1], n);
+  ++g_launches;
+  return 0;
+}
+
+int launch_tc_attn(const ucdir_op_t&, cudaStream_t, bool) { set_error("TC_ATTN not built yet"); return -2; }
+
+}  // namespace ucdir

@@ -282,17 +282,147 @@ def _conv_op(ol: OpList, *, src0: Act, w: int, dst: Act, cout: int, B: int, src1
     ol.add("UCDIR_OP_CONV_F32", p, i, {"UCDIR_CONV_F_EPS": eps})
 
 
+# ======================================================================================
+# bf16 / tcgen05 path: weight packing (layouts documented in include/ucdir_b200.h, UCDIR_OP_TC_CONV)
+# ======================================================================================
+BF16 = torch.bfloat16
+_CLS_TAPS = [[(ty, tx) for ty in range(3) for tx in range(3)
+              if not (cy == 0 and ty == 0) and not (cy == 2 and ty == 2) and not (cx == 0 and tx == 0) and not (cx == 2 and tx == 2)]
+             for cy in range(3) for cx in range(3)]
+"""taps of a 3x3 pad-1 convolution that fall inside the image, per border class cls = cy*3 + cx
+(cy: 0 top row, 1 interior, 2 bottom row; same for cx)."""
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def pack_tc_dense(w: torch.Tensor, bias, nt: int, gamma=None, beta=None):
+    """OIHW fp32 conv weight -> (W bf16 [Ntot][K = (tap, c)], TB fp32 [ncls][Ntot], TG or None).
+    With gamma/beta the GroupNorm(1,C) in front of the conv is folded (see ucdir_tc.cu header)."""
+    co, ci, kh, kw = w.shape
+    w = w.float()
+    wg = w * gamma.float().view(1, ci, 1, 1) if gamma is not None else w
+    ntot = _round_up(co, nt)
+    wq = wg.to(BF16)
+    packed = torch.zeros(ntot, kh * kw * ci, dtype=BF16, device=w.device)
+    packed[:co] = wq.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
+    b = bias.float() if bias is not None else torch.zeros(co, device=w.device)
+    if gamma is None:
+        tb = torch.zeros(1, ntot, device=w.device); tb[0, :co] = b
+        return packed.contiguous(), tb.contiguous(), None
+    wq32 = wq.float()
+    if kh == 3:
+        ncls = 9
+        tg = torch.zeros(ncls, ntot, device=w.device); tb = torch.zeros(ncls, ntot, device=w.device)
+        wb = (w * beta.float().view(1, ci, 1, 1)).sum(1)           # [co, 3, 3]
+        wgs = wq32.sum(1)
+        for cls, taps in enumerate(_CLS_TAPS):
+            for (ty, tx) in taps:
+                tg[cls, :co] += wgs[:, ty, tx]
+                tb[cls, :co] += wb[:, ty, tx]
+            tb[cls, :co] += b
+    else:
+        tg = torch.zeros(1, ntot, device=w.device); tb = torch.zeros(1, ntot, device=w.device)
+        tg[0, :co] = wq32.sum((1, 2, 3))
+        tb[0, :co] = (w * beta.float().view(1, ci, 1, 1)).sum((1, 2, 3)) + b
+    return packed.contiguous(), tb.contiguous(), tg.contiguous()
+
+
+def pack_tc_grouped(w: torch.Tensor, bias, groups: int, kc: int, gamma, beta):
+    """Grouped 3x3 conv [G*Ng, Cg, 3, 3] (spdyconv, model/ucdir.py:116) with folded GroupNorm.  When Cg < KC
+    the K chunk spans KC/Cg neighbouring groups and the rows carry zeros for the foreign channels."""
+    co, cg, kh, kw = w.shape
+    cin = cg * groups
+    ng = co // groups
+    cg_eff = max(cg, kc)
+    w = w.float()
+    dev = w.device
+    packed = torch.zeros(co, kh * kw, cg_eff, dtype=BF16, device=dev)
+    tg = torch.zeros(9, co, device=dev); tb = torch.zeros(9, co, device=dev)
+    for g in range(groups):
+        cbase = (g * cg) // cg_eff * cg_eff
+        off = g * cg - cbase
+        rows = slice(g * ng, (g + 1) * ng)
+        wg = w[rows] * gamma.float()[g * cg:(g + 1) * cg].view(1, cg, 1, 1)
+        wq = wg.to(BF16)
+        packed[rows, :, off:off + cg] = wq.permute(0, 2, 3, 1).reshape(ng, kh * kw, cg)
+        wgs = wq.float().sum(1)
+        wb = (w[rows] * beta.float()[g * cg:(g + 1) * cg].view(1, cg, 1, 1)).sum(1)
+        for cls, taps in enumerate(_CLS_TAPS):
+            for (ty, tx) in taps:
+                tg[cls, rows] += wgs[:, ty, tx]
+                tb[cls, rows] += wb[:, ty, tx]
+    tb += bias.float().view(1, co)
+    return packed.reshape(co, kh * kw * cg_eff).contiguous(), tb.contiguous(), tg.contiguous()
+
+
+def pack_tc_up_phase(w: torch.Tensor, bias, py: int, px: int, nt: int):
+    """Nearest-2x upsample followed by a 3x3 conv (model/ucdir.py:53-60) == four 2x2-tap convolutions on the
+    source grid, one per output parity (py, px); row set of tap t: py=0 -> {0}, {1,2}; py=1 -> {0,1}, {2}."""
+    co, ci, _, _ = w.shape
+    w = w.float()
+    rs = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    wp = torch.zeros(co, 2, 2, ci, device=w.device)
+    for ty in range(2):
+        for tx in range(2):
+            acc = 0
+            for dy in rs[py][ty]:
+                for dx in rs[px][tx]:
+                    acc = acc + w[:, :, dy, dx]
+            wp[:, ty, tx, :] = acc
+    ntot = _round_up(co, nt)
+    packed = torch.zeros(ntot, 4 * ci, dtype=BF16, device=w.device)
+    packed[:co] = wp.reshape(co, 4 * ci).to(BF16)
+    tb = torch.zeros(1, ntot, device=w.device); tb[0, :co] = bias.float()
+    return packed.contiguous(), tb.contiguous()
+
+
+def _tc_nt(cout: int) -> int:
+    for nt in (256, 128, 64):
+        if cout % nt == 0:
+            return nt
+    raise ValueError("no NT tile for Cout=%d" % cout)
+
+
+def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: int, nt: int, kc: int = 64,
+           src1: Optional[Act] = None, tg: int = 0, gn: int = 0, ncls: int = 1, nty: int = 3, ntx: int = 3, oy0: int = -1,
+           ox0: int = -1, stride: int = 1, groups: int = 1, act: int = 0, mode: int = 0, res: Optional[Act] = None,
+           att: int = 0, attw: int = 0, attw_stride: int = 0, dst_f32: int = 0, ncol_valid: int = 0, dst_up: int = 0,
+           dst_py: int = 0, dst_px: int = 0, eps: float = 1e-5):
+    H, W = (dst.H // 2, dst.W // 2) if dst_up else (dst.H, dst.W)
+    p = {"UCDIR_TC_P_SRC0": src0.ptr, "UCDIR_TC_P_W": w, "UCDIR_TC_P_TB": tb, "UCDIR_TC_P_DST": dst.ptr}
+    if src1 is not None: p["UCDIR_TC_P_SRC1"] = src1.ptr
+    if tg: p["UCDIR_TC_P_TG"] = tg
+    if gn:
+        p["UCDIR_TC_P_STATS0"] = src0.stats
+        if src1 is not None: p["UCDIR_TC_P_STATS1"] = src1.stats
+    if res is not None: p["UCDIR_TC_P_RES"] = res.ptr
+    if att: p["UCDIR_TC_P_ATT"] = att
+    if attw: p["UCDIR_TC_P_ATTW"] = attw
+    if dst.stats: p["UCDIR_TC_P_DST_STATS"] = dst.stats
+    i = {"UCDIR_TC_I_B": B, "UCDIR_TC_I_H": H, "UCDIR_TC_I_W": W, "UCDIR_TC_I_SRC_H": src0.H, "UCDIR_TC_I_SRC_W": src0.W,
+         "UCDIR_TC_I_C0": src0.C, "UCDIR_TC_I_C1": src1.C if src1 is not None else 0, "UCDIR_TC_I_NTOT": ntot,
+         "UCDIR_TC_I_NCOL_VALID": ncol_valid, "UCDIR_TC_I_NTY": nty, "UCDIR_TC_I_NTX": ntx, "UCDIR_TC_I_OY0": oy0,
+         "UCDIR_TC_I_OX0": ox0, "UCDIR_TC_I_STRIDE": stride, "UCDIR_TC_I_GROUPS": groups, "UCDIR_TC_I_KC": kc,
+         "UCDIR_TC_I_NT": nt, "UCDIR_TC_I_GN": gn, "UCDIR_TC_I_NCLS": ncls, "UCDIR_TC_I_ACT": act, "UCDIR_TC_I_MODE": mode,
+         "UCDIR_TC_I_DST_F32": dst_f32, "UCDIR_TC_I_DST_C": dst.C, "UCDIR_TC_I_DST_COFF": 0, "UCDIR_TC_I_DST_UP": dst_up,
+         "UCDIR_TC_I_DST_PY": dst_py, "UCDIR_TC_I_DST_PX": dst_px, "UCDIR_TC_I_RES_C": res.C if res is not None else 0,
+         "UCDIR_TC_I_ATTW_STRIDE": attw_stride}
+    ol.add("UCDIR_OP_TC_CONV", p, i, {"UCDIR_TC_F_EPS": eps})
+
+
 class _Builder:
     """Shared helpers of the UNet / predictor graph builders."""
 
-    def __init__(self, pool: Pool, BT: int, stats: torch.Tensor):
-        self.pool, self.BT = pool, BT
+    def __init__(self, pool: Pool, BT: int, stats: torch.Tensor, elem: int = 4):
+        self.pool, self.BT, self.elem = pool, BT, elem
         self.stats = stats               # double[n_slots][BT][2]
         self.next_slot = 0
         self.ops = OpList()
 
     def new(self, C, H, W, with_stats=True, keep=False, cpad: Optional[int] = None) -> Act:
-        buf = self.pool.get(self.BT * H * W * (cpad or C) * 4)
+        buf = self.pool.get(self.BT * H * W * (cpad or C) * self.elem)
         st = 0
         if with_stats:
             if self.next_slot >= self.stats.shape[0]:
@@ -324,6 +454,9 @@ class UNetEngine:
         self.ws: Optional[WeightStore] = None
         self.blocks: List[Tuple[str, object]] = []
         self._sessions: Dict[tuple, "Session"] = {}
+        self.precision = os.environ.get("UCDIR_PRECISION", "fp32")    # "fp32" (parity path) | "bf16" (tcgen05 path)
+        if self.precision not in ("fp32", "bf16"):
+            raise ValueError("UCDIR_PRECISION must be fp32 or bf16")
 
     # ---- weights ------------------------------------------------------------------------
     def invalidate_weights(self):
@@ -332,6 +465,13 @@ class UNetEngine:
 
     def invalidate_schedule(self):
         pass                            # levels are per-step kernel arguments; nothing cached per schedule
+
+    def set_precision(self, precision: str):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be fp32 or bf16")
+        if precision != self.precision:
+            self.precision = precision
+            self.invalidate_weights()
 
     def device(self):
         return next(self.m.parameters()).device
@@ -387,6 +527,8 @@ class UNetEngine:
         ws.put("final.w", pack_conv_f32(fc[3].weight)); ws.put("final.b", fc[3].bias.float())
         self.inner = inner
         self.ws = ws
+        if self.precision == "bf16":
+            self._ensure_weights_bf16()
 
     # ---- graph --------------------------------------------------------------------------
     def n_blocks(self):
@@ -549,6 +691,175 @@ class UNetEngine:
         self.last_stat_slots = bld.next_slot
         return ol
 
+    # ---- bf16 / tcgen05 graph --------------------------------------------------------------
+    def _ensure_weights_bf16(self):
+        """Packed bf16 operands + fp32 epilogue tables for every TC op (once per load)."""
+        from .model import ucdir as U
+        ws, m = self.ws, self.m
+
+        def put3(name, triple):
+            w, tb, tg = triple
+            ws.put(name + ".tcw", w); ws.put(name + ".tb", tb)
+            if tg is not None:
+                ws.put(name + ".tg", tg)
+
+        for name, layer in self.blocks:
+            rb = layer.res_block
+            cout = rb.dim_out
+            put3(name + ".conv1", pack_tc_dense(rb.conv1.weight, rb.conv1.bias, _tc_nt(cout), rb.norm1.weight, rb.norm1.bias))
+            kc = 64 if cout >= 512 else (32 if cout == 256 else 16)
+            put3(name + ".spdy", pack_tc_grouped(rb.spdyconv.weight, rb.spdyconv.bias, rb.nset, kc, rb.norm2.weight, rb.norm2.bias))
+            if isinstance(rb.res_conv, torch.nn.Conv2d):
+                put3(name + ".res", pack_tc_dense(rb.res_conv.weight, rb.res_conv.bias, _tc_nt(cout)))
+            if layer.with_attn:
+                at = layer.attn
+                put3(name + ".attn.qkv", pack_tc_dense(at.qkv.weight, None, 256, at.norm.weight, at.norm.bias))
+                put3(name + ".attn.out", pack_tc_dense(at.out.weight, at.out.bias, _tc_nt(at.out.out_channels)))
+        for grp in ("downs", "ups"):
+            for k, layer in enumerate(getattr(m, grp)):
+                name = "%s.%d" % (grp, k)
+                if isinstance(layer, torch.nn.Conv2d):          # in-conv: 6 -> 16 zero-padded input channels (KC = 16)
+                    w = layer.weight
+                    w = torch.cat([w, w.new_zeros(w.shape[0], 16 - w.shape[1], 3, 3)], dim=1)
+                    put3(name, pack_tc_dense(w, layer.bias, _tc_nt(layer.out_channels)))
+                elif isinstance(layer, U.Downsample):
+                    put3(name, pack_tc_dense(layer.conv.weight, layer.conv.bias, _tc_nt(layer.conv.out_channels)))
+                elif isinstance(layer, U.Upsample):
+                    for py in range(2):
+                        for px in range(2):
+                            w, tb = pack_tc_up_phase(layer.conv.weight, layer.conv.bias, py, px, _tc_nt(layer.conv.out_channels))
+                            ws.put("%s.p%d%d.tcw" % (name, py, px), w); ws.put("%s.p%d%d.tb" % (name, py, px), tb)
+        fc = m.final_conv
+        put3("final", pack_tc_dense(fc[3].weight, fc[3].bias, 16))
+
+    def build_forward_ops_bf16(self, pool: Pool, BT: int, TH: int, TW: int, x_in: torch.Tensor, gmaps: List[torch.Tensor],
+                               attw: torch.Tensor, attw_stride: int, eps_ptr: int, stats: torch.Tensor) -> OpList:
+        """Same graph as build_forward_ops on the tcgen05 path: bf16 NHWC activations, x_in[BT,TH,TW,16] bf16."""
+        from .model import ucdir as U
+        ws, m = self.ws, self.m
+        bld = _Builder(pool, BT, stats, elem=2)
+        ol = bld.ops
+        nbytes = stats.numel() * stats.element_size()
+        ol.add("UCDIR_OP_MEMSET", {0: stats.data_ptr()}, {0: nbytes & 0x7FFFFFFF, 1: nbytes >> 31})
+        blk_index = {name: k for k, (name, _) in enumerate(self.blocks)}
+
+        def block(name, layer, x: Act, skip: Optional[Act]) -> Act:
+            rb = layer.res_block
+            cout = rb.dim_out
+            k = blk_index[name]
+            nt = _tc_nt(cout)
+            h1 = bld.new(cout, x.H, x.W)
+            _tc_op(ol, src0=x, src1=skip, w=ws.ptr(name + ".conv1.tcw"), tb=ws.ptr(name + ".conv1.tb"),
+                   tg=ws.ptr(name + ".conv1.tg"), gn=1, ncls=9, act=1, dst=h1, ntot=cout, B=BT, nt=nt)
+            if ws.has(name + ".res.tcw"):
+                res = bld.new(cout, x.H, x.W, with_stats=False)
+                _tc_op(ol, src0=x, src1=skip, w=ws.ptr(name + ".res.tcw"), tb=ws.ptr(name + ".res.tb"), nty=1, ntx=1, oy0=0,
+                       ox0=0, dst=res, ntot=cout, B=BT, nt=nt)
+                own_res = True
+            else:
+                if skip is not None:
+                    raise RuntimeError("identity residual with a concatenated input")
+                res, own_res = x, False
+            out = bld.new(cout, x.H, x.W)
+            kc = 64 if cout >= 512 else (32 if cout == 256 else 16)
+            _tc_op(ol, src0=h1, w=ws.ptr(name + ".spdy.tcw"), tb=ws.ptr(name + ".spdy.tb"), tg=ws.ptr(name + ".spdy.tg"),
+                   gn=1, ncls=9, groups=rb.nset, kc=kc, nt=min(cout, 256), mode=1, att=gmaps[k].data_ptr(),
+                   attw=attw.data_ptr() + k * 8 * 4, attw_stride=attw_stride, res=res, dst=out, ntot=cout * rb.nset, B=BT)
+            bld.release(h1)
+            if own_res:
+                bld.release(res)
+            bld.release(x)
+            bld.release(skip)
+            if layer.with_attn:
+                out = attention(name, out)
+            return out
+
+        def attention(name, x: Act) -> Act:
+            C, N = x.C, x.H * x.W
+            qkv = bld.new(3 * C, x.H, x.W, with_stats=False)
+            _tc_op(ol, src0=x, w=ws.ptr(name + ".attn.qkv.tcw"), tb=ws.ptr(name + ".attn.qkv.tb"),
+                   tg=ws.ptr(name + ".attn.qkv.tg"), gn=1, ncls=1, nty=1, ntx=1, oy0=0, ox0=0, dst=qkv, ntot=3 * C, B=BT, nt=256)
+            if N * N >= 2 ** 31 or N * 3 * C >= 2 ** 31:
+                raise RuntimeError("attention over %d tokens exceeds the 32-bit strides of the attention GEMMs" % N)
+            S = pool.get(BT * N * N * 4)
+            ol.add("UCDIR_OP_SGEMM_F32",
+                   {"UCDIR_SGEMM_P_A": qkv.ptr, "UCDIR_SGEMM_P_B": qkv.ptr + C * 2, "UCDIR_SGEMM_P_C": S.data_ptr()},
+                   {"UCDIR_SGEMM_I_BATCH": BT, "UCDIR_SGEMM_I_M": N, "UCDIR_SGEMM_I_N": N, "UCDIR_SGEMM_I_K": C,
+                    "UCDIR_SGEMM_I_LDA": 3 * C, "UCDIR_SGEMM_I_LDB": 3 * C, "UCDIR_SGEMM_I_LDC": N,
+                    "UCDIR_SGEMM_I_SA": N * 3 * C, "UCDIR_SGEMM_I_SB": N * 3 * C, "UCDIR_SGEMM_I_SC": N * N,
+                    "UCDIR_SGEMM_I_TRANSB": 1, "UCDIR_SGEMM_I_A_BF16": 1, "UCDIR_SGEMM_I_B_BF16": 1},
+                   {"UCDIR_SGEMM_F_ALPHA": 1.0 / math.sqrt(C)})
+            ol.add("UCDIR_OP_SOFTMAX_F32", {"UCDIR_SOFTMAX_P_X": S.data_ptr()},
+                   {"UCDIR_SOFTMAX_I_ROWS": BT * N, "UCDIR_SOFTMAX_I_COLS": N})
+            o = bld.new(C, x.H, x.W, with_stats=False)
+            ol.add("UCDIR_OP_SGEMM_F32",
+                   {"UCDIR_SGEMM_P_A": S.data_ptr(), "UCDIR_SGEMM_P_B": qkv.ptr + 2 * C * 2, "UCDIR_SGEMM_P_C": o.ptr},
+                   {"UCDIR_SGEMM_I_BATCH": BT, "UCDIR_SGEMM_I_M": N, "UCDIR_SGEMM_I_N": C, "UCDIR_SGEMM_I_K": N,
+                    "UCDIR_SGEMM_I_LDA": N, "UCDIR_SGEMM_I_LDB": 3 * C, "UCDIR_SGEMM_I_LDC": C,
+                    "UCDIR_SGEMM_I_SA": N * N, "UCDIR_SGEMM_I_SB": N * 3 * C, "UCDIR_SGEMM_I_SC": N * C,
+                    "UCDIR_SGEMM_I_TRANSB": 0, "UCDIR_SGEMM_I_B_BF16": 1, "UCDIR_SGEMM_I_C_BF16": 1},
+                   {"UCDIR_SGEMM_F_ALPHA": 1.0})
+            pool.put(S)
+            bld.release(qkv)
+            y = bld.new(C, x.H, x.W)
+            _tc_op(ol, src0=o, w=ws.ptr(name + ".attn.out.tcw"), tb=ws.ptr(name + ".attn.out.tb"), nty=1, ntx=1, oy0=0, ox0=0,
+                   res=x, dst=y, ntot=C, B=BT, nt=_tc_nt(C))
+            bld.release(o)
+            bld.release(x)
+            return y
+
+        feats: List[Act] = []
+        x = Act(x_in, 16, TH, TW, 0, keep=True)
+        for k, layer in enumerate(m.downs):
+            name = "downs.%d" % k
+            if isinstance(layer, torch.nn.Conv2d):
+                y = bld.new(layer.out_channels, x.H, x.W)
+                _tc_op(ol, src0=x, w=ws.ptr(name + ".tcw"), tb=ws.ptr(name + ".tb"), kc=16, dst=y, ntot=layer.out_channels,
+                       B=BT, nt=_tc_nt(layer.out_channels))
+                x = y
+            elif isinstance(layer, U.Downsample):
+                y = bld.new(x.C, x.H // 2, x.W // 2)
+                _tc_op(ol, src0=x, w=ws.ptr(name + ".tcw"), tb=ws.ptr(name + ".tb"), stride=2, dst=y, ntot=x.C, B=BT,
+                       nt=_tc_nt(x.C))
+                x = y
+            else:
+                x.keep = True
+                x = block(name, layer, x, None)
+            x.keep = True
+            feats.append(x)
+        x = feats[-1]
+        for k, layer in enumerate(m.mid):
+            x = block("mid.%d" % k, layer, x, None)
+        for k, layer in enumerate(m.ups):
+            name = "ups.%d" % k
+            if isinstance(layer, U.Upsample):
+                y = bld.new(x.C, x.H * 2, x.W * 2)
+                for py in range(2):
+                    for px in range(2):
+                        _tc_op(ol, src0=x, w=ws.ptr("%s.p%d%d.tcw" % (name, py, px)), tb=ws.ptr("%s.p%d%d.tb" % (name, py, px)),
+                               nty=2, ntx=2, oy0=py - 1, ox0=px - 1, dst=y, ntot=x.C, B=BT, nt=_tc_nt(x.C), dst_up=1,
+                               dst_py=py, dst_px=px)
+                bld.release(x)
+                x = y
+            else:
+                skip = feats.pop()
+                skip.keep = False
+                x = block(name, layer, x, skip)
+        # final_conv: GN -> Swish -> conv (model/ucdir.py:266-268); Swish sits between the norm and the conv, so
+        # the norm cannot be folded: one elementwise pass, then a 16-column (3 valid) tensor-core conv to fp32 eps
+        xn = bld.new(x.C, x.H, x.W, with_stats=False)
+        ol.add("UCDIR_OP_GN_APPLY_BF16",
+               {"UCDIR_GNA_P_SRC": x.ptr, "UCDIR_GNA_P_DST": xn.ptr, "UCDIR_GNA_P_GAMMA": ws.ptr("final.norm.w"),
+                "UCDIR_GNA_P_BETA": ws.ptr("final.norm.b"), "UCDIR_GNA_P_STATS": x.stats},
+               {"UCDIR_GNA_I_B": BT, "UCDIR_GNA_I_HW": x.H * x.W, "UCDIR_GNA_I_C": x.C, "UCDIR_GNA_I_SWISH": 1}, {0: 1e-5})
+        bld.release(x)
+        eps_dst = Act(_PtrBuf(eps_ptr), 4, TH, TW, 0, keep=True)      # type: ignore[arg-type]
+        _tc_op(ol, src0=xn, w=ws.ptr("final.tcw"), tb=ws.ptr("final.tb"), dst=eps_dst, ntot=16, B=BT, nt=16, dst_f32=1,
+               ncol_valid=m.cfg["out_channel"])
+        bld.release(xn)
+        self.last_stat_slots = bld.next_slot
+        return ol
+
     # ---- sessions -----------------------------------------------------------------------
     def session(self, cond: torch.Tensor, guide: torch.Tensor, levels=None, geometry: Optional[Geometry] = None,
                 cond_channels: Optional[int] = None) -> "Session":
@@ -557,7 +868,7 @@ class UNetEngine:
         B, _, h, w = cond.shape
         if geometry is None:
             geometry = self.default_geometry(B, h, w)
-        key = (B, h, w, geometry.kind, geometry.TH, geometry.TW, geometry.PD, cond.shape[1])
+        key = (B, h, w, geometry.kind, geometry.TH, geometry.TW, geometry.PD, cond.shape[1], self.precision)
         s = self._sessions.get(key)
         if s is None:
             self._sessions.clear()                               # one resident plan at a time: plans hold GBs
@@ -653,7 +964,9 @@ class Session:
         self.guide_tiles_all = []
         maxbt = max((b - a) for a, b in self.chunks) if self.chunks else 1
         self.stats = torch.empty((MAX_STAT_SLOTS, maxbt, 2), dtype=torch.float64, device=dev)
-        self.x_tiles = torch.empty((maxbt, g.TH, g.TW, 8), dtype=F32, device=dev)
+        self.bf16 = eng.precision == "bf16"
+        self.x_tiles = torch.empty((maxbt, g.TH, g.TW, 16), dtype=BF16, device=dev) if self.bf16 else \
+            torch.empty((maxbt, g.TH, g.TW, 8), dtype=F32, device=dev)
         # step op 0: timestep embedding -> attw table
         self.idx_temb = eng.time_embed_op(self.step_ops, self.attw, 1, 0, 0.0)
         for (a, b) in self.chunks:
@@ -676,11 +989,12 @@ class Session:
                  "UCDIR_GATHER_P_DST": self.x_tiles.data_ptr()},
                 {"UCDIR_GATHER_I_BT": BT, "UCDIR_GATHER_I_TH": g.TH, "UCDIR_GATHER_I_TW": g.TW,
                  "UCDIR_GATHER_I_IMG_H": g.IH, "UCDIR_GATHER_I_IMG_W": g.IW, "UCDIR_GATHER_I_PD": g.PD,
-                 "UCDIR_GATHER_I_CA": ca, "UCDIR_GATHER_I_CB": 6 - ca, "UCDIR_GATHER_I_CD": 8}))
+                 "UCDIR_GATHER_I_CA": ca, "UCDIR_GATHER_I_CB": 6 - ca, "UCDIR_GATHER_I_CD": 16 if self.bf16 else 8,
+                 "UCDIR_GATHER_I_OUT_BF16": 1 if self.bf16 else 0}))
             eps_ptr = self.eps.data_ptr() + a * g.TH * g.TW * 4 * 4
             stats_view = self.stats.view(-1)[:MAX_STAT_SLOTS * BT * 2].view(MAX_STAT_SLOTS, BT, 2)   # same storage
-            sub = eng.build_forward_ops(self.pool, BT, g.TH, g.TW, self.x_tiles, gmaps, self.attw, 0, eps_ptr,
-                                        stats_view)
+            build = eng.build_forward_ops_bf16 if self.bf16 else eng.build_forward_ops
+            sub = build(self.pool, BT, g.TH, g.TW, self.x_tiles, gmaps, self.attw, 0, eps_ptr, stats_view)
             self._chunk_attw_fix(sub, a)
             self.step_ops.extend(sub)
         self.n_unet_ops = len(self.step_ops)
@@ -703,7 +1017,9 @@ class Session:
         self._mix_ops = getattr(self, "_mix_ops", [])
         for o in sub.ops:
             if o.kind == K_["UCDIR_OP_CONV_F32"] and o.i[K_["UCDIR_CONV_I_MODE"]] == 1:
-                self._mix_ops.append((o, a, int(o.p[K_["UCDIR_CONV_P_ATTW"]])))
+                self._mix_ops.append((o, a, int(o.p[K_["UCDIR_CONV_P_ATTW"]]), "UCDIR_CONV_P_ATTW", "UCDIR_CONV_I_ATTW_STRIDE"))
+            elif o.kind == K_["UCDIR_OP_TC_CONV"] and o.i[K_["UCDIR_TC_I_MODE"]] == 1:
+                self._mix_ops.append((o, a, int(o.p[K_["UCDIR_TC_P_ATTW"]]), "UCDIR_TC_P_ATTW", "UCDIR_TC_I_ATTW_STRIDE"))
 
     def _set_attw_mode(self, per_tile: bool):
         """per_tile=False: one level for the whole batch (sampler).  True: levels[tile] (generic forward)."""
@@ -711,9 +1027,9 @@ class Session:
         stride = nblk * 8 if per_tile else 0
         if stride == self._attw_stride and self._bound:
             return
-        for o, a, base in self._mix_ops:
-            o.i[K_["UCDIR_CONV_I_ATTW_STRIDE"]] = stride
-            o.p[K_["UCDIR_CONV_P_ATTW"]] = base + a * stride * 4
+        for o, a, base, pk, ik in self._mix_ops:
+            o.i[K_[ik]] = stride
+            o.p[K_[pk]] = base + a * stride * 4
         self._attw_stride = stride
         self.step_ops._arr = None
 
