@@ -100,17 +100,49 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # algorithmic work of an op array (DESIGN.md "Roofline"): 2*MAC for conv / GEMM ops
 # ----------------------------------------------------------------------------------------------
-def op_flops(op, K):
-    kind = int(op.kind)
-    if kind in (K["UCDIR_OP_CONV_F32"], K.get("UCDIR_OP_TC_CONV", -1)):
-        B, H, W = op.i[K["UCDIR_CONV_I_B"]], op.i[K["UCDIR_CONV_I_H"]], op.i[K["UCDIR_CONV_I_W"]]
-        cin = op.i[K["UCDIR_CONV_I_C0"]] + op.i[K["UCDIR_CONV_I_C1"]]
-        ks, groups, cout = op.i[K["UCDIR_CONV_I_KSIZE"]], op.i[K["UCDIR_CONV_I_GROUPS"]], op.i[K["UCDIR_CONV_I_COUT"]]
-        return 2.0 * B * H * W * ks * ks * (cin // groups) * cout
-    if kind == K["UCDIR_OP_SGEMM_F32"]:
-        return 2.0 * op.i[K["UCDIR_SGEMM_I_BATCH"]] * op.i[K["UCDIR_SGEMM_I_M"]] * op.i[K["UCDIR_SGEMM_I_N"]] * \
-            op.i[K["UCDIR_SGEMM_I_K"]]
-    return 0.0
+def unet_algorithmic_flops(unet, H, W):
+    """2*MAC of one DY3h.naiveforward on an HxW sample, from the reference's layer shapes (model/ucdir.py:205-293):
+    returns (conv_flops, attention_core_flops).  Independent of how a precision mode executes the layers
+    (zero-padded K chunks, phase-decomposed upsampling and padded output columns do not count)."""
+    from ucdir_b200.model import ucdir as U
+    conv = attn = 0.0
+    feats = []
+
+    def block(layer, cin, h, w):
+        nonlocal conv, attn
+        rb = layer.res_block
+        co = rb.dim_out
+        conv += 2.0 * h * w * 9 * cin * co                       # conv1
+        conv += 2.0 * h * w * 9 * (co // rb.nset) * co * rb.nset  # spdyconv (grouped, C -> 8C)
+        if cin != co:
+            conv += 2.0 * h * w * cin * co                       # res_conv 1x1
+        if layer.with_attn:
+            n = h * w
+            conv += 2.0 * n * co * 3 * co + 2.0 * n * co * co    # qkv, out 1x1
+            attn += 4.0 * n * n * co                             # QK^T and PV
+        return co
+
+    c, h, w = None, H, W
+    for layer in unet.downs:
+        if isinstance(layer, torch.nn.Conv2d):
+            conv += 2.0 * h * w * 9 * layer.in_channels * layer.out_channels
+            c = layer.out_channels
+        elif isinstance(layer, U.Downsample):
+            h, w = h // 2, w // 2
+            conv += 2.0 * h * w * 9 * c * c
+        else:
+            c = block(layer, c, h, w)
+        feats.append(c)
+    for layer in unet.mid:
+        c = block(layer, c, h, w)
+    for layer in unet.ups:
+        if isinstance(layer, U.Upsample):
+            h, w = h * 2, w * 2
+            conv += 2.0 * h * w * 9 * c * c
+        else:
+            c = block(layer, c + feats.pop(), h, w)
+    conv += 2.0 * h * w * 9 * c * unet.cfg["out_channel"]
+    return conv, attn
 
 
 def run_ours(args):
@@ -209,18 +241,13 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel class (convolution implicit GEMMs), from the live per-op events ----
     step_ops = sess.step_ops.ops
-    conv_kinds = {K["UCDIR_OP_CONV_F32"], K.get("UCDIR_OP_TC_CONV", -1)}
+    conv_kinds = {K["UCDIR_OP_CONV_F32"], K["UCDIR_OP_TC_CONV"]}
     by_kind_ms = {}
-    conv_ms = conv_flops = all_flops = 0.0
-    n_step_ops = len(step_ops)
-    # records come in call order: [step ops ..., tail op] per step; op_index restarts at 0 in each call
     for ms, idx, kind in prof:
         by_kind_ms[kind] = by_kind_ms.get(kind, 0.0) + ms
-    for o in step_ops:
-        f = op_flops(o, K)
-        all_flops += f
-        if int(o.kind) in conv_kinds:
-            conv_flops += f
+    my_tiles = sess.my_tiles[1] - sess.my_tiles[0]
+    conv_tile, attn_tile = unet_algorithmic_flops(unet, sess.geo.TH, sess.geo.TW)
+    conv_flops, all_flops = conv_tile * my_tiles, (conv_tile + attn_tile) * my_tiles
     conv_ms = sum(v for k, v in by_kind_ms.items() if k in conv_kinds) / args.steps
     n_conv = sum(1 for o in step_ops if int(o.kind) in conv_kinds)
     peaks = load_peaks()

@@ -23,7 +23,7 @@ class Case:
         return self
 
     def on(self, dev):
-        return {k: v.to(dev).contiguous() for k, v in self.t.items()}
+        return {k: v.clone().to(dev).contiguous() for k, v in self.t.items()}
 
 
 def run_both(case, build):
