@@ -145,6 +145,40 @@ def unet_algorithmic_flops(unet, H, W):
     return conv, attn
 
 
+def dump_op_profile(path, step_ops, prof, steps, K):
+    """Per-op device time (CUDA events, averaged over the timed steps) with the shape fields of each record."""
+    per = {}
+    n_ops = len(step_ops)
+    for ms, idx, kind in prof:
+        if idx < n_ops and int(step_ops[idx].kind) == kind:
+            per[idx] = per.get(idx, 0.0) + ms
+    names = {v: k for k, v in K.items() if k.startswith("UCDIR_OP_") and not k.endswith(("NPTR", "NINT", "NFLT"))}
+    rows = []
+    for idx, o in enumerate(step_ops):
+        kind = int(o.kind)
+        r = {"op": idx, "kind": names.get(kind, str(kind)), "ms": round(per.get(idx, 0.0) / steps, 4)}
+        if kind == K["UCDIR_OP_TC_CONV"]:
+            g = lambda n: int(o.i[K["UCDIR_TC_I_" + n]])
+            r.update(B=g("B"), H=g("H"), W=g("W"), C0=g("C0"), C1=g("C1"), N=g("NTOT"), taps=g("NTY") * g("NTX"), stride=g("STRIDE"),
+                     groups=g("GROUPS"), KC=g("KC"), NT=g("NT"), mode=g("MODE"), gn=g("GN"))
+            cin = (g("C0") + g("C1")) // g("GROUPS")
+            r["gflop"] = round(2e-9 * g("B") * g("H") * g("W") * g("NTY") * g("NTX") * cin * g("NTOT"), 2)
+        elif kind == K["UCDIR_OP_CONV_F32"]:
+            g = lambda n: int(o.i[K["UCDIR_CONV_I_" + n]])
+            r.update(B=g("B"), H=g("H"), W=g("W"), C0=g("C0"), C1=g("C1"), N=g("COUT"), taps=g("KSIZE") ** 2, stride=g("STRIDE"),
+                     groups=g("GROUPS"), mode=g("MODE"))
+            r["gflop"] = round(2e-9 * g("B") * g("H") * g("W") * g("KSIZE") ** 2 * ((g("C0") + g("C1")) // g("GROUPS")) * g("COUT"), 2)
+        elif kind == K["UCDIR_OP_SGEMM_F32"]:
+            g = lambda n: int(o.i[K["UCDIR_SGEMM_I_" + n]])
+            r.update(B=g("BATCH"), M=g("M"), N=g("N"), K=g("K"))
+            r["gflop"] = round(2e-9 * g("BATCH") * g("M") * g("N") * g("K"), 2)
+        if r.get("gflop") and r["ms"] > 0:
+            r["tflops"] = round(r["gflop"] / r["ms"], 1)
+        rows.append(r)
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    json.dump(rows, open(path, "w"), indent=0)
+
+
 def run_ours(args):
     import ucdir_b200
     from ucdir_b200 import _lib
@@ -250,6 +284,8 @@ def run_ours(args):
     conv_flops, all_flops = conv_tile * my_tiles, (conv_tile + attn_tile) * my_tiles
     conv_ms = sum(v for k, v in by_kind_ms.items() if k in conv_kinds) / args.steps
     n_conv = sum(1 for o in step_ops if int(o.kind) in conv_kinds)
+    if args.dump_ops and rank == 0:
+        dump_op_profile(args.dump_ops, step_ops, prof, args.steps, K)
     peaks = load_peaks()
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     names = {v: k for k, v in K.items() if k.startswith("UCDIR_OP_") and k not in ("UCDIR_OP_NPTR", "UCDIR_OP_NINT", "UCDIR_OP_NFLT")}
@@ -384,6 +420,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("UCDIR_PRECISION", "fp32"), choices=["fp32", "bf16"])
     ap.add_argument("--cpu-tiles", type=int, default=4, help="tile forwards per CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dump-ops", default="", help="write the per-op device-time profile of the timed steps to this JSON file")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== smoke" ; timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 ; echo "smoke rc=$?" ; tail -3 gpurun_out/smoke.log
 echo "== pytest gpu" ; timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1 ; echo "pytest rc=$?" ; tail -15 gpurun_out/pytest_gpu.log
-echo "== bench" ; timeout 900 python bench.py --steps ${STEPS:-5} --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err ; echo "bench rc=$?" ; tail -2 gpurun_out/bench.err ; cat gpurun_out/bench.json
+echo "== bench" ; timeout 900 python bench.py --steps ${STEPS:-5} --warmup 3 --dump-ops gpurun_out/ops_profile.json ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err ; echo "bench rc=$?" ; tail -2 gpurun_out/bench.err ; cat gpurun_out/bench.json
 if [ "${NCU:-1}" = "1" ]; then
 echo "== ncu launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu ${BENCH_ARGS:-} > gpurun_out/ncu_bench.log 2>&1 ; echo "ncu rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:ucdir -c 4000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu ${BENCH_ARGS:-} > gpurun_out/ncu_bench.log 2>&1 ; echo "ncu rc=$?"
 fi

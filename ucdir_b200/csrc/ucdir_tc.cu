@@ -33,6 +33,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -120,7 +123,7 @@ struct TcParams {
   void* dst; double* dst_stats;
   int B, H, W, srcH, srcW;
   int Ntot, ncol_valid;
-  int bw, bh, bn, tiles_x, tiles_y;
+  int bw, bh, bn, tiles_x, tiles_y, m_tiles;
   int nty, ntx, oy0, ox0, stride;
   int nchunk, c0_chunks, groups, Ng, Cg, cg_eff;
   int gn, ncls, act, mode, dst_f32;
@@ -128,49 +131,55 @@ struct TcParams {
   double gn_count; float eps;
 };
 
-constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int TC_EPI_WARPS = 8;
 
 template <int KC, int NT>
-struct TcSmem {
+struct TcCfg {
   static constexpr int A_BYTES = 128 * KC * 2;
   static constexpr int B_BYTES = NT * KC * 2;
   static constexpr int B_PAD = (B_BYTES + 1023) & ~1023;
   static constexpr int STAGE = A_BYTES + B_PAD;
-  static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*align slack*/ + 128 /*barriers*/;
+  static constexpr int STAGES_RAW = 196608 / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 12 ? 12 : (STAGES_RAW < 4 ? 4 : STAGES_RAW);
+  static constexpr int SLOTW = NT < 32 ? 32 : NT;          // TMEM columns per accumulator slot
+  static constexpr int NSLOT = 512 / SLOTW;                // accumulator ring: MMA of item i+1.. overlaps epilogue of item i
+  static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + (2 * STAGES + 2 * NSLOT) * 8 + 64;
 };
 
+// Persistent CTA (one per SM).  Work item = (M tile, N sub-tile of NT columns); a CTA owns a contiguous range of
+// items, N fastest, so consecutive items re-read the same activation tile from L2.  Three pipelines:
+//   smem ring   full[s]/empty[s]            TMA producer  <-> MMA issuer
+//   TMEM ring   tmem_full[j]/tmem_empty[j]  MMA issuer    <-> epilogue warps   (NSLOT accumulators of NT columns)
 template <int KC, int NT>
-__global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0,
-                                                             const __grid_constant__ CUtensorMap mapA1,
-                                                             const __grid_constant__ CUtensorMap mapB, const TcParams p) {
-  using S = TcSmem<KC, NT>;
-  constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0,
+                                                                const __grid_constant__ CUtensorMap mapA1,
+                                                                const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  using S = TcCfg<KC, NT>;
+  constexpr int STAGES = S::STAGES, NSLOT = S::NSLOT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * S::STAGE);
-  uint64_t* empty = full + TC_STAGES;
-  uint64_t* tmem_full = empty + TC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint64_t* tmem_empty = tmem_full + NSLOT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + NSLOT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // ---- tile coordinates ----
-  const int m = blockIdx.x;
-  const int tx_i = m % p.tiles_x, ty_i = (m / p.tiles_x) % p.tiles_y, tn_i = m / (p.tiles_x * p.tiles_y);
-  const int x0 = tx_i * p.bw, y0 = ty_i * p.bh, n0 = tn_i * p.bn;
-  const int ncol0 = blockIdx.y * NT;
-  const int g = p.groups > 1 ? ncol0 / p.Ng : 0;
+  const int n_sub = p.Ntot / NT;
+  const long long total = (long long)p.m_tiles * n_sub;
+  const long long it0 = total * blockIdx.x / gridDim.x, it1 = total * (blockIdx.x + 1) / gridDim.x;
   const int nslab = p.nty * p.ntx * p.nchunk;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
     if (p.c0_chunks < p.nchunk && p.groups == 1) prefetch_tmap(&mapA1);
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int j = 0; j < NSLOT; ++j) { mbar_init(&tmem_full[j], 1); mbar_init(&tmem_empty[j], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -182,156 +191,195 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)(p.bw * p.bh * p.bn * KC * 2 + NT * KC * 2);
-      const int cgrp0 = p.groups > 1 ? (g * p.Cg) / p.cg_eff * p.cg_eff : 0;
-      for (int i = 0; i < nslab; ++i) {
-        const int s = i % TC_STAGES;
-        const uint32_t ph = (i / TC_STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        const int tap = i / p.nchunk, j = i - tap * p.nchunk;
-        const int ty = tap / p.ntx, tx = tap - ty * p.ntx;
-        uint8_t* sa = smem + s * S::STAGE;
-        uint8_t* sb = sa + S::A_BYTES;
-        mbar_expect_tx(&full[s], tx_bytes);
-        const int cx = x0 * p.stride + tx + p.ox0, cy = y0 * p.stride + ty + p.oy0;
-        if (p.groups > 1 || j < p.c0_chunks) tma_load_4d(&mapA0, &full[s], sa, cgrp0 + j * KC, cx, cy, n0);
-        else tma_load_4d(&mapA1, &full[s], sa, (j - p.c0_chunks) * KC, cx, cy, n0);
-        tma_load_2d(&mapB, &full[s], sb, i * KC, ncol0);
+      uint32_t gs = 0;                                  // global slab counter of this CTA (smem ring position)
+      for (long long it = it0; it < it1; ++it) {
+        const int m = (int)(it / n_sub), ns = (int)(it - (long long)m * n_sub);
+        const int tx_i = m % p.tiles_x, ty_i = (m / p.tiles_x) % p.tiles_y, tn_i = m / (p.tiles_x * p.tiles_y);
+        const int x0 = tx_i * p.bw, y0 = ty_i * p.bh, n0 = tn_i * p.bn;
+        const int ncol0 = ns * NT;
+        const int cgrp0 = p.groups > 1 ? ((ncol0 / p.Ng) * p.Cg) / p.cg_eff * p.cg_eff : 0;
+        for (int i = 0; i < nslab; ++i, ++gs) {
+          const int s = gs % STAGES;
+          const uint32_t ph = (gs / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          const int tap = i / p.nchunk, j = i - tap * p.nchunk;
+          const int ty = tap / p.ntx, tx = tap - ty * p.ntx;
+          uint8_t* sa = smem + s * S::STAGE;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_expect_tx(&full[s], tx_bytes);
+          const int cx = x0 * p.stride + tx + p.ox0, cy = y0 * p.stride + ty + p.oy0;
+          if (p.groups > 1 || j < p.c0_chunks) tma_load_4d(&mapA0, &full[s], sa, cgrp0 + j * KC, cx, cy, n0);
+          else tma_load_4d(&mapA1, &full[s], sa, (j - p.c0_chunks) * KC, cx, cy, n0);
+          tma_load_2d(&mapB, &full[s], sb, i * KC, ncol0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      for (int i = 0; i < nslab; ++i) {
-        const int s = i % TC_STAGES;
-        const uint32_t ph = (i / TC_STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      uint32_t gs = 0, li = 0;
+      for (long long it = it0; it < it1; ++it, ++li) {
+        const int slot = li % NSLOT;
+        const uint32_t sph = (li / NSLOT) & 1;
+        mbar_wait(&tmem_empty[slot], sph ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * S::STAGE), sb = sa + S::A_BYTES;
-        const uint64_t ad = make_desc(sa, KC * 2), bd = make_desc(sb, KC * 2);
+        const uint32_t tacc = tmem_base + (uint32_t)(slot * S::SLOTW);
+        for (int i = 0; i < nslab; ++i, ++gs) {
+          const int s = gs % STAGES;
+          const uint32_t ph = (gs / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * S::STAGE), sb = sa + S::A_BYTES;
+          const uint64_t ad = make_desc(sa, KC * 2), bd = make_desc(sb, KC * 2);
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k)
-          umma_bf16(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (i | k) != 0);
-        umma_commit(&empty[s]);            // frees the smem slot once these MMAs have read it
+          for (int k = 0; k < KC / 16; ++k)
+            umma_bf16(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (i | k) != 0);
+          umma_commit(&empty[s]);            // frees the smem slot once these MMAs have read it
+        }
+        umma_commit(&tmem_full[slot]);       // accumulator of this item complete
       }
-      umma_commit(tmem_full);              // accumulator complete
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                          // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;                // two warps per quadrant take alternate column chunks
     const int r = q * 32 + lane;                     // accumulator row = pixel slot of the tile
     const int box = p.bw * p.bh;
     const int nn = r / box, rr = r - nn * box;
     const int yy = rr / p.bw, xx = rr - yy * p.bw;
-    const int img = n0 + nn, y = y0 + yy, x = x0 + xx;
-    const bool valid = (r < box * p.bn) && img < p.B && y < p.H && x < p.W;
-    float rstd = 1.f, mr = 0.f;
-    int cls = 0;
-    if (p.gn && valid) {
-      GnScalars sc = gn_scalars(p.stats0, p.stats1, img, p.gn_count, p.eps);
-      rstd = sc.rstd; mr = sc.mean * sc.rstd;
-      if (p.ncls == 9) cls = (y == 0 ? 0 : (y == p.H - 1 ? 2 : 1)) * 3 + (x == 0 ? 0 : (x == p.W - 1 ? 2 : 1));
-    }
-    const float* tb = p.tb + (size_t)cls * p.Ntot + ncol0;
-    const float* tg = p.tg ? p.tg + (size_t)cls * p.Ntot + ncol0 : nullptr;
-    const size_t pix_in = ((size_t)(valid ? img : 0) * p.H + (valid ? y : 0)) * p.W + (valid ? x : 0);
-    const size_t pix_out = p.dstUp ? ((size_t)(valid ? img : 0) * 2 * p.H + 2 * (valid ? y : 0) + p.dstPy) * (2 * p.W) + 2 * (valid ? x : 0) + p.dstPx
-                                   : pix_in;
-    float aw[8];
-    if (p.mode == 1) {
-      const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.att + pix_in * 8));
-      const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.att + pix_in * 8 + 4));
-      const float* w8 = p.attw + (size_t)(valid ? img : 0) * p.attwStride;
-      aw[0] = t0.x * __ldg(w8 + 0); aw[1] = t0.y * __ldg(w8 + 1); aw[2] = t0.z * __ldg(w8 + 2); aw[3] = t0.w * __ldg(w8 + 3);
-      aw[4] = t1.x * __ldg(w8 + 4); aw[5] = t1.y * __ldg(w8 + 5); aw[6] = t1.z * __ldg(w8 + 6); aw[7] = t1.w * __ldg(w8 + 7);
-    }
-    float s1 = 0.f, s2 = 0.f;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     constexpr int CH = NT < 32 ? 16 : 32;
+    uint32_t li = 0;
+    int m_prev = -1;
+    bool valid = false;
+    int img = 0, y = 0, x = 0, cls = 0;
+    float rstd = 1.f, mr = 0.f;
+    size_t pix_in = 0, pix_out = 0;
+    float aw[8];
+    for (long long it = it0; it < it1; ++it, ++li) {
+      const int m = (int)(it / n_sub), ns = (int)(it - (long long)m * n_sub);
+      const int ncol0 = ns * NT;
+      const int slot = li % NSLOT;
+      const uint32_t sph = (li / NSLOT) & 1;
+      if (m != m_prev) {                              // per-pixel state changes only with the M tile
+        m_prev = m;
+        const int tx_i = m % p.tiles_x, ty_i = (m / p.tiles_x) % p.tiles_y, tn_i = m / (p.tiles_x * p.tiles_y);
+        img = tn_i * p.bn + nn; y = ty_i * p.bh + yy; x = tx_i * p.bw + xx;
+        valid = (r < box * p.bn) && img < p.B && y < p.H && x < p.W;
+        rstd = 1.f; mr = 0.f; cls = 0;
+        if (!valid) { img = 0; y = 0; x = 0; }
+        if (p.gn && valid) {
+          GnScalars sc = gn_scalars(p.stats0, p.stats1, img, p.gn_count, p.eps);
+          rstd = sc.rstd; mr = sc.mean * sc.rstd;
+          if (p.ncls == 9) cls = (y == 0 ? 0 : (y == p.H - 1 ? 2 : 1)) * 3 + (x == 0 ? 0 : (x == p.W - 1 ? 2 : 1));
+        }
+        pix_in = ((size_t)img * p.H + y) * p.W + x;
+        pix_out = p.dstUp ? ((size_t)img * 2 * p.H + 2 * y + p.dstPy) * (2 * p.W) + 2 * x + p.dstPx : pix_in;
+        if (p.mode == 1) {
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.att + pix_in * 8));
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.att + pix_in * 8 + 4));
+          const float* w8 = p.attw + (size_t)img * p.attwStride;
+          aw[0] = t0.x * __ldg(w8 + 0); aw[1] = t0.y * __ldg(w8 + 1); aw[2] = t0.z * __ldg(w8 + 2); aw[3] = t0.w * __ldg(w8 + 3);
+          aw[4] = t1.x * __ldg(w8 + 4); aw[5] = t1.y * __ldg(w8 + 5); aw[6] = t1.z * __ldg(w8 + 6); aw[7] = t1.w * __ldg(w8 + 7);
+        }
+      }
+      const float* tb = p.tb + (size_t)cls * p.Ntot + ncol0;
+      const float* tg = p.tg ? p.tg + (size_t)cls * p.Ntot + ncol0 : nullptr;
+      float s1 = 0.f, s2 = 0.f;
+      mbar_wait(&tmem_full[slot], sph);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < NT; c0 += CH) {
-      uint32_t rv[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      if (CH == 32) tmem_ld32(taddr, rv); else tmem_ld16(taddr, rv);
-      tmem_ld_wait();
-      if (!valid) continue;
-      float v[CH];
+      for (int c0 = half * CH; c0 < NT; c0 += 2 * CH) {
+        uint32_t rv[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * S::SLOTW + c0);
+        if (CH == 32) tmem_ld32(taddr, rv); else tmem_ld16(taddr, rv);
+        tmem_ld_wait();
+        if (!valid) continue;
+        float v[CH];
 #pragma unroll
-      for (int j = 0; j < CH; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(tb + c0 + j));
-        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tg) g4 = __ldg(reinterpret_cast<const float4*>(tg + c0 + j));
-        v[j + 0] = fmaf(__uint_as_float(rv[j + 0]), rstd, fmaf(-mr, g4.x, b4.x));
-        v[j + 1] = fmaf(__uint_as_float(rv[j + 1]), rstd, fmaf(-mr, g4.y, b4.y));
-        v[j + 2] = fmaf(__uint_as_float(rv[j + 2]), rstd, fmaf(-mr, g4.z, b4.z));
-        v[j + 3] = fmaf(__uint_as_float(rv[j + 3]), rstd, fmaf(-mr, g4.w, b4.w));
-      }
-      if (p.mode == 1) {
-        // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
-        constexpr int NO = CH / 8;
-        const int cbase = (ncol0 + c0) >> 3;
-        __align__(8) __nv_bfloat16 o[NO];
-        const __nv_bfloat16* rp = p.res + pix_in * p.resC + cbase;
-#pragma unroll
-        for (int c = 0; c < NO; ++c) {
-          float h = 0.f;
-#pragma unroll
-          for (int s = 0; s < 8; ++s) h = fmaf(v[c * 8 + s], aw[s], h);
-          const float t = swish_f(h) + __bfloat162float(rp[c]);
-          o[c] = __float2bfloat16(t);
-          const float tr = __bfloat162float(o[c]);
-          s1 += tr; s2 += tr * tr;
+        for (int j = 0; j < CH; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(tb + c0 + j));
+          float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (tg) g4 = __ldg(reinterpret_cast<const float4*>(tg + c0 + j));
+          v[j + 0] = fmaf(__uint_as_float(rv[j + 0]), rstd, fmaf(-mr, g4.x, b4.x));
+          v[j + 1] = fmaf(__uint_as_float(rv[j + 1]), rstd, fmaf(-mr, g4.y, b4.y));
+          v[j + 2] = fmaf(__uint_as_float(rv[j + 2]), rstd, fmaf(-mr, g4.z, b4.z));
+          v[j + 3] = fmaf(__uint_as_float(rv[j + 3]), rstd, fmaf(-mr, g4.w, b4.w));
         }
-        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix_out * p.dstC + p.dstCoff + cbase;
-        if (NO == 4) *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(o);
-        else *reinterpret_cast<uint32_t*>(d) = *reinterpret_cast<const uint32_t*>(o);
-      } else {
-        const int nb = ncol0 + c0;
-        if (p.act == 1) {
+        if (p.mode == 1) {
+          // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
+          constexpr int NO = CH / 8;
+          const int cbase = (ncol0 + c0) >> 3;
+          __align__(8) __nv_bfloat16 o[NO];
+          const __nv_bfloat16* rp = p.res + pix_in * p.resC + cbase;
+          __align__(8) __nv_bfloat16 rres[NO];
+          if (NO == 4) *reinterpret_cast<uint2*>(rres) = __ldg(reinterpret_cast<const uint2*>(rp));
+          else *reinterpret_cast<uint32_t*>(rres) = __ldg(reinterpret_cast<const uint32_t*>(rp));
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = swish_f(v[j]);
-        }
-        if (p.res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix_in * p.resC + nb);
+          for (int c = 0; c < NO; ++c) {
+            float h = 0.f;
 #pragma unroll
-          for (int j = 0; j < CH; j += 8) {
-            const uint4 u = __ldg(rp + j / 8);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(h2[e]);
-              v[j + 2 * e] += f.x; v[j + 2 * e + 1] += f.y;
-            }
+            for (int s = 0; s < 8; ++s) h = fmaf(v[c * 8 + s], aw[s], h);
+            const float t = swish_f(h) + __bfloat162float(rres[c]);
+            o[c] = __float2bfloat16(t);
+            const float tr = __bfloat162float(o[c]);
+            s1 += tr; s2 += tr * tr;
           }
-        }
-        if (p.dst_f32) {
-          float* d = reinterpret_cast<float*>(p.dst) + pix_out * p.dstC + p.dstCoff + nb;
-#pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (nb + j < p.ncol_valid) { d[j] = v[j]; s1 += v[j]; s2 += v[j] * v[j]; }
+          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix_out * p.dstC + p.dstCoff + cbase;
+          if (NO == 4) *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(o);
+          else *reinterpret_cast<uint32_t*>(d) = *reinterpret_cast<const uint32_t*>(o);
         } else {
-          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix_out * p.dstC + p.dstCoff + nb;
+          const int nb = ncol0 + c0;
+          if (p.act == 1) {
 #pragma unroll
-          for (int j = 0; j < CH; j += 8) {
-            __align__(16) __nv_bfloat162 o2[4];
+            for (int j = 0; j < CH; ++j) v[j] = swish_f(v[j]);
+          }
+          if (p.res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix_in * p.resC + nb);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              o2[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-              const float2 f = __bfloat1622float2(o2[e]);
-              s1 += f.x + f.y; s2 += f.x * f.x + f.y * f.y;
+            for (int j = 0; j < CH; j += 8) {
+              const uint4 u = __ldg(rp + j / 8);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h2[e]);
+                v[j + 2 * e] += f.x; v[j + 2 * e + 1] += f.y;
+              }
             }
-            *reinterpret_cast<uint4*>(d + j) = *reinterpret_cast<const uint4*>(o2);
+          }
+          if (p.dst_f32) {
+            float* d = reinterpret_cast<float*>(p.dst) + pix_out * p.dstC + p.dstCoff + nb;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (nb + j < p.ncol_valid) { d[j] = v[j]; s1 += v[j]; s2 += v[j] * v[j]; }
+          } else {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix_out * p.dstC + p.dstCoff + nb;
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              __align__(16) __nv_bfloat162 o2[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                o2[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+                const float2 f = __bfloat1622float2(o2[e]);
+                s1 += f.x + f.y; s2 += f.x * f.x + f.y * f.y;
+              }
+              *reinterpret_cast<uint4*>(d + j) = *reinterpret_cast<const uint4*>(o2);
+            }
           }
         }
       }
-    }
-    if (p.dst_stats) {
-      if (p.bn == 1) {
-        const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
-        if (lane == 0 && n0 < p.B) { atomicAdd(p.dst_stats + 2 * n0, d1); atomicAdd(p.dst_stats + 2 * n0 + 1, d2); }
-      } else if (valid) {
-        atomicAdd(p.dst_stats + 2 * img, (double)s1); atomicAdd(p.dst_stats + 2 * img + 1, (double)s2);
+      // this warp is done reading the accumulator slot: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+      if (p.dst_stats) {
+        if (p.bn == 1) {
+          const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
+          const int im0 = (m / (p.tiles_x * p.tiles_y)) * p.bn;
+          if (lane == 0 && im0 < p.B) { atomicAdd(p.dst_stats + 2 * im0, d1); atomicAdd(p.dst_stats + 2 * im0 + 1, d2); }
+        } else if (valid) {
+          atomicAdd(p.dst_stats + 2 * img, (double)s1); atomicAdd(p.dst_stats + 2 * img + 1, (double)s2);
+        }
       }
     }
     tc_fence_before();
@@ -339,7 +387,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -407,7 +455,7 @@ static void choose_tile(int W, int H, int B, int stride, int* bw, int* bh, int* 
 
 template <int KC, int NT>
 static int launch_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t st) {
-  using S = TcSmem<KC, NT>;
+  using S = TcCfg<KC, NT>;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(tc_conv_kernel<KC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
@@ -471,7 +519,8 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   p.tiles_x = (p.W + p.bw - 1) / p.bw; p.tiles_y = (p.H + p.bh - 1) / p.bh;
   const int tiles_n = (p.B + p.bn - 1) / p.bn;
   const long mt = (long)p.tiles_x * p.tiles_y * tiles_n;
-  if (mt > 0x7fffffffL || p.Ntot / NT > 65535) { set_error("tc_conv: grid too large"); return -2; }
+  if (mt > 0x7fffffffL) { set_error("tc_conv: too many M tiles"); return -2; }
+  p.m_tiles = (int)mt;
   if (dry) return 0;
   CUtensorMap a0, a1, bm;
   int rc = make_act_map(&a0, src0, C0, p.srcW, p.srcH, p.B, KC, p.bw, p.bh, p.bn, p.stride);
@@ -481,7 +530,10 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   const int Ktot = p.nty * p.ntx * p.nchunk * KC;
   rc = make_w_map(&bm, w, Ktot, p.Ntot, KC, NT);
   if (rc) return rc;
-  dim3 grid((unsigned)mt, p.Ntot / NT, 1);
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  const long long items = (long long)mt * (p.Ntot / NT);
+  dim3 grid((unsigned)(items < n_sm ? items : n_sm), 1, 1);      // persistent: one CTA per SM
 #define INST(kc, nt) if (KC == kc && NT == nt) { rc = launch_inst<kc, nt>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
   INST(64, 16) INST(64, 64) INST(64, 128) INST(64, 256)
   INST(32, 256) INST(32, 128)

@@ -293,6 +293,14 @@ _CLS_TAPS = [[(ty, tx) for ty in range(3) for tx in range(3)
 (cy: 0 top row, 1 interior, 2 bottom row; same for cx)."""
 
 
+def _cls_mask(device) -> torch.Tensor:
+    m = torch.zeros(9, 3, 3)
+    for cls, taps in enumerate(_CLS_TAPS):
+        for (ty, tx) in taps:
+            m[cls, ty, tx] = 1.0
+    return m.to(device)
+
+
 def _round_up(v, m):
     return (v + m - 1) // m * m
 
@@ -317,11 +325,9 @@ def pack_tc_dense(w: torch.Tensor, bias, nt: int, gamma=None, beta=None):
         tg = torch.zeros(ncls, ntot, device=w.device); tb = torch.zeros(ncls, ntot, device=w.device)
         wb = (w * beta.float().view(1, ci, 1, 1)).sum(1)           # [co, 3, 3]
         wgs = wq32.sum(1)
-        for cls, taps in enumerate(_CLS_TAPS):
-            for (ty, tx) in taps:
-                tg[cls, :co] += wgs[:, ty, tx]
-                tb[cls, :co] += wb[:, ty, tx]
-            tb[cls, :co] += b
+        mask = _cls_mask(w.device)
+        tg[:, :co] = torch.einsum("cyx,nyx->cn", mask, wgs)
+        tb[:, :co] = torch.einsum("cyx,nyx->cn", mask, wb) + b.view(1, co)
     else:
         tg = torch.zeros(1, ntot, device=w.device); tb = torch.zeros(1, ntot, device=w.device)
         tg[0, :co] = wq32.sum((1, 2, 3))
@@ -340,6 +346,7 @@ def pack_tc_grouped(w: torch.Tensor, bias, groups: int, kc: int, gamma, beta):
     dev = w.device
     packed = torch.zeros(co, kh * kw, cg_eff, dtype=BF16, device=dev)
     tg = torch.zeros(9, co, device=dev); tb = torch.zeros(9, co, device=dev)
+    mask = _cls_mask(dev)
     for g in range(groups):
         cbase = (g * cg) // cg_eff * cg_eff
         off = g * cg - cbase
@@ -349,10 +356,8 @@ def pack_tc_grouped(w: torch.Tensor, bias, groups: int, kc: int, gamma, beta):
         packed[rows, :, off:off + cg] = wq.permute(0, 2, 3, 1).reshape(ng, kh * kw, cg)
         wgs = wq.float().sum(1)
         wb = (w[rows] * beta.float()[g * cg:(g + 1) * cg].view(1, cg, 1, 1)).sum(1)
-        for cls, taps in enumerate(_CLS_TAPS):
-            for (ty, tx) in taps:
-                tg[cls, rows] += wgs[:, ty, tx]
-                tb[cls, rows] += wb[:, ty, tx]
+        tg[:, rows] = torch.einsum("cyx,nyx->cn", mask, wgs)
+        tb[:, rows] = torch.einsum("cyx,nyx->cn", mask, wb)
     tb += bias.float().view(1, co)
     return packed.reshape(co, kh * kw * cg_eff).contiguous(), tb.contiguous(), tg.contiguous()
 
