@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define UCDIR_ABI_VERSION 5
+#define UCDIR_ABI_VERSION 6
 
 #define UCDIR_OP_NPTR 16
 #define UCDIR_OP_NINT 32
@@ -187,7 +187,9 @@ enum ucdir_tc_int {
   UCDIR_TC_I_GROUPS = 14, UCDIR_TC_I_KC = 15, UCDIR_TC_I_NT = 16, UCDIR_TC_I_GN = 17, UCDIR_TC_I_NCLS = 18,
   UCDIR_TC_I_ACT = 19, UCDIR_TC_I_MODE = 20, UCDIR_TC_I_DST_F32 = 21, UCDIR_TC_I_DST_C = 22,
   UCDIR_TC_I_DST_COFF = 23, UCDIR_TC_I_DST_UP = 24, UCDIR_TC_I_DST_PY = 25, UCDIR_TC_I_DST_PX = 26,
-  UCDIR_TC_I_RES_C = 27, UCDIR_TC_I_ATTW_STRIDE = 28
+  UCDIR_TC_I_RES_C = 27, UCDIR_TC_I_ATTW_STRIDE = 28,
+  UCDIR_TC_I_KB = 29,      /* K elements per weight slab row (0 = KC); grouped convs: max(Cin/groups, 16) */
+  UCDIR_TC_I_NSPLIT = 30   /* groups per NT-column work item that share one KC-channel activation slab (0 = 1) */
 };
 enum ucdir_tc_flt { UCDIR_TC_F_EPS = 0 };
 

@@ -305,9 +305,10 @@ def emu_tc_conv(op, mem):
     x = mem.view(_p(op, "UCDIR_TC_P_SRC0"), (B, sH, sW, C0), bf).float()
     if C1:
         x = torch.cat([x, mem.view(_p(op, "UCDIR_TC_P_SRC1"), (B, sH, sW, C1), bf).float()], dim=-1)
+    KB = g("KB") or KC
     if groups > 1:
         Cg, Ng = Cin // groups, Ntot // groups
-        cg_eff = max(Cg, KC)
+        cg_eff = max(Cg, KB)                                   # weight-row K per tap (pack_tc_grouped)
     else:
         Cg, Ng, cg_eff = Cin, Ntot, Cin
     ktap = cg_eff

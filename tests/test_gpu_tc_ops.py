@@ -119,8 +119,8 @@ def test_tc_grouped_mix(C, B, H, W):
     w = rnd(g, 8 * C, C // 8, 3, 3, scale=1.0 / np.sqrt(C // 8 * 9))
     bias = rnd(g, 8 * C, scale=0.1)
     gamma, beta = 1 + 0.3 * rnd(g, C), 0.2 * rnd(g, C)
-    kc = 64 if C >= 512 else (32 if C == 256 else 16)
-    wp, tb, tg = E.pack_tc_grouped(w, bias, 8, kc, gamma, beta)
+    kc, kb, nt, nsplit = E.tc_mix_tiling(C)
+    wp, tb, tg = E.pack_tc_grouped(w, bias, 8, kb, gamma, beta)
     c.add("w", wp).add("tb", tb).add("tg", tg).add("s0", stats_of(c.t["h1"]))
     c.add("att", rnd(g, B, H, W, 8)).add("attw", rnd(g, B, 8)).add("res", rnd(g, B, H, W, C).to(BF))
     c.add("dst", torch.zeros(B, H, W, C, dtype=BF)).add("dstats", torch.zeros(B, 2, dtype=torch.float64))
@@ -128,7 +128,7 @@ def test_tc_grouped_mix(C, B, H, W):
     def build(t):
         ol = E.OpList()
         E._tc_op(ol, src0=act(t["h1"], C, H, W, t["s0"]), w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), tg=t["tg"].data_ptr(),
-                 gn=1, ncls=9, groups=8, kc=kc, nt=min(C, 256), mode=1, att=t["att"].data_ptr(), attw=t["attw"].data_ptr(),
+                 gn=1, ncls=9, groups=8, kc=kc, kb=kb, nsplit=nsplit, nt=nt, mode=1, att=t["att"].data_ptr(), attw=t["attw"].data_ptr(),
                  attw_stride=8, res=act(t["res"], C, H, W), dst=act(t["dst"], C, H, W, t["dstats"]), ntot=8 * C, B=B)
         return ol
     host, dev = run_both(c, build)

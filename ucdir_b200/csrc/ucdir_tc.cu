@@ -134,10 +134,13 @@ struct TcParams {
 constexpr int TC_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 constexpr int TC_EPI_WARPS = 8;
 
-template <int KC, int NT>
+// KA: channels per A slab row (64/32/16 -> 128/64/32-byte swizzled rows); KB: K elements per B slab row;
+// NT: output columns per work item; NSPLIT: independent column groups of an item that read different K slices of
+// the same A slab (grouped convolution with small groups: 4 groups of 64 columns share one 32-channel A slab).
+template <int KA, int KB, int NT, int NSPLIT>
 struct TcCfg {
-  static constexpr int A_BYTES = 128 * KC * 2;
-  static constexpr int B_BYTES = NT * KC * 2;
+  static constexpr int A_BYTES = 128 * KA * 2;
+  static constexpr int B_BYTES = NT * KB * 2;
   static constexpr int B_PAD = (B_BYTES + 1023) & ~1023;
   static constexpr int STAGE = A_BYTES + B_PAD;
   static constexpr int STAGES_RAW = 196608 / STAGE;
@@ -147,15 +150,45 @@ struct TcCfg {
   static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + (2 * STAGES + 2 * NSLOT) * 8 + 64;
 };
 
-// Persistent CTA (one per SM).  Work item = (M tile, N sub-tile of NT columns); a CTA owns a contiguous range of
-// items, N fastest, so consecutive items re-read the same activation tile from L2.  Three pipelines:
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred;
+}
+
+// Work-item cursor shared by the three roles: items are (M tile, N sub-tile) pairs, N fastest; advancing is
+// increments and compares only (the producer issues one TMA pair per ~60 instructions, so divisions matter).
+struct ItemCursor {
+  int ns, tx_i, ty_i, tn_i;
+  __device__ __forceinline__ void init(long long it, int n_sub, int tiles_x, int tiles_y) {
+    const long long m = it / n_sub;
+    ns = (int)(it - m * n_sub);
+    tx_i = (int)(m % tiles_x);
+    const long long t = m / tiles_x;
+    ty_i = (int)(t % tiles_y);
+    tn_i = (int)(t / tiles_y);
+  }
+  __device__ __forceinline__ bool next(int n_sub, int tiles_x, int tiles_y) {   // returns true when the M tile changed
+    if (++ns < n_sub) return false;
+    ns = 0;
+    if (++tx_i == tiles_x) { tx_i = 0; if (++ty_i == tiles_y) { ty_i = 0; ++tn_i; } }
+    return true;
+  }
+};
+
+// Persistent CTA (one per SM).  A CTA owns a contiguous range of work items.  Three pipelines:
 //   smem ring   full[s]/empty[s]            TMA producer  <-> MMA issuer
 //   TMEM ring   tmem_full[j]/tmem_empty[j]  MMA issuer    <-> epilogue warps   (NSLOT accumulators of NT columns)
-template <int KC, int NT>
+template <int KA, int KB, int NT, int NSPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                 const __grid_constant__ CUtensorMap mapA1,
                                                                 const __grid_constant__ CUtensorMap mapB, const TcParams p) {
-  using S = TcCfg<KC, NT>;
+  using S = TcCfg<KA, KB, NT, NSPLIT>;
   constexpr int STAGES = S::STAGES, NSLOT = S::NSLOT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -169,7 +202,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   const int n_sub = p.Ntot / NT;
   const long long total = (long long)p.m_tiles * n_sub;
   const long long it0 = total * blockIdx.x / gridDim.x, it1 = total * (blockIdx.x + 1) / gridDim.x;
-  const int nslab = p.nty * p.ntx * p.nchunk;
+  const int n_items = (int)(it1 - it0);
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
@@ -188,57 +221,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(p.bw * p.bh * p.bn * KC * 2 + NT * KC * 2);
-      uint32_t gs = 0;                                  // global slab counter of this CTA (smem ring position)
-      for (long long it = it0; it < it1; ++it) {
-        const int m = (int)(it / n_sub), ns = (int)(it - (long long)m * n_sub);
-        const int tx_i = m % p.tiles_x, ty_i = (m / p.tiles_x) % p.tiles_y, tn_i = m / (p.tiles_x * p.tiles_y);
-        const int x0 = tx_i * p.bw, y0 = ty_i * p.bh, n0 = tn_i * p.bn;
-        const int ncol0 = ns * NT;
-        const int cgrp0 = p.groups > 1 ? ((ncol0 / p.Ng) * p.Cg) / p.cg_eff * p.cg_eff : 0;
-        for (int i = 0; i < nslab; ++i, ++gs) {
-          const int s = gs % STAGES;
-          const uint32_t ph = (gs / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          const int tap = i / p.nchunk, j = i - tap * p.nchunk;
-          const int ty = tap / p.ntx, tx = tap - ty * p.ntx;
-          uint8_t* sa = smem + s * S::STAGE;
-          uint8_t* sb = sa + S::A_BYTES;
-          mbar_expect_tx(&full[s], tx_bytes);
-          const int cx = x0 * p.stride + tx + p.ox0, cy = y0 * p.stride + ty + p.oy0;
-          if (p.groups > 1 || j < p.c0_chunks) tma_load_4d(&mapA0, &full[s], sa, cgrp0 + j * KC, cx, cy, n0);
-          else tma_load_4d(&mapA1, &full[s], sa, (j - p.c0_chunks) * KC, cx, cy, n0);
-          tma_load_2d(&mapB, &full[s], sb, i * KC, ncol0);
+    // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
+    const uint32_t tx_bytes = (uint32_t)(p.bw * p.bh * p.bn * KA * 2 + NT * KB * 2);
+    ItemCursor cur; cur.init(it0, n_sub, p.tiles_x, p.tiles_y);
+    int stage = 0; uint32_t phase = 0;
+    for (int li = 0; li < n_items; ++li) {
+      const int x0 = cur.tx_i * p.bw * p.stride + p.ox0, y0 = cur.ty_i * p.bh * p.stride + p.oy0, n0 = cur.tn_i * p.bn;
+      const int ncol0 = cur.ns * NT;
+      const int cgrp0 = p.groups > 1 ? ((ncol0 / p.Ng) * p.Cg) / p.cg_eff * p.cg_eff : 0;
+      int kb = 0;                                       // K coordinate of the B slab
+      for (int ty = 0; ty < p.nty; ++ty) {
+        for (int tx = 0; tx < p.ntx; ++tx) {
+          for (int j = 0; j < p.nchunk; ++j, kb += KB) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one()) {
+              uint8_t* sa = smem + stage * S::STAGE;
+              mbar_expect_tx(&full[stage], tx_bytes);
+              if (p.groups > 1 || j < p.c0_chunks) tma_load_4d(&mapA0, &full[stage], sa, cgrp0 + j * KA, x0 + tx, y0 + ty, n0);
+              else tma_load_4d(&mapA1, &full[stage], sa, (j - p.c0_chunks) * KA, x0 + tx, y0 + ty, n0);
+              tma_load_2d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
+      cur.next(n_sub, p.tiles_x, p.tiles_y);
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      uint32_t gs = 0, li = 0;
-      for (long long it = it0; it < it1; ++it, ++li) {
-        const int slot = li % NSLOT;
-        const uint32_t sph = (li / NSLOT) & 1;
-        mbar_wait(&tmem_empty[slot], sph ^ 1);          // epilogue has drained this accumulator
+    // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====================
+    constexpr int NSUB = NT / NSPLIT;                   // columns per MMA
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NSUB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr int KSTEPS = KB / 16;
+    constexpr int CGS = KA / NSPLIT;                    // channels of the A slab that belong to one split
+    const int nslab = p.nty * p.ntx * p.nchunk;
+    int stage = 0; uint32_t phase = 0;
+    int slot = 0; uint32_t sph = 0;
+    for (int li = 0; li < n_items; ++li) {
+      mbar_wait(&tmem_empty[slot], sph ^ 1);            // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(slot * S::SLOTW);
+      for (int i = 0; i < nslab; ++i) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)(slot * S::SLOTW);
-        for (int i = 0; i < nslab; ++i, ++gs) {
-          const int s = gs % STAGES;
-          const uint32_t ph = (gs / STAGES) & 1;
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * S::STAGE), sb = sa + S::A_BYTES;
-          const uint64_t ad = make_desc(sa, KC * 2), bd = make_desc(sb, KC * 2);
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE), sb = sa + S::A_BYTES;
+          const uint64_t ad = make_desc(sa, KA * 2), bd = make_desc(sb, KB * 2);
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k)
-            umma_bf16(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (i | k) != 0);
-          umma_commit(&empty[s]);            // frees the smem slot once these MMAs have read it
+          for (int sp = 0; sp < NSPLIT; ++sp) {
+            // split sp reads the 16-element K slice that holds its CGS channels, and its own rows of the B slab
+            const uint32_t a_off = NSPLIT > 1 ? (uint32_t)((sp * CGS) / 16) * 32u : 0u;
+            const uint32_t b_off = (uint32_t)(sp * NSUB * KB * 2);
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              umma_bf16(tacc + (uint32_t)(sp * NSUB), ad + (uint64_t)((a_off + k * 32) >> 4), bd + (uint64_t)((b_off + k * 32) >> 4), idesc,
+                        (i | k) != 0);
+          }
+          umma_commit(&empty[stage]);          // frees the smem slot once these MMAs have read it
+          if (i == nslab - 1) umma_commit(&tmem_full[slot]);   // accumulator of this item complete
         }
-        umma_commit(&tmem_full[slot]);       // accumulator of this item complete
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++slot == NSLOT) { slot = 0; sph ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -249,22 +294,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     const int nn = r / box, rr = r - nn * box;
     const int yy = rr / p.bw, xx = rr - yy * p.bw;
     constexpr int CH = NT < 32 ? 16 : 32;
-    uint32_t li = 0;
-    int m_prev = -1;
+    ItemCursor cur; cur.init(it0, n_sub, p.tiles_x, p.tiles_y);
+    bool new_m = true;
     bool valid = false;
     int img = 0, y = 0, x = 0, cls = 0;
     float rstd = 1.f, mr = 0.f;
     size_t pix_in = 0, pix_out = 0;
     float aw[8];
-    for (long long it = it0; it < it1; ++it, ++li) {
-      const int m = (int)(it / n_sub), ns = (int)(it - (long long)m * n_sub);
-      const int ncol0 = ns * NT;
-      const int slot = li % NSLOT;
-      const uint32_t sph = (li / NSLOT) & 1;
-      if (m != m_prev) {                              // per-pixel state changes only with the M tile
-        m_prev = m;
-        const int tx_i = m % p.tiles_x, ty_i = (m / p.tiles_x) % p.tiles_y, tn_i = m / (p.tiles_x * p.tiles_y);
-        img = tn_i * p.bn + nn; y = ty_i * p.bh + yy; x = tx_i * p.bw + xx;
+    float s1 = 0.f, s2 = 0.f;                        // GroupNorm statistics of what this thread stored, current image
+    int stat_img = -1;
+    int slot = 0; uint32_t sph = 0;
+    for (int li = 0; li < n_items; ++li) {
+      const int ncol0 = cur.ns * NT;
+      if (new_m) {                                    // per-pixel state changes only with the M tile
+        const int im0 = cur.tn_i * p.bn;
+        if (p.dst_stats && p.bn == 1 && im0 != stat_img) {
+          if (stat_img >= 0) {
+            const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
+            if (lane == 0) { atomicAdd(p.dst_stats + 2 * stat_img, d1); atomicAdd(p.dst_stats + 2 * stat_img + 1, d2); }
+          }
+          stat_img = im0; s1 = 0.f; s2 = 0.f;
+        }
+        img = im0 + nn; y = cur.ty_i * p.bh + yy; x = cur.tx_i * p.bw + xx;
         valid = (r < box * p.bn) && img < p.B && y < p.H && x < p.W;
         rstd = 1.f; mr = 0.f; cls = 0;
         if (!valid) { img = 0; y = 0; x = 0; }
@@ -285,7 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       }
       const float* tb = p.tb + (size_t)cls * p.Ntot + ncol0;
       const float* tg = p.tg ? p.tg + (size_t)cls * p.Ntot + ncol0 : nullptr;
-      float s1 = 0.f, s2 = 0.f;
+      float t1s = 0.f, t2s = 0.f;
       mbar_wait(&tmem_full[slot], sph);
       tc_fence_after();
 #pragma unroll 1
@@ -323,7 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             const float t = swish_f(h) + __bfloat162float(rres[c]);
             o[c] = __float2bfloat16(t);
             const float tr = __bfloat162float(o[c]);
-            s1 += tr; s2 += tr * tr;
+            t1s += tr; t2s += tr * tr;
           }
           __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix_out * p.dstC + p.dstCoff + cbase;
           if (NO == 4) *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(o);
@@ -351,7 +402,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             float* d = reinterpret_cast<float*>(p.dst) + pix_out * p.dstC + p.dstCoff + nb;
 #pragma unroll
             for (int j = 0; j < CH; ++j)
-              if (nb + j < p.ncol_valid) { d[j] = v[j]; s1 += v[j]; s2 += v[j] * v[j]; }
+              if (nb + j < p.ncol_valid) { d[j] = v[j]; t1s += v[j]; t2s += v[j] * v[j]; }
           } else {
             __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix_out * p.dstC + p.dstCoff + nb;
 #pragma unroll
@@ -361,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               for (int e = 0; e < 4; ++e) {
                 o2[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
                 const float2 f = __bfloat1622float2(o2[e]);
-                s1 += f.x + f.y; s2 += f.x * f.x + f.y * f.y;
+                t1s += f.x + f.y; t2s += f.x * f.x + f.y * f.y;
               }
               *reinterpret_cast<uint4*>(d + j) = *reinterpret_cast<const uint4*>(o2);
             }
@@ -372,15 +423,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+      if (++slot == NSLOT) { slot = 0; sph ^= 1; }
       if (p.dst_stats) {
-        if (p.bn == 1) {
-          const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
-          const int im0 = (m / (p.tiles_x * p.tiles_y)) * p.bn;
-          if (lane == 0 && im0 < p.B) { atomicAdd(p.dst_stats + 2 * im0, d1); atomicAdd(p.dst_stats + 2 * im0 + 1, d2); }
-        } else if (valid) {
-          atomicAdd(p.dst_stats + 2 * img, (double)s1); atomicAdd(p.dst_stats + 2 * img + 1, (double)s2);
-        }
+        if (p.bn == 1) { s1 += t1s; s2 += t2s; }      // flushed when the image changes / at the end
+        else if (valid) { atomicAdd(p.dst_stats + 2 * img, (double)t1s); atomicAdd(p.dst_stats + 2 * img + 1, (double)t2s); }
       }
+      new_m = cur.next(n_sub, p.tiles_x, p.tiles_y);
+    }
+    if (p.dst_stats && p.bn == 1 && stat_img >= 0) {
+      const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
+      if (lane == 0) { atomicAdd(p.dst_stats + 2 * stat_img, d1); atomicAdd(p.dst_stats + 2 * stat_img + 1, d2); }
     }
     tc_fence_before();
   }
@@ -453,16 +505,16 @@ static void choose_tile(int W, int H, int B, int stride, int* bw, int* bh, int* 
   *bw = bbw; *bh = bbh; *bn = bbn;
 }
 
-template <int KC, int NT>
+template <int KA, int KB, int NT, int NSPLIT>
 static int launch_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t st) {
-  using S = TcCfg<KC, NT>;
+  using S = TcCfg<KA, KB, NT, NSPLIT>;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(tc_conv_kernel<KC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tc_conv_kernel<KA, KB, NT, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
       set_error("tc_conv: cannot opt in to %d bytes of shared memory: %s", S::TOTAL, cudaGetErrorString(cudaGetLastError())); return -3; }
     attr = true;
   }
-  tc_conv_kernel<KC, NT><<<grid, TC_THREADS, S::TOTAL, st>>>(a0, a1, b, p);
+  tc_conv_kernel<KA, KB, NT, NSPLIT><<<grid, TC_THREADS, S::TOTAL, st>>>(a0, a1, b, p);
   return 0;
 }
 
@@ -480,6 +532,7 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   p.nty = op.i[UCDIR_TC_I_NTY]; p.ntx = op.i[UCDIR_TC_I_NTX]; p.oy0 = op.i[UCDIR_TC_I_OY0]; p.ox0 = op.i[UCDIR_TC_I_OX0];
   p.stride = op.i[UCDIR_TC_I_STRIDE]; p.groups = op.i[UCDIR_TC_I_GROUPS];
   const int KC = op.i[UCDIR_TC_I_KC], NT = op.i[UCDIR_TC_I_NT];
+  const int KB = op.i[UCDIR_TC_I_KB] ? op.i[UCDIR_TC_I_KB] : KC, NSPLIT = op.i[UCDIR_TC_I_NSPLIT] ? op.i[UCDIR_TC_I_NSPLIT] : 1;
   p.gn = op.i[UCDIR_TC_I_GN]; p.ncls = op.i[UCDIR_TC_I_NCLS]; p.act = op.i[UCDIR_TC_I_ACT]; p.mode = op.i[UCDIR_TC_I_MODE];
   p.dst_f32 = op.i[UCDIR_TC_I_DST_F32];
   p.dstC = op.i[UCDIR_TC_I_DST_C]; p.dstCoff = op.i[UCDIR_TC_I_DST_COFF]; p.dstUp = op.i[UCDIR_TC_I_DST_UP];
@@ -495,12 +548,18 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   if (p.groups > 1) {
     if (C1 || Cin % p.groups || p.Ntot % p.groups) { set_error("tc_conv: bad grouped config"); return -2; }
     p.Cg = Cin / p.groups; p.Ng = p.Ntot / p.groups;
-    p.cg_eff = p.Cg > KC ? p.Cg : KC;
-    if (p.cg_eff % KC || Cin % p.cg_eff || p.Ng % NT) { set_error("tc_conv: grouped conv needs KC | max(Cg,KC) | Cin and NT | Cout/groups"); return -2; }
+    // an item of NT columns covers max(1, NT/Ng) groups; its A slab holds their KC consecutive channels
+    const int gpi = NT > p.Ng ? NT / p.Ng : 1;
+    if ((NT > p.Ng ? NT % p.Ng : p.Ng % NT) || gpi != NSPLIT) { set_error("tc_conv: grouped conv needs NT/Ng = NSPLIT (NT=%d Ng=%d NSPLIT=%d)", NT, p.Ng, NSPLIT); return -2; }
+    p.cg_eff = p.Cg * gpi > KC ? p.Cg * gpi : KC;
+    if (p.cg_eff % KC || Cin % p.cg_eff) { set_error("tc_conv: grouped conv needs KC | max(Cg*NSPLIT, KC) | Cin"); return -2; }
+    if (KB != (p.Cg > 16 ? p.Cg : 16) && !(NSPLIT == 1 && KB == KC)) { set_error("tc_conv: grouped conv needs KB = max(Cg, 16)"); return -2; }
     p.nchunk = p.cg_eff / KC; p.c0_chunks = p.nchunk;
+    if (NSPLIT > 1 && p.nchunk != 1) { set_error("tc_conv: split items need one chunk per tap"); return -2; }
   } else {
     if (C0 % KC || C1 % KC) { set_error("tc_conv: C0=%d / C1=%d must be multiples of KC=%d", C0, C1, KC); return -2; }
     if (C1 > 0 && !src1) { set_error("tc_conv: null src1"); return -1; }
+    if (NSPLIT != 1 || KB != KC) { set_error("tc_conv: dense conv needs NSPLIT = 1 and KB = KC"); return -2; }
     p.Cg = Cin; p.Ng = p.Ntot; p.cg_eff = Cin; p.nchunk = Cin / KC; p.c0_chunks = C0 / KC;
   }
   if (p.Ntot % NT) { set_error("tc_conv: Ntot=%d not a multiple of NT=%d", p.Ntot, NT); return -2; }
@@ -527,19 +586,19 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   if (rc) return rc;
   if (C1 > 0) { rc = make_act_map(&a1, src1, C1, p.srcW, p.srcH, p.B, KC, p.bw, p.bh, p.bn, p.stride); if (rc) return rc; }
   else a1 = a0;
-  const int Ktot = p.nty * p.ntx * p.nchunk * KC;
-  rc = make_w_map(&bm, w, Ktot, p.Ntot, KC, NT);
+  const int Ktot = p.nty * p.ntx * p.nchunk * KB;
+  rc = make_w_map(&bm, w, Ktot, p.Ntot, KB, NT);
   if (rc) return rc;
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
   const long long items = (long long)mt * (p.Ntot / NT);
   dim3 grid((unsigned)(items < n_sm ? items : n_sm), 1, 1);      // persistent: one CTA per SM
-#define INST(kc, nt) if (KC == kc && NT == nt) { rc = launch_inst<kc, nt>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
-  INST(64, 16) INST(64, 64) INST(64, 128) INST(64, 256)
-  INST(32, 256) INST(32, 128)
-  INST(16, 64) INST(16, 128)
+#define INST(ka, kb, nt, ns) if (KC == ka && KB == kb && NT == nt && NSPLIT == ns) { rc = launch_inst<ka, kb, nt, ns>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
+  INST(64, 64, 16, 1) INST(64, 64, 64, 1) INST(64, 64, 128, 1) INST(64, 64, 256, 1)
+  INST(16, 16, 64, 1)
+  INST(32, 16, 256, 4) INST(32, 16, 256, 2) INST(32, 32, 256, 1)
 #undef INST
-  set_error("tc_conv: no kernel instance for KC=%d NT=%d", KC, NT);
+  set_error("tc_conv: no kernel instance for KC=%d KB=%d NT=%d NSPLIT=%d", KC, KB, NT, NSPLIT);
   return -2;
 }
 

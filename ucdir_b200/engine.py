@@ -394,7 +394,7 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
            src1: Optional[Act] = None, tg: int = 0, gn: int = 0, ncls: int = 1, nty: int = 3, ntx: int = 3, oy0: int = -1,
            ox0: int = -1, stride: int = 1, groups: int = 1, act: int = 0, mode: int = 0, res: Optional[Act] = None,
            att: int = 0, attw: int = 0, attw_stride: int = 0, dst_f32: int = 0, ncol_valid: int = 0, dst_up: int = 0,
-           dst_py: int = 0, dst_px: int = 0, eps: float = 1e-5):
+           dst_py: int = 0, dst_px: int = 0, eps: float = 1e-5, kb: int = 0, nsplit: int = 1):
     H, W = (dst.H // 2, dst.W // 2) if dst_up else (dst.H, dst.W)
     p = {"UCDIR_TC_P_SRC0": src0.ptr, "UCDIR_TC_P_W": w, "UCDIR_TC_P_TB": tb, "UCDIR_TC_P_DST": dst.ptr}
     if src1 is not None: p["UCDIR_TC_P_SRC1"] = src1.ptr
@@ -413,8 +413,17 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
          "UCDIR_TC_I_NT": nt, "UCDIR_TC_I_GN": gn, "UCDIR_TC_I_NCLS": ncls, "UCDIR_TC_I_ACT": act, "UCDIR_TC_I_MODE": mode,
          "UCDIR_TC_I_DST_F32": dst_f32, "UCDIR_TC_I_DST_C": dst.C, "UCDIR_TC_I_DST_COFF": 0, "UCDIR_TC_I_DST_UP": dst_up,
          "UCDIR_TC_I_DST_PY": dst_py, "UCDIR_TC_I_DST_PX": dst_px, "UCDIR_TC_I_RES_C": res.C if res is not None else 0,
-         "UCDIR_TC_I_ATTW_STRIDE": attw_stride}
+         "UCDIR_TC_I_ATTW_STRIDE": attw_stride, "UCDIR_TC_I_KB": kb or kc, "UCDIR_TC_I_NSPLIT": nsplit}
     ol.add("UCDIR_OP_TC_CONV", p, i, {"UCDIR_TC_F_EPS": eps})
+
+
+def tc_mix_tiling(cout: int):
+    """(KC, KB, NT, NSPLIT) of the grouped spdyconv + mix op for C = cout (8 groups of C/8 channels -> 8 x C
+    columns): a 256-column work item covers 256/C groups which share one 32-channel activation slab."""
+    cg = cout // 8
+    if cout >= 512:
+        return 64, 64, 256, 1
+    return 32, max(cg, 16), 256, max(256 // cout, 1)
 
 
 class _Builder:
@@ -712,8 +721,8 @@ class UNetEngine:
             rb = layer.res_block
             cout = rb.dim_out
             put3(name + ".conv1", pack_tc_dense(rb.conv1.weight, rb.conv1.bias, _tc_nt(cout), rb.norm1.weight, rb.norm1.bias))
-            kc = 64 if cout >= 512 else (32 if cout == 256 else 16)
-            put3(name + ".spdy", pack_tc_grouped(rb.spdyconv.weight, rb.spdyconv.bias, rb.nset, kc, rb.norm2.weight, rb.norm2.bias))
+            put3(name + ".spdy", pack_tc_grouped(rb.spdyconv.weight, rb.spdyconv.bias, rb.nset, tc_mix_tiling(cout)[1],
+                                                 rb.norm2.weight, rb.norm2.bias))
             if isinstance(rb.res_conv, torch.nn.Conv2d):
                 put3(name + ".res", pack_tc_dense(rb.res_conv.weight, rb.res_conv.bias, _tc_nt(cout)))
             if layer.with_attn:
@@ -766,9 +775,9 @@ class UNetEngine:
                     raise RuntimeError("identity residual with a concatenated input")
                 res, own_res = x, False
             out = bld.new(cout, x.H, x.W)
-            kc = 64 if cout >= 512 else (32 if cout == 256 else 16)
+            kc, kb, mnt, nsplit = tc_mix_tiling(cout)
             _tc_op(ol, src0=h1, w=ws.ptr(name + ".spdy.tcw"), tb=ws.ptr(name + ".spdy.tb"), tg=ws.ptr(name + ".spdy.tg"),
-                   gn=1, ncls=9, groups=rb.nset, kc=kc, nt=min(cout, 256), mode=1, att=gmaps[k].data_ptr(),
+                   gn=1, ncls=9, groups=rb.nset, kc=kc, kb=kb, nsplit=nsplit, nt=mnt, mode=1, att=gmaps[k].data_ptr(),
                    attw=attw.data_ptr() + k * 8 * 4, attw_stride=attw_stride, res=res, dst=out, ntot=cout * rb.nset, B=BT)
             bld.release(h1)
             if own_res:
