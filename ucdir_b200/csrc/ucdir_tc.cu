@@ -150,6 +150,10 @@ struct TcCfg {
   static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + (2 * STAGES + 2 * NSLOT) * 8 + 64;
 };
 
+// bf16 path: the result is rounded to 8 mantissa bits, so MUFU.EX2 / MUFU.RCP accuracy is ample (5 instructions
+// instead of ~20 for the IEEE division of the fp32 parity path's swish_f).
+__device__ __forceinline__ float swish_fast(float x) { return x * __frcp_rn(1.0f + __expf(-x)); }
+
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile(
@@ -303,6 +307,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     float aw[8];
     float s1 = 0.f, s2 = 0.f;                        // GroupNorm statistics of what this thread stored, current image
     int stat_img = -1;
+    int gn_img = -1; float gn_rstd = 1.f, gn_mr = 0.f;   // GroupNorm scalars of the last image seen (FP64 math, cached)
     int slot = 0; uint32_t sph = 0;
     for (int li = 0; li < n_items; ++li) {
       const int ncol0 = cur.ns * NT;
@@ -320,8 +325,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         rstd = 1.f; mr = 0.f; cls = 0;
         if (!valid) { img = 0; y = 0; x = 0; }
         if (p.gn && valid) {
-          GnScalars sc = gn_scalars(p.stats0, p.stats1, img, p.gn_count, p.eps);
-          rstd = sc.rstd; mr = sc.mean * sc.rstd;
+          if (img != gn_img) {
+            GnScalars sc = gn_scalars(p.stats0, p.stats1, img, p.gn_count, p.eps);
+            gn_img = img; gn_rstd = sc.rstd; gn_mr = sc.mean * sc.rstd;
+          }
+          rstd = gn_rstd; mr = gn_mr;
           if (p.ncls == 9) cls = (y == 0 ? 0 : (y == p.H - 1 ? 2 : 1)) * 3 + (x == 0 ? 0 : (x == p.W - 1 ? 2 : 1));
         }
         pix_in = ((size_t)img * p.H + y) * p.W + x;
@@ -341,37 +349,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = half * CH; c0 < NT; c0 += 2 * CH) {
+        // issue the global loads this chunk needs (residual, epilogue tables) before waiting on the TMEM load
+        constexpr int NO = CH / 8;
+        uint2 res_mix = make_uint2(0u, 0u);
+        uint4 res_pl[CH / 8];
+        float v[CH];                                  // starts as the per-column additive term, then the folded value
+        if (valid) {
+          if (p.mode == 1) {
+            const __nv_bfloat16* rp = p.res + pix_in * p.resC + ((ncol0 + c0) >> 3);
+            if (NO == 4) res_mix = __ldg(reinterpret_cast<const uint2*>(rp));
+            else res_mix.x = __ldg(reinterpret_cast<const uint32_t*>(rp));
+          } else if (p.res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix_in * p.resC + ncol0 + c0);
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) res_pl[j] = __ldg(rp + j);
+          }
+#pragma unroll
+          for (int j = 0; j < CH; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(tb + c0 + j));
+            if (tg) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(tg + c0 + j));
+              v[j + 0] = fmaf(-mr, g.x, b.x); v[j + 1] = fmaf(-mr, g.y, b.y); v[j + 2] = fmaf(-mr, g.z, b.z); v[j + 3] = fmaf(-mr, g.w, b.w);
+            } else { v[j + 0] = b.x; v[j + 1] = b.y; v[j + 2] = b.z; v[j + 3] = b.w; }
+          }
+        }
         uint32_t rv[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * S::SLOTW + c0);
         if (CH == 32) tmem_ld32(taddr, rv); else tmem_ld16(taddr, rv);
         tmem_ld_wait();
         if (!valid) continue;
-        float v[CH];
 #pragma unroll
-        for (int j = 0; j < CH; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(tb + c0 + j));
-          float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (tg) g4 = __ldg(reinterpret_cast<const float4*>(tg + c0 + j));
-          v[j + 0] = fmaf(__uint_as_float(rv[j + 0]), rstd, fmaf(-mr, g4.x, b4.x));
-          v[j + 1] = fmaf(__uint_as_float(rv[j + 1]), rstd, fmaf(-mr, g4.y, b4.y));
-          v[j + 2] = fmaf(__uint_as_float(rv[j + 2]), rstd, fmaf(-mr, g4.z, b4.z));
-          v[j + 3] = fmaf(__uint_as_float(rv[j + 3]), rstd, fmaf(-mr, g4.w, b4.w));
-        }
+        for (int j = 0; j < CH; ++j) v[j] = fmaf(__uint_as_float(rv[j]), rstd, v[j]);
         if (p.mode == 1) {
           // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
-          constexpr int NO = CH / 8;
           const int cbase = (ncol0 + c0) >> 3;
           __align__(8) __nv_bfloat16 o[NO];
-          const __nv_bfloat16* rp = p.res + pix_in * p.resC + cbase;
-          __align__(8) __nv_bfloat16 rres[NO];
-          if (NO == 4) *reinterpret_cast<uint2*>(rres) = __ldg(reinterpret_cast<const uint2*>(rp));
-          else *reinterpret_cast<uint32_t*>(rres) = __ldg(reinterpret_cast<const uint32_t*>(rp));
+          const __nv_bfloat16* rres = reinterpret_cast<const __nv_bfloat16*>(&res_mix);
 #pragma unroll
           for (int c = 0; c < NO; ++c) {
             float h = 0.f;
 #pragma unroll
             for (int s = 0; s < 8; ++s) h = fmaf(v[c * 8 + s], aw[s], h);
-            const float t = swish_f(h) + __bfloat162float(rres[c]);
+            const float t = swish_fast(h) + __bfloat162float(rres[c]);
             o[c] = __float2bfloat16(t);
             const float tr = __bfloat162float(o[c]);
             t1s += tr; t2s += tr * tr;
@@ -383,14 +402,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           const int nb = ncol0 + c0;
           if (p.act == 1) {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = swish_f(v[j]);
+            for (int j = 0; j < CH; ++j) v[j] = swish_fast(v[j]);
           }
           if (p.res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix_in * p.resC + nb);
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
-              const uint4 u = __ldg(rp + j / 8);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&res_pl[j / 8]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 f = __bfloat1622float2(h2[e]);
