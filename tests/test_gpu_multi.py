@@ -1,0 +1,67 @@
+"""Multi-GPU (NCCL) check, skipped unless the box has >= 2 GPUs: the tile-sharded step (each rank computes
+its slice of the 121 tiles, one all_gather_into_tensor per step) must equal the unsharded step."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["UCDIR_ROOT"])
+import ucdir_b200
+from ucdir_b200.model.networks import define_G
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+for precision in ("fp32", "bf16"):
+    os.environ["UCDIR_PRECISION"] = precision
+    torch.manual_seed(1234)
+    net = define_G({"model": ucdir_b200.SID_MODEL_OPT}).to(dev)
+    net.set_new_noise_schedule(ucdir_b200.SID_VAL_SCHEDULE, dev)
+    unet = net.denoise_fn
+    unet.tile_skip, unet.tile_padding, unet.tile_trigger = 128, 16, 0
+    g = torch.Generator().manual_seed(3)
+    x_in = (torch.rand(1, 3, 512, 640, generator=g) * 2 - 1).to(dev)
+    guide = (torch.rand(1, 3, 512, 640, generator=g) * 2 - 1).to(dev)
+    x_t = torch.randn(1, 3, 512, 640, generator=g).to(dev)
+    z = torch.randn(1, 3, 512, 640, generator=g).to(dev)
+    net._noise_source = lambda shape: z
+    os.environ["UCDIR_SHARD"] = "tiles"
+    a = net.p_sample(x_t, 20, condition_x=x_in, kwargs={"guide": guide})
+    sess = next(iter(unet.engine()._sessions.values()))
+    assert sess.world == world and sess.group is not None
+    unet.engine()._sessions.clear()
+    os.environ["UCDIR_SHARD"] = "none"
+    b = net.p_sample(x_t, 20, condition_x=x_in, kwargs={"guide": guide})
+    sess = next(iter(unet.engine()._sessions.values()))
+    assert sess.world == 1
+    err = (a - b).abs().max().item()
+    # per-tile arithmetic is rank independent; only the fp64 atomic order of the GroupNorm sums can differ
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    print("rank", rank, precision, "sharded vs unsharded max abs diff", err)
+    assert err <= tol, err
+    gathered = [torch.empty_like(a) for _ in range(world)]
+    dist.all_gather(gathered, a)
+    assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree after the all-gather"
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sharded_equals_unsharded_nccl():
+    n = min(torch.cuda.device_count(), 8)
+    env = dict(os.environ, UCDIR_ROOT=ROOT)
+    path = os.path.join(ROOT, "gpurun_out", "_multi_worker.py")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    open(path, "w").write(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29611", path]
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:]
