@@ -231,6 +231,7 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     launches0 = _lib.launch_count()
+    sess.time_collective = world > 1
     _lib.profile_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -239,6 +240,8 @@ def run_ours(args):
     ev1.record()
     barrier()
     prof = _lib.profile_end()
+    sess.time_collective = False
+    coll_ms = sum(a.elapsed_time(b) for a, b in sess.collective_events) / max(args.steps, 1)
     launches = _lib.launch_count() - launches0
     ms_total = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
@@ -322,6 +325,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": out_pin.numel() * 4, "steps": e_steps,
                 "api": "GaussianDiffusion.p_sample(x_host->dev, t, condition_x, guide) -> host"},
         "gpu_launches": int(launches),
+        "collective": None if world == 1 else {"kind": "NCCL all_gather_into_tensor of tile interiors, 1 per step",
+                                               "bytes_total_per_step": int(sess.eps.numel() * 4), "ms_per_step": round(coll_ms, 3)},
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clk,

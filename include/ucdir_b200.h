@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define UCDIR_ABI_VERSION 6
+#define UCDIR_ABI_VERSION 7
 
 #define UCDIR_OP_NPTR 16
 #define UCDIR_OP_NINT 32
@@ -64,7 +64,8 @@ enum ucdir_op_kind {
   UCDIR_OP_TC_CONV = 10,
   UCDIR_OP_TC_ATTN = 11,
   UCDIR_OP_GN_APPLY_BF16 = 12,
-  UCDIR_OP_CAST = 13
+  UCDIR_OP_CAST = 13,
+  UCDIR_OP_CROP_TILES = 14
 };
 
 /* ---- UCDIR_OP_CONV_F32: dst = epilogue( conv( prologue(concat(src0, src1)) ) ) -----------------
@@ -198,6 +199,12 @@ enum ucdir_gna_ptr { UCDIR_GNA_P_SRC = 0, UCDIR_GNA_P_DST = 1, UCDIR_GNA_P_GAMMA
 enum ucdir_gna_int { UCDIR_GNA_I_B = 0, UCDIR_GNA_I_HW = 1, UCDIR_GNA_I_C = 2, UCDIR_GNA_I_SWISH = 3 };
 
 /* ---- UCDIR_OP_CAST: p[1][k] = cast(p[0][k]) for k < i[0] + (i[1] << 31); i[2] = 0: fp32 -> bf16, 1: bf16 -> fp32 -- */
+
+/* ---- UCDIR_OP_CROP_TILES: DST[BT,IH,IW,4] = SRC[BT,TH,TW,4][:, OY:OY+IH, OX:OX+IW] (fp32): the tile interiors that are
+ * stitched (utils/util.py:144-145) and, in tile-sharded mode, all-gathered once per step ------------------------ */
+enum ucdir_crop_ptr { UCDIR_CROP_P_SRC = 0, UCDIR_CROP_P_DST = 1 };
+enum ucdir_crop_int { UCDIR_CROP_I_BT = 0, UCDIR_CROP_I_TH = 1, UCDIR_CROP_I_TW = 2, UCDIR_CROP_I_IH = 3, UCDIR_CROP_I_IW = 4,
+                      UCDIR_CROP_I_OY = 5, UCDIR_CROP_I_OX = 6 };
 
 /* ---- UCDIR_OP_MEMSET: cudaMemsetAsync(p[0], 0, i[0] + (i[1] << 31)) ------------------------------------ */
 

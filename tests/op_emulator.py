@@ -405,12 +405,19 @@ def emu_cast(op, mem):
         mem.view(int(op.p[1]), (n,)).copy_(mem.view(int(op.p[0]), (n,), torch.bfloat16).float())
 
 
+def emu_crop(op, mem):
+    g = lambda n: _i(op, "UCDIR_CROP_I_" + n)
+    BT, TH, TW, IH, IW, OY, OX = g("BT"), g("TH"), g("TW"), g("IH"), g("IW"), g("OY"), g("OX")
+    src = mem.view(_p(op, "UCDIR_CROP_P_SRC"), (BT, TH, TW, 4))
+    mem.view(_p(op, "UCDIR_CROP_P_DST"), (BT, IH, IW, 4)).copy_(src[:, OY:OY + IH, OX:OX + IW])
+
+
 DISPATCH = {
     K["UCDIR_OP_CONV_F32"]: emu_conv, K["UCDIR_OP_SGEMM_F32"]: emu_sgemm, K["UCDIR_OP_SOFTMAX_F32"]: emu_softmax,
     K["UCDIR_OP_GUIDANCE"]: emu_guidance, K["UCDIR_OP_TIME_EMBED"]: emu_time_embed,
     K["UCDIR_OP_GATHER_TILES"]: emu_gather, K["UCDIR_OP_SCATTER"]: emu_scatter, K["UCDIR_OP_MAXPOOL2"]: emu_maxpool,
     K["UCDIR_OP_MEMSET"]: emu_memset, K["UCDIR_OP_TC_CONV"]: emu_tc_conv, K["UCDIR_OP_GN_APPLY_BF16"]: emu_gn_apply,
-    K["UCDIR_OP_CAST"]: emu_cast,
+    K["UCDIR_OP_CAST"]: emu_cast, K["UCDIR_OP_CROP_TILES"]: emu_crop,
 }
 
 LAUNCHED = []

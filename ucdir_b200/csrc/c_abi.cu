@@ -43,6 +43,7 @@ static int dispatch(const ucdir_op_t& op, cudaStream_t st, bool dry) {
     case UCDIR_OP_TC_ATTN: return launch_tc_attn(op, st, dry);
     case UCDIR_OP_GN_APPLY_BF16: return launch_gn_apply_bf16(op, st, dry);
     case UCDIR_OP_CAST: return launch_cast(op, st, dry);
+    case UCDIR_OP_CROP_TILES: return launch_crop_tiles(op, st, dry);
     default: set_error("unknown op kind %d", op.kind); return -1;
   }
 }

@@ -277,4 +277,32 @@ int launch_scatter(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tile interior crop: DST[BT, IH, IW, 4] = SRC[BT, TH, TW, 4][:, OY:OY+IH, OX:OX+IW]  (fp32, float4 per pixel).
+// Only the interiors of the tiles are ever stitched (utils/util.py:144-145), so only they travel in the
+// per-step all-gather of the tile-sharded mode.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) crop_tiles_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int BT, int TH,
+                                                         int TW, int IH, int IW, int OY, int OX) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)BT * IH * IW;
+  if (idx >= total) return;
+  int x = idx % IW; size_t t = idx / IW;
+  int y = t % IH; int b = t / IH;
+  dst[idx] = __ldg(src + ((size_t)b * TH + y + OY) * TW + x + OX);
+}
+
+int launch_crop_tiles(const ucdir_op_t& op, cudaStream_t st, bool dry) {
+  int BT = op.i[UCDIR_CROP_I_BT], TH = op.i[UCDIR_CROP_I_TH], TW = op.i[UCDIR_CROP_I_TW], IH = op.i[UCDIR_CROP_I_IH],
+      IW = op.i[UCDIR_CROP_I_IW], OY = op.i[UCDIR_CROP_I_OY], OX = op.i[UCDIR_CROP_I_OX];
+  if (!op.p[UCDIR_CROP_P_SRC] || !op.p[UCDIR_CROP_P_DST]) { set_error("crop_tiles: null pointer"); return -1; }
+  if (BT <= 0 || IH <= 0 || IW <= 0 || OY < 0 || OX < 0 || OY + IH > TH || OX + IW > TW) { set_error("crop_tiles: bad dims"); return -1; }
+  if (dry) return 0;
+  size_t total = (size_t)BT * IH * IW;
+  crop_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float4*)op.p[UCDIR_CROP_P_SRC], (float4*)op.p[UCDIR_CROP_P_DST],
+                                                                   BT, TH, TW, IH, IW, OY, OX);
+  ++g_launches;
+  return 0;
+}
+
 }  // namespace ucdir

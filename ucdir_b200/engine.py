@@ -964,7 +964,12 @@ class Session:
         self.x0 = torch.tensor(g.xs, dtype=torch.int32, device=dev)
         self.cond = torch.empty((g.B, in_channels, g.IH, g.IW), dtype=F32, device=dev)
         self.guide = torch.empty((g.B, 3, g.IH, g.IW), dtype=F32, device=dev)
-        self.eps = torch.empty((self.NT_pad, g.TH, g.TW, 4), dtype=F32, device=dev)
+        # only tile interiors are stitched (utils/util.py:144-145): the step's eps lives in a compact
+        # [tile, TH-2c, TW-2c, 4] buffer, which is also what the sharded mode all-gathers
+        self.crop = eng.m.tile_padding if g.kind == "tiled" else 0
+        self.eps = torch.empty((self.NT_pad, g.TH - 2 * self.crop, g.TW - 2 * self.crop, 4), dtype=F32, device=dev)
+        self.time_collective = False
+        self.collective_events: List[tuple] = []
         per_chunk = max(1, _max_chunk_pixels() // (g.TH * g.TW))
         self.chunks = [(a, min(a + per_chunk, hi)) for a in range(lo, hi, per_chunk)]
         self.pool = Pool(dev)
@@ -1005,12 +1010,23 @@ class Session:
                  "UCDIR_GATHER_I_IMG_H": g.IH, "UCDIR_GATHER_I_IMG_W": g.IW, "UCDIR_GATHER_I_PD": g.PD,
                  "UCDIR_GATHER_I_CA": ca, "UCDIR_GATHER_I_CB": 6 - ca, "UCDIR_GATHER_I_CD": 16 if self.bf16 else 8,
                  "UCDIR_GATHER_I_OUT_BF16": 1 if self.bf16 else 0}))
-            eps_ptr = self.eps.data_ptr() + a * g.TH * g.TW * 4 * 4
+            ih, iw = g.TH - 2 * self.crop, g.TW - 2 * self.crop
+            if self.crop:
+                if not hasattr(self, "eps_full"):
+                    self.eps_full = torch.empty((maxbt, g.TH, g.TW, 4), dtype=F32, device=dev)
+                eps_ptr = self.eps_full.data_ptr()
+            else:
+                eps_ptr = self.eps.data_ptr() + a * g.TH * g.TW * 4 * 4
             stats_view = self.stats.view(-1)[:MAX_STAT_SLOTS * BT * 2].view(MAX_STAT_SLOTS, BT, 2)   # same storage
             build = eng.build_forward_ops_bf16 if self.bf16 else eng.build_forward_ops
             sub = build(self.pool, BT, g.TH, g.TW, self.x_tiles, gmaps, self.attw, 0, eps_ptr, stats_view)
             self._chunk_attw_fix(sub, a)
             self.step_ops.extend(sub)
+            if self.crop:
+                self.step_ops.add("UCDIR_OP_CROP_TILES",
+                                  {"UCDIR_CROP_P_SRC": self.eps_full.data_ptr(), "UCDIR_CROP_P_DST": self.eps.data_ptr() + a * ih * iw * 16},
+                                  {"UCDIR_CROP_I_BT": BT, "UCDIR_CROP_I_TH": g.TH, "UCDIR_CROP_I_TW": g.TW, "UCDIR_CROP_I_IH": ih,
+                                   "UCDIR_CROP_I_IW": iw, "UCDIR_CROP_I_OY": self.crop, "UCDIR_CROP_I_OX": self.crop})
         self.n_unet_ops = len(self.step_ops)
         # the scatter (+ posterior) closes the step; kept as a separate one-op list so that a collective can
         # be issued between the UNet ops and it
@@ -1020,8 +1036,8 @@ class Session:
                            "UCDIR_SCATTER_P_OWNER_X": self.owner_x.data_ptr(), "UCDIR_SCATTER_P_Y0": self.y0.data_ptr(),
                            "UCDIR_SCATTER_P_X0": self.x0.data_ptr()},
                           {"UCDIR_SCATTER_I_BIMG": g.B, "UCDIR_SCATTER_I_IMG_H": g.IH, "UCDIR_SCATTER_I_IMG_W": g.IW,
-                           "UCDIR_SCATTER_I_NTY": g.nty, "UCDIR_SCATTER_I_NTX": g.ntx, "UCDIR_SCATTER_I_TH": g.TH,
-                           "UCDIR_SCATTER_I_TW": g.TW, "UCDIR_SCATTER_I_PD": g.PD, "UCDIR_SCATTER_I_CE": 4,
+                           "UCDIR_SCATTER_I_NTY": g.nty, "UCDIR_SCATTER_I_NTX": g.ntx, "UCDIR_SCATTER_I_TH": g.TH - 2 * self.crop,
+                           "UCDIR_SCATTER_I_TW": g.TW - 2 * self.crop, "UCDIR_SCATTER_I_PD": g.PD - self.crop, "UCDIR_SCATTER_I_CE": 4,
                            "UCDIR_SCATTER_I_MODE": 0, "UCDIR_SCATTER_I_CLIP": 1, "UCDIR_SCATTER_I_C": 3})
         self._attw_stride = 0
         self._bound = False
@@ -1068,8 +1084,14 @@ class Session:
             ops._arr = None
         _run_ops(ops.array(), len(ops), self.stream())
         if self.group is not None:
+            if self.time_collective:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             torch.distributed.all_gather_into_tensor(self.eps, self.eps[self.rank * self.per_rank:(self.rank + 1) * self.per_rank],
                                                      group=self.group)
+            if self.time_collective:
+                e1.record()
+                self.collective_events.append((e0, e1))
 
     def eps_only(self, levels: torch.Tensor, out: torch.Tensor):
         """Generic DY3h.forward: per-image noise levels from a device tensor, eps stitched into `out`."""
