@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define UCDIR_ABI_VERSION 7
+#define UCDIR_ABI_VERSION 8
 
 #define UCDIR_OP_NPTR 16
 #define UCDIR_OP_NINT 32
@@ -153,7 +153,9 @@ enum ucdir_gather_int {
  * (model/diffusion.py:150-158,171-172,182-183; NOISE NULL => 0; CLIP=0 skips the clamp).                     */
 enum ucdir_scatter_ptr {
   UCDIR_SCATTER_P_EPS = 0, UCDIR_SCATTER_P_OWNER_Y = 1, UCDIR_SCATTER_P_OWNER_X = 2, UCDIR_SCATTER_P_Y0 = 3,
-  UCDIR_SCATTER_P_X0 = 4, UCDIR_SCATTER_P_XT = 5, UCDIR_SCATTER_P_NOISE = 6, UCDIR_SCATTER_P_OUT = 7
+  UCDIR_SCATTER_P_X0 = 4, UCDIR_SCATTER_P_XT = 5, UCDIR_SCATTER_P_NOISE = 6, UCDIR_SCATTER_P_OUT = 7,
+  UCDIR_SCATTER_P_PARAMS = 8   /* optional device float[7] {A, B, C1, C2, SIGMA, clip, use_noise} overriding f[] / CLIP / NOISE:
+                                  lets a captured CUDA graph be replayed for every step of the schedule */
 };
 enum ucdir_scatter_int {
   UCDIR_SCATTER_I_BIMG = 0, UCDIR_SCATTER_I_IMG_H = 1, UCDIR_SCATTER_I_IMG_W = 2, UCDIR_SCATTER_I_NTY = 3,
@@ -214,6 +216,13 @@ int ucdir_run_ops(const ucdir_op_t* ops, int n_ops, void* stream);
 
 /* Validate ops without launching (same return codes). */
 int ucdir_check_ops(const ucdir_op_t* ops, int n_ops);
+
+/* CUDA graphs: capture ops[0..n) once (tensor maps and launch parameters are baked into the nodes), replay with one
+ * launch per step.  Everything that changes between steps must live in device memory the ops point at
+ * (UCDIR_TEMB_P_LEVELS, UCDIR_SCATTER_P_PARAMS, fixed input / output buffers).  capture returns 0 and a handle. */
+int ucdir_graph_capture(const ucdir_op_t* ops, int n_ops, void** graph_out);
+int ucdir_graph_launch(void* graph, void* stream);
+int ucdir_graph_destroy(void* graph);
 
 /* Per-op device timing for benchmarks: between begin and end every op run by ucdir_run_ops is bracketed by CUDA
  * events on its stream.  ucdir_profile_end waits for the last event and fills up to `cap` records

@@ -268,12 +268,21 @@ def emu_scatter(op, mem):
         out.copy_(e)
         return
     xt = mem.view(_p(op, "UCDIR_SCATTER_P_XT"), (BI, Cc, IH, IW))
-    f = lambda n: torch.tensor(_f(op, "UCDIR_SCATTER_F_" + n), dtype=torch.float32)
+    pp = _p(op, "UCDIR_SCATTER_P_PARAMS")
+    npz = _p(op, "UCDIR_SCATTER_P_NOISE")
+    if pp:
+        pv = mem.view(pp, (7,))
+        names = ["A", "B", "C1", "C2", "SIGMA"]
+        f = lambda n: pv[names.index(n)].clone()
+        clip = bool(pv[5] != 0)
+        if pv[6] == 0:
+            npz = 0
+    else:
+        f = lambda n: torch.tensor(_f(op, "UCDIR_SCATTER_F_" + n), dtype=torch.float32)
     x0_ = f("A") * xt - f("B") * e
     if clip:
         x0_ = x0_.clamp(-1.0, 1.0)
     mean = f("C1") * x0_ + f("C2") * xt
-    npz = _p(op, "UCDIR_SCATTER_P_NOISE")
     z = mem.view(npz, (BI, Cc, IH, IW)) if npz else torch.zeros_like(xt)
     out.copy_(mean + z * f("SIGMA"))
 

@@ -37,7 +37,8 @@ class Op(ctypes.Structure):
 
 
 EXPORTS = ["ucdir_run_ops", "ucdir_check_ops", "ucdir_abi_version", "ucdir_op_sizeof", "ucdir_last_error",
-           "ucdir_launch_count", "ucdir_device_ok", "ucdir_profile_begin", "ucdir_profile_end"]
+           "ucdir_launch_count", "ucdir_device_ok", "ucdir_profile_begin", "ucdir_profile_end", "ucdir_graph_capture",
+           "ucdir_graph_launch", "ucdir_graph_destroy"]
 
 _lib = None
 
@@ -64,6 +65,12 @@ def load(require_device=True):
         lib.ucdir_last_error.restype = ctypes.c_char_p
         lib.ucdir_launch_count.restype = ctypes.c_longlong
         lib.ucdir_device_ok.restype = ctypes.c_int
+        lib.ucdir_graph_capture.argtypes = [ctypes.POINTER(Op), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        lib.ucdir_graph_capture.restype = ctypes.c_int
+        lib.ucdir_graph_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.ucdir_graph_launch.restype = ctypes.c_int
+        lib.ucdir_graph_destroy.argtypes = [ctypes.c_void_p]
+        lib.ucdir_graph_destroy.restype = ctypes.c_int
         lib.ucdir_profile_begin.restype = ctypes.c_int
         lib.ucdir_profile_end.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int),
                                           ctypes.POINTER(ctypes.c_int), ctypes.c_int]
@@ -127,3 +134,26 @@ def profile_end(cap=1 << 20):
     if n < 0:
         raise UcdirLibraryError("ucdir_profile_end failed: %s" % last_error())
     return [(ms[k], idx[k], kind[k]) for k in range(n)]
+
+
+class Graph:
+    """A captured op list (CUDA graph).  Replay = one launch; see ucdir_graph_capture in the header."""
+
+    def __init__(self, ops, n):
+        h = ctypes.c_void_p()
+        rc = load().ucdir_graph_capture(ops, n, ctypes.byref(h))
+        if rc != 0:
+            raise UcdirLibraryError("ucdir_graph_capture failed (%d): %s" % (rc, last_error()))
+        self.h = h
+
+    def launch(self, stream):
+        rc = _lib.ucdir_graph_launch(self.h, ctypes.c_void_p(stream))
+        if rc != 0:
+            raise UcdirLibraryError("ucdir_graph_launch failed (%d): %s" % (rc, last_error()))
+
+    def __del__(self):
+        try:
+            if _lib is not None and self.h:
+                _lib.ucdir_graph_destroy(self.h)
+        except Exception:
+            pass

@@ -74,6 +74,53 @@ int ucdir_check_ops(const ucdir_op_t* ops, int n_ops) {
   return 0;
 }
 
+struct UcdirGraph { cudaGraph_t graph; cudaGraphExec_t exec; long long kernels; };
+
+int ucdir_graph_capture(const ucdir_op_t* ops, int n_ops, void** graph_out) {
+  if (!ops || n_ops <= 0 || !graph_out) { ucdir::set_error("graph_capture: bad arguments"); return -1; }
+  if (ucdir::g_prof) { ucdir::set_error("graph_capture: not while profiling"); return -1; }
+  cudaStream_t cs;
+  if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { ucdir::set_error("graph_capture: stream: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
+  const long long before = ucdir::g_launches;
+  if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    ucdir::set_error("graph_capture: begin: %s", cudaGetErrorString(cudaGetLastError())); cudaStreamDestroy(cs); return -3; }
+  int rc = 0;
+  for (int k = 0; k < n_ops && !rc; ++k) {
+    rc = ucdir::dispatch(ops[k], cs, false);
+    if (rc) { char tmp[400]; snprintf(tmp, sizeof(tmp), "%s", ucdir::g_err); ucdir::set_error("graph_capture: op %d (kind %d): %s", k, ops[k].kind, tmp); }
+  }
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(cs, &g);
+  const long long kernels = ucdir::g_launches - before;
+  ucdir::g_launches = before;                       // nothing ran yet; launches are counted per replay
+  cudaStreamDestroy(cs);
+  if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+  if (e != cudaSuccess || !g) { ucdir::set_error("graph_capture: end: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return -3; }
+  cudaGraphExec_t ex = nullptr;
+  e = cudaGraphInstantiate(&ex, g, 0);
+  if (e != cudaSuccess) { ucdir::set_error("graph_capture: instantiate: %s", cudaGetErrorString(e)); cudaGraphDestroy(g); (void)cudaGetLastError(); return -3; }
+  UcdirGraph* h = new UcdirGraph{g, ex, kernels};
+  *graph_out = h;
+  return 0;
+}
+
+int ucdir_graph_launch(void* graph, void* stream) {
+  UcdirGraph* h = (UcdirGraph*)graph;
+  if (!h) { ucdir::set_error("graph_launch: null graph"); return -1; }
+  cudaError_t e = cudaGraphLaunch(h->exec, (cudaStream_t)stream);
+  if (e != cudaSuccess) { ucdir::set_error("graph_launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return -3; }
+  ucdir::g_launches += h->kernels;
+  return 0;
+}
+
+int ucdir_graph_destroy(void* graph) {
+  UcdirGraph* h = (UcdirGraph*)graph;
+  if (!h) return 0;
+  cudaGraphExecDestroy(h->exec); cudaGraphDestroy(h->graph);
+  delete h;
+  return 0;
+}
+
 int ucdir_profile_begin(void) { ucdir::g_prof = true; ucdir::g_ev_used = 0; return 0; }
 
 int ucdir_profile_end(float* ms, int* op_index, int* kind, int cap) {

@@ -227,7 +227,13 @@ __global__ void __launch_bounds__(256) scatter_kernel(const float* __restrict__ 
                                                       const int* __restrict__ x0s, const float* __restrict__ xt,
                                                       const float* __restrict__ noise, float* __restrict__ out, int BI,
                                                       int IH, int IW, int NTY, int NTX, int TH, int TW, int PD, int CE, int C,
-                                                      int mode, int clip, float ca, float cb, float c1, float c2, float sigma) {
+                                                      int mode, int clip, float ca, float cb, float c1, float c2, float sigma,
+                                                      const float* __restrict__ params) {
+  if (params) {   // per-step scalars resident on the device (CUDA-graph replay): {A, B, C1, C2, SIGMA, clip, use_noise}
+    ca = params[0]; cb = params[1]; c1 = params[2]; c2 = params[3]; sigma = params[4];
+    clip = params[5] != 0.f;
+    if (params[6] == 0.f) noise = nullptr;
+  }
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t plane = (size_t)IH * IW;
   size_t total = (size_t)BI * plane;
@@ -272,7 +278,8 @@ int launch_scatter(const ucdir_op_t& op, cudaStream_t st, bool dry) {
       (const int*)op.p[UCDIR_SCATTER_P_X0], (const float*)op.p[UCDIR_SCATTER_P_XT], (const float*)op.p[UCDIR_SCATTER_P_NOISE],
       (float*)op.p[UCDIR_SCATTER_P_OUT], BI, IH, IW, op.i[UCDIR_SCATTER_I_NTY], op.i[UCDIR_SCATTER_I_NTX],
       op.i[UCDIR_SCATTER_I_TH], op.i[UCDIR_SCATTER_I_TW], op.i[UCDIR_SCATTER_I_PD], CE, C, mode, op.i[UCDIR_SCATTER_I_CLIP],
-      op.f[UCDIR_SCATTER_F_A], op.f[UCDIR_SCATTER_F_B], op.f[UCDIR_SCATTER_F_C1], op.f[UCDIR_SCATTER_F_C2], op.f[UCDIR_SCATTER_F_SIGMA]);
+      op.f[UCDIR_SCATTER_F_A], op.f[UCDIR_SCATTER_F_B], op.f[UCDIR_SCATTER_F_C1], op.f[UCDIR_SCATTER_F_C2], op.f[UCDIR_SCATTER_F_SIGMA],
+      (const float*)op.p[UCDIR_SCATTER_P_PARAMS]);
   ++g_launches;
   return 0;
 }

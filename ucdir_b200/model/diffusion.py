@@ -120,6 +120,8 @@ class GaussianDiffusion(nn.Module):
         if sess.group is None:
             self._shared_gen = None
             return
+        if self._shared_gen is not None:
+            return                      # one shared stream per process group; every rank advances it in lockstep
         seed = torch.randint(0, 2 ** 62, (1,), device=device, dtype=torch.int64)
         torch.distributed.broadcast(seed, 0, group=sess.group)
         self._shared_gen = torch.Generator(device=device)
@@ -136,6 +138,25 @@ class GaussianDiffusion(nn.Module):
         return (float(s["sqrt_recip_alphas_cumprod"][t]), float(s["sqrt_recipm1_alphas_cumprod"][t]),
                 float(s["posterior_mean_coef1"][t]), float(s["posterior_mean_coef2"][t]), float(sigma))
 
+    def _params_table(self, device, clip=True):
+        """Device table [T, 8] of the per-step kernel scalars {level, A, B, C1, C2, sigma, clip, use_noise}
+        (model/diffusion.py:150-163,183), built once per schedule; a step D2D-copies its row (no per-step H2D)."""
+        key = (str(device), self.num_timesteps, bool(clip), id(self._sched_host))
+        if getattr(self, "_ptable_key", None) != key:
+            rows = [[self.noise_level(t), *self._step_scalars(t), 1.0 if clip else 0.0, 1.0 if t > 0 else 0.0]
+                    for t in range(self.num_timesteps)]
+            self._ptable = torch.tensor(rows, dtype=torch.float32, device=device)
+            self._ptable_key = key
+        return self._ptable
+
+    def _fill_noise(self, buf):
+        if self._noise_source is not None:
+            buf.copy_(self._noise_source(tuple(buf.shape)).to(device=buf.device, dtype=torch.float32))
+        elif self._shared_gen is not None:
+            buf.normal_(generator=self._shared_gen)
+        else:
+            buf.normal_()
+
     def noise_level(self, t):
         """fp32 value of sqrt_alphas_cumprod_prev[t+1] (model/diffusion.py:162-163)."""
         return float(np.float32(self.sqrt_alphas_cumprod_prev[t + 1]))
@@ -147,10 +168,13 @@ class GaussianDiffusion(nn.Module):
         if condition_x is None:
             raise NotImplementedError("ucdir_b200: unconditional sampling is not on the hot path")
         sess = self.denoise_fn.engine().session(condition_x, kwargs["guide"])
-        noise = self._randn(x.shape, x.device) if t > 0 else None
-        out = torch.empty_like(x)
-        sess.step(x.contiguous(), out, self.noise_level(t), self._step_scalars(t), noise, clip_denoised)
-        return out
+        self._sync_noise_stream(sess, x.device)
+        table = self._params_table(x.device, clip_denoised)
+        sess.load_state(x)
+        if t > 0:
+            self._fill_noise(sess.noise)
+        sess.step_resident(table[t])
+        return sess.state().clone()
 
     @torch.no_grad()
     def p_sample_loop(self, x_in, continous=False, kwargs={}):
@@ -169,17 +193,16 @@ class GaussianDiffusion(nn.Module):
         ret[:b] = x
         sess = self.denoise_fn.engine().session(x, kwargs["guide"])
         self._sync_noise_stream(sess, device)
-        img = self._randn(x.shape, device).contiguous()
-        nxt = torch.empty_like(img)
+        table = self._params_table(device)
+        sess.load_state(self._randn(x.shape, device))
         row = 1
         for i in reversed(range(T)):
-            noise = self._randn(x.shape, device) if i > 0 else None
-            sess.step(img, nxt, self.noise_level(i), self._step_scalars(i), noise, True)
-            img, nxt = nxt, img
+            if i > 0:
+                self._fill_noise(sess.noise)
+            sess.step_resident(table[i])
             if i % sample_inter == 0:
-                ret[row * b:(row + 1) * b] = img
+                ret[row * b:(row + 1) * b] = sess.state()
                 row += 1
-        self._shared_gen = None
         return ret if continous else ret[-1]
 
     @torch.no_grad()
