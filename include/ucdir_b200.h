@@ -37,10 +37,10 @@
 extern "C" {
 #endif
 
-#define UCDIR_ABI_VERSION 8
+#define UCDIR_ABI_VERSION 9
 
 #define UCDIR_OP_NPTR 16
-#define UCDIR_OP_NINT 32
+#define UCDIR_OP_NINT 48
 #define UCDIR_OP_NFLT 8
 
 typedef struct ucdir_op {
@@ -114,8 +114,8 @@ enum ucdir_sgemm_int {
 enum ucdir_sgemm_flt { UCDIR_SGEMM_F_ALPHA = 0 };
 
 /* ---- UCDIR_OP_SOFTMAX_F32: in-place softmax over each row of X[ROWS][COLS] --------------------------- */
-enum ucdir_softmax_ptr { UCDIR_SOFTMAX_P_X = 0 };
-enum ucdir_softmax_int { UCDIR_SOFTMAX_I_ROWS = 0, UCDIR_SOFTMAX_I_COLS = 1 };
+enum ucdir_softmax_ptr { UCDIR_SOFTMAX_P_X = 0, UCDIR_SOFTMAX_P_OUT_BF16 = 1 /* optional: write bf16 probabilities here, rows OUT_LD apart (tail zeroed), instead of in place */ };
+enum ucdir_softmax_int { UCDIR_SOFTMAX_I_ROWS = 0, UCDIR_SOFTMAX_I_COLS = 1, UCDIR_SOFTMAX_I_OUT_LD = 2, UCDIR_SOFTMAX_I_IN_LD = 3 /* 0 = COLS */ };
 
 /* ---- UCDIR_OP_GUIDANCE: DST[B,H,W,8] = conv3x3(SimpleGate(conv1x1(bilinear(GUIDE[B,GH,GW,4])))) --------- */
 enum ucdir_guid_ptr {
@@ -181,7 +181,8 @@ enum ucdir_pool_int { UCDIR_POOL_I_B = 0, UCDIR_POOL_I_H = 1, UCDIR_POOL_I_W = 2
 enum ucdir_tc_ptr {
   UCDIR_TC_P_SRC0 = 0, UCDIR_TC_P_SRC1 = 1, UCDIR_TC_P_W = 2, UCDIR_TC_P_TB = 3, UCDIR_TC_P_TG = 4,
   UCDIR_TC_P_STATS0 = 5, UCDIR_TC_P_STATS1 = 6, UCDIR_TC_P_RES = 7, UCDIR_TC_P_ATT = 8, UCDIR_TC_P_ATTW = 9,
-  UCDIR_TC_P_DST = 10, UCDIR_TC_P_DST_STATS = 11
+  UCDIR_TC_P_DST = 10, UCDIR_TC_P_DST_STATS = 11,
+  UCDIR_TC_P_DST2 = 12     /* bf16 [B][NTOT - T_COL0][T_LD]: columns >= T_COL0 are stored transposed here (attention V^T) */
 };
 enum ucdir_tc_int {
   UCDIR_TC_I_B = 0, UCDIR_TC_I_H = 1, UCDIR_TC_I_W = 2, UCDIR_TC_I_SRC_H = 3, UCDIR_TC_I_SRC_W = 4,
@@ -192,9 +193,16 @@ enum ucdir_tc_int {
   UCDIR_TC_I_DST_COFF = 23, UCDIR_TC_I_DST_UP = 24, UCDIR_TC_I_DST_PY = 25, UCDIR_TC_I_DST_PX = 26,
   UCDIR_TC_I_RES_C = 27, UCDIR_TC_I_ATTW_STRIDE = 28,
   UCDIR_TC_I_KB = 29,      /* K elements per weight slab row (0 = KC); grouped convs: max(Cin/groups, 16) */
-  UCDIR_TC_I_NSPLIT = 30   /* groups per NT-column work item that share one KC-channel activation slab (0 = 1) */
+  UCDIR_TC_I_NSPLIT = 30,  /* groups per NT-column work item that share one KC-channel activation slab (0 = 1) */
+  /* batched GEMM use (the attention einsums, model/ucdir.py:174,179): SRC0 pixel rows are SRC_CSTRIDE elements apart
+   * (0 = C0, lets a channel slice of a wider tensor be the A operand); W_BATCHED=1: W is per image, [B][NTOT][C0] with
+   * rows W_ROWSTRIDE elements apart and images W_BATCHSTRIDE (LO + HI<<31) elements apart; f[ALPHA] scales the result */
+  UCDIR_TC_I_SRC_CSTRIDE = 31, UCDIR_TC_I_W_BATCHED = 32, UCDIR_TC_I_W_ROWSTRIDE = 33,
+  UCDIR_TC_I_W_BATCHSTRIDE_LO = 34, UCDIR_TC_I_W_BATCHSTRIDE_HI = 35,
+  UCDIR_TC_I_T_COL0 = 36, UCDIR_TC_I_T_LD = 37,  /* transposed store of columns >= T_COL0 into DST2, row pitch T_LD */
+  UCDIR_TC_I_W_ROWS = 38                         /* batched weights: rows that exist per image (0 = NTOT); the rest read as 0 */
 };
-enum ucdir_tc_flt { UCDIR_TC_F_EPS = 0 };
+enum ucdir_tc_flt { UCDIR_TC_F_EPS = 0, UCDIR_TC_F_ALPHA = 1 /* 0 = 1.0 */ };
 
 /* ---- UCDIR_OP_GN_APPLY_BF16: DST = [Swish](GroupNorm(1,C)(SRC)) on bf16 NHWC [B][HW][C]; f[0] = eps ------------ */
 enum ucdir_gna_ptr { UCDIR_GNA_P_SRC = 0, UCDIR_GNA_P_DST = 1, UCDIR_GNA_P_GAMMA = 2, UCDIR_GNA_P_BETA = 3, UCDIR_GNA_P_STATS = 4 };

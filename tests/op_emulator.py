@@ -177,8 +177,16 @@ def emu_sgemm(op, mem):
 
 def emu_softmax(op, mem):
     rows, cols = _i(op, "UCDIR_SOFTMAX_I_ROWS"), _i(op, "UCDIR_SOFTMAX_I_COLS")
-    X = mem.view(_p(op, "UCDIR_SOFTMAX_P_X"), (rows, cols))
-    X.copy_(torch.softmax(X, dim=-1))
+    in_ld = _i(op, "UCDIR_SOFTMAX_I_IN_LD") or cols
+    X = mem.view(_p(op, "UCDIR_SOFTMAX_P_X"), (rows, in_ld))[:, :cols]
+    o = _p(op, "UCDIR_SOFTMAX_P_OUT_BF16")
+    if o:
+        out_ld = _i(op, "UCDIR_SOFTMAX_I_OUT_LD")
+        P = mem.view(o, (rows, out_ld), torch.bfloat16)
+        P.zero_()
+        P[:, :cols] = torch.softmax(X, dim=-1).to(torch.bfloat16)
+    else:
+        X.copy_(torch.softmax(X, dim=-1))
 
 
 def emu_guidance(op, mem):
@@ -311,7 +319,10 @@ def emu_tc_conv(op, mem):
     eps = _f(op, "UCDIR_TC_F_EPS")
     bf = torch.bfloat16
     Cin = C0 + C1
-    x = mem.view(_p(op, "UCDIR_TC_P_SRC0"), (B, sH, sW, C0), bf).float()
+    cstride = g("SRC_CSTRIDE") or C0
+    x = mem.view(_p(op, "UCDIR_TC_P_SRC0"), ((B * sH * sW - 1) * cstride + C0,), bf)
+    x = torch.as_strided(x, (B, sH, sW, C0), (sH * sW * cstride, sW * cstride, cstride, 1)).float()
+    wb = g("W_BATCHED")
     if C1:
         x = torch.cat([x, mem.view(_p(op, "UCDIR_TC_P_SRC1"), (B, sH, sW, C1), bf).float()], dim=-1)
     KB = g("KB") or KC
@@ -322,7 +333,14 @@ def emu_tc_conv(op, mem):
         Cg, Ng, cg_eff = Cin, Ntot, Cin
     ktap = cg_eff
     Ktot = nty * ntx * ktap
-    wp = mem.view(_p(op, "UCDIR_TC_P_W"), (Ntot, nty * ntx, ktap), bf).float()
+    if wb:                                                       # per-image weights [B][Ntot][C0], strided
+        rs = g("W_ROWSTRIDE"); bs = g("W_BATCHSTRIDE_LO") + (g("W_BATCHSTRIDE_HI") << 31)
+        n_rows = g("W_ROWS") or Ntot                              # rows beyond the image's extent are TMA zero fill
+        wraw = mem.view(_p(op, "UCDIR_TC_P_W"), ((B - 1) * bs + (n_rows - 1) * rs + C0,), bf)
+        wbat = torch.zeros(B, Ntot, C0)
+        wbat[:, :n_rows] = torch.as_strided(wraw, (B, n_rows, C0), (bs, rs, 1)).float()
+    else:
+        wp = mem.view(_p(op, "UCDIR_TC_P_W"), (Ntot, nty * ntx, ktap), bf).float()
     acc = torch.zeros(B, H, W, Ntot)
     ys = torch.arange(H) * stride
     xs = torch.arange(W) * stride
@@ -332,6 +350,9 @@ def emu_tc_conv(op, mem):
             vy, vx = (sy >= 0) & (sy < sH), (sx >= 0) & (sx < sW)
             patch = x[:, sy.clamp(0, sH - 1)][:, :, sx.clamp(0, sW - 1)]
             patch = patch * (vy.view(1, -1, 1, 1) & vx.view(1, 1, -1, 1))
+            if wb:
+                acc += torch.einsum("bhwc,bnc->bhwn", patch, wbat)
+                continue
             for gi in range(groups):
                 cb = (gi * Cg) // cg_eff * cg_eff if groups > 1 else 0
                 rows = slice(gi * Ng, (gi + 1) * Ng)
@@ -355,7 +376,8 @@ def emu_tc_conv(op, mem):
             cls = torch.zeros(H, W, dtype=torch.long)
         v = acc * rstd - mr * tg[cls].unsqueeze(0) + tb[cls].unsqueeze(0)
     else:
-        v = acc + tb[0].view(1, 1, 1, -1)
+        alpha = float(op.f[K["UCDIR_TC_F_ALPHA"]]) or 1.0
+        v = acc * alpha + tb[0].view(1, 1, 1, -1)
     if mode == 1:
         att = mem.view(_p(op, "UCDIR_TC_P_ATT"), (B, H, W, 8))
         base = _p(op, "UCDIR_TC_P_ATTW")
@@ -376,6 +398,13 @@ def emu_tc_conv(op, mem):
         nout = ncv
     odt = torch.float32 if dst_f32 else bf
     out = out.to(odt)
+    d2 = _p(op, "UCDIR_TC_P_DST2")
+    if d2:                                                       # columns >= T_COL0 go transposed to DST2[b][col][pixel]
+        t0, tld = g("T_COL0"), g("T_LD")
+        vt = mem.view(d2, (B, Ntot - t0, tld), bf)
+        vt[:, :, :H * W] = out[..., t0:].reshape(B, H * W, Ntot - t0).transpose(1, 2)
+        out = out[..., :t0]
+        nout = t0
     if dstUp:
         dst = mem.view(_p(op, "UCDIR_TC_P_DST"), (B, 2 * H, 2 * W, dstC), odt)
         dst[:, dpy::2, dpx::2, dstCoff:dstCoff + nout] = out

@@ -212,3 +212,47 @@ def test_sgemm_bf16_operands():
     host, dev = run_both(c, build)
     assert_close(dev["S"], host["S"], "softmax(QK^T)", rtol=1e-3, atol=1e-4)
     assert_close(dev["O"], host["O"], "PV")
+
+
+@pytest.mark.parametrize("B,H,W,C", [(3, 16, 16, 512), (2, 8, 8, 512), (2, 18, 18, 128)])
+def test_tc_attention_chain(B, H, W, C):
+    """qkv conv (V^T written transposed) -> S = alpha Q K^T (batched weights) -> softmax -> O = P V, all on the
+    tensor-core kernel, against the interpreter and against torch's attention on the same bf16 qkv."""
+    import math
+    g = torch.Generator().manual_seed(77 + H)
+    N = H * W
+    NP = (N + 7) & ~7
+    nt_s = 256 if N % 256 == 0 else (128 if N % 128 == 0 else 64)
+    NS = (N + nt_s - 1) // nt_s * nt_s
+    x = rnd(g, B, H, W, C).to(BF)
+    wq = rnd(g, 3 * C, C, 1, 1, scale=1.5 / np.sqrt(C))
+    wp, tb, _ = E.pack_tc_dense(wq, None, 256 if (3 * C) % 256 == 0 else 128)
+    c = Case().add("x", x).add("w", wp).add("tb", tb).add("zeros", torch.zeros(4096))
+    c.add("qk", torch.zeros(B, H, W, 2 * C, dtype=BF)).add("vt", torch.zeros(B, C, NP, dtype=BF))
+    c.add("S", torch.zeros(B, N, NS)).add("P", torch.zeros(B, N, NP, dtype=BF)).add("O", torch.zeros(B, H, W, C, dtype=BF))
+    nt_qkv = 256 if (3 * C) % 256 == 0 else 128
+
+    def build(t):
+        ol = E.OpList()
+        qk = act(t["qk"], 2 * C, H, W)
+        E._tc_op(ol, src0=act(t["x"], C, H, W), w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), nty=1, ntx=1, oy0=0, ox0=0, dst=qk,
+                 ntot=3 * C, B=B, nt=nt_qkv, dst2=t["vt"].data_ptr(), t_col0=2 * C, t_ld=NP)
+        E._tc_op(ol, src0=act(t["qk"], C, H, W), src_cstride=2 * C, w=t["qk"].data_ptr() + C * 2, w_batched=1, w_rowstride=2 * C,
+                 w_batchstride=N * 2 * C, w_rows=N, tb=t["zeros"].data_ptr(), nty=1, ntx=1, oy0=0, ox0=0, dst=act(t["S"], NS, H, W),
+                 ntot=NS, B=B, nt=nt_s, dst_f32=1, ncol_valid=NS, alpha=1.0 / math.sqrt(C))
+        ol.add("UCDIR_OP_SOFTMAX_F32", {"UCDIR_SOFTMAX_P_X": t["S"].data_ptr(), "UCDIR_SOFTMAX_P_OUT_BF16": t["P"].data_ptr()},
+               {"UCDIR_SOFTMAX_I_ROWS": B * N, "UCDIR_SOFTMAX_I_COLS": N, "UCDIR_SOFTMAX_I_IN_LD": NS, "UCDIR_SOFTMAX_I_OUT_LD": NP})
+        E._tc_op(ol, src0=act(t["P"], N, H, W), src_cstride=NP, w=t["vt"].data_ptr(), w_batched=1, w_rowstride=NP,
+                 w_batchstride=C * NP, tb=t["zeros"].data_ptr(), nty=1, ntx=1, oy0=0, ox0=0, dst=act(t["O"], C, H, W), ntot=C, B=B,
+                 nt=E._tc_nt(C))
+        return ol
+    host, dev = run_both(c, build)
+    assert_close(dev["qk"], host["qk"], "q,k")
+    assert_close(dev["vt"][..., :N], host["vt"][..., :N], "V^T")
+    assert_close(dev["S"][..., :N], host["S"][..., :N], "scores", rtol=1e-2, atol=1e-2)
+    assert_close(dev["P"], host["P"], "softmax")
+    assert_close(dev["O"], host["O"], "O = P V")
+    q, k = dev["qk"].float().reshape(B, N, 2 * C).split(C, dim=-1)
+    v = dev["vt"].float()[..., :N].transpose(1, 2)
+    want = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(C), dim=-1) @ v
+    assert_close(dev["O"].reshape(B, N, C), want, "O vs torch attention", rtol=3e-2, atol=3e-2)

@@ -366,10 +366,10 @@ int launch_sgemm_f32(const ucdir_op_t& op, cudaStream_t st, bool dry) {
 // ------------------------------------------------------------------------------------------------
 // Row softmax in place (model/ucdir.py:176).  One CTA per row.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ X, int cols) {
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ X, int cols, int in_ld, __nv_bfloat16* __restrict__ out, int out_ld) {
   __shared__ float red[8];
   __shared__ float bc;
-  float* row = X + (size_t)blockIdx.x * cols;
+  float* row = X + (size_t)blockIdx.x * in_ld;
   const int tid = threadIdx.x;
   float mx = -INFINITY;
   for (int c = tid; c < cols; c += 256) mx = fmaxf(mx, row[c]);
@@ -388,15 +388,22 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ X
   if (tid == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; bc = s; }
   __syncthreads();
   const float tot = bc;
-  for (int c = tid; c < cols; c += 256) row[c] = row[c] / tot;
+  if (out) {
+    __nv_bfloat16* o = out + (size_t)blockIdx.x * out_ld;
+    for (int c = tid; c < out_ld; c += 256) o[c] = __float2bfloat16(c < cols ? row[c] / tot : 0.f);
+  } else {
+    for (int c = tid; c < cols; c += 256) row[c] = row[c] / tot;
+  }
 }
 
 int launch_softmax_f32(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   float* X = (float*)op.p[UCDIR_SOFTMAX_P_X];
   int rows = op.i[UCDIR_SOFTMAX_I_ROWS], cols = op.i[UCDIR_SOFTMAX_I_COLS];
   if (!X || rows <= 0 || cols <= 0) { set_error("softmax: bad args"); return -1; }
+  if (op.p[UCDIR_SOFTMAX_P_OUT_BF16] && op.i[UCDIR_SOFTMAX_I_OUT_LD] < cols) { set_error("softmax: OUT_LD < COLS"); return -1; }
   if (dry) return 0;
-  softmax_rows_kernel<<<rows, 256, 0, st>>>(X, cols);
+  softmax_rows_kernel<<<rows, 256, 0, st>>>(X, cols, op.i[UCDIR_SOFTMAX_I_IN_LD] ? op.i[UCDIR_SOFTMAX_I_IN_LD] : cols,
+                                            (__nv_bfloat16*)op.p[UCDIR_SOFTMAX_P_OUT_BF16], op.i[UCDIR_SOFTMAX_I_OUT_LD]);
   ++g_launches;
   return 0;
 }

@@ -70,6 +70,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -129,6 +135,9 @@ struct TcParams {
   int gn, ncls, act, mode, dst_f32;
   int dstC, dstCoff, dstUp, dstPy, dstPx, resC, attwStride;
   double gn_count; float eps;
+  float alpha;                 // scale on the accumulator when gn == 0 (attention: 1/sqrt(C))
+  int w_batched;               // weights are per image: [B][Ntot][K] (attention K / V^T operands)
+  __nv_bfloat16* dst2; int t_col0, t_ld;   // columns >= t_col0 are stored transposed: dst2[img][col - t_col0][pixel], row pitch t_ld
 };
 
 constexpr int TC_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
@@ -243,7 +252,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               mbar_expect_tx(&full[stage], tx_bytes);
               if (p.groups > 1 || j < p.c0_chunks) tma_load_4d(&mapA0, &full[stage], sa, cgrp0 + j * KA, x0 + tx, y0 + ty, n0);
               else tma_load_4d(&mapA1, &full[stage], sa, (j - p.c0_chunks) * KA, x0 + tx, y0 + ty, n0);
-              tma_load_2d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0);
+              if (p.w_batched) tma_load_3d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0, n0);
+              else tma_load_2d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0);
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -322,7 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         }
         img = im0 + nn; y = cur.ty_i * p.bh + yy; x = cur.tx_i * p.bw + xx;
         valid = (r < box * p.bn) && img < p.B && y < p.H && x < p.W;
-        rstd = 1.f; mr = 0.f; cls = 0;
+        rstd = p.alpha; mr = 0.f; cls = 0;
         if (!valid) { img = 0; y = 0; x = 0; }
         if (p.gn && valid) {
           if (img != gn_img) {
@@ -420,6 +430,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < CH; ++j)
               if (nb + j < p.ncol_valid) { d[j] = v[j]; t1s += v[j]; t2s += v[j] * v[j]; }
+          } else if (p.dst2 && nb >= p.t_col0) {
+            // transposed store (attention V^T): lanes hold consecutive pixels, so each store is one coalesced run
+            __nv_bfloat16* d = p.dst2 + ((size_t)img * (p.Ntot - p.t_col0) + (nb - p.t_col0)) * p.t_ld + (y * p.W + x);
+#pragma unroll
+            for (int j = 0; j < CH; ++j) d[(size_t)j * p.t_ld] = __float2bfloat16(v[j]);
           } else {
             __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix_out * p.dstC + p.dstCoff + nb;
 #pragma unroll
@@ -479,11 +494,11 @@ static EncodeTiledFn get_encode() {
 
 static CUtensorMapSwizzle swz(int kc) { return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B); }
 
-static int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int B, int kc, int bw, int bh, int bn, int stride) {
+static int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int B, int kc, int bw, int bh, int bn, int stride, int cstride) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("tc_conv: cuTensorMapEncodeTiled unavailable"); return -3; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  cuuint64_t strides[3] = {(cuuint64_t)cstride * 2, (cuuint64_t)cstride * 2 * W, (cuuint64_t)cstride * 2 * W * H};
   cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
   cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
@@ -492,16 +507,16 @@ static int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, i
                                      C, W, H, B, kc, bw, bh, bn, stride, (int)r); return -3; }
   return 0;
 }
-static int make_w_map(CUtensorMap* m, const void* base, int Ktot, int Ntot, int kc, int nt) {
+static int make_w_map(CUtensorMap* m, const void* base, int Ktot, int Ntot, int kc, int nt, int row_stride, int batch, long long batch_stride) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("tc_conv: cuTensorMapEncodeTiled unavailable"); return -3; }
-  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Ntot};
-  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)nt};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+  cuuint64_t dims[3] = {(cuuint64_t)Ktot, (cuuint64_t)Ntot, (cuuint64_t)(batch > 0 ? batch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)batch_stride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)nt, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, batch > 0 ? 3 : 2, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("tc_conv: cuTensorMapEncodeTiled(weights K=%d N=%d box %dx%d) failed: %d", Ktot, Ntot, kc, nt, (int)r); return -3; }
+  if (r != CUDA_SUCCESS) { set_error("tc_conv: cuTensorMapEncodeTiled(weights K=%d N=%d box %dx%d row stride %d batch %d) failed: %d", Ktot, Ntot, kc, nt, row_stride, batch, (int)r); return -3; }
   return 0;
 }
 
@@ -556,6 +571,12 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   p.dstPy = op.i[UCDIR_TC_I_DST_PY]; p.dstPx = op.i[UCDIR_TC_I_DST_PX]; p.resC = op.i[UCDIR_TC_I_RES_C];
   p.attwStride = op.i[UCDIR_TC_I_ATTW_STRIDE];
   p.eps = op.f[UCDIR_TC_F_EPS];
+  p.alpha = op.f[UCDIR_TC_F_ALPHA] != 0.f ? op.f[UCDIR_TC_F_ALPHA] : 1.f;
+  p.w_batched = op.i[UCDIR_TC_I_W_BATCHED];
+  p.dst2 = (__nv_bfloat16*)op.p[UCDIR_TC_P_DST2]; p.t_col0 = op.i[UCDIR_TC_I_T_COL0]; p.t_ld = op.i[UCDIR_TC_I_T_LD];
+  const int cstride0 = op.i[UCDIR_TC_I_SRC_CSTRIDE] ? op.i[UCDIR_TC_I_SRC_CSTRIDE] : op.i[UCDIR_TC_I_C0];
+  const int w_rowstride = op.i[UCDIR_TC_I_W_ROWSTRIDE];
+  const long long w_batchstride = (long long)op.i[UCDIR_TC_I_W_BATCHSTRIDE_LO] + ((long long)op.i[UCDIR_TC_I_W_BATCHSTRIDE_HI] << 31);
   if (!src0 || !w || !p.dst || !p.tb) { set_error("tc_conv: null src0/w/dst/tb"); return -1; }
   if (p.B <= 0 || p.H <= 0 || p.W <= 0 || C0 <= 0 || p.Ntot <= 0 || p.groups < 1) { set_error("tc_conv: bad dims"); return -1; }
   if (p.stride != 1 && p.stride != 2) { set_error("tc_conv: stride must be 1 or 2"); return -2; }
@@ -574,10 +595,10 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
     p.nchunk = p.cg_eff / KC; p.c0_chunks = p.nchunk;
     if (NSPLIT > 1 && p.nchunk != 1) { set_error("tc_conv: split items need one chunk per tap"); return -2; }
   } else {
-    if (C0 % KC || C1 % KC) { set_error("tc_conv: C0=%d / C1=%d must be multiples of KC=%d", C0, C1, KC); return -2; }
+    if ((C0 % KC && !(C1 == 0 && p.w_batched)) || C1 % KC) { set_error("tc_conv: C0=%d / C1=%d must be multiples of KC=%d", C0, C1, KC); return -2; }
     if (C1 > 0 && !src1) { set_error("tc_conv: null src1"); return -1; }
     if (NSPLIT != 1 || KB != KC) { set_error("tc_conv: dense conv needs NSPLIT = 1 and KB = KC"); return -2; }
-    p.Cg = Cin; p.Ng = p.Ntot; p.cg_eff = Cin; p.nchunk = Cin / KC; p.c0_chunks = C0 / KC;
+    p.Cg = Cin; p.Ng = p.Ntot; p.cg_eff = Cin; p.nchunk = (Cin + KC - 1) / KC; p.c0_chunks = (C0 + KC - 1) / KC;   // a K tail is zero filled by TMA
   }
   if (p.Ntot % NT) { set_error("tc_conv: Ntot=%d not a multiple of NT=%d", p.Ntot, NT); return -2; }
   if (p.gn) {
@@ -591,7 +612,9 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   if (p.stats1 == nullptr && C1 > 0 && p.gn) { set_error("tc_conv: stats1 missing"); return -1; }
   if (C1 == 0) p.stats1 = nullptr;
   p.gn_count = (double)Cin * p.srcH * p.srcW;
-  choose_tile(p.W, p.H, p.B, p.stride, &p.bw, &p.bh, &p.bn);
+  if (p.w_batched && (p.groups != 1 || C1 || w_rowstride <= 0)) { set_error("tc_conv: batched weights need a dense single-source op and a row stride"); return -2; }
+  if (p.dst2 && (p.t_ld <= 0 || p.t_col0 % NT || p.mode == 1 || p.dstUp)) { set_error("tc_conv: bad transposed-store config"); return -2; }
+  choose_tile(p.W, p.H, p.w_batched ? 1 : p.B, p.stride, &p.bw, &p.bh, &p.bn);
   p.tiles_x = (p.W + p.bw - 1) / p.bw; p.tiles_y = (p.H + p.bh - 1) / p.bh;
   const int tiles_n = (p.B + p.bn - 1) / p.bn;
   const long mt = (long)p.tiles_x * p.tiles_y * tiles_n;
@@ -599,12 +622,13 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   p.m_tiles = (int)mt;
   if (dry) return 0;
   CUtensorMap a0, a1, bm;
-  int rc = make_act_map(&a0, src0, C0, p.srcW, p.srcH, p.B, KC, p.bw, p.bh, p.bn, p.stride);
+  int rc = make_act_map(&a0, src0, C0, p.srcW, p.srcH, p.B, KC, p.bw, p.bh, p.bn, p.stride, cstride0);
   if (rc) return rc;
-  if (C1 > 0) { rc = make_act_map(&a1, src1, C1, p.srcW, p.srcH, p.B, KC, p.bw, p.bh, p.bn, p.stride); if (rc) return rc; }
+  if (C1 > 0) { rc = make_act_map(&a1, src1, C1, p.srcW, p.srcH, p.B, KC, p.bw, p.bh, p.bn, p.stride, C1); if (rc) return rc; }
   else a1 = a0;
   const int Ktot = p.nty * p.ntx * p.nchunk * KB;
-  rc = make_w_map(&bm, w, Ktot, p.Ntot, KB, NT);
+  if (p.w_batched) rc = make_w_map(&bm, w, C0, op.i[UCDIR_TC_I_W_ROWS] ? op.i[UCDIR_TC_I_W_ROWS] : p.Ntot, KB, NT, w_rowstride, p.B, w_batchstride);
+  else rc = make_w_map(&bm, w, Ktot, p.Ntot, KB, NT, Ktot, 0, 0);
   if (rc) return rc;
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }

@@ -394,7 +394,9 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
            src1: Optional[Act] = None, tg: int = 0, gn: int = 0, ncls: int = 1, nty: int = 3, ntx: int = 3, oy0: int = -1,
            ox0: int = -1, stride: int = 1, groups: int = 1, act: int = 0, mode: int = 0, res: Optional[Act] = None,
            att: int = 0, attw: int = 0, attw_stride: int = 0, dst_f32: int = 0, ncol_valid: int = 0, dst_up: int = 0,
-           dst_py: int = 0, dst_px: int = 0, eps: float = 1e-5, kb: int = 0, nsplit: int = 1):
+           dst_py: int = 0, dst_px: int = 0, eps: float = 1e-5, kb: int = 0, nsplit: int = 1, src_cstride: int = 0,
+           w_batched: int = 0, w_rowstride: int = 0, w_batchstride: int = 0, alpha: float = 0.0, dst2: int = 0, t_col0: int = 0,
+           t_ld: int = 0, w_rows: int = 0):
     H, W = (dst.H // 2, dst.W // 2) if dst_up else (dst.H, dst.W)
     p = {"UCDIR_TC_P_SRC0": src0.ptr, "UCDIR_TC_P_W": w, "UCDIR_TC_P_TB": tb, "UCDIR_TC_P_DST": dst.ptr}
     if src1 is not None: p["UCDIR_TC_P_SRC1"] = src1.ptr
@@ -413,8 +415,12 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
          "UCDIR_TC_I_NT": nt, "UCDIR_TC_I_GN": gn, "UCDIR_TC_I_NCLS": ncls, "UCDIR_TC_I_ACT": act, "UCDIR_TC_I_MODE": mode,
          "UCDIR_TC_I_DST_F32": dst_f32, "UCDIR_TC_I_DST_C": dst.C, "UCDIR_TC_I_DST_COFF": 0, "UCDIR_TC_I_DST_UP": dst_up,
          "UCDIR_TC_I_DST_PY": dst_py, "UCDIR_TC_I_DST_PX": dst_px, "UCDIR_TC_I_RES_C": res.C if res is not None else 0,
-         "UCDIR_TC_I_ATTW_STRIDE": attw_stride, "UCDIR_TC_I_KB": kb or kc, "UCDIR_TC_I_NSPLIT": nsplit}
-    ol.add("UCDIR_OP_TC_CONV", p, i, {"UCDIR_TC_F_EPS": eps})
+         "UCDIR_TC_I_ATTW_STRIDE": attw_stride, "UCDIR_TC_I_KB": kb or kc, "UCDIR_TC_I_NSPLIT": nsplit,
+         "UCDIR_TC_I_SRC_CSTRIDE": src_cstride, "UCDIR_TC_I_W_BATCHED": w_batched, "UCDIR_TC_I_W_ROWSTRIDE": w_rowstride,
+         "UCDIR_TC_I_W_BATCHSTRIDE_LO": w_batchstride & 0x7FFFFFFF, "UCDIR_TC_I_W_BATCHSTRIDE_HI": w_batchstride >> 31,
+         "UCDIR_TC_I_T_COL0": t_col0, "UCDIR_TC_I_T_LD": t_ld, "UCDIR_TC_I_W_ROWS": w_rows}
+    if dst2: p["UCDIR_TC_P_DST2"] = dst2
+    ol.add("UCDIR_OP_TC_CONV", p, i, {"UCDIR_TC_F_EPS": eps, "UCDIR_TC_F_ALPHA": alpha})
 
 
 def tc_mix_tiling(cout: int):
@@ -745,6 +751,7 @@ class UNetEngine:
                             ws.put("%s.p%d%d.tcw" % (name, py, px), w); ws.put("%s.p%d%d.tb" % (name, py, px), tb)
         fc = m.final_conv
         put3("final", pack_tc_dense(fc[3].weight, fc[3].bias, 16))
+        ws.put("zeros", torch.zeros(65536, dtype=F32, device=ws.device))    # bias table of the attention GEMMs
 
     def build_forward_ops_bf16(self, pool: Pool, BT: int, TH: int, TW: int, x_in: torch.Tensor, gmaps: List[torch.Tensor],
                                attw: torch.Tensor, attw_stride: int, eps_ptr: int, stats: torch.Tensor) -> OpList:
@@ -789,32 +796,36 @@ class UNetEngine:
             return out
 
         def attention(name, x: Act) -> Act:
+            """SelfAttention.forward (model/ucdir.py:165-182) on the tensor cores: the two einsums are batched GEMMs
+            of the same tcgen05 kernel -- Q (a channel slice of the qkv conv's output) is the activation operand,
+            K resp. V^T are per-image "weights" (3-D tensor map); V^T is written by the qkv conv's epilogue."""
             C, N = x.C, x.H * x.W
-            qkv = bld.new(3 * C, x.H, x.W, with_stats=False)
+            NP = (N + 7) & ~7                                   # 16-byte aligned row pitch of P and V^T
+            nt_s = 256 if N % 256 == 0 else (128 if N % 128 == 0 else 64)
+            NS = (N + nt_s - 1) // nt_s * nt_s                  # score columns incl. zero padding
+            if N * 2 * C >= 2 ** 31 or C * NP >= 2 ** 62:
+                raise RuntimeError("attention over %d tokens exceeds the tensor-map strides" % N)
+            qk = bld.new(2 * C, x.H, x.W, with_stats=False)
+            vt = pool.get(BT * C * NP * 2)
             _tc_op(ol, src0=x, w=ws.ptr(name + ".attn.qkv.tcw"), tb=ws.ptr(name + ".attn.qkv.tb"),
-                   tg=ws.ptr(name + ".attn.qkv.tg"), gn=1, ncls=1, nty=1, ntx=1, oy0=0, ox0=0, dst=qkv, ntot=3 * C, B=BT, nt=256)
-            if N * N >= 2 ** 31 or N * 3 * C >= 2 ** 31:
-                raise RuntimeError("attention over %d tokens exceeds the 32-bit strides of the attention GEMMs" % N)
-            S = pool.get(BT * N * N * 4)
-            ol.add("UCDIR_OP_SGEMM_F32",
-                   {"UCDIR_SGEMM_P_A": qkv.ptr, "UCDIR_SGEMM_P_B": qkv.ptr + C * 2, "UCDIR_SGEMM_P_C": S.data_ptr()},
-                   {"UCDIR_SGEMM_I_BATCH": BT, "UCDIR_SGEMM_I_M": N, "UCDIR_SGEMM_I_N": N, "UCDIR_SGEMM_I_K": C,
-                    "UCDIR_SGEMM_I_LDA": 3 * C, "UCDIR_SGEMM_I_LDB": 3 * C, "UCDIR_SGEMM_I_LDC": N,
-                    "UCDIR_SGEMM_I_SA": N * 3 * C, "UCDIR_SGEMM_I_SB": N * 3 * C, "UCDIR_SGEMM_I_SC": N * N,
-                    "UCDIR_SGEMM_I_TRANSB": 1, "UCDIR_SGEMM_I_A_BF16": 1, "UCDIR_SGEMM_I_B_BF16": 1},
-                   {"UCDIR_SGEMM_F_ALPHA": 1.0 / math.sqrt(C)})
-            ol.add("UCDIR_OP_SOFTMAX_F32", {"UCDIR_SOFTMAX_P_X": S.data_ptr()},
-                   {"UCDIR_SOFTMAX_I_ROWS": BT * N, "UCDIR_SOFTMAX_I_COLS": N})
+                   tg=ws.ptr(name + ".attn.qkv.tg"), gn=1, ncls=1, nty=1, ntx=1, oy0=0, ox0=0, dst=qk, ntot=3 * C, B=BT, nt=256,
+                   dst2=vt.data_ptr(), t_col0=2 * C, t_ld=NP)
+            S = pool.get(BT * N * NS * 4)
+            zeros = ws.ptr("zeros")
+            q_act = Act(qk.buf, C, x.H, x.W, 0, keep=True)
+            s_dst = Act(S, NS, x.H, x.W, 0, keep=True)
+            _tc_op(ol, src0=q_act, src_cstride=2 * C, w=qk.ptr + C * 2, w_batched=1, w_rowstride=2 * C, w_batchstride=N * 2 * C,
+                   w_rows=N, tb=zeros, nty=1, ntx=1, oy0=0, ox0=0, dst=s_dst, ntot=NS, B=BT, nt=nt_s, dst_f32=1, ncol_valid=NS,
+                   alpha=1.0 / math.sqrt(C))
+            P = pool.get(BT * N * NP * 2)
+            ol.add("UCDIR_OP_SOFTMAX_F32", {"UCDIR_SOFTMAX_P_X": S.data_ptr(), "UCDIR_SOFTMAX_P_OUT_BF16": P.data_ptr()},
+                   {"UCDIR_SOFTMAX_I_ROWS": BT * N, "UCDIR_SOFTMAX_I_COLS": N, "UCDIR_SOFTMAX_I_IN_LD": NS, "UCDIR_SOFTMAX_I_OUT_LD": NP})
             o = bld.new(C, x.H, x.W, with_stats=False)
-            ol.add("UCDIR_OP_SGEMM_F32",
-                   {"UCDIR_SGEMM_P_A": S.data_ptr(), "UCDIR_SGEMM_P_B": qkv.ptr + 2 * C * 2, "UCDIR_SGEMM_P_C": o.ptr},
-                   {"UCDIR_SGEMM_I_BATCH": BT, "UCDIR_SGEMM_I_M": N, "UCDIR_SGEMM_I_N": C, "UCDIR_SGEMM_I_K": N,
-                    "UCDIR_SGEMM_I_LDA": N, "UCDIR_SGEMM_I_LDB": 3 * C, "UCDIR_SGEMM_I_LDC": C,
-                    "UCDIR_SGEMM_I_SA": N * N, "UCDIR_SGEMM_I_SB": N * 3 * C, "UCDIR_SGEMM_I_SC": N * C,
-                    "UCDIR_SGEMM_I_TRANSB": 0, "UCDIR_SGEMM_I_B_BF16": 1, "UCDIR_SGEMM_I_C_BF16": 1},
-                   {"UCDIR_SGEMM_F_ALPHA": 1.0})
-            pool.put(S)
-            bld.release(qkv)
+            p_act = Act(P, N, x.H, x.W, 0, keep=True)
+            _tc_op(ol, src0=p_act, src_cstride=NP, w=vt.data_ptr(), w_batched=1, w_rowstride=NP, w_batchstride=C * NP, tb=zeros,
+                   nty=1, ntx=1, oy0=0, ox0=0, dst=o, ntot=C, B=BT, nt=_tc_nt(C))
+            pool.put(S); pool.put(P); pool.put(vt)
+            bld.release(qk)
             y = bld.new(C, x.H, x.W)
             _tc_op(ol, src0=o, w=ws.ptr(name + ".attn.out.tcw"), tb=ws.ptr(name + ".attn.out.tb"), nty=1, ntx=1, oy0=0, ox0=0,
                    res=x, dst=y, ntot=C, B=BT, nt=_tc_nt(C))
