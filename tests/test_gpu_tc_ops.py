@@ -249,7 +249,7 @@ def test_tc_attention_chain(B, H, W, C):
     host, dev = run_both(c, build)
     assert_close(dev["qk"], host["qk"], "q,k")
     assert_close(dev["vt"][..., :N], host["vt"][..., :N], "V^T")
-    assert_close(dev["S"][..., :N], host["S"][..., :N], "scores", rtol=1e-2, atol=1e-2)
+    # S is scratch after the softmax (the kernel keeps the exponentials in place), so P is what is compared
     assert_close(dev["P"], host["P"], "softmax")
     assert_close(dev["O"], host["O"], "O = P V")
     q, k = dev["qk"].float().reshape(B, N, 2 * C).split(C, dim=-1)
