@@ -161,7 +161,12 @@ struct TcCfg {
 
 // bf16 path: the result is rounded to 8 mantissa bits, so MUFU.EX2 / MUFU.RCP accuracy is ample (5 instructions
 // instead of ~20 for the IEEE division of the fp32 parity path's swish_f).
-__device__ __forceinline__ float swish_fast(float x) { return x * __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float swish_fast(float x) { return x * rcp_approx(1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
@@ -379,7 +384,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             const float4 b = __ldg(reinterpret_cast<const float4*>(tb + c0 + j));
             if (tg) {
               const float4 g = __ldg(reinterpret_cast<const float4*>(tg + c0 + j));
-              v[j + 0] = fmaf(-mr, g.x, b.x); v[j + 1] = fmaf(-mr, g.y, b.y); v[j + 2] = fmaf(-mr, g.z, b.z); v[j + 3] = fmaf(-mr, g.w, b.w);
+              const float2 nm = make_float2(-mr, -mr);
+              const float2 lo = __ffma2_rn(nm, make_float2(g.x, g.y), make_float2(b.x, b.y));
+              const float2 hi = __ffma2_rn(nm, make_float2(g.z, g.w), make_float2(b.z, b.w));
+              v[j + 0] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
             } else { v[j + 0] = b.x; v[j + 1] = b.y; v[j + 2] = b.z; v[j + 3] = b.w; }
           }
         }
@@ -388,8 +396,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         if (CH == 32) tmem_ld32(taddr, rv); else tmem_ld16(taddr, rv);
         tmem_ld_wait();
         if (!valid) continue;
+        {
+          const float2 rs2 = make_float2(rstd, rstd);
 #pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = fmaf(__uint_as_float(rv[j]), rstd, v[j]);
+          for (int j = 0; j < CH; j += 2) {     // packed fp32 pairs (FFMA2)
+            const float2 t = __ffma2_rn(make_float2(__uint_as_float(rv[j]), __uint_as_float(rv[j + 1])), rs2, make_float2(v[j], v[j + 1]));
+            v[j] = t.x; v[j + 1] = t.y;
+          }
+        }
         if (p.mode == 1) {
           // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
           const int cbase = (ncol0 + c0) >> 3;
@@ -397,9 +411,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           const __nv_bfloat16* rres = reinterpret_cast<const __nv_bfloat16*>(&res_mix);
 #pragma unroll
           for (int c = 0; c < NO; ++c) {
-            float h = 0.f;
+            float2 h2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int s = 0; s < 8; ++s) h = fmaf(v[c * 8 + s], aw[s], h);
+            for (int s = 0; s < 8; s += 2) h2 = __ffma2_rn(make_float2(v[c * 8 + s], v[c * 8 + s + 1]), make_float2(aw[s], aw[s + 1]), h2);
+            const float h = h2.x + h2.y;
             const float t = swish_fast(h) + __bfloat162float(rres[c]);
             o[c] = __float2bfloat16(t);
             const float tr = __bfloat162float(o[c]);
