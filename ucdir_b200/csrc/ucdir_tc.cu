@@ -140,8 +140,9 @@ struct TcParams {
   __nv_bfloat16* dst2; int t_col0, t_ld;   // columns >= t_col0 are stored transposed: dst2[img][col - t_col0][pixel], row pitch t_ld
 };
 
-constexpr int TC_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 8;           // two per TMEM lane quadrant
+constexpr int TC_FIRST_EPI_WARP = 4;      // warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps}: shrinks to 88 registers
+constexpr int TC_THREADS = 32 * (TC_FIRST_EPI_WARP + TC_EPI_WARPS);   // warpgroups 1..2 = epilogue: grow to 208 registers
 
 // KA: channels per A slab row (64/32/16 -> 128/64/32-byte swizzled rows); KB: K elements per B slab row;
 // NT: output columns per work item; NSPLIT: independent column groups of an item that read different K slices of
@@ -153,7 +154,7 @@ struct TcCfg {
   static constexpr int B_PAD = (B_BYTES + 1023) & ~1023;
   static constexpr int STAGE = A_BYTES + B_PAD;
   static constexpr int STAGES_RAW = 196608 / STAGE;
-  static constexpr int STAGES = STAGES_RAW > 12 ? 12 : (STAGES_RAW < 4 ? 4 : STAGES_RAW);
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 4 ? 4 : STAGES_RAW);   // <= 8: the rest of the 228 KB stays L1 for the epilogue's loads
   static constexpr int SLOTW = NT < 32 ? 32 : NT;          // TMEM columns per accumulator slot
   static constexpr int NSLOT = 512 / SLOTW;                // accumulator ring: MMA of item i+1.. overlaps epilogue of item i
   static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + (2 * STAGES + 2 * NSLOT) * 8 + 64;
@@ -202,7 +203,10 @@ struct ItemCursor {
 // Persistent CTA (one per SM).  A CTA owns a contiguous range of work items.  Three pipelines:
 //   smem ring   full[s]/empty[s]            TMA producer  <-> MMA issuer
 //   TMEM ring   tmem_full[j]/tmem_empty[j]  MMA issuer    <-> epilogue warps   (NSLOT accumulators of NT columns)
-template <int KA, int KB, int NT, int NSPLIT>
+// EPI selects the epilogue at compile time (the chunk loop is the hot code of the small-K layers):
+enum { EPI_PLAIN = 0, EPI_MIX = 1, EPI_F32 = 2, EPI_PLAIN_T = 3 };
+
+template <int KA, int KB, int NT, int NSPLIT, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                 const __grid_constant__ CUtensorMap mapA1,
                                                                 const __grid_constant__ CUtensorMap mapB, const TcParams p) {
@@ -237,7 +241,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
+  // Register reallocation between warpgroups (setmaxnreg is warpgroup-wide, first statement of each role branch):
+  // the epilogue keeps a chunk of accumulators, its folded-GroupNorm terms and the next chunk's table values in flight.
+  if (warp < TC_FIRST_EPI_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
     const uint32_t tx_bytes = (uint32_t)(p.bw * p.bh * p.bn * KA * 2 + NT * KB * 2);
@@ -304,10 +311,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       }
       if (++slot == NSLOT) { slot = 0; sph ^= 1; }
     }
+  }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int q = warp & 3;                          // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;                // two warps per quadrant take alternate column chunks
+    const int half = (warp - TC_FIRST_EPI_WARP) >> 2;  // two warps per quadrant take alternate column chunks
     const int r = q * 32 + lane;                     // accumulator row = pixel slot of the tile
     const int box = p.bw * p.bh;
     const int nn = r / box, rr = r - nn * box;
@@ -349,7 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         }
         pix_in = ((size_t)img * p.H + y) * p.W + x;
         pix_out = p.dstUp ? ((size_t)img * 2 * p.H + 2 * y + p.dstPy) * (2 * p.W) + 2 * x + p.dstPx : pix_in;
-        if (p.mode == 1) {
+        if (EPI == EPI_MIX) {
           const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.att + pix_in * 8));
           const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.att + pix_in * 8 + 4));
           const float* w8 = p.attw + (size_t)img * p.attwStride;
@@ -360,35 +369,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const float* tb = p.tb + (size_t)cls * p.Ntot + ncol0;
       const float* tg = p.tg ? p.tg + (size_t)cls * p.Ntot + ncol0 : nullptr;
       float t1s = 0.f, t2s = 0.f;
+      // Per-column additive term of the folded GroupNorm, cadd[j] = TB[cls][n] - mean*rstd*TG[cls][n]: the table loads
+      // are issued one chunk ahead (and, for the first chunk, before waiting for the accumulator) so their L2 latency
+      // overlaps the MMA wait / the previous chunk's math instead of stalling every chunk.
+      constexpr int CSTEP = (TC_EPI_WARPS / 4) * CH;
+      float cadd[CH];
+      float4 tb4[CH / 4], tg4[CH / 4];
+      auto issue_tables = [&](int c0) {
+#pragma unroll
+        for (int j = 0; j < CH / 4; ++j) {
+          tb4[j] = __ldg(reinterpret_cast<const float4*>(tb + c0) + j);
+          tg4[j] = tg ? __ldg(reinterpret_cast<const float4*>(tg + c0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto finish_tables = [&]() {
+        const float2 nm = make_float2(-mr, -mr);
+#pragma unroll
+        for (int j = 0; j < CH / 4; ++j) {
+          const float2 lo = __ffma2_rn(nm, make_float2(tg4[j].x, tg4[j].y), make_float2(tb4[j].x, tb4[j].y));
+          const float2 hi = __ffma2_rn(nm, make_float2(tg4[j].z, tg4[j].w), make_float2(tb4[j].z, tb4[j].w));
+          cadd[4 * j + 0] = lo.x; cadd[4 * j + 1] = lo.y; cadd[4 * j + 2] = hi.x; cadd[4 * j + 3] = hi.y;
+        }
+      };
+      if (valid && half * CH < NT) { issue_tables(half * CH); finish_tables(); }
       mbar_wait(&tmem_full[slot], sph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = half * CH; c0 < NT; c0 += 2 * CH) {
-        // issue the global loads this chunk needs (residual, epilogue tables) before waiting on the TMEM load
+      for (int c0 = half * CH; c0 < NT; c0 += CSTEP) {
+        // issue the residual load this chunk needs before waiting on the TMEM load
         constexpr int NO = CH / 8;
         uint2 res_mix = make_uint2(0u, 0u);
         uint4 res_pl[CH / 8];
-        float v[CH];                                  // starts as the per-column additive term, then the folded value
         if (valid) {
-          if (p.mode == 1) {
+          if (EPI == EPI_MIX) {
             const __nv_bfloat16* rp = p.res + pix_in * p.resC + ((ncol0 + c0) >> 3);
             if (NO == 4) res_mix = __ldg(reinterpret_cast<const uint2*>(rp));
             else res_mix.x = __ldg(reinterpret_cast<const uint32_t*>(rp));
-          } else if (p.res) {
+          } else if (EPI != EPI_F32 && p.res) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix_in * p.resC + ncol0 + c0);
 #pragma unroll
             for (int j = 0; j < CH / 8; ++j) res_pl[j] = __ldg(rp + j);
-          }
-#pragma unroll
-          for (int j = 0; j < CH; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(tb + c0 + j));
-            if (tg) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(tg + c0 + j));
-              const float2 nm = make_float2(-mr, -mr);
-              const float2 lo = __ffma2_rn(nm, make_float2(g.x, g.y), make_float2(b.x, b.y));
-              const float2 hi = __ffma2_rn(nm, make_float2(g.z, g.w), make_float2(b.z, b.w));
-              v[j + 0] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
-            } else { v[j + 0] = b.x; v[j + 1] = b.y; v[j + 2] = b.z; v[j + 3] = b.w; }
           }
         }
         uint32_t rv[32];
@@ -396,15 +416,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         if (CH == 32) tmem_ld32(taddr, rv); else tmem_ld16(taddr, rv);
         tmem_ld_wait();
         if (!valid) continue;
+        float v[CH];
         {
           const float2 rs2 = make_float2(rstd, rstd);
 #pragma unroll
           for (int j = 0; j < CH; j += 2) {     // packed fp32 pairs (FFMA2)
-            const float2 t = __ffma2_rn(make_float2(__uint_as_float(rv[j]), __uint_as_float(rv[j + 1])), rs2, make_float2(v[j], v[j + 1]));
+            const float2 t = __ffma2_rn(make_float2(__uint_as_float(rv[j]), __uint_as_float(rv[j + 1])), rs2, make_float2(cadd[j], cadd[j + 1]));
             v[j] = t.x; v[j + 1] = t.y;
           }
         }
-        if (p.mode == 1) {
+        const bool more = c0 + CSTEP < NT;
+        if (more) issue_tables(c0 + CSTEP);            // in flight while this chunk's epilogue math runs
+        if (EPI == EPI_MIX) {
           // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
           const int cbase = (ncol0 + c0) >> 3;
           __align__(8) __nv_bfloat16 o[NO];
@@ -429,7 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = swish_fast(v[j]);
           }
-          if (p.res) {
+          if (EPI != EPI_F32 && p.res) {
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&res_pl[j / 8]);
@@ -440,12 +463,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               }
             }
           }
-          if (p.dst_f32) {
+          if (EPI == EPI_F32) {
             float* d = reinterpret_cast<float*>(p.dst) + pix_out * p.dstC + p.dstCoff + nb;
 #pragma unroll
             for (int j = 0; j < CH; ++j)
               if (nb + j < p.ncol_valid) { d[j] = v[j]; t1s += v[j]; t2s += v[j] * v[j]; }
-          } else if (p.dst2 && nb >= p.t_col0) {
+          } else if (EPI == EPI_PLAIN_T && nb >= p.t_col0) {
             // transposed store (attention V^T): lanes hold consecutive pixels, so each store is one coalesced run
             __nv_bfloat16* d = p.dst2 + ((size_t)img * (p.Ntot - p.t_col0) + (nb - p.t_col0)) * p.t_ld + (y * p.W + x);
 #pragma unroll
@@ -465,6 +488,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             }
           }
         }
+        if (more) finish_tables();
       }
       // this warp is done reading the accumulator slot: hand it back to the MMA issuer
       tc_fence_before();
@@ -552,16 +576,16 @@ static void choose_tile(int W, int H, int B, int stride, int* bw, int* bh, int* 
   *bw = bbw; *bh = bbh; *bn = bbn;
 }
 
-template <int KA, int KB, int NT, int NSPLIT>
+template <int KA, int KB, int NT, int NSPLIT, int EPI>
 static int launch_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t st) {
   using S = TcCfg<KA, KB, NT, NSPLIT>;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(tc_conv_kernel<KA, KB, NT, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tc_conv_kernel<KA, KB, NT, NSPLIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
       set_error("tc_conv: cannot opt in to %d bytes of shared memory: %s", S::TOTAL, cudaGetErrorString(cudaGetLastError())); return -3; }
     attr = true;
   }
-  tc_conv_kernel<KA, KB, NT, NSPLIT><<<grid, TC_THREADS, S::TOTAL, st>>>(a0, a1, b, p);
+  tc_conv_kernel<KA, KB, NT, NSPLIT, EPI><<<grid, TC_THREADS, S::TOTAL, st>>>(a0, a1, b, p);
   return 0;
 }
 
@@ -649,12 +673,14 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
   const long long items = (long long)mt * (p.Ntot / NT);
   dim3 grid((unsigned)(items < n_sm ? items : n_sm), 1, 1);      // persistent: one CTA per SM
-#define INST(ka, kb, nt, ns) if (KC == ka && KB == kb && NT == nt && NSPLIT == ns) { rc = launch_inst<ka, kb, nt, ns>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
-  INST(64, 64, 16, 1) INST(64, 64, 64, 1) INST(64, 64, 128, 1) INST(64, 64, 256, 1)
-  INST(16, 16, 64, 1)
-  INST(32, 16, 256, 4) INST(32, 16, 256, 2) INST(32, 32, 256, 1)
+  const int epi = p.mode == 1 ? EPI_MIX : (p.dst_f32 ? EPI_F32 : (p.dst2 ? EPI_PLAIN_T : EPI_PLAIN));
+#define INST(ka, kb, nt, ns, ep) if (KC == ka && KB == kb && NT == nt && NSPLIT == ns && epi == ep) { rc = launch_inst<ka, kb, nt, ns, ep>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
+  INST(64, 64, 64, 1, EPI_PLAIN) INST(64, 64, 128, 1, EPI_PLAIN) INST(64, 64, 256, 1, EPI_PLAIN) INST(16, 16, 64, 1, EPI_PLAIN)
+  INST(64, 64, 256, 1, EPI_PLAIN_T) INST(64, 64, 128, 1, EPI_PLAIN_T)
+  INST(64, 64, 16, 1, EPI_F32) INST(64, 64, 64, 1, EPI_F32) INST(64, 64, 128, 1, EPI_F32) INST(64, 64, 256, 1, EPI_F32)
+  INST(32, 16, 256, 4, EPI_MIX) INST(32, 16, 256, 2, EPI_MIX) INST(32, 32, 256, 1, EPI_MIX) INST(64, 64, 256, 1, EPI_MIX)
 #undef INST
-  set_error("tc_conv: no kernel instance for KC=%d KB=%d NT=%d NSPLIT=%d", KC, KB, NT, NSPLIT);
+  set_error("tc_conv: no kernel instance for KC=%d KB=%d NT=%d NSPLIT=%d epilogue %d", KC, KB, NT, NSPLIT, epi);
   return -2;
 }
 
