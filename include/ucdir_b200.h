@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define UCDIR_ABI_VERSION 9
+#define UCDIR_ABI_VERSION 11
 
 #define UCDIR_OP_NPTR 16
 #define UCDIR_OP_NINT 48
@@ -65,7 +65,10 @@ enum ucdir_op_kind {
   UCDIR_OP_TC_ATTN = 11,
   UCDIR_OP_GN_APPLY_BF16 = 12,
   UCDIR_OP_CAST = 13,
-  UCDIR_OP_CROP_TILES = 14
+  UCDIR_OP_CROP_TILES = 14,
+  UCDIR_OP_GN_STATS_F32 = 15,
+  UCDIR_OP_GN_APPLY_F32 = 16,
+  UCDIR_OP_LAYOUT = 17
 };
 
 /* ---- UCDIR_OP_CONV_F32: dst = epilogue( conv( prologue(concat(src0, src1)) ) ) -----------------
@@ -98,7 +101,8 @@ enum ucdir_conv_int {
   UCDIR_CONV_I_DST_C = 15, UCDIR_CONV_I_DST_COFF = 16,               /* dst channel stride / offset */
   UCDIR_CONV_I_DST_UP = 17, UCDIR_CONV_I_DST_PY = 18, UCDIR_CONV_I_DST_PX = 19,
   UCDIR_CONV_I_RES_C = 20, UCDIR_CONV_I_ATTW_STRIDE = 21,            /* floats between samples in ATTW */
-  UCDIR_CONV_I_GN_GROUPS = 22                                        /* 1 (default) or G for the FiLM block */
+  UCDIR_CONV_I_GN_GROUPS = 22,                                       /* must be 1: G > 1 uses UCDIR_OP_GN_APPLY_F32 */
+  UCDIR_CONV_I_FILM_STRIDE = 23                                      /* floats between samples in FILM_G / FILM_B (0 = COUT) */
 };
 enum ucdir_conv_flt { UCDIR_CONV_F_EPS = 0 };
 
@@ -149,12 +153,12 @@ enum ucdir_gather_int {
  * OWNER_Y[IMG_H] / OWNER_X[IMG_W]: index of the tile row / column whose interior owns that image row /
  * column (the LAST window in reference order, utils/util.py:124-145), -1 = never written (zeros).
  * Y0[NTY] / X0[NTX]: window origins in padded coordinates.  Tile index = (img*NTY + ty)*NTX + tx.
- * MODE 0: OUT = eps.   MODE 1: x0 = clamp(A*x - B*eps); OUT = C1*x0 + C2*x + SIGMA*noise
+ * MODE 0: OUT = eps.   MODE 1: x0 = clamp(A*x - B*eps); OUT = C1*x0 + C2*x + C3*eps + SIGMA*noise
  * (model/diffusion.py:150-158,171-172,182-183; NOISE NULL => 0; CLIP=0 skips the clamp).                     */
 enum ucdir_scatter_ptr {
   UCDIR_SCATTER_P_EPS = 0, UCDIR_SCATTER_P_OWNER_Y = 1, UCDIR_SCATTER_P_OWNER_X = 2, UCDIR_SCATTER_P_Y0 = 3,
   UCDIR_SCATTER_P_X0 = 4, UCDIR_SCATTER_P_XT = 5, UCDIR_SCATTER_P_NOISE = 6, UCDIR_SCATTER_P_OUT = 7,
-  UCDIR_SCATTER_P_PARAMS = 8   /* optional device float[7] {A, B, C1, C2, SIGMA, clip, use_noise} overriding f[] / CLIP / NOISE:
+  UCDIR_SCATTER_P_PARAMS = 8   /* optional device float[8] {A, B, C1, C2, SIGMA, clip, use_noise, C3} overriding f[] / CLIP / NOISE:
                                   lets a captured CUDA graph be replayed for every step of the schedule */
 };
 enum ucdir_scatter_int {
@@ -163,7 +167,8 @@ enum ucdir_scatter_int {
   UCDIR_SCATTER_I_CE = 8, UCDIR_SCATTER_I_MODE = 9, UCDIR_SCATTER_I_CLIP = 10, UCDIR_SCATTER_I_C = 11
 };
 enum ucdir_scatter_flt {
-  UCDIR_SCATTER_F_A = 0, UCDIR_SCATTER_F_B = 1, UCDIR_SCATTER_F_C1 = 2, UCDIR_SCATTER_F_C2 = 3, UCDIR_SCATTER_F_SIGMA = 4
+  UCDIR_SCATTER_F_A = 0, UCDIR_SCATTER_F_B = 1, UCDIR_SCATTER_F_C1 = 2, UCDIR_SCATTER_F_C2 = 3, UCDIR_SCATTER_F_SIGMA = 4,
+  UCDIR_SCATTER_F_C3 = 5   /* DDIM (model/diffusion.py:287): OUT = C1*x0 + C2*x + C3*eps + SIGMA*noise */
 };
 
 /* ---- UCDIR_OP_MAXPOOL2: DST[B,H,W,C] = max 2x2 of SRC[B,2H,2W,C] (fp32 NHWC) -------------------------- */
@@ -209,6 +214,14 @@ enum ucdir_gna_ptr { UCDIR_GNA_P_SRC = 0, UCDIR_GNA_P_DST = 1, UCDIR_GNA_P_GAMMA
 enum ucdir_gna_int { UCDIR_GNA_I_B = 0, UCDIR_GNA_I_HW = 1, UCDIR_GNA_I_C = 2, UCDIR_GNA_I_SWISH = 3 };
 
 /* ---- UCDIR_OP_CAST: p[1][k] = cast(p[0][k]) for k < i[0] + (i[1] << 31); i[2] = 0: fp32 -> bf16, 1: bf16 -> fp32 -- */
+
+/* ---- UCDIR_OP_GN_STATS_F32 / UCDIR_OP_GN_APPLY_F32: GroupNorm(G, C) with G >= 1 on fp32 NHWC [B][HW][C], for the SR3-style
+ * FiLM ResnetBlock (model/ucdir.py:75-100).  STATS = double[B][G][2] {sum, sum of squares}; APPLY: f[0] = eps, SWISH as above. */
+enum ucdir_gns_ptr { UCDIR_GNS_P_SRC = 0, UCDIR_GNS_P_STATS = 1 };
+enum ucdir_gnf_ptr { UCDIR_GNF_P_SRC = 0, UCDIR_GNF_P_DST = 1, UCDIR_GNF_P_GAMMA = 2, UCDIR_GNF_P_BETA = 3, UCDIR_GNF_P_STATS = 4 };
+enum ucdir_gns_int { UCDIR_GNS_I_B = 0, UCDIR_GNS_I_HW = 1, UCDIR_GNS_I_C = 2, UCDIR_GNS_I_G = 3, UCDIR_GNS_I_SWISH = 4 };
+
+/* ---- UCDIR_OP_LAYOUT: fp32 layout change, p[0] -> p[1]; i = {B, C, HW, DIR}; DIR 0: NCHW -> NHWC, 1: NHWC -> NCHW ---------- */
 
 /* ---- UCDIR_OP_CROP_TILES: DST[BT,IH,IW,4] = SRC[BT,TH,TW,4][:, OY:OY+IH, OX:OX+IW] (fp32): the tile interiors that are
  * stitched (utils/util.py:144-145) and, in tile-sharded mode, all-gathered once per step ------------------------ */

@@ -347,6 +347,36 @@ def p_sample_loop(sched, denoise, x_in: Tensor, guide: Tensor, noises: Sequence[
     return ret if continous else ret[-1]
 
 
+def ddim_sample(sched: Dict[str, np.ndarray], denoise, x_in: Tensor, guide: Tensor, noises: Sequence[Tensor],
+                sampling_timesteps: int = 5, eta: float = 1.0) -> Tensor:
+    """GaussianDiffusion.ddim_sample + model_predictions, model/diffusion.py:213-294 (objective 'pred_noise',
+    clip_x_start=True, no re-derivation of the noise).  noises[0] is the initial image, noises[1..] the per-step z.
+    Returns the stacked trajectory [B, 1 + steps, C, H, W] (continous=True layout)."""
+    T = len(sched["betas"])
+    times = list(reversed(torch.linspace(-1, T - 1, steps=sampling_timesteps + 1).int().tolist()))
+    ac = torch.from_numpy(sched["alphas_cumprod"])
+    img = noises[0]
+    imgs = [img]
+    k = 1
+    b = x_in.shape[0]
+    for time, time_next in zip(times[:-1], times[1:]):
+        level = torch.FloatTensor([sched["sqrt_alphas_cumprod_prev_f64"][time + 1]]).repeat(b, 1)
+        eps = denoise(torch.cat([x_in, img], dim=1), level, guide)
+        x0 = torch.tensor(sched["sqrt_recip_alphas_cumprod"][time]) * img - torch.tensor(sched["sqrt_recipm1_alphas_cumprod"][time]) * eps
+        x0 = x0.clamp(-1.0, 1.0)
+        if time_next < 0:
+            img = x0
+            imgs.append(img)
+            continue
+        alpha, alpha_next = ac[time], ac[time_next]
+        sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+        c = (1 - alpha_next - sigma ** 2).sqrt()
+        img = x0 * alpha_next.sqrt() + c * eps + sigma * noises[k]
+        k += 1
+        imgs.append(img)
+    return torch.stack(imgs, dim=1)
+
+
 def super_resolution(sd: SD, layout: UNetLayout, sched, x_in: Tensor, noises: Sequence[Tensor],
                      continous: bool = False, skip: int = 1024, padding: int = 64,
                      force_tiler: bool = False) -> Tuple[Tensor, Tensor]:

@@ -162,5 +162,34 @@ def main():
          geom=np.array([64, 16], dtype=np.int64))
 
 
+def main_ddim():
+    """6. ddim_sample (model/diffusion.py:246-294) on the full sid model: T=10 schedule, 5 sampling steps, eta=1."""
+    opt = yaml.safe_load(open(os.path.join(REF, "config/sid.yaml")))
+    g = torch.Generator().manual_seed(INPUT_SEED + 5)
+    torch.manual_seed(WEIGHT_SEED)
+    net = refnet.define_G(opt).eval()
+    assert sd_digest(net.state_dict()) == str(np.load(os.path.join(OUT, "unet.npz"))["digest"])
+    so = dict(schedule="linear", n_timestep=10, linear_start=1e-6, linear_end=0.4)
+    net.set_new_noise_schedule(so, torch.device("cpu"))
+    x_in = torch.rand(1, 3, 64, 64, generator=g) * 2 - 1
+    with torch.no_grad():
+        initx = net.predictor(x_in)
+    ng = torch.Generator().manual_seed(NOISE_SEED + 1)
+    noises = [torch.randn(1, 3, 64, 64, generator=ng) for _ in range(5)]
+    it = iter(noises)
+    refdiff.torch.randn, refdiff.torch.randn_like = (lambda *a, **k: next(it)), (lambda *a, **k: next(it))
+    try:
+        with torch.no_grad():
+            traj = net.ddim_sample(x_in, continous=True, kwargs={"guide": initx})
+    finally:
+        refdiff.torch.randn, refdiff.torch.randn_like = torch.randn, torch.randn_like
+    save("ddim", x_in=x_in.numpy(), initx=initx.numpy(), noises=torch.stack(noises).numpy(), traj=traj.numpy(),
+         sched=np.array([10, 1e-6, 0.4], dtype=np.float64))
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-ddim" in sys.argv:
+        main_ddim()
+    else:
+        main()
+        main_ddim()

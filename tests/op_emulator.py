@@ -125,9 +125,11 @@ def emu_conv(op, mem):
     else:
         fb = _p(op, "UCDIR_CONV_P_FILM_B")
         if fb:
-            b_ = mem.view(fb, (B, Cout)).view(B, 1, 1, Cout)
+            fs = _i(op, "UCDIR_CONV_I_FILM_STRIDE") or Cout
+            row = lambda ptr: torch.stack([mem.view(ptr + b * fs * 4, (Cout,)) for b in range(B)]).view(B, 1, 1, Cout)
+            b_ = row(fb)
             fg = _p(op, "UCDIR_CONV_P_FILM_G")
-            y = (1 + mem.view(fg, (B, Cout)).view(B, 1, 1, Cout)) * y + b_ if fg else y + b_
+            y = (1 + row(fg)) * y + b_ if fg else y + b_
         if act == 1:
             y = swish(y)
         elif act == 2:
@@ -279,8 +281,8 @@ def emu_scatter(op, mem):
     pp = _p(op, "UCDIR_SCATTER_P_PARAMS")
     npz = _p(op, "UCDIR_SCATTER_P_NOISE")
     if pp:
-        pv = mem.view(pp, (7,))
-        names = ["A", "B", "C1", "C2", "SIGMA"]
+        pv = mem.view(pp, (8,))
+        names = ["A", "B", "C1", "C2", "SIGMA", "_clip", "_noise", "C3"]
         f = lambda n: pv[names.index(n)].clone()
         clip = bool(pv[5] != 0)
         if pv[6] == 0:
@@ -291,6 +293,8 @@ def emu_scatter(op, mem):
     if clip:
         x0_ = x0_.clamp(-1.0, 1.0)
     mean = f("C1") * x0_ + f("C2") * xt
+    if float(f("C3")) != 0.0:
+        mean = mean + f("C3") * e
     z = mem.view(npz, (BI, Cc, IH, IW)) if npz else torch.zeros_like(xt)
     out.copy_(mean + z * f("SIGMA"))
 
@@ -450,12 +454,43 @@ def emu_crop(op, mem):
     mem.view(_p(op, "UCDIR_CROP_P_DST"), (BT, IH, IW, 4)).copy_(src[:, OY:OY + IH, OX:OX + IW])
 
 
+def emu_gn_stats(op, mem):
+    g = lambda n: _i(op, "UCDIR_GNS_I_" + n)
+    B, HW, Cc, G = g("B"), g("HW"), g("C"), g("G")
+    x = mem.view(_p(op, "UCDIR_GNS_P_SRC"), (B, HW, G, Cc // G)).double()
+    st = mem.view(_p(op, "UCDIR_GNS_P_STATS"), (B, G, 2), torch.float64)
+    st[..., 0] = x.sum((1, 3)); st[..., 1] = (x * x).sum((1, 3))
+
+
+def emu_gn_apply_f32(op, mem):
+    g = lambda n: _i(op, "UCDIR_GNS_I_" + n)
+    B, HW, Cc, G, sw = g("B"), g("HW"), g("C"), g("G"), g("SWISH")
+    x = mem.view(_p(op, "UCDIR_GNF_P_SRC"), (B, HW, G, Cc // G))
+    st = mem.view(_p(op, "UCDIR_GNF_P_STATS"), (B, G, 2), torch.float64)
+    cnt = float(HW * (Cc // G))
+    mean = st[..., 0] / cnt
+    var = (st[..., 1] / cnt - mean * mean).clamp_min(0)
+    rstd = (1.0 / torch.sqrt(var + float(op.f[0]))).float().view(B, 1, G, 1)
+    y = ((x - mean.float().view(B, 1, G, 1)) * rstd).reshape(B, HW, Cc)
+    y = y * mem.view(_p(op, "UCDIR_GNF_P_GAMMA"), (Cc,)) + mem.view(_p(op, "UCDIR_GNF_P_BETA"), (Cc,))
+    mem.view(_p(op, "UCDIR_GNF_P_DST"), (B, HW, Cc)).copy_(swish(y) if sw else y)
+
+
+def emu_layout(op, mem):
+    B, Cc, HW, d = int(op.i[0]), int(op.i[1]), int(op.i[2]), int(op.i[3])
+    if d == 0:
+        mem.view(int(op.p[1]), (B, HW, Cc)).copy_(mem.view(int(op.p[0]), (B, Cc, HW)).transpose(1, 2))
+    else:
+        mem.view(int(op.p[1]), (B, Cc, HW)).copy_(mem.view(int(op.p[0]), (B, HW, Cc)).transpose(1, 2))
+
+
 DISPATCH = {
     K["UCDIR_OP_CONV_F32"]: emu_conv, K["UCDIR_OP_SGEMM_F32"]: emu_sgemm, K["UCDIR_OP_SOFTMAX_F32"]: emu_softmax,
     K["UCDIR_OP_GUIDANCE"]: emu_guidance, K["UCDIR_OP_TIME_EMBED"]: emu_time_embed,
     K["UCDIR_OP_GATHER_TILES"]: emu_gather, K["UCDIR_OP_SCATTER"]: emu_scatter, K["UCDIR_OP_MAXPOOL2"]: emu_maxpool,
     K["UCDIR_OP_MEMSET"]: emu_memset, K["UCDIR_OP_TC_CONV"]: emu_tc_conv, K["UCDIR_OP_GN_APPLY_BF16"]: emu_gn_apply,
-    K["UCDIR_OP_CAST"]: emu_cast, K["UCDIR_OP_CROP_TILES"]: emu_crop,
+    K["UCDIR_OP_CAST"]: emu_cast, K["UCDIR_OP_CROP_TILES"]: emu_crop, K["UCDIR_OP_GN_STATS_F32"]: emu_gn_stats,
+    K["UCDIR_OP_GN_APPLY_F32"]: emu_gn_apply_f32, K["UCDIR_OP_LAYOUT"]: emu_layout,
 }
 
 LAUNCHED = []

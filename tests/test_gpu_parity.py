@@ -195,3 +195,30 @@ def test_full_size_properties_1024_tiled(net, sd, layout, monkeypatch):
     net._noise_source = None
     sigma = float(np.exp(np.float32(0.5) * net._sched_host["posterior_log_variance_clipped"][10]))
     close(a - b, sigma * z, rtol=1e-4, atol=2e-5, what="posterior linear in z")
+
+
+def test_film_resnet_block_golden(golden):
+    """SURVEY 8 a14 on the GPU: FiLM ResnetBlock (8-group GroupNorm, additive and affine FiLM) vs the reference's output."""
+    from ucdir_b200.model.ucdir import ResnetBlock
+    g = golden("modules")
+    for tag, aff in (("film", False), ("filmaff", True)):
+        m = ResnetBlock(16, 32, nl_emb_dim=64, use_affine_level=aff, norm_groups=8)
+        m.load_state_dict({k[len(tag) + 3:]: T(g[k]) for k in g.files if k.startswith(tag + ".w.")}, strict=True)
+        y = m.cuda()(T(g[tag + ".x"]).cuda(), T(g[tag + ".t"]).cuda())
+        close(y, g[tag + ".y"], what="FiLM ResnetBlock " + tag)
+
+
+def test_ddim_sample_golden(net, golden):
+    """SURVEY 8f#2: ddim_sample (5 strided steps, eta=1) vs the reference's trajectory with injected noise."""
+    g = golden("ddim")
+    n, ls, le = g["sched"]
+    net.set_new_noise_schedule(dict(schedule="linear", n_timestep=int(n), linear_start=float(ls), linear_end=float(le)),
+                               torch.device("cuda"))
+    noises = iter([T(z) for z in g["noises"]])
+    net._noise_source = lambda shape: next(noises)
+    try:
+        traj = net.ddim_sample(T(g["x_in"]).cuda(), True, kwargs={"guide": T(g["initx"]).cuda()})
+    finally:
+        net._noise_source = None
+        net.set_new_noise_schedule(ucdir_b200.SID_VAL_SCHEDULE, torch.device("cuda"))
+    close(traj, g["traj"], what="ddim trajectory")

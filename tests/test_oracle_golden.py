@@ -100,3 +100,17 @@ def test_tile_windows_match_reference_rule():
     assert O.tile_windows(1056, 128, 16) == [min(i, 1056 - 128) for i in range(0, 1056, 96)]
     assert len(O.tile_windows(1056, 128, 16)) == 11
     assert O.tiler_pad(1024, 1024, 128, 16) == 16 and O.tiler_pad(96, 80, 128, 16) == 128 - 80 + 16
+
+
+def test_ddim_sample(golden, sid_weights):
+    """SURVEY 8f#2: the strided sampler (model/diffusion.py:246-294) restated in the oracle vs the reference's trajectory."""
+    import ucdir_b200
+    _, sd = sid_weights
+    g = golden("ddim")
+    n, ls, le = g["sched"]
+    sched = O.schedule_buffers(dict(schedule="linear", n_timestep=int(n), linear_start=float(ls), linear_end=float(le)))
+    lay = O.UNetLayout(**ucdir_b200.SID_MODEL_OPT["unet"])
+    den = lambda xc, lvl, gd: O.unet_forward(sd, "denoise_fn.", lay, xc, lvl, gd)
+    with torch.no_grad():
+        traj = O.ddim_sample(sched, den, T(g["x_in"]), T(g["initx"]), [T(z) for z in g["noises"]])
+    close(traj, g["traj"], rtol=1e-4, atol=2e-5)

@@ -44,6 +44,9 @@ static int dispatch(const ucdir_op_t& op, cudaStream_t st, bool dry) {
     case UCDIR_OP_GN_APPLY_BF16: return launch_gn_apply_bf16(op, st, dry);
     case UCDIR_OP_CAST: return launch_cast(op, st, dry);
     case UCDIR_OP_CROP_TILES: return launch_crop_tiles(op, st, dry);
+    case UCDIR_OP_GN_STATS_F32: return launch_gn_stats_f32(op, st, dry);
+    case UCDIR_OP_GN_APPLY_F32: return launch_gn_apply_f32(op, st, dry);
+    case UCDIR_OP_LAYOUT: return launch_layout(op, st, dry);
     default: set_error("unknown op kind %d", op.kind); return -1;
   }
 }

@@ -58,5 +58,8 @@ int launch_tc_attn(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_gn_apply_bf16(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_cast(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_crop_tiles(const ucdir_op_t& op, cudaStream_t st, bool dry);
+int launch_gn_stats_f32(const ucdir_op_t& op, cudaStream_t st, bool dry);
+int launch_gn_apply_f32(const ucdir_op_t& op, cudaStream_t st, bool dry);
+int launch_layout(const ucdir_op_t& op, cudaStream_t st, bool dry);
 
 }  // namespace ucdir

@@ -12,7 +12,7 @@ struct ConvP {
   const float* res; const float* att; const float* attw; float* dst; double* dst_stats;
   const float* film_g; const float* film_b;
   int B, H, W, C0, C1, Cout, ks, stride, up, groups, pre, act, mode, srcH, srcW;
-  int dstC, dstCoff, dstUp, dstPy, dstPx, resC, attwStride, ldw;
+  int dstC, dstCoff, dstUp, dstPy, dstPx, resC, attwStride, ldw, filmStride;
   float eps;
 };
 
@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(2 * BN) conv_f32_kernel(const ConvP p) {
     for (int j = 0; j < 8; ++j) {
       fg[j] = 0.f; fb[j] = 0.f;
       if (p.film_b && nb + j < p.Cout) {
-        fb[j] = __ldg(p.film_b + (size_t)b * p.Cout + nb + j);
-        if (p.film_g) fg[j] = __ldg(p.film_g + (size_t)b * p.Cout + nb + j);
+        fb[j] = __ldg(p.film_b + (size_t)b * p.filmStride + nb + j);
+        if (p.film_g) fg[j] = __ldg(p.film_g + (size_t)b * p.filmStride + nb + j);
       }
     }
 #pragma unroll
@@ -240,6 +240,7 @@ int launch_conv_f32(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   p.dstC = op.i[UCDIR_CONV_I_DST_C]; p.dstCoff = op.i[UCDIR_CONV_I_DST_COFF]; p.dstUp = op.i[UCDIR_CONV_I_DST_UP];
   p.dstPy = op.i[UCDIR_CONV_I_DST_PY]; p.dstPx = op.i[UCDIR_CONV_I_DST_PX]; p.resC = op.i[UCDIR_CONV_I_RES_C];
   p.attwStride = op.i[UCDIR_CONV_I_ATTW_STRIDE];
+  p.filmStride = op.i[UCDIR_CONV_I_FILM_STRIDE] ? op.i[UCDIR_CONV_I_FILM_STRIDE] : op.i[UCDIR_CONV_I_COUT];
   p.eps = op.f[UCDIR_CONV_F_EPS];
   if (!p.src0 || !p.w || !p.dst) { set_error("conv_f32: null src0/w/dst"); return -1; }
   if (p.B <= 0 || p.H <= 0 || p.W <= 0 || p.Cout <= 0 || p.C0 <= 0) { set_error("conv_f32: bad dims"); return -1; }

@@ -228,11 +228,12 @@ __global__ void __launch_bounds__(256) scatter_kernel(const float* __restrict__ 
                                                       const float* __restrict__ noise, float* __restrict__ out, int BI,
                                                       int IH, int IW, int NTY, int NTX, int TH, int TW, int PD, int CE, int C,
                                                       int mode, int clip, float ca, float cb, float c1, float c2, float sigma,
-                                                      const float* __restrict__ params) {
-  if (params) {   // per-step scalars resident on the device (CUDA-graph replay): {A, B, C1, C2, SIGMA, clip, use_noise}
+                                                      float c3, const float* __restrict__ params) {
+  if (params) {   // per-step scalars resident on the device (CUDA-graph replay): {A, B, C1, C2, SIGMA, clip, use_noise, C3}
     ca = params[0]; cb = params[1]; c1 = params[2]; c2 = params[3]; sigma = params[4];
     clip = params[5] != 0.f;
     if (params[6] == 0.f) noise = nullptr;
+    c3 = params[7];
   }
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t plane = (size_t)IH * IW;
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const float* __restrict__ 
       float x0 = __fsub_rn(__fmul_rn(ca, xv), __fmul_rn(cb, e[c]));
       if (clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
       float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv));
+      if (c3 != 0.f) mean = __fadd_rn(mean, __fmul_rn(c3, e[c]));      // DDIM: + c * pred_noise (diffusion.py:287)
       float z = noise ? noise[o + c * plane] : 0.f;
       r = __fadd_rn(mean, __fmul_rn(z, sigma));
     }
@@ -279,7 +281,7 @@ int launch_scatter(const ucdir_op_t& op, cudaStream_t st, bool dry) {
       (float*)op.p[UCDIR_SCATTER_P_OUT], BI, IH, IW, op.i[UCDIR_SCATTER_I_NTY], op.i[UCDIR_SCATTER_I_NTX],
       op.i[UCDIR_SCATTER_I_TH], op.i[UCDIR_SCATTER_I_TW], op.i[UCDIR_SCATTER_I_PD], CE, C, mode, op.i[UCDIR_SCATTER_I_CLIP],
       op.f[UCDIR_SCATTER_F_A], op.f[UCDIR_SCATTER_F_B], op.f[UCDIR_SCATTER_F_C1], op.f[UCDIR_SCATTER_F_C2], op.f[UCDIR_SCATTER_F_SIGMA],
-      (const float*)op.p[UCDIR_SCATTER_P_PARAMS]);
+      op.f[UCDIR_SCATTER_F_C3], (const float*)op.p[UCDIR_SCATTER_P_PARAMS]);
   ++g_launches;
   return 0;
 }
@@ -308,6 +310,101 @@ int launch_crop_tiles(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   size_t total = (size_t)BT * IH * IW;
   crop_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float4*)op.p[UCDIR_CROP_P_SRC], (float4*)op.p[UCDIR_CROP_P_DST],
                                                                    BT, TH, TW, IH, IW, OY, OX);
+  ++g_launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm with G > 1 groups (the SR3-style FiLM ResnetBlock, model/ucdir.py:75-100; the DY3h path uses G = 1 and
+// folds its statistics into the convolution kernels instead).  fp32 NHWC.
+//   gn_stats_f32:  STATS[b][g] = {sum, sum of squares} over H*W x C/G elements, one CTA per (sample, group)
+//   gn_apply_f32:  DST = [Swish](GroupNorm(G, C)(SRC)),  eps as torch.nn.GroupNorm
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_stats_f32_kernel(const float* __restrict__ src, double* __restrict__ stats, int HW, int C, int G) {
+  __shared__ double red[2][8];
+  const int b = blockIdx.y, g = blockIdx.x, cpg = C / G;
+  const float* base = src + (size_t)b * HW * C + g * cpg;
+  double s1 = 0, s2 = 0;
+  for (int i = threadIdx.x; i < HW * cpg; i += 256) {
+    const int pix = i / cpg, c = i - pix * cpg;
+    const double v = base[(size_t)pix * C + c];
+    s1 += v; s2 += v * v;
+  }
+  s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0, t2 = 0;
+    for (int w = 0; w < 8; ++w) { t1 += red[0][w]; t2 += red[1][w]; }
+    stats[((size_t)b * G + g) * 2] = t1; stats[((size_t)b * G + g) * 2 + 1] = t2;
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_apply_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, const double* __restrict__ stats, int HW, int C, int G,
+                                                           float eps, int swish) {
+  __shared__ float smean[64], srstd[64];
+  const int b = blockIdx.y, cpg = C / G;
+  if (threadIdx.x < G) {
+    const double cnt = (double)HW * cpg;
+    const double mean = stats[((size_t)b * G + threadIdx.x) * 2] / cnt;
+    double var = stats[((size_t)b * G + threadIdx.x) * 2 + 1] / cnt - mean * mean;
+    if (var < 0) var = 0;
+    smean[threadIdx.x] = (float)mean; srstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const size_t per = (size_t)HW * C;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < per; i += (size_t)gridDim.x * 256) {
+    const int c = (int)(i % C), g = c / cpg;
+    float v = (src[(size_t)b * per + i] - smean[g]) * srstd[g] * gamma[c] + beta[c];
+    if (swish) v = swish_f(v);
+    dst[(size_t)b * per + i] = v;
+  }
+}
+
+int launch_gn_stats_f32(const ucdir_op_t& op, cudaStream_t st, bool dry) {
+  const int B = op.i[UCDIR_GNS_I_B], HW = op.i[UCDIR_GNS_I_HW], C = op.i[UCDIR_GNS_I_C], G = op.i[UCDIR_GNS_I_G];
+  if (!op.p[UCDIR_GNS_P_SRC] || !op.p[UCDIR_GNS_P_STATS]) { set_error("gn_stats: null pointer"); return -1; }
+  if (B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G || B > 65535) { set_error("gn_stats: bad dims"); return -1; }
+  if (dry) return 0;
+  gn_stats_f32_kernel<<<dim3(G, B), 256, 0, st>>>((const float*)op.p[UCDIR_GNS_P_SRC], (double*)op.p[UCDIR_GNS_P_STATS], HW, C, G);
+  ++g_launches;
+  return 0;
+}
+
+int launch_gn_apply_f32(const ucdir_op_t& op, cudaStream_t st, bool dry) {
+  const int B = op.i[UCDIR_GNS_I_B], HW = op.i[UCDIR_GNS_I_HW], C = op.i[UCDIR_GNS_I_C], G = op.i[UCDIR_GNS_I_G];
+  for (int k = 0; k <= UCDIR_GNF_P_STATS; ++k) if (!op.p[k]) { set_error("gn_apply_f32: null pointer %d", k); return -1; }
+  if (B <= 0 || HW <= 0 || C <= 0 || G <= 0 || G > 64 || C % G || B > 65535) { set_error("gn_apply_f32: bad dims (G <= 64)"); return -1; }
+  if (dry) return 0;
+  const size_t per = (size_t)HW * C;
+  unsigned gx = (unsigned)((per + 255) / 256); if (gx > 1184) gx = 1184;
+  gn_apply_f32_kernel<<<dim3(gx, B), 256, 0, st>>>((const float*)op.p[UCDIR_GNF_P_SRC], (float*)op.p[UCDIR_GNF_P_DST], (const float*)op.p[UCDIR_GNF_P_GAMMA],
+      (const float*)op.p[UCDIR_GNF_P_BETA], (const double*)op.p[UCDIR_GNF_P_STATS], HW, C, G, op.f[0], op.i[UCDIR_GNS_I_SWISH]);
+  ++g_launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout change at a module boundary: fp32 NCHW <-> NHWC (DIR 0: NCHW -> NHWC, 1: NHWC -> NCHW).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layout_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int HW, int dir) {
+  const size_t total = (size_t)B * C * HW;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    // i indexes the NHWC tensor
+    const int c = (int)(i % C); const size_t t = i / C; const int pix = (int)(t % HW); const int b = (int)(t / HW);
+    const size_t j = ((size_t)b * C + c) * HW + pix;      // NCHW index
+    if (dir == 0) dst[i] = src[j]; else dst[j] = src[i];
+  }
+}
+
+int launch_layout(const ucdir_op_t& op, cudaStream_t st, bool dry) {
+  const int B = op.i[0], C = op.i[1], HW = op.i[2], dir = op.i[3];
+  if (!op.p[0] || !op.p[1] || B <= 0 || C <= 0 || HW <= 0) { set_error("layout: bad args"); return -1; }
+  if (dry) return 0;
+  const size_t total = (size_t)B * C * HW;
+  unsigned g = (unsigned)((total + 255) / 256); if (g > 4736) g = 4736;
+  layout_kernel<<<g, 256, 0, st>>>((const float*)op.p[0], (float*)op.p[1], B, C, HW, dir);
   ++g_launches;
   return 0;
 }

@@ -1143,7 +1143,7 @@ class Session:
         _run_ops(self.tail_ops.array(), 1, self.stream())
 
     # ---- resident stepping: state, noise and per-step scalars live on the device; one graph launch per step ------
-    PARAM_FLOATS = 8          # {level, A, B, C1, C2, SIGMA, clip, use_noise}
+    PARAM_FLOATS = 9          # {level, A, B, C1, C2, SIGMA, clip, use_noise, C3}
 
     def ensure_resident(self):
         if getattr(self, "_resident", False):
@@ -1370,3 +1370,74 @@ class PredictorEngine:
         ol._arr = None
         _run_ops(ol.array(), len(ol), _stream(x.device))
         return out
+
+
+# ======================================================================================
+# FiLM ResnetBlock (model/ucdir.py:86-100) as a module-level op on the fp32 kernels
+# ======================================================================================
+def run_film_block(mod, x: torch.Tensor, time_emb: torch.Tensor) -> torch.Tensor:
+    """h = conv(Swish(GN_g(x))); h = FiLM(h, Linear(t)); h = conv(Swish(GN_g(h))); return h + res_conv(x).
+    x: [B, C, H, W] fp32 NCHW, time_emb: [B, nl_emb_dim].  Channel counts must be multiples of 8."""
+    dev = x.device
+    _require_cuda(dev)
+    B, C, H, W = x.shape
+    Co, G = mod.dim_out, mod.norm_groups
+    if C != mod.dim or C % 8 or Co % 8 or time_emb.shape[-1] % 8:
+        raise ValueError("FiLM block: channel counts must match the module and be multiples of 8")
+    f32 = lambda t: t.detach().to(device=dev, dtype=F32).contiguous()
+    keep = []                                             # keep every buffer alive until the ops have been issued
+
+    def buf(*shape, dtype=F32):
+        t = torch.empty(shape, dtype=dtype, device=dev); keep.append(t); return t
+
+    xs = f32(x); te = f32(time_emb.reshape(B, -1)); keep += [xs, te]
+    E = te.shape[1]
+    aff = mod.noise_func.use_affine_level
+    lin = mod.noise_func.noise_func[0]
+    w_lin = pack_conv_f32(lin.weight.view(lin.out_features, E, 1, 1)).to(dev); b_lin = f32(lin.bias)
+    c1, c2 = mod.block1.block[3], mod.block2.block[3]
+    w1, w2 = pack_conv_f32(c1.weight).to(dev), pack_conv_f32(c2.weight).to(dev)
+    b1, b2 = f32(c1.bias), f32(c2.bias)
+    g1, be1 = f32(mod.block1.block[0].weight), f32(mod.block1.block[0].bias)
+    g2, be2 = f32(mod.block2.block[0].weight), f32(mod.block2.block[0].bias)
+    keep += [w_lin, b_lin, w1, w2, b1, b2, g1, be1, g2, be2]
+    x_nhwc, a1, h1, a2, h2 = buf(B, H, W, C), buf(B, H, W, C), buf(B, H, W, Co), buf(B, H, W, Co), buf(B, H, W, Co)
+    film = buf(B, 1, 1, lin.out_features)
+    st1, st2 = buf(B, G, 2, dtype=torch.float64), buf(B, G, 2, dtype=torch.float64)
+    out = torch.empty((B, Co, H, W), dtype=F32, device=dev)
+    ol = OpList()
+    A = lambda t, c, h=H, w=W: Act(t, c, h, w, 0, True)
+    ol.add("UCDIR_OP_LAYOUT", {0: xs.data_ptr(), 1: x_nhwc.data_ptr()}, {0: B, 1: C, 2: H * W, 3: 0})
+
+    def gn(src, dst, gamma, beta, stats, ch):
+        ol.add("UCDIR_OP_GN_STATS_F32", {"UCDIR_GNS_P_SRC": src.data_ptr(), "UCDIR_GNS_P_STATS": stats.data_ptr()},
+               {"UCDIR_GNS_I_B": B, "UCDIR_GNS_I_HW": H * W, "UCDIR_GNS_I_C": ch, "UCDIR_GNS_I_G": G})
+        ol.add("UCDIR_OP_GN_APPLY_F32",
+               {"UCDIR_GNF_P_SRC": src.data_ptr(), "UCDIR_GNF_P_DST": dst.data_ptr(), "UCDIR_GNF_P_GAMMA": gamma.data_ptr(),
+                "UCDIR_GNF_P_BETA": beta.data_ptr(), "UCDIR_GNF_P_STATS": stats.data_ptr()},
+               {"UCDIR_GNS_I_B": B, "UCDIR_GNS_I_HW": H * W, "UCDIR_GNS_I_C": ch, "UCDIR_GNS_I_G": G, "UCDIR_GNS_I_SWISH": 1}, {0: 1e-5})
+
+    gn(x_nhwc, a1, g1, be1, st1, C)
+    _conv_op(ol, src0=A(te, E, 1, 1), w=w_lin.data_ptr(), bias=b_lin.data_ptr(), ks=1, dst=A(film, lin.out_features, 1, 1),
+             cout=lin.out_features, B=B)                                     # FeatureWiseAffine's Linear as a 1x1 GEMM
+    _conv_op(ol, src0=A(a1, C), w=w1.data_ptr(), bias=b1.data_ptr(), dst=A(h1, Co), cout=Co, B=B)
+    o = ol.ops[-1]
+    if aff:
+        o.p[K_["UCDIR_CONV_P_FILM_G"]] = film.data_ptr()
+        o.p[K_["UCDIR_CONV_P_FILM_B"]] = film.data_ptr() + Co * 4
+    else:
+        o.p[K_["UCDIR_CONV_P_FILM_B"]] = film.data_ptr()
+    o.i[K_["UCDIR_CONV_I_FILM_STRIDE"]] = lin.out_features
+    gn(h1, a2, g2, be2, st2, Co)
+    if isinstance(mod.res_conv, torch.nn.Conv2d):
+        wr, br = pack_conv_f32(mod.res_conv.weight).to(dev), f32(mod.res_conv.bias); keep += [wr, br]
+        res = buf(B, H, W, Co)
+        _conv_op(ol, src0=A(x_nhwc, C), w=wr.data_ptr(), bias=br.data_ptr(), ks=1, dst=A(res, Co), cout=Co, B=B)
+    else:
+        res = x_nhwc
+    _conv_op(ol, src0=A(a2, Co), w=w2.data_ptr(), bias=b2.data_ptr(), res=A(res, Co), dst=A(h2, Co), cout=Co, B=B)
+    ol.add("UCDIR_OP_LAYOUT", {0: h2.data_ptr(), 1: out.data_ptr()}, {0: B, 1: Co, 2: H * W, 3: 1})
+    _run_ops(ol.array(), len(ol), _stream(dev))
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()      # buffers in `keep` are released when this returns
+    return out

@@ -139,11 +139,11 @@ class GaussianDiffusion(nn.Module):
                 float(s["posterior_mean_coef1"][t]), float(s["posterior_mean_coef2"][t]), float(sigma))
 
     def _params_table(self, device, clip=True):
-        """Device table [T, 8] of the per-step kernel scalars {level, A, B, C1, C2, sigma, clip, use_noise}
+        """Device table [T, 9] of the per-step kernel scalars {level, A, B, C1, C2, sigma, clip, use_noise, C3}
         (model/diffusion.py:150-163,183), built once per schedule; a step D2D-copies its row (no per-step H2D)."""
         key = (str(device), self.num_timesteps, bool(clip), id(self._sched_host))
         if getattr(self, "_ptable_key", None) != key:
-            rows = [[self.noise_level(t), *self._step_scalars(t), 1.0 if clip else 0.0, 1.0 if t > 0 else 0.0]
+            rows = [[self.noise_level(t), *self._step_scalars(t), 1.0 if clip else 0.0, 1.0 if t > 0 else 0.0, 0.0]
                     for t in range(self.num_timesteps)]
             self._ptable = torch.tensor(rows, dtype=torch.float32, device=device)
             self._ptable_key = key
@@ -204,6 +204,43 @@ class GaussianDiffusion(nn.Module):
                 ret[row * b:(row + 1) * b] = sess.state()
                 row += 1
         return ret if continous else ret[-1]
+
+    @torch.no_grad()
+    def ddim_sample(self, x_in, continous=False, kwargs={}, sampling_timesteps=5, eta=1.0):
+        """model/diffusion.py:246-294: strided sampler over `sampling_timesteps` of the schedule's steps
+        (the reference hard-wires sampling_timesteps=5, eta=1, objective 'pred_noise', clip_x_start=True).
+        x0 = clamp(a_t x - b_t eps);  x <- sqrt(abar_next) x0 + c eps + sigma z, and x <- x0 on the last step.
+        Same kernels as p_sample: only the scalars of the fused posterior op differ."""
+        self.ddim_sampling_eta, self.sampling_timesteps, self.objective = eta, sampling_timesteps, "pred_noise"
+        x = x_in.contiguous().float()
+        device = x.device
+        T = self.num_timesteps
+        times = list(reversed(torch.linspace(-1, T - 1, steps=sampling_timesteps + 1).int().tolist()))
+        pairs = list(zip(times[:-1], times[1:]))
+        ac = self.alphas_cumprod.detach().float().cpu()                      # fp32, as the reference's buffer
+        a_tab, b_tab = self._sched_host["sqrt_recip_alphas_cumprod"], self._sched_host["sqrt_recipm1_alphas_cumprod"]
+        rows = []
+        for time, time_next in pairs:
+            if time_next < 0:
+                rows.append([self.noise_level(time), float(a_tab[time]), float(b_tab[time]), 1.0, 0.0, 0.0, 1.0, 0.0, 0.0])
+                continue
+            alpha, alpha_next = ac[time], ac[time_next]
+            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+            c = (1 - alpha_next - sigma ** 2).sqrt()
+            rows.append([self.noise_level(time), float(a_tab[time]), float(b_tab[time]), float(alpha_next.sqrt()), 0.0,
+                         float(sigma), 1.0, 1.0, float(c)])
+        table = torch.tensor(rows, dtype=torch.float32, device=device)
+        sess = self.denoise_fn.engine().session(x, kwargs["guide"])
+        self._sync_noise_stream(sess, device)
+        sess.load_state(self._randn(x.shape, device))
+        imgs = [sess.state().clone()] if continous else None
+        for k, (time, time_next) in enumerate(pairs):
+            if time_next >= 0:
+                self._fill_noise(sess.noise)
+            sess.step_resident(table[k])
+            if continous:
+                imgs.append(sess.state().clone())
+        return torch.stack(imgs, dim=1) if continous else sess.state().clone()
 
     @torch.no_grad()
     def sample(self, batch_size=1, continous=False):

@@ -35,6 +35,44 @@ class PositionalEncoding(nn.Module):
         self.dim = dim
 
 
+class FeatureWiseAffine(nn.Module):
+    """Parameter container for ucdir.py:32-45 (FiLM: h + Linear(t) or (1 + gamma) * h + beta)."""
+
+    def __init__(self, in_channels, out_channels, use_affine_level=False):
+        super().__init__()
+        self.use_affine_level = use_affine_level
+        self.noise_func = nn.Sequential(nn.Linear(in_channels, out_channels * (1 + self.use_affine_level)))
+
+
+class Block(nn.Module):
+    """Parameter container for ucdir.py:75-83 (GroupNorm(groups) -> Swish -> [Dropout] -> conv3x3)."""
+
+    def __init__(self, dim, dim_out, groups=32, dropout=0):
+        super().__init__()
+        self.block = nn.Sequential(nn.GroupNorm(groups, dim), Swish(),
+                                   nn.Dropout(dropout) if dropout != 0 else nn.Identity(),
+                                   nn.Conv2d(dim, dim_out, 3, padding=1))
+
+
+class ResnetBlock(nn.Module):
+    """SR3-style FiLM residual block, ucdir.py:86-100, as a standalone module-level op (it is not
+    reachable through DY3h, whose forward always passes `guide`).  Same constructor, state_dict keys and
+    forward(x, time_emb) signature; runs on the fp32 CUDA kernels."""
+
+    def __init__(self, dim, dim_out, nl_emb_dim=None, dropout=0, use_affine_level=False, norm_groups=32):
+        super().__init__()
+        self.noise_func = FeatureWiseAffine(nl_emb_dim, dim_out, use_affine_level)
+        self.block1 = Block(dim, dim_out, groups=norm_groups)
+        self.block2 = Block(dim_out, dim_out, groups=norm_groups, dropout=dropout)
+        self.res_conv = nn.Conv2d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
+        self.dim, self.dim_out, self.norm_groups = dim, dim_out, norm_groups
+
+    @torch.no_grad()
+    def forward(self, x, time_emb):
+        from ..engine import run_film_block
+        return run_film_block(self, x, time_emb)
+
+
 class ResnetBlockDY3h(nn.Module):
     """Parameter container for ucdir.py:103-120 (ResBlock + spatially-adaptive integration)."""
 
