@@ -328,6 +328,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     int img = 0, y = 0, x = 0, cls = 0;
     float rstd = 1.f, mr = 0.f;
     size_t pix_in = 0, pix_out = 0;
+    const __nv_bfloat16* res_row = nullptr;          // residual row of this thread's pixel
+    uint8_t* dst_row = nullptr;                      // output row of this thread's pixel (bf16 or fp32 elements)
     float aw[8];
     float s1 = 0.f, s2 = 0.f;                        // GroupNorm statistics of what this thread stored, current image
     int stat_img = -1;
@@ -358,6 +360,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         }
         pix_in = ((size_t)img * p.H + y) * p.W + x;
         pix_out = p.dstUp ? ((size_t)img * 2 * p.H + 2 * y + p.dstPy) * (2 * p.W) + 2 * x + p.dstPx : pix_in;
+        res_row = p.res ? p.res + pix_in * p.resC : nullptr;
+        dst_row = reinterpret_cast<uint8_t*>(p.dst) + (pix_out * p.dstC + p.dstCoff) * (EPI == EPI_F32 ? 4 : 2);
         if (EPI == EPI_MIX) {
           const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.att + pix_in * 8));
           const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.att + pix_in * 8 + 4));
@@ -402,11 +406,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         uint4 res_pl[CH / 8];
         if (valid) {
           if (EPI == EPI_MIX) {
-            const __nv_bfloat16* rp = p.res + pix_in * p.resC + ((ncol0 + c0) >> 3);
+            const __nv_bfloat16* rp = res_row + ((ncol0 + c0) >> 3);
             if (NO == 4) res_mix = __ldg(reinterpret_cast<const uint2*>(rp));
             else res_mix.x = __ldg(reinterpret_cast<const uint32_t*>(rp));
           } else if (EPI != EPI_F32 && p.res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix_in * p.resC + ncol0 + c0);
+            const uint4* rp = reinterpret_cast<const uint4*>(res_row + ncol0 + c0);
 #pragma unroll
             for (int j = 0; j < CH / 8; ++j) res_pl[j] = __ldg(rp + j);
           }
@@ -443,7 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             const float tr = __bfloat162float(o[c]);
             t1s += tr; t2s += tr * tr;
           }
-          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix_out * p.dstC + p.dstCoff + cbase;
+          __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst_row) + cbase;
           if (NO == 4) *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(o);
           else *reinterpret_cast<uint32_t*>(d) = *reinterpret_cast<const uint32_t*>(o);
         } else {
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             }
           }
           if (EPI == EPI_F32) {
-            float* d = reinterpret_cast<float*>(p.dst) + pix_out * p.dstC + p.dstCoff + nb;
+            float* d = reinterpret_cast<float*>(dst_row) + nb;
 #pragma unroll
             for (int j = 0; j < CH; ++j)
               if (nb + j < p.ncol_valid) { d[j] = v[j]; t1s += v[j]; t2s += v[j] * v[j]; }
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < CH; ++j) d[(size_t)j * p.t_ld] = __float2bfloat16(v[j]);
           } else {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.dst) + pix_out * p.dstC + p.dstCoff + nb;
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst_row) + nb;
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
               __align__(16) __nv_bfloat162 o2[4];
@@ -497,7 +501,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       if (++slot == NSLOT) { slot = 0; sph ^= 1; }
       if (p.dst_stats) {
         if (p.bn == 1) { s1 += t1s; s2 += t2s; }      // flushed when the image changes / at the end
-        else if (valid) { atomicAdd(p.dst_stats + 2 * img, (double)t1s); atomicAdd(p.dst_stats + 2 * img + 1, (double)t2s); }
+        else if ((box & 31) == 0) {                   // several images per tile, but one image per warp: reduce in the warp
+          const double d1 = warp_sum_d((double)t1s), d2 = warp_sum_d((double)t2s);
+          const int wimg = __shfl_sync(0xffffffffu, img, 0);
+          const bool wvalid = __shfl_sync(0xffffffffu, (int)valid, 0) != 0;
+          if (lane == 0 && wvalid) { atomicAdd(p.dst_stats + 2 * wimg, d1); atomicAdd(p.dst_stats + 2 * wimg + 1, d2); }
+        } else if (valid) { atomicAdd(p.dst_stats + 2 * img, (double)t1s); atomicAdd(p.dst_stats + 2 * img + 1, (double)t2s); }
       }
       new_m = cur.next(n_sub, p.tiles_x, p.tiles_y);
     }
