@@ -129,7 +129,7 @@ struct TcParams {
   void* dst; double* dst_stats;
   int B, H, W, srcH, srcW;
   int Ntot, ncol_valid;
-  int bw, bh, bn, tiles_x, tiles_y, m_tiles;
+  int bw, bh, bn, tiles_x, tiles_y, tiles_n, m_tiles, bres_bytes;
   int nty, ntx, oy0, ox0, stride;
   int nchunk, c0_chunks, groups, Ng, Cg, cg_eff;
   int gn, ncls, act, mode, dst_f32;
@@ -147,17 +147,18 @@ constexpr int TC_THREADS = 32 * (TC_FIRST_EPI_WARP + TC_EPI_WARPS);   // warpgro
 // KA: channels per A slab row (64/32/16 -> 128/64/32-byte swizzled rows); KB: K elements per B slab row;
 // NT: output columns per work item; NSPLIT: independent column groups of an item that read different K slices of
 // the same A slab (grouped convolution with small groups: 4 groups of 64 columns share one 32-channel A slab).
-template <int KA, int KB, int NT, int NSPLIT>
+template <int KA, int KB, int NT, int NSPLIT, int BSTAT = 0>
 struct TcCfg {
   static constexpr int A_BYTES = 128 * KA * 2;
   static constexpr int B_BYTES = NT * KB * 2;
   static constexpr int B_PAD = (B_BYTES + 1023) & ~1023;
-  static constexpr int STAGE = A_BYTES + B_PAD;
+  static constexpr int STAGE = A_BYTES + (BSTAT ? 0 : B_PAD);   // weight-stationary: the ring holds activation slabs only
   static constexpr int STAGES_RAW = 196608 / STAGE;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 4 ? 4 : STAGES_RAW);   // <= 8: the rest of the 228 KB stays L1 for the epilogue's loads
   static constexpr int SLOTW = NT < 32 ? 32 : NT;          // TMEM columns per accumulator slot
   static constexpr int NSLOT = 512 / SLOTW;                // accumulator ring: MMA of item i+1.. overlaps epilogue of item i
-  static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + (2 * STAGES + 2 * NSLOT) * 8 + 64;
+  static constexpr int BARS = (2 * STAGES + 2 * NSLOT + 2) * 8 + 64;
+  static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + BARS;      // + the resident weight block when BSTAT
 };
 
 // bf16 path: the result is rounded to 8 mantissa bits, so MUFU.EX2 / MUFU.RCP accuracy is ample (5 instructions
@@ -184,18 +185,27 @@ __device__ __forceinline__ uint32_t elect_one() {
 // increments and compares only (the producer issues one TMA pair per ~60 instructions, so divisions matter).
 struct ItemCursor {
   int ns, tx_i, ty_i, tn_i;
-  __device__ __forceinline__ void init(long long it, int n_sub, int tiles_x, int tiles_y) {
-    const long long m = it / n_sub;
-    ns = (int)(it - m * n_sub);
+  // MFAST = 0: item = m * n_sub + ns (N fastest: consecutive items share the activation tile).
+  // MFAST = 1: item = ns * m_tiles + m (M fastest: consecutive items share the weight block -> weight-stationary).
+  template <int MFAST>
+  __device__ __forceinline__ void init(long long it, int n_sub, int m_tiles, int tiles_x, int tiles_y) {
+    long long m;
+    if (MFAST) { ns = (int)(it / m_tiles); m = it - (long long)ns * m_tiles; }
+    else { m = it / n_sub; ns = (int)(it - m * n_sub); }
     tx_i = (int)(m % tiles_x);
     const long long t = m / tiles_x;
     ty_i = (int)(t % tiles_y);
     tn_i = (int)(t / tiles_y);
   }
-  __device__ __forceinline__ bool next(int n_sub, int tiles_x, int tiles_y) {   // returns true when the M tile changed
-    if (++ns < n_sub) return false;
-    ns = 0;
+  // returns true when the M tile changed
+  template <int MFAST>
+  __device__ __forceinline__ bool next(int n_sub, int tiles_x, int tiles_y, int tiles_n) {
+    if (!MFAST) {
+      if (++ns < n_sub) return false;
+      ns = 0;
+    }
     if (++tx_i == tiles_x) { tx_i = 0; if (++ty_i == tiles_y) { ty_i = 0; ++tn_i; } }
+    if (MFAST && tn_i == tiles_n) { tn_i = 0; ++ns; }
     return true;
   }
 };
@@ -206,19 +216,23 @@ struct ItemCursor {
 // EPI selects the epilogue at compile time (the chunk loop is the hot code of the small-K layers):
 enum { EPI_PLAIN = 0, EPI_MIX = 1, EPI_F32 = 2, EPI_PLAIN_T = 3 };
 
-template <int KA, int KB, int NT, int NSPLIT, int EPI>
+template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                 const __grid_constant__ CUtensorMap mapA1,
                                                                 const __grid_constant__ CUtensorMap mapB, const TcParams p) {
-  using S = TcCfg<KA, KB, NT, NSPLIT>;
+  using S = TcCfg<KA, KB, NT, NSPLIT, BSTAT>;
   constexpr int STAGES = S::STAGES, NSLOT = S::NSLOT;
+  constexpr int BSLAB = NT * KB * 2;                  // one weight slab (all NT rows of one K slice)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE);
+  uint8_t* bres = smem + STAGES * S::STAGE;           // BSTAT: resident weight block of the current N sub-tile
+  uint64_t* full = reinterpret_cast<uint64_t*>(bres + (BSTAT ? p.bres_bytes : 0));
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint64_t* tmem_empty = tmem_full + NSLOT;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + NSLOT);
+  uint64_t* bfull = tmem_empty + NSLOT;               // BSTAT: producer -> MMA, weight block landed
+  uint64_t* bfree = bfull + 1;                        // BSTAT: MMA -> producer, all MMAs that read the old block retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfree + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_sub = p.Ntot / NT;
@@ -231,6 +245,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     if (p.c0_chunks < p.nchunk && p.groups == 1) prefetch_tmap(&mapA1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int j = 0; j < NSLOT; ++j) { mbar_init(&tmem_full[j], 1); mbar_init(&tmem_empty[j], TC_EPI_WARPS); }
+    mbar_init(bfull, 1); mbar_init(bfree, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -247,13 +262,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
-    const uint32_t tx_bytes = (uint32_t)(p.bw * p.bh * p.bn * KA * 2 + NT * KB * 2);
-    ItemCursor cur; cur.init(it0, n_sub, p.tiles_x, p.tiles_y);
+    const uint32_t tx_bytes = (uint32_t)(p.bw * p.bh * p.bn * KA * 2 + (BSTAT ? 0 : NT * KB * 2));
+    const int nslab_p = p.nty * p.ntx * p.nchunk;
+    ItemCursor cur; cur.template init<BSTAT>(it0, n_sub, p.m_tiles, p.tiles_x, p.tiles_y);
     int stage = 0; uint32_t phase = 0;
+    int cur_ns = -1; uint32_t bfree_phase = 0;
     for (int li = 0; li < n_items; ++li) {
       const int x0 = cur.tx_i * p.bw * p.stride + p.ox0, y0 = cur.ty_i * p.bh * p.stride + p.oy0, n0 = cur.tn_i * p.bn;
       const int ncol0 = cur.ns * NT;
       const int cgrp0 = p.groups > 1 ? ((ncol0 / p.Ng) * p.Cg) / p.cg_eff * p.cg_eff : 0;
+      if (BSTAT && cur.ns != cur_ns) {
+        // new N sub-tile: (re)load its whole weight block once; every following item streams activations only
+        if (cur_ns >= 0) { mbar_wait(bfree, bfree_phase); bfree_phase ^= 1; }
+        if (elect_one()) {
+          mbar_expect_tx(bfull, (uint32_t)(nslab_p * BSLAB));
+          for (int i = 0; i < nslab_p; ++i) tma_load_2d(&mapB, bfull, bres + i * BSLAB, i * KB, ncol0);
+        }
+        __syncwarp();
+        cur_ns = cur.ns;
+      }
       int kb = 0;                                       // K coordinate of the B slab
       for (int ty = 0; ty < p.nty; ++ty) {
         for (int tx = 0; tx < p.ntx; ++tx) {
@@ -264,15 +291,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               mbar_expect_tx(&full[stage], tx_bytes);
               if (p.groups > 1 || j < p.c0_chunks) tma_load_4d(&mapA0, &full[stage], sa, cgrp0 + j * KA, x0 + tx, y0 + ty, n0);
               else tma_load_4d(&mapA1, &full[stage], sa, (j - p.c0_chunks) * KA, x0 + tx, y0 + ty, n0);
-              if (p.w_batched) tma_load_3d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0, n0);
-              else tma_load_2d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0);
+              if (!BSTAT) {
+                if (p.w_batched) tma_load_3d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0, n0);
+                else tma_load_2d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0);
+              }
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
-      cur.next(n_sub, p.tiles_x, p.tiles_y);
+      cur.template next<BSTAT>(n_sub, p.tiles_x, p.tiles_y, p.tiles_n);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====================
@@ -283,7 +312,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     const int nslab = p.nty * p.ntx * p.nchunk;
     int stage = 0; uint32_t phase = 0;
     int slot = 0; uint32_t sph = 0;
+    ItemCursor cur; cur.template init<BSTAT>(it0, n_sub, p.m_tiles, p.tiles_x, p.tiles_y);
+    int cur_ns = -1; uint32_t bfull_phase = 0;
     for (int li = 0; li < n_items; ++li) {
+      if (BSTAT && cur.ns != cur_ns) { mbar_wait(bfull, bfull_phase); bfull_phase ^= 1; cur_ns = cur.ns; }
+      const int ns_now = cur.ns;
+      cur.template next<BSTAT>(n_sub, p.tiles_x, p.tiles_y, p.tiles_n);
+      const bool last_of_block = BSTAT && (cur.ns != ns_now) && (li + 1 < n_items);
       mbar_wait(&tmem_empty[slot], sph ^ 1);            // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(slot * S::SLOTW);
@@ -291,7 +326,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE), sb = sa + S::A_BYTES;
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE);
+          const uint32_t sb = BSTAT ? smem_u32(bres + i * BSLAB) : sa + S::A_BYTES;
           const uint64_t ad = make_desc(sa, KA * 2), bd = make_desc(sb, KB * 2);
 #pragma unroll
           for (int sp = 0; sp < NSPLIT; ++sp) {
@@ -304,7 +340,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                         (i | k) != 0);
           }
           umma_commit(&empty[stage]);          // frees the smem slot once these MMAs have read it
-          if (i == nslab - 1) umma_commit(&tmem_full[slot]);   // accumulator of this item complete
+          if (i == nslab - 1) {
+            umma_commit(&tmem_full[slot]);     // accumulator of this item complete
+            if (last_of_block) umma_commit(bfree);   // ... and the weight block may be overwritten
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -322,7 +361,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     const int nn = r / box, rr = r - nn * box;
     const int yy = rr / p.bw, xx = rr - yy * p.bw;
     constexpr int CH = NT < 32 ? 16 : 32;
-    ItemCursor cur; cur.init(it0, n_sub, p.tiles_x, p.tiles_y);
+    ItemCursor cur; cur.template init<BSTAT>(it0, n_sub, p.m_tiles, p.tiles_x, p.tiles_y);
     bool new_m = true;
     bool valid = false;
     int img = 0, y = 0, x = 0, cls = 0;
@@ -395,7 +434,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           cadd[4 * j + 0] = lo.x; cadd[4 * j + 1] = lo.y; cadd[4 * j + 2] = hi.x; cadd[4 * j + 3] = hi.y;
         }
       };
-      if (valid && half * CH < NT) { issue_tables(half * CH); finish_tables(); }
+      uint2 res_next = make_uint2(0u, 0u);            // mix: residual of the next chunk, loaded one chunk ahead
+      auto issue_res = [&](int c0) {
+        constexpr int NO_ = CH / 8;
+        const __nv_bfloat16* rp = res_row + ((ncol0 + c0) >> 3);
+        if (NO_ == 4) res_next = __ldg(reinterpret_cast<const uint2*>(rp));
+        else res_next.x = __ldg(reinterpret_cast<const uint32_t*>(rp));
+      };
+      if (valid && half * CH < NT) { issue_tables(half * CH); if (EPI == EPI_MIX) issue_res(half * CH); finish_tables(); }
       mbar_wait(&tmem_full[slot], sph);
       tc_fence_after();
 #pragma unroll 1
@@ -406,9 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         uint4 res_pl[CH / 8];
         if (valid) {
           if (EPI == EPI_MIX) {
-            const __nv_bfloat16* rp = res_row + ((ncol0 + c0) >> 3);
-            if (NO == 4) res_mix = __ldg(reinterpret_cast<const uint2*>(rp));
-            else res_mix.x = __ldg(reinterpret_cast<const uint32_t*>(rp));
+            res_mix = res_next;
           } else if (EPI != EPI_F32 && p.res) {
             const uint4* rp = reinterpret_cast<const uint4*>(res_row + ncol0 + c0);
 #pragma unroll
@@ -430,7 +474,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           }
         }
         const bool more = c0 + CSTEP < NT;
-        if (more) issue_tables(c0 + CSTEP);            // in flight while this chunk's epilogue math runs
+        if (more) { issue_tables(c0 + CSTEP); if (EPI == EPI_MIX) issue_res(c0 + CSTEP); }   // in flight while this chunk's math runs
         if (EPI == EPI_MIX) {
           // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
           const int cbase = (ncol0 + c0) >> 3;
@@ -508,7 +552,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           if (lane == 0 && wvalid) { atomicAdd(p.dst_stats + 2 * wimg, d1); atomicAdd(p.dst_stats + 2 * wimg + 1, d2); }
         } else if (valid) { atomicAdd(p.dst_stats + 2 * img, (double)t1s); atomicAdd(p.dst_stats + 2 * img + 1, (double)t2s); }
       }
-      new_m = cur.next(n_sub, p.tiles_x, p.tiles_y);
+      new_m = cur.template next<BSTAT>(n_sub, p.tiles_x, p.tiles_y, p.tiles_n);
     }
     if (p.dst_stats && p.bn == 1 && stat_img >= 0) {
       const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
@@ -585,16 +629,17 @@ static void choose_tile(int W, int H, int B, int stride, int* bw, int* bh, int* 
   *bw = bbw; *bh = bbh; *bn = bbn;
 }
 
-template <int KA, int KB, int NT, int NSPLIT, int EPI>
+template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT>
 static int launch_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t st) {
-  using S = TcCfg<KA, KB, NT, NSPLIT>;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(tc_conv_kernel<KA, KB, NT, NSPLIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
-      set_error("tc_conv: cannot opt in to %d bytes of shared memory: %s", S::TOTAL, cudaGetErrorString(cudaGetLastError())); return -3; }
-    attr = true;
+  using S = TcCfg<KA, KB, NT, NSPLIT, BSTAT>;
+  const int smem_bytes = S::TOTAL + (BSTAT ? p.bres_bytes : 0);
+  static int attr = 0;
+  if (attr < smem_bytes) {
+    if (cudaFuncSetAttribute(tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+      set_error("tc_conv: cannot opt in to %d bytes of shared memory: %s", smem_bytes, cudaGetErrorString(cudaGetLastError())); return -3; }
+    attr = smem_bytes;
   }
-  tc_conv_kernel<KA, KB, NT, NSPLIT, EPI><<<grid, TC_THREADS, S::TOTAL, st>>>(a0, a1, b, p);
+  tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT><<<grid, TC_THREADS, smem_bytes, st>>>(a0, a1, b, p);
   return 0;
 }
 
@@ -667,7 +712,7 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   const int tiles_n = (p.B + p.bn - 1) / p.bn;
   const long mt = (long)p.tiles_x * p.tiles_y * tiles_n;
   if (mt > 0x7fffffffL) { set_error("tc_conv: too many M tiles"); return -2; }
-  p.m_tiles = (int)mt;
+  p.m_tiles = (int)mt; p.tiles_n = tiles_n;
   if (dry) return 0;
   CUtensorMap a0, a1, bm;
   int rc = make_act_map(&a0, src0, C0, p.srcW, p.srcH, p.B, KC, p.bw, p.bh, p.bn, p.stride, cstride0);
@@ -683,11 +728,20 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   const long long items = (long long)mt * (p.Ntot / NT);
   dim3 grid((unsigned)(items < n_sm ? items : n_sm), 1, 1);      // persistent: one CTA per SM
   const int epi = p.mode == 1 ? EPI_MIX : (p.dst_f32 ? EPI_F32 : (p.dst2 ? EPI_PLAIN_T : EPI_PLAIN));
-#define INST(ka, kb, nt, ns, ep) if (KC == ka && KB == kb && NT == nt && NSPLIT == ns && epi == ep) { rc = launch_inst<ka, kb, nt, ns, ep>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
-  INST(64, 64, 64, 1, EPI_PLAIN) INST(64, 64, 128, 1, EPI_PLAIN) INST(64, 64, 256, 1, EPI_PLAIN) INST(16, 16, 64, 1, EPI_PLAIN)
-  INST(64, 64, 256, 1, EPI_PLAIN_T) INST(64, 64, 128, 1, EPI_PLAIN_T)
-  INST(64, 64, 16, 1, EPI_F32) INST(64, 64, 64, 1, EPI_F32) INST(64, 64, 128, 1, EPI_F32) INST(64, 64, 256, 1, EPI_F32)
-  INST(32, 16, 256, 4, EPI_MIX) INST(32, 16, 256, 2, EPI_MIX) INST(32, 32, 256, 1, EPI_MIX) INST(64, 64, 256, 1, EPI_MIX)
+  // weight-stationary schedule: the whole weight block of one N sub-tile stays in shared memory while the CTA walks
+  // its M tiles (items ordered N-sub-tile major).  Used for the grouped integration-module convs whose weight slabs
+  // are small, many and 32/64-byte rowed (the streamed form re-fetched them for every pixel tile).
+  const int nslab = p.nty * p.ntx * p.nchunk;
+  p.bres_bytes = nslab * NT * KB * 2;
+  // (measured on B200, round 1: no gain over the streamed form -- the mix epilogue, not L2 traffic, bounds these ops --
+  //  so it is opt-in)
+  const int bstat = (epi == EPI_MIX && !p.w_batched && p.bres_bytes <= 150 * 1024 && op.i[UCDIR_TC_I_BSTAT] == 1) ? 1 : 0;
+#define INST(ka, kb, nt, ns, ep, bs) if (KC == ka && KB == kb && NT == nt && NSPLIT == ns && epi == ep && bstat == bs) { rc = launch_inst<ka, kb, nt, ns, ep, bs>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
+  INST(64, 64, 64, 1, EPI_PLAIN, 0) INST(64, 64, 128, 1, EPI_PLAIN, 0) INST(64, 64, 256, 1, EPI_PLAIN, 0) INST(16, 16, 64, 1, EPI_PLAIN, 0)
+  INST(64, 64, 256, 1, EPI_PLAIN_T, 0) INST(64, 64, 128, 1, EPI_PLAIN_T, 0)
+  INST(64, 64, 16, 1, EPI_F32, 0) INST(64, 64, 64, 1, EPI_F32, 0) INST(64, 64, 128, 1, EPI_F32, 0) INST(64, 64, 256, 1, EPI_F32, 0)
+  INST(32, 16, 256, 4, EPI_MIX, 1) INST(32, 16, 256, 2, EPI_MIX, 1) INST(32, 32, 256, 1, EPI_MIX, 1)
+  INST(32, 16, 256, 4, EPI_MIX, 0) INST(32, 16, 256, 2, EPI_MIX, 0) INST(32, 32, 256, 1, EPI_MIX, 0) INST(64, 64, 256, 1, EPI_MIX, 0)
 #undef INST
   set_error("tc_conv: no kernel instance for KC=%d KB=%d NT=%d NSPLIT=%d epilogue %d", KC, KB, NT, NSPLIT, epi);
   return -2;
