@@ -304,8 +304,15 @@ def run_ours(args):
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     names = {v: k for k, v in K.items() if k.startswith("UCDIR_OP_") and k not in ("UCDIR_OP_NPTR", "UCDIR_OP_NINT", "UCDIR_OP_NFLT")}
     share = {names.get(k, str(k)): round(v / args.steps, 4) for k, v in sorted(by_kind_ms.items(), key=lambda kv: -kv[1])}
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_top_kernel.json")
+    if args.precision == "bf16" and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = int(tj["dram_bytes_per_launch"])
+        traffic_note = "dram read+write of the most expensive launch (%s; %s), ncu --set full; algorithmic bytes of that launch %d" % (
+            tj["kernel"].split("(")[0], tj["what"].split(",")[0], tj["algorithmic_bytes"])
     roofline = {"bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": round(achieved / peaks["bf16_sustained"], 4), "traffic": None,
+                "frac": round(achieved / peaks["bf16_sustained"], 4), "traffic": traffic, "traffic_note": traffic_note,
                 "kernel": "conv implicit-GEMM family (%s), %d launches/step on this rank" % (
                     "fp32 SIMT conv_f32_kernel" if args.precision == "fp32" else "tcgen05 bf16", n_conv),
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
@@ -433,7 +440,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3_1024_tile128", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("UCDIR_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("UCDIR_PRECISION", "bf16"), choices=["fp32", "bf16"],
+                    help="bf16 = tcgen05 tensor-core path (default, stated tolerance); fp32 = SIMT parity path (rtol 1e-3 / atol 1e-4)")
     ap.add_argument("--cpu-tiles", type=int, default=4, help="tile forwards per CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--dump-ops", default="", help="write the per-op device-time profile of the timed steps to this JSON file")
