@@ -140,21 +140,24 @@ struct TcParams {
   __nv_bfloat16* dst2; int t_col0, t_ld;   // columns >= t_col0 are stored transposed: dst2[img][col - t_col0][pixel], row pitch t_ld
 };
 
-constexpr int TC_EPI_WARPS = 8;           // two per TMEM lane quadrant
-constexpr int TC_FIRST_EPI_WARP = 4;      // warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps}: shrinks to 88 registers
-constexpr int TC_THREADS = 32 * (TC_FIRST_EPI_WARP + TC_EPI_WARPS);   // warpgroups 1..2 = epilogue: grow to 208 registers
+constexpr int TC_EPI_WARPS = 12;          // three per TMEM lane quadrant: the epilogue is latency bound, more warps hide it
+constexpr int TC_FIRST_EPI_WARP = 4;      // warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps}: shrinks to 72 registers
+constexpr int TC_THREADS = 32 * (TC_FIRST_EPI_WARP + TC_EPI_WARPS);   // warpgroups 1..2 = epilogue: grow to 144 registers
 
 // KA: channels per A slab row (64/32/16 -> 128/64/32-byte swizzled rows); KB: K elements per B slab row;
 // NT: output columns per work item; NSPLIT: independent column groups of an item that read different K slices of
 // the same A slab (grouped convolution with small groups: 4 groups of 64 columns share one 32-channel A slab).
-template <int KA, int KB, int NT, int NSPLIT, int BSTAT = 0>
+// SPS: slabs (filter taps) per pipeline stage -- the small-N layers do ~130 cycles of MMA per slab but ~500 cycles of
+// barrier round trip per stage, so they move three taps per stage.
+template <int KA, int KB, int NT, int NSPLIT, int BSTAT = 0, int SPS = 1>
 struct TcCfg {
   static constexpr int A_BYTES = 128 * KA * 2;
   static constexpr int B_BYTES = NT * KB * 2;
   static constexpr int B_PAD = (B_BYTES + 1023) & ~1023;
-  static constexpr int STAGE = A_BYTES + (BSTAT ? 0 : B_PAD);   // weight-stationary: the ring holds activation slabs only
+  static constexpr int SLAB = A_BYTES + (BSTAT ? 0 : B_PAD);    // weight-stationary: the ring holds activation slabs only
+  static constexpr int STAGE = SPS * SLAB;
   static constexpr int STAGES_RAW = 196608 / STAGE;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 4 ? 4 : STAGES_RAW);   // <= 8: the rest of the 228 KB stays L1 for the epilogue's loads
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < (SPS > 1 ? 2 : 4) ? (SPS > 1 ? 2 : 4) : STAGES_RAW);   // <= 8: the rest of the 228 KB stays L1 for the epilogue's loads
   static constexpr int SLOTW = NT < 32 ? 32 : NT;          // TMEM columns per accumulator slot
   static constexpr int NSLOT = 512 / SLOTW;                // accumulator ring: MMA of item i+1.. overlaps epilogue of item i
   static constexpr int BARS = (2 * STAGES + 2 * NSLOT + 2) * 8 + 64;
@@ -216,11 +219,11 @@ struct ItemCursor {
 // EPI selects the epilogue at compile time (the chunk loop is the hot code of the small-K layers):
 enum { EPI_PLAIN = 0, EPI_MIX = 1, EPI_F32 = 2, EPI_PLAIN_T = 3 };
 
-template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT>
+template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT, int SPS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                 const __grid_constant__ CUtensorMap mapA1,
                                                                 const __grid_constant__ CUtensorMap mapB, const TcParams p) {
-  using S = TcCfg<KA, KB, NT, NSPLIT, BSTAT>;
+  using S = TcCfg<KA, KB, NT, NSPLIT, BSTAT, SPS>;
   constexpr int STAGES = S::STAGES, NSLOT = S::NSLOT;
   constexpr int BSLAB = NT * KB * 2;                  // one weight slab (all NT rows of one K slice)
   extern __shared__ uint8_t smem_raw[];
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   // Register reallocation between warpgroups (setmaxnreg is warpgroup-wide, first statement of each role branch):
   // the epilogue keeps a chunk of accumulators, its folded-GroupNorm terms and the next chunk's table values in flight.
   if (warp < TC_FIRST_EPI_WARP) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
     const uint32_t tx_bytes = (uint32_t)(p.bw * p.bh * p.bn * KA * 2 + (BSTAT ? 0 : NT * KB * 2));
@@ -281,25 +284,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         __syncwarp();
         cur_ns = cur.ns;
       }
-      int kb = 0;                                       // K coordinate of the B slab
-      for (int ty = 0; ty < p.nty; ++ty) {
-        for (int tx = 0; tx < p.ntx; ++tx) {
-          for (int j = 0; j < p.nchunk; ++j, kb += KB) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            if (elect_one()) {
-              uint8_t* sa = smem + stage * S::STAGE;
-              mbar_expect_tx(&full[stage], tx_bytes);
-              if (p.groups > 1 || j < p.c0_chunks) tma_load_4d(&mapA0, &full[stage], sa, cgrp0 + j * KA, x0 + tx, y0 + ty, n0);
-              else tma_load_4d(&mapA1, &full[stage], sa, (j - p.c0_chunks) * KA, x0 + tx, y0 + ty, n0);
-              if (!BSTAT) {
-                if (p.w_batched) tma_load_3d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0, n0);
-                else tma_load_2d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0);
-              }
-            }
-            __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      int kb = 0, ty = 0, tx = 0, j = 0;                // K coordinate of the B slab; tap and channel chunk of the slab
+      for (int sidx = 0; sidx < nslab_p; ++sidx) {
+        const int sub = sidx % SPS;
+        if (sub == 0) mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * S::STAGE + sub * S::SLAB;
+          if (sub == 0) mbar_expect_tx(&full[stage], tx_bytes * SPS);
+          if (p.groups > 1 || j < p.c0_chunks) tma_load_4d(&mapA0, &full[stage], sa, cgrp0 + j * KA, x0 + tx, y0 + ty, n0);
+          else tma_load_4d(&mapA1, &full[stage], sa, (j - p.c0_chunks) * KA, x0 + tx, y0 + ty, n0);
+          if (!BSTAT) {
+            if (p.w_batched) tma_load_3d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0, n0);
+            else tma_load_2d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0);
           }
         }
+        __syncwarp();
+        kb += KB;
+        if (++j == p.nchunk) { j = 0; if (++tx == p.ntx) { tx = 0; ++ty; } }
+        if (sub == SPS - 1) { if (++stage == STAGES) { stage = 0; phase ^= 1; } }
       }
       cur.template next<BSTAT>(n_sub, p.tiles_x, p.tiles_y, p.tiles_n);
     }
@@ -322,25 +324,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       mbar_wait(&tmem_empty[slot], sph ^ 1);            // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(slot * S::SLOTW);
-      for (int i = 0; i < nslab; ++i) {
+      const int nstage_item = nslab / SPS;
+      for (int g = 0; g < nstage_item; ++g) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE);
-          const uint32_t sb = BSTAT ? smem_u32(bres + i * BSLAB) : sa + S::A_BYTES;
-          const uint64_t ad = make_desc(sa, KA * 2), bd = make_desc(sb, KB * 2);
 #pragma unroll
-          for (int sp = 0; sp < NSPLIT; ++sp) {
-            // split sp reads the 16-element K slice that holds its CGS channels, and its own rows of the B slab
-            const uint32_t a_off = NSPLIT > 1 ? (uint32_t)((sp * CGS) / 16) * 32u : 0u;
-            const uint32_t b_off = (uint32_t)(sp * NSUB * KB * 2);
+          for (int sub = 0; sub < SPS; ++sub) {
+            const int i = g * SPS + sub;                 // slab index within the item
+            const uint32_t sa = smem_u32(smem + stage * S::STAGE + sub * S::SLAB);
+            const uint32_t sb = BSTAT ? smem_u32(bres + i * BSLAB) : sa + S::A_BYTES;
+            const uint64_t ad = make_desc(sa, KA * 2), bd = make_desc(sb, KB * 2);
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)
-              umma_bf16(tacc + (uint32_t)(sp * NSUB), ad + (uint64_t)((a_off + k * 32) >> 4), bd + (uint64_t)((b_off + k * 32) >> 4), idesc,
-                        (i | k) != 0);
+            for (int sp = 0; sp < NSPLIT; ++sp) {
+              // split sp reads the 16-element K slice that holds its CGS channels, and its own rows of the B slab
+              const uint32_t a_off = NSPLIT > 1 ? (uint32_t)((sp * CGS) / 16) * 32u : 0u;
+              const uint32_t b_off = (uint32_t)(sp * NSUB * KB * 2);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_bf16(tacc + (uint32_t)(sp * NSUB), ad + (uint64_t)((a_off + k * 32) >> 4), bd + (uint64_t)((b_off + k * 32) >> 4), idesc,
+                          (i | k) != 0);
+            }
           }
-          umma_commit(&empty[stage]);          // frees the smem slot once these MMAs have read it
-          if (i == nslab - 1) {
+          umma_commit(&empty[stage]);          // frees the smem stage once these MMAs have read it
+          if (g == nstage_item - 1) {
             umma_commit(&tmem_full[slot]);     // accumulator of this item complete
             if (last_of_block) umma_commit(bfree);   // ... and the weight block may be overwritten
           }
@@ -353,9 +360,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   }
   } else {
     // ===================== epilogue =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
     const int q = warp & 3;                          // TMEM lane quadrant this warp may read
-    const int half = (warp - TC_FIRST_EPI_WARP) >> 2;  // two warps per quadrant take alternate column chunks
+    const int half = (warp - TC_FIRST_EPI_WARP) >> 2;  // the warps of a quadrant take alternate column chunks
     const int r = q * 32 + lane;                     // accumulator row = pixel slot of the tile
     const int box = p.bw * p.bh;
     const int nn = r / box, rr = r - nn * box;
@@ -461,8 +468,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         }
         uint32_t rv[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * S::SLOTW + c0);
+#if defined(UCDIR_ABLATE) && UCDIR_ABLATE == 2      // ablation: no TMEM loads at all
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rv[j] = 0u;
+        (void)taddr;
+#else
         if (CH == 32) tmem_ld32(taddr, rv); else tmem_ld16(taddr, rv);
         tmem_ld_wait();
+#endif
+#if defined(UCDIR_ABLATE) && (UCDIR_ABLATE == 1 || UCDIR_ABLATE == 2)   // ablation: drain TMEM, skip all epilogue math / IO
+        if (EPI == EPI_MIX) { if (rv[0] == 0x7fc12345u) t1s += 1.f; continue; }
+#endif
         if (!valid) continue;
         float v[CH];
         {
@@ -474,7 +490,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           }
         }
         const bool more = c0 + CSTEP < NT;
-        if (more) { issue_tables(c0 + CSTEP); if (EPI == EPI_MIX) issue_res(c0 + CSTEP); }   // in flight while this chunk's math runs
+        if (more && EPI == EPI_MIX) issue_res(c0 + CSTEP);   // next chunk's residual in flight while this chunk's math runs
         if (EPI == EPI_MIX) {
           // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
           const int cbase = (ncol0 + c0) >> 3;
@@ -536,7 +552,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             }
           }
         }
-        if (more) finish_tables();
+        if (more) { issue_tables(c0 + CSTEP); finish_tables(); }   // next chunk's additive terms (L1/L2 hits, short-lived registers)
       }
       // this warp is done reading the accumulator slot: hand it back to the MMA issuer
       tc_fence_before();
@@ -629,17 +645,17 @@ static void choose_tile(int W, int H, int B, int stride, int* bw, int* bh, int* 
   *bw = bbw; *bh = bbh; *bn = bbn;
 }
 
-template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT>
+template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT, int SPS>
 static int launch_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t st) {
-  using S = TcCfg<KA, KB, NT, NSPLIT, BSTAT>;
+  using S = TcCfg<KA, KB, NT, NSPLIT, BSTAT, SPS>;
   const int smem_bytes = S::TOTAL + (BSTAT ? p.bres_bytes : 0);
   static int attr = 0;
   if (attr < smem_bytes) {
-    if (cudaFuncSetAttribute(tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT, SPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
       set_error("tc_conv: cannot opt in to %d bytes of shared memory: %s", smem_bytes, cudaGetErrorString(cudaGetLastError())); return -3; }
     attr = smem_bytes;
   }
-  tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT><<<grid, TC_THREADS, smem_bytes, st>>>(a0, a1, b, p);
+  tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT, SPS><<<grid, TC_THREADS, smem_bytes, st>>>(a0, a1, b, p);
   return 0;
 }
 
@@ -736,14 +752,21 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   // (measured on B200, round 1: no gain over the streamed form -- the mix epilogue, not L2 traffic, bounds these ops --
   //  so it is opt-in)
   const int bstat = (epi == EPI_MIX && !p.w_batched && p.bres_bytes <= 150 * 1024 && op.i[UCDIR_TC_I_BSTAT] == 1) ? 1 : 0;
-#define INST(ka, kb, nt, ns, ep, bs) if (KC == ka && KB == kb && NT == nt && NSPLIT == ns && epi == ep && bstat == bs) { rc = launch_inst<ka, kb, nt, ns, ep, bs>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
-  INST(64, 64, 64, 1, EPI_PLAIN, 0) INST(64, 64, 128, 1, EPI_PLAIN, 0) INST(64, 64, 256, 1, EPI_PLAIN, 0) INST(16, 16, 64, 1, EPI_PLAIN, 0)
-  INST(64, 64, 256, 1, EPI_PLAIN_T, 0) INST(64, 64, 128, 1, EPI_PLAIN_T, 0)
-  INST(64, 64, 16, 1, EPI_F32, 0) INST(64, 64, 64, 1, EPI_F32, 0) INST(64, 64, 128, 1, EPI_F32, 0) INST(64, 64, 256, 1, EPI_F32, 0)
-  INST(32, 16, 256, 4, EPI_MIX, 1) INST(32, 16, 256, 2, EPI_MIX, 1) INST(32, 32, 256, 1, EPI_MIX, 1)
-  INST(32, 16, 256, 4, EPI_MIX, 0) INST(32, 16, 256, 2, EPI_MIX, 0) INST(32, 32, 256, 1, EPI_MIX, 0) INST(64, 64, 256, 1, EPI_MIX, 0)
+  // three filter taps per pipeline stage for the layers whose per-slab MMA work is small (N <= 128 columns per MMA)
+  // (measured on B200, round 1: no gain -- those ops are bound by their epilogue, which already overlaps the main loop --
+  //  so it is opt-in)
+  const int sps = (nslab % 3 == 0 && op.i[UCDIR_TC_I_SPS3] == 1 && (NT / NSPLIT <= 128 || (epi == EPI_MIX && KB < 64))) ? 3 : 1;
+#define INST(ka, kb, nt, ns, ep, bs, sp) if (KC == ka && KB == kb && NT == nt && NSPLIT == ns && epi == ep && bstat == bs && sps == sp) { rc = launch_inst<ka, kb, nt, ns, ep, bs, sp>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
+  INST(64, 64, 64, 1, EPI_PLAIN, 0, 1) INST(64, 64, 128, 1, EPI_PLAIN, 0, 1) INST(64, 64, 256, 1, EPI_PLAIN, 0, 1) INST(16, 16, 64, 1, EPI_PLAIN, 0, 1)
+  INST(64, 64, 64, 1, EPI_PLAIN, 0, 3) INST(64, 64, 128, 1, EPI_PLAIN, 0, 3) INST(16, 16, 64, 1, EPI_PLAIN, 0, 3)
+  INST(64, 64, 256, 1, EPI_PLAIN_T, 0, 1) INST(64, 64, 128, 1, EPI_PLAIN_T, 0, 1) INST(64, 64, 128, 1, EPI_PLAIN_T, 0, 3)
+  INST(64, 64, 16, 1, EPI_F32, 0, 1) INST(64, 64, 64, 1, EPI_F32, 0, 1) INST(64, 64, 128, 1, EPI_F32, 0, 1) INST(64, 64, 256, 1, EPI_F32, 0, 1)
+  INST(64, 64, 16, 1, EPI_F32, 0, 3) INST(64, 64, 64, 1, EPI_F32, 0, 3) INST(64, 64, 128, 1, EPI_F32, 0, 3)
+  INST(32, 16, 256, 4, EPI_MIX, 1, 3) INST(32, 16, 256, 2, EPI_MIX, 1, 3) INST(32, 32, 256, 1, EPI_MIX, 1, 3)
+  INST(32, 16, 256, 4, EPI_MIX, 0, 3) INST(32, 16, 256, 2, EPI_MIX, 0, 3) INST(32, 32, 256, 1, EPI_MIX, 0, 3) INST(64, 64, 256, 1, EPI_MIX, 0, 1)
+  INST(32, 16, 256, 4, EPI_MIX, 0, 1) INST(32, 16, 256, 2, EPI_MIX, 0, 1) INST(32, 32, 256, 1, EPI_MIX, 0, 1)
 #undef INST
-  set_error("tc_conv: no kernel instance for KC=%d KB=%d NT=%d NSPLIT=%d epilogue %d", KC, KB, NT, NSPLIT, epi);
+  set_error("tc_conv: no kernel instance for KC=%d KB=%d NT=%d NSPLIT=%d epilogue %d bstat %d sps %d", KC, KB, NT, NSPLIT, epi, bstat, sps);
   return -2;
 }
 
