@@ -130,3 +130,19 @@ def test_full_size_tile_locality_vs_oracle(net, sid_weights, monkeypatch):
         with torch.no_grad():
             want = O.unet_naiveforward(sd, "denoise_fn.", lay, xp[..., y0:y0 + 128, x0:x0 + 128], lvl, gp[..., y0:y0 + 128, x0:x0 + 128])
         check(eps[..., y0:y0 + 96, x0:x0 + 96], want[..., 16:112, 16:112], "eps 1024 tile (%d,%d)" % (ty, tx), EPS_MAX, EPS_MEAN)
+
+
+@pytest.mark.parametrize("shape", [(2, 33, 47), (1, 48, 80), (2, 256, 256)])
+def test_ragged_and_batched_shapes_vs_oracle(net, sid_weights, shape):
+    """Non-aligned, non-square and batched inputs (incl. BASELINE config C2's 256x256 -> S = 288, whose levels are
+    288/144/72/36/18 pixels wide: tile rectangles that do not divide 128) on the tensor-core path."""
+    _, sd = sid_weights
+    lay = O.UNetLayout(**ucdir_b200.SID_MODEL_OPT["unet"])
+    b, h, w = shape
+    g = torch.Generator().manual_seed(h * 1000 + w)
+    x6 = torch.rand(b, 6, h, w, generator=g) * 2 - 1
+    guide = torch.rand(b, 3, h, w, generator=g) * 2 - 1
+    lvl = torch.rand(b, 1, generator=g)
+    with torch.no_grad():
+        want = O.unet_forward(sd, "denoise_fn.", lay, x6, lvl, guide)
+    check(net.denoise_fn(x6.cuda(), lvl.cuda(), guide.cuda()), want, "eps forward %s" % (shape,), EPS_MAX, EPS_MEAN)
