@@ -146,3 +146,29 @@ def test_ragged_and_batched_shapes_vs_oracle(net, sid_weights, shape):
     with torch.no_grad():
         want = O.unet_forward(sd, "denoise_fn.", lay, x6, lvl, guide)
     check(net.denoise_fn(x6.cuda(), lvl.cuda(), guide.cuda()), want, "eps forward %s" % (shape,), EPS_MAX, EPS_MEAN)
+
+
+def test_reference_default_tiling_1152_bf16_vs_fp32_path(net):
+    """What `sr.py -p val` produces for a 1024x1024 image: DDPM.test pads it to 1152x1152 (model/model.py:127-128), which
+    is above the 1 Mpx trigger, so DY3h.forward tiles it with the reference defaults (skip 1024, padding 64) into four
+    1024x1024 tiles, each with 16384-token attention.  The CPU oracle needs minutes per tile at this size, so the check
+    is between the two independent CUDA paths: the bf16 tensor-core path against the fp32 SIMT parity path."""
+    unet = net.denoise_fn
+    eng = unet.engine()
+    assert unet.tile_skip == 1024 and unet.tile_padding == 64
+    g = torch.Generator().manual_seed(8)
+    low = torch.nn.functional.interpolate(torch.rand(1, 6, 36, 36, generator=g), size=(1152, 1152), mode="bilinear")
+    x6 = (low * 2 - 1 + 0.1 * torch.randn(1, 6, 1152, 1152, generator=g)).clamp(-1, 1).cuda()
+    guide = (low[:, :3] * 2 - 1).contiguous().cuda()
+    lvl = torch.full((1, 1), 0.6).cuda()
+    geo = eng.default_geometry(1, 1152, 1152)
+    assert geo.kind == "tiled" and geo.n_tiles == 4 and geo.TH == 1024
+    a = unet(x6, lvl, guide)
+    b = unet(x6, lvl, guide)
+    check(a, b, "1152 default tiling: idempotence", 1e-3, 1e-4)
+    eng.set_precision("fp32")
+    try:
+        ref = unet(x6, lvl, guide)
+    finally:
+        eng.set_precision("bf16")
+    check(a, ref, "1152 default tiling: bf16 vs fp32 path", EPS_MAX, EPS_MEAN)
