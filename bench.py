@@ -32,6 +32,8 @@ WORKLOADS = {
     "c3_1024_tile128": (1, 1024, 128, 16, True),
     "c2_256_b8": (8, 256, 1024, 64, False),
     "c1_128": (1, 128, 1024, 64, False),
+    # what `sr.py -p val` runs for a 1024x1024 image: DDPM.test pads to 1152x1152 -> reference-default tiler (1024, 64)
+    "c3_1152_ref_tiling": (1, 1152, 1024, 64, False),
 }
 
 

@@ -256,3 +256,25 @@ def test_tc_attention_chain(B, H, W, C):
     v = dev["vt"].float()[..., :N].transpose(1, 2)
     want = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(C), dim=-1) @ v
     assert_close(dev["O"].reshape(B, N, C), want, "O vs torch attention", rtol=3e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("rows,cols,in_ld,bf16_out", [(37, 4096, 4096, True), (5, 16384, 16384, True), (9, 2500, 2560, True), (7, 3000, 3000, False)])
+def test_softmax_long_rows(rows, cols, in_ld, bf16_out):
+    """One-pass shared-memory softmax used for rows >= 2048 columns (attention over large tiles)."""
+    g = torch.Generator().manual_seed(rows + cols)
+    out_ld = (cols + 7) & ~7
+    c = Case().add("S", rnd(g, rows, in_ld, scale=3.0)).add("P", torch.zeros(rows, out_ld, dtype=BF))
+
+    def build(t):
+        ol = E.OpList()
+        p = {"UCDIR_SOFTMAX_P_X": t["S"].data_ptr()}
+        if bf16_out:
+            p["UCDIR_SOFTMAX_P_OUT_BF16"] = t["P"].data_ptr()
+        ol.add("UCDIR_OP_SOFTMAX_F32", p, {"UCDIR_SOFTMAX_I_ROWS": rows, "UCDIR_SOFTMAX_I_COLS": cols, "UCDIR_SOFTMAX_I_IN_LD": in_ld,
+                                          "UCDIR_SOFTMAX_I_OUT_LD": out_ld})
+        return ol
+    host, dev = run_both(c, build)
+    if bf16_out:
+        assert_close(dev["P"], host["P"], "softmax bf16 out", rtol=1e-2, atol=1e-3)
+    else:
+        assert_close(dev["S"][:, :cols], host["S"][:, :cols], "softmax in place", rtol=1e-4, atol=1e-6)

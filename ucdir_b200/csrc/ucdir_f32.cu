@@ -397,14 +397,70 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ X
   }
 }
 
+// One-pass variant for long rows (attention over 1024x1024 tiles: 16384 keys): the row is read from HBM once into
+// shared memory, reduced there, and written once (bf16 probabilities or fp32 in place) -- 1.5 instead of 5 passes.
+__global__ void __launch_bounds__(512) softmax_rows_smem_kernel(float* __restrict__ X, int cols, int in_ld, __nv_bfloat16* __restrict__ out, int out_ld) {
+  extern __shared__ float srow[];
+  __shared__ float red[16];
+  __shared__ float bc;
+  float* row = X + (size_t)blockIdx.x * in_ld;
+  const int tid = threadIdx.x;
+  float mx = -INFINITY;
+  for (int c = tid * 4; c < cols; c += 512 * 4) {
+    if (c + 3 < cols && (in_ld & 3) == 0) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c);
+      *reinterpret_cast<float4*>(srow + c) = v;
+      mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    } else {
+      for (int k = c; k < cols && k < c + 4; ++k) { const float v = row[k]; srow[k] = v; mx = fmaxf(mx, v); }
+    }
+  }
+  mx = warp_max_f(mx);
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  if (tid == 0) { float m = red[0]; for (int w = 1; w < 16; ++w) m = fmaxf(m, red[w]); bc = m; }
+  __syncthreads();
+  mx = bc;
+  float sum = 0.f;
+  for (int c = tid; c < cols; c += 512) { const float e = expf(srow[c] - mx); srow[c] = e; sum += e; }
+  sum = warp_sum_f(sum);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = sum;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int w = 0; w < 16; ++w) t += red[w]; bc = t; }
+  __syncthreads();
+  const float tot = bc;
+  if (out) {
+    __nv_bfloat16* o = out + (size_t)blockIdx.x * out_ld;
+    for (int c = tid * 2; c < out_ld; c += 512 * 2) {
+      const float a = c < cols ? srow[c] / tot : 0.f, b = c + 1 < cols ? srow[c + 1] / tot : 0.f;
+      if (c + 1 < out_ld && (out_ld & 1) == 0) *reinterpret_cast<__nv_bfloat162*>(o + c) = __floats2bfloat162_rn(a, b);
+      else { o[c] = __float2bfloat16(a); if (c + 1 < out_ld) o[c + 1] = __float2bfloat16(b); }
+    }
+  } else {
+    for (int c = tid; c < cols; c += 512) row[c] = srow[c] / tot;
+  }
+}
+
 int launch_softmax_f32(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   float* X = (float*)op.p[UCDIR_SOFTMAX_P_X];
   int rows = op.i[UCDIR_SOFTMAX_I_ROWS], cols = op.i[UCDIR_SOFTMAX_I_COLS];
   if (!X || rows <= 0 || cols <= 0) { set_error("softmax: bad args"); return -1; }
   if (op.p[UCDIR_SOFTMAX_P_OUT_BF16] && op.i[UCDIR_SOFTMAX_I_OUT_LD] < cols) { set_error("softmax: OUT_LD < COLS"); return -1; }
   if (dry) return 0;
-  softmax_rows_kernel<<<rows, 256, 0, st>>>(X, cols, op.i[UCDIR_SOFTMAX_I_IN_LD] ? op.i[UCDIR_SOFTMAX_I_IN_LD] : cols,
-                                            (__nv_bfloat16*)op.p[UCDIR_SOFTMAX_P_OUT_BF16], op.i[UCDIR_SOFTMAX_I_OUT_LD]);
+  const int in_ld = op.i[UCDIR_SOFTMAX_I_IN_LD] ? op.i[UCDIR_SOFTMAX_I_IN_LD] : cols;
+  if (cols >= 2048 && cols <= 49152) {
+    static int attr = 0;
+    const int bytes = cols * 4;
+    if (attr < bytes) {
+      if (cudaFuncSetAttribute(softmax_rows_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+        set_error("softmax: cannot opt in to %d bytes of shared memory", bytes); return -3; }
+      attr = bytes;
+    }
+    softmax_rows_smem_kernel<<<rows, 512, bytes, st>>>(X, cols, in_ld, (__nv_bfloat16*)op.p[UCDIR_SOFTMAX_P_OUT_BF16], op.i[UCDIR_SOFTMAX_I_OUT_LD]);
+  } else {
+    softmax_rows_kernel<<<rows, 256, 0, st>>>(X, cols, in_ld, (__nv_bfloat16*)op.p[UCDIR_SOFTMAX_P_OUT_BF16], op.i[UCDIR_SOFTMAX_I_OUT_LD]);
+  }
   ++g_launches;
   return 0;
 }

@@ -529,9 +529,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           }
           if (EPI == EPI_F32) {
             float* d = reinterpret_cast<float*>(dst_row) + nb;
+            if (nb + CH <= p.ncol_valid && (p.dstC & 3) == 0 && (p.dstCoff & 3) == 0) {
+              // full chunk: 16-byte stores (the attention scores: each thread writes 128 contiguous bytes of its row)
 #pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (nb + j < p.ncol_valid) { d[j] = v[j]; t1s += v[j]; t2s += v[j] * v[j]; }
+              for (int j = 0; j < CH; j += 4) {
+                *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                t1s += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+                t2s += (v[j] * v[j] + v[j + 1] * v[j + 1]) + (v[j + 2] * v[j + 2] + v[j + 3] * v[j + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (nb + j < p.ncol_valid) { d[j] = v[j]; t1s += v[j]; t2s += v[j] * v[j]; }
+            }
           } else if (EPI == EPI_PLAIN_T && nb >= p.t_col0) {
             // transposed store (attention V^T): lanes hold consecutive pixels, so each store is one coalesced run
             __nv_bfloat16* d = p.dst2 + ((size_t)img * (p.Ntot - p.t_col0) + (nb - p.t_col0)) * p.t_ld + (y * p.W + x);
