@@ -34,6 +34,8 @@ WORKLOADS = {
     "c1_128": (1, 128, 1024, 64, False),
     # what `sr.py -p val` runs for a 1024x1024 image: DDPM.test pads to 1152x1152 -> reference-default tiler (1024, 64)
     "c3_1152_ref_tiling": (1, 1152, 1024, 64, False),
+    # 16 tiles of 128x128 = the per-rank share of the headline workload at 8 GPUs (for per-launch overhead studies)
+    "rank_share_16_tiles": (1, 384, 128, 16, True),
 }
 
 

@@ -84,7 +84,7 @@ def emu_conv(op, mem):
     x = mem.view(_p(op, "UCDIR_CONV_P_SRC0"), (B, sH, sW, C0))
     if C1:
         x = torch.cat([x, mem.view(_p(op, "UCDIR_CONV_P_SRC1"), (B, sH, sW, C1))], dim=-1)
-    x = x.double() if False else x.clone()
+    x = x.clone()
     if pre:
         s0 = mem.view(_p(op, "UCDIR_CONV_P_STATS0"), (B, 2), torch.float64).clone()
         if C1:

@@ -11,11 +11,17 @@
 // * GroupNorm(1,C) in front of a convolution is folded: gamma is multiplied into the packed weights and the
 //   epilogue applies v = rstd*acc - mean*rstd*TG[cls][n] + TB[cls][n], where TG/TB are per-layer tables over
 //   the 9 border classes (which taps fall outside the image) -- model/ucdir.py:109-112,161 never touch HBM.
-// * warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + tcgen05.mma issuer (one lane),
-//   warps 2..5 = epilogue (tcgen05.ld 32x32b, one TMEM lane quadrant each).
-// * epilogues: plain (bias/FiLM-free) + Swish + residual, or the integration-module mix (model/ucdir.py:135-140):
-//   8 adjacent accumulator columns weighted by the per-pixel guidance map x per-step attw, Swish, + residual.
-//   Both emit the {sum, sum^2} of what they store for the next GroupNorm.
+// * persistent CTAs (one per SM) over work items (M tile, N sub-tile); warp roles: warp 0 = TMA producer, warp 1 = TMEM
+//   allocator + tcgen05.mma issuer (whole warp runs the loop, one elect.sync lane issues), warps 4..15 = epilogue
+//   (tcgen05.ld 32x32b, three warps per TMEM lane quadrant); setmaxnreg moves registers from warpgroup 0 to the
+//   epilogue warpgroups.  smem ring (full/empty mbarriers) between producer and MMA; a ring of 512/NT TMEM
+//   accumulators (tmem_full/tmem_empty) between MMA and epilogue, so the MMAs of item i+1 overlap the epilogue of i.
+// * epilogues (compile-time EPI): plain + Swish + residual (optionally storing a column range transposed: attention
+//   V^T), fp32 output (attention scores, eps), or the integration-module mix (model/ucdir.py:135-140): 8 adjacent
+//   accumulator columns weighted by the per-pixel guidance map x per-step attw, Swish, + residual.
+//   All emit the {sum, sum^2} of what they store for the next GroupNorm.
+// * the same kernel is the batched GEMM of the attention core (model/ucdir.py:174,179): per-image "weights" through a
+//   3-D tensor map (W_BATCHED), activation operand = a channel slice of a wider tensor (SRC_CSTRIDE).
 #include <cuda.h>
 #include <cstdio>
 #include "common.cuh"

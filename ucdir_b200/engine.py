@@ -886,8 +886,7 @@ class UNetEngine:
         return ol
 
     # ---- sessions -----------------------------------------------------------------------
-    def session(self, cond: torch.Tensor, guide: torch.Tensor, levels=None, geometry: Optional[Geometry] = None,
-                cond_channels: Optional[int] = None) -> "Session":
+    def session(self, cond: torch.Tensor, guide: torch.Tensor, geometry: Optional[Geometry] = None) -> "Session":
         """A session binds one conditioning image batch (+ guidance) to a resident plan."""
         self.ensure_weights()
         B, _, h, w = cond.shape
@@ -922,7 +921,7 @@ class UNetEngine:
     def _forward_generic(self, x, time, guide, geometry):
         self.ensure_weights()
         x = x.contiguous().float()
-        sess = self.session(x, guide.contiguous().float(), geometry=geometry, cond_channels=x.shape[1])
+        sess = self.session(x, guide.contiguous().float(), geometry=geometry)
         out = torch.empty((x.shape[0], self.m.cfg["out_channel"], x.shape[2], x.shape[3]), device=x.device, dtype=F32)
         sess.eps_only(time.reshape(-1).float().contiguous(), out)
         return out
@@ -987,6 +986,7 @@ class Session:
         nblk = eng.n_blocks()
         self.levels = torch.zeros(max(NT, 1), dtype=F32, device=dev)      # per-tile noise levels (generic forward)
         self.attw = torch.empty((max(NT, 1), nblk, 8), dtype=F32, device=dev)
+        self._mix_ops: List[tuple] = []          # (op, first tile of its chunk, attw base pointer, pointer key, stride key)
         self.static_ops = OpList()
         self.step_ops = OpList()
         self.idx_gather: List[int] = []
@@ -1055,7 +1055,6 @@ class Session:
 
     # per-sample attw addressing: sample b of chunk starting at tile a reads attw[(a + b) * stride]
     def _chunk_attw_fix(self, sub: OpList, a: int):
-        self._mix_ops = getattr(self, "_mix_ops", [])
         for o in sub.ops:
             if o.kind == K_["UCDIR_OP_CONV_F32"] and o.i[K_["UCDIR_CONV_I_MODE"]] == 1:
                 self._mix_ops.append((o, a, int(o.p[K_["UCDIR_CONV_P_ATTW"]]), "UCDIR_CONV_P_ATTW", "UCDIR_CONV_I_ATTW_STRIDE"))
@@ -1120,7 +1119,7 @@ class Session:
         _run_ops(self.tail_ops.array(), 1, self.stream())
 
     def step(self, x_t: torch.Tensor, out: torch.Tensor, level: float, scalars, noise: Optional[torch.Tensor],
-             clip: bool = True, level_index=None):
+             clip: bool = True):
         """One p_sample (model/diffusion.py:160-183): eps = UNet(cat[cond, x_t], level); posterior update."""
         if self.in_channels != 3:
             raise RuntimeError("session was bound with a pre-concatenated input; step() needs cond only")
