@@ -24,6 +24,7 @@
 //   3-D tensor map (W_BATCHED), activation operand = a channel slice of a wider tensor (SRC_CSTRIDE).
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ucdir {
@@ -243,6 +244,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   uint64_t* bfree = bfull + 1;                        // BSTAT: MMA -> producer, all MMAs that read the old block retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfree + 1);
 
+  // Programmatic dependent launch: let the next kernel of the stream be scheduled while this one runs (its prologue
+  // -- barrier init, TMEM allocation, tensor-map prefetch -- then overlaps our tail); it blocks in griddepcontrol.wait
+  // until this grid has completed and flushed, so no data hazard is introduced.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_sub = p.Ntot / NT;
   const long long total = (long long)p.m_tiles * n_sub;
@@ -265,6 +270,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // everything below touches data of earlier kernels
   // Register reallocation between warpgroups (setmaxnreg is warpgroup-wide, first statement of each role branch):
   // the epilogue keeps a chunk of accumulators, its folded-GroupNorm terms and the next chunk's table values in flight.
   if (warp < TC_FIRST_EPI_WARP) {
@@ -661,6 +667,8 @@ static void choose_tile(int W, int H, int B, int stride, int* bw, int* bh, int* 
   *bw = bbw; *bh = bbh; *bn = bbn;
 }
 
+static const bool g_pdl = []() { const char* e = getenv("UCDIR_PDL"); return !(e && e[0] == '0'); }();
+
 template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT, int SPS>
 static int launch_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t st) {
   using S = TcCfg<KA, KB, NT, NSPLIT, BSTAT, SPS>;
@@ -671,7 +679,14 @@ static int launch_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
       set_error("tc_conv: cannot opt in to %d bytes of shared memory: %s", smem_bytes, cudaGetErrorString(cudaGetLastError())); return -3; }
     attr = smem_bytes;
   }
-  tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT, SPS><<<grid, TC_THREADS, smem_bytes, st>>>(a0, a1, b, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT, SPS>, a0, a1, b, p) != cudaSuccess) {
+    set_error("tc_conv: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
   return 0;
 }
 
