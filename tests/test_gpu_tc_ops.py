@@ -59,7 +59,7 @@ def stats_of(x_bf16):
     return torch.stack([v.sum(1), (v * v).sum(1)], dim=1).contiguous()
 
 
-def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1):
+def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1, row3=0):
     g = torch.Generator().manual_seed(seed)
     sH, sW = H * stride, W * stride
     c = Case()
@@ -89,7 +89,8 @@ def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1):
         E._tc_op(ol, src0=act(t["x0"], C0, sH, sW, t.get("s0")), src1=act(t["x1"], C1, sH, sW, t.get("s1")) if C1 else None,
                  w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), tg=t["tg"].data_ptr() if "tg" in t else 0, gn=1 if gn else 0,
                  ncls=9 if (gn and ks == 3) else 1, nty=ks, ntx=ks, oy0=-(ks // 2), ox0=-(ks // 2), stride=stride, act=act_,
-                 res=act(t["res"], Cout, H, W) if res else None, dst=act(t["dst"], Cout, H, W, t["dstats"]), ntot=Cout, B=B, nt=nt)
+                 res=act(t["res"], Cout, H, W) if res else None, dst=act(t["dst"], Cout, H, W, t["dstats"]), ntot=Cout, B=B, nt=nt,
+                 row3=row3)
         return ol
     return c, build
 
@@ -278,3 +279,18 @@ def test_softmax_long_rows(rows, cols, in_ld, bf16_out):
         assert_close(dev["P"], host["P"], "softmax bf16 out", rtol=1e-2, atol=1e-3)
     else:
         assert_close(dev["S"][:, :cols], host["S"][:, :cols], "softmax in place", rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(seed=31, B=2, H=128, W=128, C0=64, C1=0, Cout=64, ks=3, gn=True, act_=1, res=False, row3=1),
+    dict(seed=32, B=1, H=128, W=128, C0=128, C1=64, Cout=64, ks=3, gn=True, act_=1, res=False, row3=1),
+    dict(seed=33, B=1, H=6, W=256, C0=64, C1=0, Cout=128, ks=3, gn=False, act_=0, res=True, row3=1),
+], ids=["64_64", "128+64_64", "W256_64_128"])
+def test_tc_dense_row3(cfg):
+    """ROW3 schedule: one 130-pixel activation row per filter row, the three horizontal taps read it through
+    descriptors shifted by 0 / 1 / 2 rows (swizzle base offset).  Same results as the per-tap schedule."""
+    c, build = dense_case(**cfg)
+    host, dev = run_both(c, build)
+    assert_close(dev["dst"], host["dst"], "dst")
+    assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
+

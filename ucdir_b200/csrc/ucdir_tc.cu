@@ -128,6 +128,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes
          (layout << 61);
 }
 
+// Same, for an operand that starts `shift` rows (of 128 bytes) into a 1024-byte aligned swizzle-128B buffer.  Measured on
+// B200 (tests/test_gpu_tc_ops.py::test_tc_dense_row3): the 128B swizzle is a pure function of the shared-memory address
+// bits, so the shifted start needs no base-offset correction (base offset = shift or 8 - shift both read wrong rows).
+__device__ __forceinline__ uint64_t make_desc_shifted(uint32_t saddr_aligned, uint32_t shift) {
+  return make_desc(saddr_aligned + shift * 128u, 128u);
+}
+
 // ------------------------------------------------------------------------------------------------
 struct TcParams {
   const double* stats0; const double* stats1;
@@ -162,9 +169,13 @@ struct TcCfg {
   static constexpr int B_BYTES = NT * KB * 2;
   static constexpr int B_PAD = (B_BYTES + 1023) & ~1023;
   static constexpr int SLAB = A_BYTES + (BSTAT ? 0 : B_PAD);    // weight-stationary: the ring holds activation slabs only
-  static constexpr int STAGE = SPS * SLAB;
+  // SPS == 4 ("ROW3"): one 130-pixel activation row serves the three horizontal taps of a filter row
+  static constexpr bool ROW3 = (SPS == 4);
+  static constexpr int A_ROW = (130 * KA * 2 + 1023) & ~1023;
+  static constexpr int STAGE = ROW3 ? (A_ROW + 3 * B_PAD) : SPS * SLAB;
   static constexpr int STAGES_RAW = 196608 / STAGE;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < (SPS > 1 ? 2 : 4) ? (SPS > 1 ? 2 : 4) : STAGES_RAW);   // <= 8: the rest of the 228 KB stays L1 for the epilogue's loads
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < (SPS > 1 ? 2 : 4) ? (SPS > 1 ? 2 : 4) : STAGES_RAW);
+  static_assert(STAGES * STAGE <= 200 * 1024, "smem ring too large");   // <= 8: the rest of the 228 KB stays L1 for the epilogue's loads
   static constexpr int SLOTW = NT < 32 ? 32 : NT;          // TMEM columns per accumulator slot
   static constexpr int NSLOT = 512 / SLOTW;                // accumulator ring: MMA of item i+1.. overlaps epilogue of item i
   static constexpr int BARS = (2 * STAGES + 2 * NSLOT + 2) * 8 + 64;
@@ -296,6 +307,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         __syncwarp();
         cur_ns = cur.ns;
       }
+      if (S::ROW3) {
+        // one stage = one filter row (ty) x one channel chunk: a 130-pixel activation row + the three taps' weights
+        const uint32_t row_bytes = (uint32_t)((p.bw + 2) * KA * 2 + 3 * NT * KB * 2);
+        for (int ty = 0; ty < 3; ++ty) {
+          for (int j = 0; j < p.nchunk; ++j) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one()) {
+              uint8_t* sa = smem + stage * S::STAGE;
+              mbar_expect_tx(&full[stage], row_bytes);
+              if (j < p.c0_chunks) tma_load_4d(&mapA0, &full[stage], sa, j * KA, x0, y0 + ty, n0);
+              else tma_load_4d(&mapA1, &full[stage], sa, (j - p.c0_chunks) * KA, x0, y0 + ty, n0);
+#pragma unroll
+              for (int tx = 0; tx < 3; ++tx)
+                tma_load_2d(&mapB, &full[stage], sa + S::A_ROW + tx * S::B_PAD, ((ty * 3 + tx) * p.nchunk + j) * KB, ncol0);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        cur.template next<BSTAT>(n_sub, p.tiles_x, p.tiles_y, p.tiles_n);
+        continue;
+      }
       int kb = 0, ty = 0, tx = 0, j = 0;                // K coordinate of the B slab; tap and channel chunk of the slab
       for (int sidx = 0; sidx < nslab_p; ++sidx) {
         const int sub = sidx % SPS;
@@ -336,13 +369,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       mbar_wait(&tmem_empty[slot], sph ^ 1);            // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(slot * S::SLOTW);
-      const int nstage_item = nslab / SPS;
+      const int nstage_item = S::ROW3 ? 3 * p.nchunk : nslab / SPS;
       for (int g = 0; g < nstage_item; ++g) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        if (S::ROW3) {
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * S::STAGE);
+#pragma unroll
+            for (int tx = 0; tx < 3; ++tx) {
+              const uint64_t ad = make_desc_shifted(sa, (uint32_t)tx);
+              const uint64_t bd = make_desc(sa + S::A_ROW + tx * S::B_PAD, KB * 2);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_bf16(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (g | tx | k) != 0);
+            }
+            umma_commit(&empty[stage]);
+            if (g == nstage_item - 1) umma_commit(&tmem_full[slot]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
         if (elect_one()) {
 #pragma unroll
-          for (int sub = 0; sub < SPS; ++sub) {
+          for (int sub = 0; sub < (S::ROW3 ? 1 : SPS); ++sub) {
             const int i = g * SPS + sub;                 // slab index within the item
             const uint32_t sa = smem_u32(smem + stage * S::STAGE + sub * S::SLAB);
             const uint32_t sb = BSTAT ? smem_u32(bres + i * BSLAB) : sa + S::A_BYTES;
@@ -761,10 +812,15 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   if (mt > 0x7fffffffL) { set_error("tc_conv: too many M tiles"); return -2; }
   p.m_tiles = (int)mt; p.tiles_n = tiles_n;
   if (dry) return 0;
+  // ROW3: row tiles (128 px x 1 row) of a dense 3x3 stride-1 conv load one 130-pixel activation row per filter row and
+  // issue the three horizontal taps from shifted descriptors of that slab (3x less activation traffic from L2)
+  const bool row3 = op.i[UCDIR_TC_I_ROW3] == 1 && p.nty == 3 && p.ntx == 3 && p.stride == 1 && p.groups == 1 && KC == 64 && KB == 64 &&
+                    NSPLIT == 1 && p.bw == 128 && p.bh == 1 && p.bn == 1 && !p.w_batched && !p.dst2 && !p.dst_f32 && p.mode != 1 && NT <= 128;
+  const int abw = row3 ? p.bw + 2 : p.bw;
   CUtensorMap a0, a1, bm;
-  int rc = make_act_map(&a0, src0, C0, p.srcW, p.srcH, p.B, KC, p.bw, p.bh, p.bn, p.stride, cstride0);
+  int rc = make_act_map(&a0, src0, C0, p.srcW, p.srcH, p.B, KC, abw, p.bh, p.bn, p.stride, cstride0);
   if (rc) return rc;
-  if (C1 > 0) { rc = make_act_map(&a1, src1, C1, p.srcW, p.srcH, p.B, KC, p.bw, p.bh, p.bn, p.stride, C1); if (rc) return rc; }
+  if (C1 > 0) { rc = make_act_map(&a1, src1, C1, p.srcW, p.srcH, p.B, KC, abw, p.bh, p.bn, p.stride, C1); if (rc) return rc; }
   else a1 = a0;
   const int Ktot = p.nty * p.ntx * p.nchunk * KB;
   if (p.w_batched) rc = make_w_map(&bm, w, C0, op.i[UCDIR_TC_I_W_ROWS] ? op.i[UCDIR_TC_I_W_ROWS] : p.Ntot, KB, NT, w_rowstride, p.B, w_batchstride);
@@ -786,10 +842,12 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   // three filter taps per pipeline stage for the layers whose per-slab MMA work is small (N <= 128 columns per MMA)
   // (measured on B200, round 1: no gain -- those ops are bound by their epilogue, which already overlaps the main loop --
   //  so it is opt-in)
-  const int sps = (nslab % 3 == 0 && op.i[UCDIR_TC_I_SPS3] == 1 && (NT / NSPLIT <= 128 || (epi == EPI_MIX && KB < 64))) ? 3 : 1;
+  int sps = (nslab % 3 == 0 && op.i[UCDIR_TC_I_SPS3] == 1 && (NT / NSPLIT <= 128 || (epi == EPI_MIX && KB < 64))) ? 3 : 1;
+  if (row3) sps = 4;
 #define INST(ka, kb, nt, ns, ep, bs, sp) if (KC == ka && KB == kb && NT == nt && NSPLIT == ns && epi == ep && bstat == bs && sps == sp) { rc = launch_inst<ka, kb, nt, ns, ep, bs, sp>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
   INST(64, 64, 64, 1, EPI_PLAIN, 0, 1) INST(64, 64, 128, 1, EPI_PLAIN, 0, 1) INST(64, 64, 256, 1, EPI_PLAIN, 0, 1) INST(16, 16, 64, 1, EPI_PLAIN, 0, 1)
   INST(64, 64, 64, 1, EPI_PLAIN, 0, 3) INST(64, 64, 128, 1, EPI_PLAIN, 0, 3) INST(16, 16, 64, 1, EPI_PLAIN, 0, 3)
+  INST(64, 64, 64, 1, EPI_PLAIN, 0, 4) INST(64, 64, 128, 1, EPI_PLAIN, 0, 4)
   INST(64, 64, 256, 1, EPI_PLAIN_T, 0, 1) INST(64, 64, 128, 1, EPI_PLAIN_T, 0, 1) INST(64, 64, 128, 1, EPI_PLAIN_T, 0, 3)
   INST(64, 64, 16, 1, EPI_F32, 0, 1) INST(64, 64, 64, 1, EPI_F32, 0, 1) INST(64, 64, 128, 1, EPI_F32, 0, 1) INST(64, 64, 256, 1, EPI_F32, 0, 1)
   INST(64, 64, 16, 1, EPI_F32, 0, 3) INST(64, 64, 64, 1, EPI_F32, 0, 3) INST(64, 64, 128, 1, EPI_F32, 0, 3)
