@@ -149,3 +149,30 @@ def test_ddim_sample(emulated, golden, sid_weights):
     finally:
         net._noise_source = None
     close(traj, g["traj"])
+
+
+def test_boundary_contract_deepcopy_load_state_dict_and_reschedule(emulated, golden, sid_weights):
+    """What model/model.py does to the object define_G returns: deep-copies it for EMA (:50), loads a checkpoint into it
+    (:236-239, strict=False) and calls set_new_noise_schedule repeatedly (:59-61, sr.py:399)."""
+    import copy
+    net, sd = sid_weights
+    g = golden("unet")
+    args = (T(g["x6"]), T(g["level"]), T(g["guide"]))
+    base = net.denoise_fn(*args)
+    ema = copy.deepcopy(net)                                       # engines are per module; the copy builds its own
+    assert ema.denoise_fn._engine is None and set(ema.state_dict()) == set(net.state_dict())
+    close(ema.denoise_fn(*args), base, rtol=0, atol=0)
+    # loading different weights must invalidate the packed copies
+    sd2 = {k: (v * 0.5 if k.endswith("final_conv.3.weight") else v) for k, v in ema.state_dict().items()}
+    missing = ema.load_state_dict({k: v for k, v in sd2.items() if not k.startswith("predictor.conv10")}, strict=False)
+    assert all(k.startswith("predictor.conv10") for k in missing.missing_keys)
+    out2 = ema.denoise_fn(*args)
+    bias = sd["denoise_fn.final_conv.3.bias"].view(1, -1, 1, 1)
+    close(out2 - bias, (base - bias) * 0.5, rtol=1e-4, atol=1e-5)
+    # schedules can be replaced at will; buffers keep the reference's names, dtypes and lengths
+    for T_ in (2000, 50, 7):
+        ema.set_new_noise_schedule(dict(schedule="linear", n_timestep=T_, linear_start=1e-6, linear_end=0.01), torch.device("cpu"))
+        assert ema.num_timesteps == T_ and ema.betas.shape == (T_,) and ema.betas.dtype == torch.float32
+        assert ema.sqrt_alphas_cumprod_prev.shape == (T_ + 1,) and ema.sqrt_alphas_cumprod_prev.dtype == np.float64
+    with pytest.raises(NotImplementedError):
+        ema(T(g["x6"]))                                            # training forward (p_losses) is out of scope
