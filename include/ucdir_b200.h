@@ -208,6 +208,7 @@ enum ucdir_tc_int {
   UCDIR_TC_I_W_ROWS = 38,                        /* batched weights: rows that exist per image (0 = NTOT); the rest read as 0 */
   UCDIR_TC_I_BSTAT = 39,                         /* 1: weight-stationary schedule for grouped mix convs (weights resident in smem, items N-tile major) */
   UCDIR_TC_I_SPS3 = 40,                          /* 1: three K slabs (filter taps) per pipeline stage for the small-N layers */
+  UCDIR_TC_I_NO_CTAB = 42,                       /* 1: do not cache the folded-GroupNorm additive table of the current image in shared memory */
   UCDIR_TC_I_ROW3 = 41                           /* 1: row tiles of dense 3x3 convs share one 130-pixel activation row among the three horizontal taps */
 };
 enum ucdir_tc_flt { UCDIR_TC_F_EPS = 0, UCDIR_TC_F_ALPHA = 1 /* 0 = 1.0 */ };

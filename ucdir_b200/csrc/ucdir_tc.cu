@@ -144,6 +144,7 @@ struct TcParams {
   int B, H, W, srcH, srcW;
   int Ntot, ncol_valid;
   int bw, bh, bn, tiles_x, tiles_y, tiles_n, m_tiles, bres_bytes;
+  int ctab;                    // mix epilogue: cache cadd[9][Ntot] of the current image in shared memory (bn == 1, small Ntot)
   int nty, ntx, oy0, ox0, stride;
   int nchunk, c0_chunks, groups, Ng, Cg, cg_eff;
   int gn, ncls, act, mode, dst_f32;
@@ -235,12 +236,14 @@ struct ItemCursor {
 //   smem ring   full[s]/empty[s]            TMA producer  <-> MMA issuer
 //   TMEM ring   tmem_full[j]/tmem_empty[j]  MMA issuer    <-> epilogue warps   (NSLOT accumulators of NT columns)
 // EPI selects the epilogue at compile time (the chunk loop is the hot code of the small-K layers):
-enum { EPI_PLAIN = 0, EPI_MIX = 1, EPI_F32 = 2, EPI_PLAIN_T = 3 };
+enum { EPI_PLAIN = 0, EPI_MIX = 1, EPI_F32 = 2, EPI_PLAIN_T = 3, EPI_MIXC = 4 /* mix + additive table cached in smem */ };
 
 template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT, int SPS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                 const __grid_constant__ CUtensorMap mapA1,
                                                                 const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  constexpr bool MIX = (EPI == EPI_MIX || EPI == EPI_MIXC);
+  constexpr bool CTAB = (EPI == EPI_MIXC);
   using S = TcCfg<KA, KB, NT, NSPLIT, BSTAT, SPS>;
   constexpr int STAGES = S::STAGES, NSLOT = S::NSLOT;
   constexpr int BSLAB = NT * KB * 2;                  // one weight slab (all NT rows of one K slice)
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   uint64_t* bfull = tmem_empty + NSLOT;               // BSTAT: producer -> MMA, weight block landed
   uint64_t* bfree = bfull + 1;                        // BSTAT: MMA -> producer, all MMAs that read the old block retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfree + 1);
+  float* ctab = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~uintptr_t(15));   // [9][Ntot] when p.ctab
 
   // Programmatic dependent launch: let the next kernel of the stream be scheduled while this one runs (its prologue
   // -- barrier init, TMEM allocation, tensor-map prefetch -- then overlaps our tail); it blocks in griddepcontrol.wait
@@ -443,6 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     float s1 = 0.f, s2 = 0.f;                        // GroupNorm statistics of what this thread stored, current image
     int stat_img = -1;
     int gn_img = -1; float gn_rstd = 1.f, gn_mr = 0.f;   // GroupNorm scalars of the last image seen (FP64 math, cached)
+    int ctab_img = -1;
     int slot = 0; uint32_t sph = 0;
     for (int li = 0; li < n_items; ++li) {
       const int ncol0 = cur.ns * NT;
@@ -471,7 +476,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         pix_out = p.dstUp ? ((size_t)img * 2 * p.H + 2 * y + p.dstPy) * (2 * p.W) + 2 * x + p.dstPx : pix_in;
         res_row = p.res ? p.res + pix_in * p.resC : nullptr;
         dst_row = reinterpret_cast<uint8_t*>(p.dst) + (pix_out * p.dstC + p.dstCoff) * (EPI == EPI_F32 ? 4 : 2);
-        if (EPI == EPI_MIX) {
+        if (MIX) {
           const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.att + pix_in * 8));
           const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.att + pix_in * 8 + 4));
           const float* w8 = p.attw + (size_t)img * p.attwStride;
@@ -479,8 +484,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           aw[4] = t1.x * __ldg(w8 + 4); aw[5] = t1.y * __ldg(w8 + 5); aw[6] = t1.z * __ldg(w8 + 6); aw[7] = t1.w * __ldg(w8 + 7);
         }
       }
+      if (CTAB) {
+        // all epilogue warps walk the same items, so they all see the image change at the same item
+        const int im0 = cur.tn_i * p.bn;
+        if (im0 != ctab_img) {
+          ctab_img = im0;
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");       // everyone is done with the old table
+          const GnScalars sc = gn_scalars(p.stats0, p.stats1, im0 < p.B ? im0 : 0, p.gn_count, p.eps);
+          const float mri = sc.mean * sc.rstd;
+          const int et = threadIdx.x - 32 * TC_FIRST_EPI_WARP;
+          for (int i = et * 4; i < 9 * p.Ntot; i += 32 * TC_EPI_WARPS * 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.tb + i));
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.tg + i));
+            *reinterpret_cast<float4*>(ctab + i) = make_float4(fmaf(-mri, g.x, b.x), fmaf(-mri, g.y, b.y), fmaf(-mri, g.z, b.z), fmaf(-mri, g.w, b.w));
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        }
+      }
       const float* tb = p.tb + (size_t)cls * p.Ntot + ncol0;
       const float* tg = p.tg ? p.tg + (size_t)cls * p.Ntot + ncol0 : nullptr;
+      const float* ctab_row = ctab + (size_t)cls * p.Ntot + ncol0;
       float t1s = 0.f, t2s = 0.f;
       // Per-column additive term of the folded GroupNorm, cadd[j] = TB[cls][n] - mean*rstd*TG[cls][n]: the table loads
       // are issued one chunk ahead (and, for the first chunk, before waiting for the accumulator) so their L2 latency
@@ -489,13 +512,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       float cadd[CH];
       float4 tb4[CH / 4], tg4[CH / 4];
       auto issue_tables = [&](int c0) {
+        if (CTAB) return;
 #pragma unroll
         for (int j = 0; j < CH / 4; ++j) {
           tb4[j] = __ldg(reinterpret_cast<const float4*>(tb + c0) + j);
           tg4[j] = tg ? __ldg(reinterpret_cast<const float4*>(tg + c0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      auto finish_tables = [&]() {
+      auto finish_tables = [&](int c0) {
+        if (CTAB) {
+#pragma unroll
+          for (int j = 0; j < CH / 4; ++j) {
+            const float4 t = *reinterpret_cast<const float4*>(ctab_row + c0 + 4 * j);
+            cadd[4 * j + 0] = t.x; cadd[4 * j + 1] = t.y; cadd[4 * j + 2] = t.z; cadd[4 * j + 3] = t.w;
+          }
+          return;
+        }
         const float2 nm = make_float2(-mr, -mr);
 #pragma unroll
         for (int j = 0; j < CH / 4; ++j) {
@@ -511,7 +543,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         if (NO_ == 4) res_next = __ldg(reinterpret_cast<const uint2*>(rp));
         else res_next.x = __ldg(reinterpret_cast<const uint32_t*>(rp));
       };
-      if (valid && half * CH < NT) { issue_tables(half * CH); if (EPI == EPI_MIX) issue_res(half * CH); finish_tables(); }
+      if (valid && half * CH < NT) { issue_tables(half * CH); if (MIX) issue_res(half * CH); finish_tables(half * CH); }
       mbar_wait(&tmem_full[slot], sph);
       tc_fence_after();
 #pragma unroll 1
@@ -521,7 +553,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         uint2 res_mix = make_uint2(0u, 0u);
         uint4 res_pl[CH / 8];
         if (valid) {
-          if (EPI == EPI_MIX) {
+          if (MIX) {
             res_mix = res_next;
           } else if (EPI != EPI_F32 && p.res) {
             const uint4* rp = reinterpret_cast<const uint4*>(res_row + ncol0 + c0);
@@ -540,7 +572,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         tmem_ld_wait();
 #endif
 #if defined(UCDIR_ABLATE) && (UCDIR_ABLATE == 1 || UCDIR_ABLATE == 2)   // ablation: drain TMEM, skip all epilogue math / IO
-        if (EPI == EPI_MIX) { if (rv[0] == 0x7fc12345u) t1s += 1.f; continue; }
+        if (MIX) { if (rv[0] == 0x7fc12345u) t1s += 1.f; continue; }
 #endif
         if (!valid) continue;
         float v[CH];
@@ -553,8 +585,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           }
         }
         const bool more = c0 + CSTEP < NT;
-        if (more && EPI == EPI_MIX) issue_res(c0 + CSTEP);   // next chunk's residual in flight while this chunk's math runs
-        if (EPI == EPI_MIX) {
+        if (more && MIX) issue_res(c0 + CSTEP);   // next chunk's residual in flight while this chunk's math runs
+        if (MIX) {
           // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
           const int cbase = (ncol0 + c0) >> 3;
           __align__(8) __nv_bfloat16 o[NO];
@@ -625,7 +657,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             }
           }
         }
-        if (more) { issue_tables(c0 + CSTEP); finish_tables(); }   // next chunk's additive terms (L1/L2 hits, short-lived registers)
+        if (more) { issue_tables(c0 + CSTEP); finish_tables(c0 + CSTEP); }   // next chunk's additive terms (short-lived registers)
       }
       // this warp is done reading the accumulator slot: hand it back to the MMA issuer
       tc_fence_before();
@@ -723,7 +755,7 @@ static const bool g_pdl = []() { const char* e = getenv("UCDIR_PDL"); return !(e
 template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT, int SPS>
 static int launch_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t st) {
   using S = TcCfg<KA, KB, NT, NSPLIT, BSTAT, SPS>;
-  const int smem_bytes = S::TOTAL + (BSTAT ? p.bres_bytes : 0);
+  const int smem_bytes = S::TOTAL + (BSTAT ? p.bres_bytes : 0) + (p.ctab ? 9 * p.Ntot * 4 + 16 : 0);
   static int attr = 0;
   if (attr < smem_bytes) {
     if (cudaFuncSetAttribute(tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT, SPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
@@ -830,7 +862,9 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
   const long long items = (long long)mt * (p.Ntot / NT);
   dim3 grid((unsigned)(items < n_sm ? items : n_sm), 1, 1);      // persistent: one CTA per SM
-  const int epi = p.mode == 1 ? EPI_MIX : (p.dst_f32 ? EPI_F32 : (p.dst2 ? EPI_PLAIN_T : EPI_PLAIN));
+  p.ctab = (p.mode == 1 && p.gn && p.ncls == 9 && p.bn == 1 && p.Ntot <= 1024 && KC == 32 && KB == 16 && op.i[UCDIR_TC_I_NO_CTAB] == 0 &&
+            op.i[UCDIR_TC_I_BSTAT] == 0 && op.i[UCDIR_TC_I_SPS3] == 0) ? 1 : 0;
+  const int epi = p.mode == 1 ? (p.ctab ? EPI_MIXC : EPI_MIX) : (p.dst_f32 ? EPI_F32 : (p.dst2 ? EPI_PLAIN_T : EPI_PLAIN));
   // weight-stationary schedule: the whole weight block of one N sub-tile stays in shared memory while the CTA walks
   // its M tiles (items ordered N-sub-tile major).  Used for the grouped integration-module convs whose weight slabs
   // are small, many and 32/64-byte rowed (the streamed form re-fetched them for every pixel tile).
@@ -838,11 +872,11 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   p.bres_bytes = nslab * NT * KB * 2;
   // (measured on B200, round 1: no gain over the streamed form -- the mix epilogue, not L2 traffic, bounds these ops --
   //  so it is opt-in)
-  const int bstat = (epi == EPI_MIX && !p.w_batched && p.bres_bytes <= 150 * 1024 && op.i[UCDIR_TC_I_BSTAT] == 1) ? 1 : 0;
+  const int bstat = ((epi == EPI_MIX || epi == EPI_MIXC) && !p.w_batched && p.bres_bytes <= 150 * 1024 && op.i[UCDIR_TC_I_BSTAT] == 1) ? 1 : 0;
   // three filter taps per pipeline stage for the layers whose per-slab MMA work is small (N <= 128 columns per MMA)
   // (measured on B200, round 1: no gain -- those ops are bound by their epilogue, which already overlaps the main loop --
   //  so it is opt-in)
-  int sps = (nslab % 3 == 0 && op.i[UCDIR_TC_I_SPS3] == 1 && (NT / NSPLIT <= 128 || (epi == EPI_MIX && KB < 64))) ? 3 : 1;
+  int sps = (nslab % 3 == 0 && op.i[UCDIR_TC_I_SPS3] == 1 && (NT / NSPLIT <= 128 || ((epi == EPI_MIX || epi == EPI_MIXC) && KB < 64))) ? 3 : 1;
   if (row3) sps = 4;
 #define INST(ka, kb, nt, ns, ep, bs, sp) if (KC == ka && KB == kb && NT == nt && NSPLIT == ns && epi == ep && bstat == bs && sps == sp) { rc = launch_inst<ka, kb, nt, ns, ep, bs, sp>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
   INST(64, 64, 64, 1, EPI_PLAIN, 0, 1) INST(64, 64, 128, 1, EPI_PLAIN, 0, 1) INST(64, 64, 256, 1, EPI_PLAIN, 0, 1) INST(16, 16, 64, 1, EPI_PLAIN, 0, 1)
@@ -854,6 +888,7 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   INST(32, 16, 256, 4, EPI_MIX, 1, 3) INST(32, 16, 256, 2, EPI_MIX, 1, 3) INST(32, 32, 256, 1, EPI_MIX, 1, 3)
   INST(32, 16, 256, 4, EPI_MIX, 0, 3) INST(32, 16, 256, 2, EPI_MIX, 0, 3) INST(32, 32, 256, 1, EPI_MIX, 0, 3) INST(64, 64, 256, 1, EPI_MIX, 0, 1)
   INST(32, 16, 256, 4, EPI_MIX, 0, 1) INST(32, 16, 256, 2, EPI_MIX, 0, 1) INST(32, 32, 256, 1, EPI_MIX, 0, 1)
+  INST(32, 16, 256, 4, EPI_MIXC, 0, 1) INST(32, 16, 256, 2, EPI_MIXC, 0, 1)
 #undef INST
   set_error("tc_conv: no kernel instance for KC=%d KB=%d NT=%d NSPLIT=%d epilogue %d bstat %d sps %d", KC, KB, NT, NSPLIT, epi, bstat, sps);
   return -2;
