@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define UCDIR_ABI_VERSION 11
+#define UCDIR_ABI_VERSION 12
 
 #define UCDIR_OP_NPTR 16
 #define UCDIR_OP_NINT 48
@@ -209,7 +209,9 @@ enum ucdir_tc_int {
   UCDIR_TC_I_BSTAT = 39,                         /* 1: weight-stationary schedule for grouped mix convs (weights resident in smem, items N-tile major) */
   UCDIR_TC_I_SPS3 = 40,                          /* 1: three K slabs (filter taps) per pipeline stage for the small-N layers */
   UCDIR_TC_I_NO_CTAB = 42,                       /* 1: do not cache the folded-GroupNorm additive table of the current image in shared memory */
-  UCDIR_TC_I_ROW3 = 41                           /* 1: row tiles of dense 3x3 convs share one 130-pixel activation row among the three horizontal taps */
+  UCDIR_TC_I_ROW3 = 41,                          /* 1: row tiles of dense 3x3 convs share one 130-pixel activation row among the three horizontal taps */
+  UCDIR_TC_I_HALO = 43                           /* 1: halo schedule where it applies (grouped mix convs, C = 64 / 128 / 256): one 10 x 18 pixel TMA box per
+                                                  * 8 x 16 pixel tile serves all nine taps, weights stay resident in shared memory (ucdir_mix.cu) */
 };
 enum ucdir_tc_flt { UCDIR_TC_F_EPS = 0, UCDIR_TC_F_ALPHA = 1 /* 0 = 1.0 */ };
 

@@ -112,8 +112,14 @@ def test_tc_dense(cfg):
     assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
 
 
-@pytest.mark.parametrize("C,B,H,W", [(64, 2, 16, 16), (128, 1, 24, 16), (256, 3, 8, 8), (512, 3, 8, 8), (64, 1, 128, 128)])
-def test_tc_grouped_mix(C, B, H, W):
+@pytest.mark.parametrize("halo", [0, 1], ids=["streamed", "halo"])
+@pytest.mark.parametrize("C,B,H,W", [(64, 2, 16, 16), (128, 1, 24, 16), (256, 3, 8, 8), (512, 3, 8, 8), (64, 1, 128, 128),
+                                     (128, 3, 64, 64), (256, 3, 32, 32), (64, 2, 36, 20), (256, 1, 18, 18)])
+def test_tc_grouped_mix(C, B, H, W, halo):
+    """halo=1: csrc/ucdir_mix.cu (one halo box per 8 x 16 pixel tile, resident weights) where it applies (C <= 256);
+    the larger shapes make CTA unit ranges cross image and column-set boundaries."""
+    if halo and C > 256:
+        pytest.skip("halo schedule covers C = 64 / 128 / 256")
     g = torch.Generator().manual_seed(C + H)
     c = Case()
     c.add("h1", (torch.nn.functional.silu(rnd(g, B, H, W, C))).to(BF))
@@ -130,7 +136,7 @@ def test_tc_grouped_mix(C, B, H, W):
         ol = E.OpList()
         E._tc_op(ol, src0=act(t["h1"], C, H, W, t["s0"]), w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), tg=t["tg"].data_ptr(),
                  gn=1, ncls=9, groups=8, kc=kc, kb=kb, nsplit=nsplit, nt=nt, mode=1, att=t["att"].data_ptr(), attw=t["attw"].data_ptr(),
-                 attw_stride=8, res=act(t["res"], C, H, W), dst=act(t["dst"], C, H, W, t["dstats"]), ntot=8 * C, B=B)
+                 attw_stride=8, res=act(t["res"], C, H, W), dst=act(t["dst"], C, H, W, t["dstats"]), ntot=8 * C, B=B, halo=halo)
         return ol
     host, dev = run_both(c, build)
     assert_close(dev["dst"], host["dst"], "mix dst")

@@ -54,6 +54,8 @@ int launch_time_embed(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_gather_tiles(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_scatter(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry);
+bool tc_mix_halo_applies(const ucdir_op_t& op);
+int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st);
 int launch_tc_attn(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_gn_apply_bf16(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_cast(const ucdir_op_t& op, cudaStream_t st, bool dry);

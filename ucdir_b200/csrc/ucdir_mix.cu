@@ -1,0 +1,424 @@
+// Integration module (model/ucdir.py:116,135-140) on tcgen05, "halo" schedule: grouped 3x3 conv C -> 8C whose 8 adjacent
+// columns are mixed per pixel with the guidance map, for C = 64 / 128 / 256 (8 groups of CG = 8 / 16 / 32 channels).
+//
+// What bounds the streamed form of this op (tc_conv_kernel, EPI_MIX) is not the tensor pipe but L2 -> SM traffic (every
+// filter tap re-fetches the activation tile and its weight slab: 288 KB per 128 pixels) and the latency of the mix
+// epilogue.  This kernel removes both:
+//
+// * M tile = 8 x 16 output pixels.  ONE TMA box load brings the 10 x 18 pixel halo of the tile (64 channels = 128-byte
+//   swizzled rows, out-of-image pixels zero filled = the convolution padding).  The nine filter taps are nine views of
+//   that box: the operand descriptor of tap (ty, tx) starts (ty*10 + tx) rows into the box and strides 10 rows between
+//   8-row groups (SBO = 1280 bytes), so 8-row group g = tile row g.  The 128-byte swizzle is a function of the shared
+//   memory address only (measured on B200, see make_desc_shifted), so no base-offset correction is needed.
+// * weights are stationary: the CTA keeps the 144 KB weight block of a "column set" (512 columns for C = 64 / 128, 256
+//   for C = 256) resident in shared memory and walks the M tiles of its unit range; units are ordered set-major.
+//   L2 -> SM traffic per 128 pixels drops from 288 KB to the 23 KB halo box.
+// * 16 epilogue warps (four per TMEM lane quadrant); warp j of a quadrant owns the fixed 64-column stripe j of every
+//   256-column item = 8 output channels: two tcgen05.ld.x32, release the accumulator, then
+//   out[c] = Swish(sum_s aw[s] * (rstd*acc[c*8+s] + cadd[cls][c*8+s])) + res[c] with the folded-GroupNorm additive table
+//   of the current (image, set) cached in shared memory, 16-byte residual loads and stores.
+//
+// Packed weights, TB / TG tables and every other operand are those of the streamed form (engine.py:pack_tc_grouped).
+#include <cuda.h>
+#include <cstdlib>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace ucdir {
+
+struct MixParams {
+  const double* stats0;
+  const float* tb; const float* tg;
+  const __nv_bfloat16* res; const float* att; const float* attw;
+  __nv_bfloat16* dst; double* dst_stats;
+  int B, H, W, Ntot;
+  int tiles_x, tiles_y, m_tiles, n_units;
+  int resC, dstC, attwStride;
+  double gn_count; float eps;
+};
+
+constexpr int MX_TW = 8, MX_TH = 16;                       // M tile: 8 x 16 output pixels = 128 accumulator rows
+constexpr int MX_BW = MX_TW + 2, MX_BH = MX_TH + 2;        // halo box
+constexpr int MX_A_BYTES = MX_BW * MX_BH * 128;            // 23040: 180 pixel rows of 64 bf16 channels
+constexpr int MX_A_STAGE = (MX_A_BYTES + 1023) & ~1023;    // 23552
+constexpr int MX_ASTAGES = 2;
+constexpr int MX_WRES = 147456;                            // resident weight block of one column set
+constexpr int MX_EPI_WARPS = 16, MX_FIRST_EPI_WARP = 4;
+constexpr int MX_THREADS = 32 * (MX_FIRST_EPI_WARP + MX_EPI_WARPS);
+
+template <int CG>
+struct MixCfg {
+  static constexpr int C = 8 * CG;                         // channels; columns per group NG = 8C / 8 = C
+  static constexpr int NG = C;
+  static constexpr int NSPLIT = 256 / NG;                  // groups per 256-column item (4 / 2 / 1)
+  static constexpr int NSUB = NG;                          // columns per MMA
+  static constexpr int KB = CG < 16 ? 16 : CG;             // K elements per tap and group (C = 64: 8 real + 8 foreign, zero weights)
+  static constexpr int KSTEPS = KB / 16;
+  static constexpr int IPB = CG == 32 ? 1 : 2;             // items that share one halo box (= one 64-channel chunk)
+  static constexpr int SETCOLS = 256 * IPB;
+  static constexpr int BSLAB = 256 * KB * 2;               // one tap's weight slab of one item
+  static_assert(IPB * 9 * BSLAB == MX_WRES, "resident weight block");
+  static constexpr int CTAB_BYTES = 9 * SETCOLS * 4;
+  static constexpr int OFF_W = MX_ASTAGES * MX_A_STAGE;
+  static constexpr int OFF_CTAB = OFF_W + MX_WRES;
+  static constexpr int OFF_BARS = OFF_CTAB + CTAB_BYTES;
+  static constexpr int TOTAL = OFF_BARS + 128 + 1024 /* align slack */;
+  static_assert(OFF_W % 1024 == 0, "weight block alignment");
+};
+
+__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo_bytes, uint64_t layout) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+
+__device__ __forceinline__ float swish_ftz(float x) {       // x / (1 + 2^(-x log2 e)); result is rounded to bf16
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  return x * rcp_approx(1.0f + e);
+}
+
+// unit = (column set, M tile), set-major; M tile = (image, tile row, tile column), column fastest
+struct UnitCursor {
+  int set, img, ty, tx;
+  __device__ __forceinline__ void init(int u, int m_tiles, int tiles_x, int tiles_y) {
+    set = u / m_tiles;
+    const int m = u - set * m_tiles;
+    tx = m % tiles_x;
+    const int t = m / tiles_x;
+    ty = t % tiles_y;
+    img = t / tiles_y;
+  }
+  __device__ __forceinline__ void next(int tiles_x, int tiles_y, int B) {
+    if (++tx == tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; if (++img == B) { img = 0; ++set; } } }
+  }
+};
+
+template <int CG>
+__global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                 const __grid_constant__ CUtensorMap mapB, const MixParams p) {
+  using S = MixCfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  // keep the pointer arithmetic on the __shared__ array (no integer round trip) so table reads compile to LDS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* wres = smem + S::OFF_W;
+  float* ctab = reinterpret_cast<float*>(smem + S::OFF_CTAB);        // [9][SETCOLS] of the current (image, set)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BARS);
+  uint64_t* a_empty = a_full + MX_ASTAGES;
+  uint64_t* tmem_full = a_empty + MX_ASTAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* bfull = tmem_empty + 2;
+  uint64_t* bfree = bfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfree + 1);
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = (int)((long long)p.n_units * blockIdx.x / gridDim.x), u1 = (int)((long long)p.n_units * (blockIdx.x + 1) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&mapA); prefetch_tmap(&mapB);
+    for (int s = 0; s < MX_ASTAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int j = 0; j < 2; ++j) { mbar_init(&tmem_full[j], 1); mbar_init(&tmem_empty[j], MX_EPI_WARPS); }
+    mbar_init(bfull, 1); mbar_init(bfree, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // everything below touches data of earlier kernels
+
+  if (warp < MX_FIRST_EPI_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      UnitCursor cur; cur.init(u0, p.m_tiles, p.tiles_x, p.tiles_y);
+      int stage = 0; uint32_t phase = 0;
+      int cur_set = -1; uint32_t bfree_phase = 0;
+      for (int u = u0; u < u1; ++u) {
+        if (cur.set != cur_set) {
+          // new column set: (re)load its whole weight block; every unit that follows streams one halo box only
+          if (cur_set >= 0) { mbar_wait(bfree, bfree_phase); bfree_phase ^= 1; }
+          if (elect_one()) {
+            mbar_expect_tx(bfull, (uint32_t)MX_WRES);
+#pragma unroll 1
+            for (int i = 0; i < S::IPB * 9; ++i) {
+              const int item = i / 9, tap = i - item * 9;
+              tma_load_2d(&mapB, bfull, wres + i * S::BSLAB, tap * S::KB, cur.set * S::SETCOLS + item * 256);
+            }
+          }
+          __syncwarp();
+          cur_set = cur.set;
+        }
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        if (elect_one()) {
+          const int chunk = ((cur.set * S::SETCOLS) / S::NG * CG) >> 6;          // 64-channel chunk that holds the set's groups
+          mbar_expect_tx(&a_full[stage], (uint32_t)MX_A_BYTES);
+          tma_load_4d(&mapA, &a_full[stage], smem + stage * MX_A_STAGE, chunk * 64, cur.tx * MX_TW - 1, cur.ty * MX_TH - 1, cur.img);
+        }
+        __syncwarp();
+        if (++stage == MX_ASTAGES) { stage = 0; phase ^= 1; }
+        cur.next(p.tiles_x, p.tiles_y, p.B);
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(S::NSUB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint64_t b_layout = S::KB * 2 == 64 ? 4ull : 6ull;   // 64-byte / 32-byte swizzled weight rows
+      UnitCursor cur; cur.init(u0, p.m_tiles, p.tiles_x, p.tiles_y);
+      int stage = 0; uint32_t phase = 0;
+      int slot = 0; uint32_t sph = 0;
+      int cur_set = -1; uint32_t bfull_phase = 0;
+      for (int u = u0; u < u1; ++u) {
+        if (cur.set != cur_set) { mbar_wait(bfull, bfull_phase); bfull_phase ^= 1; cur_set = cur.set; }
+        const int set = cur.set;
+        cur.next(p.tiles_x, p.tiles_y, p.B);
+        const bool last_of_set = (cur.set != set) && (u + 1 < u1);
+        mbar_wait(&a_full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * MX_A_STAGE);
+#pragma unroll
+        for (int item = 0; item < S::IPB; ++item) {
+          mbar_wait(&tmem_empty[slot], sph ^ 1);           // the epilogue has drained this accumulator
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t tacc = tmem_base + (uint32_t)(slot * 256);
+            const uint32_t w_item = smem_u32(wres + item * 9 * S::BSLAB);
+            const int g0 = (set * S::SETCOLS + item * 256) / S::NG;            // first group of the item
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_tap = a_base + (uint32_t)(((tap / 3) * MX_BW + (tap % 3)) * 128);
+#pragma unroll
+              for (int sp = 0; sp < S::NSPLIT; ++sp) {
+                // the 32-byte K slice of the 128-byte pixel row that holds group g0 + sp
+                const uint32_t a_off = (uint32_t)((((g0 + sp) * CG * 2) & 127) & ~31);
+                const uint32_t b_addr = w_item + (uint32_t)(tap * S::BSLAB + sp * S::NSUB * S::KB * 2);
+                const uint64_t ad = make_desc_sbo(a_tap + a_off, MX_BW * 128, 2ull);
+                const uint64_t bd = make_desc_sbo(b_addr, 8 * S::KB * 2, b_layout);
+#pragma unroll
+                for (int k = 0; k < S::KSTEPS; ++k)
+                  umma_bf16(tacc + (uint32_t)(sp * S::NSUB), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (tap | k) != 0);
+              }
+            }
+            umma_commit(&tmem_full[slot]);                 // accumulator of this item complete
+            if (item == S::IPB - 1) {
+              umma_commit(&a_empty[stage]);                // halo box may be overwritten
+              if (last_of_set) umma_commit(bfree);         // ... and so may the weight block
+            }
+          }
+          __syncwarp();
+          if (++slot == 2) { slot = 0; sph ^= 1; }
+        }
+        if (++stage == MX_ASTAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int q = warp & 3;                                // TMEM lane quadrant this warp may read
+    const int stripe = (warp - MX_FIRST_EPI_WARP) >> 2;    // 64-column stripe of every item
+    const int r = q * 32 + lane;                           // accumulator row = pixel of the tile
+    const int yy = r >> 3, xx = r & 7;
+    const int et = threadIdx.x - 32 * MX_FIRST_EPI_WARP;
+    UnitCursor cur; cur.init(u0, p.m_tiles, p.tiles_x, p.tiles_y);
+    float s1 = 0.f, s2 = 0.f;                              // GroupNorm statistics of what this thread stored, current image
+    int stat_img = -1;
+    int tab_img = -1, tab_set = -1;
+    float rstd = 1.f;
+    float w8[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) w8[s] = 0.f;
+    int slot = 0; uint32_t sph = 0;
+    for (int u = u0; u < u1; ++u) {
+      const int img = cur.img, set = cur.set;
+      if (img != stat_img) {
+        if (p.dst_stats && stat_img >= 0) {
+          const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
+          if (lane == 0) { atomicAdd(p.dst_stats + 2 * stat_img, d1); atomicAdd(p.dst_stats + 2 * stat_img + 1, d2); }
+        }
+        stat_img = img; s1 = 0.f; s2 = 0.f;
+      }
+      if (img != tab_img || set != tab_set) {
+        // all epilogue warps walk the same units, so they all rebuild the additive table at the same unit
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * MX_EPI_WARPS) : "memory");       // everyone is done with the old table
+        const GnScalars sc = gn_scalars(p.stats0, nullptr, img, p.gn_count, p.eps);
+        const float mri = sc.mean * sc.rstd;
+        rstd = sc.rstd;
+        for (int i = et; i < 9 * S::SETCOLS / 4; i += 32 * MX_EPI_WARPS) {
+          const int cls = i / (S::SETCOLS / 4), j4 = i - cls * (S::SETCOLS / 4);
+          const size_t g = (size_t)cls * p.Ntot + (size_t)set * S::SETCOLS + (size_t)j4 * 4;
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.tb + g));
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.tg + g));
+          reinterpret_cast<float4*>(ctab)[i] = make_float4(fmaf(-mri, t.x, b.x), fmaf(-mri, t.y, b.y), fmaf(-mri, t.z, b.z), fmaf(-mri, t.w, b.w));
+        }
+        if (img != tab_img) {
+          const float* wp = p.attw + (size_t)img * p.attwStride;
+#pragma unroll
+          for (int s = 0; s < 8; ++s) w8[s] = __ldg(wp + s);
+        }
+        tab_img = img; tab_set = set;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * MX_EPI_WARPS) : "memory");
+      }
+      const int y = cur.ty * MX_TH + yy, x = cur.tx * MX_TW + xx;
+      const bool valid = y < p.H && x < p.W;
+      const size_t pix = valid ? ((size_t)img * p.H + y) * p.W + x : 0;
+      const int cls = (y == 0 ? 0 : (y == p.H - 1 ? 2 : 1)) * 3 + (x == 0 ? 0 : (x == p.W - 1 ? 2 : 1));
+      float aw[8];
+      {
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.att + pix * 8));
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.att + pix * 8 + 4));
+        aw[0] = t0.x * w8[0]; aw[1] = t0.y * w8[1]; aw[2] = t0.z * w8[2]; aw[3] = t0.w * w8[3];
+        aw[4] = t1.x * w8[4]; aw[5] = t1.y * w8[5]; aw[6] = t1.z * w8[6]; aw[7] = t1.w * w8[7];
+      }
+      const float2 rs2 = make_float2(rstd, rstd);
+#pragma unroll 1
+      for (int item = 0; item < S::IPB; ++item) {
+        const int lcol = item * 256 + stripe * 64;          // first column of the stripe within the set
+        const int ch0 = (set * S::SETCOLS + lcol) >> 3;     // its first output channel
+        uint4 rres = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) rres = __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.resC + ch0));
+        mbar_wait(&tmem_full[slot], sph);
+        tc_fence_after();
+        uint32_t rv[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + stripe * 64);
+        tmem_ld32(taddr, rv);
+        tmem_ld32(taddr + 32, rv + 32);
+        tmem_ld_wait();
+        // the accumulator values are in registers: hand the slot back to the MMA issuer before doing the math
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+        if (++slot == 2) { slot = 0; sph ^= 1; }
+        if (!valid) continue;
+        const float4* ct = reinterpret_cast<const float4*>(ctab + cls * S::SETCOLS + lcol);
+        const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(&rres);
+        __align__(16) __nv_bfloat16 o[8];
+        float t1s = 0.f, t2s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 ca = ct[2 * c], cb = ct[2 * c + 1];
+          const float2 v0 = __ffma2_rn(make_float2(__uint_as_float(rv[c * 8 + 0]), __uint_as_float(rv[c * 8 + 1])), rs2, make_float2(ca.x, ca.y));
+          const float2 v1 = __ffma2_rn(make_float2(__uint_as_float(rv[c * 8 + 2]), __uint_as_float(rv[c * 8 + 3])), rs2, make_float2(ca.z, ca.w));
+          const float2 v2 = __ffma2_rn(make_float2(__uint_as_float(rv[c * 8 + 4]), __uint_as_float(rv[c * 8 + 5])), rs2, make_float2(cb.x, cb.y));
+          const float2 v3 = __ffma2_rn(make_float2(__uint_as_float(rv[c * 8 + 6]), __uint_as_float(rv[c * 8 + 7])), rs2, make_float2(cb.z, cb.w));
+          // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
+          float2 h2 = __fmul2_rn(v0, make_float2(aw[0], aw[1]));
+          h2 = __ffma2_rn(v1, make_float2(aw[2], aw[3]), h2);
+          float2 g2 = __fmul2_rn(v2, make_float2(aw[4], aw[5]));
+          g2 = __ffma2_rn(v3, make_float2(aw[6], aw[7]), g2);
+          const float h = (h2.x + g2.x) + (h2.y + g2.y);
+          const float t = swish_ftz(h) + __bfloat162float(rr[c]);
+          o[c] = __float2bfloat16(t);
+          const float tr = __bfloat162float(o[c]);
+          t1s += tr; t2s += tr * tr;
+        }
+        *reinterpret_cast<uint4*>(p.dst + pix * p.dstC + ch0) = *reinterpret_cast<const uint4*>(o);
+        s1 += t1s; s2 += t2s;
+      }
+      cur.next(p.tiles_x, p.tiles_y, p.B);
+    }
+    if (p.dst_stats && stat_img >= 0) {
+      const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
+      if (lane == 0) { atomicAdd(p.dst_stats + 2 * stat_img, d1); atomicAdd(p.dst_stats + 2 * stat_img + 1, d2); }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static const bool g_mix_pdl = []() { const char* e = getenv("UCDIR_PDL"); return !(e && e[0] == '0'); }();
+
+template <int CG>
+static int launch_mix_inst(const CUtensorMap& a, const CUtensorMap& b, const MixParams& p, int grid, cudaStream_t st) {
+  using S = MixCfg<CG>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(mix_halo_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+      set_error("tc_mix_halo: cannot opt in to %d bytes of shared memory: %s", S::TOTAL, cudaGetErrorString(cudaGetLastError())); return -3; }
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(MX_THREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = g_mix_pdl ? 1 : 0;
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, mix_halo_kernel<CG>, a, b, p) != cudaSuccess) {
+    set_error("tc_mix_halo: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
+  return 0;
+}
+
+// true when the op (already validated by launch_tc_conv as a grouped mix conv) fits this kernel
+bool tc_mix_halo_applies(const ucdir_op_t& op) {
+  const int C = op.i[UCDIR_TC_I_C0], H = op.i[UCDIR_TC_I_H], W = op.i[UCDIR_TC_I_W];
+  const int KB = op.i[UCDIR_TC_I_KB] ? op.i[UCDIR_TC_I_KB] : op.i[UCDIR_TC_I_KC];
+  return op.i[UCDIR_TC_I_HALO] == 1 && op.i[UCDIR_TC_I_MODE] == 1 && op.i[UCDIR_TC_I_GROUPS] == 8 && (C == 64 || C == 128 || C == 256) &&
+         op.i[UCDIR_TC_I_C1] == 0 && op.i[UCDIR_TC_I_NTOT] == 8 * C && op.i[UCDIR_TC_I_GN] == 1 && op.i[UCDIR_TC_I_NCLS] == 9 &&
+         op.i[UCDIR_TC_I_NTY] == 3 && op.i[UCDIR_TC_I_NTX] == 3 && op.i[UCDIR_TC_I_OY0] == -1 && op.i[UCDIR_TC_I_OX0] == -1 &&
+         op.i[UCDIR_TC_I_STRIDE] == 1 && KB == (C / 8 < 16 ? 16 : C / 8) && H >= 2 && W >= 2 && op.i[UCDIR_TC_I_SRC_H] == H &&
+         op.i[UCDIR_TC_I_SRC_W] == W && !op.i[UCDIR_TC_I_DST_F32] && !op.i[UCDIR_TC_I_DST_UP] && !op.i[UCDIR_TC_I_W_BATCHED] &&
+         !op.p[UCDIR_TC_P_DST2] && op.i[UCDIR_TC_I_DST_COFF] == 0 && (op.i[UCDIR_TC_I_SRC_CSTRIDE] == 0 || op.i[UCDIR_TC_I_SRC_CSTRIDE] == C) &&
+         op.i[UCDIR_TC_I_DST_C] % 8 == 0 && op.i[UCDIR_TC_I_RES_C] % 8 == 0 && op.p[UCDIR_TC_P_TG] && op.p[UCDIR_TC_P_STATS0];
+}
+
+int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st) {
+  MixParams p;
+  p.stats0 = (const double*)op.p[UCDIR_TC_P_STATS0];
+  p.tb = (const float*)op.p[UCDIR_TC_P_TB]; p.tg = (const float*)op.p[UCDIR_TC_P_TG];
+  p.res = (const __nv_bfloat16*)op.p[UCDIR_TC_P_RES]; p.att = (const float*)op.p[UCDIR_TC_P_ATT]; p.attw = (const float*)op.p[UCDIR_TC_P_ATTW];
+  p.dst = (__nv_bfloat16*)op.p[UCDIR_TC_P_DST]; p.dst_stats = (double*)op.p[UCDIR_TC_P_DST_STATS];
+  p.B = op.i[UCDIR_TC_I_B]; p.H = op.i[UCDIR_TC_I_H]; p.W = op.i[UCDIR_TC_I_W]; p.Ntot = op.i[UCDIR_TC_I_NTOT];
+  const int C = op.i[UCDIR_TC_I_C0], CG = C / 8, KB = CG < 16 ? 16 : CG;
+  p.resC = op.i[UCDIR_TC_I_RES_C]; p.dstC = op.i[UCDIR_TC_I_DST_C]; p.attwStride = op.i[UCDIR_TC_I_ATTW_STRIDE];
+  p.eps = op.f[UCDIR_TC_F_EPS];
+  p.gn_count = (double)C * p.H * p.W;
+  p.tiles_x = (p.W + MX_TW - 1) / MX_TW; p.tiles_y = (p.H + MX_TH - 1) / MX_TH;
+  const long long mt = (long long)p.tiles_x * p.tiles_y * p.B;
+  const int setcols = CG == 32 ? 256 : 512;
+  const long long units = mt * (p.Ntot / setcols);
+  if (units > 0x7fffffffLL) { set_error("tc_mix_halo: too many units"); return -2; }
+  p.m_tiles = (int)mt; p.n_units = (int)units;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("tc_mix_halo: cuTensorMapEncodeTiled unavailable"); return -3; }
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * p.W, (cuuint64_t)C * 2 * p.W * p.H};
+    cuuint32_t box[4] = {64, MX_BW, MX_BH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.p[UCDIR_TC_P_SRC0]), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tc_mix_halo: cuTensorMapEncodeTiled(activation C=%d W=%d H=%d B=%d) failed: %d", C, p.W, p.H, p.B, (int)r); return -3; }
+  }
+  {
+    const int Ktot = 9 * KB;
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p.Ntot};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KB, 256};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.p[UCDIR_TC_P_W]), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tc_mix_halo: cuTensorMapEncodeTiled(weights K=%d N=%d) failed: %d", Ktot, p.Ntot, (int)r); return -3; }
+  }
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  const int grid = units < n_sm ? (int)units : n_sm;       // persistent: one CTA per SM
+  int rc;
+  if (CG == 8) rc = launch_mix_inst<8>(ma, mb, p, grid, st);
+  else if (CG == 16) rc = launch_mix_inst<16>(ma, mb, p, grid, st);
+  else rc = launch_mix_inst<32>(ma, mb, p, grid, st);
+  if (rc) return rc;
+  ++g_launches;
+  return 0;
+}
+
+}  // namespace ucdir

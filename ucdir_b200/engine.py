@@ -396,7 +396,7 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
            att: int = 0, attw: int = 0, attw_stride: int = 0, dst_f32: int = 0, ncol_valid: int = 0, dst_up: int = 0,
            dst_py: int = 0, dst_px: int = 0, eps: float = 1e-5, kb: int = 0, nsplit: int = 1, src_cstride: int = 0,
            w_batched: int = 0, w_rowstride: int = 0, w_batchstride: int = 0, alpha: float = 0.0, dst2: int = 0, t_col0: int = 0,
-           t_ld: int = 0, w_rows: int = 0, row3: Optional[int] = None):
+           t_ld: int = 0, w_rows: int = 0, row3: Optional[int] = None, halo: Optional[int] = None):
     H, W = (dst.H // 2, dst.W // 2) if dst_up else (dst.H, dst.W)
     p = {"UCDIR_TC_P_SRC0": src0.ptr, "UCDIR_TC_P_W": w, "UCDIR_TC_P_TB": tb, "UCDIR_TC_P_DST": dst.ptr}
     if src1 is not None: p["UCDIR_TC_P_SRC1"] = src1.ptr
@@ -419,7 +419,7 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
          "UCDIR_TC_I_SRC_CSTRIDE": src_cstride, "UCDIR_TC_I_W_BATCHED": w_batched, "UCDIR_TC_I_W_ROWSTRIDE": w_rowstride,
          "UCDIR_TC_I_W_BATCHSTRIDE_LO": w_batchstride & 0x7FFFFFFF, "UCDIR_TC_I_W_BATCHSTRIDE_HI": w_batchstride >> 31,
          "UCDIR_TC_I_T_COL0": t_col0, "UCDIR_TC_I_T_LD": t_ld, "UCDIR_TC_I_W_ROWS": w_rows,
-         "UCDIR_TC_I_ROW3": _TC_ROW3 if row3 is None else row3}
+         "UCDIR_TC_I_ROW3": _TC_ROW3 if row3 is None else row3, "UCDIR_TC_I_HALO": _TC_HALO if halo is None else halo}
     if dst2: p["UCDIR_TC_P_DST2"] = dst2
     ol.add("UCDIR_OP_TC_CONV", p, i, {"UCDIR_TC_F_EPS": eps, "UCDIR_TC_F_ALPHA": alpha})
 
@@ -427,6 +427,11 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
 _TC_ROW3 = 0 if os.environ.get("UCDIR_TC_ROW3", "1") == "0" else 1
 """Request the shared-activation-row schedule for dense 3x3 convs on 128-pixel-wide rows (the library applies it only
 where its preconditions hold).  On unless UCDIR_TC_ROW3=0."""
+
+
+_TC_HALO = 0 if os.environ.get("UCDIR_TC_HALO", "1") == "0" else 1
+"""Request the halo / weight-stationary schedule (csrc/ucdir_mix.cu) for the integration-module convs with C = 64 / 128 /
+256 (the library applies it only where its preconditions hold).  On unless UCDIR_TC_HALO=0."""
 
 
 def tc_mix_tiling(cout: int):
