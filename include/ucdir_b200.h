@@ -261,6 +261,10 @@ int ucdir_abi_version(void);
 int ucdir_op_sizeof(void);
 const char* ucdir_last_error(void);
 /* Number of kernel launches issued by this process through ucdir_run_ops since load. */
+/* Which kernel a UCDIR_OP_TC_CONV record is routed to (no device needed): 0 = streamed (tc_conv_kernel), 1 = halo schedule of
+ * the integration-module convs (ucdir_mix.cu), 2 = halo / super-tile schedule of the Cout = 64 / 128 3x3 convs (ucdir_dhalo.cu);
+ * negative = not a TC_CONV op. */
+int ucdir_tc_schedule(const ucdir_op_t* op);
 long long ucdir_launch_count(void);
 /* Device capability probe: returns 0 iff the current device is sm_100 (B200). */
 int ucdir_device_ok(void);

@@ -41,8 +41,12 @@ def assert_close(got, want, what, rtol=2e-2, atol=2e-2):
     got, want = got.float(), want.float()
     err = (got - want).abs()
     scale = want.abs().max().item() + 1e-6
-    bad = (err > atol * scale + rtol * want.abs()).float().mean().item()
-    assert bad == 0.0, f"{what}: max err {err.max().item():.4e} (scale {scale:.3e}), {bad:.3%} elements out of tolerance"
+    mask = err > atol * scale + rtol * want.abs()
+    bad = mask.float().mean().item()
+    where = mask.nonzero()[:12].tolist() if bad else []
+    assert bad == 0.0, (f"{what}: max err {err.max().item():.4e} (scale {scale:.3e}), {bad:.3%} elements out of tolerance; "
+                        f"first bad indices {where}, got {[round(got[tuple(i)].item(), 4) for i in where[:6]]} "
+                        f"want {[round(want[tuple(i)].item(), 4) for i in where[:6]]}")
 
 
 def act(t, C, H, W, stats=None):
@@ -59,7 +63,7 @@ def stats_of(x_bf16):
     return torch.stack([v.sum(1), (v * v).sum(1)], dim=1).contiguous()
 
 
-def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1, row3=0):
+def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1, row3=0, halo=0):
     g = torch.Generator().manual_seed(seed)
     sH, sW = H * stride, W * stride
     c = Case()
@@ -90,7 +94,7 @@ def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1, row3=0)
                  w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), tg=t["tg"].data_ptr() if "tg" in t else 0, gn=1 if gn else 0,
                  ncls=9 if (gn and ks == 3) else 1, nty=ks, ntx=ks, oy0=-(ks // 2), ox0=-(ks // 2), stride=stride, act=act_,
                  res=act(t["res"], Cout, H, W) if res else None, dst=act(t["dst"], Cout, H, W, t["dstats"]), ntot=Cout, B=B, nt=nt,
-                 row3=row3)
+                 row3=row3, halo=halo)
         return ol
     return c, build
 
@@ -107,6 +111,24 @@ def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1, row3=0)
 ], ids=lambda c: "C%d+%d_%d_k%d_s%d_%dx%d" % (c["C0"], c["C1"], c["Cout"], c["ks"], c.get("stride", 1), c["H"], c["W"]))
 def test_tc_dense(cfg):
     c, build = dense_case(**cfg)
+    host, dev = run_both(c, build)
+    assert_close(dev["dst"], host["dst"], "dst")
+    assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(seed=21, B=2, H=16, W=16, C0=64, C1=0, Cout=64),
+    dict(seed=22, B=1, H=128, W=128, C0=64, C1=0, Cout=64),
+    dict(seed=23, B=2, H=40, W=72, C0=128, C1=64, Cout=64),       # partial super tiles in both directions, concat input
+    dict(seed=24, B=3, H=64, W=64, C0=256, C1=128, Cout=128),
+    dict(seed=25, B=2, H=24, W=20, C0=128, C1=0, Cout=128),
+    dict(seed=26, B=5, H=48, W=96, C0=64, C1=0, Cout=64, act_=0),   # 90 items: most CTAs get one, images change inside a CTA's range
+], ids=lambda c: "C%d+%d_%d_%dx%dx%d" % (c["C0"], c["C1"], c["Cout"], c["B"], c["H"], c["W"]))
+def test_tc_dense_halo(cfg):
+    """csrc/ucdir_dhalo.cu: super tiles of 256/Cout 8x16-pixel tiles, one halo box per 64-channel chunk serves all nine taps."""
+    cfg = dict(dict(ks=3, gn=True, act_=1, res=False, halo=1), **cfg)
+    c, build = dense_case(**cfg)
+    assert _lib.tc_schedule(build(c.on("cpu")).array()[0]) == 2
     host, dev = run_both(c, build)
     assert_close(dev["dst"], host["dst"], "dst")
     assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
@@ -138,6 +160,7 @@ def test_tc_grouped_mix(C, B, H, W, halo):
                  gn=1, ncls=9, groups=8, kc=kc, kb=kb, nsplit=nsplit, nt=nt, mode=1, att=t["att"].data_ptr(), attw=t["attw"].data_ptr(),
                  attw_stride=8, res=act(t["res"], C, H, W), dst=act(t["dst"], C, H, W, t["dstats"]), ntot=8 * C, B=B, halo=halo)
         return ol
+    assert _lib.tc_schedule(build(c.on("cpu")).array()[0]) == halo
     host, dev = run_both(c, build)
     assert_close(dev["dst"], host["dst"], "mix dst")
     assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)

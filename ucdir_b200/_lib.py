@@ -38,7 +38,7 @@ class Op(ctypes.Structure):
 
 EXPORTS = ["ucdir_run_ops", "ucdir_check_ops", "ucdir_abi_version", "ucdir_op_sizeof", "ucdir_last_error",
            "ucdir_launch_count", "ucdir_device_ok", "ucdir_profile_begin", "ucdir_profile_end", "ucdir_graph_capture",
-           "ucdir_graph_launch", "ucdir_graph_destroy"]
+           "ucdir_graph_launch", "ucdir_graph_destroy", "ucdir_tc_schedule"]
 
 _lib = None
 
@@ -65,6 +65,8 @@ def load(require_device=True):
         lib.ucdir_last_error.restype = ctypes.c_char_p
         lib.ucdir_launch_count.restype = ctypes.c_longlong
         lib.ucdir_device_ok.restype = ctypes.c_int
+        lib.ucdir_tc_schedule.argtypes = [ctypes.POINTER(Op)]
+        lib.ucdir_tc_schedule.restype = ctypes.c_int
         lib.ucdir_graph_capture.argtypes = [ctypes.POINTER(Op), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
         lib.ucdir_graph_capture.restype = ctypes.c_int
         lib.ucdir_graph_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
@@ -115,6 +117,11 @@ def check_ops(ops, n):
     rc = load(require_device=False).ucdir_check_ops(ops, n)
     if rc != 0:
         raise UcdirLibraryError("ucdir_check_ops failed (%d): %s" % (rc, last_error()))
+
+
+def tc_schedule(op) -> int:
+    """0 = streamed tc_conv_kernel, 1 = halo mix kernel, 2 = halo dense kernel (see ucdir_tc_schedule in the header)."""
+    return int(load(require_device=False).ucdir_tc_schedule(ctypes.byref(op)))
 
 
 def launch_count():

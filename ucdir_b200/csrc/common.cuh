@@ -56,6 +56,11 @@ int launch_scatter(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry);
 bool tc_mix_halo_applies(const ucdir_op_t& op);
 int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st);
+bool tc_dense_halo_applies(const ucdir_op_t& op);
+int launch_tc_dense_halo(const ucdir_op_t& op, cudaStream_t st);
+// setmaxnreg moves registers between warpgroups through a per-CTA pool that holds only what the CTA itself released:
+// what `low_threads` threads release going from the launch allocation down to `low` must cover what `high_threads` need.
+int check_reg_pool(const void* kernel, const char* name, int low_threads, int low, int high_threads, int high);
 int launch_tc_attn(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_gn_apply_bf16(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_cast(const ucdir_op_t& op, cudaStream_t st, bool dry);

@@ -31,11 +31,21 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok;
 }
-// Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (surfacing as a CUDA error) after ~2 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) { printf("ucdir tc_conv: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+    if ((++spins & 1023u) == 0) {
+      uint64_t t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > 2000000000ull) {
+        printf("ucdir tc: mbarrier timeout (block %d thread %d, barrier @%u parity %u)\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
+    }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

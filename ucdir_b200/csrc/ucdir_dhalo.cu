@@ -1,0 +1,382 @@
+// Dense 3x3 stride-1 convolution with few output channels (Cout = 64 / 128: conv1 of the ResnetBlockDY3h blocks at the two
+// finest levels, model/ucdir.py:109-111,124-126) on tcgen05, "halo" schedule.
+//
+// The streamed form (tc_conv_kernel) is bound by L2 -> SM traffic on these layers: with only 64 / 128 accumulator columns
+// per pixel tile, every filter tap re-fetches a 16 KB activation slab and an 8 / 16 KB weight slab for ~130 / 260 cycles
+// of tensor work.  Here a work item is a SUPER TILE of MT = 256 / Cout adjacent 8 x 16 pixel tiles:
+//
+// * one TMA box per 64-channel chunk brings the (8*MT + 2) x 18 pixel halo of the super tile; the nine taps of the MT
+//   tiles are views of that box (operand descriptor start = (ty*BW + tx + 8*mt) rows in, 8-row groups BW rows apart --
+//   see ucdir_mix.cu for the addressing argument), so activations cross L2 -> SM ~1.2x instead of 9x (3x with ROW3);
+// * every weight slab (one tap of one chunk) is used by the MT tiles of the item before it is released, so weights cross
+//   MT times less often;  MT x Cout = 256 accumulator columns per item, two items in TMEM (MMA of item i+1 overlaps
+//   the epilogue of item i);
+// * separate producer warps for activations and weights (the activation box of chunk j+1 is in flight while the taps
+//   of chunk j stream), 16 epilogue warps (warp j of a quadrant drains the 64-column stripe j of every item).
+//
+// torch.cat((x, skip)) inputs are two tensor maps visited by the same chunk loop; GroupNorm(1,C) of the input is folded
+// exactly as in tc_conv_kernel (gamma in the weights, 9 border classes of additive terms); Swish epilogue; statistics
+// of the stored tensor for the next GroupNorm.
+#include <cuda.h>
+#include <cstdlib>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace ucdir {
+
+struct DhParams {
+  const double* stats0; const double* stats1;
+  const float* tb; const float* tg;
+  __nv_bfloat16* dst; double* dst_stats;
+  int B, H, W;
+  int nchunk, c0_chunks;
+  int tiles_x, tiles_y, n_items;
+  int act, dstC, dstCoff;
+  double gn_count; float eps;
+};
+
+constexpr int DH_EPI_WARPS = 16, DH_FIRST_EPI_WARP = 4;
+constexpr int DH_THREADS = 32 * (DH_FIRST_EPI_WARP + DH_EPI_WARPS);
+constexpr int DH_REGS_LOW = 40, DH_REGS_HIGH = 104;      // see MX_REGS_LOW / MX_REGS_HIGH in ucdir_mix.cu
+
+template <int NT>
+struct DhCfg {
+  static constexpr int MT = 256 / NT;                     // 8 x 16 pixel tiles per item
+  static constexpr int SW = 8 * MT;                       // super tile width
+  static constexpr int BW = SW + 2, BH = 18;              // halo box
+  static constexpr int A_BYTES = BW * BH * 128;
+  static constexpr int A_STAGE = (A_BYTES + 1023) & ~1023;
+  static constexpr int ASTG = NT == 64 ? 2 : 3;
+  static constexpr int BSLAB = NT * 128;                  // one tap of one 64-channel chunk
+  static constexpr int BSTG = NT == 64 ? 6 : 5;
+  static constexpr int OFF_B = ASTG * A_STAGE;
+  static constexpr int OFF_CTAB = OFF_B + BSTG * BSLAB;
+  static constexpr int OFF_BARS = OFF_CTAB + 9 * NT * 4;
+  static constexpr int TOTAL = OFF_BARS + 256 + 1024 /* align slack */;
+  static_assert(TOTAL <= 227 * 1024, "shared memory");
+};
+
+__device__ __forceinline__ uint64_t dh_desc(uint32_t saddr, uint32_t sbo_bytes) {      // 128-byte swizzled K-major operand
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ float dh_swish(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  return x * rcp_approx(1.0f + e);
+}
+
+struct SuperCursor {            // item = (image, super-tile row, super-tile column), column fastest
+  int img, ty, tx;
+  __device__ __forceinline__ void init(int it, int tiles_x, int tiles_y) {
+    tx = it % tiles_x;
+    const int t = it / tiles_x;
+    ty = t % tiles_y;
+    img = t / tiles_y;
+  }
+  __device__ __forceinline__ void next(int tiles_x, int tiles_y) {
+    if (++tx == tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++img; } }
+  }
+};
+
+template <int NT>
+__global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_constant__ CUtensorMap mapA0,
+                                                                   const __grid_constant__ CUtensorMap mapA1,
+                                                                   const __grid_constant__ CUtensorMap mapB, const DhParams p) {
+  using S = DhCfg<NT>;
+  constexpr int MT = S::MT, ASTG = S::ASTG, BSTG = S::BSTG;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* bring = smem + S::OFF_B;
+  float* ctab = reinterpret_cast<float*>(smem + S::OFF_CTAB);          // [9][NT] additive terms of the current image
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BARS);
+  uint64_t* a_empty = a_full + ASTG;
+  uint64_t* b_full = a_empty + ASTG;
+  uint64_t* b_empty = b_full + BSTG;
+  uint64_t* tmem_full = b_empty + BSTG;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int it0 = (int)((long long)p.n_items * blockIdx.x / gridDim.x), it1 = (int)((long long)p.n_items * (blockIdx.x + 1) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
+    if (p.c0_chunks < p.nchunk) prefetch_tmap(&mapA1);
+    for (int s = 0; s < ASTG; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < BSTG; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int j = 0; j < 2; ++j) { mbar_init(&tmem_full[j], 1); mbar_init(&tmem_empty[j], DH_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // everything below touches data of earlier kernels
+
+  if (warp < DH_FIRST_EPI_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DH_REGS_LOW));
+    if (warp == 0) {
+      // ===================== activation producer: one halo box per (item, 64-channel chunk) =====================
+      SuperCursor cur; cur.init(it0, p.tiles_x, p.tiles_y);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = it0; it < it1; ++it) {
+        const int x0 = cur.tx * S::SW - 1, y0 = cur.ty * 16 - 1;
+        for (int j = 0; j < p.nchunk; ++j) {
+          mbar_wait(&a_empty[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&a_full[stage], (uint32_t)S::A_BYTES);
+            if (j < p.c0_chunks) tma_load_4d(&mapA0, &a_full[stage], smem + stage * S::A_STAGE, j * 64, x0, y0, cur.img);
+            else tma_load_4d(&mapA1, &a_full[stage], smem + stage * S::A_STAGE, (j - p.c0_chunks) * 64, x0, y0, cur.img);
+          }
+          __syncwarp();
+          if (++stage == ASTG) { stage = 0; phase ^= 1; }
+        }
+        cur.next(p.tiles_x, p.tiles_y);
+      }
+    } else if (warp == 2) {
+      // ===================== weight producer: one slab per (item, chunk, tap) =====================
+      int stage = 0; uint32_t phase = 0;
+      for (int it = it0; it < it1; ++it) {
+        for (int j = 0; j < p.nchunk; ++j) {
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[stage], (uint32_t)S::BSLAB);
+              tma_load_2d(&mapB, &b_full[stage], bring + stage * S::BSLAB, (tap * p.nchunk + j) * 64, 0);
+            }
+            __syncwarp();
+            if (++stage == BSTG) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int as = 0; uint32_t aph = 0;
+      int bs = 0; uint32_t bph = 0;
+      int slot = 0; uint32_t sph = 0;
+      for (int it = it0; it < it1; ++it) {
+        mbar_wait(&tmem_empty[slot], sph ^ 1);             // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(slot * 256);
+        for (int j = 0; j < p.nchunk; ++j) {
+          mbar_wait(&a_full[as], aph);
+          const uint32_t a_base = smem_u32(smem + as * S::A_STAGE);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            if (elect_one()) {
+              const int ty = tap / 3, tx = tap - ty * 3;
+              const uint32_t a_tap = a_base + (uint32_t)((ty * S::BW + tx) * 128);
+              const uint64_t bd = dh_desc(smem_u32(bring + bs * S::BSLAB), 1024);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint64_t ad = dh_desc(a_tap + (uint32_t)(mt * 8 * 128), S::BW * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tacc + (uint32_t)(mt * NT), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (j | tap | k) != 0);
+              }
+              umma_commit(&b_empty[bs]);                   // weight slab may be overwritten
+              if (tap == 8) {
+                umma_commit(&a_empty[as]);                 // ... and so may the halo box
+                if (j == p.nchunk - 1) umma_commit(&tmem_full[slot]);
+              }
+            }
+            __syncwarp();
+            if (++bs == BSTG) { bs = 0; bph ^= 1; }
+          }
+          if (++as == ASTG) { as = 0; aph ^= 1; }
+        }
+        if (++slot == 2) { slot = 0; sph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DH_REGS_HIGH));
+    const int q = warp & 3;                                // TMEM lane quadrant this warp may read
+    const int stripe = (warp - DH_FIRST_EPI_WARP) >> 2;    // 64-column stripe of the item's 256 accumulator columns
+    const int mt = (stripe * 64) / NT, ncol0 = (stripe * 64) % NT;
+    const int r = q * 32 + lane;
+    const int yy = r >> 3, xx = mt * 8 + (r & 7);
+    const int et = threadIdx.x - 32 * DH_FIRST_EPI_WARP;
+    SuperCursor cur; cur.init(it0, p.tiles_x, p.tiles_y);
+    float s1 = 0.f, s2 = 0.f;
+    int stat_img = -1;
+    float rstd = 1.f;
+    int slot = 0; uint32_t sph = 0;
+    for (int it = it0; it < it1; ++it) {
+      const int img = cur.img;
+      if (img != stat_img) {
+        if (p.dst_stats && stat_img >= 0) {
+          const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
+          if (lane == 0) { atomicAdd(p.dst_stats + 2 * stat_img, d1); atomicAdd(p.dst_stats + 2 * stat_img + 1, d2); }
+        }
+        stat_img = img; s1 = 0.f; s2 = 0.f;
+        // all epilogue warps walk the same items, so they all rebuild the additive table at the same item
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * DH_EPI_WARPS) : "memory");
+        const GnScalars sc = gn_scalars(p.stats0, p.stats1, img, p.gn_count, p.eps);
+        const float mri = sc.mean * sc.rstd;
+        rstd = sc.rstd;
+        for (int i = et; i < 9 * NT; i += 32 * DH_EPI_WARPS) ctab[i] = fmaf(-mri, __ldg(p.tg + i), __ldg(p.tb + i));
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * DH_EPI_WARPS) : "memory");
+      }
+      const int y = cur.ty * 16 + yy, x = cur.tx * S::SW + xx;
+      const bool valid = y < p.H && x < p.W;
+      const size_t pix = valid ? ((size_t)img * p.H + y) * p.W + x : 0;
+      const int cls = (y == 0 ? 0 : (y == p.H - 1 ? 2 : 1)) * 3 + (x == 0 ? 0 : (x == p.W - 1 ? 2 : 1));
+      mbar_wait(&tmem_full[slot], sph);
+      tc_fence_after();
+      uint32_t rv[64];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + stripe * 64);
+      tmem_ld32(taddr, rv);
+      tmem_ld32(taddr + 32, rv + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+      if (++slot == 2) { slot = 0; sph ^= 1; }
+      if (valid) {
+        const float4* ct = reinterpret_cast<const float4*>(ctab + cls * NT + ncol0);
+        __nv_bfloat16* d = p.dst + pix * p.dstC + p.dstCoff + ncol0;
+        const float2 rs2 = make_float2(rstd, rstd);
+        float t1s = 0.f, t2s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) {
+          const float4 ca = ct[c / 4], cb = ct[c / 4 + 1];
+          float2 v[4];
+          v[0] = __ffma2_rn(make_float2(__uint_as_float(rv[c + 0]), __uint_as_float(rv[c + 1])), rs2, make_float2(ca.x, ca.y));
+          v[1] = __ffma2_rn(make_float2(__uint_as_float(rv[c + 2]), __uint_as_float(rv[c + 3])), rs2, make_float2(ca.z, ca.w));
+          v[2] = __ffma2_rn(make_float2(__uint_as_float(rv[c + 4]), __uint_as_float(rv[c + 5])), rs2, make_float2(cb.x, cb.y));
+          v[3] = __ffma2_rn(make_float2(__uint_as_float(rv[c + 6]), __uint_as_float(rv[c + 7])), rs2, make_float2(cb.z, cb.w));
+          __align__(16) __nv_bfloat162 o2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (p.act == 1) { v[e].x = dh_swish(v[e].x); v[e].y = dh_swish(v[e].y); }
+            o2[e] = __floats2bfloat162_rn(v[e].x, v[e].y);
+            const float2 f = __bfloat1622float2(o2[e]);
+            t1s += f.x + f.y; t2s += f.x * f.x + f.y * f.y;
+          }
+          *reinterpret_cast<uint4*>(d + c) = *reinterpret_cast<const uint4*>(o2);
+        }
+        s1 += t1s; s2 += t2s;
+      }
+      cur.next(p.tiles_x, p.tiles_y);
+    }
+    if (p.dst_stats && stat_img >= 0) {
+      const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
+      if (lane == 0) { atomicAdd(p.dst_stats + 2 * stat_img, d1); atomicAdd(p.dst_stats + 2 * stat_img + 1, d2); }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static const bool g_dh_pdl = []() { const char* e = getenv("UCDIR_PDL"); return !(e && e[0] == '0'); }();
+
+template <int NT>
+static int launch_dh_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const DhParams& p, int grid, cudaStream_t st) {
+  using S = DhCfg<NT>;
+  static bool attr = false;
+  if (!attr) {
+    if (int rc = check_reg_pool((const void*)dense_halo_kernel<NT>, "tc_dense_halo", 32 * DH_FIRST_EPI_WARP, DH_REGS_LOW, 32 * DH_EPI_WARPS, DH_REGS_HIGH)) return rc;
+    if (cudaFuncSetAttribute(dense_halo_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+      set_error("tc_dense_halo: cannot opt in to %d bytes of shared memory: %s", S::TOTAL, cudaGetErrorString(cudaGetLastError())); return -3; }
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(DH_THREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = g_dh_pdl ? 1 : 0;
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, dense_halo_kernel<NT>, a0, a1, b, p) != cudaSuccess) {
+    set_error("tc_dense_halo: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
+  return 0;
+}
+
+// true when the op (already validated by launch_tc_conv as a dense conv) fits this kernel
+bool tc_dense_halo_applies(const ucdir_op_t& op) {
+  const int C0 = op.i[UCDIR_TC_I_C0], C1 = op.i[UCDIR_TC_I_C1], H = op.i[UCDIR_TC_I_H], W = op.i[UCDIR_TC_I_W];
+  const int NT = op.i[UCDIR_TC_I_NT];
+  const int KB = op.i[UCDIR_TC_I_KB] ? op.i[UCDIR_TC_I_KB] : op.i[UCDIR_TC_I_KC];
+  return op.i[UCDIR_TC_I_HALO] == 1 && op.i[UCDIR_TC_I_MODE] == 0 && op.i[UCDIR_TC_I_GROUPS] == 1 && (NT == 64 || NT == 128) &&
+         op.i[UCDIR_TC_I_NTOT] == NT && op.i[UCDIR_TC_I_KC] == 64 && KB == 64 && C0 % 64 == 0 && C1 % 64 == 0 &&
+         op.i[UCDIR_TC_I_GN] == 1 && op.i[UCDIR_TC_I_NCLS] == 9 && op.i[UCDIR_TC_I_NTY] == 3 && op.i[UCDIR_TC_I_NTX] == 3 &&
+         op.i[UCDIR_TC_I_OY0] == -1 && op.i[UCDIR_TC_I_OX0] == -1 && op.i[UCDIR_TC_I_STRIDE] == 1 && H >= 2 && W >= 2 &&
+         op.i[UCDIR_TC_I_SRC_H] == H && op.i[UCDIR_TC_I_SRC_W] == W && !op.p[UCDIR_TC_P_RES] && !op.i[UCDIR_TC_I_DST_F32] &&
+         !op.i[UCDIR_TC_I_DST_UP] && !op.i[UCDIR_TC_I_W_BATCHED] && !op.p[UCDIR_TC_P_DST2] &&
+         (op.i[UCDIR_TC_I_SRC_CSTRIDE] == 0 || op.i[UCDIR_TC_I_SRC_CSTRIDE] == C0) && op.i[UCDIR_TC_I_DST_C] % 8 == 0 &&
+         op.i[UCDIR_TC_I_DST_COFF] % 8 == 0 && (op.i[UCDIR_TC_I_NCOL_VALID] == 0 || op.i[UCDIR_TC_I_NCOL_VALID] == NT) &&
+         op.p[UCDIR_TC_P_TG] && op.p[UCDIR_TC_P_STATS0] && (C1 == 0 || (op.p[UCDIR_TC_P_SRC1] && op.p[UCDIR_TC_P_STATS1]));
+}
+
+static int dh_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int B, int bw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("tc_dense_halo: cuTensorMapEncodeTiled unavailable"); return -3; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, 18, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("tc_dense_halo: cuTensorMapEncodeTiled(activation C=%d W=%d H=%d B=%d box %d) failed: %d", C, W, H, B, bw, (int)r); return -3; }
+  return 0;
+}
+
+int launch_tc_dense_halo(const ucdir_op_t& op, cudaStream_t st) {
+  DhParams p;
+  const int C0 = op.i[UCDIR_TC_I_C0], C1 = op.i[UCDIR_TC_I_C1], NT = op.i[UCDIR_TC_I_NT];
+  p.stats0 = (const double*)op.p[UCDIR_TC_P_STATS0]; p.stats1 = C1 ? (const double*)op.p[UCDIR_TC_P_STATS1] : nullptr;
+  p.tb = (const float*)op.p[UCDIR_TC_P_TB]; p.tg = (const float*)op.p[UCDIR_TC_P_TG];
+  p.dst = (__nv_bfloat16*)op.p[UCDIR_TC_P_DST]; p.dst_stats = (double*)op.p[UCDIR_TC_P_DST_STATS];
+  p.B = op.i[UCDIR_TC_I_B]; p.H = op.i[UCDIR_TC_I_H]; p.W = op.i[UCDIR_TC_I_W];
+  p.c0_chunks = C0 / 64; p.nchunk = (C0 + C1) / 64;
+  p.act = op.i[UCDIR_TC_I_ACT]; p.dstC = op.i[UCDIR_TC_I_DST_C]; p.dstCoff = op.i[UCDIR_TC_I_DST_COFF];
+  p.eps = op.f[UCDIR_TC_F_EPS];
+  p.gn_count = (double)(C0 + C1) * p.H * p.W;
+  const int sw = 8 * (256 / NT);
+  p.tiles_x = (p.W + sw - 1) / sw; p.tiles_y = (p.H + 15) / 16;
+  const long long items = (long long)p.tiles_x * p.tiles_y * p.B;
+  if (items > 0x7fffffffLL) { set_error("tc_dense_halo: too many items"); return -2; }
+  p.n_items = (int)items;
+  CUtensorMap a0, a1, mb;
+  int rc = dh_act_map(&a0, op.p[UCDIR_TC_P_SRC0], C0, p.W, p.H, p.B, sw + 2);
+  if (rc) return rc;
+  if (C1 > 0) { rc = dh_act_map(&a1, op.p[UCDIR_TC_P_SRC1], C1, p.W, p.H, p.B, sw + 2); if (rc) return rc; }
+  else a1 = a0;
+  {
+    EncodeTiledFn enc = get_encode();
+    const int Ktot = 9 * (C0 + C1);
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)NT};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)NT};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.p[UCDIR_TC_P_W]), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tc_dense_halo: cuTensorMapEncodeTiled(weights K=%d N=%d) failed: %d", Ktot, NT, (int)r); return -3; }
+  }
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  const int grid = items < n_sm ? (int)items : n_sm;       // persistent: one CTA per SM
+  rc = NT == 64 ? launch_dh_inst<64>(a0, a1, mb, p, grid, st) : launch_dh_inst<128>(a0, a1, mb, p, grid, st);
+  if (rc) return rc;
+  ++g_launches;
+  return 0;
+}
+
+}  // namespace ucdir

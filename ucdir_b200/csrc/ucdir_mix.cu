@@ -45,6 +45,9 @@ constexpr int MX_ASTAGES = 2;
 constexpr int MX_WRES = 147456;                            // resident weight block of one column set
 constexpr int MX_EPI_WARPS = 16, MX_FIRST_EPI_WARP = 4;
 constexpr int MX_THREADS = 32 * (MX_FIRST_EPI_WARP + MX_EPI_WARPS);
+// 640 threads launch with 96 registers each; warpgroup 0 shrinks to 40 (releasing 56 x 128) so the four epilogue
+// warpgroups can grow to 104 (8 x 512) -- the pool only holds what the CTA released (checked on the host before launch)
+constexpr int MX_REGS_LOW = 40, MX_REGS_HIGH = 104;
 
 template <int CG>
 struct MixCfg {
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
   asm volatile("griddepcontrol.wait;" ::: "memory");     // everything below touches data of earlier kernels
 
   if (warp < MX_FIRST_EPI_WARP) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MX_REGS_LOW));
     if (warp == 0) {
       // ===================== TMA producer =====================
       UnitCursor cur; cur.init(u0, p.m_tiles, p.tiles_x, p.tiles_y);
@@ -186,9 +189,10 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
             const uint32_t tacc = tmem_base + (uint32_t)(slot * 256);
             const uint32_t w_item = smem_u32(wres + item * 9 * S::BSLAB);
             const int g0 = (set * S::SETCOLS + item * 256) / S::NG;            // first group of the item
-#pragma unroll
+#pragma unroll 1                                            // descriptors are computed per tap: warpgroup 0 runs on 40 registers
             for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t a_tap = a_base + (uint32_t)(((tap / 3) * MX_BW + (tap % 3)) * 128);
+              const int ty = tap / 3, tx = tap - ty * 3;
+              const uint32_t a_tap = a_base + (uint32_t)((ty * MX_BW + tx) * 128);
 #pragma unroll
               for (int sp = 0; sp < S::NSPLIT; ++sp) {
                 // the 32-byte K slice of the 128-byte pixel row that holds group g0 + sp
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
     }
   } else {
     // ===================== epilogue =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MX_REGS_HIGH));
     const int q = warp & 3;                                // TMEM lane quadrant this warp may read
     const int stripe = (warp - MX_FIRST_EPI_WARP) >> 2;    // 64-column stripe of every item
     const int r = q * 32 + lane;                           // accumulator row = pixel of the tile
@@ -341,6 +345,7 @@ static int launch_mix_inst(const CUtensorMap& a, const CUtensorMap& b, const Mix
   using S = MixCfg<CG>;
   static bool attr = false;
   if (!attr) {
+    if (int rc = check_reg_pool((const void*)mix_halo_kernel<CG>, "tc_mix_halo", 32 * MX_FIRST_EPI_WARP, MX_REGS_LOW, 32 * MX_EPI_WARPS, MX_REGS_HIGH)) return rc;
     if (cudaFuncSetAttribute(mix_halo_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
       set_error("tc_mix_halo: cannot opt in to %d bytes of shared memory: %s", S::TOTAL, cudaGetErrorString(cudaGetLastError())); return -3; }
     attr = true;

@@ -622,6 +622,18 @@ static void choose_tile(int W, int H, int B, int stride, int* bw, int* bh, int* 
   *bw = bbw; *bh = bbh; *bn = bbn;
 }
 
+int check_reg_pool(const void* kernel, const char* name, int low_threads, int low, int high_threads, int high) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) { set_error("%s: cudaFuncGetAttributes failed: %s", name, cudaGetErrorString(cudaGetLastError())); return -3; }
+  const int r = fa.numRegs;
+  if (r < low || low_threads * (r - low) < high_threads * (high - r)) {
+    set_error("%s: compiled with %d registers per thread; %d threads releasing down to %d cannot cover %d threads growing to %d (setmaxnreg would spin forever)",
+              name, r, low_threads, low, high_threads, high);
+    return -3;
+  }
+  return 0;
+}
+
 static const bool g_pdl = []() { const char* e = getenv("UCDIR_PDL"); return !(e && e[0] == '0'); }();
 
 template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT, int SPS>
@@ -717,6 +729,7 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   p.m_tiles = (int)mt; p.tiles_n = tiles_n;
   if (dry) return 0;
   if (tc_mix_halo_applies(op)) return launch_tc_mix_halo(op, st);      // halo / weight-stationary form of the mix convs (ucdir_mix.cu)
+  if (tc_dense_halo_applies(op)) return launch_tc_dense_halo(op, st);  // halo / super-tile form of the Cout = 64 / 128 3x3 convs (ucdir_dhalo.cu)
   // ROW3: row tiles (128 px x 1 row) of a dense 3x3 stride-1 conv load one 130-pixel activation row per filter row and
   // issue the three horizontal taps from shifted descriptors of that slab (3x less activation traffic from L2)
   const bool row3 = op.i[UCDIR_TC_I_ROW3] == 1 && p.nty == 3 && p.ntx == 3 && p.stride == 1 && p.groups == 1 && KC == 64 && KB == 64 &&
