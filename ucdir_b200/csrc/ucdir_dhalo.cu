@@ -60,10 +60,14 @@ __device__ __forceinline__ uint64_t dh_desc(uint32_t saddr, uint32_t sbo_bytes) 
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-__device__ __forceinline__ float dh_swish(float x) {
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-  return x * rcp_approx(1.0f + e);
+// Swish from ONE special-function op: x*sigmoid(x) = h + h*tanh(h) with h = x/2 (the epilogue scales by 1/2 for free).
+// tanh.approx has a relative error of 2^-11, i.e. |error| <= |x| * 2.5e-4 -- below the bf16 rounding of the stored result
+// except in the negative tail, where it stays under 1.5e-3 absolute.  The ex2 + rcp form costs two MUFU ops per element
+// and the MUFU unit issues 16 per SM per clock: at 64 / 128 output channels that was a third of this kernel's epilogue.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 struct SuperCursor {            // item = (image, super-tile row, super-tile column), column fastest
@@ -79,7 +83,7 @@ struct SuperCursor {            // item = (image, super-tile row, super-tile col
   }
 };
 
-template <int NT>
+template <int NT, int ACT>
 __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                    const __grid_constant__ CUtensorMap mapA1,
                                                                    const __grid_constant__ CUtensorMap mapB, const DhParams p) {
@@ -224,50 +228,60 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
         asm volatile("bar.sync 1, %0;" ::"n"(32 * DH_EPI_WARPS) : "memory");
         const GnScalars sc = gn_scalars(p.stats0, p.stats1, img, p.gn_count, p.eps);
         const float mri = sc.mean * sc.rstd;
-        rstd = sc.rstd;
-        for (int i = et; i < 9 * NT; i += 32 * DH_EPI_WARPS) ctab[i] = fmaf(-mri, __ldg(p.tg + i), __ldg(p.tb + i));
+        const float half = ACT ? 0.5f : 1.0f;             // Swish works on x / 2 (tanh form)
+        rstd = half * sc.rstd;
+        for (int i = et; i < 9 * NT; i += 32 * DH_EPI_WARPS) ctab[i] = half * fmaf(-mri, __ldg(p.tg + i), __ldg(p.tb + i));
         asm volatile("bar.sync 1, %0;" ::"n"(32 * DH_EPI_WARPS) : "memory");
       }
       const int y = cur.ty * 16 + yy, x = cur.tx * S::SW + xx;
       const bool valid = y < p.H && x < p.W;
       const size_t pix = valid ? ((size_t)img * p.H + y) * p.W + x : 0;
       const int cls = (y == 0 ? 0 : (y == p.H - 1 ? 2 : 1)) * 3 + (x == 0 ? 0 : (x == p.W - 1 ? 2 : 1));
+      const float4* ct = reinterpret_cast<const float4*>(ctab + cls * NT + ncol0);
+      __nv_bfloat16* d = p.dst + pix * p.dstC + p.dstCoff + ncol0;
+      const float2 rs2 = make_float2(rstd, rstd);          // (ACT: rstd / 2, and the table holds half the additive terms)
+      float2 st1 = make_float2(0.f, 0.f), st2 = make_float2(0.f, 0.f);
       mbar_wait(&tmem_full[slot], sph);
       tc_fence_after();
-      uint32_t rv[64];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + stripe * 64);
-      tmem_ld32(taddr, rv);
-      tmem_ld32(taddr + 32, rv + 32);
+      // 16 columns per step; the TMEM load of step k+1 is in flight during the math of step k
+      uint32_t rbuf[2][16];
+      tmem_ld16(taddr, rbuf[0]);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[slot]);
-      if (++slot == 2) { slot = 0; sph ^= 1; }
-      if (valid) {
-        const float4* ct = reinterpret_cast<const float4*>(ctab + cls * NT + ncol0);
-        __nv_bfloat16* d = p.dst + pix * p.dstC + p.dstCoff + ncol0;
-        const float2 rs2 = make_float2(rstd, rstd);
-        float t1s = 0.f, t2s = 0.f;
 #pragma unroll
-        for (int c = 0; c < 64; c += 8) {
-          const float4 ca = ct[c / 4], cb = ct[c / 4 + 1];
-          float2 v[4];
-          v[0] = __ffma2_rn(make_float2(__uint_as_float(rv[c + 0]), __uint_as_float(rv[c + 1])), rs2, make_float2(ca.x, ca.y));
-          v[1] = __ffma2_rn(make_float2(__uint_as_float(rv[c + 2]), __uint_as_float(rv[c + 3])), rs2, make_float2(ca.z, ca.w));
-          v[2] = __ffma2_rn(make_float2(__uint_as_float(rv[c + 4]), __uint_as_float(rv[c + 5])), rs2, make_float2(cb.x, cb.y));
-          v[3] = __ffma2_rn(make_float2(__uint_as_float(rv[c + 6]), __uint_as_float(rv[c + 7])), rs2, make_float2(cb.z, cb.w));
-          __align__(16) __nv_bfloat162 o2[4];
+      for (int k = 0; k < 4; ++k) {
+        if (k < 3) tmem_ld16(taddr + 16 * (k + 1), rbuf[(k + 1) & 1]);
+        if (valid) {
+          const uint32_t* rv = rbuf[k & 1];
+          __align__(16) __nv_bfloat162 o2[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (p.act == 1) { v[e].x = dh_swish(v[e].x); v[e].y = dh_swish(v[e].y); }
-            o2[e] = __floats2bfloat162_rn(v[e].x, v[e].y);
-            const float2 f = __bfloat1622float2(o2[e]);
-            t1s += f.x + f.y; t2s += f.x * f.x + f.y * f.y;
+          for (int j = 0; j < 4; ++j) {
+            const float4 c4 = ct[4 * k + j];
+            float2 va = __ffma2_rn(make_float2(__uint_as_float(rv[4 * j + 0]), __uint_as_float(rv[4 * j + 1])), rs2, make_float2(c4.x, c4.y));
+            float2 vb = __ffma2_rn(make_float2(__uint_as_float(rv[4 * j + 2]), __uint_as_float(rv[4 * j + 3])), rs2, make_float2(c4.z, c4.w));
+            if (ACT) {
+              va = __ffma2_rn(va, make_float2(tanh_approx(va.x), tanh_approx(va.y)), va);
+              vb = __ffma2_rn(vb, make_float2(tanh_approx(vb.x), tanh_approx(vb.y)), vb);
+            }
+            o2[2 * j] = __floats2bfloat162_rn(va.x, va.y);
+            o2[2 * j + 1] = __floats2bfloat162_rn(vb.x, vb.y);
+            // statistics from the fp32 values (their bf16 rounding is zero-mean noise of relative size 2^-9)
+            st1 = __fadd2_rn(st1, __fadd2_rn(va, vb));
+            st2 = __ffma2_rn(va, va, __ffma2_rn(vb, vb, st2));
           }
-          *reinterpret_cast<uint4*>(d + c) = *reinterpret_cast<const uint4*>(o2);
+          *reinterpret_cast<uint4*>(d + 16 * k) = *reinterpret_cast<const uint4*>(o2);
+          *reinterpret_cast<uint4*>(d + 16 * k + 8) = *reinterpret_cast<const uint4*>(o2 + 4);
         }
-        s1 += t1s; s2 += t2s;
+        if (k < 3) tmem_ld_wait();
+        if (k == 2) {
+          // every accumulator value of this stripe is in registers: hand the slot back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+        }
       }
+      if (++slot == 2) { slot = 0; sph ^= 1; }
+      s1 += st1.x + st1.y; s2 += st2.x + st2.y;
       cur.next(p.tiles_x, p.tiles_y);
     }
     if (p.dst_stats && stat_img >= 0) {
@@ -288,13 +302,13 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 static const bool g_dh_pdl = []() { const char* e = getenv("UCDIR_PDL"); return !(e && e[0] == '0'); }();
 
-template <int NT>
+template <int NT, int ACT>
 static int launch_dh_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const DhParams& p, int grid, cudaStream_t st) {
   using S = DhCfg<NT>;
   static bool attr = false;
   if (!attr) {
-    if (int rc = check_reg_pool((const void*)dense_halo_kernel<NT>, "tc_dense_halo", 32 * DH_FIRST_EPI_WARP, DH_REGS_LOW, 32 * DH_EPI_WARPS, DH_REGS_HIGH)) return rc;
-    if (cudaFuncSetAttribute(dense_halo_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+    if (int rc = check_reg_pool((const void*)dense_halo_kernel<NT, ACT>, "tc_dense_halo", 32 * DH_FIRST_EPI_WARP, DH_REGS_LOW, 32 * DH_EPI_WARPS, DH_REGS_HIGH)) return rc;
+    if (cudaFuncSetAttribute(dense_halo_kernel<NT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
       set_error("tc_dense_halo: cannot opt in to %d bytes of shared memory: %s", S::TOTAL, cudaGetErrorString(cudaGetLastError())); return -3; }
     attr = true;
   }
@@ -304,7 +318,7 @@ static int launch_dh_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CU
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = g_dh_pdl ? 1 : 0;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, dense_halo_kernel<NT>, a0, a1, b, p) != cudaSuccess) {
+  if (cudaLaunchKernelEx(&cfg, dense_halo_kernel<NT, ACT>, a0, a1, b, p) != cudaSuccess) {
     set_error("tc_dense_halo: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
   return 0;
 }
@@ -373,7 +387,8 @@ int launch_tc_dense_halo(const ucdir_op_t& op, cudaStream_t st) {
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
   const int grid = items < n_sm ? (int)items : n_sm;       // persistent: one CTA per SM
-  rc = NT == 64 ? launch_dh_inst<64>(a0, a1, mb, p, grid, st) : launch_dh_inst<128>(a0, a1, mb, p, grid, st);
+  if (NT == 64) rc = p.act == 1 ? launch_dh_inst<64, 1>(a0, a1, mb, p, grid, st) : launch_dh_inst<64, 0>(a0, a1, mb, p, grid, st);
+  else rc = p.act == 1 ? launch_dh_inst<128, 1>(a0, a1, mb, p, grid, st) : launch_dh_inst<128, 0>(a0, a1, mb, p, grid, st);
   if (rc) return rc;
   ++g_launches;
   return 0;

@@ -73,10 +73,12 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo_b
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
-__device__ __forceinline__ float swish_ftz(float x) {       // x / (1 + 2^(-x log2 e)); result is rounded to bf16
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-  return x * rcp_approx(1.0f + e);
+// Swish from one special-function op: x*sigmoid(x) = h + h*tanh(h), h = x/2 (see ucdir_dhalo.cu:tanh_approx for the error
+// bound); the 1/2 is folded into the per-step attw factors, so the mixed sum arrives as h.
+__device__ __forceinline__ float swish_half(float h) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(h));
+  return fmaf(h, y, h);
 }
 
 // unit = (column set, M tile), set-major; M tile = (image, tile row, tile column), column fastest
@@ -234,6 +236,24 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
 #pragma unroll
     for (int s = 0; s < 8; ++s) w8[s] = 0.f;
     int slot = 0; uint32_t sph = 0;
+    // Software pipeline: the guidance-map row of unit u+1 and the residual row of the next item are requested while the
+    // current item is processed (they stream from HBM; requested at the point of use they stalled every item for a full
+    // DRAM round trip -- 30% of all warp samples in the first ncu capture of this kernel).
+    bool n_valid = false; uint32_t n_pix = 0; int n_cls = 0;
+    float4 n_att0 = make_float4(0.f, 0.f, 0.f, 0.f), n_att1 = n_att0;
+    auto fetch_unit = [&]() {
+      const int y = cur.ty * MX_TH + yy, x = cur.tx * MX_TW + xx;
+      n_valid = y < p.H && x < p.W;
+      n_pix = n_valid ? (uint32_t)((cur.img * p.H + y) * p.W + x) : 0u;
+      n_cls = (y == 0 ? 0 : (y == p.H - 1 ? 2 : 1)) * 3 + (x == 0 ? 0 : (x == p.W - 1 ? 2 : 1));
+      n_att0 = __ldg(reinterpret_cast<const float4*>(p.att + (size_t)n_pix * 8));
+      n_att1 = __ldg(reinterpret_cast<const float4*>(p.att + (size_t)n_pix * 8 + 4));
+    };
+    auto load_res = [&](uint32_t pix, int set, int item) {
+      return __ldg(reinterpret_cast<const uint4*>(p.res + (size_t)pix * p.resC + ((set * S::SETCOLS + item * 256 + stripe * 64) >> 3)));
+    };
+    fetch_unit();
+    uint4 res_nxt = load_res(n_pix, cur.set, 0);
     for (int u = u0; u < u1; ++u) {
       const int img = cur.img, set = cur.set;
       if (img != stat_img) {
@@ -259,68 +279,81 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
         if (img != tab_img) {
           const float* wp = p.attw + (size_t)img * p.attwStride;
 #pragma unroll
-          for (int s = 0; s < 8; ++s) w8[s] = __ldg(wp + s);
+          for (int s = 0; s < 8; ++s) w8[s] = 0.5f * __ldg(wp + s);     // 1/2: the Swish below works on x / 2
         }
         tab_img = img; tab_set = set;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * MX_EPI_WARPS) : "memory");
       }
-      const int y = cur.ty * MX_TH + yy, x = cur.tx * MX_TW + xx;
-      const bool valid = y < p.H && x < p.W;
-      const size_t pix = valid ? ((size_t)img * p.H + y) * p.W + x : 0;
-      const int cls = (y == 0 ? 0 : (y == p.H - 1 ? 2 : 1)) * 3 + (x == 0 ? 0 : (x == p.W - 1 ? 2 : 1));
-      float aw[8];
-      {
-        const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.att + pix * 8));
-        const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.att + pix * 8 + 4));
-        aw[0] = t0.x * w8[0]; aw[1] = t0.y * w8[1]; aw[2] = t0.z * w8[2]; aw[3] = t0.w * w8[3];
-        aw[4] = t1.x * w8[4]; aw[5] = t1.y * w8[5]; aw[6] = t1.z * w8[6]; aw[7] = t1.w * w8[7];
-      }
+      // operands of this unit were requested one unit ago
+      const bool valid = n_valid;
+      const uint32_t pix = n_pix;
+      const int cls = n_cls;
+      float2 aw2[4];
+      aw2[0] = make_float2(n_att0.x * w8[0], n_att0.y * w8[1]); aw2[1] = make_float2(n_att0.z * w8[2], n_att0.w * w8[3]);
+      aw2[2] = make_float2(n_att1.x * w8[4], n_att1.y * w8[5]); aw2[3] = make_float2(n_att1.z * w8[6], n_att1.w * w8[7]);
+      cur.next(p.tiles_x, p.tiles_y, p.B);
+      const bool more = u + 1 < u1;
+      if (more) fetch_unit();                                // ... and those of the next unit are requested now
       const float2 rs2 = make_float2(rstd, rstd);
-#pragma unroll 1
+#pragma unroll
       for (int item = 0; item < S::IPB; ++item) {
         const int lcol = item * 256 + stripe * 64;          // first column of the stripe within the set
         const int ch0 = (set * S::SETCOLS + lcol) >> 3;     // its first output channel
-        uint4 rres = make_uint4(0u, 0u, 0u, 0u);
-        if (valid) rres = __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.resC + ch0));
+        const uint4 res_cur = res_nxt;
+        if (item + 1 < S::IPB) res_nxt = load_res(pix, set, item + 1);
+        else if (more) res_nxt = load_res(n_pix, cur.set, 0);
         mbar_wait(&tmem_full[slot], sph);
         tc_fence_after();
-        uint32_t rv[64];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + stripe * 64);
-        tmem_ld32(taddr, rv);
-        tmem_ld32(taddr + 32, rv + 32);
-        tmem_ld_wait();
-        // the accumulator values are in registers: hand the slot back to the MMA issuer before doing the math
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[slot]);
-        if (++slot == 2) { slot = 0; sph ^= 1; }
-        if (!valid) continue;
         const float4* ct = reinterpret_cast<const float4*>(ctab + cls * S::SETCOLS + lcol);
-        const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(&rres);
-        __align__(16) __nv_bfloat16 o[8];
-        float t1s = 0.f, t2s = 0.f;
+        const __nv_bfloat162* rr = reinterpret_cast<const __nv_bfloat162*>(&res_cur);
+        __align__(16) __nv_bfloat162 o[4];
+        float2 st1 = make_float2(0.f, 0.f), st2 = make_float2(0.f, 0.f);
+        // 16 columns (two output channels) per step; the TMEM load of step k+1 is in flight during the math of step k
+        uint32_t rbuf[2][16];
+        tmem_ld16(taddr, rbuf[0]);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 ca = ct[2 * c], cb = ct[2 * c + 1];
-          const float2 v0 = __ffma2_rn(make_float2(__uint_as_float(rv[c * 8 + 0]), __uint_as_float(rv[c * 8 + 1])), rs2, make_float2(ca.x, ca.y));
-          const float2 v1 = __ffma2_rn(make_float2(__uint_as_float(rv[c * 8 + 2]), __uint_as_float(rv[c * 8 + 3])), rs2, make_float2(ca.z, ca.w));
-          const float2 v2 = __ffma2_rn(make_float2(__uint_as_float(rv[c * 8 + 4]), __uint_as_float(rv[c * 8 + 5])), rs2, make_float2(cb.x, cb.y));
-          const float2 v3 = __ffma2_rn(make_float2(__uint_as_float(rv[c * 8 + 6]), __uint_as_float(rv[c * 8 + 7])), rs2, make_float2(cb.z, cb.w));
-          // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
-          float2 h2 = __fmul2_rn(v0, make_float2(aw[0], aw[1]));
-          h2 = __ffma2_rn(v1, make_float2(aw[2], aw[3]), h2);
-          float2 g2 = __fmul2_rn(v2, make_float2(aw[4], aw[5]));
-          g2 = __ffma2_rn(v3, make_float2(aw[6], aw[7]), g2);
-          const float h = (h2.x + g2.x) + (h2.y + g2.y);
-          const float t = swish_ftz(h) + __bfloat162float(rr[c]);
-          o[c] = __float2bfloat16(t);
-          const float tr = __bfloat162float(o[c]);
-          t1s += tr; t2s += tr * tr;
+        for (int k = 0; k < 4; ++k) {
+          if (k < 3) tmem_ld16(taddr + 16 * (k + 1), rbuf[(k + 1) & 1]);
+          if (valid) {
+            const uint32_t* rv = rbuf[k & 1];
+            float hh[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float4 ca = ct[4 * k + 2 * e], cb = ct[4 * k + 2 * e + 1];
+              const float2 v0 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 0]), __uint_as_float(rv[e * 8 + 1])), rs2, make_float2(ca.x, ca.y));
+              const float2 v1 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 2]), __uint_as_float(rv[e * 8 + 3])), rs2, make_float2(ca.z, ca.w));
+              const float2 v2 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 4]), __uint_as_float(rv[e * 8 + 5])), rs2, make_float2(cb.x, cb.y));
+              const float2 v3 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 6]), __uint_as_float(rv[e * 8 + 7])), rs2, make_float2(cb.z, cb.w));
+              // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
+              float2 h2 = __fmul2_rn(v0, aw2[0]);
+              h2 = __ffma2_rn(v1, aw2[1], h2);
+              float2 g2 = __fmul2_rn(v2, aw2[2]);
+              g2 = __ffma2_rn(v3, aw2[3], g2);
+              hh[e] = (h2.x + g2.x) + (h2.y + g2.y);
+            }
+            const float2 rf = __bfloat1622float2(rr[k]);
+            const float2 tv = make_float2(swish_half(hh[0]) + rf.x, swish_half(hh[1]) + rf.y);
+            o[k] = __floats2bfloat162_rn(tv.x, tv.y);
+            // statistics from the fp32 values (their bf16 rounding is zero-mean noise of relative size 2^-9)
+            st1 = __fadd2_rn(st1, tv);
+            st2 = __ffma2_rn(tv, tv, st2);
+          }
+          if (k < 3) tmem_ld_wait();
+          if (k == 2) {
+            // every accumulator value of this stripe is in registers: hand the slot back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+          }
         }
-        *reinterpret_cast<uint4*>(p.dst + pix * p.dstC + ch0) = *reinterpret_cast<const uint4*>(o);
-        s1 += t1s; s2 += t2s;
+        if (++slot == 2) { slot = 0; sph ^= 1; }
+        if (valid) {
+          *reinterpret_cast<uint4*>(p.dst + (size_t)pix * p.dstC + ch0) = *reinterpret_cast<const uint4*>(o);
+          s1 += st1.x + st1.y; s2 += st2.x + st2.y;
+        }
       }
-      cur.next(p.tiles_x, p.tiles_y, p.B);
     }
     if (p.dst_stats && stat_img >= 0) {
       const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
@@ -389,7 +422,7 @@ int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st) {
   const long long mt = (long long)p.tiles_x * p.tiles_y * p.B;
   const int setcols = CG == 32 ? 256 : 512;
   const long long units = mt * (p.Ntot / setcols);
-  if (units > 0x7fffffffLL) { set_error("tc_mix_halo: too many units"); return -2; }
+  if (units > 0x7fffffffLL || (long long)p.B * p.H * p.W > 0x7fffffffLL) { set_error("tc_mix_halo: too many units / pixels"); return -2; }
   p.m_tiles = (int)mt; p.n_units = (int)units;
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("tc_mix_halo: cuTensorMapEncodeTiled unavailable"); return -3; }
