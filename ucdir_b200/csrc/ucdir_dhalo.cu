@@ -56,10 +56,6 @@ struct DhCfg {
   static_assert(TOTAL <= 227 * 1024, "shared memory");
 };
 
-__device__ __forceinline__ uint64_t dh_desc(uint32_t saddr, uint32_t sbo_bytes) {      // 128-byte swizzled K-major operand
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
 // Swish from ONE special-function op: x*sigmoid(x) = h + h*tanh(h) with h = x/2 (the epilogue scales by 1/2 for free).
 // tanh.approx has a relative error of 2^-11, i.e. |error| <= |x| * 2.5e-4 -- below the bf16 rounding of the stored result
 // except in the negative tail, where it stays under 1.5e-3 absolute.  The ex2 + rcp form costs two MUFU ops per element
@@ -179,14 +175,15 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
             tc_fence_after();
             if (elect_one()) {
               const int ty = tap / 3, tx = tap - ty * 3;
-              const uint32_t a_tap = a_base + (uint32_t)((ty * S::BW + tx) * 128);
-              const uint64_t bd = dh_desc(smem_u32(bring + bs * S::BSLAB), 1024);
+              constexpr uint32_t a_hi = desc_hi(S::BW * 128, 2u), b_hi = desc_hi(1024, 2u);
+              const uint32_t a_lo = desc_lo(a_base) + (uint32_t)(((ty * S::BW + tx) * 128) >> 4);
+              const uint32_t b_lo = desc_lo(smem_u32(bring + bs * S::BSLAB));
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
-                const uint64_t ad = dh_desc(a_tap + (uint32_t)(mt * 8 * 128), S::BW * 128);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16(tacc + (uint32_t)(mt * NT), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (j | tap | k) != 0);
+                  umma_bf16_lohi(tacc + (uint32_t)(mt * NT), a_lo + (uint32_t)((mt * 8 * 128) >> 4) + (uint32_t)(k * 2), a_hi,
+                                 b_lo + (uint32_t)(k * 2), b_hi, idesc, (j | tap | k) != 0);
               }
               umma_commit(&b_empty[bs]);                   // weight slab may be overwritten
               if (tap == 8) {

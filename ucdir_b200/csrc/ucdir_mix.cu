@@ -53,8 +53,11 @@ template <int CG>
 struct MixCfg {
   static constexpr int C = 8 * CG;                         // channels; columns per group NG = 8C / 8 = C
   static constexpr int NG = C;
-  static constexpr int NSPLIT = 256 / NG;                  // groups per 256-column item (4 / 2 / 1)
-  static constexpr int NSUB = NG;                          // columns per MMA
+  // MMAs per tap and 256-column item.  C = 64: groups 2j and 2j+1 live in the same 32-byte K slice of the pixel row (their
+  // weight rows carry zeros for the other group's 8 channels), so ONE N = 128 MMA serves both -- the A slice is read from
+  // shared memory once instead of twice (at N = 64 the operand reads, 6 KB per 32 tensor cycles, exceed the 128 B/clk port).
+  static constexpr int NSPLIT = CG == 8 ? 2 : 256 / NG;    // 2 / 2 / 1
+  static constexpr int NSUB = 256 / NSPLIT;                // columns per MMA
   static constexpr int KB = CG < 16 ? 16 : CG;             // K elements per tap and group (C = 64: 8 real + 8 foreign, zero weights)
   static constexpr int KSTEPS = KB / 16;
   static constexpr int IPB = CG == 32 ? 1 : 2;             // items that share one halo box (= one 64-channel chunk)
@@ -68,10 +71,6 @@ struct MixCfg {
   static constexpr int TOTAL = OFF_BARS + 128 + 1024 /* align slack */;
   static_assert(OFF_W % 1024 == 0, "weight block alignment");
 };
-
-__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo_bytes, uint64_t layout) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
-}
 
 // Swish from one special-function op: x*sigmoid(x) = h + h*tanh(h), h = x/2 (see ucdir_dhalo.cu:tanh_approx for the error
 // bound); the 1/2 is folded into the per-step attw factors, so the mixed sum arrives as h.
@@ -170,7 +169,6 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(S::NSUB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      constexpr uint64_t b_layout = S::KB * 2 == 64 ? 4ull : 6ull;   // 64-byte / 32-byte swizzled weight rows
       UnitCursor cur; cur.init(u0, p.m_tiles, p.tiles_x, p.tiles_y);
       int stage = 0; uint32_t phase = 0;
       int slot = 0; uint32_t sph = 0;
@@ -189,23 +187,26 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
           tc_fence_after();
           if (elect_one()) {
             const uint32_t tacc = tmem_base + (uint32_t)(slot * 256);
-            const uint32_t w_item = smem_u32(wres + item * 9 * S::BSLAB);
             const int g0 = (set * S::SETCOLS + item * 256) / S::NG;            // first group of the item
-#pragma unroll 1                                            // descriptors are computed per tap: warpgroup 0 runs on 40 registers
+            constexpr int GPS = S::NSUB / S::NG;                                // groups per MMA
+            constexpr uint32_t a_hi = desc_hi(MX_BW * 128, 2u), b_hi = desc_hi(8 * S::KB * 2, S::KB * 2 == 64 ? 4u : 6u);
+            // the 32-byte K slice of the 128-byte pixel row that holds the first group of split sp, as a descriptor offset
+            uint32_t a_lo0[S::NSPLIT];
+#pragma unroll
+            for (int sp = 0; sp < S::NSPLIT; ++sp) a_lo0[sp] = desc_lo(a_base) + (uint32_t)(((((g0 + sp * GPS) * CG * 2) & 127) & ~31) >> 4);
+            uint32_t b_lo = desc_lo(smem_u32(wres + item * 9 * S::BSLAB));
+#pragma unroll 1                                            // one 32-bit add per descriptor and tap: warpgroup 0 runs on 40 registers
             for (int tap = 0; tap < 9; ++tap) {
               const int ty = tap / 3, tx = tap - ty * 3;
-              const uint32_t a_tap = a_base + (uint32_t)((ty * MX_BW + tx) * 128);
+              const uint32_t a_tap = (uint32_t)(((ty * MX_BW + tx) * 128) >> 4);
 #pragma unroll
               for (int sp = 0; sp < S::NSPLIT; ++sp) {
-                // the 32-byte K slice of the 128-byte pixel row that holds group g0 + sp
-                const uint32_t a_off = (uint32_t)((((g0 + sp) * CG * 2) & 127) & ~31);
-                const uint32_t b_addr = w_item + (uint32_t)(tap * S::BSLAB + sp * S::NSUB * S::KB * 2);
-                const uint64_t ad = make_desc_sbo(a_tap + a_off, MX_BW * 128, 2ull);
-                const uint64_t bd = make_desc_sbo(b_addr, 8 * S::KB * 2, b_layout);
 #pragma unroll
                 for (int k = 0; k < S::KSTEPS; ++k)
-                  umma_bf16(tacc + (uint32_t)(sp * S::NSUB), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (tap | k) != 0);
+                  umma_bf16_lohi(tacc + (uint32_t)(sp * S::NSUB), a_lo0[sp] + a_tap + (uint32_t)(k * 2), a_hi,
+                                 b_lo + (uint32_t)((sp * S::NSUB * S::KB * 2) >> 4) + (uint32_t)(k * 2), b_hi, idesc, (tap | k) != 0);
               }
+              b_lo += (uint32_t)(S::BSLAB >> 4);
             }
             umma_commit(&tmem_full[slot]);                 // accumulator of this item complete
             if (item == S::IPB - 1) {
