@@ -67,8 +67,10 @@ struct MixCfg {
   static constexpr int CTAB_BYTES = 9 * SETCOLS * 4;
   static constexpr int OFF_W = MX_ASTAGES * MX_A_STAGE;
   static constexpr int OFF_CTAB = OFF_W + MX_WRES;
-  static constexpr int OFF_BARS = OFF_CTAB + CTAB_BYTES;
+  static constexpr int OFF_RES = OFF_CTAB + CTAB_BYTES;   // residual staging: [epilogue warp][2][32 lanes] x 16 bytes (cp.async)
+  static constexpr int OFF_BARS = OFF_RES + MX_EPI_WARPS * 2 * 32 * 16;
   static constexpr int TOTAL = OFF_BARS + 128 + 1024 /* align slack */;
+  static_assert(TOTAL <= 227 * 1024, "shared memory");
   static_assert(OFF_W % 1024 == 0, "weight block alignment");
 };
 
@@ -79,6 +81,14 @@ __device__ __forceinline__ float swish_half(float h) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(h));
   return fmaf(h, y, h);
 }
+
+// 16-byte asynchronous global -> shared copy (completion is tracked per thread by cp.async groups, not by the register
+// scoreboards a prefetch into registers shares with every other load in flight)
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // unit = (column set, M tile), set-major; M tile = (image, tile row, tile column), column fastest
 struct UnitCursor {
@@ -250,12 +260,17 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
       n_att0 = __ldg(reinterpret_cast<const float4*>(p.att + (size_t)n_pix * 8));
       n_att1 = __ldg(reinterpret_cast<const float4*>(p.att + (size_t)n_pix * 8 + 4));
     };
-    auto load_res = [&](uint32_t pix, int set, int item) {
-      return __ldg(reinterpret_cast<const uint4*>(p.res + (size_t)pix * p.resC + ((set * S::SETCOLS + item * 256 + stripe * 64) >> 3)));
+    // The residual row of the NEXT item travels global -> shared by cp.async into this thread's own 16-byte slot (double
+    // buffered); the thread reads it back after cp.async.wait_group, so no cross-thread synchronisation is involved.
+    const uint32_t res_slot = smem_u32(smem + S::OFF_RES) + (uint32_t)(((warp - MX_FIRST_EPI_WARP) * 64 + lane) * 16);
+    auto request_res = [&](int buf, uint32_t pix, int set, int item) {
+      cp_async16(res_slot + (uint32_t)(buf * 512), p.res + (size_t)pix * p.resC + ((set * S::SETCOLS + item * 256 + stripe * 64) >> 3));
+      cp_async_commit();
     };
     fetch_unit();
-    uint4 res_nxt = load_res(n_pix, cur.set, 0);
-    for (int u = u0; u < u1; ++u) {
+    request_res(0, n_pix, cur.set, 0);
+    int rbuf_i = 0;                                          // staging buffer that holds the current item's residual
+    for (int left = u1 - u0; left > 0; --left) {
       const int img = cur.img, set = cur.set;
       if (img != stat_img) {
         if (p.dst_stats && stat_img >= 0) {
@@ -293,36 +308,47 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
       aw2[0] = make_float2(n_att0.x * w8[0], n_att0.y * w8[1]); aw2[1] = make_float2(n_att0.z * w8[2], n_att0.w * w8[3]);
       aw2[2] = make_float2(n_att1.x * w8[4], n_att1.y * w8[5]); aw2[3] = make_float2(n_att1.z * w8[6], n_att1.w * w8[7]);
       cur.next(p.tiles_x, p.tiles_y, p.B);
-      const bool more = u + 1 < u1;
+      const bool more = left > 1;
       if (more) fetch_unit();                                // ... and those of the next unit are requested now
       const float2 rs2 = make_float2(rstd, rstd);
 #pragma unroll
       for (int item = 0; item < S::IPB; ++item) {
         const int lcol = item * 256 + stripe * 64;          // first column of the stripe within the set
         const int ch0 = (set * S::SETCOLS + lcol) >> 3;     // its first output channel
-        const uint4 res_cur = res_nxt;
-        if (item + 1 < S::IPB) res_nxt = load_res(pix, set, item + 1);
-        else if (more) res_nxt = load_res(n_pix, cur.set, 0);
+        // request the residual of the next item (an empty group keeps the group count uniform at the very end)
+        if (item + 1 < S::IPB) request_res(rbuf_i ^ 1, pix, set, item + 1);
+        else if (more) request_res(rbuf_i ^ 1, n_pix, cur.set, 0);
+        else cp_async_commit();
         mbar_wait(&tmem_full[slot], sph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + stripe * 64);
         const float4* ct = reinterpret_cast<const float4*>(ctab + cls * S::SETCOLS + lcol);
+        cp_async_wait1();                                   // everything but the request just made has landed
+        const uint4 res_cur = *reinterpret_cast<const uint4*>(smem + S::OFF_RES + ((warp - MX_FIRST_EPI_WARP) * 64 + rbuf_i * 32 + lane) * 16);
+        rbuf_i ^= 1;
         const __nv_bfloat162* rr = reinterpret_cast<const __nv_bfloat162*>(&res_cur);
         __align__(16) __nv_bfloat162 o[4];
         float2 st1 = make_float2(0.f, 0.f), st2 = make_float2(0.f, 0.f);
         // 16 columns (two output channels) per step; the TMEM load of step k+1 is in flight during the math of step k
         uint32_t rbuf[2][16];
+        float4 cbuf[2][4];                                  // additive terms of step k / k+1 (read ahead of the TMEM wait)
         tmem_ld16(taddr, rbuf[0]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cbuf[0][j] = ct[j];
         tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (k < 3) tmem_ld16(taddr + 16 * (k + 1), rbuf[(k + 1) & 1]);
+          if (k < 3) {
+            tmem_ld16(taddr + 16 * (k + 1), rbuf[(k + 1) & 1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cbuf[(k + 1) & 1][j] = ct[4 * (k + 1) + j];
+          }
           if (valid) {
             const uint32_t* rv = rbuf[k & 1];
             float hh[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const float4 ca = ct[4 * k + 2 * e], cb = ct[4 * k + 2 * e + 1];
+              const float4 ca = cbuf[k & 1][2 * e], cb = cbuf[k & 1][2 * e + 1];
               const float2 v0 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 0]), __uint_as_float(rv[e * 8 + 1])), rs2, make_float2(ca.x, ca.y));
               const float2 v1 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 2]), __uint_as_float(rv[e * 8 + 3])), rs2, make_float2(ca.z, ca.w));
               const float2 v2 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 4]), __uint_as_float(rv[e * 8 + 5])), rs2, make_float2(cb.x, cb.y));
