@@ -67,4 +67,4 @@ def test_tc_schedule_routing():
     assert [mix(C, 0) for C in (64, 128, 256, 512)] == [0, 0, 0, 0]
     assert dense(64, 64, 1) == 2 and dense(192, 64, 1) == 2 and dense(384, 128, 1) == 2
     assert dense(64, 64, 0) == 0 and dense(256, 256, 1) == 0 and dense(64, 64, 1, ks=1) == 0
-    assert dense(64, 64, 1, gn=0) == 0 and dense(64, 64, 1, stride=2) == 0
+    assert dense(64, 64, 1, gn=0) == 2 and dense(64, 64, 1, stride=2) == 0

@@ -63,7 +63,7 @@ def stats_of(x_bf16):
     return torch.stack([v.sum(1), (v * v).sum(1)], dim=1).contiguous()
 
 
-def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1, row3=0, halo=0):
+def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1, row3=0, halo=0, kc=64):
     g = torch.Generator().manual_seed(seed)
     sH, sW = H * stride, W * stride
     c = Case()
@@ -94,7 +94,7 @@ def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1, row3=0,
                  w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), tg=t["tg"].data_ptr() if "tg" in t else 0, gn=1 if gn else 0,
                  ncls=9 if (gn and ks == 3) else 1, nty=ks, ntx=ks, oy0=-(ks // 2), ox0=-(ks // 2), stride=stride, act=act_,
                  res=act(t["res"], Cout, H, W) if res else None, dst=act(t["dst"], Cout, H, W, t["dstats"]), ntot=Cout, B=B, nt=nt,
-                 row3=row3, halo=halo)
+                 row3=row3, halo=halo, kc=kc)
         return ol
     return c, build
 
@@ -123,6 +123,8 @@ def test_tc_dense(cfg):
     dict(seed=24, B=3, H=64, W=64, C0=256, C1=128, Cout=128),
     dict(seed=25, B=2, H=24, W=20, C0=128, C1=0, Cout=128),
     dict(seed=26, B=5, H=48, W=96, C0=64, C1=0, Cout=64, act_=0),   # 90 items: most CTAs get one, images change inside a CTA's range
+    dict(seed=27, B=2, H=40, W=72, C0=16, C1=0, Cout=64, gn=False, act_=0, kc=16),     # the in-conv: 32-byte pixel rows, no GroupNorm
+    dict(seed=28, B=1, H=128, W=128, C0=16, C1=0, Cout=64, gn=False, act_=0, kc=16),
 ], ids=lambda c: "C%d+%d_%d_%dx%dx%d" % (c["C0"], c["C1"], c["Cout"], c["B"], c["H"], c["W"]))
 def test_tc_dense_halo(cfg):
     """csrc/ucdir_dhalo.cu: super tiles of 256/Cout 8x16-pixel tiles, one halo box per 64-channel chunk serves all nine taps."""

@@ -31,7 +31,7 @@ struct DhParams {
   int B, H, W;
   int nchunk, c0_chunks;
   int tiles_x, tiles_y, n_items;
-  int act, dstC, dstCoff;
+  int gn, act, dstC, dstCoff;
   double gn_count; float eps;
 };
 
@@ -39,15 +39,20 @@ constexpr int DH_EPI_WARPS = 16, DH_FIRST_EPI_WARP = 4;
 constexpr int DH_THREADS = 32 * (DH_FIRST_EPI_WARP + DH_EPI_WARPS);
 constexpr int DH_REGS_LOW = 40, DH_REGS_HIGH = 104;      // see MX_REGS_LOW / MX_REGS_HIGH in ucdir_mix.cu
 
-template <int NT>
+// KC = channels per chunk = one pixel row of the halo box: 64 (128-byte rows, 128B swizzle) or 16 (the in-conv's zero-padded
+// 6 -> 16 input channels: 32-byte rows, 32B swizzle, one K step per tap)
+template <int NT, int KC>
 struct DhCfg {
+  static constexpr int ROWB = KC * 2;                     // bytes per pixel row of a chunk
+  static constexpr uint32_t LAYOUT = KC == 64 ? 2u : 6u;  // operand descriptor swizzle mode: 128B / 32B
+  static constexpr int KSTEPS = KC / 16;
   static constexpr int MT = 256 / NT;                     // 8 x 16 pixel tiles per item
   static constexpr int SW = 8 * MT;                       // super tile width
   static constexpr int BW = SW + 2, BH = 18;              // halo box
-  static constexpr int A_BYTES = BW * BH * 128;
+  static constexpr int A_BYTES = BW * BH * ROWB;
   static constexpr int A_STAGE = (A_BYTES + 1023) & ~1023;
   static constexpr int ASTG = NT == 64 ? 2 : 3;
-  static constexpr int BSLAB = NT * 128;                  // one tap of one 64-channel chunk
+  static constexpr int BSLAB = NT * ROWB;                 // one tap of one chunk
   static constexpr int BSTG = NT == 64 ? 6 : 5;
   static constexpr int OFF_B = ASTG * A_STAGE;
   static constexpr int OFF_CTAB = OFF_B + BSTG * BSLAB;
@@ -79,11 +84,11 @@ struct SuperCursor {            // item = (image, super-tile row, super-tile col
   }
 };
 
-template <int NT, int ACT>
+template <int NT, int ACT, int KC>
 __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                    const __grid_constant__ CUtensorMap mapA1,
                                                                    const __grid_constant__ CUtensorMap mapB, const DhParams p) {
-  using S = DhCfg<NT>;
+  using S = DhCfg<NT, KC>;
   constexpr int MT = S::MT, ASTG = S::ASTG, BSTG = S::BSTG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -131,8 +136,8 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
           mbar_wait(&a_empty[stage], phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(&a_full[stage], (uint32_t)S::A_BYTES);
-            if (j < p.c0_chunks) tma_load_4d(&mapA0, &a_full[stage], smem + stage * S::A_STAGE, j * 64, x0, y0, cur.img);
-            else tma_load_4d(&mapA1, &a_full[stage], smem + stage * S::A_STAGE, (j - p.c0_chunks) * 64, x0, y0, cur.img);
+            if (j < p.c0_chunks) tma_load_4d(&mapA0, &a_full[stage], smem + stage * S::A_STAGE, j * KC, x0, y0, cur.img);
+            else tma_load_4d(&mapA1, &a_full[stage], smem + stage * S::A_STAGE, (j - p.c0_chunks) * KC, x0, y0, cur.img);
           }
           __syncwarp();
           if (++stage == ASTG) { stage = 0; phase ^= 1; }
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
             mbar_wait(&b_empty[stage], phase ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&b_full[stage], (uint32_t)S::BSLAB);
-              tma_load_2d(&mapB, &b_full[stage], bring + stage * S::BSLAB, (tap * p.nchunk + j) * 64, 0);
+              tma_load_2d(&mapB, &b_full[stage], bring + stage * S::BSLAB, (tap * p.nchunk + j) * KC, 0);
             }
             __syncwarp();
             if (++stage == BSTG) { stage = 0; phase ^= 1; }
@@ -175,14 +180,14 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
             tc_fence_after();
             if (elect_one()) {
               const int ty = tap / 3, tx = tap - ty * 3;
-              constexpr uint32_t a_hi = desc_hi(S::BW * 128, 2u), b_hi = desc_hi(1024, 2u);
-              const uint32_t a_lo = desc_lo(a_base) + (uint32_t)(((ty * S::BW + tx) * 128) >> 4);
+              constexpr uint32_t a_hi = desc_hi(S::BW * S::ROWB, S::LAYOUT), b_hi = desc_hi(8 * S::ROWB, S::LAYOUT);
+              const uint32_t a_lo = desc_lo(a_base) + (uint32_t)(((ty * S::BW + tx) * S::ROWB) >> 4);
               const uint32_t b_lo = desc_lo(smem_u32(bring + bs * S::BSLAB));
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16_lohi(tacc + (uint32_t)(mt * NT), a_lo + (uint32_t)((mt * 8 * 128) >> 4) + (uint32_t)(k * 2), a_hi,
+                for (int k = 0; k < S::KSTEPS; ++k)
+                  umma_bf16_lohi(tacc + (uint32_t)(mt * NT), a_lo + (uint32_t)((mt * 8 * S::ROWB) >> 4) + (uint32_t)(k * 2), a_hi,
                                  b_lo + (uint32_t)(k * 2), b_hi, idesc, (j | tap | k) != 0);
               }
               umma_commit(&b_empty[bs]);                   // weight slab may be overwritten
@@ -223,11 +228,16 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
         stat_img = img; s1 = 0.f; s2 = 0.f;
         // all epilogue warps walk the same items, so they all rebuild the additive table at the same item
         asm volatile("bar.sync 1, %0;" ::"n"(32 * DH_EPI_WARPS) : "memory");
-        const GnScalars sc = gn_scalars(p.stats0, p.stats1, img, p.gn_count, p.eps);
-        const float mri = sc.mean * sc.rstd;
         const float half = ACT ? 0.5f : 1.0f;             // Swish works on x / 2 (tanh form)
-        rstd = half * sc.rstd;
-        for (int i = et; i < 9 * NT; i += 32 * DH_EPI_WARPS) ctab[i] = half * fmaf(-mri, __ldg(p.tg + i), __ldg(p.tb + i));
+        if (p.gn) {
+          const GnScalars sc = gn_scalars(p.stats0, p.stats1, img, p.gn_count, p.eps);
+          const float mri = sc.mean * sc.rstd;
+          rstd = half * sc.rstd;
+          for (int i = et; i < 9 * NT; i += 32 * DH_EPI_WARPS) ctab[i] = half * fmaf(-mri, __ldg(p.tg + i), __ldg(p.tb + i));
+        } else {                                          // no GroupNorm in front: the additive term is the bias for every class
+          rstd = half;
+          for (int i = et; i < 9 * NT; i += 32 * DH_EPI_WARPS) ctab[i] = half * __ldg(p.tb + i % NT);
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * DH_EPI_WARPS) : "memory");
       }
       const int y = cur.ty * 16 + yy, x = cur.tx * S::SW + xx;
@@ -299,13 +309,13 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 static const bool g_dh_pdl = []() { const char* e = getenv("UCDIR_PDL"); return !(e && e[0] == '0'); }();
 
-template <int NT, int ACT>
+template <int NT, int ACT, int KC>
 static int launch_dh_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const DhParams& p, int grid, cudaStream_t st) {
-  using S = DhCfg<NT>;
+  using S = DhCfg<NT, KC>;
   static bool attr = false;
   if (!attr) {
-    if (int rc = check_reg_pool((const void*)dense_halo_kernel<NT, ACT>, "tc_dense_halo", 32 * DH_FIRST_EPI_WARP, DH_REGS_LOW, 32 * DH_EPI_WARPS, DH_REGS_HIGH)) return rc;
-    if (cudaFuncSetAttribute(dense_halo_kernel<NT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+    if (int rc = check_reg_pool((const void*)dense_halo_kernel<NT, ACT, KC>, "tc_dense_halo", 32 * DH_FIRST_EPI_WARP, DH_REGS_LOW, 32 * DH_EPI_WARPS, DH_REGS_HIGH)) return rc;
+    if (cudaFuncSetAttribute(dense_halo_kernel<NT, ACT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
       set_error("tc_dense_halo: cannot opt in to %d bytes of shared memory: %s", S::TOTAL, cudaGetErrorString(cudaGetLastError())); return -3; }
     attr = true;
   }
@@ -315,7 +325,7 @@ static int launch_dh_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CU
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = g_dh_pdl ? 1 : 0;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, dense_halo_kernel<NT, ACT>, a0, a1, b, p) != cudaSuccess) {
+  if (cudaLaunchKernelEx(&cfg, dense_halo_kernel<NT, ACT, KC>, a0, a1, b, p) != cudaSuccess) {
     set_error("tc_dense_halo: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
   return 0;
 }
@@ -325,38 +335,42 @@ bool tc_dense_halo_applies(const ucdir_op_t& op) {
   const int C0 = op.i[UCDIR_TC_I_C0], C1 = op.i[UCDIR_TC_I_C1], H = op.i[UCDIR_TC_I_H], W = op.i[UCDIR_TC_I_W];
   const int NT = op.i[UCDIR_TC_I_NT];
   const int KB = op.i[UCDIR_TC_I_KB] ? op.i[UCDIR_TC_I_KB] : op.i[UCDIR_TC_I_KC];
+  const int KC = op.i[UCDIR_TC_I_KC], gn = op.i[UCDIR_TC_I_GN];
+  const bool chunks_ok = (KC == 64 && KB == 64 && C0 % 64 == 0 && C1 % 64 == 0) || (KC == 16 && KB == 16 && C0 == 16 && C1 == 0 && NT == 64);
+  const bool gn_ok = gn == 1 ? (op.i[UCDIR_TC_I_NCLS] == 9 && op.p[UCDIR_TC_P_TG] && op.p[UCDIR_TC_P_STATS0] && (C1 == 0 || op.p[UCDIR_TC_P_STATS1]))
+                             : (gn == 0);
   return op.i[UCDIR_TC_I_HALO] == 1 && op.i[UCDIR_TC_I_MODE] == 0 && op.i[UCDIR_TC_I_GROUPS] == 1 && (NT == 64 || NT == 128) &&
-         op.i[UCDIR_TC_I_NTOT] == NT && op.i[UCDIR_TC_I_KC] == 64 && KB == 64 && C0 % 64 == 0 && C1 % 64 == 0 &&
-         op.i[UCDIR_TC_I_GN] == 1 && op.i[UCDIR_TC_I_NCLS] == 9 && op.i[UCDIR_TC_I_NTY] == 3 && op.i[UCDIR_TC_I_NTX] == 3 &&
+         op.i[UCDIR_TC_I_NTOT] == NT && chunks_ok && gn_ok && op.i[UCDIR_TC_I_NTY] == 3 && op.i[UCDIR_TC_I_NTX] == 3 &&
          op.i[UCDIR_TC_I_OY0] == -1 && op.i[UCDIR_TC_I_OX0] == -1 && op.i[UCDIR_TC_I_STRIDE] == 1 && H >= 2 && W >= 2 &&
          op.i[UCDIR_TC_I_SRC_H] == H && op.i[UCDIR_TC_I_SRC_W] == W && !op.p[UCDIR_TC_P_RES] && !op.i[UCDIR_TC_I_DST_F32] &&
-         !op.i[UCDIR_TC_I_DST_UP] && !op.i[UCDIR_TC_I_W_BATCHED] && !op.p[UCDIR_TC_P_DST2] &&
+         !op.i[UCDIR_TC_I_DST_UP] && !op.i[UCDIR_TC_I_W_BATCHED] && !op.p[UCDIR_TC_P_DST2] && op.i[UCDIR_TC_I_ACT] <= 1 &&
          (op.i[UCDIR_TC_I_SRC_CSTRIDE] == 0 || op.i[UCDIR_TC_I_SRC_CSTRIDE] == C0) && op.i[UCDIR_TC_I_DST_C] % 8 == 0 &&
          op.i[UCDIR_TC_I_DST_COFF] % 8 == 0 && (op.i[UCDIR_TC_I_NCOL_VALID] == 0 || op.i[UCDIR_TC_I_NCOL_VALID] == NT) &&
-         op.p[UCDIR_TC_P_TG] && op.p[UCDIR_TC_P_STATS0] && (C1 == 0 || (op.p[UCDIR_TC_P_SRC1] && op.p[UCDIR_TC_P_STATS1]));
+         (C1 == 0 || op.p[UCDIR_TC_P_SRC1]);
 }
 
-static int dh_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int B, int bw) {
+static int dh_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int B, int bw, int kc) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("tc_dense_halo: cuTensorMapEncodeTiled unavailable"); return -3; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, 18, 1};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)bw, 18, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("tc_dense_halo: cuTensorMapEncodeTiled(activation C=%d W=%d H=%d B=%d box %d) failed: %d", C, W, H, B, bw, (int)r); return -3; }
   return 0;
 }
 
 int launch_tc_dense_halo(const ucdir_op_t& op, cudaStream_t st) {
   DhParams p;
-  const int C0 = op.i[UCDIR_TC_I_C0], C1 = op.i[UCDIR_TC_I_C1], NT = op.i[UCDIR_TC_I_NT];
+  const int C0 = op.i[UCDIR_TC_I_C0], C1 = op.i[UCDIR_TC_I_C1], NT = op.i[UCDIR_TC_I_NT], KC = op.i[UCDIR_TC_I_KC];
+  p.gn = op.i[UCDIR_TC_I_GN];
   p.stats0 = (const double*)op.p[UCDIR_TC_P_STATS0]; p.stats1 = C1 ? (const double*)op.p[UCDIR_TC_P_STATS1] : nullptr;
   p.tb = (const float*)op.p[UCDIR_TC_P_TB]; p.tg = (const float*)op.p[UCDIR_TC_P_TG];
   p.dst = (__nv_bfloat16*)op.p[UCDIR_TC_P_DST]; p.dst_stats = (double*)op.p[UCDIR_TC_P_DST_STATS];
   p.B = op.i[UCDIR_TC_I_B]; p.H = op.i[UCDIR_TC_I_H]; p.W = op.i[UCDIR_TC_I_W];
-  p.c0_chunks = C0 / 64; p.nchunk = (C0 + C1) / 64;
+  p.c0_chunks = C0 / KC; p.nchunk = (C0 + C1) / KC;
   p.act = op.i[UCDIR_TC_I_ACT]; p.dstC = op.i[UCDIR_TC_I_DST_C]; p.dstCoff = op.i[UCDIR_TC_I_DST_COFF];
   p.eps = op.f[UCDIR_TC_F_EPS];
   p.gn_count = (double)(C0 + C1) * p.H * p.W;
@@ -366,26 +380,28 @@ int launch_tc_dense_halo(const ucdir_op_t& op, cudaStream_t st) {
   if (items > 0x7fffffffLL) { set_error("tc_dense_halo: too many items"); return -2; }
   p.n_items = (int)items;
   CUtensorMap a0, a1, mb;
-  int rc = dh_act_map(&a0, op.p[UCDIR_TC_P_SRC0], C0, p.W, p.H, p.B, sw + 2);
+  int rc = dh_act_map(&a0, op.p[UCDIR_TC_P_SRC0], C0, p.W, p.H, p.B, sw + 2, KC);
   if (rc) return rc;
-  if (C1 > 0) { rc = dh_act_map(&a1, op.p[UCDIR_TC_P_SRC1], C1, p.W, p.H, p.B, sw + 2); if (rc) return rc; }
+  if (C1 > 0) { rc = dh_act_map(&a1, op.p[UCDIR_TC_P_SRC1], C1, p.W, p.H, p.B, sw + 2, KC); if (rc) return rc; }
   else a1 = a0;
   {
     EncodeTiledFn enc = get_encode();
     const int Ktot = 9 * (C0 + C1);
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)NT};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)NT};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)NT};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.p[UCDIR_TC_P_W]), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tc_dense_halo: cuTensorMapEncodeTiled(weights K=%d N=%d) failed: %d", Ktot, NT, (int)r); return -3; }
   }
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
   const int grid = items < n_sm ? (int)items : n_sm;       // persistent: one CTA per SM
-  if (NT == 64) rc = p.act == 1 ? launch_dh_inst<64, 1>(a0, a1, mb, p, grid, st) : launch_dh_inst<64, 0>(a0, a1, mb, p, grid, st);
-  else rc = p.act == 1 ? launch_dh_inst<128, 1>(a0, a1, mb, p, grid, st) : launch_dh_inst<128, 0>(a0, a1, mb, p, grid, st);
+  if (KC == 16) rc = p.act == 1 ? launch_dh_inst<64, 1, 16>(a0, a1, mb, p, grid, st) : launch_dh_inst<64, 0, 16>(a0, a1, mb, p, grid, st);
+  else if (NT == 64) rc = p.act == 1 ? launch_dh_inst<64, 1, 64>(a0, a1, mb, p, grid, st) : launch_dh_inst<64, 0, 64>(a0, a1, mb, p, grid, st);
+  else rc = p.act == 1 ? launch_dh_inst<128, 1, 64>(a0, a1, mb, p, grid, st) : launch_dh_inst<128, 0, 64>(a0, a1, mb, p, grid, st);
   if (rc) return rc;
   ++g_launches;
   return 0;
