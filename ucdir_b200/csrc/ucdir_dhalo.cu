@@ -31,7 +31,7 @@ struct DhParams {
   int B, H, W;
   int nchunk, c0_chunks;
   int tiles_x, tiles_y, n_items;
-  int gn, act, dstC, dstCoff;
+  int gn, act, dstC, dstCoff, st32;
   double gn_count; float eps;
 };
 
@@ -276,8 +276,15 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
             st1 = __fadd2_rn(st1, __fadd2_rn(va, vb));
             st2 = __ffma2_rn(va, va, __ffma2_rn(vb, vb, st2));
           }
-          *reinterpret_cast<uint4*>(d + 16 * k) = *reinterpret_cast<const uint4*>(o2);
-          *reinterpret_cast<uint4*>(d + 16 * k + 8) = *reinterpret_cast<const uint4*>(o2 + 4);
+          const uint32_t* ow = reinterpret_cast<const uint32_t*>(o2);
+          if (p.st32) {
+            // one 256-bit store = one whole 32-byte sector per pixel (two 16-byte stores are two partial-sector writes at L2)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(d + 16 * k), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]),
+                         "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
+          } else {
+            *reinterpret_cast<uint4*>(d + 16 * k) = *reinterpret_cast<const uint4*>(o2);
+            *reinterpret_cast<uint4*>(d + 16 * k + 8) = *reinterpret_cast<const uint4*>(o2 + 4);
+          }
         }
         if (k < 3) tmem_ld_wait();
         if (k == 2) {
@@ -373,6 +380,7 @@ int launch_tc_dense_halo(const ucdir_op_t& op, cudaStream_t st) {
   p.c0_chunks = C0 / KC; p.nchunk = (C0 + C1) / KC;
   p.act = op.i[UCDIR_TC_I_ACT]; p.dstC = op.i[UCDIR_TC_I_DST_C]; p.dstCoff = op.i[UCDIR_TC_I_DST_COFF];
   p.eps = op.f[UCDIR_TC_F_EPS];
+  p.st32 = (p.dstC % 16 == 0 && p.dstCoff % 16 == 0 && (reinterpret_cast<uintptr_t>(p.dst) & 31) == 0) ? 1 : 0;
   p.gn_count = (double)(C0 + C1) * p.H * p.W;
   const int sw = 8 * (256 / NT);
   p.tiles_x = (p.W + sw - 1) / sw; p.tiles_y = (p.H + 15) / 16;
