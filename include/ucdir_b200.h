@@ -24,6 +24,7 @@
  *                          utils/util.py:144-146 ; model/diffusion.py:150-158,171-172,182-183
  *   UCDIR_OP_MAXPOOL2      nn.MaxPool2d(2)                              model/ucdir.py:363-375
  *   UCDIR_OP_TC_*          bf16 tcgen05/TMA versions of CONV / attention (same reference lines)
+ *   UCDIR_OP_TO_IMAGE_U8   result crop + tensor2img                     model/model.py:137, core/metrics.py:8-34
  *
  * Activation layout inside the library: NHWC ("pixel-major, channel-innermost"), fp32 or bf16.
  * Image layout at the boundary: the reference's NCHW fp32.
@@ -68,7 +69,8 @@ enum ucdir_op_kind {
   UCDIR_OP_CROP_TILES = 14,
   UCDIR_OP_GN_STATS_F32 = 15,
   UCDIR_OP_GN_APPLY_F32 = 16,
-  UCDIR_OP_LAYOUT = 17
+  UCDIR_OP_LAYOUT = 17,
+  UCDIR_OP_TO_IMAGE_U8 = 18
 };
 
 /* ---- UCDIR_OP_CONV_F32: dst = epilogue( conv( prologue(concat(src0, src1)) ) ) -----------------
@@ -228,6 +230,14 @@ enum ucdir_gnf_ptr { UCDIR_GNF_P_SRC = 0, UCDIR_GNF_P_DST = 1, UCDIR_GNF_P_GAMMA
 enum ucdir_gns_int { UCDIR_GNS_I_B = 0, UCDIR_GNS_I_HW = 1, UCDIR_GNS_I_C = 2, UCDIR_GNS_I_G = 3, UCDIR_GNS_I_SWISH = 4 };
 
 /* ---- UCDIR_OP_LAYOUT: fp32 layout change, p[0] -> p[1]; i = {B, C, HW, DIR}; DIR 0: NCHW -> NHWC, 1: NHWC -> NCHW ---------- */
+
+/* ---- UCDIR_OP_TO_IMAGE_U8: DST[B][H-2*PD][W-2*PD][C] (uint8, HWC) = round(((clamp(SRC, MIN, MAX) - MIN) / (MAX - MIN)) * 255) of the
+ * fp32 NCHW SRC[B][C][H][W] cropped by PD pixels per side: the caller-side tail of the path fused into one pass -- the
+ * `[..., pd:-pd, pd:-pd]` crop of model/model.py:137 and core/metrics.py:8-34 (tensor2img: clamp, rescale, HWC, *255, round
+ * half to even, uint8) -- so that one quarter of the bytes crosses PCIe.  f = {MIN, MAX}. */
+enum ucdir_img_ptr { UCDIR_IMG_P_SRC = 0, UCDIR_IMG_P_DST = 1 };
+enum ucdir_img_int { UCDIR_IMG_I_B = 0, UCDIR_IMG_I_C = 1, UCDIR_IMG_I_H = 2, UCDIR_IMG_I_W = 3, UCDIR_IMG_I_PD = 4 };
+enum ucdir_img_flt { UCDIR_IMG_F_MIN = 0, UCDIR_IMG_F_MAX = 1 };
 
 /* ---- UCDIR_OP_CROP_TILES: DST[BT,IH,IW,4] = SRC[BT,TH,TW,4][:, OY:OY+IH, OX:OX+IW] (fp32): the tile interiors that are
  * stitched (utils/util.py:144-145) and, in tile-sharded mode, all-gathered once per step ------------------------ */

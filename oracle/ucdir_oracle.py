@@ -379,8 +379,27 @@ def ddim_sample(sched: Dict[str, np.ndarray], denoise, x_in: Tensor, guide: Tens
 
 def super_resolution(sd: SD, layout: UNetLayout, sched, x_in: Tensor, noises: Sequence[Tensor],
                      continous: bool = False, skip: int = 1024, padding: int = 64,
-                     force_tiler: bool = False) -> Tuple[Tensor, Tensor]:
-    """ResiGaussianGuideDY.super_resolution, model/diffusion.py:473-478.  Returns (result, initx)."""
+                     force_tiler: bool = False, guide_from: str = "initx") -> Tuple[Tensor, Tensor]:
+    """ResiGaussianGuideDY.super_resolution, model/diffusion.py:473-478 (guide_from="initx"), and
+    ResiGaussianGuideDY_de.super_resolution, model/diffusion.py:518-523 (guide_from="input": the degraded input guides).
+    Returns (result, initx)."""
     initx = predictor_forward(sd, "predictor.", x_in)
     den = lambda xc, lvl, g: unet_forward(sd, "denoise_fn.", layout, xc, lvl, g, skip, padding, force_tiler)
-    return p_sample_loop(sched, den, x_in, initx, noises, continous) + initx, initx
+    guide = initx if guide_from == "initx" else x_in
+    return p_sample_loop(sched, den, x_in, guide, noises, continous) + initx, initx
+
+
+def tensor2img(tensor: Tensor, min_max=(-1, 1)) -> np.ndarray:
+    """core/metrics.py:8-34 for the 3D / batch-1 4D uint8 case: clamp, rescale to [0,1], HWC, * 255.0, round (numpy: half to
+    even), uint8."""
+    t = tensor.squeeze().float().cpu().clamp(*min_max)
+    t = (t - min_max[0]) / (min_max[1] - min_max[0])
+    img = np.transpose(t.numpy(), (1, 2, 0)) if t.dim() == 3 else t.numpy()
+    return (img * 255.0).round().astype(np.uint8)
+
+
+def ddpm_test(sd: SD, layout: UNetLayout, sched, sr: Tensor, noises: Sequence[Tensor], continous: bool = False, pd: int = 64) -> Tensor:
+    """DDPM.test, model/model.py:124-138: reflect-pad the degraded input by 64, super_resolution, crop."""
+    x = F.pad(sr, (pd, pd, pd, pd), mode="reflect")
+    out, _ = super_resolution(sd, layout, sched, x, noises, continous)
+    return out[..., pd:-pd, pd:-pd]

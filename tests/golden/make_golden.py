@@ -187,9 +187,52 @@ def main_ddim():
          sched=np.array([10, 1e-6, 0.4], dtype=np.float64))
 
 
+def main_variants():
+    """7. ResiGaussianGuideDY_de.super_resolution (model/diffusion.py:481-523; guidance = the degraded input): T=4, injected
+    noise, continous=False.  Same seed and constructor order as ResiGaussianGuideDY, hence the same weights (sha256 checked)."""
+    opt = yaml.safe_load(open(os.path.join(REF, "config/sid.yaml")))
+    opt["model"]["diffusion_name"] = "ResiGaussianGuideDY_de"
+    g = torch.Generator().manual_seed(INPUT_SEED + 7)
+    torch.manual_seed(WEIGHT_SEED)
+    net = refnet.define_G(opt).eval()
+    assert sd_digest(net.state_dict()) == str(np.load(os.path.join(OUT, "unet.npz"))["digest"])
+    so = dict(schedule="linear", n_timestep=4, linear_start=1e-6, linear_end=0.4)
+    net.set_new_noise_schedule(so, torch.device("cpu"))
+    x_in = torch.rand(1, 3, 64, 64, generator=g) * 2 - 1
+    ng = torch.Generator().manual_seed(NOISE_SEED + 2)
+    noises = [torch.randn(1, 3, 64, 64, generator=ng) for _ in range(4)]
+    it = iter(noises)
+    refdiff.torch.randn, refdiff.torch.randn_like = (lambda *a, **k: next(it)), (lambda *a, **k: next(it))
+    try:
+        with torch.no_grad():
+            out = net.super_resolution(x_in, False)
+    finally:
+        refdiff.torch.randn, refdiff.torch.randn_like = torch.randn, torch.randn_like
+    save("sr_de", x_in=x_in.numpy(), noises=torch.stack(noises).numpy(), out=out.numpy(), initx=net.pre_initx.numpy(),
+         sched=np.array([4, 1e-6, 0.4], dtype=np.float64))
+
+
+def main_image():
+    """8. core/metrics.py:8-34 tensor2img on a tensor with out-of-range values and exact rounding ties."""
+    import core.metrics as refmetrics
+    g = torch.Generator().manual_seed(INPUT_SEED + 8)
+    x = torch.randn(1, 3, 40, 56, generator=g) * 0.8
+    ties = (torch.arange(0, 256, dtype=torch.float32) + 0.5) / 255.0 * 2 - 1          # values that land on k + 0.5 after * 255
+    x[0, 0, 0, :56] = ties[:56]; x[0, 1, 1, :56] = ties[100:156]; x[0, 2, 2, :56] = ties[199:255]
+    img = refmetrics.tensor2img(x.clone())
+    img_crop = refmetrics.tensor2img(x[..., 8:-8, 8:-8].clone())
+    save("image", x=x.numpy(), img=img, img_crop=img_crop, crop=np.array(8))
+
+
 if __name__ == "__main__":
-    if "--only-ddim" in sys.argv:
+    if "--only-image" in sys.argv:
+        main_image()
+    elif "--only-ddim" in sys.argv:
         main_ddim()
+    elif "--only-variants" in sys.argv:
+        main_variants()
     else:
         main()
         main_ddim()
+        main_variants()
+        main_image()

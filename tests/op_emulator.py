@@ -484,13 +484,23 @@ def emu_layout(op, mem):
         mem.view(int(op.p[1]), (B, Cc, HW)).copy_(mem.view(int(op.p[0]), (B, HW, Cc)).transpose(1, 2))
 
 
+def emu_to_image(op, mem):
+    g = lambda n: _i(op, "UCDIR_IMG_I_" + n)
+    B, C, H, W, PD = g("B"), g("C"), g("H"), g("W"), g("PD")
+    lo, hi = np.float32(_f(op, "UCDIR_IMG_F_MIN")), np.float32(_f(op, "UCDIR_IMG_F_MAX"))
+    src = mem.view(_p(op, "UCDIR_IMG_P_SRC"), (B, C, H, W))[:, :, PD:H - PD, PD:W - PD]
+    v = ((src.clamp(float(lo), float(hi)) - float(lo)) / float(hi - lo)).numpy()            # fp32, as core/metrics.py:14-16
+    img = (v * np.float32(255.0)).round().astype(np.uint8)                                  # :29-31 (numpy rounds half to even)
+    mem.view(_p(op, "UCDIR_IMG_P_DST"), (B, H - 2 * PD, W - 2 * PD, C), torch.uint8).copy_(torch.from_numpy(img).permute(0, 2, 3, 1))
+
+
 DISPATCH = {
     K["UCDIR_OP_CONV_F32"]: emu_conv, K["UCDIR_OP_SGEMM_F32"]: emu_sgemm, K["UCDIR_OP_SOFTMAX_F32"]: emu_softmax,
     K["UCDIR_OP_GUIDANCE"]: emu_guidance, K["UCDIR_OP_TIME_EMBED"]: emu_time_embed,
     K["UCDIR_OP_GATHER_TILES"]: emu_gather, K["UCDIR_OP_SCATTER"]: emu_scatter, K["UCDIR_OP_MAXPOOL2"]: emu_maxpool,
     K["UCDIR_OP_MEMSET"]: emu_memset, K["UCDIR_OP_TC_CONV"]: emu_tc_conv, K["UCDIR_OP_GN_APPLY_BF16"]: emu_gn_apply,
     K["UCDIR_OP_CAST"]: emu_cast, K["UCDIR_OP_CROP_TILES"]: emu_crop, K["UCDIR_OP_GN_STATS_F32"]: emu_gn_stats,
-    K["UCDIR_OP_GN_APPLY_F32"]: emu_gn_apply_f32, K["UCDIR_OP_LAYOUT"]: emu_layout,
+    K["UCDIR_OP_GN_APPLY_F32"]: emu_gn_apply_f32, K["UCDIR_OP_LAYOUT"]: emu_layout, K["UCDIR_OP_TO_IMAGE_U8"]: emu_to_image,
 }
 
 LAUNCHED = []

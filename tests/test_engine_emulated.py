@@ -101,6 +101,43 @@ def test_super_resolution_e2e(emulated, golden, sid_weights):
     assert sess.launches_per_step() > 100
 
 
+def _variant_net(name):
+    """A diffusion wrapper variant with the seeded sid weights (same constructor order => same state_dict)."""
+    from ucdir_b200.model.networks import define_G
+    opt = dict(ucdir_b200.SID_MODEL_OPT, diffusion_name=name)
+    torch.manual_seed(1234)
+    return define_G({"model": opt})
+
+
+def test_degraded_guidance_wrapper(emulated, golden, sid_weights):
+    """ResiGaussianGuideDY_de.super_resolution (model/diffusion.py:518-523) against the reference's own output."""
+    _, sd = sid_weights
+    net = _variant_net("ResiGaussianGuideDY_de")
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    g = golden("sr_de")
+    n, ls, le = g["sched"]
+    net.set_new_noise_schedule(dict(schedule="linear", n_timestep=int(n), linear_start=float(ls), linear_end=float(le)),
+                               torch.device("cpu"))
+    noises = iter([T(z) for z in g["noises"]])
+    net._noise_source = lambda shape: next(noises)
+    out = net.super_resolution(T(g["x_in"]), False)
+    close(net.pre_initx, g["initx"], rtol=1e-4, atol=1e-5)
+    close(out, g["out"])
+
+
+def test_initxloss_wrapper_is_guide_dy_at_inference(emulated, golden, sid_weights):
+    """ResiGaussianGuideDY_initxloss (model/diffusion.py:528-571) differs only in its training loss."""
+    net = _variant_net("ResiGaussianGuideDY_initxloss")
+    g = golden("sr_e2e")
+    n, ls, le = g["sched"]
+    net.set_new_noise_schedule(dict(schedule="linear", n_timestep=int(n), linear_start=float(ls), linear_end=float(le)),
+                               torch.device("cpu"))
+    noises = iter([T(z) for z in g["noises"]])
+    net._noise_source = lambda shape: next(noises)
+    out = net.super_resolution(T(g["x_in"]), True)
+    close(out, g["out"])
+
+
 def test_bf16_graph_matches_reference_within_bf16_tolerance(emulated, golden, sid_weights):
     """tcgen05-path graph (GroupNorm folded into weights + border-class tables, grouped K chunks with zero
     filled foreign channels, 4-phase upsample convs, bf16 storage) executed by the CPU interpreter."""
@@ -176,3 +213,44 @@ def test_boundary_contract_deepcopy_load_state_dict_and_reschedule(emulated, gol
         assert ema.sqrt_alphas_cumprod_prev.shape == (T_ + 1,) and ema.sqrt_alphas_cumprod_prev.dtype == np.float64
     with pytest.raises(NotImplementedError):
         ema(T(g["x6"]))                                            # training forward (p_losses) is out of scope
+
+
+def test_tensor2img_op(emulated, golden):
+    """UCDIR_OP_TO_IMAGE_U8 wiring (ucdir_b200.utils.image.tensor2img) against the reference's tensor2img output, bit exact."""
+    from ucdir_b200.utils.image import tensor2img
+    g = golden("image")
+    x = T(g["x"])
+    assert np.array_equal(tensor2img(x), g["img"])
+    assert np.array_equal(tensor2img(x, crop=int(g["crop"])), g["img_crop"])
+    assert np.array_equal(tensor2img(x[0]), g["img"])                      # (C,H,W) input
+    with pytest.raises(NotImplementedError):
+        tensor2img(x, out_type=np.float32)
+
+
+def test_ddpm_inference_wrapper(emulated, sid_weights, monkeypatch):
+    """DDPMInference.feed_data / test / get_current_visuals (model/model.py:124-138,167-179): reflect pad by 64, sample, crop --
+    against the oracle's restatement, T=1 schedule, injected noise."""
+    from oracle import ucdir_oracle as O
+    from ucdir_b200.model import model as M
+    net, sd = sid_weights
+    monkeypatch.setattr(M.networks, "define_G", lambda opt: net)
+    dd = M.DDPMInference({"model": ucdir_b200.SID_MODEL_OPT}, device="cpu")
+    so = dict(schedule="linear", n_timestep=1, linear_start=1e-6, linear_end=0.4)
+    dd.set_new_noise_schedule(so, schedule_phase="val")
+    gen = torch.Generator().manual_seed(3)
+    sr = torch.rand(1, 3, 72, 80, generator=gen) * 2 - 1
+    noise = torch.randn(1, 3, 72 + 128, 80 + 128, generator=gen)
+    net._noise_source = lambda shape: noise
+    try:
+        dd.feed_data({"SR": sr.clone(), "HR": sr.clone(), "Index": 0})
+        dd.test(continous=False)
+    finally:
+        net._noise_source = None
+    vis = dd.get_current_visuals()
+    assert vis["SR"].shape == sr.shape and torch.equal(vis["INF"], sr) and net.training
+    lay = O.UNetLayout(**ucdir_b200.SID_MODEL_OPT["unet"])
+    with torch.no_grad():
+        want = O.ddpm_test(sd, lay, O.schedule_buffers(so), sr, [noise], continous=False)
+    close(vis["SR"], want)
+    assert np.array_equal(dd.current_image(), O.tensor2img(vis["SR"])) or \
+        np.abs(dd.current_image().astype(int) - O.tensor2img(want).astype(int)).max() <= 1

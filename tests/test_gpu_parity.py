@@ -92,6 +92,22 @@ def test_super_resolution_golden_e2e(net, golden):
     close(out, g["out"], what="super_resolution T=4 continous")
 
 
+def test_degraded_guidance_wrapper_golden(golden):
+    """ResiGaussianGuideDY_de.super_resolution (model/diffusion.py:518-523; the degraded input guides) on the CUDA path."""
+    from ucdir_b200.model.networks import define_G
+    torch.manual_seed(1234)
+    net = define_G({"model": dict(ucdir_b200.SID_MODEL_OPT, diffusion_name="ResiGaussianGuideDY_de")}).cuda().eval()
+    g = golden("sr_de")
+    n, ls, le = g["sched"]
+    net.set_new_noise_schedule(dict(schedule="linear", n_timestep=int(n), linear_start=float(ls), linear_end=float(le)),
+                               torch.device("cuda"))
+    noises = iter([T(z) for z in g["noises"]])
+    net._noise_source = lambda shape: next(noises)
+    out = net.super_resolution(T(g["x_in"]).cuda(), False)
+    close(net.pre_initx, g["initx"], what="initx")
+    close(out, g["out"], what="ResiGaussianGuideDY_de.super_resolution T=4")
+
+
 def test_teacher_forced_steps_vs_oracle_c1(net, sd, layout):
     """BASELINE config C1 (1x3x128x128, T=4): every step is fed the oracle's x_t so that errors cannot
     compound; eps-equivalent check via x_{t-1} of the same inputs."""
@@ -222,3 +238,14 @@ def test_ddim_sample_golden(net, golden):
         net._noise_source = None
         net.set_new_noise_schedule(ucdir_b200.SID_VAL_SCHEDULE, torch.device("cuda"))
     close(traj, g["traj"], what="ddim trajectory")
+
+
+def test_tensor2img_kernel_bit_exact(golden):
+    """UCDIR_OP_TO_IMAGE_U8 (crop + core/metrics.py:8-34 on the device) against the reference's own uint8 output."""
+    from ucdir_b200.utils.image import tensor2img
+    g = golden("image")
+    x = T(g["x"]).cuda()
+    assert np.array_equal(tensor2img(x), g["img"])
+    assert np.array_equal(tensor2img(x, crop=int(g["crop"])), g["img_crop"])
+    with pytest.raises(Exception):
+        tensor2img(T(g["x"]))                                  # CPU tensor: no fallback

@@ -82,6 +82,22 @@ def test_super_resolution_e2e(golden, sid_weights):
     close(out, g["out"], rtol=1e-4, atol=2e-5)
 
 
+def test_super_resolution_degraded_guidance(golden, sid_weights):
+    """ResiGaussianGuideDY_de (model/diffusion.py:481-523): the degraded input, not initx, guides the integration modules."""
+    import ucdir_b200
+    _, sd = sid_weights
+    g = golden("sr_de")
+    n, ls, le = g["sched"]
+    sched = O.schedule_buffers(dict(schedule="linear", n_timestep=int(n), linear_start=float(ls), linear_end=float(le)))
+    lay = O.UNetLayout(**ucdir_b200.SID_MODEL_OPT["unet"])
+    with torch.no_grad():
+        out, initx = O.super_resolution(sd, lay, sched, T(g["x_in"]), [T(z) for z in g["noises"]], continous=False, guide_from="input")
+        out_wrong, _ = O.super_resolution(sd, lay, sched, T(g["x_in"]), [T(z) for z in g["noises"]], continous=False)
+    close(initx, g["initx"], rtol=1e-5, atol=1e-6)
+    close(out, g["out"], rtol=1e-4, atol=2e-5)
+    assert (out_wrong - T(g["out"])).abs().max().item() > 1e-3       # the guide source matters
+
+
 def test_tiler(golden, sid_weights):
     import ucdir_b200
     _, sd = sid_weights
@@ -114,3 +130,12 @@ def test_ddim_sample(golden, sid_weights):
     with torch.no_grad():
         traj = O.ddim_sample(sched, den, T(g["x_in"]), T(g["initx"]), [T(z) for z in g["noises"]])
     close(traj, g["traj"], rtol=1e-4, atol=2e-5)
+
+
+def test_tensor2img(golden):
+    """core/metrics.py:8-34 incl. clamping and round-half-to-even ties, against the reference's own output."""
+    g = golden("image")
+    x = T(g["x"])
+    assert np.array_equal(O.tensor2img(x), g["img"])
+    c = int(g["crop"])
+    assert np.array_equal(O.tensor2img(x[..., c:-c, c:-c]), g["img_crop"])

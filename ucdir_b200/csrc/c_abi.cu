@@ -47,6 +47,7 @@ static int dispatch(const ucdir_op_t& op, cudaStream_t st, bool dry) {
     case UCDIR_OP_GN_STATS_F32: return launch_gn_stats_f32(op, st, dry);
     case UCDIR_OP_GN_APPLY_F32: return launch_gn_apply_f32(op, st, dry);
     case UCDIR_OP_LAYOUT: return launch_layout(op, st, dry);
+    case UCDIR_OP_TO_IMAGE_U8: return launch_to_image_u8(op, st, dry);
     default: set_error("unknown op kind %d", op.kind); return -1;
   }
 }

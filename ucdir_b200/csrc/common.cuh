@@ -68,5 +68,6 @@ int launch_crop_tiles(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_gn_stats_f32(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_gn_apply_f32(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_layout(const ucdir_op_t& op, cudaStream_t st, bool dry);
+int launch_to_image_u8(const ucdir_op_t& op, cudaStream_t st, bool dry);
 
 }  // namespace ucdir

@@ -323,6 +323,42 @@ int launch_crop_tiles(const ucdir_op_t& op, cudaStream_t st, bool dry) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Result image: crop + clamp + rescale + HWC uint8 in one pass (model/model.py:137 crop, core/metrics.py:8-34 tensor2img).
+// Arithmetic order of the reference: (clamp(x) - min) / (max - min) in fp32, * 255.0f in fp32, round half to even.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) to_image_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int B, int C, int H, int W,
+                                                          int PD, float lo, float hi) {
+  const int OH = H - 2 * PD, OW = W - 2 * PD;
+  const size_t total = (size_t)B * OH * OW;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = (int)(idx % OW); size_t t = idx / OW;
+  const int y = (int)(t % OH); const int b = (int)(t / OH);
+  const size_t plane = (size_t)H * W;
+  const float* s = src + (size_t)b * C * plane + (size_t)(y + PD) * W + (x + PD);
+  uint8_t* d = dst + idx * C;
+  const float range = __fsub_rn(hi, lo);
+  for (int c = 0; c < C; ++c) {
+    float v = fminf(fmaxf(__ldg(s + c * plane), lo), hi);
+    v = __fdiv_rn(__fsub_rn(v, lo), range);
+    d[c] = (uint8_t)rintf(__fmul_rn(v, 255.0f));
+  }
+}
+
+int launch_to_image_u8(const ucdir_op_t& op, cudaStream_t st, bool dry) {
+  const int B = op.i[UCDIR_IMG_I_B], C = op.i[UCDIR_IMG_I_C], H = op.i[UCDIR_IMG_I_H], W = op.i[UCDIR_IMG_I_W], PD = op.i[UCDIR_IMG_I_PD];
+  if (!op.p[UCDIR_IMG_P_SRC] || !op.p[UCDIR_IMG_P_DST]) { set_error("to_image_u8: null pointer"); return -1; }
+  if (B <= 0 || C <= 0 || C > 4 || H <= 0 || W <= 0 || PD < 0 || 2 * PD >= H || 2 * PD >= W) { set_error("to_image_u8: bad dims"); return -1; }
+  if (!(op.f[UCDIR_IMG_F_MAX] > op.f[UCDIR_IMG_F_MIN])) { set_error("to_image_u8: MAX must exceed MIN"); return -1; }
+  if (dry) return 0;
+  const size_t total = (size_t)B * (H - 2 * PD) * (W - 2 * PD);
+  to_image_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)op.p[UCDIR_IMG_P_SRC], (uint8_t*)op.p[UCDIR_IMG_P_DST], B, C, H, W,
+                                                                    PD, op.f[UCDIR_IMG_F_MIN], op.f[UCDIR_IMG_F_MAX]);
+  ++g_launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // GroupNorm with G > 1 groups (the SR3-style FiLM ResnetBlock, model/ucdir.py:75-100; the DY3h path uses G = 1 and
 // folds its statistics into the convolution kernels instead).  fp32 NHWC.
 //   gn_stats_f32:  STATS[b][g] = {sum, sum of squares} over H*W x C/G elements, one CTA per (sample, group)

@@ -272,3 +272,29 @@ class ResiGaussianGuideDY(GaussianDiffusion):
         initx = self.predictor(x_in)
         self.pre_initx = initx
         return self.p_sample_loop(x_in, continous, kwargs={"guide": initx}) + initx
+
+
+class ResiGaussianGuideDY_de(GaussianDiffusion):
+    """model/diffusion.py:481-523: residual diffusion whose guidance is the degraded input itself ("degraded guidance"),
+    not the initial prediction.  Same parameters and state_dict keys as ResiGaussianGuideDY."""
+
+    def __init__(self, denoise_fn, image_size, channels=3, loss_type="l1", conditional=True, schedule_opt=None):
+        super().__init__(denoise_fn, image_size, channels, loss_type, conditional, schedule_opt)
+        self.predictor = UNetSeeInDark()
+
+    @torch.no_grad()
+    def super_resolution(self, x_in, continous=False):
+        """model/diffusion.py:518-523."""
+        initx = self.predictor(x_in)
+        self.pre_initx = initx
+        return self.p_sample_loop(x_in, continous, kwargs={"guide": x_in}) + initx
+
+
+class ResiGaussianGuideDY_initxloss(ResiGaussianGuideDY):
+    """model/diffusion.py:528-571: differs from ResiGaussianGuideDY only in its training loss (an extra L1 term on the
+    initial prediction); inference (`super_resolution`, :567-571) is identical except that `pre_initx` is not recorded."""
+
+    @torch.no_grad()
+    def super_resolution(self, x_in, continous=False):
+        initx = self.predictor(x_in)
+        return self.p_sample_loop(x_in, continous, kwargs={"guide": initx}) + initx
