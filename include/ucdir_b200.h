@@ -189,7 +189,8 @@ enum ucdir_tc_ptr {
   UCDIR_TC_P_SRC0 = 0, UCDIR_TC_P_SRC1 = 1, UCDIR_TC_P_W = 2, UCDIR_TC_P_TB = 3, UCDIR_TC_P_TG = 4,
   UCDIR_TC_P_STATS0 = 5, UCDIR_TC_P_STATS1 = 6, UCDIR_TC_P_RES = 7, UCDIR_TC_P_ATT = 8, UCDIR_TC_P_ATTW = 9,
   UCDIR_TC_P_DST = 10, UCDIR_TC_P_DST_STATS = 11,
-  UCDIR_TC_P_DST2 = 12     /* bf16 [B][NTOT - T_COL0][T_LD]: columns >= T_COL0 are stored transposed here (attention V^T) */
+  UCDIR_TC_P_DST2 = 12,    /* bf16 [B][NTOT - T_COL0][T_LD]: columns >= T_COL0 are stored transposed here (attention V^T) */
+  UCDIR_TC_P_SRC_GAMMA = 13, UCDIR_TC_P_SRC_BETA = 14   /* fp32 [C0]: affine of the SRC_GN_SWISH source transform */
 };
 enum ucdir_tc_int {
   UCDIR_TC_I_B = 0, UCDIR_TC_I_H = 1, UCDIR_TC_I_W = 2, UCDIR_TC_I_SRC_H = 3, UCDIR_TC_I_SRC_W = 4,
@@ -212,8 +213,13 @@ enum ucdir_tc_int {
   UCDIR_TC_I_SPS3 = 40,                          /* 1: three K slabs (filter taps) per pipeline stage for the small-N layers */
   UCDIR_TC_I_NO_CTAB = 42,                       /* 1: do not cache the folded-GroupNorm additive table of the current image in shared memory */
   UCDIR_TC_I_ROW3 = 41,                          /* 1: row tiles of dense 3x3 convs share one 130-pixel activation row among the three horizontal taps */
+  UCDIR_TC_I_SRC_GN_SWISH = 44,                  /* 1: the source is first mapped through Swish(GroupNorm(1,C0)(SRC0)) (affine SRC_GAMMA / SRC_BETA, statistics
+                                                  * STATS0, result rounded to bf16) -- final_conv, model/ucdir.py:266-268, whose Swish keeps the norm from being
+                                                  * folded into the weights.  Applied to the landed halo box in shared memory (ucdir_fhalo.cu); needs a 3x3
+                                                  * stride-1 conv of C0 <= 128 channels with GN = 0, NT = NTOT = 16 and DST_F32 = 1 */
   UCDIR_TC_I_HALO = 43                           /* 1: halo schedule where it applies (grouped mix convs, C = 64 / 128 / 256): one 10 x 18 pixel TMA box per
-                                                  * 8 x 16 pixel tile serves all nine taps, weights stay resident in shared memory (ucdir_mix.cu) */
+                                                  * 8 x 16 pixel tile serves all nine taps, weights stay resident in shared memory (ucdir_mix.cu); 3x3 convs with 64 / 128 output
+                                                  * channels: super tiles (ucdir_dhalo.cu) */
 };
 enum ucdir_tc_flt { UCDIR_TC_F_EPS = 0, UCDIR_TC_F_ALPHA = 1 /* 0 = 1.0 */ };
 
@@ -272,8 +278,8 @@ int ucdir_op_sizeof(void);
 const char* ucdir_last_error(void);
 /* Number of kernel launches issued by this process through ucdir_run_ops since load. */
 /* Which kernel a UCDIR_OP_TC_CONV record is routed to (no device needed): 0 = streamed (tc_conv_kernel), 1 = halo schedule of
- * the integration-module convs (ucdir_mix.cu), 2 = halo / super-tile schedule of the Cout = 64 / 128 3x3 convs (ucdir_dhalo.cu);
- * negative = not a TC_CONV op. */
+ * the integration-module convs (ucdir_mix.cu), 2 = halo / super-tile schedule of the Cout = 64 / 128 3x3 convs (ucdir_dhalo.cu),
+ * 3 = fused GroupNorm + Swish + conv of final_conv (ucdir_fhalo.cu); negative = not a TC_CONV op. */
 int ucdir_tc_schedule(const ucdir_op_t* op);
 long long ucdir_launch_count(void);
 /* Device capability probe: returns 0 iff the current device is sm_100 (B200). */

@@ -326,6 +326,15 @@ def emu_tc_conv(op, mem):
     cstride = g("SRC_CSTRIDE") or C0
     x = mem.view(_p(op, "UCDIR_TC_P_SRC0"), ((B * sH * sW - 1) * cstride + C0,), bf)
     x = torch.as_strided(x, (B, sH, sW, C0), (sH * sW * cstride, sW * cstride, cstride, 1)).float()
+    if g("SRC_GN_SWISH"):                                        # final_conv: Swish(GroupNorm(x)) on the source, rounded to bf16
+        s0 = mem.view(_p(op, "UCDIR_TC_P_STATS0"), (B, 2), torch.float64)
+        cnt = float(C0 * sH * sW)
+        mean = s0[:, 0] / cnt
+        var = (s0[:, 1] / cnt - mean * mean).clamp_min(0)
+        rstd = (1.0 / torch.sqrt(var + eps)).float().view(B, 1, 1, 1)
+        gam = mem.view(_p(op, "UCDIR_TC_P_SRC_GAMMA"), (C0,)); bet = mem.view(_p(op, "UCDIR_TC_P_SRC_BETA"), (C0,))
+        a = rstd * gam.view(1, 1, 1, -1)
+        x = swish(x * a + (bet.view(1, 1, 1, -1) - a * mean.float().view(B, 1, 1, 1))).to(bf).float()
     wb = g("W_BATCHED")
     if C1:
         x = torch.cat([x, mem.view(_p(op, "UCDIR_TC_P_SRC1"), (B, sH, sW, C1), bf).float()], dim=-1)

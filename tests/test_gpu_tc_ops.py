@@ -136,6 +136,31 @@ def test_tc_dense_halo(cfg):
     assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 64), (1, 128, 128, 64), (3, 40, 72, 64), (2, 24, 36, 128)])
+def test_tc_final_conv_fused_gn_swish(B, H, W, C):
+    """csrc/ucdir_fhalo.cu: final_conv (GroupNorm -> Swish -> conv3x3 to 3 fp32 channels, model/ucdir.py:266-268) with the
+    norm + activation applied to the landed halo box in shared memory; out-of-image pixels must stay zero padding."""
+    g = torch.Generator().manual_seed(B * H + C)
+    c = Case()
+    c.add("x", (rnd(g, B, H, W, C) * 0.9 + 0.2).to(BF))
+    w = rnd(g, 3, C, 3, 3, scale=1.0 / np.sqrt(C * 9))
+    bias = rnd(g, 3, scale=0.1)
+    wp, tb, _ = E.pack_tc_dense(w, bias, 16)
+    c.add("w", wp).add("tb", tb).add("gamma", 1 + 0.3 * rnd(g, C)).add("beta", 0.2 * rnd(g, C)).add("s0", stats_of(c.t["x"]))
+    c.add("dst", torch.zeros(B, H, W, 4))
+
+    def build(t):
+        ol = E.OpList()
+        E._tc_op(ol, src0=act(t["x"], C, H, W, t["s0"]), w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), dst=act(t["dst"], 4, H, W),
+                 ntot=16, B=B, nt=16, dst_f32=1, ncol_valid=3, src_gn_swish=1, src_gamma=t["gamma"].data_ptr(),
+                 src_beta=t["beta"].data_ptr())
+        return ol
+    assert _lib.tc_schedule(build(c.on("cpu")).array()[0]) == 3
+    host, dev = run_both(c, build)
+    assert_close(dev["dst"][..., :3], host["dst"][..., :3], "eps")
+    assert float(dev["dst"][..., 3].abs().max()) == 0.0          # the pad column is not written
+
+
 @pytest.mark.parametrize("halo", [0, 1], ids=["streamed", "halo"])
 @pytest.mark.parametrize("C,B,H,W", [(64, 2, 16, 16), (128, 1, 24, 16), (256, 3, 8, 8), (512, 3, 8, 8), (64, 1, 128, 128),
                                      (128, 3, 64, 64), (256, 3, 32, 32), (64, 2, 36, 20), (256, 1, 18, 18)])

@@ -151,6 +151,7 @@ const char* ucdir_last_error(void) { return ucdir::g_err; }
 long long ucdir_launch_count(void) { return ucdir::g_launches; }
 int ucdir_tc_schedule(const ucdir_op_t* op) {
   if (!op || op->kind != UCDIR_OP_TC_CONV) return -1;
+  if (ucdir::tc_final_halo_applies(*op)) return 3;
   if (ucdir::tc_mix_halo_applies(*op)) return 1;
   if (ucdir::tc_dense_halo_applies(*op)) return 2;
   return 0;

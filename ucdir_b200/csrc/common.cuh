@@ -56,6 +56,8 @@ int launch_scatter(const ucdir_op_t& op, cudaStream_t st, bool dry);
 int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry);
 bool tc_mix_halo_applies(const ucdir_op_t& op);
 int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st);
+bool tc_final_halo_applies(const ucdir_op_t& op);
+int launch_tc_final_halo(const ucdir_op_t& op, cudaStream_t st);
 bool tc_dense_halo_applies(const ucdir_op_t& op);
 int launch_tc_dense_halo(const ucdir_op_t& op, cudaStream_t st);
 // setmaxnreg moves registers between warpgroups through a per-CTA pool that holds only what the CTA itself released:

@@ -727,7 +727,12 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   const long mt = (long)p.tiles_x * p.tiles_y * tiles_n;
   if (mt > 0x7fffffffL) { set_error("tc_conv: too many M tiles"); return -2; }
   p.m_tiles = (int)mt; p.tiles_n = tiles_n;
+  if (op.i[UCDIR_TC_I_SRC_GN_SWISH] && !tc_final_halo_applies(op)) {
+    set_error("tc_conv: SRC_GN_SWISH needs a 3x3 stride-1 conv of <= 128 channels (multiple of 64) with GN = 0, NT = NTOT = 16, DST_F32 = 1, SRC_GAMMA / SRC_BETA / STATS0");
+    return -2;
+  }
   if (dry) return 0;
+  if (tc_final_halo_applies(op)) return launch_tc_final_halo(op, st);  // GroupNorm + Swish + conv of final_conv in one kernel (ucdir_fhalo.cu)
   if (tc_mix_halo_applies(op)) return launch_tc_mix_halo(op, st);      // halo / weight-stationary form of the mix convs (ucdir_mix.cu)
   if (tc_dense_halo_applies(op)) return launch_tc_dense_halo(op, st);  // halo / super-tile form of the Cout = 64 / 128 3x3 convs (ucdir_dhalo.cu)
   // ROW3: row tiles (128 px x 1 row) of a dense 3x3 stride-1 conv load one 130-pixel activation row per filter row and
@@ -791,19 +796,38 @@ __global__ void __launch_bounds__(256) gn_apply_bf16_kernel(const __nv_bfloat16*
   const int b = blockIdx.y;
   const GnScalars sc = gn_scalars(stats, nullptr, b, count, eps);
   const size_t n8 = per_sample / 8;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // 8 channels per thread and iteration; when the grid stride is a multiple of the row length every iteration of a thread
+  // sees the same 8 channels, so their scale / shift are computed once (16 scalar loads per 16 bytes of data otherwise)
+  const bool invariant = (stride * 8) % (size_t)C == 0;
+  float sa[8], sb[8];
+  auto load_affine = [&](int c) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sa[k] = sc.rstd * __ldg(gamma + c + k);
+      sb[k] = __ldg(beta + c + k) - sa[k] * sc.mean;
+    }
+  };
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (invariant && i0 < n8) load_affine((int)((i0 * 8) % C));
+  for (size_t i = i0; i < n8; i += stride) {
     const size_t e = i * 8;
-    const int c = (int)(e % C);
+    if (!invariant) load_affine((int)(e % C));
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (size_t)b * per_sample + e));
     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
     __align__(16) __nv_bfloat162 o2[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float2 f = __bfloat1622float2(h2[k]);
-      const float a0 = sc.rstd * __ldg(gamma + c + 2 * k), a1 = sc.rstd * __ldg(gamma + c + 2 * k + 1);
-      f.x = f.x * a0 + (__ldg(beta + c + 2 * k) - a0 * sc.mean);
-      f.y = f.y * a1 + (__ldg(beta + c + 2 * k + 1) - a1 * sc.mean);
-      if (swish) { f.x = swish_f(f.x); f.y = swish_f(f.y); }
+      f.x = f.x * sa[2 * k] + sb[2 * k];
+      f.y = f.y * sa[2 * k + 1] + sb[2 * k + 1];
+      if (swish) {      // x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op; the result is rounded to bf16 (see ucdir_dhalo.cu)
+        const float hx = 0.5f * f.x, hy = 0.5f * f.y;
+        float tx, ty;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(hx));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(hy));
+        f.x = fmaf(hx, tx, hx); f.y = fmaf(hy, ty, hy);
+      }
       o2[k] = __floats2bfloat162_rn(f.x, f.y);
     }
     *reinterpret_cast<uint4*>(dst + (size_t)b * per_sample + e) = *reinterpret_cast<const uint4*>(o2);

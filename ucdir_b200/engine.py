@@ -396,7 +396,8 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
            att: int = 0, attw: int = 0, attw_stride: int = 0, dst_f32: int = 0, ncol_valid: int = 0, dst_up: int = 0,
            dst_py: int = 0, dst_px: int = 0, eps: float = 1e-5, kb: int = 0, nsplit: int = 1, src_cstride: int = 0,
            w_batched: int = 0, w_rowstride: int = 0, w_batchstride: int = 0, alpha: float = 0.0, dst2: int = 0, t_col0: int = 0,
-           t_ld: int = 0, w_rows: int = 0, row3: Optional[int] = None, halo: Optional[int] = None):
+           t_ld: int = 0, w_rows: int = 0, row3: Optional[int] = None, halo: Optional[int] = None, src_gn_swish: int = 0,
+           src_gamma: int = 0, src_beta: int = 0):
     H, W = (dst.H // 2, dst.W // 2) if dst_up else (dst.H, dst.W)
     p = {"UCDIR_TC_P_SRC0": src0.ptr, "UCDIR_TC_P_W": w, "UCDIR_TC_P_TB": tb, "UCDIR_TC_P_DST": dst.ptr}
     if src1 is not None: p["UCDIR_TC_P_SRC1"] = src1.ptr
@@ -421,6 +422,9 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
          "UCDIR_TC_I_T_COL0": t_col0, "UCDIR_TC_I_T_LD": t_ld, "UCDIR_TC_I_W_ROWS": w_rows,
          "UCDIR_TC_I_ROW3": _TC_ROW3 if row3 is None else row3, "UCDIR_TC_I_HALO": _TC_HALO if halo is None else halo}
     if dst2: p["UCDIR_TC_P_DST2"] = dst2
+    if src_gn_swish:
+        p["UCDIR_TC_P_SRC_GAMMA"], p["UCDIR_TC_P_SRC_BETA"], p["UCDIR_TC_P_STATS0"] = src_gamma, src_beta, src0.stats
+        i["UCDIR_TC_I_SRC_GN_SWISH"] = 1
     ol.add("UCDIR_OP_TC_CONV", p, i, {"UCDIR_TC_F_EPS": eps, "UCDIR_TC_F_ALPHA": alpha})
 
 
@@ -881,18 +885,25 @@ class UNetEngine:
                 skip = feats.pop()
                 skip.keep = False
                 x = block(name, layer, x, skip)
-        # final_conv: GN -> Swish -> conv (model/ucdir.py:266-268); Swish sits between the norm and the conv, so
-        # the norm cannot be folded: one elementwise pass, then a 16-column (3 valid) tensor-core conv to fp32 eps
-        xn = bld.new(x.C, x.H, x.W, with_stats=False)
-        ol.add("UCDIR_OP_GN_APPLY_BF16",
-               {"UCDIR_GNA_P_SRC": x.ptr, "UCDIR_GNA_P_DST": xn.ptr, "UCDIR_GNA_P_GAMMA": ws.ptr("final.norm.w"),
-                "UCDIR_GNA_P_BETA": ws.ptr("final.norm.b"), "UCDIR_GNA_P_STATS": x.stats},
-               {"UCDIR_GNA_I_B": BT, "UCDIR_GNA_I_HW": x.H * x.W, "UCDIR_GNA_I_C": x.C, "UCDIR_GNA_I_SWISH": 1}, {0: 1e-5})
-        bld.release(x)
+        # final_conv: GN -> Swish -> conv (model/ucdir.py:266-268); Swish sits between the norm and the conv, so the norm
+        # cannot be folded into the weights.  Halo schedule: ONE kernel applies GN + Swish to the landed activation box in
+        # shared memory and runs the 16-column (3 valid) conv to fp32 eps (csrc/ucdir_fhalo.cu).  Otherwise: one elementwise
+        # pass, then the streamed conv.
         eps_dst = Act(_PtrBuf(eps_ptr), 4, TH, TW, 0, keep=True)      # type: ignore[arg-type]
-        _tc_op(ol, src0=xn, w=ws.ptr("final.tcw"), tb=ws.ptr("final.tb"), dst=eps_dst, ntot=16, B=BT, nt=16, dst_f32=1,
-               ncol_valid=m.cfg["out_channel"])
-        bld.release(xn)
+        if _TC_HALO and x.C % 64 == 0 and x.C <= 128:
+            _tc_op(ol, src0=x, w=ws.ptr("final.tcw"), tb=ws.ptr("final.tb"), dst=eps_dst, ntot=16, B=BT, nt=16, dst_f32=1,
+                   ncol_valid=m.cfg["out_channel"], src_gn_swish=1, src_gamma=ws.ptr("final.norm.w"), src_beta=ws.ptr("final.norm.b"))
+            bld.release(x)
+        else:
+            xn = bld.new(x.C, x.H, x.W, with_stats=False)
+            ol.add("UCDIR_OP_GN_APPLY_BF16",
+                   {"UCDIR_GNA_P_SRC": x.ptr, "UCDIR_GNA_P_DST": xn.ptr, "UCDIR_GNA_P_GAMMA": ws.ptr("final.norm.w"),
+                    "UCDIR_GNA_P_BETA": ws.ptr("final.norm.b"), "UCDIR_GNA_P_STATS": x.stats},
+                   {"UCDIR_GNA_I_B": BT, "UCDIR_GNA_I_HW": x.H * x.W, "UCDIR_GNA_I_C": x.C, "UCDIR_GNA_I_SWISH": 1}, {0: 1e-5})
+            bld.release(x)
+            _tc_op(ol, src0=xn, w=ws.ptr("final.tcw"), tb=ws.ptr("final.tb"), dst=eps_dst, ntot=16, B=BT, nt=16, dst_f32=1,
+                   ncol_valid=m.cfg["out_channel"])
+            bld.release(xn)
         self.last_stat_slots = bld.next_slot
         return ol
 
