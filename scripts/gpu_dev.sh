@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 echo "== tc op tests"
-timeout ${T_TESTS:-240} python -m pytest tests/test_gpu_tc_ops.py -q -x --timeout 60 --timeout-method thread ${PYTEST_ARGS:--k halo} > gpurun_out/pytest_tc.log 2>&1
+timeout ${T_TESTS:-240} python -m pytest tests/test_gpu_tc_ops.py -q -x --timeout 60 --timeout-method thread ${PYTEST_ARGS:--k "halo or final"} > gpurun_out/pytest_tc.log 2>&1
 rc=$?; echo "rc=$rc"; grep -v "mbarrier timeout" gpurun_out/pytest_tc.log | tail -${TAIL:-40} | cut -c1-600
 grep "mbarrier timeout" gpurun_out/pytest_tc.log | sed 's/thread [0-9]*/thread N/' | sort | uniq -c | head -20
 if [ $rc -ne 0 ] && [ "${FORCE_BENCH:-0}" != "1" ]; then exit 0; fi
