@@ -489,6 +489,7 @@ class UNetEngine:
         self.ws: Optional[WeightStore] = None
         self.blocks: List[Tuple[str, object]] = []
         self._sessions: Dict[tuple, "Session"] = {}
+        self._geo_cache: Dict[tuple, Geometry] = {}
         self.precision = os.environ.get("UCDIR_PRECISION", "fp32")    # "fp32" (parity path) | "bf16" (tcgen05 path)
         if self.precision not in ("fp32", "bf16"):
             raise ValueError("UCDIR_PRECISION must be fp32 or bf16")
@@ -924,10 +925,17 @@ class UNetEngine:
         return s
 
     def default_geometry(self, B, h, w) -> Geometry:
+        """model/ucdir.py:295-307 dispatch.  Memoised: building the tile tables costs ~2.5 ms of numpy, which a stateless
+        p_sample() per step paid on every call (a fifth of a bf16 step; far more on a loaded host)."""
         m = self.m
-        if h * w > m.tile_trigger:
-            return geometry_tiled(B, h, w, m.tile_skip, m.tile_padding)
-        return geometry_direct(B, h, w)
+        key = (B, h, w, m.tile_trigger, m.tile_skip, m.tile_padding)
+        hit = self._geo_cache.get(key)
+        if hit is None:
+            if len(self._geo_cache) > 16:
+                self._geo_cache.clear()
+            hit = geometry_tiled(B, h, w, m.tile_skip, m.tile_padding) if h * w > m.tile_trigger else geometry_direct(B, h, w)
+            self._geo_cache[key] = hit
+        return hit
 
     # ---- reference-signature entry points ------------------------------------------------
     def forward(self, x, time, guide):
