@@ -41,6 +41,7 @@ EXPORTS = ["ucdir_run_ops", "ucdir_check_ops", "ucdir_abi_version", "ucdir_op_si
            "ucdir_graph_launch", "ucdir_graph_destroy", "ucdir_tc_schedule"]
 
 _lib = None
+_device_ok = False
 
 
 class UcdirLibraryError(RuntimeError):
@@ -49,7 +50,7 @@ class UcdirLibraryError(RuntimeError):
 
 def load(require_device=True):
     """Load the shared library (building is __graft_entry__.build()'s / ucdir_b200.build's job)."""
-    global _lib
+    global _lib, _device_ok
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise UcdirLibraryError(
@@ -83,10 +84,13 @@ def load(require_device=True):
         if lib.ucdir_op_sizeof() != ctypes.sizeof(Op):
             raise UcdirLibraryError("ucdir_op_t size mismatch: C %d vs ctypes %d" % (lib.ucdir_op_sizeof(), ctypes.sizeof(Op)))
         _lib = lib
-    if require_device:
+    if require_device and not _device_ok:
+        # once per process: ucdir_device_ok() is a cudaGetDeviceProperties call (milliseconds), and this function sits on the
+        # path of every stateless p_sample() / forward() call
         rc = _lib.ucdir_device_ok()
         if rc != 0:
             raise UcdirLibraryError("ucdir_b200 needs a B200 (sm_100) CUDA device: %s" % last_error())
+        _device_ok = True
     return _lib
 
 
