@@ -14,9 +14,13 @@
 //   for C = 256) resident in shared memory and walks the M tiles of its unit range; units are ordered set-major.
 //   L2 -> SM traffic per 128 pixels drops from 288 KB to the 23 KB halo box.
 // * 16 epilogue warps (four per TMEM lane quadrant); warp j of a quadrant owns the fixed 64-column stripe j of every
-//   256-column item = 8 output channels: two tcgen05.ld.x32, release the accumulator, then
-//   out[c] = Swish(sum_s aw[s] * (rstd*acc[c*8+s] + cadd[cls][c*8+s])) + res[c] with the folded-GroupNorm additive table
-//   of the current (image, set) cached in shared memory, 16-byte residual loads and stores.
+//   256-column item = 8 output channels.  TMEM is read 16 columns at a time, the load of step k+1 in flight during the math
+//   of step k;  out[c] = Swish(sum_s aw[s] * (rstd*acc[c*8+s] + cadd[cls][c*8+s])) + res[c], with the folded-GroupNorm
+//   additive table of the current (image, set) in shared memory (read one step ahead), the guidance row of the next tile
+//   prefetched into registers, the residual row of the next item staged by cp.async, Swish as h + h*tanh(h) (one MUFU op).
+// * measured (ncu, profiles/r01_ncu_halo_kernels.md): an M = 128, N = 128, K = 16 MMA from shared-memory operands takes
+//   ~125 cycles, not its 64 tensor cycles -- operand fetch (A 4 KB + B 4 KB) runs at ~64 B/clk per SM -- so the C = 64 item
+//   costs >= 18 x 125 = 2250 cycles; the epilogue was brought from ~3200 to ~2700 cycles per item to sit next to that.
 //
 // Packed weights, TB / TG tables and every other operand are those of the streamed form (engine.py:pack_tc_grouped).
 #include <cuda.h>

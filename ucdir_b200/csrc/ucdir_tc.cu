@@ -1,4 +1,8 @@
-// bf16 tensor-core path (sm_100a): implicit-GEMM convolution on tcgen05 with TMA-staged NHWC tiles.
+// bf16 tensor-core path (sm_100a): implicit-GEMM convolution on tcgen05 with TMA-staged NHWC tiles -- the STREAMED form (one
+// activation slab + one weight slab per filter tap and channel chunk).  launch_tc_conv routes three op families to dedicated
+// halo-schedule kernels instead (ucdir_tc_schedule() tells which): the integration-module convs with C <= 256 (ucdir_mix.cu),
+// the 3x3 convs with 64 / 128 output channels incl. the in-conv (ucdir_dhalo.cu) and final_conv with its GroupNorm + Swish
+// (ucdir_fhalo.cu).  Everything else -- strided, 1x1, 2x2-phase upsample, >= 256-column and attention GEMMs -- runs here.
 //
 //   D[128 pixels x NT channels] (fp32, TMEM)  +=  A[128 pixels x KC] (bf16, smem)  *  B[NT x KC]^T (bf16, smem)
 //
