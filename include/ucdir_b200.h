@@ -190,7 +190,11 @@ enum ucdir_tc_ptr {
   UCDIR_TC_P_STATS0 = 5, UCDIR_TC_P_STATS1 = 6, UCDIR_TC_P_RES = 7, UCDIR_TC_P_ATT = 8, UCDIR_TC_P_ATTW = 9,
   UCDIR_TC_P_DST = 10, UCDIR_TC_P_DST_STATS = 11,
   UCDIR_TC_P_DST2 = 12,    /* bf16 [B][NTOT - T_COL0][T_LD]: columns >= T_COL0 are stored transposed here (attention V^T) */
-  UCDIR_TC_P_SRC_GAMMA = 13, UCDIR_TC_P_SRC_BETA = 14   /* fp32 [C0]: affine of the SRC_GN_SWISH source transform */
+  UCDIR_TC_P_SRC_GAMMA = 13, UCDIR_TC_P_SRC_BETA = 14,  /* fp32 [C0]: affine of the SRC_GN_SWISH source transform */
+  /* RES_FUSED (exclusive with SRC_GN_SWISH; W2 / TB2 share its slots): the block's 1x1 res_conv of the same input */
+  UCDIR_TC_P_W2 = 13,      /* bf16 [NTOT][C0 + C1], K-major */
+  UCDIR_TC_P_TB2 = 14,     /* fp32 [NTOT] bias */
+  UCDIR_TC_P_DST_RES = 15  /* bf16 [B][H][W][DST_RES_C] */
 };
 enum ucdir_tc_int {
   UCDIR_TC_I_B = 0, UCDIR_TC_I_H = 1, UCDIR_TC_I_W = 2, UCDIR_TC_I_SRC_H = 3, UCDIR_TC_I_SRC_W = 4,
@@ -217,6 +221,10 @@ enum ucdir_tc_int {
                                                   * STATS0, result rounded to bf16) -- final_conv, model/ucdir.py:266-268, whose Swish keeps the norm from being
                                                   * folded into the weights.  Applied to the landed halo box in shared memory (ucdir_fhalo.cu); needs a 3x3
                                                   * stride-1 conv of C0 <= 128 channels with GN = 0, NT = NTOT = 16 and DST_F32 = 1 */
+  UCDIR_TC_I_RES_FUSED = 45,                     /* 1: also compute DST_RES = conv1x1(concat(SRC0, SRC1); W2) + TB2 (model/ucdir.py:118,140: res_conv(x) of the
+                                                  * same un-normalised input as conv1) from the centre-tap view of the halo box already in shared memory;
+                                                  * needs the 64-channel halo schedule (ucdir_dhalo.cu), refused otherwise */
+  UCDIR_TC_I_DST_RES_C = 46,                     /* channels per pixel row of DST_RES */
   UCDIR_TC_I_HALO = 43                           /* 1: halo schedule where it applies (grouped mix convs, C = 64 / 128 / 256): one 10 x 18 pixel TMA box per
                                                   * 8 x 16 pixel tile serves all nine taps, weights stay resident in shared memory (ucdir_mix.cu); 3x3 convs with 64 / 128 output
                                                   * channels: super tiles (ucdir_dhalo.cu) */

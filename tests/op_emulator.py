@@ -370,6 +370,12 @@ def emu_tc_conv(op, mem):
                 cb = (gi * Cg) // cg_eff * cg_eff if groups > 1 else 0
                 rows = slice(gi * Ng, (gi + 1) * Ng)
                 acc[..., rows] += patch[..., cb:cb + cg_eff] @ wp[rows, ty * ntx + tx].t()
+    if g("RES_FUSED"):                                           # the block's 1x1 res_conv of the same (un-normalised) input
+        w2 = mem.view(_p(op, "UCDIR_TC_P_W2"), (Ntot, Cin), bf).float()
+        b2 = mem.view(_p(op, "UCDIR_TC_P_TB2"), (Ntot,))
+        rC = g("DST_RES_C")
+        dres = mem.view(_p(op, "UCDIR_TC_P_DST_RES"), (B, H, W, rC), bf)
+        dres[..., :Ntot] = (x @ w2.t() + b2.view(1, 1, 1, -1)).to(bf)
     tb = mem.view(_p(op, "UCDIR_TC_P_TB"), (ncls if gn else 1, Ntot))
     if gn:
         s0 = mem.view(_p(op, "UCDIR_TC_P_STATS0"), (B, 2), torch.float64).clone()

@@ -63,7 +63,7 @@ def stats_of(x_bf16):
     return torch.stack([v.sum(1), (v * v).sum(1)], dim=1).contiguous()
 
 
-def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1, row3=0, halo=0, kc=64):
+def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1, row3=0, halo=0, kc=64, fuse_res=False):
     g = torch.Generator().manual_seed(seed)
     sH, sW = H * stride, W * stride
     c = Case()
@@ -87,10 +87,14 @@ def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1, row3=0,
     if res:
         c.add("res", rnd(g, B, H, W, Cout).to(BF))
     c.add("dst", torch.zeros(B, H, W, Cout, dtype=BF)).add("dstats", torch.zeros(B, 2, dtype=torch.float64))
+    if fuse_res:                                   # the block's 1x1 res_conv of the same input, computed by the same launch
+        w2p, tb2, _ = E.pack_tc_dense(rnd(g, Cout, Cin, 1, 1, scale=1.0 / np.sqrt(Cin)), rnd(g, Cout, scale=0.1), nt)
+        c.add("w2", w2p).add("tb2", tb2).add("dres", torch.zeros(B, H, W, Cout, dtype=BF))
 
     def build(t):
         ol = E.OpList()
-        E._tc_op(ol, src0=act(t["x0"], C0, sH, sW, t.get("s0")), src1=act(t["x1"], C1, sH, sW, t.get("s1")) if C1 else None,
+        extra = dict(w2=t["w2"].data_ptr(), tb2=t["tb2"].data_ptr(), dst_res=act(t["dres"], Cout, H, W)) if fuse_res else {}
+        E._tc_op(ol, **extra, src0=act(t["x0"], C0, sH, sW, t.get("s0")), src1=act(t["x1"], C1, sH, sW, t.get("s1")) if C1 else None,
                  w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), tg=t["tg"].data_ptr() if "tg" in t else 0, gn=1 if gn else 0,
                  ncls=9 if (gn and ks == 3) else 1, nty=ks, ntx=ks, oy0=-(ks // 2), ox0=-(ks // 2), stride=stride, act=act_,
                  res=act(t["res"], Cout, H, W) if res else None, dst=act(t["dst"], Cout, H, W, t["dstats"]), ntot=Cout, B=B, nt=nt,
@@ -125,7 +129,11 @@ def test_tc_dense(cfg):
     dict(seed=26, B=5, H=48, W=96, C0=64, C1=0, Cout=64, act_=0),   # 90 items: most CTAs get one, images change inside a CTA's range
     dict(seed=27, B=2, H=40, W=72, C0=16, C1=0, Cout=64, gn=False, act_=0, kc=16),     # the in-conv: 32-byte pixel rows, no GroupNorm
     dict(seed=28, B=1, H=128, W=128, C0=16, C1=0, Cout=64, gn=False, act_=0, kc=16),
-], ids=lambda c: "C%d+%d_%d_%dx%dx%d" % (c["C0"], c["C1"], c["Cout"], c["B"], c["H"], c["W"]))
+    dict(seed=29, B=2, H=40, W=72, C0=64, C1=64, Cout=64, fuse_res=True),      # + fused 1x1 res_conv, 2 tiles per item
+    dict(seed=30, B=1, H=128, W=128, C0=128, C1=64, Cout=64, fuse_res=True),
+    dict(seed=31, B=3, H=64, W=64, C0=256, C1=128, Cout=128, fuse_res=True),    # 1 tile per item
+    dict(seed=32, B=2, H=24, W=20, C0=64, C1=0, Cout=128, fuse_res=True),
+], ids=lambda c: "C%d+%d_%d_%dx%dx%d%s" % (c["C0"], c["C1"], c["Cout"], c["B"], c["H"], c["W"], "_res" if c.get("fuse_res") else ""))
 def test_tc_dense_halo(cfg):
     """csrc/ucdir_dhalo.cu: super tiles of 256/Cout 8x16-pixel tiles, one halo box per 64-channel chunk serves all nine taps."""
     cfg = dict(dict(ks=3, gn=True, act_=1, res=False, halo=1), **cfg)
@@ -134,6 +142,9 @@ def test_tc_dense_halo(cfg):
     host, dev = run_both(c, build)
     assert_close(dev["dst"], host["dst"], "dst")
     assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
+    if cfg.get("fuse_res"):
+        assert float(host["dres"].abs().max()) > 0.1
+        assert_close(dev["dres"], host["dres"], "fused res_conv")
 
 
 @pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 64), (1, 128, 128, 64), (3, 40, 72, 64), (2, 24, 36, 128)])

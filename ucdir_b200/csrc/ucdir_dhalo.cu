@@ -28,10 +28,11 @@ struct DhParams {
   const double* stats0; const double* stats1;
   const float* tb; const float* tg;
   __nv_bfloat16* dst; double* dst_stats;
+  const float* tb2; __nv_bfloat16* dst2;                 // RES: bias and destination of the fused 1x1 res_conv
   int B, H, W;
   int nchunk, c0_chunks;
   int tiles_x, tiles_y, n_items;
-  int gn, act, dstC, dstCoff, st32;
+  int gn, act, dstC, dstCoff, st32, dst2C, st32_2;
   double gn_count; float eps;
 };
 
@@ -41,12 +42,16 @@ constexpr int DH_REGS_LOW = 40, DH_REGS_HIGH = 104;      // see MX_REGS_LOW / MX
 
 // KC = channels per chunk = one pixel row of the halo box: 64 (128-byte rows, 128B swizzle) or 16 (the in-conv's zero-padded
 // 6 -> 16 input channels: 32-byte rows, 32B swizzle, one K step per tap)
-template <int NT, int KC>
+// RES = 1: the block's 1x1 res_conv (model/ucdir.py:118,140: res_conv(x) of the SAME un-normalised input) rides along: its
+// operand is the centre-tap view of the halo box that is already in shared memory, so the input is not read from HBM a second
+// time.  The item then is 128/NT tiles with NT conv1 + NT res_conv accumulator columns each.
+template <int NT, int KC, int RES = 0>
 struct DhCfg {
   static constexpr int ROWB = KC * 2;                     // bytes per pixel row of a chunk
   static constexpr uint32_t LAYOUT = KC == 64 ? 2u : 6u;  // operand descriptor swizzle mode: 128B / 32B
   static constexpr int KSTEPS = KC / 16;
-  static constexpr int MT = 256 / NT;                     // 8 x 16 pixel tiles per item
+  static constexpr int MT = (RES ? 128 : 256) / NT;       // 8 x 16 pixel tiles per item
+  static constexpr int SLABS = 9 + RES;                   // weight slabs per chunk: nine taps (+ the res_conv)
   static constexpr int SW = 8 * MT;                       // super tile width
   static constexpr int BW = SW + 2, BH = 18;              // halo box
   static constexpr int A_BYTES = BW * BH * ROWB;
@@ -56,7 +61,7 @@ struct DhCfg {
   static constexpr int BSTG = NT == 64 ? 6 : 5;
   static constexpr int OFF_B = ASTG * A_STAGE;
   static constexpr int OFF_CTAB = OFF_B + BSTG * BSLAB;
-  static constexpr int OFF_BARS = OFF_CTAB + 9 * NT * 4;
+  static constexpr int OFF_BARS = OFF_CTAB + 9 * NT * 4 + NT * 4;   // + bias table of the res_conv
   static constexpr int TOTAL = OFF_BARS + 256 + 1024 /* align slack */;
   static_assert(TOTAL <= 227 * 1024, "shared memory");
 };
@@ -84,16 +89,18 @@ struct SuperCursor {            // item = (image, super-tile row, super-tile col
   }
 };
 
-template <int NT, int ACT, int KC>
+template <int NT, int ACT, int KC, int RES>
 __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                    const __grid_constant__ CUtensorMap mapA1,
-                                                                   const __grid_constant__ CUtensorMap mapB, const DhParams p) {
-  using S = DhCfg<NT, KC>;
+                                                                   const __grid_constant__ CUtensorMap mapB,
+                                                                   const __grid_constant__ CUtensorMap mapB2, const DhParams p) {
+  using S = DhCfg<NT, KC, RES>;
   constexpr int MT = S::MT, ASTG = S::ASTG, BSTG = S::BSTG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* bring = smem + S::OFF_B;
   float* ctab = reinterpret_cast<float*>(smem + S::OFF_CTAB);          // [9][NT] additive terms of the current image
+  float* btab2 = ctab + 9 * NT;                                         // [NT] bias of the fused res_conv
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BARS);
   uint64_t* a_empty = a_full + ASTG;
   uint64_t* b_full = a_empty + ASTG;
@@ -109,6 +116,7 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
   if (threadIdx.x == 0) {
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
     if (p.c0_chunks < p.nchunk) prefetch_tmap(&mapA1);
+    if (RES) prefetch_tmap(&mapB2);
     for (int s = 0; s < ASTG; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < BSTG; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int j = 0; j < 2; ++j) { mbar_init(&tmem_full[j], 1); mbar_init(&tmem_empty[j], DH_EPI_WARPS); }
@@ -150,11 +158,12 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
       for (int it = it0; it < it1; ++it) {
         for (int j = 0; j < p.nchunk; ++j) {
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < S::SLABS; ++tap) {        // slab 9 = the res_conv's weights of this chunk
             mbar_wait(&b_empty[stage], phase ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&b_full[stage], (uint32_t)S::BSLAB);
-              tma_load_2d(&mapB, &b_full[stage], bring + stage * S::BSLAB, (tap * p.nchunk + j) * KC, 0);
+              if (tap < 9) tma_load_2d(&mapB, &b_full[stage], bring + stage * S::BSLAB, (tap * p.nchunk + j) * KC, 0);
+              else tma_load_2d(&mapB2, &b_full[stage], bring + stage * S::BSLAB, j * KC, 0);
             }
             __syncwarp();
             if (++stage == BSTG) { stage = 0; phase ^= 1; }
@@ -175,23 +184,26 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
           mbar_wait(&a_full[as], aph);
           const uint32_t a_base = smem_u32(smem + as * S::A_STAGE);
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < S::SLABS; ++tap) {
             mbar_wait(&b_full[bs], bph);
             tc_fence_after();
             if (elect_one()) {
-              const int ty = tap / 3, tx = tap - ty * 3;
+              const bool is_res = RES && tap == 9;          // the res_conv reads the centre-tap view
+              const int ty = is_res ? 1 : tap / 3, tx = is_res ? 1 : tap - (tap / 3) * 3;
               constexpr uint32_t a_hi = desc_hi(S::BW * S::ROWB, S::LAYOUT), b_hi = desc_hi(8 * S::ROWB, S::LAYOUT);
               const uint32_t a_lo = desc_lo(a_base) + (uint32_t)(((ty * S::BW + tx) * S::ROWB) >> 4);
               const uint32_t b_lo = desc_lo(smem_u32(bring + bs * S::BSLAB));
+              const uint32_t tdst = tacc + (is_res ? (uint32_t)(MT * NT) : 0u);
+              const uint32_t first = is_res ? (uint32_t)j : (uint32_t)(j | tap);
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
                 for (int k = 0; k < S::KSTEPS; ++k)
-                  umma_bf16_lohi(tacc + (uint32_t)(mt * NT), a_lo + (uint32_t)((mt * 8 * S::ROWB) >> 4) + (uint32_t)(k * 2), a_hi,
-                                 b_lo + (uint32_t)(k * 2), b_hi, idesc, (j | tap | k) != 0);
+                  umma_bf16_lohi(tdst + (uint32_t)(mt * NT), a_lo + (uint32_t)((mt * 8 * S::ROWB) >> 4) + (uint32_t)(k * 2), a_hi,
+                                 b_lo + (uint32_t)(k * 2), b_hi, idesc, (first | (uint32_t)k) != 0);
               }
               umma_commit(&b_empty[bs]);                   // weight slab may be overwritten
-              if (tap == 8) {
+              if (tap == S::SLABS - 1) {
                 umma_commit(&a_empty[as]);                 // ... and so may the halo box
                 if (j == p.nchunk - 1) umma_commit(&tmem_full[slot]);
               }
@@ -209,7 +221,10 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DH_REGS_HIGH));
     const int q = warp & 3;                                // TMEM lane quadrant this warp may read
     const int stripe = (warp - DH_FIRST_EPI_WARP) >> 2;    // 64-column stripe of the item's 256 accumulator columns
-    const int mt = (stripe * 64) / NT, ncol0 = (stripe * 64) % NT;
+    // RES: the first MT*NT columns are conv1 (tile mt, columns ncol0..), the next MT*NT the res_conv of the same tiles
+    const bool is_res = RES && stripe * 64 >= MT * NT;
+    const int local = stripe * 64 - (is_res ? MT * NT : 0);
+    const int mt = local / NT, ncol0 = local % NT;
     const int r = q * 32 + lane;
     const int yy = r >> 3, xx = mt * 8 + (r & 7);
     const int et = threadIdx.x - 32 * DH_FIRST_EPI_WARP;
@@ -238,15 +253,20 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
           rstd = half;
           for (int i = et; i < 9 * NT; i += 32 * DH_EPI_WARPS) ctab[i] = half * __ldg(p.tb + i % NT);
         }
+        if (RES) for (int i = et; i < NT; i += 32 * DH_EPI_WARPS) btab2[i] = __ldg(p.tb2 + i);
         asm volatile("bar.sync 1, %0;" ::"n"(32 * DH_EPI_WARPS) : "memory");
       }
       const int y = cur.ty * 16 + yy, x = cur.tx * S::SW + xx;
       const bool valid = y < p.H && x < p.W;
       const size_t pix = valid ? ((size_t)img * p.H + y) * p.W + x : 0;
       const int cls = (y == 0 ? 0 : (y == p.H - 1 ? 2 : 1)) * 3 + (x == 0 ? 0 : (x == p.W - 1 ? 2 : 1));
-      const float4* ct = reinterpret_cast<const float4*>(ctab + cls * NT + ncol0);
-      __nv_bfloat16* d = p.dst + pix * p.dstC + p.dstCoff + ncol0;
-      const float2 rs2 = make_float2(rstd, rstd);          // (ACT: rstd / 2, and the table holds half the additive terms)
+      // conv1 stripes: folded GroupNorm (+ Swish) into dst; res_conv stripes: + bias into dst2, no activation, no statistics
+      const float4* ct = reinterpret_cast<const float4*>(is_res ? btab2 + ncol0 : ctab + cls * NT + ncol0);
+      __nv_bfloat16* d = is_res ? p.dst2 + pix * p.dst2C + ncol0 : p.dst + pix * p.dstC + p.dstCoff + ncol0;
+      const bool st32 = is_res ? p.st32_2 != 0 : p.st32 != 0;
+      const bool act_here = ACT && !is_res;
+      const float rs = is_res ? 1.0f : rstd;               // (ACT: rstd / 2, and the table holds half the additive terms)
+      const float2 rs2 = make_float2(rs, rs);
       float2 st1 = make_float2(0.f, 0.f), st2 = make_float2(0.f, 0.f);
       mbar_wait(&tmem_full[slot], sph);
       tc_fence_after();
@@ -266,7 +286,7 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
             const float4 c4 = ct[4 * k + j];
             float2 va = __ffma2_rn(make_float2(__uint_as_float(rv[4 * j + 0]), __uint_as_float(rv[4 * j + 1])), rs2, make_float2(c4.x, c4.y));
             float2 vb = __ffma2_rn(make_float2(__uint_as_float(rv[4 * j + 2]), __uint_as_float(rv[4 * j + 3])), rs2, make_float2(c4.z, c4.w));
-            if (ACT) {
+            if (act_here) {
               va = __ffma2_rn(va, make_float2(tanh_approx(va.x), tanh_approx(va.y)), va);
               vb = __ffma2_rn(vb, make_float2(tanh_approx(vb.x), tanh_approx(vb.y)), vb);
             }
@@ -277,7 +297,7 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
             st2 = __ffma2_rn(va, va, __ffma2_rn(vb, vb, st2));
           }
           const uint32_t* ow = reinterpret_cast<const uint32_t*>(o2);
-          if (p.st32) {
+          if (st32) {
             // one 256-bit store = one whole 32-byte sector per pixel (two 16-byte stores are two partial-sector writes at L2)
             asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(d + 16 * k), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]),
                          "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
@@ -295,7 +315,7 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
         }
       }
       if (++slot == 2) { slot = 0; sph ^= 1; }
-      s1 += st1.x + st1.y; s2 += st2.x + st2.y;
+      if (!is_res) { s1 += st1.x + st1.y; s2 += st2.x + st2.y; }
       cur.next(p.tiles_x, p.tiles_y);
     }
     if (p.dst_stats && stat_img >= 0) {
@@ -316,13 +336,14 @@ __global__ void __launch_bounds__(DH_THREADS, 1) dense_halo_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 static const bool g_dh_pdl = []() { const char* e = getenv("UCDIR_PDL"); return !(e && e[0] == '0'); }();
 
-template <int NT, int ACT, int KC>
-static int launch_dh_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const DhParams& p, int grid, cudaStream_t st) {
-  using S = DhCfg<NT, KC>;
+template <int NT, int ACT, int KC, int RES>
+static int launch_dh_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& b2, const DhParams& p, int grid,
+                          cudaStream_t st) {
+  using S = DhCfg<NT, KC, RES>;
   static bool attr = false;
   if (!attr) {
-    if (int rc = check_reg_pool((const void*)dense_halo_kernel<NT, ACT, KC>, "tc_dense_halo", 32 * DH_FIRST_EPI_WARP, DH_REGS_LOW, 32 * DH_EPI_WARPS, DH_REGS_HIGH)) return rc;
-    if (cudaFuncSetAttribute(dense_halo_kernel<NT, ACT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+    if (int rc = check_reg_pool((const void*)dense_halo_kernel<NT, ACT, KC, RES>, "tc_dense_halo", 32 * DH_FIRST_EPI_WARP, DH_REGS_LOW, 32 * DH_EPI_WARPS, DH_REGS_HIGH)) return rc;
+    if (cudaFuncSetAttribute(dense_halo_kernel<NT, ACT, KC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
       set_error("tc_dense_halo: cannot opt in to %d bytes of shared memory: %s", S::TOTAL, cudaGetErrorString(cudaGetLastError())); return -3; }
     attr = true;
   }
@@ -332,7 +353,7 @@ static int launch_dh_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CU
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = g_dh_pdl ? 1 : 0;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, dense_halo_kernel<NT, ACT, KC>, a0, a1, b, p) != cudaSuccess) {
+  if (cudaLaunchKernelEx(&cfg, dense_halo_kernel<NT, ACT, KC, RES>, a0, a1, b, b2, p) != cudaSuccess) {
     set_error("tc_dense_halo: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
   return 0;
 }
@@ -353,7 +374,9 @@ bool tc_dense_halo_applies(const ucdir_op_t& op) {
          !op.i[UCDIR_TC_I_DST_UP] && !op.i[UCDIR_TC_I_W_BATCHED] && !op.p[UCDIR_TC_P_DST2] && op.i[UCDIR_TC_I_ACT] <= 1 &&
          (op.i[UCDIR_TC_I_SRC_CSTRIDE] == 0 || op.i[UCDIR_TC_I_SRC_CSTRIDE] == C0) && op.i[UCDIR_TC_I_DST_C] % 8 == 0 &&
          op.i[UCDIR_TC_I_DST_COFF] % 8 == 0 && (op.i[UCDIR_TC_I_NCOL_VALID] == 0 || op.i[UCDIR_TC_I_NCOL_VALID] == NT) &&
-         (C1 == 0 || op.p[UCDIR_TC_P_SRC1]);
+         (C1 == 0 || op.p[UCDIR_TC_P_SRC1]) &&
+         (op.i[UCDIR_TC_I_RES_FUSED] == 0 || (KC == 64 && op.p[UCDIR_TC_P_W2] && op.p[UCDIR_TC_P_TB2] && op.p[UCDIR_TC_P_DST_RES] &&
+                                              op.i[UCDIR_TC_I_DST_RES_C] >= NT && op.i[UCDIR_TC_I_DST_RES_C] % 8 == 0 && !op.i[UCDIR_TC_I_SRC_GN_SWISH]));
 }
 
 static int dh_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int B, int bw, int kc) {
@@ -382,12 +405,15 @@ int launch_tc_dense_halo(const ucdir_op_t& op, cudaStream_t st) {
   p.eps = op.f[UCDIR_TC_F_EPS];
   p.st32 = (p.dstC % 16 == 0 && p.dstCoff % 16 == 0 && (reinterpret_cast<uintptr_t>(p.dst) & 31) == 0) ? 1 : 0;
   p.gn_count = (double)(C0 + C1) * p.H * p.W;
-  const int sw = 8 * (256 / NT);
+  const int res = op.i[UCDIR_TC_I_RES_FUSED] ? 1 : 0;
+  p.tb2 = (const float*)op.p[UCDIR_TC_P_TB2]; p.dst2 = (__nv_bfloat16*)op.p[UCDIR_TC_P_DST_RES]; p.dst2C = op.i[UCDIR_TC_I_DST_RES_C];
+  p.st32_2 = (res && p.dst2C % 16 == 0 && (reinterpret_cast<uintptr_t>(p.dst2) & 31) == 0) ? 1 : 0;
+  const int sw = 8 * ((res ? 128 : 256) / NT);
   p.tiles_x = (p.W + sw - 1) / sw; p.tiles_y = (p.H + 15) / 16;
   const long long items = (long long)p.tiles_x * p.tiles_y * p.B;
   if (items > 0x7fffffffLL) { set_error("tc_dense_halo: too many items"); return -2; }
   p.n_items = (int)items;
-  CUtensorMap a0, a1, mb;
+  CUtensorMap a0, a1, mb, mb2;
   int rc = dh_act_map(&a0, op.p[UCDIR_TC_P_SRC0], C0, p.W, p.H, p.B, sw + 2, KC);
   if (rc) return rc;
   if (C1 > 0) { rc = dh_act_map(&a1, op.p[UCDIR_TC_P_SRC1], C1, p.W, p.H, p.B, sw + 2, KC); if (rc) return rc; }
@@ -404,12 +430,27 @@ int launch_tc_dense_halo(const ucdir_op_t& op, cudaStream_t st) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tc_dense_halo: cuTensorMapEncodeTiled(weights K=%d N=%d) failed: %d", Ktot, NT, (int)r); return -3; }
   }
+  mb2 = mb;
+  if (res) {                                              // 1x1 res_conv weights [NT][C0 + C1], K-major (engine.py:pack_tc_dense)
+    EncodeTiledFn enc = get_encode();
+    const int Ktot = C0 + C1;
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)NT};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)NT};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mb2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.p[UCDIR_TC_P_W2]), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tc_dense_halo: cuTensorMapEncodeTiled(res_conv weights K=%d N=%d) failed: %d", Ktot, NT, (int)r); return -3; }
+  }
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
   const int grid = items < n_sm ? (int)items : n_sm;       // persistent: one CTA per SM
-  if (KC == 16) rc = p.act == 1 ? launch_dh_inst<64, 1, 16>(a0, a1, mb, p, grid, st) : launch_dh_inst<64, 0, 16>(a0, a1, mb, p, grid, st);
-  else if (NT == 64) rc = p.act == 1 ? launch_dh_inst<64, 1, 64>(a0, a1, mb, p, grid, st) : launch_dh_inst<64, 0, 64>(a0, a1, mb, p, grid, st);
-  else rc = p.act == 1 ? launch_dh_inst<128, 1, 64>(a0, a1, mb, p, grid, st) : launch_dh_inst<128, 0, 64>(a0, a1, mb, p, grid, st);
+  const bool act = p.act == 1;
+  if (KC == 16) rc = act ? launch_dh_inst<64, 1, 16, 0>(a0, a1, mb, mb2, p, grid, st) : launch_dh_inst<64, 0, 16, 0>(a0, a1, mb, mb2, p, grid, st);
+  else if (NT == 64 && !res) rc = act ? launch_dh_inst<64, 1, 64, 0>(a0, a1, mb, mb2, p, grid, st) : launch_dh_inst<64, 0, 64, 0>(a0, a1, mb, mb2, p, grid, st);
+  else if (NT == 64) rc = act ? launch_dh_inst<64, 1, 64, 1>(a0, a1, mb, mb2, p, grid, st) : launch_dh_inst<64, 0, 64, 1>(a0, a1, mb, mb2, p, grid, st);
+  else if (!res) rc = act ? launch_dh_inst<128, 1, 64, 0>(a0, a1, mb, mb2, p, grid, st) : launch_dh_inst<128, 0, 64, 0>(a0, a1, mb, mb2, p, grid, st);
+  else rc = act ? launch_dh_inst<128, 1, 64, 1>(a0, a1, mb, mb2, p, grid, st) : launch_dh_inst<128, 0, 64, 1>(a0, a1, mb, mb2, p, grid, st);
   if (rc) return rc;
   ++g_launches;
   return 0;

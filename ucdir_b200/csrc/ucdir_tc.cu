@@ -735,6 +735,10 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
     set_error("tc_conv: SRC_GN_SWISH needs a 3x3 stride-1 conv of <= 128 channels (multiple of 64) with GN = 0, NT = NTOT = 16, DST_F32 = 1, SRC_GAMMA / SRC_BETA / STATS0");
     return -2;
   }
+  if (op.i[UCDIR_TC_I_RES_FUSED] && !tc_dense_halo_applies(op)) {
+    set_error("tc_conv: RES_FUSED needs the halo schedule of a GroupNorm-folded 3x3 stride-1 conv with 64 / 128 output channels, KC = 64, W2 / TB2 / DST_RES");
+    return -2;
+  }
   if (dry) return 0;
   if (tc_final_halo_applies(op)) return launch_tc_final_halo(op, st);  // GroupNorm + Swish + conv of final_conv in one kernel (ucdir_fhalo.cu)
   if (tc_mix_halo_applies(op)) return launch_tc_mix_halo(op, st);      // halo / weight-stationary form of the mix convs (ucdir_mix.cu)

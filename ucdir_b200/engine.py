@@ -397,7 +397,7 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
            dst_py: int = 0, dst_px: int = 0, eps: float = 1e-5, kb: int = 0, nsplit: int = 1, src_cstride: int = 0,
            w_batched: int = 0, w_rowstride: int = 0, w_batchstride: int = 0, alpha: float = 0.0, dst2: int = 0, t_col0: int = 0,
            t_ld: int = 0, w_rows: int = 0, row3: Optional[int] = None, halo: Optional[int] = None, src_gn_swish: int = 0,
-           src_gamma: int = 0, src_beta: int = 0):
+           src_gamma: int = 0, src_beta: int = 0, w2: int = 0, tb2: int = 0, dst_res: Optional[Act] = None):
     H, W = (dst.H // 2, dst.W // 2) if dst_up else (dst.H, dst.W)
     p = {"UCDIR_TC_P_SRC0": src0.ptr, "UCDIR_TC_P_W": w, "UCDIR_TC_P_TB": tb, "UCDIR_TC_P_DST": dst.ptr}
     if src1 is not None: p["UCDIR_TC_P_SRC1"] = src1.ptr
@@ -425,6 +425,9 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
     if src_gn_swish:
         p["UCDIR_TC_P_SRC_GAMMA"], p["UCDIR_TC_P_SRC_BETA"], p["UCDIR_TC_P_STATS0"] = src_gamma, src_beta, src0.stats
         i["UCDIR_TC_I_SRC_GN_SWISH"] = 1
+    if dst_res is not None:                  # fused 1x1 res_conv of the same input (halo schedule only)
+        p["UCDIR_TC_P_W2"], p["UCDIR_TC_P_TB2"], p["UCDIR_TC_P_DST_RES"] = w2, tb2, dst_res.ptr
+        i["UCDIR_TC_I_RES_FUSED"], i["UCDIR_TC_I_DST_RES_C"] = 1, dst_res.C
     ol.add("UCDIR_OP_TC_CONV", p, i, {"UCDIR_TC_F_EPS": eps, "UCDIR_TC_F_ALPHA": alpha})
 
 
@@ -433,6 +436,9 @@ _TC_ROW3 = 0 if os.environ.get("UCDIR_TC_ROW3", "1") == "0" else 1
 where its preconditions hold).  On unless UCDIR_TC_ROW3=0."""
 
 
+_TC_FUSE_RES = 0 if os.environ.get("UCDIR_TC_FUSE_RES", "1") == "0" else 1
+"""Fuse a block's 1x1 res_conv into its conv1 launch where the halo schedule applies (csrc/ucdir_dhalo.cu, RES).  On unless
+UCDIR_TC_FUSE_RES=0."""
 _TC_HALO = 0 if os.environ.get("UCDIR_TC_HALO", "1") == "0" else 1
 """Request the halo / weight-stationary schedule (csrc/ucdir_mix.cu) for the integration-module convs with C = 64 / 128 /
 256 (the library applies it only where its preconditions hold).  On unless UCDIR_TC_HALO=0."""
@@ -786,12 +792,18 @@ class UNetEngine:
             k = blk_index[name]
             nt = _tc_nt(cout)
             h1 = bld.new(cout, x.H, x.W)
+            has_res = ws.has(name + ".res.tcw")
+            # the halo schedule computes the 1x1 res_conv from the activation box conv1 already holds in shared memory
+            fuse_res = (has_res and _TC_HALO and _TC_FUSE_RES and cout in (64, 128) and x.C % 64 == 0 and
+                        (skip is None or skip.C % 64 == 0))
+            res = bld.new(cout, x.H, x.W, with_stats=False) if has_res else None
             _tc_op(ol, src0=x, src1=skip, w=ws.ptr(name + ".conv1.tcw"), tb=ws.ptr(name + ".conv1.tb"),
-                   tg=ws.ptr(name + ".conv1.tg"), gn=1, ncls=9, act=1, dst=h1, ntot=cout, B=BT, nt=nt)
-            if ws.has(name + ".res.tcw"):
-                res = bld.new(cout, x.H, x.W, with_stats=False)
-                _tc_op(ol, src0=x, src1=skip, w=ws.ptr(name + ".res.tcw"), tb=ws.ptr(name + ".res.tb"), nty=1, ntx=1, oy0=0,
-                       ox0=0, dst=res, ntot=cout, B=BT, nt=nt)
+                   tg=ws.ptr(name + ".conv1.tg"), gn=1, ncls=9, act=1, dst=h1, ntot=cout, B=BT, nt=nt,
+                   **(dict(w2=ws.ptr(name + ".res.tcw"), tb2=ws.ptr(name + ".res.tb"), dst_res=res) if fuse_res else {}))
+            if has_res:
+                if not fuse_res:
+                    _tc_op(ol, src0=x, src1=skip, w=ws.ptr(name + ".res.tcw"), tb=ws.ptr(name + ".res.tb"), nty=1, ntx=1, oy0=0,
+                           ox0=0, dst=res, ntot=cout, B=BT, nt=nt)
                 own_res = True
             else:
                 if skip is not None:
