@@ -56,9 +56,9 @@ struct DhCfg {
   static constexpr int BW = SW + 2, BH = 18;              // halo box
   static constexpr int A_BYTES = BW * BH * ROWB;
   static constexpr int A_STAGE = (A_BYTES + 1023) & ~1023;
-  static constexpr int ASTG = NT == 64 ? 2 : 3;
+  static constexpr int ASTG = RES ? (NT == 64 ? 3 : 4) : (NT == 64 ? 2 : 3);   // RES items are half as large: one more box in flight
   static constexpr int BSLAB = NT * ROWB;                 // one tap of one chunk
-  static constexpr int BSTG = NT == 64 ? 6 : 5;
+  static constexpr int BSTG = RES ? (NT == 64 ? 8 : 7) : (NT == 64 ? 6 : 5);
   static constexpr int OFF_B = ASTG * A_STAGE;
   static constexpr int OFF_CTAB = OFF_B + BSTG * BSLAB;
   static constexpr int OFF_BARS = OFF_CTAB + 9 * NT * 4 + NT * 4;   // + bias table of the res_conv
