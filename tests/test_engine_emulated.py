@@ -254,3 +254,29 @@ def test_ddpm_inference_wrapper(emulated, sid_weights, monkeypatch):
     close(vis["SR"], want)
     assert np.array_equal(dd.current_image(), O.tensor2img(vis["SR"])) or \
         np.abs(dd.current_image().astype(int) - O.tensor2img(want).astype(int)).max() <= 1
+
+
+def test_fused_res_conv_graph_equals_separate_ops(emulated, golden, sid_weights, monkeypatch):
+    """bf16 graph with the 1x1 res_conv folded into the conv1 record (UCDIR_TC_I_RES_FUSED, csrc/ucdir_dhalo.cu) against the same
+    graph with separate records: fewer ops, identical result in the CPU interpreter, every record valid for the C ABI."""
+    net, _ = sid_weights
+    unet = net.denoise_fn
+    eng = unet.engine()
+    eng.set_precision("bf16")
+    g = golden("unet")
+    outs, n_ops = {}, {}
+    try:
+        for fuse in (1, 0):
+            monkeypatch.setattr(engine, "_TC_FUSE_RES", fuse)
+            eng._sessions.clear()
+            outs[fuse] = unet(T(g["x6"]), T(g["level"]), T(g["guide"])).clone()
+            sess = next(iter(eng._sessions.values()))
+            _lib.check_ops(sess.step_ops.array(), len(sess.step_ops))
+            n_ops[fuse] = len(sess.step_ops)
+            fused = [o for o in sess.step_ops.ops if o.kind == _lib.C["UCDIR_OP_TC_CONV"] and o.i[_lib.C["UCDIR_TC_I_RES_FUSED"]]]
+            assert (len(fused) == 7) == bool(fuse)
+            assert all(_lib.tc_schedule(o) == 2 for o in fused)
+    finally:
+        eng.set_precision("fp32")
+    assert n_ops[1] == n_ops[0] - 7
+    assert torch.equal(outs[1], outs[0])

@@ -66,16 +66,6 @@ struct DhCfg {
   static_assert(TOTAL <= 227 * 1024, "shared memory");
 };
 
-// Swish from ONE special-function op: x*sigmoid(x) = h + h*tanh(h) with h = x/2 (the epilogue scales by 1/2 for free).
-// tanh.approx has a relative error of 2^-11, i.e. |error| <= |x| * 2.5e-4 -- below the bf16 rounding of the stored result
-// except in the negative tail, where it stays under 1.5e-3 absolute.  The ex2 + rcp form costs two MUFU ops per element
-// and the MUFU unit issues 16 per SM per clock: at 64 / 128 output channels that was a third of this kernel's epilogue.
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 struct SuperCursor {            // item = (image, super-tile row, super-tile column), column fastest
   int img, ty, tx;
   __device__ __forceinline__ void init(int it, int tiles_x, int tiles_y) {

@@ -180,10 +180,7 @@ __global__ void __launch_bounds__(FH_THREADS, 1) final_halo_kernel(const __grid_
           for (int k = 0; k < 4; ++k) {
             float2 f = __bfloat1622float2(h2[k]);
             const float hx = fmaf(f.x, sa[2 * k], sb[2 * k]), hy = fmaf(f.y, sa[2 * k + 1], sb[2 * k + 1]);
-            float tx_, ty_;
-            asm("tanh.approx.f32 %0, %1;" : "=f"(tx_) : "f"(hx));
-            asm("tanh.approx.f32 %0, %1;" : "=f"(ty_) : "f"(hy));
-            h2[k] = __floats2bfloat162_rn(fmaf(hx, tx_, hx), fmaf(hy, ty_, hy));
+            h2[k] = __floats2bfloat162_rn(swish_half(hx), swish_half(hy));
           }
           box[v] = u;
         }

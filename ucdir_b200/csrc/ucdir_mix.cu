@@ -78,14 +78,6 @@ struct MixCfg {
   static_assert(OFF_W % 1024 == 0, "weight block alignment");
 };
 
-// Swish from one special-function op: x*sigmoid(x) = h + h*tanh(h), h = x/2 (see ucdir_dhalo.cu:tanh_approx for the error
-// bound); the 1/2 is folded into the per-step attw factors, so the mixed sum arrives as h.
-__device__ __forceinline__ float swish_half(float h) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(h));
-  return fmaf(h, y, h);
-}
-
 // 16-byte asynchronous global -> shared copy (completion is tracked per thread by cp.async groups, not by the register
 // scoreboards a prefetch into registers shares with every other load in flight)
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {

@@ -829,12 +829,8 @@ __global__ void __launch_bounds__(256) gn_apply_bf16_kernel(const __nv_bfloat16*
       float2 f = __bfloat1622float2(h2[k]);
       f.x = f.x * sa[2 * k] + sb[2 * k];
       f.y = f.y * sa[2 * k + 1] + sb[2 * k + 1];
-      if (swish) {      // x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op; the result is rounded to bf16 (see ucdir_dhalo.cu)
-        const float hx = 0.5f * f.x, hy = 0.5f * f.y;
-        float tx, ty;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(hx));
-        asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(hy));
-        f.x = fmaf(hx, tx, hx); f.y = fmaf(hy, ty, hy);
+      if (swish) {      // x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op; the result is rounded to bf16 (tc_ptx.cuh)
+        f.x = swish_half(0.5f * f.x); f.y = swish_half(0.5f * f.y);
       }
       o2[k] = __floats2bfloat162_rn(f.x, f.y);
     }
