@@ -221,7 +221,7 @@ enum ucdir_tc_int {
                                                   * STATS0, result rounded to bf16) -- final_conv, model/ucdir.py:266-268, whose Swish keeps the norm from being
                                                   * folded into the weights.  Applied to the landed halo box in shared memory (ucdir_fhalo.cu); needs a 3x3
                                                   * stride-1 conv of C0 <= 128 channels with GN = 0, NT = NTOT = 16 and DST_F32 = 1 */
-  UCDIR_TC_I_RES_FUSED = 45,                     /* 1: also compute DST_RES = conv1x1(concat(SRC0, SRC1); W2) + TB2 (model/ucdir.py:118,140: res_conv(x) of the
+  UCDIR_TC_I_RES_FUSED = 45,                     /* 1: also compute DST_RES = conv1x1(concat(SRC0, SRC1); W2) + TB2 (model/ucdir.py:120,140: res_conv(x) of the
                                                   * same un-normalised input as conv1) from the centre-tap view of the halo box already in shared memory;
                                                   * needs the 64-channel halo schedule (ucdir_dhalo.cu), refused otherwise */
   UCDIR_TC_I_DST_RES_C = 46,                     /* channels per pixel row of DST_RES */

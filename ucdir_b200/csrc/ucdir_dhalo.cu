@@ -42,7 +42,7 @@ constexpr int DH_REGS_LOW = 40, DH_REGS_HIGH = 104;      // see MX_REGS_LOW / MX
 
 // KC = channels per chunk = one pixel row of the halo box: 64 (128-byte rows, 128B swizzle) or 16 (the in-conv's zero-padded
 // 6 -> 16 input channels: 32-byte rows, 32B swizzle, one K step per tap)
-// RES = 1: the block's 1x1 res_conv (model/ucdir.py:118,140: res_conv(x) of the SAME un-normalised input) rides along: its
+// RES = 1: the block's 1x1 res_conv (model/ucdir.py:120,140: res_conv(x) of the SAME un-normalised input) rides along: its
 // operand is the centre-tap view of the halo box that is already in shared memory, so the input is not read from HBM a second
 // time.  The item then is 128/NT tiles with NT conv1 + NT res_conv accumulator columns each.
 template <int NT, int KC, int RES = 0>
