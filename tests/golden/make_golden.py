@@ -224,8 +224,43 @@ def main_image():
     save("image", x=x.numpy(), img=img, img_crop=img_crop, crop=np.array(8))
 
 
+def main_wrappers():
+    """9. What the reference's guide-less wrappers do with the only UNet it ships (DY3h needs `guide`): record the exception
+    type each one raises (model/diffusion.py:302-304,428-432,620-622,650-662) -> tests/golden/wrappers.json."""
+    import json
+    opt = yaml.safe_load(open(os.path.join(REF, "config/sid.yaml")))
+    rec = {}
+    x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(INPUT_SEED + 9)) * 2 - 1
+    so = dict(schedule="linear", n_timestep=2, linear_start=1e-6, linear_end=0.4)
+
+    def attempt(fn):
+        try:
+            with torch.no_grad():
+                fn()
+            return {"error": None}
+        except Exception as e:                      # noqa: BLE001 -- recording whatever the reference raises
+            return {"error": type(e).__name__, "message": str(e)[:200]}
+
+    for name in ("ResiGaussianDiffusion", "ResiPercepGaussianDiffusion", "NoDiffusion"):
+        opt["model"]["diffusion_name"] = name
+        torch.manual_seed(WEIGHT_SEED)
+        net = refnet.define_G(opt).eval()
+        same = sd_digest(net.state_dict()) == str(np.load(os.path.join(OUT, "unet.npz"))["digest"])
+        rec[name] = dict(attempt(lambda: (net.set_new_noise_schedule(so, torch.device("cpu")), net.super_resolution(x))),
+                         digest_matches_guide_dy=same)
+    opt["model"]["diffusion_name"] = "ResiGaussianGuideDY"
+    torch.manual_seed(WEIGHT_SEED)
+    net = refnet.define_G(opt).eval()
+    net.set_new_noise_schedule(so, torch.device("cpu"))
+    rec["GaussianDiffusion.super_resolution"] = attempt(lambda: refdiff.GaussianDiffusion.super_resolution(net, x))
+    json.dump(rec, open(os.path.join(OUT, "wrappers.json"), "w"), indent=1, sort_keys=True)
+    print(rec)
+
+
 if __name__ == "__main__":
-    if "--only-image" in sys.argv:
+    if "--only-wrappers" in sys.argv:
+        main_wrappers()
+    elif "--only-image" in sys.argv:
         main_image()
     elif "--only-ddim" in sys.argv:
         main_ddim()
@@ -236,3 +271,4 @@ if __name__ == "__main__":
         main_ddim()
         main_variants()
         main_image()
+        main_wrappers()

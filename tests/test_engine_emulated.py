@@ -280,3 +280,155 @@ def test_fused_res_conv_graph_equals_separate_ops(emulated, golden, sid_weights,
         eng.set_precision("fp32")
     assert n_ops[1] == n_ops[0] - 7
     assert torch.equal(outs[1], outs[0])
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# round 2: binding / invalidation regressions
+# --------------------------------------------------------------------------------------------------------------------
+def _sched(net, T_=2):
+    so = dict(schedule="linear", n_timestep=T_, linear_start=1e-6, linear_end=0.4)
+    net.set_new_noise_schedule(so, torch.device("cpu"))
+    return so
+
+
+@pytest.mark.parametrize("variant", ["ResiGaussianGuideDY", "ResiGaussianGuideDY_de", "ResiGaussianGuideDY_initxloss"])
+def test_same_shape_images_back_to_back_do_not_share_guidance(emulated, sid_weights, variant):
+    """A validation loop over same-shape images (sr.py:518-525): every image must get its own guidance maps even when its
+    tensors land on the allocation the previous image just freed.  Round 1 keyed the bind on (data_ptr, _version, shape) and
+    returned the previous image's result.  Three different images in a loop, previous tensors deleted, each equal to the
+    oracle; recycled addresses are forced by reusing one storage through fresh tensor objects."""
+    from oracle import ucdir_oracle as O
+    _, sd = sid_weights
+    net = _variant_net(variant)
+    so = _sched(net, 1)
+    lay = O.UNetLayout(**ucdir_b200.SID_MODEL_OPT["unet"])
+    gen = torch.Generator().manual_seed(21)
+    storage = torch.empty(1, 3, 40, 48)
+    noise = torch.randn(1, 3, 40, 48, generator=gen)
+    net._noise_source = lambda shape: noise
+    outs = []
+    for k in range(3):
+        img = torch.rand(1, 3, 40, 48, generator=gen) * 2 - 1
+        # a NEW tensor object at the SAME address with version 0: what the caching allocator hands out after `del`
+        x = torch.frombuffer(memoryview(storage.numpy()), dtype=torch.float32).view(1, 3, 40, 48)
+        storage.copy_(img)
+        assert x.data_ptr() == storage.data_ptr() and x._version == 0
+        out = net.super_resolution(x, False)
+        with torch.no_grad():
+            want, _ = O.super_resolution(sd, lay, O.schedule_buffers(so), img, [noise], continous=False,
+                                         guide_from="input" if variant == "ResiGaussianGuideDY_de" else "initx")
+        close(out, want)
+        outs.append(out.clone())
+        del x, out
+    assert not torch.allclose(outs[0], outs[1]) and not torch.allclose(outs[1], outs[2])
+
+
+def test_reference_style_denoise_fn_loop_rebinds_cond_every_call(emulated, sid_weights):
+    """The generic drop-in forward under the REFERENCE's own sampler / dpm_solver wrapper (model/diffusion.py:166,
+    sr.py:203-205): `denoise_fn(torch.cat([cond, x_t], 1), level, guide=initx)` with a fresh cat tensor per step (usually at
+    the address of the previous one).  cond must be re-copied on every call; the guidance maps (a function of `guide` only)
+    are computed once for as long as the caller passes the same guide object."""
+    from oracle import ucdir_oracle as O
+    net, sd = sid_weights
+    lay = O.UNetLayout(**ucdir_b200.SID_MODEL_OPT["unet"])
+    gen = torch.Generator().manual_seed(5)
+    cond = torch.rand(1, 3, 40, 48, generator=gen) * 2 - 1
+    guide = torch.rand(1, 3, 40, 48, generator=gen) * 2 - 1
+    lvl = torch.full((1, 1), 0.7)
+    eng = net.denoise_fn.engine()
+    eng._sessions.clear()
+    storage = torch.empty(1, 6, 40, 48)
+    binds = []
+    for k in range(3):
+        xt = torch.randn(1, 3, 40, 48, generator=gen)
+        storage.copy_(torch.cat([cond, xt], 1))
+        x6 = torch.frombuffer(memoryview(storage.numpy()), dtype=torch.float32).view(1, 6, 40, 48)   # same address, version 0
+        eps = net.denoise_fn(x6, lvl, guide)
+        with torch.no_grad():
+            want = O.unet_forward(sd, "denoise_fn.", lay, torch.cat([cond, xt], 1), lvl, guide)
+        close(eps, want)
+        binds.append(next(iter(eng._sessions.values())).n_binds)
+    assert binds == [1, 1, 1], binds                   # guidance maps computed once
+    guide2 = guide.clone()
+    net.denoise_fn(x6, lvl, guide2)
+    assert next(iter(eng._sessions.values())).n_binds == 2      # a different guide object recomputes them
+    guide2.mul_(0.5)                                            # ... and so does an in-place edit of the bound one
+    eps = net.denoise_fn(x6, lvl, guide2)
+    assert next(iter(eng._sessions.values())).n_binds == 3
+    with torch.no_grad():
+        close(eps, O.unet_forward(sd, "denoise_fn.", lay, x6, lvl, guide2))
+
+
+def test_in_place_parameter_update_repacks_weights(emulated, golden, sid_weights):
+    """Optimizers (and any `p.mul_()` / `p.copy_()` under no_grad) write parameters in place; packed kernel weights and plans
+    must follow (round 1 only invalidated on load_state_dict / .to()).  Detected through the parameters' version counters;
+    writes through a `.data` view bypass those by design and need `engine().invalidate_weights()` (also checked)."""
+    import copy
+    net, _ = sid_weights
+    net = copy.deepcopy(net)
+    g = golden("unet")
+    args = (T(g["x6"]), T(g["level"]), T(g["guide"]))
+    base = net.denoise_fn(*args).clone()
+    with torch.no_grad():
+        net.denoise_fn.final_conv[3].weight.mul_(0.5)
+    bias = net.denoise_fn.final_conv[3].bias.detach().view(1, -1, 1, 1)
+    close(net.denoise_fn(*args) - bias, (base - bias) * 0.5, rtol=1e-4, atol=1e-5)
+    p0 = net.predictor(T(g["xp"])).clone()
+    with torch.no_grad():
+        net.predictor.conv10_1.weight.mul_(2.0)
+    b10 = net.predictor.conv10_1.bias.detach().view(1, -1, 1, 1)
+    close(net.predictor(T(g["xp"])) - b10, (p0 - b10) * 2.0, rtol=1e-4, atol=1e-5)
+    net.predictor.conv10_1.weight.data.mul_(0.5)                 # invisible to the version counter
+    net.predictor.engine().invalidate_weights()
+    close(net.predictor(T(g["xp"])), p0, rtol=1e-4, atol=1e-5)
+
+
+def test_guideless_wrappers_fail_like_the_reference(emulated, golden, sid_weights):
+    """ResiGaussianDiffusion / ResiPercepGaussianDiffusion / NoDiffusion / GaussianDiffusion.super_resolution call denoise_fn
+    without `guide` (model/diffusion.py:302-304,428-432,620-622,650-662); with the only UNet the reference ships that is a
+    TypeError there (recorded in tests/golden/wrappers.json by make_golden.py) and here.  Constructors keep the state_dict."""
+    import json, os
+    _, sd = sid_weights
+    rec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "wrappers.json")))
+    x = T(golden("unet")["xp"])
+    for name in ("ResiGaussianDiffusion", "ResiPercepGaussianDiffusion", "NoDiffusion"):
+        net = _variant_net(name)
+        assert list(net.state_dict().keys()) == list(sd.keys())
+        for k in ("denoise_fn.final_conv.3.weight", "predictor.conv10_1.weight"):
+            assert torch.equal(net.state_dict()[k], sd[k])
+        _sched(net, 2)
+        assert rec[name]["error"] == "TypeError"
+        with pytest.raises(TypeError, match="guide"):
+            net.super_resolution(x)
+    base = _variant_net("ResiGaussianGuideDY")
+    _sched(base, 2)
+    assert rec["GaussianDiffusion.super_resolution"]["error"] == "TypeError"
+    with pytest.raises(TypeError, match="guide"):
+        ucdir_b200.model.diffusion.GaussianDiffusion.super_resolution(base, x)
+
+
+def test_product_schedule_buffers_bit_exact(golden, sid_weights):
+    """The PRODUCT's set_new_noise_schedule (not the oracle's) against the reference's buffers: 12 fp32 vectors + the float64
+    numpy attribute, bit for bit, for every schedule in tests/golden/schedule.npz."""
+    import ucdir_b200.model.diffusion  # noqa: F401
+    net, _ = sid_weights
+    g = golden("schedule")
+    kinds = {"sidval": "linear", "yamlval": "linear", "train": "linear", "quad": "quad", "warm": "warmup10"}
+    for tag, kind in kinds.items():
+        n, ls, le = g[f"{tag}.opt"]
+        net.set_new_noise_schedule(dict(schedule=kind, n_timestep=int(n), linear_start=float(ls), linear_end=float(le)), torch.device("cpu"))
+        checked = 0
+        for k in g.files:
+            if not k.startswith(tag + ".") or k.endswith(".opt"):
+                continue
+            field = k.split(".", 1)[1]
+            want = g[k]
+            have = net.sqrt_alphas_cumprod_prev if field == "sqrt_alphas_cumprod_prev_f64" else getattr(net, field).numpy()
+            assert have.dtype == want.dtype and np.array_equal(have, want), (tag, field)
+            checked += 1
+        assert checked == 13, (tag, checked)
+    # schedule arrived through load_state_dict only (model/model.py:236-239): samplers rebuild their host copies lazily
+    import copy
+    other = copy.deepcopy(net)
+    other._sched_host = None
+    assert other._step_scalars(1) == net._step_scalars(1)

@@ -2,8 +2,10 @@
 
 Stated bf16 tolerance (BASELINE.json north_star "stated bf16 tolerance"; SURVEY 8d measured 7e-3 max / 1.2e-3
 mean on eps for bf16 operand rounding alone, this path also stores activations in bf16):
-    per UNet evaluation (eps, |eps| <= ~1.7):   max abs err <= 5e-2,  mean abs err <= 5e-3
-    per denoising step and final image in [-1,1]: max abs err <= 5e-2, mean abs err <= 4e-3
+    per UNet evaluation (eps, |eps| <= ~1.7):   max abs err <= 2e-2,  mean abs err <= 2.5e-3
+    per denoising step and final image in [-1,1]: max abs err <= 2e-2, mean abs err <= 2e-3
+(about 2x the measured values of profiles/r01_bf16_errors.json: eps 8.6e-3 / 1.45e-3, images 9.0e-3 / 5.4e-4 -- a kernel
+regression that doubles the error fails.)
 The measured errors are written to gpurun_out/bf16_errors.json (copied to profiles/ for DESIGN.md)."""
 import json
 import os
@@ -17,8 +19,8 @@ from oracle import ucdir_oracle as O
 
 pytestmark = pytest.mark.gpu
 T = lambda a: torch.from_numpy(np.asarray(a))
-EPS_MAX, EPS_MEAN = 5e-2, 5e-3
-IMG_MAX, IMG_MEAN = 5e-2, 4e-3
+EPS_MAX, EPS_MEAN = 2e-2, 2.5e-3
+IMG_MAX, IMG_MEAN = 2e-2, 2e-3
 REPORT = {}
 
 

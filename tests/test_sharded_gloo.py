@@ -31,6 +31,8 @@ torch.manual_seed(1234)
 net = define_G({"model": ucdir_b200.SID_MODEL_OPT})
 unet = net.denoise_fn
 unet.tile_skip, unet.tile_padding, unet.tile_trigger = 64, 16, 0
+assert unet.engine().shard_mode == "none"          # sharding is opt-in: the reference launcher runs one image per rank
+unet.engine().set_shard_mode("tiles")
 g = np.load(os.path.join(os.environ["UCDIR_ROOT"], "tests", "golden", "tiler.npz"))
 T = lambda a: torch.from_numpy(np.asarray(a))
 out = unet(T(g["x"]), T(g["level"]), T(g["guide"]))
@@ -52,6 +54,33 @@ np.save(os.environ["UCDIR_OUT"] + ".rank%d.npy" % rank, torch.stack([res_a, res_
 print("RANK", rank, "tiles", sess.my_tiles, "tiler_err", err)
 assert err < 2e-4, err
 if world > 1:
+    # ranks that hold DIFFERENT images must not be stitched together: the bind-time checksum exchange raises on every rank
+    bad = x_in + 0.01 * rank
+    try:
+        net.p_sample_loop(bad, True, kwargs={"guide": guide})
+        raise SystemExit("tile sharding accepted rank-divergent inputs")
+    except RuntimeError as e:
+        assert "different conditioning images" in str(e), e
+# batch sharding (SURVEY 8e(2)): B = 3 samples over `world` ranks, whole trajectory per rank, ONE gather at the end
+unet.tile_skip, unet.tile_padding, unet.tile_trigger = 1024, 64, 1 << 30
+unet.engine().set_shard_mode("batch")
+gen = torch.Generator().manual_seed(11)
+xb = torch.rand(3, 3, 40, 48, generator=gen) * 2 - 1
+gb = torch.rand(3, 3, 40, 48, generator=gen) * 2 - 1
+ng = torch.Generator().manual_seed(5)
+net._noise_source = lambda shape: torch.randn(shape, generator=ng)
+import torch.distributed as _d
+calls = {"n": 0}
+_orig = _d.all_gather_into_tensor
+def _count(*a, **k):
+    calls["n"] += 1
+    return _orig(*a, **k)
+_d.all_gather_into_tensor = _count
+res_c = net.p_sample_loop(xb, True, kwargs={"guide": gb})
+_d.all_gather_into_tensor = _orig
+assert calls["n"] == (1 if world > 1 else 0), calls       # collective-free trajectory
+np.save(os.environ["UCDIR_OUT"] + ".batch.rank%d.npy" % rank, res_c.numpy())
+if world > 1:
     dist.barrier(); dist.destroy_process_group()
 '''
 
@@ -66,12 +95,16 @@ def _run(world, tmp_path, tag):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o[-3000:]
-    return [np.load(str(tmp_path / tag) + ".rank%d.npy" % r) for r in range(world)]
+    return [(np.load(str(tmp_path / tag) + ".rank%d.npy" % r), np.load(str(tmp_path / tag) + ".batch.rank%d.npy" % r))
+            for r in range(world)]
 
 
 def test_two_ranks_match_single_process(tmp_path):
-    single = _run(1, tmp_path, "w1")[0]
-    r0, r1 = _run(2, tmp_path, "w2")
+    single, single_b = _run(1, tmp_path, "w1")[0]
+    (r0, b0), (r1, b1) = _run(2, tmp_path, "w2")
+    # batch sharding: rank 0 ran samples 0-1, rank 1 sample 2; after the single end-of-trajectory gather both hold all rows
+    assert np.array_equal(b0, b1) and b0.shape == single_b.shape == (3 * 3, 3, 40, 48)
+    np.testing.assert_allclose(b0, single_b, rtol=0, atol=1e-6)
     # both ranks hold the full stitched result after the all-gather and drew the same noise (broadcast seed)
     assert np.array_equal(r0, r1)
     assert np.isfinite(r0).all() and r0.shape == single.shape

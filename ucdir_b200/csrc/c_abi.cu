@@ -18,6 +18,12 @@ static void prof_mark(cudaStream_t st, int op_index, int kind) {
   g_ev_op[g_ev_used] = op_index; g_ev_kind[g_ev_used] = kind;
   cudaEventRecord(g_ev[g_ev_used++], st);
 }
+int sm_count() {
+  static int n_dev[UCDIR_MAX_DEV] = {};
+  const int d = cur_dev();
+  if (!n_dev[d]) { cudaDeviceGetAttribute(&n_dev[d], cudaDevAttrMultiProcessorCount, d); if (n_dev[d] <= 0) n_dev[d] = 148; }
+  return n_dev[d];
+}
 void set_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }

@@ -42,6 +42,13 @@ __device__ __forceinline__ GnScalars gn_scalars(const double* s0, const double* 
 }
 
 void set_error(const char* fmt, ...);
+
+// Per-device caches: function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) and the SM count belong to a DEVICE,
+// not to the process -- a process that touches a second GPU must opt in again there.  Launch-side statics are indexed by
+// the current device ordinal.
+constexpr int UCDIR_MAX_DEV = 64;
+inline int cur_dev() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < UCDIR_MAX_DEV) ? d : 0; }
+int sm_count();   // multiprocessors of the current device (cached per device, c_abi.cu)
 extern long long g_launches;
 
 // launchers implemented per translation unit

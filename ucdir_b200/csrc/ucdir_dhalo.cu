@@ -330,7 +330,8 @@ template <int NT, int ACT, int KC, int RES>
 static int launch_dh_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& b2, const DhParams& p, int grid,
                           cudaStream_t st) {
   using S = DhCfg<NT, KC, RES>;
-  static bool attr = false;
+  static bool attr_dev[UCDIR_MAX_DEV] = {};
+  bool& attr = attr_dev[cur_dev()];
   if (!attr) {
     if (int rc = check_reg_pool((const void*)dense_halo_kernel<NT, ACT, KC, RES>, "tc_dense_halo", 32 * DH_FIRST_EPI_WARP, DH_REGS_LOW, 32 * DH_EPI_WARPS, DH_REGS_HIGH)) return rc;
     if (cudaFuncSetAttribute(dense_halo_kernel<NT, ACT, KC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
@@ -432,8 +433,7 @@ int launch_tc_dense_halo(const ucdir_op_t& op, cudaStream_t st) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tc_dense_halo: cuTensorMapEncodeTiled(res_conv weights K=%d N=%d) failed: %d", Ktot, NT, (int)r); return -3; }
   }
-  static int n_sm = 0;
-  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  const int n_sm = sm_count();
   const int grid = items < n_sm ? (int)items : n_sm;       // persistent: one CTA per SM
   const bool act = p.act == 1;
   if (KC == 16) rc = act ? launch_dh_inst<64, 1, 16, 0>(a0, a1, mb, mb2, p, grid, st) : launch_dh_inst<64, 0, 16, 0>(a0, a1, mb, mb2, p, grid, st);

@@ -501,7 +501,8 @@ int launch_softmax_f32(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   if (dry) return 0;
   const int in_ld = op.i[UCDIR_SOFTMAX_I_IN_LD] ? op.i[UCDIR_SOFTMAX_I_IN_LD] : cols;
   if (cols >= 2048 && cols <= 49152) {
-    static int attr = 0;
+    static int attr_dev[UCDIR_MAX_DEV] = {};
+    int& attr = attr_dev[cur_dev()];
     const int bytes = cols * 4;
     if (attr < bytes) {
       if (cudaFuncSetAttribute(softmax_rows_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {

@@ -296,14 +296,14 @@ int launch_tc_final_halo(const ucdir_op_t& op, cudaStream_t st) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tc_final_halo: cuTensorMapEncodeTiled(weights K=%d) failed: %d", Ktot, (int)r); return -3; }
   }
-  static bool attr = false;
+  static bool attr_dev[UCDIR_MAX_DEV] = {};
+  bool& attr = attr_dev[cur_dev()];
   if (!attr) {
     if (cudaFuncSetAttribute(final_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_TOTAL) != cudaSuccess) {
       set_error("tc_final_halo: cannot opt in to %d bytes of shared memory: %s", FH_TOTAL, cudaGetErrorString(cudaGetLastError())); return -3; }
     attr = true;
   }
-  static int n_sm = 0;
-  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  const int n_sm = sm_count();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(items < n_sm ? items : n_sm)); cfg.blockDim = dim3(FH_THREADS); cfg.dynamicSmemBytes = FH_TOTAL; cfg.stream = st;
   cudaLaunchAttribute attrs[1];

@@ -399,7 +399,8 @@ static const bool g_mix_pdl = []() { const char* e = getenv("UCDIR_PDL"); return
 template <int CG>
 static int launch_mix_inst(const CUtensorMap& a, const CUtensorMap& b, const MixParams& p, int grid, cudaStream_t st) {
   using S = MixCfg<CG>;
-  static bool attr = false;
+  static bool attr_dev[UCDIR_MAX_DEV] = {};
+  bool& attr = attr_dev[cur_dev()];
   if (!attr) {
     if (int rc = check_reg_pool((const void*)mix_halo_kernel<CG>, "tc_mix_halo", 32 * MX_FIRST_EPI_WARP, MX_REGS_LOW, 32 * MX_EPI_WARPS, MX_REGS_HIGH)) return rc;
     if (cudaFuncSetAttribute(mix_halo_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
@@ -470,8 +471,7 @@ int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tc_mix_halo: cuTensorMapEncodeTiled(weights K=%d N=%d) failed: %d", Ktot, p.Ntot, (int)r); return -3; }
   }
-  static int n_sm = 0;
-  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  const int n_sm = sm_count();
   const int grid = units < n_sm ? (int)units : n_sm;       // persistent: one CTA per SM
   int rc;
   if (CG == 8) rc = launch_mix_inst<8>(ma, mb, p, grid, st);

@@ -644,7 +644,8 @@ template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT, int SPS>
 static int launch_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t st) {
   using S = TcCfg<KA, KB, NT, NSPLIT, BSTAT, SPS>;
   const int smem_bytes = S::TOTAL + (BSTAT ? p.bres_bytes : 0) + (p.ctab ? 9 * p.Ntot * 4 + 16 : 0);
-  static int attr = 0;
+  static int attr_dev[UCDIR_MAX_DEV] = {};
+  int& attr = attr_dev[cur_dev()];
   if (attr < smem_bytes) {
     if (cudaFuncSetAttribute(tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT, SPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
       set_error("tc_conv: cannot opt in to %d bytes of shared memory: %s", smem_bytes, cudaGetErrorString(cudaGetLastError())); return -3; }
@@ -757,8 +758,7 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   if (p.w_batched) rc = make_w_map(&bm, w, C0, op.i[UCDIR_TC_I_W_ROWS] ? op.i[UCDIR_TC_I_W_ROWS] : p.Ntot, KB, NT, w_rowstride, p.B, w_batchstride);
   else rc = make_w_map(&bm, w, Ktot, p.Ntot, KB, NT, Ktot, 0, 0);
   if (rc) return rc;
-  static int n_sm = 0;
-  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  const int n_sm = sm_count();
   const long long items = (long long)mt * (p.Ntot / NT);
   dim3 grid((unsigned)(items < n_sm ? items : n_sm), 1, 1);      // persistent: one CTA per SM
   p.ctab = (p.mode == 1 && p.gn && p.ncls == 9 && p.bn == 1 && p.Ntot <= 1024 && KC == 32 && KB == 16 && op.i[UCDIR_TC_I_NO_CTAB] == 0 &&

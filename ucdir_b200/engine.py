@@ -48,6 +48,37 @@ def _stream(dev) -> int:
     return torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0
 
 
+class _NullGuard:
+    def __enter__(self): return self
+    def __exit__(self, *a): return False
+
+
+_NULL_GUARD = _NullGuard()
+
+
+def _on_device(fn):
+    """Method decorator: run with self.dev as the current CUDA device (see _device_guard)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        g = _device_guard(self.dev)
+        if g is _NULL_GUARD:
+            return fn(self, *a, **k)
+        with g:
+            return fn(self, *a, **k)
+    return wrapper
+
+
+def _device_guard(dev):
+    """Make `dev` the current CUDA device around library calls: ucdir_run_ops / graph capture launch on the CURRENT device
+    with a stream handle of `dev`, so a process that touches a second GPU must switch first.  A no-op when it already is
+    current (the one-process-per-GPU launch) and on the CPU test seam."""
+    if dev.type != "cuda" or _TEST_CPU_PLAN or torch.cuda.current_device() == (dev.index or 0):
+        return _NULL_GUARD
+    return torch.cuda.device(dev)
+
+
 # ======================================================================================
 # geometry: which windows of which (reflect padded) image form the tile batch
 # ======================================================================================
@@ -481,6 +512,10 @@ class _Builder:
 # UNet engine
 # ======================================================================================
 MAX_STAT_SLOTS = 192
+PRECISIONS = ("fp32", "bf16", "fp32_tc")
+"""fp32: SIMT FFMA kernels (debug / bit-level reference of the kernel semantics).  bf16: tcgen05, bf16 operands, stated bf16
+tolerance.  fp32_tc: tcgen05 with split operands (x = hi + lo, both bf16; hi*hi + hi*lo + lo*hi accumulated in fp32 TMEM),
+meets the reference's fp32 tolerance (rtol 1e-3 / atol 1e-4) at one third of the bf16 tensor rate (SURVEY 8d "Tolerances")."""
 
 
 def _max_chunk_pixels():
@@ -496,21 +531,34 @@ class UNetEngine:
         self.blocks: List[Tuple[str, object]] = []
         self._sessions: Dict[tuple, "Session"] = {}
         self._geo_cache: Dict[tuple, Geometry] = {}
-        self.precision = os.environ.get("UCDIR_PRECISION", "fp32")    # "fp32" (parity path) | "bf16" (tcgen05 path)
-        if self.precision not in ("fp32", "bf16"):
-            raise ValueError("UCDIR_PRECISION must be fp32 or bf16")
+        self._params: Optional[list] = None
+        self._packed_version = -1
+        self.precision = os.environ.get("UCDIR_PRECISION", "fp32")    # see PRECISIONS
+        if self.precision not in PRECISIONS:
+            raise ValueError("UCDIR_PRECISION must be one of %s" % (PRECISIONS,))
+        self.shard_mode = os.environ.get("UCDIR_SHARD", "none")       # "none" | "tiles" | "batch" 
+        if self.shard_mode not in ("none", "tiles", "batch"):
+            raise ValueError("UCDIR_SHARD must be none, tiles or batch")
 
     # ---- weights ------------------------------------------------------------------------
     def invalidate_weights(self):
         self.ws = None
+        self._params = None
         self._sessions.clear()
 
     def invalidate_schedule(self):
         pass                            # levels are per-step kernel arguments; nothing cached per schedule
 
+    def set_shard_mode(self, mode: str):
+        if mode not in ("none", "tiles", "batch"):
+            raise ValueError("shard mode must be none, tiles or batch")
+        if mode != self.shard_mode:
+            self.shard_mode = mode
+            self._sessions.clear()
+
     def set_precision(self, precision: str):
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be fp32 or bf16")
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % (PRECISIONS,))
         if precision != self.precision:
             self.precision = precision
             self.invalidate_weights()
@@ -525,11 +573,22 @@ class UNetEngine:
                 if isinstance(layer, U.ResnetBlocWithAttn):
                     yield "%s.%d" % (grp, k), layer
 
+    def _param_version(self) -> int:
+        """Sum of the parameters' in-place version counters: changes when an optimizer step, the reference's EMA update
+        (model/model.py:81-91, `p.data.mul_().add_()`) or any other in-place write touches a weight after it was packed."""
+        if self._params is None:
+            self._params = list(self.m.parameters())
+        return sum(p._version for p in self._params)
+
     def ensure_weights(self):
         dev = self.device()
         _require_cuda(dev)
-        if self.ws is not None and self.ws.device == dev:
+        ver = self._param_version()
+        if self.ws is not None and self.ws.device == dev and ver == self._packed_version:
             return
+        if self.ws is not None:
+            self._sessions.clear()               # plans and captured graphs point at the old packed weights
+        self._packed_version = ver
         ws = WeightStore(dev)
         m = self.m
         inner = m.cfg["inner_channel"]
@@ -927,7 +986,7 @@ class UNetEngine:
         B, _, h, w = cond.shape
         if geometry is None:
             geometry = self.default_geometry(B, h, w)
-        key = (B, h, w, geometry.kind, geometry.TH, geometry.TW, geometry.PD, cond.shape[1], self.precision)
+        key = (B, h, w, geometry.kind, geometry.TH, geometry.TW, geometry.PD, cond.shape[1], self.precision, self.shard_mode)
         s = self._sessions.get(key)
         if s is None:
             self._sessions.clear()                               # one resident plan at a time: plans hold GBs
@@ -997,7 +1056,9 @@ class Session:
         self.in_channels = in_channels          # 3: cond only (x_t supplied per step); 6: already concatenated
         self.group = None
         self.rank, self.world = 0, 1
-        if os.environ.get("UCDIR_SHARD", "tiles") == "tiles" and torch.distributed.is_available() \
+        # Tile sharding is opt-in (UCDIR_SHARD=tiles or engine.shard_mode = "tiles"): the reference's own launcher line runs
+        # a DIFFERENT image on every rank (data/__init__.py:30), which must keep working untouched under torchrun.
+        if eng.shard_mode == "tiles" and torch.distributed.is_available() \
                 and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
             self.group = torch.distributed.group.WORLD
             self.rank, self.world = torch.distributed.get_rank(), torch.distributed.get_world_size()
@@ -1094,6 +1155,9 @@ class Session:
                            "UCDIR_SCATTER_I_MODE": 0, "UCDIR_SCATTER_I_CLIP": 1, "UCDIR_SCATTER_I_C": 3})
         self._attw_stride = 0
         self._bound = False
+        self._guide_ref, self._guide_ver = None, -1
+        self._cond_ref, self._cond_ver = None, -1
+        self.n_binds = 0                         # guidance recomputations (tests assert on it)
 
     # per-sample attw addressing: sample b of chunk starting at tile a reads attw[(a + b) * stride]
     def _chunk_attw_fix(self, sub: OpList, a: int):
@@ -1120,18 +1184,40 @@ class Session:
         return _stream(self.dev)
 
     def bind(self, cond: torch.Tensor, guide: torch.Tensor):
-        """Copy the conditioning batch in and (re)compute the step-invariant guidance maps.  Re-binding the
-        very same tensors (same storage, same version counter) is a no-op, so a stateless p_sample() per step
-        does not redo per-image work."""
-        sig = (cond.data_ptr(), cond._version, tuple(cond.shape), guide.data_ptr(), guide._version, tuple(guide.shape))
-        if self._bound and sig == getattr(self, "_bind_sig", None):
-            return
-        self._bind_sig = sig
+        """Copy the conditioning batch in and (re)compute the step-invariant guidance maps.
+
+        `cond` is copied on every call (12.6 MB D2D at 1024^2: microseconds next to a UNet step).  The guidance maps depend
+        on `guide` only; they are recomputed unless the caller passes the very same tensor OBJECT again, unmodified.  The
+        session keeps a strong reference to the bound guide, so "same object" cannot be a recycled allocation (round 1
+        compared data_ptr / _version / shape, which a fresh tensor landing on a freed block of the caching allocator also
+        satisfies -> the previous image's guidance was silently reused)."""
         self.cond.copy_(cond)
+        same = self._bound and (guide is self._guide_ref) and guide._version == self._guide_ver
+        if self.group is not None and not (same and cond is self._cond_ref and cond._version == self._cond_ver):
+            self._check_ranks_agree(cond, guide)
+            self._cond_ref, self._cond_ver = cond, cond._version
+        if same:
+            return
         self.guide.copy_(guide)
-        if len(self.static_ops):
-            _run_ops(self.static_ops.array(), len(self.static_ops), self.stream())
+        self._guide_ref, self._guide_ver = guide, guide._version
+        with _device_guard(self.dev):
+            if len(self.static_ops):
+                _run_ops(self.static_ops.array(), len(self.static_ops), self.stream())
         self._bound = True
+        self.n_binds += 1
+
+    def _check_ranks_agree(self, cond, guide):
+        """Tile sharding computes ONE image with all ranks: every rank must hold the same conditioning batch.  (The
+        reference's own multi-GPU mode gives every rank a different image, data/__init__.py:30; mixing the two would
+        stitch tiles of different images.)  One small all-gather of two checksums per image."""
+        mine = torch.stack([cond.double().sum(), guide.double().sum()]).to(self.dev)
+        allv = torch.empty(self.world * 2, dtype=torch.float64, device=self.dev)
+        torch.distributed.all_gather_into_tensor(allv, mine, group=self.group)
+        allv = allv.view(self.world, 2)
+        if not bool((allv == allv[0:1]).all().item()):
+            raise RuntimeError("UCDIR_SHARD=tiles: ranks hold different conditioning images (checksums %s); tile sharding "
+                               "needs the same image on every rank -- use the default (one image per rank) otherwise"
+                               % allv.tolist())
 
     # ---- one UNet evaluation over all tiles, result stitched to NCHW ---------------------------
     def _run_unet(self, x_t: Optional[torch.Tensor]):
@@ -1144,6 +1230,7 @@ class Session:
         if self.group is not None:
             self._all_gather()
 
+    @_on_device
     def eps_only(self, levels: torch.Tensor, out: torch.Tensor):
         """Generic DY3h.forward: per-image noise levels from a device tensor, eps stitched into `out`."""
         g = self.geo
@@ -1160,6 +1247,7 @@ class Session:
         self.tail_ops._arr = None
         _run_ops(self.tail_ops.array(), 1, self.stream())
 
+    @_on_device
     def step(self, x_t: torch.Tensor, out: torch.Tensor, level: float, scalars, noise: Optional[torch.Tensor],
              clip: bool = True):
         """One p_sample (model/diffusion.py:160-183): eps = UNet(cat[cond, x_t], level); posterior update."""
@@ -1236,6 +1324,7 @@ class Session:
                 graphs.append((_lib.Graph(body.array(), len(body)), _lib.Graph(tail.array(), 1)))
         self.graphs = graphs
 
+    @_on_device
     def load_state(self, x: torch.Tensor):
         self.ensure_resident()
         if self.use_graphs and self.graphs is None:
@@ -1246,6 +1335,7 @@ class Session:
     def state(self) -> torch.Tensor:
         return self.xbuf[self.cur]
 
+    @_on_device
     def step_resident(self, params_row: torch.Tensor):
         """One p_sample on the resident state.  params_row: device float[8] for this step (D2D copied into the
         slot the ops read); the caller has already filled self.noise when the step uses noise."""
@@ -1293,6 +1383,7 @@ class PredictorEngine:
 
     def invalidate_weights(self):
         self.ws = None
+        self._params = None
         self._plans.clear()
 
     def device(self):
@@ -1301,8 +1392,13 @@ class PredictorEngine:
     def ensure_weights(self):
         dev = self.device()
         _require_cuda(dev)
-        if self.ws is not None and self.ws.device == dev:
+        if getattr(self, "_params", None) is None:
+            self._params = list(self.m.parameters())
+        ver = sum(p._version for p in self._params)
+        if self.ws is not None and self.ws.device == dev and ver == getattr(self, "_packed_version", -1):
             return
+        self._packed_version = ver
+        self._plans.clear()
         ws = WeightStore(dev)
         for name, layer in self.m.named_children():
             if isinstance(layer, torch.nn.ConvTranspose2d):
@@ -1409,7 +1505,8 @@ class PredictorEngine:
         out = torch.empty((B, 3, h, w), dtype=F32, device=x.device)
         ol.ops[idx_scatter].p[K_["UCDIR_SCATTER_P_OUT"]] = out.data_ptr()
         ol._arr = None
-        _run_ops(ol.array(), len(ol), _stream(x.device))
+        with _device_guard(x.device):
+            _run_ops(ol.array(), len(ol), _stream(x.device))
         return out
 
 
@@ -1478,7 +1575,8 @@ def run_film_block(mod, x: torch.Tensor, time_emb: torch.Tensor) -> torch.Tensor
         res = x_nhwc
     _conv_op(ol, src0=A(a2, Co), w=w2.data_ptr(), bias=b2.data_ptr(), res=A(res, Co), dst=A(h2, Co), cout=Co, B=B)
     ol.add("UCDIR_OP_LAYOUT", {0: h2.data_ptr(), 1: out.data_ptr()}, {0: B, 1: Co, 2: H * W, 3: 1})
-    _run_ops(ol.array(), len(ol), _stream(dev))
+    with _device_guard(dev):
+        _run_ops(ol.array(), len(ol), _stream(dev))
     if dev.type == "cuda":
         torch.cuda.current_stream(dev).synchronize()      # buffers in `keep` are released when this returns
     return out

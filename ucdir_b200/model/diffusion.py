@@ -127,13 +127,26 @@ class GaussianDiffusion(nn.Module):
         self._shared_gen = torch.Generator(device=device)
         self._shared_gen.manual_seed(int(seed.item()))
 
+    _SCHED_KEYS = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                   "posterior_mean_coef2", "posterior_log_variance_clipped", "alphas_cumprod")
+
+    def _host_schedule(self):
+        """fp32 host copies of the schedule vectors the samplers read.  Rebuilt from the registered buffers when they arrived
+        through load_state_dict only (no set_new_noise_schedule call on this object)."""
+        if self._sched_host is None:
+            if not hasattr(self, "betas"):
+                raise RuntimeError("no noise schedule: call set_new_noise_schedule(schedule_opt, device) first "
+                                   "(model/diffusion.py:101)")
+            self._sched_host = {k: getattr(self, k).detach().float().cpu().numpy() for k in self._SCHED_KEYS}
+            if getattr(self, "sqrt_alphas_cumprod_prev", None) is None:
+                ac = getattr(self, "alphas_cumprod").detach().double().cpu().numpy()
+                self.sqrt_alphas_cumprod_prev = np.sqrt(np.append(1.0, ac))
+            self.num_timesteps = int(self.betas.shape[0])
+        return self._sched_host
+
     def _step_scalars(self, t):
         """The five per-step scalars of model/diffusion.py:150-158,183 as fp32 values."""
-        s = self._sched_host
-        if s is None:  # schedule buffers arrived through load_state_dict only
-            s = self._sched_host = {k: getattr(self, k).detach().float().cpu().numpy() for k in (
-                "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
-                "posterior_mean_coef2", "posterior_log_variance_clipped")}
+        s = self._host_schedule()
         sigma = np.exp(np.float32(0.5) * s["posterior_log_variance_clipped"][t], dtype=np.float32)
         return (float(s["sqrt_recip_alphas_cumprod"][t]), float(s["sqrt_recipm1_alphas_cumprod"][t]),
                 float(s["posterior_mean_coef1"][t]), float(s["posterior_mean_coef2"][t]), float(sigma))
@@ -141,6 +154,7 @@ class GaussianDiffusion(nn.Module):
     def _params_table(self, device, clip=True):
         """Device table [T, 9] of the per-step kernel scalars {level, A, B, C1, C2, sigma, clip, use_noise, C3}
         (model/diffusion.py:150-163,183), built once per schedule; a step D2D-copies its row (no per-step H2D)."""
+        self._host_schedule()
         key = (str(device), self.num_timesteps, bool(clip), id(self._sched_host))
         if getattr(self, "_ptable_key", None) != key:
             rows = [[self.noise_level(t), *self._step_scalars(t), 1.0 if clip else 0.0, 1.0 if t > 0 else 0.0, 0.0]
@@ -161,13 +175,22 @@ class GaussianDiffusion(nn.Module):
         """fp32 value of sqrt_alphas_cumprod_prev[t+1] (model/diffusion.py:162-163)."""
         return float(np.float32(self.sqrt_alphas_cumprod_prev[t + 1]))
 
+    def _guide_of(self, kwargs):
+        g = (kwargs or {}).get("guide")
+        if g is None:
+            # the reference fails at the same place: DY3h.forward(x, time, guide) has no default for `guide`
+            # (model/ucdir.py:295), so guide-less samplers raise TypeError from inside denoise_fn
+            raise TypeError("DY3h.forward() missing 1 required positional argument: 'guide' (the only UNet the reference "
+                            "ships needs kwargs={'guide': ...}; model/diffusion.py:166, model/ucdir.py:295)")
+        return g
+
     @torch.no_grad()
     def p_sample(self, x, t, clip_denoised=True, condition_x=None, kwargs={}):
         """model/diffusion.py:160-183 for one step on explicit tensors (generic entry; the loop below
         uses a resident session instead)."""
         if condition_x is None:
             raise NotImplementedError("ucdir_b200: unconditional sampling is not on the hot path")
-        sess = self.denoise_fn.engine().session(condition_x, kwargs["guide"])
+        sess = self.denoise_fn.engine().session(condition_x, self._guide_of(kwargs))
         self._sync_noise_stream(sess, x.device)
         table = self._params_table(x.device, clip_denoised)
         sess.load_state(x)
@@ -176,6 +199,78 @@ class GaussianDiffusion(nn.Module):
         sess.step_resident(table[t])
         return sess.state().clone()
 
+    # ---- batch sharding: samples are independent for the whole trajectory -------------------------
+    def _batch_rows(self, b):
+        """(lo, hi, per, world, group) of this rank's samples when the engine is in shard mode "batch" under an
+        initialised process group; (0, b, b, 1, None) otherwise."""
+        eng = self.denoise_fn.engine()
+        dist = torch.distributed
+        if eng.shard_mode != "batch" or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return 0, b, b, 1, None
+        world, rank = dist.get_world_size(), dist.get_rank()
+        per = (b + world - 1) // world
+        lo = min(rank * per, b)
+        return lo, min(lo + per, b), per, world, dist.group.WORLD
+
+    def _run_steps(self, x, guide, table, use_noise, snap):
+        """The sampler loop shared by p_sample_loop and ddim_sample: K steps whose kernel scalars are the rows of the
+        device `table`; use_noise[k]: draw z before step k; snap[k]: record the state after step k.  Returns
+        (snapshots [n_snap, b, C, H, W], final state [b, C, H, W]).
+
+        Shard mode "batch": every rank runs the whole trajectory for its own b/world samples -- no per-step collective -- and
+        ONE all-gather at the end reassembles the batch (the reference's multi-GPU mode, data/__init__.py:30, is the
+        same idea at image granularity).  With an injected noise source every rank draws the full-batch tensor and keeps its
+        rows, so sharded == unsharded bit for bit."""
+        b, device = x.shape[0], x.device
+        lo, hi, per, world, group = self._batch_rows(b)
+        n_snap = sum(1 for v in snap if v)
+        shape_full = tuple(x.shape)
+        if hi > lo:
+            xs, gs = (x, guide) if world == 1 else (x[lo:hi].contiguous(), guide[lo:hi].contiguous())
+            sess = self.denoise_fn.engine().session(xs, gs)
+            self._sync_noise_stream(sess, device)
+
+            def draw(dst=None):
+                if world == 1:
+                    if dst is None:
+                        return self._randn(shape_full, device)
+                    return self._fill_noise(dst)
+                if self._noise_source is not None:
+                    z = self._noise_source(shape_full).to(device=device, dtype=torch.float32)[lo:hi]
+                else:
+                    z = torch.randn((hi - lo,) + shape_full[1:], device=device)
+                if dst is None:
+                    return z
+                dst.copy_(z)
+
+            sess.load_state(draw())
+            snaps = torch.empty((n_snap, per) + shape_full[1:], device=device, dtype=torch.float32)
+            row = 0
+            for k in range(table.shape[0]):
+                if use_noise[k]:
+                    draw(sess.noise)
+                sess.step_resident(table[k])
+                if snap[k]:
+                    snaps[row, :hi - lo] = sess.state()
+                    row += 1
+            final = sess.state()
+        else:                                   # more ranks than samples: this rank only takes part in the gather
+            if self._noise_source is not None:
+                for k in range(1 + sum(1 for v in use_noise if v)):
+                    self._noise_source(shape_full)
+            snaps = torch.zeros((n_snap, per) + shape_full[1:], device=device, dtype=torch.float32)
+            final = None
+        if world == 1:
+            return snaps, final.clone()
+        mine = torch.zeros((n_snap + 1, per) + shape_full[1:], device=device, dtype=torch.float32)
+        mine[:n_snap] = snaps
+        if final is not None:
+            mine[n_snap, :hi - lo] = final
+        allr = torch.empty(world * mine.numel(), device=device, dtype=torch.float32)
+        torch.distributed.all_gather_into_tensor(allr, mine.view(-1), group=group)
+        allr = allr.view((world,) + tuple(mine.shape)).permute(1, 0, 2, 3, 4, 5).reshape((n_snap + 1, world * per) + shape_full[1:])[:, :b]
+        return allr[:n_snap].contiguous(), allr[n_snap].contiguous()
+
     @torch.no_grad()
     def p_sample_loop(self, x_in, continous=False, kwargs={}):
         """model/diffusion.py:185-211 (conditional branch): ancestral sampling, snapshots every
@@ -183,27 +278,21 @@ class GaussianDiffusion(nn.Module):
         preallocated and written in place."""
         if not self.conditional:
             raise NotImplementedError("ucdir_b200: unconditional sampling is not on the hot path")
+        guide = self._guide_of(kwargs)
+        self._host_schedule()
         T = self.num_timesteps
         sample_inter = 1 | (T // 10)
         x = x_in.contiguous().float()
         b = x.shape[0]
-        device = x.device
-        n_snap = sum(1 for i in range(T) if i % sample_inter == 0)
-        ret = torch.empty((b * (1 + n_snap),) + tuple(x.shape[1:]), device=device, dtype=torch.float32)
+        order = list(reversed(range(T)))
+        table = self._params_table(x.device)[order]
+        snaps, final = self._run_steps(x, guide, table, [i > 0 for i in order], [i % sample_inter == 0 for i in order])
+        if not continous:
+            return snaps[-1, -1] if snaps.shape[0] else x[-1]                # ret_img[-1] (model/diffusion.py:211)
+        ret = torch.empty((b * (1 + snaps.shape[0]),) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
         ret[:b] = x
-        sess = self.denoise_fn.engine().session(x, kwargs["guide"])
-        self._sync_noise_stream(sess, device)
-        table = self._params_table(device)
-        sess.load_state(self._randn(x.shape, device))
-        row = 1
-        for i in reversed(range(T)):
-            if i > 0:
-                self._fill_noise(sess.noise)
-            sess.step_resident(table[i])
-            if i % sample_inter == 0:
-                ret[row * b:(row + 1) * b] = sess.state()
-                row += 1
-        return ret if continous else ret[-1]
+        ret[b:] = snaps.reshape((-1,) + tuple(x.shape[1:]))
+        return ret
 
     @torch.no_grad()
     def ddim_sample(self, x_in, continous=False, kwargs={}, sampling_timesteps=5, eta=1.0):
@@ -212,13 +301,15 @@ class GaussianDiffusion(nn.Module):
         x0 = clamp(a_t x - b_t eps);  x <- sqrt(abar_next) x0 + c eps + sigma z, and x <- x0 on the last step.
         Same kernels as p_sample: only the scalars of the fused posterior op differ."""
         self.ddim_sampling_eta, self.sampling_timesteps, self.objective = eta, sampling_timesteps, "pred_noise"
+        guide = self._guide_of(kwargs)
         x = x_in.contiguous().float()
         device = x.device
+        host = self._host_schedule()
         T = self.num_timesteps
         times = list(reversed(torch.linspace(-1, T - 1, steps=sampling_timesteps + 1).int().tolist()))
         pairs = list(zip(times[:-1], times[1:]))
         ac = self.alphas_cumprod.detach().float().cpu()                      # fp32, as the reference's buffer
-        a_tab, b_tab = self._sched_host["sqrt_recip_alphas_cumprod"], self._sched_host["sqrt_recipm1_alphas_cumprod"]
+        a_tab, b_tab = host["sqrt_recip_alphas_cumprod"], host["sqrt_recipm1_alphas_cumprod"]
         rows = []
         for time, time_next in pairs:
             if time_next < 0:
@@ -230,17 +321,21 @@ class GaussianDiffusion(nn.Module):
             rows.append([self.noise_level(time), float(a_tab[time]), float(b_tab[time]), float(alpha_next.sqrt()), 0.0,
                          float(sigma), 1.0, 1.0, float(c)])
         table = torch.tensor(rows, dtype=torch.float32, device=device)
-        sess = self.denoise_fn.engine().session(x, kwargs["guide"])
+        if not continous:
+            return self._run_steps(x, guide, table, [tn >= 0 for _, tn in pairs], [False] * len(pairs))[1]
+        # continous: the reference stacks [initial noise, state after every step] along dim 1 (model/diffusion.py:257,289,293)
+        if self._batch_rows(x.shape[0])[3] != 1:
+            raise NotImplementedError("ddim_sample(continous=True) is not batch-sharded; use continous=False")
+        sess = self.denoise_fn.engine().session(x, guide)
         self._sync_noise_stream(sess, device)
         sess.load_state(self._randn(x.shape, device))
-        imgs = [sess.state().clone()] if continous else None
+        imgs = [sess.state().clone()]
         for k, (time, time_next) in enumerate(pairs):
             if time_next >= 0:
                 self._fill_noise(sess.noise)
             sess.step_resident(table[k])
-            if continous:
-                imgs.append(sess.state().clone())
-        return torch.stack(imgs, dim=1) if continous else sess.state().clone()
+            imgs.append(sess.state().clone())
+        return torch.stack(imgs, dim=1)
 
     @torch.no_grad()
     def sample(self, batch_size=1, continous=False):
@@ -248,7 +343,7 @@ class GaussianDiffusion(nn.Module):
 
     @torch.no_grad()
     def super_resolution(self, x_in, continous=False):
-        """model/diffusion.py:302-304."""
+        """model/diffusion.py:302-304.  No guide is passed, so with DY3h this raises TypeError -- in the reference as well."""
         return self.p_sample_loop(x_in, continous)
 
     def p_losses(self, x_in, noise=None):
@@ -298,3 +393,39 @@ class ResiGaussianGuideDY_initxloss(ResiGaussianGuideDY):
     def super_resolution(self, x_in, continous=False):
         initx = self.predictor(x_in)
         return self.p_sample_loop(x_in, continous, kwargs={"guide": initx}) + initx
+
+
+class _GuidelessResidual(GaussianDiffusion):
+    """Shared body of the reference's guide-less residual wrappers: `initx = predictor(x)`, then a sampler that calls
+    `denoise_fn(cat[cond, x], level)` WITHOUT a guide.  The only UNet the reference ships (`DY3h`, model/ucdir.py:295) has no
+    default for `guide`, so in the reference these wrappers raise TypeError from inside `denoise_fn` on the first step
+    (SURVEY 2.1 #14, 8f#4); the mirror keeps the constructor (same parameters, same state_dict keys, same RNG draw order:
+    denoise_fn first, predictor second) and the same failure, after running the predictor like the reference does."""
+
+    def __init__(self, denoise_fn, image_size, channels=3, loss_type="l1", conditional=True, schedule_opt=None):
+        super().__init__(denoise_fn, image_size, channels, loss_type, conditional, schedule_opt)
+        self.predictor = UNetSeeInDark()
+
+    @torch.no_grad()
+    def super_resolution(self, x_in, continous=False):
+        initx = self.predictor(x_in)
+        return self.p_sample_loop(x_in, continous) + initx           # -> TypeError: guide (as in the reference)
+
+
+class ResiGaussianDiffusion(_GuidelessResidual):
+    """model/diffusion.py:393-432."""
+
+
+class ResiPercepGaussianDiffusion(_GuidelessResidual):
+    """model/diffusion.py:573-622 (differs from ResiGaussianDiffusion in its training loss only)."""
+
+
+class NoDiffusion(_GuidelessResidual):
+    """model/diffusion.py:625-662: no sampler loop -- `denoise_fn(predictor(x), level_1)` in one call, again without a guide
+    (and with a 3-channel input for a 6-channel in-conv): TypeError in the reference, TypeError here."""
+
+    @torch.no_grad()
+    def super_resolution(self, x_in, continous=False):
+        initx = self.predictor(x_in)
+        self._guide_of(None)                                          # raises
+        return initx
