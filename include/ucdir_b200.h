@@ -38,10 +38,10 @@
 extern "C" {
 #endif
 
-#define UCDIR_ABI_VERSION 12
+#define UCDIR_ABI_VERSION 13
 
 #define UCDIR_OP_NPTR 16
-#define UCDIR_OP_NINT 48
+#define UCDIR_OP_NINT 56
 #define UCDIR_OP_NFLT 8
 
 typedef struct ucdir_op {
@@ -143,7 +143,8 @@ enum ucdir_temb_flt { UCDIR_TEMB_F_LEVEL = 0 };
 /* ---- UCDIR_OP_GATHER_TILES: DST[BT,TH,TW,CD] from NCHW fp32 images with on-the-fly reflect padding -------
  * TAB = int32[BT][3] {image index, y0, x0}: tile origin in padded coordinates; source pixel of padded
  * coordinate P is reflect(P - PD) (PD=0 with bottom/right overhang reproduces model/ucdir.py:303-306).
- * Channels: CA from SRC_A, then CB from SRC_B (may be NULL/0), zero-filled up to CD.  OUT_BF16=1 writes bf16. */
+ * Channels: CA from SRC_A, then CB from SRC_B (may be NULL/0), zero-filled up to CD.  OUT_BF16=1 writes bf16;
+ * OUT_BF16=2 writes (hi, lo) bf16 plane pairs, 2*CD elements per pixel (UCDIR_TC_I_SPLIT). */
 enum ucdir_gather_ptr { UCDIR_GATHER_P_SRC_A = 0, UCDIR_GATHER_P_SRC_B = 1, UCDIR_GATHER_P_TAB = 2, UCDIR_GATHER_P_DST = 3 };
 enum ucdir_gather_int {
   UCDIR_GATHER_I_BT = 0, UCDIR_GATHER_I_TH = 1, UCDIR_GATHER_I_TW = 2, UCDIR_GATHER_I_IMG_H = 3,
@@ -225,17 +226,33 @@ enum ucdir_tc_int {
                                                   * same un-normalised input as conv1) from the centre-tap view of the halo box already in shared memory;
                                                   * needs the 64-channel halo schedule (ucdir_dhalo.cu), refused otherwise */
   UCDIR_TC_I_DST_RES_C = 46,                     /* channels per pixel row of DST_RES */
+  /* ---- fp32-tolerance mode ("fp32_tc", SURVEY 8d "Tolerances": split-operand MMA) --------------------------------------
+   * SPLIT = 1: every bf16 tensor of the op is a PAIR of planes (hi, lo) with value = hi + lo (hi = bf16(v), lo = bf16(v - hi):
+   * 16 mantissa bits), stored side by side in the pixel row: [hi: C channels | lo: C channels] (row pitch 2*C elements, so
+   * C0 / C1 / DST_C / RES_C stay the LOGICAL channel counts).  The K loop runs three passes per filter tap,
+   *     A_hi * W_hi  +  A_lo * W_hi  +  A_hi * W_lo      (fp32 accumulation in TMEM; the lo * lo term, 2^-18 relative, is dropped)
+   * with weights packed per tap as [W_hi(src0) | W_hi(src0) | W_hi(src1) | W_hi(src1) | W_lo(src0) | W_lo(src1)]
+   * (grouped: [W_hi | W_hi | W_lo] per group chunk).  The epilogue works in fp32 with the exact Swish, stores (hi, lo) pairs
+   * and accumulates the GroupNorm statistics from the fp32 values.  DST_F32 outputs (attention scores, eps) are plain fp32.
+   * DST2 (transposed V^T) rows are [hi: T_LD | lo: T_LD].  Only the streamed kernel implements it (no halo schedules). */
+  UCDIR_TC_I_SPLIT = 47,
+  UCDIR_TC_I_SRC_LO_OFF = 48,                    /* SPLIT: elements from the hi to the lo plane inside a SRC0 row (0 = C0); with SRC_CSTRIDE for channel slices */
+  UCDIR_TC_I_W_LO_OFF = 49,                      /* SPLIT + W_BATCHED: elements from the hi to the lo plane inside a weight row (W_ROWSTRIDE = physical pitch) */
   UCDIR_TC_I_HALO = 43                           /* 1: halo schedule where it applies (grouped mix convs, C = 64 / 128 / 256): one 10 x 18 pixel TMA box per
                                                   * 8 x 16 pixel tile serves all nine taps, weights stay resident in shared memory (ucdir_mix.cu); 3x3 convs with 64 / 128 output
                                                   * channels: super tiles (ucdir_dhalo.cu) */
 };
 enum ucdir_tc_flt { UCDIR_TC_F_EPS = 0, UCDIR_TC_F_ALPHA = 1 /* 0 = 1.0 */ };
 
-/* ---- UCDIR_OP_GN_APPLY_BF16: DST = [Swish](GroupNorm(1,C)(SRC)) on bf16 NHWC [B][HW][C]; f[0] = eps ------------ */
+/* ---- UCDIR_OP_GN_APPLY_BF16: DST = [Swish](GroupNorm(1,C)(SRC)) on bf16 NHWC [B][HW][C]; f[0] = eps ------------
+ * SPLIT = 1: SRC and DST are (hi, lo) plane pairs [B][HW][2*C] (see UCDIR_TC_I_SPLIT), fp32 math, exact Swish. */
 enum ucdir_gna_ptr { UCDIR_GNA_P_SRC = 0, UCDIR_GNA_P_DST = 1, UCDIR_GNA_P_GAMMA = 2, UCDIR_GNA_P_BETA = 3, UCDIR_GNA_P_STATS = 4 };
-enum ucdir_gna_int { UCDIR_GNA_I_B = 0, UCDIR_GNA_I_HW = 1, UCDIR_GNA_I_C = 2, UCDIR_GNA_I_SWISH = 3 };
+enum ucdir_gna_int { UCDIR_GNA_I_B = 0, UCDIR_GNA_I_HW = 1, UCDIR_GNA_I_C = 2, UCDIR_GNA_I_SWISH = 3, UCDIR_GNA_I_SPLIT = 4 };
 
-/* ---- UCDIR_OP_CAST: p[1][k] = cast(p[0][k]) for k < i[0] + (i[1] << 31); i[2] = 0: fp32 -> bf16, 1: bf16 -> fp32 -- */
+/* ---- UCDIR_OP_CAST: p[1][k] = cast(p[0][k]) for k < i[0] + (i[1] << 31); i[2] = 0: fp32 -> bf16, 1: bf16 -> fp32 --
+ * i[2] = 2 (fp32_tc attention probabilities): rows of fp32 -> rows of (hi, lo) bf16 plane pairs: for r < i[0] + (i[1] << 31),
+ * c < i[3] (COLS): p[1][r][c] = hi, p[1][r][i[5] + c] = lo of p[0][r * i[4] + c]; i[4] = fp32 row pitch, i[5] = plane pitch
+ * (output row = 2 * i[5] elements; columns COLS..i[5] of both planes are zeroed). */
 
 /* ---- UCDIR_OP_GN_STATS_F32 / UCDIR_OP_GN_APPLY_F32: GroupNorm(G, C) with G >= 1 on fp32 NHWC [B][HW][C], for the SR3-style
  * FiLM ResnetBlock (model/ucdir.py:75-100).  STATS = double[B][G][2] {sum, sum of squares}; APPLY: f[0] = eps, SWISH as above. */

@@ -238,12 +238,13 @@ def emu_gather(op, mem):
     BT, TH, TW = _i(op, "UCDIR_GATHER_I_BT"), _i(op, "UCDIR_GATHER_I_TH"), _i(op, "UCDIR_GATHER_I_TW")
     IH, IW, PD = _i(op, "UCDIR_GATHER_I_IMG_H"), _i(op, "UCDIR_GATHER_I_IMG_W"), _i(op, "UCDIR_GATHER_I_PD")
     CA, CB, CD = _i(op, "UCDIR_GATHER_I_CA"), _i(op, "UCDIR_GATHER_I_CB"), _i(op, "UCDIR_GATHER_I_CD")
-    odt = torch.bfloat16 if _i(op, "UCDIR_GATHER_I_OUT_BF16") else torch.float32
+    mode = _i(op, "UCDIR_GATHER_I_OUT_BF16")
+    odt = torch.bfloat16 if mode else torch.float32
     tab = mem.view(_p(op, "UCDIR_GATHER_P_TAB"), (BT, 3), torch.int32).numpy()
     nimg = int(tab[:, 0].max()) + 1
     A = mem.view(_p(op, "UCDIR_GATHER_P_SRC_A"), (nimg, CA, IH, IW))
     Bs = mem.view(_p(op, "UCDIR_GATHER_P_SRC_B"), (nimg, CB, IH, IW)) if CB else None
-    dst = mem.view(_p(op, "UCDIR_GATHER_P_DST"), (BT, TH, TW, CD), odt)
+    dst = mem.view(_p(op, "UCDIR_GATHER_P_DST"), (BT, TH, TW, 2 * CD if mode == 2 else CD), odt)
     for t in range(BT):
         img, y0, x0 = (int(v) for v in tab[t])
         sy = torch.from_numpy(_reflect(np.arange(TH) + y0 - PD, IH))
@@ -252,6 +253,12 @@ def emu_gather(op, mem):
         dst[t, :, :, :CA] = A[img][:, sy][:, :, sx].permute(1, 2, 0).to(odt)
         if CB:
             dst[t, :, :, CA:CA + CB] = Bs[img][:, sy][:, :, sx].permute(1, 2, 0).to(odt)
+        if mode == 2:                                             # lo planes
+            va = A[img][:, sy][:, :, sx].permute(1, 2, 0)
+            dst[t, :, :, CD:CD + CA] = (va - va.to(odt).float()).to(odt)
+            if CB:
+                vb = Bs[img][:, sy][:, :, sx].permute(1, 2, 0)
+                dst[t, :, :, CD + CA:CD + CA + CB] = (vb - vb.to(odt).float()).to(odt)
 
 
 def emu_scatter(op, mem):
@@ -323,9 +330,12 @@ def emu_tc_conv(op, mem):
     eps = _f(op, "UCDIR_TC_F_EPS")
     bf = torch.bfloat16
     Cin = C0 + C1
-    cstride = g("SRC_CSTRIDE") or C0
-    x = mem.view(_p(op, "UCDIR_TC_P_SRC0"), ((B * sH * sW - 1) * cstride + C0,), bf)
-    x = torch.as_strided(x, (B, sH, sW, C0), (sH * sW * cstride, sW * cstride, cstride, 1)).float()
+    split = g("SPLIT")                                           # fp32_tc: (hi, lo) plane pairs, value = hi + lo
+    cstride = g("SRC_CSTRIDE") or (2 * C0 if split else C0)
+    a_lo = (g("SRC_LO_OFF") or C0) if split else 0
+    x = mem.view(_p(op, "UCDIR_TC_P_SRC0"), ((B * sH * sW - 1) * cstride + a_lo + C0,), bf)
+    xs = lambda off: torch.as_strided(x, (B, sH, sW, C0), (sH * sW * cstride, sW * cstride, cstride, 1), off).float()
+    x = xs(0) + xs(a_lo) if split else xs(0)
     if g("SRC_GN_SWISH"):                                        # final_conv: Swish(GroupNorm(x)) on the source, rounded to bf16
         s0 = mem.view(_p(op, "UCDIR_TC_P_STATS0"), (B, 2), torch.float64)
         cnt = float(C0 * sH * sW)
@@ -336,7 +346,10 @@ def emu_tc_conv(op, mem):
         a = rstd * gam.view(1, 1, 1, -1)
         x = swish(x * a + (bet.view(1, 1, 1, -1) - a * mean.float().view(B, 1, 1, 1))).to(bf).float()
     wb = g("W_BATCHED")
-    if C1:
+    if C1 and split:
+        x1 = mem.view(_p(op, "UCDIR_TC_P_SRC1"), (B, sH, sW, 2 * C1), bf).float()
+        x = torch.cat([x, x1[..., :C1] + x1[..., C1:]], dim=-1)
+    elif C1:
         x = torch.cat([x, mem.view(_p(op, "UCDIR_TC_P_SRC1"), (B, sH, sW, C1), bf).float()], dim=-1)
     KB = g("KB") or KC
     if groups > 1:
@@ -349,9 +362,20 @@ def emu_tc_conv(op, mem):
     if wb:                                                       # per-image weights [B][Ntot][C0], strided
         rs = g("W_ROWSTRIDE"); bs = g("W_BATCHSTRIDE_LO") + (g("W_BATCHSTRIDE_HI") << 31)
         n_rows = g("W_ROWS") or Ntot                              # rows beyond the image's extent are TMA zero fill
-        wraw = mem.view(_p(op, "UCDIR_TC_P_W"), ((B - 1) * bs + (n_rows - 1) * rs + C0,), bf)
+        b_lo = g("W_LO_OFF") if split else 0
+        wraw = mem.view(_p(op, "UCDIR_TC_P_W"), ((B - 1) * bs + (n_rows - 1) * rs + b_lo + C0,), bf)
         wbat = torch.zeros(B, Ntot, C0)
         wbat[:, :n_rows] = torch.as_strided(wraw, (B, n_rows, C0), (bs, rs, 1)).float()
+        if split:
+            wbat[:, :n_rows] += torch.as_strided(wraw, (B, n_rows, C0), (bs, rs, 1), b_lo).float()
+    elif split:
+        # per tap [W_hi(s0) | W_hi(s0) | W_hi(s1) | W_hi(s1) | W_lo(s0) | W_lo(s1)] (grouped: [W_hi | W_hi | W_lo])
+        w3 = mem.view(_p(op, "UCDIR_TC_P_W"), (Ntot, nty * ntx, 3 * ktap), bf).float()
+        c0k = ktap if groups > 1 else C0
+        c1k = ktap - c0k
+        h0, h0b, h1, h1b, l0, l1 = torch.split(w3, [c0k, c0k, c1k, c1k, c0k, c1k], dim=-1)
+        assert torch.equal(h0, h0b) and torch.equal(h1, h1b), "SPLIT weight rows: the two W_hi copies differ"
+        wp = torch.cat([h0 + l0, h1 + l1], dim=-1)
     else:
         wp = mem.view(_p(op, "UCDIR_TC_P_W"), (Ntot, nty * ntx, ktap), bf).float()
     acc = torch.zeros(B, H, W, Ntot)
@@ -404,32 +428,52 @@ def emu_tc_conv(op, mem):
         a = att * aw.view(B, 1, 1, 8)
         c = Ntot // 8
         h = (v.reshape(B, H, W, c, 8) * a.unsqueeze(3)).sum(-1)
-        res = mem.view(_p(op, "UCDIR_TC_P_RES"), (B, H, W, resC), bf)[..., :c].float()
+        if split:
+            r2 = mem.view(_p(op, "UCDIR_TC_P_RES"), (B, H, W, 2 * resC), bf).float()
+            res = r2[..., :c] + r2[..., resC:resC + c]
+        else:
+            res = mem.view(_p(op, "UCDIR_TC_P_RES"), (B, H, W, resC), bf)[..., :c].float()
         out = swish(h) + res
         nout = c
     else:
         if act == 1:
             v = swish(v)
         rp = _p(op, "UCDIR_TC_P_RES")
-        if rp:
+        if rp and split:
+            r2 = mem.view(rp, (B, H, W, 2 * resC), bf).float()
+            v = v + r2[..., :Ntot] + r2[..., resC:resC + Ntot]
+        elif rp:
             v = v + mem.view(rp, (B, H, W, resC), bf)[..., :Ntot].float()
         out = v[..., :ncv]
         nout = ncv
     odt = torch.float32 if dst_f32 else bf
+    pair = bool(split and not dst_f32)                           # (hi, lo) output planes
+    lo_of = lambda t: (t - t.to(bf).float()).to(bf)
+    out32 = out
     out = out.to(odt)
     d2 = _p(op, "UCDIR_TC_P_DST2")
     if d2:                                                       # columns >= T_COL0 go transposed to DST2[b][col][pixel]
         t0, tld = g("T_COL0"), g("T_LD")
-        vt = mem.view(d2, (B, Ntot - t0, tld), bf)
-        vt[:, :, :H * W] = out[..., t0:].reshape(B, H * W, Ntot - t0).transpose(1, 2)
-        out = out[..., :t0]
+        vt = mem.view(d2, (B, Ntot - t0, 2 * tld if pair else tld), bf)
+        tr = out32[..., t0:].reshape(B, H * W, Ntot - t0).transpose(1, 2)
+        vt[:, :, :H * W] = tr.to(bf)
+        if pair:
+            vt[:, :, tld:tld + H * W] = lo_of(tr)
+        out, out32 = out[..., :t0], out32[..., :t0]
         nout = t0
+    pitch = 2 * dstC if pair else dstC
     if dstUp:
-        dst = mem.view(_p(op, "UCDIR_TC_P_DST"), (B, 2 * H, 2 * W, dstC), odt)
+        dst = mem.view(_p(op, "UCDIR_TC_P_DST"), (B, 2 * H, 2 * W, pitch), odt)
         dst[:, dpy::2, dpx::2, dstCoff:dstCoff + nout] = out
+        if pair:
+            dst[:, dpy::2, dpx::2, dstC + dstCoff:dstC + dstCoff + nout] = lo_of(out32)
     else:
-        dst = mem.view(_p(op, "UCDIR_TC_P_DST"), (B, H, W, dstC), odt)
+        dst = mem.view(_p(op, "UCDIR_TC_P_DST"), (B, H, W, pitch), odt)
         dst[..., dstCoff:dstCoff + nout] = out
+        if pair:
+            dst[..., dstC + dstCoff:dstC + dstCoff + nout] = lo_of(out32)
+    if pair:
+        out = out32                                              # statistics of the fp32 values
     sp = _p(op, "UCDIR_TC_P_DST_STATS")
     if sp:
         st = mem.view(sp, (B, 2), torch.float64)
@@ -441,7 +485,12 @@ def emu_tc_conv(op, mem):
 def emu_gn_apply(op, mem):
     B, HW, Cc, sw = _i(op, "UCDIR_GNA_I_B"), _i(op, "UCDIR_GNA_I_HW"), _i(op, "UCDIR_GNA_I_C"), _i(op, "UCDIR_GNA_I_SWISH")
     bf = torch.bfloat16
-    x = mem.view(_p(op, "UCDIR_GNA_P_SRC"), (B, HW, Cc), bf).float()
+    split = _i(op, "UCDIR_GNA_I_SPLIT")
+    if split:
+        x2 = mem.view(_p(op, "UCDIR_GNA_P_SRC"), (B, HW, 2 * Cc), bf).float()
+        x = x2[..., :Cc] + x2[..., Cc:]
+    else:
+        x = mem.view(_p(op, "UCDIR_GNA_P_SRC"), (B, HW, Cc), bf).float()
     st = mem.view(_p(op, "UCDIR_GNA_P_STATS"), (B, 2), torch.float64)
     cnt = float(HW * Cc)
     mean = st[:, 0] / cnt
@@ -451,11 +500,24 @@ def emu_gn_apply(op, mem):
     y = (x - mean.float().view(B, 1, 1)) * rstd * gamma + beta
     if sw:
         y = swish(y)
+    if split:
+        d = mem.view(_p(op, "UCDIR_GNA_P_DST"), (B, HW, 2 * Cc), bf)
+        d[..., :Cc] = y.to(bf)
+        d[..., Cc:] = (y - y.to(bf).float()).to(bf)
+        return
     mem.view(_p(op, "UCDIR_GNA_P_DST"), (B, HW, Cc), bf).copy_(y.to(bf))
 
 
 def emu_cast(op, mem):
     n = int(op.i[0]) + (int(op.i[1]) << 31)
+    if int(op.i[2]) == 2:                                         # fp32 rows -> (hi, lo) bf16 plane pairs
+        cols, in_ld, out_ld = int(op.i[3]), int(op.i[4]), int(op.i[5])
+        src = mem.view(int(op.p[0]), (n, in_ld))[:, :cols]
+        dst = mem.view(int(op.p[1]), (n, 2 * out_ld), torch.bfloat16)
+        dst.zero_()
+        dst[:, :cols] = src.to(torch.bfloat16)
+        dst[:, out_ld:out_ld + cols] = (src - src.to(torch.bfloat16).float()).to(torch.bfloat16)
+        return
     if int(op.i[2]) == 0:
         mem.view(int(op.p[1]), (n,), torch.bfloat16).copy_(mem.view(int(op.p[0]), (n,)).to(torch.bfloat16))
     else:

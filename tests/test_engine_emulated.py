@@ -432,3 +432,25 @@ def test_product_schedule_buffers_bit_exact(golden, sid_weights):
     other = copy.deepcopy(net)
     other._sched_host = None
     assert other._step_scalars(1) == net._step_scalars(1)
+
+
+def test_fp32_tc_graph_meets_fp32_tolerance(emulated, golden, sid_weights):
+    """precision "fp32_tc": split-operand (hi + lo bf16 pairs) tensor-core graph -- three K passes per tap, plane-pair
+    activations, exact epilogue math -- executed by the CPU interpreter must meet the reference's fp32 tolerance
+    (rtol 1e-3 / atol 1e-4), and every record must pass the C ABI's argument checks and route to the streamed kernel."""
+    net, _ = sid_weights
+    unet = net.denoise_fn
+    eng = unet.engine()
+    eng.set_precision("fp32_tc")
+    try:
+        g = golden("unet")
+        eps = unet(T(g["x6"]), T(g["level"]), T(g["guide"]))
+        sess = next(iter(eng._sessions.values()))
+        _lib.check_ops(sess.step_ops.array(), len(sess.step_ops))
+        tc = [o for o in sess.step_ops.ops if o.kind == _lib.C["UCDIR_OP_TC_CONV"]]
+        assert tc and all(o.i[_lib.C["UCDIR_TC_I_SPLIT"]] == 1 and _lib.tc_schedule(o) == 0 for o in tc)
+        close(eps, g["eps"])
+        eps2 = unet.naiveforward(T(g["xs"]), T(g["lv2"]), T(g["gs"]))
+        close(eps2, g["eps2"])
+    finally:
+        eng.set_precision("fp32")

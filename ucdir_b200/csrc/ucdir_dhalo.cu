@@ -358,7 +358,7 @@ bool tc_dense_halo_applies(const ucdir_op_t& op) {
   const bool chunks_ok = (KC == 64 && KB == 64 && C0 % 64 == 0 && C1 % 64 == 0) || (KC == 16 && KB == 16 && C0 == 16 && C1 == 0 && NT == 64);
   const bool gn_ok = gn == 1 ? (op.i[UCDIR_TC_I_NCLS] == 9 && op.p[UCDIR_TC_P_TG] && op.p[UCDIR_TC_P_STATS0] && (C1 == 0 || op.p[UCDIR_TC_P_STATS1]))
                              : (gn == 0);
-  return op.i[UCDIR_TC_I_HALO] == 1 && op.i[UCDIR_TC_I_MODE] == 0 && op.i[UCDIR_TC_I_GROUPS] == 1 && (NT == 64 || NT == 128) &&
+  return op.i[UCDIR_TC_I_HALO] == 1 && op.i[UCDIR_TC_I_SPLIT] == 0 && op.i[UCDIR_TC_I_MODE] == 0 && op.i[UCDIR_TC_I_GROUPS] == 1 && (NT == 64 || NT == 128) &&
          op.i[UCDIR_TC_I_NTOT] == NT && chunks_ok && gn_ok && op.i[UCDIR_TC_I_NTY] == 3 && op.i[UCDIR_TC_I_NTX] == 3 &&
          op.i[UCDIR_TC_I_OY0] == -1 && op.i[UCDIR_TC_I_OX0] == -1 && op.i[UCDIR_TC_I_STRIDE] == 1 && H >= 2 && W >= 2 &&
          op.i[UCDIR_TC_I_SRC_H] == H && op.i[UCDIR_TC_I_SRC_W] == W && !op.p[UCDIR_TC_P_RES] && !op.i[UCDIR_TC_I_DST_F32] &&

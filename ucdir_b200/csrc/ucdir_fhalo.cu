@@ -247,7 +247,7 @@ bool tc_final_halo_applies(const ucdir_op_t& op) {
   const int C0 = op.i[UCDIR_TC_I_C0], H = op.i[UCDIR_TC_I_H], W = op.i[UCDIR_TC_I_W];
   const int KB = op.i[UCDIR_TC_I_KB] ? op.i[UCDIR_TC_I_KB] : op.i[UCDIR_TC_I_KC];
   const int ncv = op.i[UCDIR_TC_I_NCOL_VALID] ? op.i[UCDIR_TC_I_NCOL_VALID] : op.i[UCDIR_TC_I_NTOT];
-  return op.i[UCDIR_TC_I_SRC_GN_SWISH] == 1 && op.i[UCDIR_TC_I_MODE] == 0 && op.i[UCDIR_TC_I_GROUPS] == 1 && op.i[UCDIR_TC_I_NT] == FH_NT &&
+  return op.i[UCDIR_TC_I_SRC_GN_SWISH] == 1 && op.i[UCDIR_TC_I_SPLIT] == 0 && op.i[UCDIR_TC_I_MODE] == 0 && op.i[UCDIR_TC_I_GROUPS] == 1 && op.i[UCDIR_TC_I_NT] == FH_NT &&
          op.i[UCDIR_TC_I_NTOT] == FH_NT && op.i[UCDIR_TC_I_KC] == 64 && KB == 64 && C0 % 64 == 0 && C0 / 64 <= FH_MAX_CHUNKS &&
          op.i[UCDIR_TC_I_C1] == 0 && op.i[UCDIR_TC_I_GN] == 0 && op.i[UCDIR_TC_I_ACT] == 0 && op.i[UCDIR_TC_I_NTY] == 3 &&
          op.i[UCDIR_TC_I_NTX] == 3 && op.i[UCDIR_TC_I_OY0] == -1 && op.i[UCDIR_TC_I_OX0] == -1 && op.i[UCDIR_TC_I_STRIDE] == 1 &&

@@ -164,7 +164,7 @@ __device__ __forceinline__ int reflect_idx(int q, int n) {
   return q;
 }
 
-template <bool BF16>
+template <int BF16>
 __global__ void __launch_bounds__(256) gather_tiles_kernel(const float* __restrict__ srcA, const float* __restrict__ srcB,
                                                            const int* __restrict__ tab, void* __restrict__ dstv, int BT,
                                                            int TH, int TW, int IH, int IW, int PD, int CA, int CB, int CD) {
@@ -182,7 +182,14 @@ __global__ void __launch_bounds__(256) gather_tiles_kernel(const float* __restri
   for (int c = 0; c < 16; ++c) v[c] = 0.f;
   for (int c = 0; c < CA; ++c) v[c] = __ldg(srcA + ((size_t)img * CA + c) * plane + sp);
   for (int c = 0; c < CB; ++c) v[CA + c] = __ldg(srcB + ((size_t)img * CB + c) * plane + sp);
-  if (BF16) {
+  if (BF16 == 2) {               // (hi, lo) plane pairs for the fp32-tolerance tensor-core mode: [hi: CD | lo: CD] per pixel
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dstv) + idx * 2 * CD;
+    for (int c = 0; c < CD; ++c) {
+      const __nv_bfloat16 hi = __float2bfloat16(v[c]);
+      d[c] = hi;
+      d[CD + c] = __float2bfloat16(v[c] - __bfloat162float(hi));
+    }
+  } else if (BF16) {
     __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dstv) + idx * CD;
     if (CD == 16) {               // the tensor-core path's 16-channel pixel rows: two 16-byte stores instead of 16 two-byte ones
       __align__(16) __nv_bfloat162 o[8];
@@ -215,11 +222,14 @@ int launch_gather_tiles(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   if (dry) return 0;
   size_t total = (size_t)BT * TH * TW;
   unsigned grid = (unsigned)((total + 255) / 256);
-  if (op.i[UCDIR_GATHER_I_OUT_BF16])
-    gather_tiles_kernel<true><<<grid, 256, 0, st>>>((const float*)op.p[UCDIR_GATHER_P_SRC_A], (const float*)op.p[UCDIR_GATHER_P_SRC_B],
+  if (op.i[UCDIR_GATHER_I_OUT_BF16] == 2)
+    gather_tiles_kernel<2><<<grid, 256, 0, st>>>((const float*)op.p[UCDIR_GATHER_P_SRC_A], (const float*)op.p[UCDIR_GATHER_P_SRC_B],
+        (const int*)op.p[UCDIR_GATHER_P_TAB], op.p[UCDIR_GATHER_P_DST], BT, TH, TW, IH, IW, PD, CA, CB, CD);
+  else if (op.i[UCDIR_GATHER_I_OUT_BF16])
+    gather_tiles_kernel<1><<<grid, 256, 0, st>>>((const float*)op.p[UCDIR_GATHER_P_SRC_A], (const float*)op.p[UCDIR_GATHER_P_SRC_B],
         (const int*)op.p[UCDIR_GATHER_P_TAB], op.p[UCDIR_GATHER_P_DST], BT, TH, TW, IH, IW, PD, CA, CB, CD);
   else
-    gather_tiles_kernel<false><<<grid, 256, 0, st>>>((const float*)op.p[UCDIR_GATHER_P_SRC_A], (const float*)op.p[UCDIR_GATHER_P_SRC_B],
+    gather_tiles_kernel<0><<<grid, 256, 0, st>>>((const float*)op.p[UCDIR_GATHER_P_SRC_A], (const float*)op.p[UCDIR_GATHER_P_SRC_B],
         (const int*)op.p[UCDIR_GATHER_P_TAB], op.p[UCDIR_GATHER_P_DST], BT, TH, TW, IH, IW, PD, CA, CB, CD);
   ++g_launches;
   return 0;

@@ -422,7 +422,7 @@ static int launch_mix_inst(const CUtensorMap& a, const CUtensorMap& b, const Mix
 bool tc_mix_halo_applies(const ucdir_op_t& op) {
   const int C = op.i[UCDIR_TC_I_C0], H = op.i[UCDIR_TC_I_H], W = op.i[UCDIR_TC_I_W];
   const int KB = op.i[UCDIR_TC_I_KB] ? op.i[UCDIR_TC_I_KB] : op.i[UCDIR_TC_I_KC];
-  return op.i[UCDIR_TC_I_HALO] == 1 && op.i[UCDIR_TC_I_MODE] == 1 && op.i[UCDIR_TC_I_GROUPS] == 8 && (C == 64 || C == 128 || C == 256) &&
+  return op.i[UCDIR_TC_I_HALO] == 1 && op.i[UCDIR_TC_I_SPLIT] == 0 && op.i[UCDIR_TC_I_MODE] == 1 && op.i[UCDIR_TC_I_GROUPS] == 8 && (C == 64 || C == 128 || C == 256) &&
          op.i[UCDIR_TC_I_C1] == 0 && op.i[UCDIR_TC_I_NTOT] == 8 * C && op.i[UCDIR_TC_I_GN] == 1 && op.i[UCDIR_TC_I_NCLS] == 9 &&
          op.i[UCDIR_TC_I_NTY] == 3 && op.i[UCDIR_TC_I_NTX] == 3 && op.i[UCDIR_TC_I_OY0] == -1 && op.i[UCDIR_TC_I_OX0] == -1 &&
          op.i[UCDIR_TC_I_STRIDE] == 1 && KB == (C / 8 < 16 ? 16 : C / 8) && H >= 2 && W >= 2 && op.i[UCDIR_TC_I_SRC_H] == H &&

@@ -52,7 +52,49 @@ struct TcParams {
   float alpha;                 // scale on the accumulator when gn == 0 (attention: 1/sqrt(C))
   int w_batched;               // weights are per image: [B][Ntot][K] (attention K / V^T operands)
   __nv_bfloat16* dst2; int t_col0, t_ld;   // columns >= t_col0 are stored transposed: dst2[img][col - t_col0][pixel], row pitch t_ld
+  // fp32-tolerance mode (UCDIR_TC_I_SPLIT): operands are (hi, lo) bf16 plane pairs, three K passes per tap
+  int n0, n1;                  // chunks per plane of src0 / src1 (dense); grouped: n0 = chunks per pass
+  int a0_lo, a1_lo;            // channel offset of the lo plane inside a pixel row of src0 / src1
+  int b_lo;                    // batched weights: K offset of the lo plane inside a weight row
+  int dst_lo, res_lo, t_lo;    // element offset of the lo plane inside a dst / residual / dst2 row
 };
+
+// Which activation slab chunk j of a filter tap reads (map 0 / 1, channel coordinate) and, for batched weights, the K
+// coordinate of its weight slab.  Plain mode: [src0 chunks | src1 chunks].  Split mode: [s0 hi | s0 lo | s1 hi | s1 lo | s0 hi | s1 hi]
+// against weights [W_hi | W_hi | W_hi | W_hi | W_lo | W_lo]; grouped: [hi | lo | hi] of the group's chunk(s).
+template <int KA, int KB, bool SPLIT>
+__device__ __forceinline__ void chunk_source(const TcParams& p, int j, int cgrp0, int kb_seq, bool& use1, int& coff, int& kb) {
+  kb = kb_seq;
+  if (!SPLIT) {
+    use1 = !(p.groups > 1 || j < p.c0_chunks);
+    coff = use1 ? (j - p.c0_chunks) * KA : cgrp0 + j * KA;
+    return;
+  }
+  use1 = false;
+  if (p.groups > 1) {
+    const int pass = j / p.n0, jj = j - pass * p.n0;
+    coff = cgrp0 + jj * KA + (pass == 1 ? p.a0_lo : 0);
+    return;
+  }
+  int q = j;
+  if (q < 2 * p.n0) {
+    const bool lo = q >= p.n0;
+    if (lo) q -= p.n0;
+    coff = q * KA + (lo ? p.a0_lo : 0);
+    if (p.w_batched) kb = q * KB;
+  } else if ((q -= 2 * p.n0) < 2 * p.n1) {
+    use1 = true;
+    const bool lo = q >= p.n1;
+    if (lo) q -= p.n1;
+    coff = q * KA + (lo ? p.a1_lo : 0);
+  } else if ((q -= 2 * p.n1) < p.n0) {
+    coff = q * KA;
+    if (p.w_batched) kb = p.b_lo + q * KB;
+  } else {
+    use1 = true;
+    coff = (q - p.n0) * KA;
+  }
+}
 
 constexpr int TC_EPI_WARPS = 12;          // three per TMEM lane quadrant: the epilogue is latency bound, more warps hide it
 constexpr int TC_FIRST_EPI_WARP = 4;      // warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps}: shrinks to 72 registers
@@ -117,7 +159,7 @@ struct ItemCursor {
 // EPI selects the epilogue at compile time (the chunk loop is the hot code of the small-K layers):
 enum { EPI_PLAIN = 0, EPI_MIX = 1, EPI_F32 = 2, EPI_PLAIN_T = 3, EPI_MIXC = 4 /* mix + additive table cached in smem */ };
 
-template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT, int SPS>
+template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT, int SPS, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                 const __grid_constant__ CUtensorMap mapA1,
                                                                 const __grid_constant__ CUtensorMap mapB, const TcParams p) {
@@ -150,7 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
-    if (p.c0_chunks < p.nchunk && p.groups == 1) prefetch_tmap(&mapA1);
+    if ((SPLIT ? p.n1 > 0 : p.c0_chunks < p.nchunk) && p.groups == 1) prefetch_tmap(&mapA1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int j = 0; j < NSLOT; ++j) { mbar_init(&tmem_full[j], 1); mbar_init(&tmem_empty[j], TC_EPI_WARPS); }
     mbar_init(bfull, 1); mbar_init(bfree, 1);
@@ -199,8 +241,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             if (elect_one()) {
               uint8_t* sa = smem + stage * S::STAGE;
               mbar_expect_tx(&full[stage], row_bytes);
-              if (j < p.c0_chunks) tma_load_4d(&mapA0, &full[stage], sa, j * KA, x0, y0 + ty, n0);
-              else tma_load_4d(&mapA1, &full[stage], sa, (j - p.c0_chunks) * KA, x0, y0 + ty, n0);
+              bool use1; int coff, kbx;
+              chunk_source<KA, KB, SPLIT>(p, j, 0, 0, use1, coff, kbx);
+              tma_load_4d(use1 ? &mapA1 : &mapA0, &full[stage], sa, coff, x0, y0 + ty, n0);
 #pragma unroll
               for (int tx = 0; tx < 3; ++tx)
                 tma_load_2d(&mapB, &full[stage], sa + S::A_ROW + tx * S::B_PAD, ((ty * 3 + tx) * p.nchunk + j) * KB, ncol0);
@@ -219,11 +262,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         if (elect_one()) {
           uint8_t* sa = smem + stage * S::STAGE + sub * S::SLAB;
           if (sub == 0) mbar_expect_tx(&full[stage], tx_bytes * SPS);
-          if (p.groups > 1 || j < p.c0_chunks) tma_load_4d(&mapA0, &full[stage], sa, cgrp0 + j * KA, x0 + tx, y0 + ty, n0);
-          else tma_load_4d(&mapA1, &full[stage], sa, (j - p.c0_chunks) * KA, x0 + tx, y0 + ty, n0);
+          bool use1; int coff, kbx;
+          chunk_source<KA, KB, SPLIT>(p, j, cgrp0, kb, use1, coff, kbx);
+          tma_load_4d(use1 ? &mapA1 : &mapA0, &full[stage], sa, coff, x0 + tx, y0 + ty, n0);
           if (!BSTAT) {
-            if (p.w_batched) tma_load_3d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0, n0);
-            else tma_load_2d(&mapB, &full[stage], sa + S::A_BYTES, kb, ncol0);
+            if (p.w_batched) tma_load_3d(&mapB, &full[stage], sa + S::A_BYTES, kbx, ncol0, n0);
+            else tma_load_2d(&mapB, &full[stage], sa + S::A_BYTES, kbx, ncol0);
           }
         }
         __syncwarp();
@@ -416,11 +460,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         }
       };
       uint2 res_next = make_uint2(0u, 0u);            // mix: residual of the next chunk, loaded one chunk ahead
+      uint2 res_next_lo = make_uint2(0u, 0u);         // SPLIT: its lo plane
       auto issue_res = [&](int c0) {
         constexpr int NO_ = CH / 8;
         const __nv_bfloat16* rp = res_row + ((ncol0 + c0) >> 3);
         if (NO_ == 4) res_next = __ldg(reinterpret_cast<const uint2*>(rp));
         else res_next.x = __ldg(reinterpret_cast<const uint32_t*>(rp));
+        if (SPLIT) {
+          if (NO_ == 4) res_next_lo = __ldg(reinterpret_cast<const uint2*>(rp + p.res_lo));
+          else res_next_lo.x = __ldg(reinterpret_cast<const uint32_t*>(rp + p.res_lo));
+        }
       };
       if (valid && half * CH < NT) { issue_tables(half * CH); if (MIX) issue_res(half * CH); finish_tables(half * CH); }
       mbar_wait(&tmem_full[slot], sph);
@@ -429,15 +478,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       for (int c0 = half * CH; c0 < NT; c0 += CSTEP) {
         // issue the residual load this chunk needs before waiting on the TMEM load
         constexpr int NO = CH / 8;
-        uint2 res_mix = make_uint2(0u, 0u);
+        uint2 res_mix = make_uint2(0u, 0u), res_mix_lo = make_uint2(0u, 0u);
         uint4 res_pl[CH / 8];
+        uint4 res_pl_lo[SPLIT ? CH / 8 : 1];
         if (valid) {
           if (MIX) {
-            res_mix = res_next;
+            res_mix = res_next; res_mix_lo = res_next_lo;
           } else if (EPI != EPI_F32 && p.res) {
             const uint4* rp = reinterpret_cast<const uint4*>(res_row + ncol0 + c0);
 #pragma unroll
             for (int j = 0; j < CH / 8; ++j) res_pl[j] = __ldg(rp + j);
+            if (SPLIT) {
+              const uint4* rl = reinterpret_cast<const uint4*>(res_row + p.res_lo + ncol0 + c0);
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) res_pl_lo[j] = __ldg(rl + j);
+            }
           }
         }
         uint32_t rv[32];
@@ -469,34 +524,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
           const int cbase = (ncol0 + c0) >> 3;
           __align__(8) __nv_bfloat16 o[NO];
+          __align__(8) __nv_bfloat16 ol[NO];
           const __nv_bfloat16* rres = reinterpret_cast<const __nv_bfloat16*>(&res_mix);
+          const __nv_bfloat16* rres_lo = reinterpret_cast<const __nv_bfloat16*>(&res_mix_lo);
 #pragma unroll
           for (int c = 0; c < NO; ++c) {
             float2 h2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int s = 0; s < 8; s += 2) h2 = __ffma2_rn(make_float2(v[c * 8 + s], v[c * 8 + s + 1]), make_float2(aw[s], aw[s + 1]), h2);
             const float h = h2.x + h2.y;
-            const float t = swish_fast(h) + __bfloat162float(rres[c]);
-            o[c] = __float2bfloat16(t);
-            const float tr = __bfloat162float(o[c]);
-            t1s += tr; t2s += tr * tr;
+            if (SPLIT) {
+              const float t = swish_f(h) + (__bfloat162float(rres[c]) + __bfloat162float(rres_lo[c]));
+              o[c] = __float2bfloat16(t);
+              ol[c] = __float2bfloat16(t - __bfloat162float(o[c]));
+              t1s += t; t2s += t * t;
+            } else {
+              const float t = swish_fast(h) + __bfloat162float(rres[c]);
+              o[c] = __float2bfloat16(t);
+              const float tr = __bfloat162float(o[c]);
+              t1s += tr; t2s += tr * tr;
+            }
           }
           __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst_row) + cbase;
           if (NO == 4) *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(o);
           else *reinterpret_cast<uint32_t*>(d) = *reinterpret_cast<const uint32_t*>(o);
+          if (SPLIT) {
+            if (NO == 4) *reinterpret_cast<uint2*>(d + p.dst_lo) = *reinterpret_cast<const uint2*>(ol);
+            else *reinterpret_cast<uint32_t*>(d + p.dst_lo) = *reinterpret_cast<const uint32_t*>(ol);
+          }
         } else {
           const int nb = ncol0 + c0;
           if (p.act == 1) {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = swish_fast(v[j]);
+            for (int j = 0; j < CH; ++j) v[j] = SPLIT ? swish_f(v[j]) : swish_fast(v[j]);
           }
           if (EPI != EPI_F32 && p.res) {
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&res_pl[j / 8]);
+              const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&res_pl_lo[SPLIT ? j / 8 : 0]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h2[e]);
+                float2 f = __bfloat1622float2(h2[e]);
+                if (SPLIT) { const float2 g = __bfloat1622float2(l2[e]); f.x += g.x; f.y += g.y; }
                 v[j + 2 * e] += f.x; v[j + 2 * e + 1] += f.y;
               }
             }
@@ -520,19 +590,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             // transposed store (attention V^T): lanes hold consecutive pixels, so each store is one coalesced run
             __nv_bfloat16* d = p.dst2 + ((size_t)img * (p.Ntot - p.t_col0) + (nb - p.t_col0)) * p.t_ld + (y * p.W + x);
 #pragma unroll
-            for (int j = 0; j < CH; ++j) d[(size_t)j * p.t_ld] = __float2bfloat16(v[j]);
+            for (int j = 0; j < CH; ++j) {
+              const __nv_bfloat16 hi = __float2bfloat16(v[j]);
+              d[(size_t)j * p.t_ld] = hi;
+              if (SPLIT) d[(size_t)j * p.t_ld + p.t_lo] = __float2bfloat16(v[j] - __bfloat162float(hi));
+            }
           } else {
             __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst_row) + nb;
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
               __align__(16) __nv_bfloat162 o2[4];
+              __align__(16) __nv_bfloat162 l2[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 o2[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
                 const float2 f = __bfloat1622float2(o2[e]);
-                t1s += f.x + f.y; t2s += f.x * f.x + f.y * f.y;
+                if (SPLIT) {
+                  const float a = v[j + 2 * e], b = v[j + 2 * e + 1];
+                  l2[e] = __floats2bfloat162_rn(a - f.x, b - f.y);
+                  t1s += a + b; t2s += a * a + b * b;
+                } else {
+                  t1s += f.x + f.y; t2s += f.x * f.x + f.y * f.y;
+                }
               }
               *reinterpret_cast<uint4*>(d + j) = *reinterpret_cast<const uint4*>(o2);
+              if (SPLIT) *reinterpret_cast<uint4*>(d + p.dst_lo + j) = *reinterpret_cast<const uint4*>(l2);
             }
           }
         }
@@ -640,14 +722,14 @@ int check_reg_pool(const void* kernel, const char* name, int low_threads, int lo
 
 static const bool g_pdl = []() { const char* e = getenv("UCDIR_PDL"); return !(e && e[0] == '0'); }();
 
-template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT, int SPS>
+template <int KA, int KB, int NT, int NSPLIT, int EPI, int BSTAT, int SPS, bool SPLIT = false>
 static int launch_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t st) {
   using S = TcCfg<KA, KB, NT, NSPLIT, BSTAT, SPS>;
   const int smem_bytes = S::TOTAL + (BSTAT ? p.bres_bytes : 0) + (p.ctab ? 9 * p.Ntot * 4 + 16 : 0);
   static int attr_dev[UCDIR_MAX_DEV] = {};
   int& attr = attr_dev[cur_dev()];
   if (attr < smem_bytes) {
-    if (cudaFuncSetAttribute(tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT, SPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT, SPS, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
       set_error("tc_conv: cannot opt in to %d bytes of shared memory: %s", smem_bytes, cudaGetErrorString(cudaGetLastError())); return -3; }
     attr = smem_bytes;
   }
@@ -657,7 +739,7 @@ static int launch_inst(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT, SPS>, a0, a1, b, p) != cudaSuccess) {
+  if (cudaLaunchKernelEx(&cfg, tc_conv_kernel<KA, KB, NT, NSPLIT, EPI, BSTAT, SPS, SPLIT>, a0, a1, b, p) != cudaSuccess) {
     set_error("tc_conv: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
   return 0;
 }
@@ -686,7 +768,8 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   p.alpha = op.f[UCDIR_TC_F_ALPHA] != 0.f ? op.f[UCDIR_TC_F_ALPHA] : 1.f;
   p.w_batched = op.i[UCDIR_TC_I_W_BATCHED];
   p.dst2 = (__nv_bfloat16*)op.p[UCDIR_TC_P_DST2]; p.t_col0 = op.i[UCDIR_TC_I_T_COL0]; p.t_ld = op.i[UCDIR_TC_I_T_LD];
-  const int cstride0 = op.i[UCDIR_TC_I_SRC_CSTRIDE] ? op.i[UCDIR_TC_I_SRC_CSTRIDE] : op.i[UCDIR_TC_I_C0];
+  const int split = op.i[UCDIR_TC_I_SPLIT] ? 1 : 0;
+  const int cstride0 = op.i[UCDIR_TC_I_SRC_CSTRIDE] ? op.i[UCDIR_TC_I_SRC_CSTRIDE] : (split ? 2 : 1) * op.i[UCDIR_TC_I_C0];
   const int w_rowstride = op.i[UCDIR_TC_I_W_ROWSTRIDE];
   const long long w_batchstride = (long long)op.i[UCDIR_TC_I_W_BATCHSTRIDE_LO] + ((long long)op.i[UCDIR_TC_I_W_BATCHSTRIDE_HI] << 31);
   if (!src0 || !w || !p.dst || !p.tb) { set_error("tc_conv: null src0/w/dst/tb"); return -1; }
@@ -706,11 +789,28 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
     if (KB != (p.Cg > 16 ? p.Cg : 16) && !(NSPLIT == 1 && KB == KC)) { set_error("tc_conv: grouped conv needs KB = max(Cg, 16)"); return -2; }
     p.nchunk = p.cg_eff / KC; p.c0_chunks = p.nchunk;
     if (NSPLIT > 1 && p.nchunk != 1) { set_error("tc_conv: split items need one chunk per tap"); return -2; }
+    p.n0 = p.nchunk; p.n1 = 0;
   } else {
     if ((C0 % KC && !(C1 == 0 && p.w_batched)) || C1 % KC) { set_error("tc_conv: C0=%d / C1=%d must be multiples of KC=%d", C0, C1, KC); return -2; }
     if (C1 > 0 && !src1) { set_error("tc_conv: null src1"); return -1; }
     if (NSPLIT != 1 || KB != KC) { set_error("tc_conv: dense conv needs NSPLIT = 1 and KB = KC"); return -2; }
     p.Cg = Cin; p.Ng = p.Ntot; p.cg_eff = Cin; p.nchunk = (Cin + KC - 1) / KC; p.c0_chunks = (C0 + KC - 1) / KC;   // a K tail is zero filled by TMA
+    p.n0 = p.c0_chunks; p.n1 = C1 / KC;
+  }
+  // fp32-tolerance mode: (hi, lo) plane pairs, three K passes per tap
+  p.a0_lo = p.a1_lo = p.b_lo = p.dst_lo = p.res_lo = p.t_lo = 0;
+  if (split) {
+    if (op.i[UCDIR_TC_I_SRC_GN_SWISH] || op.i[UCDIR_TC_I_RES_FUSED] || op.i[UCDIR_TC_I_BSTAT] || op.i[UCDIR_TC_I_SPS3]) {
+      set_error("tc_conv: SPLIT runs on the streamed kernel only (no SRC_GN_SWISH / RES_FUSED / BSTAT / SPS3)"); return -2; }
+    p.a0_lo = op.i[UCDIR_TC_I_SRC_LO_OFF] ? op.i[UCDIR_TC_I_SRC_LO_OFF] : (p.groups > 1 ? Cin : C0);
+    p.a1_lo = C1;
+    p.b_lo = op.i[UCDIR_TC_I_W_LO_OFF];
+    if (p.w_batched && p.b_lo <= 0) { set_error("tc_conv: SPLIT with batched weights needs W_LO_OFF"); return -1; }
+    if (p.a0_lo % 8 || (p.w_batched && p.b_lo % 8)) { set_error("tc_conv: SPLIT plane offsets must be multiples of 8 elements"); return -2; }
+    p.nchunk *= 3;
+    if (!p.dst_f32) { p.dst_lo = p.dstC; p.dstC *= 2; }
+    if (p.res) { p.res_lo = p.resC; p.resC *= 2; }
+    if (p.dst2) { p.t_lo = p.t_ld; p.t_ld *= 2; }
   }
   if (p.Ntot % NT) { set_error("tc_conv: Ntot=%d not a multiple of NT=%d", p.Ntot, NT); return -2; }
   if (p.gn) {
@@ -750,18 +850,21 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
                     NSPLIT == 1 && p.bw == 128 && p.bh == 1 && p.bn == 1 && !p.w_batched && !p.dst2 && !p.dst_f32 && p.mode != 1 && NT <= 128;
   const int abw = row3 ? p.bw + 2 : p.bw;
   CUtensorMap a0, a1, bm;
-  int rc = make_act_map(&a0, src0, C0, p.srcW, p.srcH, p.B, KC, abw, p.bh, p.bn, p.stride, cstride0);
+  // split: the channel extent of a map covers both planes (the lo plane starts a*_lo channels into the pixel row)
+  const int ext0 = split ? p.a0_lo + (p.groups > 1 ? Cin : p.n0 * KC) : C0;
+  if (split && ext0 > cstride0) { set_error("tc_conv: SPLIT planes (%d + %d channels) exceed the source row pitch %d", p.a0_lo, ext0 - p.a0_lo, cstride0); return -2; }
+  int rc = make_act_map(&a0, src0, ext0, p.srcW, p.srcH, p.B, KC, abw, p.bh, p.bn, p.stride, cstride0);
   if (rc) return rc;
-  if (C1 > 0) { rc = make_act_map(&a1, src1, C1, p.srcW, p.srcH, p.B, KC, abw, p.bh, p.bn, p.stride, C1); if (rc) return rc; }
+  if (C1 > 0) { rc = make_act_map(&a1, src1, split ? 2 * C1 : C1, p.srcW, p.srcH, p.B, KC, abw, p.bh, p.bn, p.stride, split ? 2 * C1 : C1); if (rc) return rc; }
   else a1 = a0;
   const int Ktot = p.nty * p.ntx * p.nchunk * KB;
-  if (p.w_batched) rc = make_w_map(&bm, w, C0, op.i[UCDIR_TC_I_W_ROWS] ? op.i[UCDIR_TC_I_W_ROWS] : p.Ntot, KB, NT, w_rowstride, p.B, w_batchstride);
+  if (p.w_batched) rc = make_w_map(&bm, w, split ? p.b_lo + p.n0 * KB : C0, op.i[UCDIR_TC_I_W_ROWS] ? op.i[UCDIR_TC_I_W_ROWS] : p.Ntot, KB, NT, w_rowstride, p.B, w_batchstride);
   else rc = make_w_map(&bm, w, Ktot, p.Ntot, KB, NT, Ktot, 0, 0);
   if (rc) return rc;
   const int n_sm = sm_count();
   const long long items = (long long)mt * (p.Ntot / NT);
   dim3 grid((unsigned)(items < n_sm ? items : n_sm), 1, 1);      // persistent: one CTA per SM
-  p.ctab = (p.mode == 1 && p.gn && p.ncls == 9 && p.bn == 1 && p.Ntot <= 1024 && KC == 32 && KB == 16 && op.i[UCDIR_TC_I_NO_CTAB] == 0 &&
+  p.ctab = (!split && p.mode == 1 && p.gn && p.ncls == 9 && p.bn == 1 && p.Ntot <= 1024 && KC == 32 && KB == 16 && op.i[UCDIR_TC_I_NO_CTAB] == 0 &&
             op.i[UCDIR_TC_I_BSTAT] == 0 && op.i[UCDIR_TC_I_SPS3] == 0) ? 1 : 0;
   const int epi = p.mode == 1 ? (p.ctab ? EPI_MIXC : EPI_MIX) : (p.dst_f32 ? EPI_F32 : (p.dst2 ? EPI_PLAIN_T : EPI_PLAIN));
   // weight-stationary schedule: the whole weight block of one N sub-tile stays in shared memory while the CTA walks
@@ -777,6 +880,14 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   //  so it is opt-in)
   int sps = (nslab % 3 == 0 && op.i[UCDIR_TC_I_SPS3] == 1 && (NT / NSPLIT <= 128 || ((epi == EPI_MIX || epi == EPI_MIXC) && KB < 64))) ? 3 : 1;
   if (row3) sps = 4;
+#define INSTS(ka, kb, nt, ns, ep, sp) if (split && KC == ka && KB == kb && NT == nt && NSPLIT == ns && epi == ep && sps == sp) { rc = launch_inst<ka, kb, nt, ns, ep, 0, sp, true>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
+  INSTS(64, 64, 64, 1, EPI_PLAIN, 1) INSTS(64, 64, 128, 1, EPI_PLAIN, 1) INSTS(64, 64, 256, 1, EPI_PLAIN, 1) INSTS(16, 16, 64, 1, EPI_PLAIN, 1)
+  INSTS(64, 64, 64, 1, EPI_PLAIN, 4) INSTS(64, 64, 128, 1, EPI_PLAIN, 4)
+  INSTS(64, 64, 256, 1, EPI_PLAIN_T, 1)
+  INSTS(64, 64, 16, 1, EPI_F32, 1) INSTS(64, 64, 64, 1, EPI_F32, 1) INSTS(64, 64, 128, 1, EPI_F32, 1) INSTS(64, 64, 256, 1, EPI_F32, 1)
+  INSTS(32, 16, 256, 4, EPI_MIX, 1) INSTS(32, 16, 256, 2, EPI_MIX, 1) INSTS(32, 32, 256, 1, EPI_MIX, 1) INSTS(64, 64, 256, 1, EPI_MIX, 1)
+#undef INSTS
+  if (split) { set_error("tc_conv: no SPLIT kernel instance for KC=%d KB=%d NT=%d NSPLIT=%d epilogue %d sps %d", KC, KB, NT, NSPLIT, epi, sps); return -2; }
 #define INST(ka, kb, nt, ns, ep, bs, sp) if (KC == ka && KB == kb && NT == nt && NSPLIT == ns && epi == ep && bstat == bs && sps == sp) { rc = launch_inst<ka, kb, nt, ns, ep, bs, sp>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
   INST(64, 64, 64, 1, EPI_PLAIN, 0, 1) INST(64, 64, 128, 1, EPI_PLAIN, 0, 1) INST(64, 64, 256, 1, EPI_PLAIN, 0, 1) INST(16, 16, 64, 1, EPI_PLAIN, 0, 1)
   INST(64, 64, 64, 1, EPI_PLAIN, 0, 3) INST(64, 64, 128, 1, EPI_PLAIN, 0, 3) INST(16, 16, 64, 1, EPI_PLAIN, 0, 3)
@@ -838,6 +949,40 @@ __global__ void __launch_bounds__(256) gn_apply_bf16_kernel(const __nv_bfloat16*
   }
 }
 
+// fp32-tolerance mode: source and destination are (hi, lo) plane pairs [B][HW][2*C]; fp32 math, exact Swish.
+__global__ void __launch_bounds__(256) gn_apply_split_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const double* __restrict__ stats, int C, size_t n_pix, double count, float eps, int swish) {
+  const int b = blockIdx.y;
+  const GnScalars sc = gn_scalars(stats, nullptr, b, count, eps);
+  const int c8 = C / 8;
+  const size_t total = n_pix * c8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i / c8; const int c = (int)(i - pix * c8) * 8;
+    const size_t row = ((size_t)b * n_pix + pix) * 2 * C;
+    const uint4 uh = __ldg(reinterpret_cast<const uint4*>(src + row + c));
+    const uint4 ul = __ldg(reinterpret_cast<const uint4*>(src + row + C + c));
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&uh);
+    const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ul);
+    __align__(16) __nv_bfloat162 oh[4];
+    __align__(16) __nv_bfloat162 ol[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fh = __bfloat1622float2(h2[k]), fl = __bfloat1622float2(l2[k]);
+      float x0 = fh.x + fl.x, x1 = fh.y + fl.y;
+      const float a0 = sc.rstd * __ldg(gamma + c + 2 * k), a1 = sc.rstd * __ldg(gamma + c + 2 * k + 1);
+      x0 = (x0 - sc.mean) * a0 + __ldg(beta + c + 2 * k);
+      x1 = (x1 - sc.mean) * a1 + __ldg(beta + c + 2 * k + 1);
+      if (swish) { x0 = swish_f(x0); x1 = swish_f(x1); }
+      oh[k] = __floats2bfloat162_rn(x0, x1);
+      const float2 r = __bfloat1622float2(oh[k]);
+      ol[k] = __floats2bfloat162_rn(x0 - r.x, x1 - r.y);
+    }
+    *reinterpret_cast<uint4*>(dst + row + c) = *reinterpret_cast<const uint4*>(oh);
+    *reinterpret_cast<uint4*>(dst + row + C + c) = *reinterpret_cast<const uint4*>(ol);
+  }
+}
+
 int launch_gn_apply_bf16(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   const int B = op.i[UCDIR_GNA_I_B], HW = op.i[UCDIR_GNA_I_HW], C = op.i[UCDIR_GNA_I_C];
   for (int k = 0; k <= UCDIR_GNA_P_STATS; ++k) if (!op.p[k]) { set_error("gn_apply: null pointer %d", k); return -1; }
@@ -845,6 +990,13 @@ int launch_gn_apply_bf16(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   if (dry) return 0;
   const size_t per = (size_t)HW * C;
   unsigned gx = (unsigned)((per / 8 + 255) / 256); if (gx > 2368) gx = 2368;       // 16 CTAs per SM x 148
+  if (op.i[UCDIR_GNA_I_SPLIT]) {
+    gn_apply_split_kernel<<<dim3(gx, B), 256, 0, st>>>((const __nv_bfloat16*)op.p[UCDIR_GNA_P_SRC], (__nv_bfloat16*)op.p[UCDIR_GNA_P_DST],
+        (const float*)op.p[UCDIR_GNA_P_GAMMA], (const float*)op.p[UCDIR_GNA_P_BETA], (const double*)op.p[UCDIR_GNA_P_STATS], C, (size_t)HW,
+        (double)per, op.f[0], op.i[UCDIR_GNA_I_SWISH]);
+    ++g_launches;
+    return 0;
+  }
   gn_apply_bf16_kernel<<<dim3(gx, B), 256, 0, st>>>((const __nv_bfloat16*)op.p[UCDIR_GNA_P_SRC], (__nv_bfloat16*)op.p[UCDIR_GNA_P_DST],
       (const float*)op.p[UCDIR_GNA_P_GAMMA], (const float*)op.p[UCDIR_GNA_P_BETA], (const double*)op.p[UCDIR_GNA_P_STATS], C, per,
       (double)per, op.f[0], op.i[UCDIR_GNA_I_SWISH]);
@@ -858,9 +1010,34 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16*
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = __bfloat162float(s[i]);
 }
+// fp32 rows -> (hi, lo) bf16 plane pairs (fp32_tc attention probabilities): one thread per output column pair
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, size_t rows, int cols, int in_ld, int out_ld) {
+  const int half = out_ld / 2;                       // out_ld is even (checked by the launcher)
+  const size_t total = rows * half;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / half; const int c = (int)(i - r * half) * 2;
+    const float a = c < cols ? s[r * in_ld + c] : 0.f, b = c + 1 < cols ? s[r * in_ld + c + 1] : 0.f;
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+    const float2 f = __bfloat1622float2(hi);
+    __nv_bfloat16* o = d + r * 2 * out_ld + c;
+    *reinterpret_cast<__nv_bfloat162*>(o) = hi;
+    *reinterpret_cast<__nv_bfloat162*>(o + out_ld) = __floats2bfloat162_rn(a - f.x, b - f.y);
+  }
+}
+
 int launch_cast(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   const size_t n = (size_t)op.i[0] + ((size_t)op.i[1] << 31);
   if (!op.p[0] || !op.p[1] || n == 0) { set_error("cast: bad args"); return -1; }
+  if (op.i[2] == 2) {
+    const int cols = op.i[3], in_ld = op.i[4], out_ld = op.i[5];
+    if (cols <= 0 || in_ld < cols || out_ld < cols || (out_ld & 1)) { set_error("cast: bad split-rows dims"); return -1; }
+    if (dry) return 0;
+    const size_t total = n * (size_t)(out_ld / 2);
+    unsigned g2 = (unsigned)((total + 255) / 256 > 4736 ? 4736 : (total + 255) / 256);
+    split_rows_kernel<<<g2, 256, 0, st>>>((const float*)op.p[0], (__nv_bfloat16*)op.p[1], n, cols, in_ld, out_ld);
+    ++g_launches;
+    return 0;
+  }
   if (dry) return 0;
   unsigned g = (unsigned)((n + 255) / 256); if (g > 4736) g = 4736;
   if (op.i[2] == 0) cast_f32_bf16_kernel<<<g, 256, 0, st>>>((const float*)op.p[0], (__nv_bfloat16*)op.p[1], n);

@@ -208,6 +208,7 @@ class Act:
     W: int
     stats: int                   # device pointer to double[BT][2] or 0
     keep: bool = False
+    split: bool = False          # fp32_tc: (hi, lo) bf16 plane pairs, pixel row = [hi: C | lo: C]
 
     @property
     def ptr(self): return self.buf.data_ptr()
@@ -336,21 +337,42 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
-def pack_tc_dense(w: torch.Tensor, bias, nt: int, gamma=None, beta=None):
+def split_hi_lo(t: torch.Tensor):
+    """fp32 -> (hi, lo) bf16 with hi + lo == t to 16 mantissa bits (UCDIR_TC_I_SPLIT)."""
+    t = t.float()
+    hi = t.to(BF16)
+    return hi, (t - hi.float()).to(BF16)
+
+
+def _split_k(wt: torch.Tensor, c0: Optional[int] = None) -> torch.Tensor:
+    """[..., taps, ci] fp32 -> [..., taps, 3*ci] bf16 in the K order of a SPLIT op: per tap
+    [W_hi(src0) | W_hi(src0) | W_hi(src1) | W_hi(src1) | W_lo(src0) | W_lo(src1)] (src0 = channels [0, c0))."""
+    ci = wt.shape[-1]
+    c0 = ci if c0 is None else c0
+    hi, lo = split_hi_lo(wt)
+    return torch.cat([hi[..., :c0], hi[..., :c0], hi[..., c0:], hi[..., c0:], lo[..., :c0], lo[..., c0:]], dim=-1)
+
+
+def pack_tc_dense(w: torch.Tensor, bias, nt: int, gamma=None, beta=None, split: bool = False, c0: Optional[int] = None):
     """OIHW fp32 conv weight -> (W bf16 [Ntot][K = (tap, c)], TB fp32 [ncls][Ntot], TG or None).
-    With gamma/beta the GroupNorm(1,C) in front of the conv is folded (see ucdir_tc.cu header)."""
+    With gamma/beta the GroupNorm(1,C) in front of the conv is folded (see ucdir_tc.cu header).
+    split: fp32_tc operand pairs (three K passes per tap, see _split_k); tables from the fp32 weights."""
     co, ci, kh, kw = w.shape
     w = w.float()
     wg = w * gamma.float().view(1, ci, 1, 1) if gamma is not None else w
     ntot = _round_up(co, nt)
     wq = wg.to(BF16)
-    packed = torch.zeros(ntot, kh * kw * ci, dtype=BF16, device=w.device)
-    packed[:co] = wq.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
+    kmul = 3 if split else 1
+    packed = torch.zeros(ntot, kh * kw * ci * kmul, dtype=BF16, device=w.device)
+    if split:
+        packed[:co] = _split_k(wg.permute(0, 2, 3, 1).reshape(co, kh * kw, ci), c0).reshape(co, kh * kw * ci * 3)
+    else:
+        packed[:co] = wq.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
     b = bias.float() if bias is not None else torch.zeros(co, device=w.device)
     if gamma is None:
         tb = torch.zeros(1, ntot, device=w.device); tb[0, :co] = b
         return packed.contiguous(), tb.contiguous(), None
-    wq32 = wq.float()
+    wq32 = wg if split else wq.float()
     if kh == 3:
         ncls = 9
         tg = torch.zeros(ncls, ntot, device=w.device); tb = torch.zeros(ncls, ntot, device=w.device)
@@ -366,16 +388,17 @@ def pack_tc_dense(w: torch.Tensor, bias, nt: int, gamma=None, beta=None):
     return packed.contiguous(), tb.contiguous(), tg.contiguous()
 
 
-def pack_tc_grouped(w: torch.Tensor, bias, groups: int, kc: int, gamma, beta):
+def pack_tc_grouped(w: torch.Tensor, bias, groups: int, kc: int, gamma, beta, split: bool = False):
     """Grouped 3x3 conv [G*Ng, Cg, 3, 3] (spdyconv, model/ucdir.py:116) with folded GroupNorm.  When Cg < KC
-    the K chunk spans KC/Cg neighbouring groups and the rows carry zeros for the foreign channels."""
+    the K chunk spans KC/Cg neighbouring groups and the rows carry zeros for the foreign channels.
+    split: per tap [W_hi | W_hi | W_lo] over the group's chunk (UCDIR_TC_I_SPLIT)."""
     co, cg, kh, kw = w.shape
     cin = cg * groups
     ng = co // groups
     cg_eff = max(cg, kc)
     w = w.float()
     dev = w.device
-    packed = torch.zeros(co, kh * kw, cg_eff, dtype=BF16, device=dev)
+    packed32 = torch.zeros(co, kh * kw, cg_eff, device=dev)
     tg = torch.zeros(9, co, device=dev); tb = torch.zeros(9, co, device=dev)
     mask = _cls_mask(dev)
     for g in range(groups):
@@ -383,17 +406,20 @@ def pack_tc_grouped(w: torch.Tensor, bias, groups: int, kc: int, gamma, beta):
         off = g * cg - cbase
         rows = slice(g * ng, (g + 1) * ng)
         wg = w[rows] * gamma.float()[g * cg:(g + 1) * cg].view(1, cg, 1, 1)
-        wq = wg.to(BF16)
-        packed[rows, :, off:off + cg] = wq.permute(0, 2, 3, 1).reshape(ng, kh * kw, cg)
-        wgs = wq.float().sum(1)
+        packed32[rows, :, off:off + cg] = wg.permute(0, 2, 3, 1).reshape(ng, kh * kw, cg)
+        wgs = (wg if split else wg.to(BF16).float()).sum(1)
         wb = (w[rows] * beta.float()[g * cg:(g + 1) * cg].view(1, cg, 1, 1)).sum(1)
         tg[:, rows] = torch.einsum("cyx,nyx->cn", mask, wgs)
         tb[:, rows] = torch.einsum("cyx,nyx->cn", mask, wb)
     tb += bias.float().view(1, co)
-    return packed.reshape(co, kh * kw * cg_eff).contiguous(), tb.contiguous(), tg.contiguous()
+    if split:
+        packed = _split_k(packed32).reshape(co, kh * kw * cg_eff * 3)
+    else:
+        packed = packed32.to(BF16).reshape(co, kh * kw * cg_eff)
+    return packed.contiguous(), tb.contiguous(), tg.contiguous()
 
 
-def pack_tc_up_phase(w: torch.Tensor, bias, py: int, px: int, nt: int):
+def pack_tc_up_phase(w: torch.Tensor, bias, py: int, px: int, nt: int, split: bool = False):
     """Nearest-2x upsample followed by a 3x3 conv (model/ucdir.py:53-60) == four 2x2-tap convolutions on the
     source grid, one per output parity (py, px); row set of tap t: py=0 -> {0}, {1,2}; py=1 -> {0,1}, {2}."""
     co, ci, _, _ = w.shape
@@ -408,8 +434,8 @@ def pack_tc_up_phase(w: torch.Tensor, bias, py: int, px: int, nt: int):
                     acc = acc + w[:, :, dy, dx]
             wp[:, ty, tx, :] = acc
     ntot = _round_up(co, nt)
-    packed = torch.zeros(ntot, 4 * ci, dtype=BF16, device=w.device)
-    packed[:co] = wp.reshape(co, 4 * ci).to(BF16)
+    packed = torch.zeros(ntot, 4 * ci * (3 if split else 1), dtype=BF16, device=w.device)
+    packed[:co] = _split_k(wp.reshape(co, 4, ci)).reshape(co, 12 * ci) if split else wp.reshape(co, 4 * ci).to(BF16)
     tb = torch.zeros(1, ntot, device=w.device); tb[0, :co] = bias.float()
     return packed.contiguous(), tb.contiguous()
 
@@ -428,7 +454,8 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
            dst_py: int = 0, dst_px: int = 0, eps: float = 1e-5, kb: int = 0, nsplit: int = 1, src_cstride: int = 0,
            w_batched: int = 0, w_rowstride: int = 0, w_batchstride: int = 0, alpha: float = 0.0, dst2: int = 0, t_col0: int = 0,
            t_ld: int = 0, w_rows: int = 0, row3: Optional[int] = None, halo: Optional[int] = None, src_gn_swish: int = 0,
-           src_gamma: int = 0, src_beta: int = 0, w2: int = 0, tb2: int = 0, dst_res: Optional[Act] = None):
+           src_gamma: int = 0, src_beta: int = 0, w2: int = 0, tb2: int = 0, dst_res: Optional[Act] = None,
+           split: int = 0, src_lo_off: int = 0, w_lo_off: int = 0):
     H, W = (dst.H // 2, dst.W // 2) if dst_up else (dst.H, dst.W)
     p = {"UCDIR_TC_P_SRC0": src0.ptr, "UCDIR_TC_P_W": w, "UCDIR_TC_P_TB": tb, "UCDIR_TC_P_DST": dst.ptr}
     if src1 is not None: p["UCDIR_TC_P_SRC1"] = src1.ptr
@@ -452,6 +479,9 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
          "UCDIR_TC_I_W_BATCHSTRIDE_LO": w_batchstride & 0x7FFFFFFF, "UCDIR_TC_I_W_BATCHSTRIDE_HI": w_batchstride >> 31,
          "UCDIR_TC_I_T_COL0": t_col0, "UCDIR_TC_I_T_LD": t_ld, "UCDIR_TC_I_W_ROWS": w_rows,
          "UCDIR_TC_I_ROW3": _TC_ROW3 if row3 is None else row3, "UCDIR_TC_I_HALO": _TC_HALO if halo is None else halo}
+    if split:
+        i["UCDIR_TC_I_SPLIT"], i["UCDIR_TC_I_HALO"] = 1, 0
+        i["UCDIR_TC_I_SRC_LO_OFF"], i["UCDIR_TC_I_W_LO_OFF"] = src_lo_off, w_lo_off
     if dst2: p["UCDIR_TC_P_DST2"] = dst2
     if src_gn_swish:
         p["UCDIR_TC_P_SRC_GAMMA"], p["UCDIR_TC_P_SRC_BETA"], p["UCDIR_TC_P_STATS0"] = src_gamma, src_beta, src0.stats
@@ -487,8 +517,9 @@ def tc_mix_tiling(cout: int):
 class _Builder:
     """Shared helpers of the UNet / predictor graph builders."""
 
-    def __init__(self, pool: Pool, BT: int, stats: torch.Tensor, elem: int = 4):
-        self.pool, self.BT, self.elem = pool, BT, elem
+    def __init__(self, pool: Pool, BT: int, stats: torch.Tensor, elem: int = 4, split: bool = False):
+        self.pool, self.BT, self.elem = pool, BT, elem * (2 if split else 1)
+        self.split = split
         self.stats = stats               # double[n_slots][BT][2]
         self.next_slot = 0
         self.ops = OpList()
@@ -501,7 +532,7 @@ class _Builder:
                 raise RuntimeError("statistics arena exhausted")
             st = self.stats.data_ptr() + self.next_slot * self.BT * 16
             self.next_slot += 1
-        return Act(buf, cpad or C, H, W, st, keep)
+        return Act(buf, cpad or C, H, W, st, keep, self.split)
 
     def release(self, a: Optional[Act]):
         if a is not None and not a.keep:
@@ -628,8 +659,19 @@ class UNetEngine:
         ws.put("final.w", pack_conv_f32(fc[3].weight)); ws.put("final.b", fc[3].bias.float())
         self.inner = inner
         self.ws = ws
-        if self.precision == "bf16":
-            self._ensure_weights_bf16()
+        # channels of the running activation in front of every block (first source of the up blocks' concatenated input)
+        from .model import ucdir as U2
+        self._block_c0 = {}
+        c = None
+        for grp in ("downs", "mid", "ups"):
+            for k, layer in enumerate(getattr(m, grp)):
+                if isinstance(layer, torch.nn.Conv2d):
+                    c = layer.out_channels
+                elif isinstance(layer, U2.ResnetBlocWithAttn):
+                    self._block_c0["%s.%d" % (grp, k)] = c
+                    c = layer.res_block.dim_out
+        if self.precision in ("bf16", "fp32_tc"):
+            self._ensure_weights_bf16(split=self.precision == "fp32_tc")
 
     # ---- graph --------------------------------------------------------------------------
     def n_blocks(self):
@@ -793,10 +835,15 @@ class UNetEngine:
         return ol
 
     # ---- bf16 / tcgen05 graph --------------------------------------------------------------
-    def _ensure_weights_bf16(self):
-        """Packed bf16 operands + fp32 epilogue tables for every TC op (once per load)."""
+    def _ensure_weights_bf16(self, split: bool = False):
+        """Packed bf16 operands + fp32 epilogue tables for every TC op (once per load).  split: fp32_tc operand pairs."""
         from .model import ucdir as U
         ws, m = self.ws, self.m
+        sp = dict(split=True) if split else {}
+
+        def c0_of(name, layer):
+            """channels of the first source of a block's conv1 / res_conv (the up blocks read torch.cat((x, skip)))."""
+            return self._block_c0.get(name)
 
         def put3(name, triple):
             w, tb, tg = triple
@@ -807,39 +854,43 @@ class UNetEngine:
         for name, layer in self.blocks:
             rb = layer.res_block
             cout = rb.dim_out
-            put3(name + ".conv1", pack_tc_dense(rb.conv1.weight, rb.conv1.bias, _tc_nt(cout), rb.norm1.weight, rb.norm1.bias))
+            c0 = dict(c0=c0_of(name, layer)) if split else {}
+            put3(name + ".conv1", pack_tc_dense(rb.conv1.weight, rb.conv1.bias, _tc_nt(cout), rb.norm1.weight, rb.norm1.bias, **sp, **c0))
             put3(name + ".spdy", pack_tc_grouped(rb.spdyconv.weight, rb.spdyconv.bias, rb.nset, tc_mix_tiling(cout)[1],
-                                                 rb.norm2.weight, rb.norm2.bias))
+                                                 rb.norm2.weight, rb.norm2.bias, **sp))
             if isinstance(rb.res_conv, torch.nn.Conv2d):
-                put3(name + ".res", pack_tc_dense(rb.res_conv.weight, rb.res_conv.bias, _tc_nt(cout)))
+                put3(name + ".res", pack_tc_dense(rb.res_conv.weight, rb.res_conv.bias, _tc_nt(cout), **sp, **c0))
             if layer.with_attn:
                 at = layer.attn
-                put3(name + ".attn.qkv", pack_tc_dense(at.qkv.weight, None, 256, at.norm.weight, at.norm.bias))
-                put3(name + ".attn.out", pack_tc_dense(at.out.weight, at.out.bias, _tc_nt(at.out.out_channels)))
+                put3(name + ".attn.qkv", pack_tc_dense(at.qkv.weight, None, 256, at.norm.weight, at.norm.bias, **sp))
+                put3(name + ".attn.out", pack_tc_dense(at.out.weight, at.out.bias, _tc_nt(at.out.out_channels), **sp))
         for grp in ("downs", "ups"):
             for k, layer in enumerate(getattr(m, grp)):
                 name = "%s.%d" % (grp, k)
                 if isinstance(layer, torch.nn.Conv2d):          # in-conv: 6 -> 16 zero-padded input channels (KC = 16)
                     w = layer.weight
                     w = torch.cat([w, w.new_zeros(w.shape[0], 16 - w.shape[1], 3, 3)], dim=1)
-                    put3(name, pack_tc_dense(w, layer.bias, _tc_nt(layer.out_channels)))
+                    put3(name, pack_tc_dense(w, layer.bias, _tc_nt(layer.out_channels), **sp))
                 elif isinstance(layer, U.Downsample):
-                    put3(name, pack_tc_dense(layer.conv.weight, layer.conv.bias, _tc_nt(layer.conv.out_channels)))
+                    put3(name, pack_tc_dense(layer.conv.weight, layer.conv.bias, _tc_nt(layer.conv.out_channels), **sp))
                 elif isinstance(layer, U.Upsample):
                     for py in range(2):
                         for px in range(2):
-                            w, tb = pack_tc_up_phase(layer.conv.weight, layer.conv.bias, py, px, _tc_nt(layer.conv.out_channels))
+                            w, tb = pack_tc_up_phase(layer.conv.weight, layer.conv.bias, py, px, _tc_nt(layer.conv.out_channels), **sp)
                             ws.put("%s.p%d%d.tcw" % (name, py, px), w); ws.put("%s.p%d%d.tb" % (name, py, px), tb)
         fc = m.final_conv
-        put3("final", pack_tc_dense(fc[3].weight, fc[3].bias, 16))
+        put3("final", pack_tc_dense(fc[3].weight, fc[3].bias, 16, **sp))
         ws.put("zeros", torch.zeros(65536, dtype=F32, device=ws.device))    # bias table of the attention GEMMs
 
     def build_forward_ops_bf16(self, pool: Pool, BT: int, TH: int, TW: int, x_in: torch.Tensor, gmaps: List[torch.Tensor],
-                               attw: torch.Tensor, attw_stride: int, eps_ptr: int, stats: torch.Tensor) -> OpList:
-        """Same graph as build_forward_ops on the tcgen05 path: bf16 NHWC activations, x_in[BT,TH,TW,16] bf16."""
+                               attw: torch.Tensor, attw_stride: int, eps_ptr: int, stats: torch.Tensor, split: bool = False) -> OpList:
+        """Same graph as build_forward_ops on the tcgen05 path: bf16 NHWC activations, x_in[BT,TH,TW,16] bf16.
+        split (precision fp32_tc): every activation is a (hi, lo) bf16 plane pair and every op a three-pass split-operand
+        MMA on the streamed kernel (include/ucdir_b200.h, UCDIR_TC_I_SPLIT); x_in[BT,TH,TW,2*16]."""
         from .model import ucdir as U
         ws, m = self.ws, self.m
-        bld = _Builder(pool, BT, stats, elem=2)
+        bld = _Builder(pool, BT, stats, elem=2, split=split)
+        sp = 1 if split else 0
         ol = bld.ops
         nbytes = stats.numel() * stats.element_size()
         ol.add("UCDIR_OP_MEMSET", {0: stats.data_ptr()}, {0: nbytes & 0x7FFFFFFF, 1: nbytes >> 31})
@@ -853,15 +904,15 @@ class UNetEngine:
             h1 = bld.new(cout, x.H, x.W)
             has_res = ws.has(name + ".res.tcw")
             # the halo schedule computes the 1x1 res_conv from the activation box conv1 already holds in shared memory
-            fuse_res = (has_res and _TC_HALO and _TC_FUSE_RES and cout in (64, 128) and x.C % 64 == 0 and
+            fuse_res = (has_res and not split and _TC_HALO and _TC_FUSE_RES and cout in (64, 128) and x.C % 64 == 0 and
                         (skip is None or skip.C % 64 == 0))
             res = bld.new(cout, x.H, x.W, with_stats=False) if has_res else None
-            _tc_op(ol, src0=x, src1=skip, w=ws.ptr(name + ".conv1.tcw"), tb=ws.ptr(name + ".conv1.tb"),
+            _tc_op(ol, split=sp, src0=x, src1=skip, w=ws.ptr(name + ".conv1.tcw"), tb=ws.ptr(name + ".conv1.tb"),
                    tg=ws.ptr(name + ".conv1.tg"), gn=1, ncls=9, act=1, dst=h1, ntot=cout, B=BT, nt=nt,
                    **(dict(w2=ws.ptr(name + ".res.tcw"), tb2=ws.ptr(name + ".res.tb"), dst_res=res) if fuse_res else {}))
             if has_res:
                 if not fuse_res:
-                    _tc_op(ol, src0=x, src1=skip, w=ws.ptr(name + ".res.tcw"), tb=ws.ptr(name + ".res.tb"), nty=1, ntx=1, oy0=0,
+                    _tc_op(ol, split=sp, src0=x, src1=skip, w=ws.ptr(name + ".res.tcw"), tb=ws.ptr(name + ".res.tb"), nty=1, ntx=1, oy0=0,
                            ox0=0, dst=res, ntot=cout, B=BT, nt=nt)
                 own_res = True
             else:
@@ -870,7 +921,7 @@ class UNetEngine:
                 res, own_res = x, False
             out = bld.new(cout, x.H, x.W)
             kc, kb, mnt, nsplit = tc_mix_tiling(cout)
-            _tc_op(ol, src0=h1, w=ws.ptr(name + ".spdy.tcw"), tb=ws.ptr(name + ".spdy.tb"), tg=ws.ptr(name + ".spdy.tg"),
+            _tc_op(ol, split=sp, src0=h1, w=ws.ptr(name + ".spdy.tcw"), tb=ws.ptr(name + ".spdy.tb"), tg=ws.ptr(name + ".spdy.tg"),
                    gn=1, ncls=9, groups=rb.nset, kc=kc, kb=kb, nsplit=nsplit, nt=mnt, mode=1, att=gmaps[k].data_ptr(),
                    attw=attw.data_ptr() + k * 8 * 4, attw_stride=attw_stride, res=res, dst=out, ntot=cout * rb.nset, B=BT)
             bld.release(h1)
@@ -887,6 +938,8 @@ class UNetEngine:
             of the same tcgen05 kernel -- Q (a channel slice of the qkv conv's output) is the activation operand,
             K resp. V^T are per-image "weights" (3-D tensor map); V^T is written by the qkv conv's epilogue."""
             C, N = x.C, x.H * x.W
+            if split:
+                return attention_split(name, x)
             NP = (N + 7) & ~7                                   # 16-byte aligned row pitch of P and V^T
             nt_s = 256 if N % 256 == 0 else (128 if N % 128 == 0 else 64)
             NS = (N + nt_s - 1) // nt_s * nt_s                  # score columns incl. zero padding
@@ -894,14 +947,14 @@ class UNetEngine:
                 raise RuntimeError("attention over %d tokens exceeds the tensor-map strides" % N)
             qk = bld.new(2 * C, x.H, x.W, with_stats=False)
             vt = pool.get(BT * C * NP * 2)
-            _tc_op(ol, src0=x, w=ws.ptr(name + ".attn.qkv.tcw"), tb=ws.ptr(name + ".attn.qkv.tb"),
+            _tc_op(ol, split=sp, src0=x, w=ws.ptr(name + ".attn.qkv.tcw"), tb=ws.ptr(name + ".attn.qkv.tb"),
                    tg=ws.ptr(name + ".attn.qkv.tg"), gn=1, ncls=1, nty=1, ntx=1, oy0=0, ox0=0, dst=qk, ntot=3 * C, B=BT, nt=256,
                    dst2=vt.data_ptr(), t_col0=2 * C, t_ld=NP)
             S = pool.get(BT * N * NS * 4)
             zeros = ws.ptr("zeros")
             q_act = Act(qk.buf, C, x.H, x.W, 0, keep=True)
             s_dst = Act(S, NS, x.H, x.W, 0, keep=True)
-            _tc_op(ol, src0=q_act, src_cstride=2 * C, w=qk.ptr + C * 2, w_batched=1, w_rowstride=2 * C, w_batchstride=N * 2 * C,
+            _tc_op(ol, split=sp, src0=q_act, src_cstride=2 * C, w=qk.ptr + C * 2, w_batched=1, w_rowstride=2 * C, w_batchstride=N * 2 * C,
                    w_rows=N, tb=zeros, nty=1, ntx=1, oy0=0, ox0=0, dst=s_dst, ntot=NS, B=BT, nt=nt_s, dst_f32=1, ncol_valid=NS,
                    alpha=1.0 / math.sqrt(C))
             P = pool.get(BT * N * NP * 2)
@@ -909,29 +962,71 @@ class UNetEngine:
                    {"UCDIR_SOFTMAX_I_ROWS": BT * N, "UCDIR_SOFTMAX_I_COLS": N, "UCDIR_SOFTMAX_I_IN_LD": NS, "UCDIR_SOFTMAX_I_OUT_LD": NP})
             o = bld.new(C, x.H, x.W, with_stats=False)
             p_act = Act(P, N, x.H, x.W, 0, keep=True)
-            _tc_op(ol, src0=p_act, src_cstride=NP, w=vt.data_ptr(), w_batched=1, w_rowstride=NP, w_batchstride=C * NP, tb=zeros,
+            _tc_op(ol, split=sp, src0=p_act, src_cstride=NP, w=vt.data_ptr(), w_batched=1, w_rowstride=NP, w_batchstride=C * NP, tb=zeros,
                    nty=1, ntx=1, oy0=0, ox0=0, dst=o, ntot=C, B=BT, nt=_tc_nt(C))
             pool.put(S); pool.put(P); pool.put(vt)
             bld.release(qk)
             y = bld.new(C, x.H, x.W)
-            _tc_op(ol, src0=o, w=ws.ptr(name + ".attn.out.tcw"), tb=ws.ptr(name + ".attn.out.tb"), nty=1, ntx=1, oy0=0, ox0=0,
+            _tc_op(ol, split=sp, src0=o, w=ws.ptr(name + ".attn.out.tcw"), tb=ws.ptr(name + ".attn.out.tb"), nty=1, ntx=1, oy0=0, ox0=0,
+                   res=x, dst=y, ntot=C, B=BT, nt=_tc_nt(C))
+            bld.release(o)
+            bld.release(x)
+            return y
+
+        def attention_split(name, x: Act) -> Act:
+            """The same chain with (hi, lo) operand pairs: qk rows [q_hi k_hi | q_lo k_lo], V^T rows [hi: NP | lo: NP]
+            (zeroed first: the K tail of P x V^T must not meet stale bytes), fp32 scores, fp32 softmax in place, probabilities
+            split into plane pairs by UCDIR_OP_CAST mode 2."""
+            C, N = x.C, x.H * x.W
+            NP = _round_up(N, 64)                               # plane pitch of P and V^T: whole K chunks, zero padded
+            nt_s = 256 if N % 256 == 0 else (128 if N % 128 == 0 else 64)
+            NS = _round_up(N, nt_s)
+            if N * 4 * C >= 2 ** 31 or N * NS >= 2 ** 62:
+                raise RuntimeError("attention over %d tokens exceeds the tensor-map strides" % N)
+            qk = bld.new(2 * C, x.H, x.W, with_stats=False)      # physical rows of 4C
+            vt = pool.get(BT * C * 2 * NP * 2)
+            nb = BT * C * 2 * NP * 2
+            ol.add("UCDIR_OP_MEMSET", {0: vt.data_ptr()}, {0: nb & 0x7FFFFFFF, 1: nb >> 31})
+            _tc_op(ol, split=1, src0=x, w=ws.ptr(name + ".attn.qkv.tcw"), tb=ws.ptr(name + ".attn.qkv.tb"),
+                   tg=ws.ptr(name + ".attn.qkv.tg"), gn=1, ncls=1, nty=1, ntx=1, oy0=0, ox0=0, dst=qk, ntot=3 * C, B=BT, nt=256,
+                   dst2=vt.data_ptr(), t_col0=2 * C, t_ld=NP)
+            S = pool.get(BT * N * NS * 4)
+            zeros = ws.ptr("zeros")
+            q_act = Act(qk.buf, C, x.H, x.W, 0, keep=True, split=True)
+            s_dst = Act(S, NS, x.H, x.W, 0, keep=True)
+            _tc_op(ol, split=1, src0=q_act, src_cstride=4 * C, src_lo_off=2 * C, w=qk.ptr + C * 2, w_batched=1, w_rowstride=4 * C,
+                   w_lo_off=2 * C, w_batchstride=N * 4 * C, w_rows=N, tb=zeros, nty=1, ntx=1, oy0=0, ox0=0, dst=s_dst, ntot=NS, B=BT,
+                   nt=nt_s, dst_f32=1, ncol_valid=NS, alpha=1.0 / math.sqrt(C))
+            ol.add("UCDIR_OP_SOFTMAX_F32", {"UCDIR_SOFTMAX_P_X": S.data_ptr()},
+                   {"UCDIR_SOFTMAX_I_ROWS": BT * N, "UCDIR_SOFTMAX_I_COLS": N, "UCDIR_SOFTMAX_I_IN_LD": NS})
+            P = pool.get(BT * N * 2 * NP * 2)
+            rows = BT * N
+            ol.add("UCDIR_OP_CAST", {0: S.data_ptr(), 1: P.data_ptr()}, {0: rows & 0x7FFFFFFF, 1: rows >> 31, 2: 2, 3: N, 4: NS, 5: NP})
+            o = bld.new(C, x.H, x.W, with_stats=False)
+            p_act = Act(P, N, x.H, x.W, 0, keep=True, split=True)
+            _tc_op(ol, split=1, src0=p_act, src_cstride=2 * NP, src_lo_off=NP, w=vt.data_ptr(), w_batched=1, w_rowstride=2 * NP,
+                   w_lo_off=NP, w_batchstride=C * 2 * NP, tb=zeros, nty=1, ntx=1, oy0=0, ox0=0, dst=o, ntot=C, B=BT, nt=_tc_nt(C))
+            pool.put(S); pool.put(P); pool.put(vt)
+            bld.release(qk)
+            y = bld.new(C, x.H, x.W)
+            _tc_op(ol, split=1, src0=o, w=ws.ptr(name + ".attn.out.tcw"), tb=ws.ptr(name + ".attn.out.tb"), nty=1, ntx=1, oy0=0, ox0=0,
                    res=x, dst=y, ntot=C, B=BT, nt=_tc_nt(C))
             bld.release(o)
             bld.release(x)
             return y
 
         feats: List[Act] = []
-        x = Act(x_in, 16, TH, TW, 0, keep=True)
+        x = Act(x_in, 16, TH, TW, 0, keep=True, split=split)
         for k, layer in enumerate(m.downs):
             name = "downs.%d" % k
             if isinstance(layer, torch.nn.Conv2d):
                 y = bld.new(layer.out_channels, x.H, x.W)
-                _tc_op(ol, src0=x, w=ws.ptr(name + ".tcw"), tb=ws.ptr(name + ".tb"), kc=16, dst=y, ntot=layer.out_channels,
+                _tc_op(ol, split=sp, src0=x, w=ws.ptr(name + ".tcw"), tb=ws.ptr(name + ".tb"), kc=16, dst=y, ntot=layer.out_channels,
                        B=BT, nt=_tc_nt(layer.out_channels))
                 x = y
             elif isinstance(layer, U.Downsample):
                 y = bld.new(x.C, x.H // 2, x.W // 2)
-                _tc_op(ol, src0=x, w=ws.ptr(name + ".tcw"), tb=ws.ptr(name + ".tb"), stride=2, dst=y, ntot=x.C, B=BT,
+                _tc_op(ol, split=sp, src0=x, w=ws.ptr(name + ".tcw"), tb=ws.ptr(name + ".tb"), stride=2, dst=y, ntot=x.C, B=BT,
                        nt=_tc_nt(x.C))
                 x = y
             else:
@@ -948,7 +1043,7 @@ class UNetEngine:
                 y = bld.new(x.C, x.H * 2, x.W * 2)
                 for py in range(2):
                     for px in range(2):
-                        _tc_op(ol, src0=x, w=ws.ptr("%s.p%d%d.tcw" % (name, py, px)), tb=ws.ptr("%s.p%d%d.tb" % (name, py, px)),
+                        _tc_op(ol, split=sp, src0=x, w=ws.ptr("%s.p%d%d.tcw" % (name, py, px)), tb=ws.ptr("%s.p%d%d.tb" % (name, py, px)),
                                nty=2, ntx=2, oy0=py - 1, ox0=px - 1, dst=y, ntot=x.C, B=BT, nt=_tc_nt(x.C), dst_up=1,
                                dst_py=py, dst_px=px)
                 bld.release(x)
@@ -962,8 +1057,8 @@ class UNetEngine:
         # shared memory and runs the 16-column (3 valid) conv to fp32 eps (csrc/ucdir_fhalo.cu).  Otherwise: one elementwise
         # pass, then the streamed conv.
         eps_dst = Act(_PtrBuf(eps_ptr), 4, TH, TW, 0, keep=True)      # type: ignore[arg-type]
-        if _TC_HALO and x.C % 64 == 0 and x.C <= 128:
-            _tc_op(ol, src0=x, w=ws.ptr("final.tcw"), tb=ws.ptr("final.tb"), dst=eps_dst, ntot=16, B=BT, nt=16, dst_f32=1,
+        if _TC_HALO and not split and x.C % 64 == 0 and x.C <= 128:
+            _tc_op(ol, split=sp, src0=x, w=ws.ptr("final.tcw"), tb=ws.ptr("final.tb"), dst=eps_dst, ntot=16, B=BT, nt=16, dst_f32=1,
                    ncol_valid=m.cfg["out_channel"], src_gn_swish=1, src_gamma=ws.ptr("final.norm.w"), src_beta=ws.ptr("final.norm.b"))
             bld.release(x)
         else:
@@ -971,9 +1066,10 @@ class UNetEngine:
             ol.add("UCDIR_OP_GN_APPLY_BF16",
                    {"UCDIR_GNA_P_SRC": x.ptr, "UCDIR_GNA_P_DST": xn.ptr, "UCDIR_GNA_P_GAMMA": ws.ptr("final.norm.w"),
                     "UCDIR_GNA_P_BETA": ws.ptr("final.norm.b"), "UCDIR_GNA_P_STATS": x.stats},
-                   {"UCDIR_GNA_I_B": BT, "UCDIR_GNA_I_HW": x.H * x.W, "UCDIR_GNA_I_C": x.C, "UCDIR_GNA_I_SWISH": 1}, {0: 1e-5})
+                   {"UCDIR_GNA_I_B": BT, "UCDIR_GNA_I_HW": x.H * x.W, "UCDIR_GNA_I_C": x.C, "UCDIR_GNA_I_SWISH": 1,
+                    "UCDIR_GNA_I_SPLIT": sp}, {0: 1e-5})
             bld.release(x)
-            _tc_op(ol, src0=xn, w=ws.ptr("final.tcw"), tb=ws.ptr("final.tb"), dst=eps_dst, ntot=16, B=BT, nt=16, dst_f32=1,
+            _tc_op(ol, split=sp, src0=xn, w=ws.ptr("final.tcw"), tb=ws.ptr("final.tb"), dst=eps_dst, ntot=16, B=BT, nt=16, dst_f32=1,
                    ncol_valid=m.cfg["out_channel"])
             bld.release(xn)
         self.last_stat_slots = bld.next_slot
@@ -1097,8 +1193,9 @@ class Session:
         self.guide_tiles_all = []
         maxbt = max((b - a) for a, b in self.chunks) if self.chunks else 1
         self.stats = torch.empty((MAX_STAT_SLOTS, maxbt, 2), dtype=torch.float64, device=dev)
-        self.bf16 = eng.precision == "bf16"
-        self.x_tiles = torch.empty((maxbt, g.TH, g.TW, 16), dtype=BF16, device=dev) if self.bf16 else \
+        self.bf16 = eng.precision in ("bf16", "fp32_tc")          # tensor-core path (bf16 storage; fp32_tc: hi/lo plane pairs)
+        self.split = eng.precision == "fp32_tc"
+        self.x_tiles = torch.empty((maxbt, g.TH, g.TW, 32 if self.split else 16), dtype=BF16, device=dev) if self.bf16 else \
             torch.empty((maxbt, g.TH, g.TW, 8), dtype=F32, device=dev)
         # step op 0: timestep embedding -> attw table
         self.idx_temb = eng.time_embed_op(self.step_ops, self.attw, 1, 0, 0.0)
@@ -1123,7 +1220,7 @@ class Session:
                 {"UCDIR_GATHER_I_BT": BT, "UCDIR_GATHER_I_TH": g.TH, "UCDIR_GATHER_I_TW": g.TW,
                  "UCDIR_GATHER_I_IMG_H": g.IH, "UCDIR_GATHER_I_IMG_W": g.IW, "UCDIR_GATHER_I_PD": g.PD,
                  "UCDIR_GATHER_I_CA": ca, "UCDIR_GATHER_I_CB": 6 - ca, "UCDIR_GATHER_I_CD": 16 if self.bf16 else 8,
-                 "UCDIR_GATHER_I_OUT_BF16": 1 if self.bf16 else 0}))
+                 "UCDIR_GATHER_I_OUT_BF16": (2 if self.split else 1) if self.bf16 else 0}))
             ih, iw = g.TH - 2 * self.crop, g.TW - 2 * self.crop
             if self.crop:
                 if not hasattr(self, "eps_full"):
@@ -1132,8 +1229,11 @@ class Session:
             else:
                 eps_ptr = self.eps.data_ptr() + a * g.TH * g.TW * 4 * 4
             stats_view = self.stats.view(-1)[:MAX_STAT_SLOTS * BT * 2].view(MAX_STAT_SLOTS, BT, 2)   # same storage
-            build = eng.build_forward_ops_bf16 if self.bf16 else eng.build_forward_ops
-            sub = build(self.pool, BT, g.TH, g.TW, self.x_tiles, gmaps, self.attw, 0, eps_ptr, stats_view)
+            if self.bf16:
+                sub = eng.build_forward_ops_bf16(self.pool, BT, g.TH, g.TW, self.x_tiles, gmaps, self.attw, 0, eps_ptr, stats_view,
+                                                 split=self.split)
+            else:
+                sub = eng.build_forward_ops(self.pool, BT, g.TH, g.TW, self.x_tiles, gmaps, self.attw, 0, eps_ptr, stats_view)
             self._chunk_attw_fix(sub, a)
             self.step_ops.extend(sub)
             if self.crop:
