@@ -89,7 +89,7 @@ def swish(x: Tensor) -> Tensor:
 def positional_encoding(noise_level: Tensor, dim: int) -> Tensor:
     """model/ucdir.py:24-29.  noise_level (B,1) -> (B,1,dim)."""
     count = dim // 2
-    step = torch.arange(count, dtype=noise_level.dtype) / count
+    step = torch.arange(count, dtype=noise_level.dtype, device=noise_level.device) / count
     enc = noise_level.unsqueeze(1) * torch.exp(-math.log(1e4) * step.unsqueeze(0))
     return torch.cat([torch.sin(enc), torch.cos(enc)], dim=-1)
 

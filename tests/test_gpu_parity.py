@@ -18,11 +18,16 @@ RTOL, ATOL = 1e-3, 1e-4
 T = lambda a: torch.from_numpy(np.asarray(a))
 
 
+REPORT, MODE = {}, ["-"]
+
+
 def close(a, b, rtol=RTOL, atol=ATOL, what=""):
     a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
     assert a.shape == b.shape, (a.shape, b.shape)
     err = (a - b).abs()
     bad = (err > atol + rtol * b.abs()).float().mean().item()
+    REPORT.setdefault(MODE[0], {})[what] = {"max_abs_err": err.max().item(), "mean_abs_err": err.mean().item(),
+                                            "ref_absmax": b.abs().max().item(), "frac_outside": bad}
     assert bad == 0.0, f"{what}: max abs err {err.max().item():.3e}, {bad:.2%} of elements outside rtol={rtol} atol={atol}"
 
 
@@ -37,8 +42,13 @@ def net(sid_weights, request):
     n = n.to("cuda")
     n.set_new_noise_schedule(ucdir_b200.SID_VAL_SCHEDULE, torch.device("cuda"))
     n.denoise_fn.engine().set_precision(request.param)
+    MODE[0] = request.param
     yield n
     n.denoise_fn.engine().set_precision("fp32")
+    MODE[0] = "-"
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(REPORT, open("gpurun_out/fp32_errors.json", "w"), indent=1)      # measured errors per mode, copied to profiles/
 
 
 @pytest.fixture(scope="module")
