@@ -454,3 +454,35 @@ def test_fp32_tc_graph_meets_fp32_tolerance(emulated, golden, sid_weights):
         close(eps2, g["eps2"])
     finally:
         eng.set_precision("fp32")
+
+
+def test_reference_ddpm_methods_drive_our_module(emulated, sid_weights):
+    """The reference's own `DDPM.feed_data / test / get_current_visuals / set_new_noise_schedule` (model/model.py:101-179,
+    unmodified, imported through tests/shims) operating on the module ucdir_b200.define_G returns, kernels emulated on CPU.
+    `DDPM.__init__` itself needs CUDA + a process group (it hard-codes torch.device('cuda') and wraps in DDP): that part runs on
+    the GPU box in tests/test_gpu_reference_caller.py; here the object is built without it."""
+    from oracle import ucdir_oracle as O
+    from tests import shims
+    if shims.install() is None:
+        pytest.skip("reference tree not available")
+    import model.model as refmodel
+    net, sd = sid_weights
+    dd = refmodel.DDPM.__new__(refmodel.DDPM)
+    dd.opt, dd.device, dd.netG, dd.schedule_phase = {"phase": "val"}, torch.device("cpu"), net, None
+    so = dict(schedule="linear", n_timestep=1, linear_start=1e-6, linear_end=0.4)
+    dd.set_new_noise_schedule(so, schedule_phase="val")
+    gen = torch.Generator().manual_seed(3)
+    sr = torch.rand(1, 3, 72, 80, generator=gen) * 2 - 1
+    noise = torch.randn(1, 3, 72 + 128, 80 + 128, generator=gen)
+    net._noise_source = lambda shape: noise
+    try:
+        dd.feed_data({"SR": sr.clone(), "HR": sr.clone(), "Index": torch.tensor([0])})
+        dd.test(continous=True)
+    finally:
+        net._noise_source = None
+    vis = dd.get_current_visuals()
+    lay = O.UNetLayout(**ucdir_b200.SID_MODEL_OPT["unet"])
+    with torch.no_grad():
+        want = O.ddpm_test(sd, lay, O.schedule_buffers(so), sr, [noise], continous=True)
+    close(vis["SR"], want)
+    assert torch.equal(vis["INF"], sr) and net.training
