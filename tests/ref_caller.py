@@ -1,7 +1,7 @@
 """Runner (subprocess of tests/test_gpu_reference_caller.py): drives the REFERENCE's own caller code against ucdir_b200.
 
     python tests/ref_caller.py ddpm  <workdir>     # model/model.py DDPM(opt): DDP wrap, EMA deepcopy, load_network, test()
-    python tests/ref_caller.py sr_py <workdir>     # the unmodified sr.py, `-p val`, through runpy
+    python tests/ref_caller.py sr_py <workdir>     # the unmodified sr.py source, `-p val`, executed as __main__
 
 The only binding added is the one INTEGRATION.md section 1 documents: `model.networks.define_G = ucdir_b200...define_G`
 (+ import shims for modules this image lacks, tests/shims).  For comparability with the CPU oracle the sampler noise is drawn
@@ -9,7 +9,6 @@ from a seeded CPU generator (the `_noise_source` test hook) -- CUDA and CPU gene
 TEST INFRASTRUCTURE ONLY."""
 import json
 import os
-import runpy
 import sys
 
 import numpy as np
@@ -97,8 +96,12 @@ def run_sr_py(work):
     os.chdir(work)
     sys.argv = ["sr.py", "-p", "val", "-c", os.path.join(ref, "config", "sid.yaml"), "-launcher", "pytorch", "-d",
                 "--checkpoint", os.path.join(work, "ckpt", "I_E")]
+    # The script's source is executed unchanged in THIS process's __main__ namespace rather than through runpy.run_path: runpy
+    # swaps sys.modules['__main__'] for a temporary module whose __file__ is sr.py, and the DataLoader workers sr.py spawns
+    # (utils/dist_utils.py:11 sets the 'spawn' start method) would then re-import sr.py -- without the import shims.
+    path = os.path.join(ref, "sr.py")
     try:
-        runpy.run_path(os.path.join(ref, "sr.py"), run_name="__main__")
+        exec(compile(open(path).read(), path, "exec"), sys.modules["__main__"].__dict__)
     finally:
         np.savez(os.path.join(work, "sr_py_out.npz"), **{k.replace(".", "_"): v for k, v in saved.items()})
     print("sr.py ok", sorted(saved))

@@ -54,7 +54,7 @@ def test_reference_ddpm_wraps_define_g(tmp_path, sid_weights):
     so = dict(schedule="linear", n_timestep=3, linear_start=1e-6, linear_end=0.4)
     json.dump(so, open(tmp_path / "sched.json", "w"))
     g = torch.Generator().manual_seed(12)
-    imgs = torch.rand(2, 3, 40, 48, generator=g) * 2 - 1
+    imgs = torch.rand(2, 3, 72, 80, generator=g) * 2 - 1
     np.savez(tmp_path / "inputs.npz", sr=imgs.numpy())
     _run("ddpm", tmp_path)
     out = np.load(tmp_path / "ddpm_out.npz")
@@ -62,7 +62,7 @@ def test_reference_ddpm_wraps_define_g(tmp_path, sid_weights):
     sched = O.schedule_buffers(so)
     assert np.array_equal(out["betas"], sched["betas"])
     gen = torch.Generator().manual_seed(NOISE_SEED)
-    shape = (1, 3, 40 + 128, 48 + 128)
+    shape = (1, 3, 72 + 128, 80 + 128)
     for k in range(2):
         noises = [torch.randn(shape, generator=gen) for _ in range(3)]
         with torch.no_grad():
@@ -78,7 +78,7 @@ def test_reference_ddpm_wraps_define_g(tmp_path, sid_weights):
 
 
 def test_sr_py_val_runs_unchanged(tmp_path, sid_weights):
-    """`python sr.py -p val -c config/sid.yaml -launcher pytorch -d --checkpoint ...` (README.md:55-58) through runpy, unchanged:
+    """`python sr.py -p val -c config/sid.yaml -launcher pytorch -d --checkpoint ...` (README.md:55-58), its source executed unchanged as __main__:
     core/logger.py parses the yaml (val schedule: 'sid' -> T = 50, debug -> T = 10), data/ builds the PairDataset loader over
     two synthetic low-light PNG pairs, DDPM wraps define_G's network, every image goes through feed_data / test(continous=True) /
     get_current_visuals / tensor2img / save_jpg and the PSNR / SSIM summary is logged.  The final SR image of every input equals
@@ -93,14 +93,14 @@ def test_sr_py_val_runs_unchanged(tmp_path, sid_weights):
     rng = np.random.RandomState(5)
     names = ["a0001", "a0002"]
     for n in names:
-        scene = rng.randint(0, 256, size=(40, 48, 3)).astype(np.uint8)
+        scene = rng.randint(0, 256, size=(72, 80, 3)).astype(np.uint8)
         Image.fromarray(scene).save(gt / (n + ".png"))
         Image.fromarray((scene * 0.1).astype(np.uint8)).save(lq / (n + ".png"))
     log = _run("sr_py", tmp_path)
     assert "# Validation # PSNR" in log
     out = np.load(tmp_path / "sr_py_out.npz")
     lay = O.UNetLayout(**ucdir_b200.SID_MODEL_OPT["unet"])
-    so = dict(schedule="linear", n_timestep=10, linear_start=1e-6, linear_end=0.1)      # sid.yaml val schedule, debug T = 10
+    so = dict(schedule="linear", n_timestep=10, linear_start=1e-6, linear_end=0.4)      # core/logger.py:58-61 (sid: 0.4), debug: T = 10
     sched = O.schedule_buffers(so)
     gen = torch.Generator().manual_seed(NOISE_SEED)
     for n in names:
@@ -108,7 +108,7 @@ def test_sr_py_val_runs_unchanged(tmp_path, sid_weights):
         assert len(key) == 1, out.files
         lq_img = torch.from_numpy(np.asarray(Image.open(lq / (n + ".png")).convert("RGB")).copy()).permute(2, 0, 1).float() / 255.0
         x = (lq_img * 2 - 1).unsqueeze(0)               # data/util.py transform_augment(split='val', min_max=(-1, 1))
-        noises = [torch.randn((1, 3, 40 + 128, 48 + 128), generator=gen) for _ in range(10)]
+        noises = [torch.randn((1, 3, 72 + 128, 80 + 128), generator=gen) for _ in range(10)]
         with torch.no_grad():
             want = O.ddpm_test(sd, lay, sched, x, noises, continous=True)
         want_img = O.tensor2img(want[-1])
