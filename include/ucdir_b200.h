@@ -244,6 +244,16 @@ enum ucdir_tc_int {
 };
 enum ucdir_tc_flt { UCDIR_TC_F_EPS = 0, UCDIR_TC_F_ALPHA = 1 /* 0 = 1.0 */ };
 
+/* ---- UCDIR_OP_TC_ATTN: O = softmax(Q K^T * SCALE) V for one head of C = 512 channels, fused (ucdir_attn.cu) ---------------
+ * SelfAttention.forward's two einsums and softmax (model/ucdir.py:174-179) in one kernel: scores in TMEM, online softmax in
+ * registers, probabilities through shared memory; the N x N matrices never touch HBM.
+ * QK = bf16 [B][N][QK_LD]: the qkv convolution's output rows, Q = channels [0, C), K = channels [C, 2C);
+ * VT = bf16 [B][C][VT_LD]: V transposed (written by that convolution through UCDIR_TC_P_DST2); O = bf16 [B][N][O_LD].
+ * f[SCALE] = 0 means 1 / sqrt(C) (model/ucdir.py:174). */
+enum ucdir_attn_ptr { UCDIR_ATTN_P_QK = 0, UCDIR_ATTN_P_VT = 1, UCDIR_ATTN_P_O = 2 };
+enum ucdir_attn_int { UCDIR_ATTN_I_B = 0, UCDIR_ATTN_I_N = 1, UCDIR_ATTN_I_C = 2, UCDIR_ATTN_I_QK_LD = 3, UCDIR_ATTN_I_VT_LD = 4, UCDIR_ATTN_I_O_LD = 5 };
+enum ucdir_attn_flt { UCDIR_ATTN_F_SCALE = 0 };
+
 /* ---- UCDIR_OP_GN_APPLY_BF16: DST = [Swish](GroupNorm(1,C)(SRC)) on bf16 NHWC [B][HW][C]; f[0] = eps ------------
  * SPLIT = 1: SRC and DST are (hi, lo) plane pairs [B][HW][2*C] (see UCDIR_TC_I_SPLIT), fp32 math, exact Swish. */
 enum ucdir_gna_ptr { UCDIR_GNA_P_SRC = 0, UCDIR_GNA_P_DST = 1, UCDIR_GNA_P_GAMMA = 2, UCDIR_GNA_P_BETA = 3, UCDIR_GNA_P_STATS = 4 };

@@ -482,6 +482,21 @@ def emu_tc_conv(op, mem):
         st[:, 1] += (vd * vd).sum(1)
 
 
+def emu_tc_attn(op, mem):
+    """UCDIR_OP_TC_ATTN restated: bf16 Q / K / V^T, fp32 scores and softmax, bf16 probabilities (unnormalised in the kernel,
+    normalised here: same values up to rounding), fp32 accumulation, bf16 output."""
+    g = lambda n: _i(op, "UCDIR_ATTN_I_" + n)
+    B, N, Cc, qk_ld, vt_ld, o_ld = g("B"), g("N"), g("C"), g("QK_LD"), g("VT_LD"), g("O_LD")
+    bf = torch.bfloat16
+    qk = mem.view(_p(op, "UCDIR_ATTN_P_QK"), (B, N, qk_ld), bf).float()
+    vt = mem.view(_p(op, "UCDIR_ATTN_P_VT"), (B, Cc, vt_ld), bf).float()[:, :, :N]
+    scale = float(op.f[K["UCDIR_ATTN_F_SCALE"]]) or 1.0 / math.sqrt(Cc)
+    q, k = qk[..., :Cc], qk[..., Cc:2 * Cc]
+    att = torch.softmax(torch.bmm(q, k.transpose(1, 2)) * scale, dim=-1).to(bf).float()
+    o = torch.bmm(att, vt.transpose(1, 2))
+    mem.view(_p(op, "UCDIR_ATTN_P_O"), (B, N, o_ld), bf)[..., :Cc] = o.to(bf)
+
+
 def emu_gn_apply(op, mem):
     B, HW, Cc, sw = _i(op, "UCDIR_GNA_I_B"), _i(op, "UCDIR_GNA_I_HW"), _i(op, "UCDIR_GNA_I_C"), _i(op, "UCDIR_GNA_I_SWISH")
     bf = torch.bfloat16
@@ -578,6 +593,7 @@ DISPATCH = {
     K["UCDIR_OP_MEMSET"]: emu_memset, K["UCDIR_OP_TC_CONV"]: emu_tc_conv, K["UCDIR_OP_GN_APPLY_BF16"]: emu_gn_apply,
     K["UCDIR_OP_CAST"]: emu_cast, K["UCDIR_OP_CROP_TILES"]: emu_crop, K["UCDIR_OP_GN_STATS_F32"]: emu_gn_stats,
     K["UCDIR_OP_GN_APPLY_F32"]: emu_gn_apply_f32, K["UCDIR_OP_LAYOUT"]: emu_layout, K["UCDIR_OP_TO_IMAGE_U8"]: emu_to_image,
+    K["UCDIR_OP_TC_ATTN"]: emu_tc_attn,
 }
 
 LAUNCHED = []

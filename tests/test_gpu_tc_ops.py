@@ -361,3 +361,76 @@ def test_tc_dense_row3(cfg):
     assert_close(dev["dst"], host["dst"], "dst")
     assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
 
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# fused attention core (csrc/ucdir_attn.cu): UCDIR_OP_TC_ATTN against torch on the same bf16 operands
+# --------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N", [(3, 256), (2, 400), (1, 1296), (2, 64), (1, 16), (1, 2176)])
+def test_tc_flash_attention(B, N):
+    """N = 256 / 400 / 1296: the token counts of 128 / 160 / 288-pixel samples; 64 and 16: less than one key block /
+    one MMA K step; 2176 = 17 key blocks (lazy-rescale path across many blocks, both score buffers, ring wrap-around).
+    Scores are scaled up so that the softmax is peaked (row maxima move between blocks) for half of the cases."""
+    C = 512
+    g = torch.Generator().manual_seed(N * 7 + B)
+    NP = (N + 7) & ~7
+    for peak in (1.0, 6.0):
+        qk = (rnd(g, B, N, 2 * C) * peak).to(BF)
+        v = rnd(g, B, N, C).to(BF)
+        vt = torch.zeros(B, C, NP, dtype=BF)
+        vt[:, :, :N] = v.transpose(1, 2)
+        vt[:, :, N:] = float("nan")                                  # the pitch padding must never be read
+        c = Case().add("qk", qk).add("vt", vt).add("o", torch.zeros(B, N, C, dtype=BF))
+
+        def build(t):
+            ol = E.OpList()
+            ol.add("UCDIR_OP_TC_ATTN", {"UCDIR_ATTN_P_QK": t["qk"].data_ptr(), "UCDIR_ATTN_P_VT": t["vt"].data_ptr(), "UCDIR_ATTN_P_O": t["o"].data_ptr()},
+                   {"UCDIR_ATTN_I_B": B, "UCDIR_ATTN_I_N": N, "UCDIR_ATTN_I_C": C, "UCDIR_ATTN_I_QK_LD": 2 * C, "UCDIR_ATTN_I_VT_LD": NP,
+                    "UCDIR_ATTN_I_O_LD": C}, {"UCDIR_ATTN_F_SCALE": 1.0 / np.sqrt(C)})
+            return ol
+
+        ol = build(c.on("cuda"))                                      # record validation (no launch)
+        _lib.check_ops(ol.array(), len(ol))
+        devt = c.on("cuda")
+        ol = build(devt)
+        _lib.run_ops(ol.array(), len(ol), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = devt["o"].cpu().float()
+        q, k = qk[..., :C].float(), qk[..., C:].float()
+        att = torch.softmax(torch.bmm(q, k.transpose(1, 2)) / np.sqrt(C), dim=-1)
+        want = torch.bmm(att, v.float())
+        assert torch.isfinite(got).all(), "non-finite output (N=%d peak=%g)" % (N, peak)
+        assert_close(got, want, "flash attention B=%d N=%d peak=%g" % (B, N, peak), rtol=2e-2, atol=1e-2)
+
+
+def test_tc_flash_attention_16k_tokens_vs_materialised_path():
+    """N = 16 384 (a 1024x1024 tile at 1/8 resolution -- what `sr.py -p val` runs): the fused kernel against the three-launch
+    form (score GEMM to fp32 in HBM, softmax, PV GEMM) of the same library on identical operands."""
+    C, N, B = 512, 16384, 1
+    g = torch.Generator().manual_seed(4)
+    x = (rnd(g, B, 128, 128, C) * 0.5).to(BF).cuda()
+    wq = (rnd(g, 3 * C, C) * (1.0 / np.sqrt(C))).to(BF).cuda()
+    tb = torch.zeros(3 * C).cuda()
+    qk = torch.empty(B, N, 2 * C, dtype=BF, device="cuda")
+    vt = torch.empty(B, C, N, dtype=BF, device="cuda")
+    o1 = torch.empty(B, N, C, dtype=BF, device="cuda"); o2 = torch.empty_like(o1)
+    S = torch.empty(B, N, N, dtype=torch.float32, device="cuda"); P = torch.empty(B, N, N, dtype=BF, device="cuda")
+    zeros = torch.zeros(N, device="cuda")
+    ol = E.OpList()
+    xa = act(x, C, 128, 128)
+    E._tc_op(ol, src0=xa, w=wq.data_ptr(), tb=tb.data_ptr(), nty=1, ntx=1, oy0=0, ox0=0, dst=act(qk, 2 * C, 128, 128), ntot=3 * C, B=B, nt=256,
+             dst2=vt.data_ptr(), t_col0=2 * C, t_ld=N)
+    ol.add("UCDIR_OP_TC_ATTN", {"UCDIR_ATTN_P_QK": qk.data_ptr(), "UCDIR_ATTN_P_VT": vt.data_ptr(), "UCDIR_ATTN_P_O": o1.data_ptr()},
+           {"UCDIR_ATTN_I_B": B, "UCDIR_ATTN_I_N": N, "UCDIR_ATTN_I_C": C, "UCDIR_ATTN_I_QK_LD": 2 * C, "UCDIR_ATTN_I_VT_LD": N, "UCDIR_ATTN_I_O_LD": C})
+    E._tc_op(ol, src0=act(qk, C, 128, 128), src_cstride=2 * C, w=qk.data_ptr() + C * 2, w_batched=1, w_rowstride=2 * C, w_batchstride=N * 2 * C,
+             w_rows=N, tb=zeros.data_ptr(), nty=1, ntx=1, oy0=0, ox0=0, dst=act(S, N, 128, 128), ntot=N, B=B, nt=256, dst_f32=1, ncol_valid=N,
+             alpha=1.0 / np.sqrt(C))
+    ol.add("UCDIR_OP_SOFTMAX_F32", {"UCDIR_SOFTMAX_P_X": S.data_ptr(), "UCDIR_SOFTMAX_P_OUT_BF16": P.data_ptr()},
+           {"UCDIR_SOFTMAX_I_ROWS": B * N, "UCDIR_SOFTMAX_I_COLS": N, "UCDIR_SOFTMAX_I_IN_LD": N, "UCDIR_SOFTMAX_I_OUT_LD": N})
+    E._tc_op(ol, src0=act(P, N, 128, 128), src_cstride=N, w=vt.data_ptr(), w_batched=1, w_rowstride=N, w_batchstride=C * N, tb=zeros.data_ptr(),
+             nty=1, ntx=1, oy0=0, ox0=0, dst=act(o2, C, 128, 128), ntot=C, B=B, nt=256)
+    _lib.run_ops(ol.array(), len(ol), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    a, b = o1.float().cpu(), o2.float().cpu()
+    assert torch.isfinite(a).all()
+    assert_close(a, b, "flash vs materialised attention, 16384 tokens", rtol=2e-2, atol=1e-2)

@@ -1046,6 +1046,4 @@ int launch_cast(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   return 0;
 }
 
-int launch_tc_attn(const ucdir_op_t&, cudaStream_t, bool) { set_error("TC_ATTN not built yet"); return -2; }
-
 }  // namespace ucdir

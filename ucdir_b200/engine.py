@@ -500,6 +500,9 @@ where its preconditions hold).  On unless UCDIR_TC_ROW3=0."""
 _TC_FUSE_RES = 0 if os.environ.get("UCDIR_TC_FUSE_RES", "1") == "0" else 1
 """Fuse a block's 1x1 res_conv into its conv1 launch where the halo schedule applies (csrc/ucdir_dhalo.cu, RES).  On unless
 UCDIR_TC_FUSE_RES=0."""
+_TC_FLASH = 0 if os.environ.get("UCDIR_TC_FLASH", "1") == "0" else 1
+"""Fused attention core (csrc/ucdir_attn.cu: QK^T -> online softmax -> PV in one kernel, scores / probabilities never in HBM) for
+the 512-channel attention layers of the bf16 path.  UCDIR_TC_FLASH=0 keeps the three-launch form (score GEMM, softmax, PV GEMM)."""
 _TC_HALO = 0 if os.environ.get("UCDIR_TC_HALO", "1") == "0" else 1
 """Request the halo / weight-stationary schedule (csrc/ucdir_mix.cu) for the integration-module convs with C = 64 / 128 /
 256 (the library applies it only where its preconditions hold).  On unless UCDIR_TC_HALO=0."""
@@ -950,6 +953,19 @@ class UNetEngine:
             _tc_op(ol, split=sp, src0=x, w=ws.ptr(name + ".attn.qkv.tcw"), tb=ws.ptr(name + ".attn.qkv.tb"),
                    tg=ws.ptr(name + ".attn.qkv.tg"), gn=1, ncls=1, nty=1, ntx=1, oy0=0, ox0=0, dst=qk, ntot=3 * C, B=BT, nt=256,
                    dst2=vt.data_ptr(), t_col0=2 * C, t_ld=NP)
+            if _TC_FLASH and C == 512:
+                o = bld.new(C, x.H, x.W, with_stats=False)
+                ol.add("UCDIR_OP_TC_ATTN", {"UCDIR_ATTN_P_QK": qk.ptr, "UCDIR_ATTN_P_VT": vt.data_ptr(), "UCDIR_ATTN_P_O": o.ptr},
+                       {"UCDIR_ATTN_I_B": BT, "UCDIR_ATTN_I_N": N, "UCDIR_ATTN_I_C": C, "UCDIR_ATTN_I_QK_LD": 2 * C,
+                        "UCDIR_ATTN_I_VT_LD": NP, "UCDIR_ATTN_I_O_LD": C}, {"UCDIR_ATTN_F_SCALE": 1.0 / math.sqrt(C)})
+                pool.put(vt)
+                bld.release(qk)
+                y = bld.new(C, x.H, x.W)
+                _tc_op(ol, split=sp, src0=o, w=ws.ptr(name + ".attn.out.tcw"), tb=ws.ptr(name + ".attn.out.tb"), nty=1, ntx=1, oy0=0,
+                       ox0=0, res=x, dst=y, ntot=C, B=BT, nt=_tc_nt(C))
+                bld.release(o)
+                bld.release(x)
+                return y
             S = pool.get(BT * N * NS * 4)
             zeros = ws.ptr("zeros")
             q_act = Act(qk.buf, C, x.H, x.W, 0, keep=True)
