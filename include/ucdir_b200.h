@@ -238,6 +238,9 @@ enum ucdir_tc_int {
   UCDIR_TC_I_SPLIT = 47,
   UCDIR_TC_I_SRC_LO_OFF = 48,                    /* SPLIT: elements from the hi to the lo plane inside a SRC0 row (0 = C0); with SRC_CSTRIDE for channel slices */
   UCDIR_TC_I_W_LO_OFF = 49,                      /* SPLIT + W_BATCHED: elements from the hi to the lo plane inside a weight row (W_ROWSTRIDE = physical pitch) */
+  UCDIR_TC_I_DST_CROP = 50,                      /* fused final conv only: DST is [B][H - 2*CROP][W - 2*CROP][DST_C] and receives only the interior of every
+                                                  * sample -- the part of a tile that is stitched (utils/util.py:144-145) and, sharded, all-gathered; replaces a
+                                                  * separate UCDIR_OP_CROP_TILES pass */
   UCDIR_TC_I_HALO = 43                           /* 1: halo schedule where it applies (grouped mix convs, C = 64 / 128 / 256): one 10 x 18 pixel TMA box per
                                                   * 8 x 16 pixel tile serves all nine taps, weights stay resident in shared memory (ucdir_mix.cu); 3x3 convs with 64 / 128 output
                                                   * channels: super tiles (ucdir_dhalo.cu) */

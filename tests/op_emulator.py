@@ -462,6 +462,11 @@ def emu_tc_conv(op, mem):
         out, out32 = out[..., :t0], out32[..., :t0]
         nout = t0
     pitch = 2 * dstC if pair else dstC
+    crop = g("DST_CROP")
+    if crop:                                                     # fused final conv: only the interior, compact destination
+        dst = mem.view(_p(op, "UCDIR_TC_P_DST"), (B, H - 2 * crop, W - 2 * crop, pitch), odt)
+        dst[..., dstCoff:dstCoff + nout] = out[:, crop:H - crop, crop:W - crop]
+        return
     if dstUp:
         dst = mem.view(_p(op, "UCDIR_TC_P_DST"), (B, 2 * H, 2 * W, pitch), odt)
         dst[:, dpy::2, dpx::2, dstCoff:dstCoff + nout] = out

@@ -26,6 +26,7 @@ struct FhParams {
   int B, H, W;
   int nchunk, tiles_x, tiles_y, n_items;
   int dstC, dstCoff, ncol_valid;
+  int crop;                    // DST holds only the interior: [B][H - 2*crop][W - 2*crop][dstC] (the stitched part of a tile)
   double gn_count; float eps;
 };
 
@@ -218,8 +219,8 @@ __global__ void __launch_bounds__(FH_THREADS, 1) final_halo_kernel(const __grid_
 #pragma unroll
       for (int mt = 0; mt < FH_MT; ++mt) {
         const int x = tx * FH_SW + mt * 8 + xx;
-        if (y < p.H && x < p.W) {
-          float* d = p.dst + (((size_t)img * p.H + y) * p.W + x) * p.dstC + p.dstCoff;
+        if (y >= p.crop && y < p.H - p.crop && x >= p.crop && x < p.W - p.crop) {
+          float* d = p.dst + (((size_t)img * (p.H - 2 * p.crop) + (y - p.crop)) * (p.W - 2 * p.crop) + (x - p.crop)) * p.dstC + p.dstCoff;
 #pragma unroll
           for (int n = 0; n < 4; ++n)
             if (n < p.ncol_valid) d[n] = __uint_as_float(rv[mt][n]) + bias[n];
@@ -267,6 +268,8 @@ int launch_tc_final_halo(const ucdir_op_t& op, cudaStream_t st) {
   p.B = op.i[UCDIR_TC_I_B]; p.H = op.i[UCDIR_TC_I_H]; p.W = op.i[UCDIR_TC_I_W];
   p.nchunk = C0 / 64;
   p.dstC = op.i[UCDIR_TC_I_DST_C]; p.dstCoff = op.i[UCDIR_TC_I_DST_COFF];
+  p.crop = op.i[UCDIR_TC_I_DST_CROP];
+  if (p.crop < 0 || 2 * p.crop >= op.i[UCDIR_TC_I_H] || 2 * p.crop >= op.i[UCDIR_TC_I_W]) { set_error("tc_final_halo: bad DST_CROP"); return -1; }
   p.ncol_valid = op.i[UCDIR_TC_I_NCOL_VALID] ? op.i[UCDIR_TC_I_NCOL_VALID] : FH_NT;
   p.eps = op.f[UCDIR_TC_F_EPS];
   p.gn_count = (double)C0 * p.H * p.W;

@@ -757,7 +757,8 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   p.Ntot = op.i[UCDIR_TC_I_NTOT]; p.ncol_valid = op.i[UCDIR_TC_I_NCOL_VALID] ? op.i[UCDIR_TC_I_NCOL_VALID] : p.Ntot;
   p.nty = op.i[UCDIR_TC_I_NTY]; p.ntx = op.i[UCDIR_TC_I_NTX]; p.oy0 = op.i[UCDIR_TC_I_OY0]; p.ox0 = op.i[UCDIR_TC_I_OX0];
   p.stride = op.i[UCDIR_TC_I_STRIDE]; p.groups = op.i[UCDIR_TC_I_GROUPS];
-  const int KC = op.i[UCDIR_TC_I_KC], NT = op.i[UCDIR_TC_I_NT];
+  const int KC = op.i[UCDIR_TC_I_KC];
+  int NT = op.i[UCDIR_TC_I_NT];
   const int KB = op.i[UCDIR_TC_I_KB] ? op.i[UCDIR_TC_I_KB] : KC, NSPLIT = op.i[UCDIR_TC_I_NSPLIT] ? op.i[UCDIR_TC_I_NSPLIT] : 1;
   p.gn = op.i[UCDIR_TC_I_GN]; p.ncls = op.i[UCDIR_TC_I_NCLS]; p.act = op.i[UCDIR_TC_I_ACT]; p.mode = op.i[UCDIR_TC_I_MODE];
   p.dst_f32 = op.i[UCDIR_TC_I_DST_F32];
@@ -836,6 +837,7 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
     set_error("tc_conv: SRC_GN_SWISH needs a 3x3 stride-1 conv of <= 128 channels (multiple of 64) with GN = 0, NT = NTOT = 16, DST_F32 = 1, SRC_GAMMA / SRC_BETA / STATS0");
     return -2;
   }
+  if (op.i[UCDIR_TC_I_DST_CROP] && !tc_final_halo_applies(op)) { set_error("tc_conv: DST_CROP needs the fused final conv (SRC_GN_SWISH, ucdir_fhalo.cu)"); return -2; }
   if (op.i[UCDIR_TC_I_RES_FUSED] && !tc_dense_halo_applies(op)) {
     set_error("tc_conv: RES_FUSED needs the halo schedule of a GroupNorm-folded 3x3 stride-1 conv with 64 / 128 output channels, KC = 64, W2 / TB2 / DST_RES");
     return -2;
@@ -844,6 +846,26 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   if (tc_final_halo_applies(op)) return launch_tc_final_halo(op, st);  // GroupNorm + Swish + conv of final_conv in one kernel (ucdir_fhalo.cu)
   if (tc_mix_halo_applies(op)) return launch_tc_mix_halo(op, st);      // halo / weight-stationary form of the mix convs (ucdir_mix.cu)
   if (tc_dense_halo_applies(op)) return launch_tc_dense_halo(op, st);  // halo / super-tile form of the Cout = 64 / 128 3x3 convs (ucdir_dhalo.cu)
+  // Small grids (the <= 16x16-pixel levels of a 16-tile rank share: 8..32 pixel tiles x 2 column tiles for 148 SMs): a narrower
+  // column tile multiplies the work items.  An M = 128, K = 16 MMA costs ~90 / 125 / 186 cycles at N = 64 / 128 / 256 (operand
+  // fetch bound), so narrow tiles only pay when the grid is not full; pick the width with the lowest
+  // ceil(items / CTAs) x cycles-per-item estimate among the instantiated ones.
+  const int n_sm = sm_count();
+  if (p.groups == 1 && p.mode != 1 && NSPLIT == 1 && KC == 64 && !op.i[UCDIR_TC_I_SPS3] && getenv("UCDIR_TC_NT_AUTO") == nullptr) {
+    const bool plain_t = p.dst2 != nullptr;
+    int best_nt = NT; double best = 1e30;
+    const int cand[3] = {256, 128, 64};
+    const double cyc[3] = {186.0, 125.0, 90.0};
+    for (int c = 0; c < 3; ++c) {
+      const int nt = cand[c];
+      if (nt > NT || p.Ntot % nt || (plain_t && (nt < 128 || p.t_col0 % nt))) continue;
+      const long long it = (long long)mt * (p.Ntot / nt);
+      const long long per_cta = (it + n_sm - 1) / n_sm;
+      const double est = (double)per_cta * cyc[c] + 400.0 * (double)per_cta;      // + per-item epilogue / pipeline refill
+      if (est < best * 0.97) { best = est; best_nt = nt; }
+    }
+    NT = best_nt;
+  }
   // ROW3: row tiles (128 px x 1 row) of a dense 3x3 stride-1 conv load one 130-pixel activation row per filter row and
   // issue the three horizontal taps from shifted descriptors of that slab (3x less activation traffic from L2)
   const bool row3 = op.i[UCDIR_TC_I_ROW3] == 1 && p.nty == 3 && p.ntx == 3 && p.stride == 1 && p.groups == 1 && KC == 64 && KB == 64 &&
@@ -861,7 +883,6 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   if (p.w_batched) rc = make_w_map(&bm, w, split ? p.b_lo + p.n0 * KB : C0, op.i[UCDIR_TC_I_W_ROWS] ? op.i[UCDIR_TC_I_W_ROWS] : p.Ntot, KB, NT, w_rowstride, p.B, w_batchstride);
   else rc = make_w_map(&bm, w, Ktot, p.Ntot, KB, NT, Ktot, 0, 0);
   if (rc) return rc;
-  const int n_sm = sm_count();
   const long long items = (long long)mt * (p.Ntot / NT);
   dim3 grid((unsigned)(items < n_sm ? items : n_sm), 1, 1);      // persistent: one CTA per SM
   p.ctab = (!split && p.mode == 1 && p.gn && p.ncls == 9 && p.bn == 1 && p.Ntot <= 1024 && KC == 32 && KB == 16 && op.i[UCDIR_TC_I_NO_CTAB] == 0 &&
@@ -883,7 +904,7 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
 #define INSTS(ka, kb, nt, ns, ep, sp) if (split && KC == ka && KB == kb && NT == nt && NSPLIT == ns && epi == ep && sps == sp) { rc = launch_inst<ka, kb, nt, ns, ep, 0, sp, true>(a0, a1, bm, p, grid, st); if (rc) return rc; ++g_launches; return 0; }
   INSTS(64, 64, 64, 1, EPI_PLAIN, 1) INSTS(64, 64, 128, 1, EPI_PLAIN, 1) INSTS(64, 64, 256, 1, EPI_PLAIN, 1) INSTS(16, 16, 64, 1, EPI_PLAIN, 1)
   INSTS(64, 64, 64, 1, EPI_PLAIN, 4) INSTS(64, 64, 128, 1, EPI_PLAIN, 4)
-  INSTS(64, 64, 256, 1, EPI_PLAIN_T, 1)
+  INSTS(64, 64, 256, 1, EPI_PLAIN_T, 1) INSTS(64, 64, 128, 1, EPI_PLAIN_T, 1)
   INSTS(64, 64, 16, 1, EPI_F32, 1) INSTS(64, 64, 64, 1, EPI_F32, 1) INSTS(64, 64, 128, 1, EPI_F32, 1) INSTS(64, 64, 256, 1, EPI_F32, 1)
   INSTS(32, 16, 256, 4, EPI_MIX, 1) INSTS(32, 16, 256, 2, EPI_MIX, 1) INSTS(32, 32, 256, 1, EPI_MIX, 1) INSTS(64, 64, 256, 1, EPI_MIX, 1)
 #undef INSTS

@@ -455,7 +455,7 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
            w_batched: int = 0, w_rowstride: int = 0, w_batchstride: int = 0, alpha: float = 0.0, dst2: int = 0, t_col0: int = 0,
            t_ld: int = 0, w_rows: int = 0, row3: Optional[int] = None, halo: Optional[int] = None, src_gn_swish: int = 0,
            src_gamma: int = 0, src_beta: int = 0, w2: int = 0, tb2: int = 0, dst_res: Optional[Act] = None,
-           split: int = 0, src_lo_off: int = 0, w_lo_off: int = 0):
+           split: int = 0, src_lo_off: int = 0, w_lo_off: int = 0, dst_crop: int = 0):
     H, W = (dst.H // 2, dst.W // 2) if dst_up else (dst.H, dst.W)
     p = {"UCDIR_TC_P_SRC0": src0.ptr, "UCDIR_TC_P_W": w, "UCDIR_TC_P_TB": tb, "UCDIR_TC_P_DST": dst.ptr}
     if src1 is not None: p["UCDIR_TC_P_SRC1"] = src1.ptr
@@ -483,6 +483,7 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
         i["UCDIR_TC_I_SPLIT"], i["UCDIR_TC_I_HALO"] = 1, 0
         i["UCDIR_TC_I_SRC_LO_OFF"], i["UCDIR_TC_I_W_LO_OFF"] = src_lo_off, w_lo_off
     if dst2: p["UCDIR_TC_P_DST2"] = dst2
+    if dst_crop: i["UCDIR_TC_I_DST_CROP"] = dst_crop
     if src_gn_swish:
         p["UCDIR_TC_P_SRC_GAMMA"], p["UCDIR_TC_P_SRC_BETA"], p["UCDIR_TC_P_STATS0"] = src_gamma, src_beta, src0.stats
         i["UCDIR_TC_I_SRC_GN_SWISH"] = 1
@@ -553,7 +554,7 @@ meets the reference's fp32 tolerance (rtol 1e-3 / atol 1e-4) at one third of the
 
 
 def _max_chunk_pixels():
-    return int(os.environ.get("UCDIR_CHUNK_PIXELS", 2 * 1024 * 1024 + 256 * 1024))
+    return int(os.environ.get("UCDIR_CHUNK_PIXELS", 4 * 1024 * 1024 + 512 * 1024))
 
 
 class UNetEngine:
@@ -837,6 +838,24 @@ class UNetEngine:
         self.last_stat_slots = bld.next_slot
         return ol
 
+    def attw_rows(self, levels: torch.Tensor) -> torch.Tensor:
+        """The per-block timestep weights attw[L][n_blocks][8] (PositionalEncoding + noise_level_mlp + every block's
+        noise_func, model/ucdir.py:24-29,212-214,106,125) for L noise levels in ONE launch.  The level of step t is a
+        function of the schedule only (model/diffusion.py:162-163), so the samplers build this table once per schedule and a
+        step copies its row next to the other per-step scalars: the denoising step itself has no timestep-embedding launch."""
+        self.ensure_weights()
+        dev = self.device()
+        levels = levels.detach().to(device=dev, dtype=F32).contiguous()
+        L = int(levels.numel())
+        out = torch.empty((L, len(self.blocks), 8), dtype=F32, device=dev)
+        ol = OpList()
+        self.time_embed_op(ol, out, L, levels.data_ptr(), 0.0)
+        with _device_guard(dev):
+            _run_ops(ol.array(), len(ol), _stream(dev))
+        if dev.type == "cuda":
+            torch.cuda.current_stream(dev).synchronize()        # `levels` may be a temporary
+        return out
+
     # ---- bf16 / tcgen05 graph --------------------------------------------------------------
     def _ensure_weights_bf16(self, split: bool = False):
         """Packed bf16 operands + fp32 epilogue tables for every TC op (once per load).  split: fp32_tc operand pairs."""
@@ -886,7 +905,8 @@ class UNetEngine:
         ws.put("zeros", torch.zeros(65536, dtype=F32, device=ws.device))    # bias table of the attention GEMMs
 
     def build_forward_ops_bf16(self, pool: Pool, BT: int, TH: int, TW: int, x_in: torch.Tensor, gmaps: List[torch.Tensor],
-                               attw: torch.Tensor, attw_stride: int, eps_ptr: int, stats: torch.Tensor, split: bool = False) -> OpList:
+                               attw: torch.Tensor, attw_stride: int, eps_ptr: int, stats: torch.Tensor, split: bool = False,
+                               eps_crop: int = 0) -> OpList:
         """Same graph as build_forward_ops on the tcgen05 path: bf16 NHWC activations, x_in[BT,TH,TW,16] bf16.
         split (precision fp32_tc): every activation is a (hi, lo) bf16 plane pair and every op a three-pass split-operand
         MMA on the streamed kernel (include/ucdir_b200.h, UCDIR_TC_I_SPLIT); x_in[BT,TH,TW,2*16]."""
@@ -1073,9 +1093,12 @@ class UNetEngine:
         # shared memory and runs the 16-column (3 valid) conv to fp32 eps (csrc/ucdir_fhalo.cu).  Otherwise: one elementwise
         # pass, then the streamed conv.
         eps_dst = Act(_PtrBuf(eps_ptr), 4, TH, TW, 0, keep=True)      # type: ignore[arg-type]
+        if eps_crop and not self.fused_final_crop(split, x.C):
+            raise RuntimeError("eps_crop needs the fused final conv")
         if _TC_HALO and not split and x.C % 64 == 0 and x.C <= 128:
             _tc_op(ol, split=sp, src0=x, w=ws.ptr("final.tcw"), tb=ws.ptr("final.tb"), dst=eps_dst, ntot=16, B=BT, nt=16, dst_f32=1,
-                   ncol_valid=m.cfg["out_channel"], src_gn_swish=1, src_gamma=ws.ptr("final.norm.w"), src_beta=ws.ptr("final.norm.b"))
+                   ncol_valid=m.cfg["out_channel"], src_gn_swish=1, src_gamma=ws.ptr("final.norm.w"), src_beta=ws.ptr("final.norm.b"),
+                   dst_crop=eps_crop)
             bld.release(x)
         else:
             xn = bld.new(x.C, x.H, x.W, with_stats=False)
@@ -1090,6 +1113,12 @@ class UNetEngine:
             bld.release(xn)
         self.last_stat_slots = bld.next_slot
         return ol
+
+    def fused_final_crop(self, split: bool, c_final: Optional[int] = None) -> bool:
+        """True when final_conv runs as the fused halo kernel, which can write the tile interiors straight into the compact eps
+        buffer (UCDIR_TC_I_DST_CROP) -- no separate crop pass."""
+        c = self.m.prec if c_final is None else c_final
+        return bool(_TC_HALO and not split and c % 64 == 0 and c <= 128)
 
     # ---- sessions -----------------------------------------------------------------------
     def session(self, cond: torch.Tensor, guide: torch.Tensor, geometry: Optional[Geometry] = None) -> "Session":
@@ -1238,21 +1267,22 @@ class Session:
                  "UCDIR_GATHER_I_CA": ca, "UCDIR_GATHER_I_CB": 6 - ca, "UCDIR_GATHER_I_CD": 16 if self.bf16 else 8,
                  "UCDIR_GATHER_I_OUT_BF16": (2 if self.split else 1) if self.bf16 else 0}))
             ih, iw = g.TH - 2 * self.crop, g.TW - 2 * self.crop
-            if self.crop:
+            fuse_crop = bool(self.crop) and self.bf16 and eng.fused_final_crop(self.split)
+            if self.crop and not fuse_crop:
                 if not hasattr(self, "eps_full"):
                     self.eps_full = torch.empty((maxbt, g.TH, g.TW, 4), dtype=F32, device=dev)
                 eps_ptr = self.eps_full.data_ptr()
             else:
-                eps_ptr = self.eps.data_ptr() + a * g.TH * g.TW * 4 * 4
+                eps_ptr = self.eps.data_ptr() + a * ih * iw * 4 * 4
             stats_view = self.stats.view(-1)[:MAX_STAT_SLOTS * BT * 2].view(MAX_STAT_SLOTS, BT, 2)   # same storage
             if self.bf16:
                 sub = eng.build_forward_ops_bf16(self.pool, BT, g.TH, g.TW, self.x_tiles, gmaps, self.attw, 0, eps_ptr, stats_view,
-                                                 split=self.split)
+                                                 split=self.split, eps_crop=self.crop if fuse_crop else 0)
             else:
                 sub = eng.build_forward_ops(self.pool, BT, g.TH, g.TW, self.x_tiles, gmaps, self.attw, 0, eps_ptr, stats_view)
             self._chunk_attw_fix(sub, a)
             self.step_ops.extend(sub)
-            if self.crop:
+            if self.crop and not fuse_crop:
                 self.step_ops.add("UCDIR_OP_CROP_TILES",
                                   {"UCDIR_CROP_P_SRC": self.eps_full.data_ptr(), "UCDIR_CROP_P_DST": self.eps.data_ptr() + a * ih * iw * 16},
                                   {"UCDIR_CROP_I_BT": BT, "UCDIR_CROP_I_TH": g.TH, "UCDIR_CROP_I_TW": g.TW, "UCDIR_CROP_I_IH": ih,
@@ -1388,7 +1418,10 @@ class Session:
         _run_ops(self.tail_ops.array(), 1, self.stream())
 
     # ---- resident stepping: state, noise and per-step scalars live on the device; one graph launch per step ------
-    PARAM_FLOATS = 9          # {level, A, B, C1, C2, SIGMA, clip, use_noise, C3}
+    PARAM_FLOATS = 9          # {level, A, B, C1, C2, SIGMA, clip, use_noise, C3} followed by attw[n_blocks][8] of that level
+
+    def param_floats(self) -> int:
+        return self.PARAM_FLOATS + self.eng.n_blocks() * 8
 
     def ensure_resident(self):
         if getattr(self, "_resident", False):
@@ -1399,17 +1432,23 @@ class Session:
         self._set_attw_mode(False)
         self.xbuf = [torch.zeros((g.B, 3, g.IH, g.IW), dtype=F32, device=dev) for _ in range(2)]
         self.noise = torch.zeros((g.B, 3, g.IH, g.IW), dtype=F32, device=dev)
-        self.params = torch.zeros(self.PARAM_FLOATS, dtype=F32, device=dev)
+        self.params = torch.zeros(self.param_floats(), dtype=F32, device=dev)
+        attw_base = self.params.data_ptr() + self.PARAM_FLOATS * 4
+        mix_ids = {id(o): (pk, ik, int(o.p[K_[pk]]) - (self.attw.data_ptr() + a * self._attw_stride * 4))
+                   for o, a, base, pk, ik in self._mix_ops}       # id(op) -> (pointer key, stride key, byte offset of its block row)
         self.cur = 0
         self.res_ops: List[Tuple[OpList, OpList]] = []
         clone = lambda o: _lib.Op.from_buffer_copy(o)
         for par in (0, 1):
             body, tail = OpList(), OpList()
             for idx, o in enumerate(self.step_ops.ops):
-                c = clone(o)
                 if idx == self.idx_temb:
-                    c.p[K_["UCDIR_TEMB_P_LEVELS"]] = self.params.data_ptr()
-                    c.i[K_["UCDIR_TEMB_I_L"]] = 1
+                    continue                     # attw of the step's level arrives with the parameter row (engine.attw_rows)
+                c = clone(o)
+                if id(o) in mix_ids:
+                    pk, ik, off = mix_ids[id(o)]
+                    c.p[K_[pk]] = attw_base + off
+                    c.i[K_[ik]] = 0
                 if idx in self.idx_gather:
                     c.p[K_["UCDIR_GATHER_P_SRC_B"]] = self.xbuf[par].data_ptr()
                 body.ops.append(c)
@@ -1453,8 +1492,9 @@ class Session:
 
     @_on_device
     def step_resident(self, params_row: torch.Tensor):
-        """One p_sample on the resident state.  params_row: device float[8] for this step (D2D copied into the
-        slot the ops read); the caller has already filled self.noise when the step uses noise."""
+        """One p_sample on the resident state.  params_row: device float[param_floats()] for this step -- the nine scalars and
+        the attw rows of the step's level -- D2D copied into the slot the ops read; the caller has already filled self.noise
+        when the step uses noise."""
         self.params.copy_(params_row)
         body, tail = self.res_ops[self.cur]
         st = self.stream()

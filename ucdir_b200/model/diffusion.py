@@ -151,15 +151,25 @@ class GaussianDiffusion(nn.Module):
         return (float(s["sqrt_recip_alphas_cumprod"][t]), float(s["sqrt_recipm1_alphas_cumprod"][t]),
                 float(s["posterior_mean_coef1"][t]), float(s["posterior_mean_coef2"][t]), float(sigma))
 
+    def _with_attw(self, rows, device):
+        """[K, 9] per-step scalar rows -> device table [K, 9 + n_blocks * 8]: each row followed by the timestep weights attw of
+        its noise level (model/ucdir.py:106,125,212-214), one kernel launch for the whole table."""
+        tab = torch.tensor(rows, dtype=torch.float32, device=device)
+        attw = self.denoise_fn.engine().attw_rows(tab[:, 0])
+        return torch.cat([tab, attw.reshape(tab.shape[0], -1)], dim=1).contiguous()
+
     def _params_table(self, device, clip=True):
-        """Device table [T, 9] of the per-step kernel scalars {level, A, B, C1, C2, sigma, clip, use_noise, C3}
-        (model/diffusion.py:150-163,183), built once per schedule; a step D2D-copies its row (no per-step H2D)."""
+        """Device table [T, 9 + n_blocks * 8] of the per-step kernel scalars {level, A, B, C1, C2, sigma, clip, use_noise, C3}
+        (model/diffusion.py:150-163,183) and the timestep weights of each level, built once per schedule (and weight version);
+        a step D2D-copies its row (no per-step H2D, no per-step timestep-embedding launch)."""
         self._host_schedule()
-        key = (str(device), self.num_timesteps, bool(clip), id(self._sched_host))
+        eng = self.denoise_fn.engine()
+        eng.ensure_weights()
+        key = (str(device), self.num_timesteps, bool(clip), id(self._sched_host), eng._packed_version, id(eng.ws))
         if getattr(self, "_ptable_key", None) != key:
             rows = [[self.noise_level(t), *self._step_scalars(t), 1.0 if clip else 0.0, 1.0 if t > 0 else 0.0, 0.0]
                     for t in range(self.num_timesteps)]
-            self._ptable = torch.tensor(rows, dtype=torch.float32, device=device)
+            self._ptable = self._with_attw(rows, device)
             self._ptable_key = key
         return self._ptable
 
@@ -320,7 +330,7 @@ class GaussianDiffusion(nn.Module):
             c = (1 - alpha_next - sigma ** 2).sqrt()
             rows.append([self.noise_level(time), float(a_tab[time]), float(b_tab[time]), float(alpha_next.sqrt()), 0.0,
                          float(sigma), 1.0, 1.0, float(c)])
-        table = torch.tensor(rows, dtype=torch.float32, device=device)
+        table = self._with_attw(rows, device)
         if not continous:
             return self._run_steps(x, guide, table, [tn >= 0 for _, tn in pairs], [False] * len(pairs))[1]
         # continous: the reference stacks [initial noise, state after every step] along dim 1 (model/diffusion.py:257,289,293)
