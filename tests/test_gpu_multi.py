@@ -20,7 +20,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-for precision in ("fp32", "bf16"):
+for precision in ("fp32_tc", "bf16"):
     os.environ["UCDIR_PRECISION"] = precision
     torch.manual_seed(1234)
     net = define_G({"model": ucdir_b200.SID_MODEL_OPT}).to(dev)
@@ -33,23 +33,39 @@ for precision in ("fp32", "bf16"):
     x_t = torch.randn(1, 3, 512, 640, generator=g).to(dev)
     z = torch.randn(1, 3, 512, 640, generator=g).to(dev)
     net._noise_source = lambda shape: z
-    os.environ["UCDIR_SHARD"] = "tiles"
+    assert unet.engine().shard_mode == "none"      # opt-in: the reference launcher runs a different image on every rank
+    unet.engine().set_shard_mode("tiles")
     a = net.p_sample(x_t, 20, condition_x=x_in, kwargs={"guide": guide})
     sess = next(iter(unet.engine()._sessions.values()))
     assert sess.world == world and sess.group is not None
-    unet.engine()._sessions.clear()
-    os.environ["UCDIR_SHARD"] = "none"
+    unet.engine().set_shard_mode("none")
     b = net.p_sample(x_t, 20, condition_x=x_in, kwargs={"guide": guide})
     sess = next(iter(unet.engine()._sessions.values()))
     assert sess.world == 1
     err = (a - b).abs().max().item()
     # per-tile arithmetic is rank independent; only the fp64 atomic order of the GroupNorm sums can differ
-    tol = 1e-5 if precision == "fp32" else 2e-2
+    tol = 1e-5 if precision == "fp32_tc" else 2e-2
     print("rank", rank, precision, "sharded vs unsharded max abs diff", err)
     assert err <= tol, err
     gathered = [torch.empty_like(a) for _ in range(world)]
     dist.all_gather(gathered, a)
     assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree after the all-gather"
+    # batch sharding (SURVEY 8e(2)): every rank runs the whole trajectory of its own samples, ONE gather at the end
+    unet.tile_skip, unet.tile_padding, unet.tile_trigger = 1024, 64, 1024 * 1024
+    nb = world + 1                                   # uneven split: the last rank gets fewer (or no) samples
+    xb = (torch.rand(nb, 3, 72, 88, generator=g) * 2 - 1).to(dev)
+    gb = (torch.rand(nb, 3, 72, 88, generator=g) * 2 - 1).to(dev)
+    net.set_new_noise_schedule(dict(schedule="linear", n_timestep=3, linear_start=1e-6, linear_end=0.4), dev)
+    outs = {}
+    for mode in ("batch", "none"):
+        unet.engine().set_shard_mode(mode)
+        ng = torch.Generator().manual_seed(5)
+        net._noise_source = lambda shape: torch.randn(shape, generator=ng)
+        outs[mode] = net.p_sample_loop(xb, True, kwargs={"guide": gb})
+    unet.engine().set_shard_mode("none")
+    errb = (outs["batch"] - outs["none"]).abs().max().item()
+    print("rank", rank, precision, "batch-sharded vs unsharded max abs diff", errb)
+    assert outs["batch"].shape == outs["none"].shape and errb <= tol, errb
 dist.barrier(); dist.destroy_process_group()
 '''
 
