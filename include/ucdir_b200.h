@@ -323,6 +323,30 @@ long long ucdir_launch_count(void);
 /* Device capability probe: returns 0 iff the current device is sm_100 (B200). */
 int ucdir_device_ok(void);
 
+/* ---- weight packing (host side, no device): OIHW fp32 checkpoint tensors -> kernel layouts ----------------------------------
+ * For hosts that are not ucdir_b200/engine.py: everything UCDIR_OP_TC_CONV / UCDIR_OP_CONV_F32 expects in P_W / P_TB / P_TG can be
+ * produced from a state_dict with these calls (done once after load_state_dict).  All pointers are HOST memory; outputs
+ * are sized by the *_sizes / *_size queries (element counts); bf16 outputs are raw uint16.  Return >= 0 on success, < 0 on error.
+ *   dense:   Conv2d weight [COUT][CIN][KS][KS] (KS 1 or 3) -> W bf16 [round_up(COUT, NT)][KS*KS*CIN (x3 when SPLIT)], TB fp32
+ *            [NCLS][NTOT], TG fp32 [NCLS][NTOT] when GAMMA/BETA (the GroupNorm(1,C) in front of the conv) are given: NCLS = 9 border
+ *            classes for KS = 3, 1 for KS = 1; without GAMMA: NCLS = 1, TB = bias, TG untouched.  C0 = channels of the first source
+ *            of a concatenated input (SPLIT layout only; 0 = CIN).  Returns NCLS.
+ *   grouped: spdyconv weight [COUT][CG][3][3] with GROUPS groups (model/ucdir.py:116), folded norm2; KC = MMA K chunk (engine:
+ *            tc_mix_tiling(C)[1]); TB / TG fp32 [9][COUT].
+ *   up_phase: Upsample conv [COUT][CIN][3][3] (model/ucdir.py:53-60) -> the 2x2-tap weights of output parity (PY, PX).
+ *   conv_f32: the SIMT path's [GROUPS][KS*KS*CG][ld] layout (ld = round_up(COUT/GROUPS, 4)), CG zero padded to PAD_CIN_TO. */
+int ucdir_pack_tc_dense_sizes(int cout, int cin, int ks, int nt, int split, int has_gn, int* w_elems, int* n_cls, int* n_tot);
+int ucdir_pack_tc_dense(const float* w, const float* bias, const float* gamma, const float* beta, int cout, int cin, int ks, int nt,
+                        int split, int c0, uint16_t* w_out, float* tb_out, float* tg_out);
+int ucdir_pack_tc_grouped_sizes(int cout, int cg, int groups, int kc, int split, int* w_elems);
+int ucdir_pack_tc_grouped(const float* w, const float* bias, const float* gamma, const float* beta, int cout, int cg, int groups, int kc,
+                          int split, uint16_t* w_out, float* tb_out, float* tg_out);
+int ucdir_pack_tc_up_phase_sizes(int cout, int cin, int nt, int split, int* w_elems, int* n_tot);
+int ucdir_pack_tc_up_phase(const float* w, const float* bias, int cout, int cin, int py, int px, int nt, int split, uint16_t* w_out,
+                           float* tb_out);
+int ucdir_pack_conv_f32_size(int cout, int cg, int ks, int groups, int pad_cin_to);
+int ucdir_pack_conv_f32(const float* w, int cout, int cg, int ks, int groups, int pad_cin_to, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,3 +68,76 @@ def test_tc_schedule_routing():
     assert dense(64, 64, 1) == 2 and dense(192, 64, 1) == 2 and dense(384, 128, 1) == 2
     assert dense(64, 64, 0) == 0 and dense(256, 256, 1) == 0 and dense(64, 64, 1, ks=1) == 0
     assert dense(64, 64, 1, gn=0) == 2 and dense(64, 64, 1, stride=2) == 0
+
+
+def test_c_abi_weight_packers_match_the_engine(tmp_path):
+    """ucdir_pack_* (host-side C++, csrc/ucdir_pack.cu) against the torch packers the engine uses (engine.pack_tc_* / pack_conv_f32):
+    bf16 operands bit for bit, fp32 tables up to summation order -- so a non-Python host gets the same kernel inputs."""
+    import numpy as np
+    import torch
+    from ucdir_b200 import engine as E
+    lib = _lib.load(require_device=False)
+    F, U16, I = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_int)
+    fp = lambda a: a.ctypes.data_as(F) if a is not None else None
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=g)
+    bits = lambda t: t.contiguous().view(torch.int16).numpy().view(np.uint16)
+
+    def np32(t):
+        return None if t is None else np.ascontiguousarray(t.numpy(), dtype=np.float32)
+
+    # dense 3x3 / 1x1, with and without folded GroupNorm, plain and split (concatenated input: c0 = 64 of 96 channels)
+    for (co, ci, ks, nt, gn, split, c0) in [(64, 96, 3, 64, True, False, 0), (64, 96, 3, 64, True, True, 64), (48, 32, 1, 64, False, False, 0),
+                                            (3, 64, 3, 16, False, True, 0), (128, 64, 1, 128, True, True, 0)]:
+        w, b = r(co, ci, ks, ks) * 0.2, r(co)
+        gam, bet = (r(ci) * 0.5 + 1, r(ci) * 0.1) if gn else (None, None)
+        pw, ptb, ptg = E.pack_tc_dense(w, b, nt, gam, bet, split=split, c0=(c0 or None))
+        we, ncls, ntot = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert lib.ucdir_pack_tc_dense_sizes(co, ci, ks, nt, int(split), int(gn), ctypes.byref(we), ctypes.byref(ncls), ctypes.byref(ntot)) == 0
+        assert we.value == pw.numel() and ntot.value == pw.shape[0] and ncls.value == ptb.shape[0]
+        ow = np.zeros(we.value, np.uint16); otb = np.zeros((ncls.value, ntot.value), np.float32); otg = np.zeros_like(otb)
+        wn, bn, gn_, ben = np32(w), np32(b), np32(gam), np32(bet)
+        rc = lib.ucdir_pack_tc_dense(fp(wn), fp(bn), fp(gn_), fp(ben), co, ci, ks, nt, int(split), c0, ow.ctypes.data_as(U16), fp(otb), fp(otg) if gn else None)
+        assert rc == ncls.value, _lib.last_error()
+        assert np.array_equal(ow, bits(pw).reshape(-1)), (co, ci, ks, split)
+        np.testing.assert_allclose(otb, ptb.numpy(), rtol=1e-5, atol=1e-5)
+        if gn:
+            np.testing.assert_allclose(otg, ptg.numpy(), rtol=1e-5, atol=1e-5)
+    # grouped spdyconv for C = 64 (Cg = 8 < KC: zero-filled chunks) and C = 512, plain and split
+    for (C, split) in [(64, False), (64, True), (512, False)]:
+        cg, co = C // 8, 8 * C
+        w, b, gam, bet = r(co, cg, 3, 3) * 0.2, r(co), r(C) * 0.5 + 1, r(C) * 0.1
+        kc = E.tc_mix_tiling(C)[1]
+        pw, ptb, ptg = E.pack_tc_grouped(w, b, 8, kc, gam, bet, split=split)
+        we = ctypes.c_int()
+        assert lib.ucdir_pack_tc_grouped_sizes(co, cg, 8, kc, int(split), ctypes.byref(we)) == 0 and we.value == pw.numel()
+        ow = np.zeros(we.value, np.uint16); otb = np.zeros((9, co), np.float32); otg = np.zeros_like(otb)
+        wn, bn, gn_, ben = np32(w), np32(b), np32(gam), np32(bet)
+        assert lib.ucdir_pack_tc_grouped(fp(wn), fp(bn), fp(gn_), fp(ben), co, cg, 8, kc, int(split), ow.ctypes.data_as(U16), fp(otb), fp(otg)) == 9
+        assert np.array_equal(ow, bits(pw).reshape(-1)), (C, split)
+        np.testing.assert_allclose(otb, ptb.numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(otg, ptg.numpy(), rtol=1e-5, atol=1e-5)
+    # upsample phases
+    w, b = r(64, 64, 3, 3) * 0.2, r(64)
+    for split in (False, True):
+        for py in range(2):
+            for px in range(2):
+                pw, ptb = E.pack_tc_up_phase(w, b, py, px, 64, split=split)
+                we, ntot = ctypes.c_int(), ctypes.c_int()
+                assert lib.ucdir_pack_tc_up_phase_sizes(64, 64, 64, int(split), ctypes.byref(we), ctypes.byref(ntot)) == 0 and we.value == pw.numel()
+                ow = np.zeros(we.value, np.uint16); otb = np.zeros(ntot.value, np.float32)
+                wn, bn = np32(w), np32(b)
+                assert lib.ucdir_pack_tc_up_phase(fp(wn), fp(bn), 64, 64, py, px, 64, int(split), ow.ctypes.data_as(U16), fp(otb)) == 0
+                # the pre-summed weights are sums of up to four fp32 values: order-dependent in the last bit before the bf16 rounding
+                diff = np.abs(ow.view(np.int16).astype(np.int32) - bits(pw).reshape(-1).view(np.int16).astype(np.int32))
+                assert (diff <= (1 if not split else 2 ** 15)).all() and (diff != 0).mean() < (0.01 if not split else 0.2), (split, py, px)
+                np.testing.assert_allclose(otb, ptb.numpy().reshape(-1), rtol=0, atol=0)
+    # SIMT layout
+    w = r(24, 6, 3, 3)
+    want = E.pack_conv_f32(w, pad_cin_to=8)
+    n = lib.ucdir_pack_conv_f32_size(24, 6, 3, 1, 8)
+    assert n == want.numel()
+    out = np.zeros(n, np.float32)
+    wn = np32(w)
+    assert lib.ucdir_pack_conv_f32(fp(wn), 24, 6, 3, 1, 8, fp(out)) == 0
+    assert np.array_equal(out, want.numpy().reshape(-1))

@@ -112,3 +112,13 @@ def test_two_ranks_match_single_process(tmp_path):
     np.testing.assert_allclose(r0[0], single[0], rtol=0, atol=1e-6)
     # the shared-seed stream really produced noise (snapshots differ from the injected-noise run)
     assert not np.array_equal(r0[0][1:], r0[1][1:])
+
+
+def test_four_ranks_with_an_idle_rank_match_single_process(tmp_path):
+    """9 tiles / 3 samples over FOUR ranks: the last rank owns no tile and no sample (empty step body, gather-only participant)."""
+    single, single_b = _run(1, tmp_path, "w1")[0]
+    res = _run(4, tmp_path, "w4")
+    for r, b in res:
+        assert np.array_equal(r, res[0][0]) and np.array_equal(b, res[0][1])
+    np.testing.assert_allclose(res[0][0][0], single[0], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(res[0][1], single_b, rtol=0, atol=1e-6)

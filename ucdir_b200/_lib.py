@@ -38,7 +38,9 @@ class Op(ctypes.Structure):
 
 EXPORTS = ["ucdir_run_ops", "ucdir_check_ops", "ucdir_abi_version", "ucdir_op_sizeof", "ucdir_last_error",
            "ucdir_launch_count", "ucdir_device_ok", "ucdir_profile_begin", "ucdir_profile_end", "ucdir_graph_capture",
-           "ucdir_graph_launch", "ucdir_graph_destroy", "ucdir_tc_schedule"]
+           "ucdir_graph_launch", "ucdir_graph_destroy", "ucdir_tc_schedule",
+           "ucdir_pack_tc_dense_sizes", "ucdir_pack_tc_dense", "ucdir_pack_tc_grouped_sizes", "ucdir_pack_tc_grouped",
+           "ucdir_pack_tc_up_phase_sizes", "ucdir_pack_tc_up_phase", "ucdir_pack_conv_f32_size", "ucdir_pack_conv_f32"]
 
 _lib = None
 _device_ok = False

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libucdir_b200.so")
-SOURCES = ["c_abi.cu", "ucdir_f32.cu", "ucdir_misc.cu", "ucdir_tc.cu", "ucdir_mix.cu", "ucdir_dhalo.cu", "ucdir_fhalo.cu", "ucdir_attn.cu"]
+SOURCES = ["c_abi.cu", "ucdir_f32.cu", "ucdir_misc.cu", "ucdir_tc.cu", "ucdir_mix.cu", "ucdir_dhalo.cu", "ucdir_fhalo.cu", "ucdir_attn.cu", "ucdir_pack.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -1,7 +1,9 @@
 // C ABI of libucdir_b200.so: op dispatcher, error reporting, capability probe.  See include/ucdir_b200.h.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 
 namespace ucdir {
@@ -27,6 +29,40 @@ int sm_count() {
 void set_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
+
+// NVTX ranges (SURVEY 5 "tracing"): with UCDIR_NVTX=1 every op issued by ucdir_run_ops / captured by ucdir_graph_capture is
+// wrapped in a range named after its kind and shape, and graph replays in "ucdir step graph" -- visible in nsys / ncu --nvtx.
+static const bool g_nvtx = []() { const char* e = getenv("UCDIR_NVTX"); return e && e[0] == '1'; }();
+static const char* kind_name(int k) {
+  switch (k) {
+    case UCDIR_OP_CONV_F32: return "conv_f32"; case UCDIR_OP_SGEMM_F32: return "sgemm_f32"; case UCDIR_OP_SOFTMAX_F32: return "softmax";
+    case UCDIR_OP_GUIDANCE: return "guidance"; case UCDIR_OP_TIME_EMBED: return "time_embed"; case UCDIR_OP_GATHER_TILES: return "gather_tiles";
+    case UCDIR_OP_SCATTER: return "scatter+posterior"; case UCDIR_OP_MAXPOOL2: return "maxpool2"; case UCDIR_OP_MEMSET: return "memset";
+    case UCDIR_OP_TC_CONV: return "tc_conv"; case UCDIR_OP_TC_ATTN: return "tc_attn"; case UCDIR_OP_GN_APPLY_BF16: return "gn_apply";
+    case UCDIR_OP_CAST: return "cast"; case UCDIR_OP_CROP_TILES: return "crop_tiles"; case UCDIR_OP_GN_STATS_F32: return "gn_stats";
+    case UCDIR_OP_GN_APPLY_F32: return "gn_apply_f32"; case UCDIR_OP_LAYOUT: return "layout"; case UCDIR_OP_TO_IMAGE_U8: return "to_image_u8";
+    default: return "op";
+  }
+}
+struct NvtxOp {
+  bool on;
+  NvtxOp(const ucdir_op_t& op, int index) : on(g_nvtx) {
+    if (!on) return;
+    char name[160];
+    if (op.kind == UCDIR_OP_TC_CONV)
+      snprintf(name, sizeof(name), "#%d tc_conv %dx%dx%d C%d+%d->%d taps%d g%d mode%d%s", index, op.i[UCDIR_TC_I_B], op.i[UCDIR_TC_I_H], op.i[UCDIR_TC_I_W],
+               op.i[UCDIR_TC_I_C0], op.i[UCDIR_TC_I_C1], op.i[UCDIR_TC_I_NTOT], op.i[UCDIR_TC_I_NTY] * op.i[UCDIR_TC_I_NTX], op.i[UCDIR_TC_I_GROUPS],
+               op.i[UCDIR_TC_I_MODE], op.i[UCDIR_TC_I_SPLIT] ? " split" : "");
+    else if (op.kind == UCDIR_OP_CONV_F32)
+      snprintf(name, sizeof(name), "#%d conv_f32 %dx%dx%d C%d+%d->%d k%d g%d mode%d", index, op.i[UCDIR_CONV_I_B], op.i[UCDIR_CONV_I_H], op.i[UCDIR_CONV_I_W],
+               op.i[UCDIR_CONV_I_C0], op.i[UCDIR_CONV_I_C1], op.i[UCDIR_CONV_I_COUT], op.i[UCDIR_CONV_I_KSIZE], op.i[UCDIR_CONV_I_GROUPS], op.i[UCDIR_CONV_I_MODE]);
+    else if (op.kind == UCDIR_OP_TC_ATTN)
+      snprintf(name, sizeof(name), "#%d tc_attn B%d N%d C%d", index, op.i[UCDIR_ATTN_I_B], op.i[UCDIR_ATTN_I_N], op.i[UCDIR_ATTN_I_C]);
+    else snprintf(name, sizeof(name), "#%d %s", index, kind_name(op.kind));
+    nvtxRangePushA(name);
+  }
+  ~NvtxOp() { if (on) nvtxRangePop(); }
+};
 
 static int dispatch(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   switch (op.kind) {
@@ -66,6 +102,7 @@ int ucdir_run_ops(const ucdir_op_t* ops, int n_ops, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (ucdir::g_prof) ucdir::prof_mark(st, -1, 0);
   for (int k = 0; k < n_ops; ++k) {
+    ucdir::NvtxOp range(ops[k], k);
     int rc = ucdir::dispatch(ops[k], st, false);
     if (ucdir::g_prof && !rc) ucdir::prof_mark(st, k, ops[k].kind);
     if (rc) { char tmp[400]; snprintf(tmp, sizeof(tmp), "%s", ucdir::g_err); ucdir::set_error("op %d (kind %d): %s", k, ops[k].kind, tmp); return rc; }
@@ -96,6 +133,7 @@ int ucdir_graph_capture(const ucdir_op_t* ops, int n_ops, void** graph_out) {
     ucdir::set_error("graph_capture: begin: %s", cudaGetErrorString(cudaGetLastError())); cudaStreamDestroy(cs); return -3; }
   int rc = 0;
   for (int k = 0; k < n_ops && !rc; ++k) {
+    ucdir::NvtxOp range(ops[k], k);
     rc = ucdir::dispatch(ops[k], cs, false);
     if (rc) { char tmp[400]; snprintf(tmp, sizeof(tmp), "%s", ucdir::g_err); ucdir::set_error("graph_capture: op %d (kind %d): %s", k, ops[k].kind, tmp); }
   }
@@ -117,7 +155,9 @@ int ucdir_graph_capture(const ucdir_op_t* ops, int n_ops, void** graph_out) {
 int ucdir_graph_launch(void* graph, void* stream) {
   UcdirGraph* h = (UcdirGraph*)graph;
   if (!h) { ucdir::set_error("graph_launch: null graph"); return -1; }
+  if (ucdir::g_nvtx) nvtxRangePushA("ucdir step graph");
   cudaError_t e = cudaGraphLaunch(h->exec, (cudaStream_t)stream);
+  if (ucdir::g_nvtx) nvtxRangePop();
   if (e != cudaSuccess) { ucdir::set_error("graph_launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return -3; }
   ucdir::g_launches += h->kernels;
   return 0;

@@ -31,7 +31,11 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok;
 }
-// Bounded wait: a protocol bug traps (surfacing as a CUDA error) after ~2 s instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (surfacing as a CUDA error) after ~2 s instead of hanging the GPU.  Builds that run under
+// compute-sanitizer (kernels 10-100x slower) raise the limit: UCDIR_NVCC_EXTRA=-DUCDIR_MBAR_TIMEOUT_NS=... (scripts/run_sanitizer.sh).
+#ifndef UCDIR_MBAR_TIMEOUT_NS
+#define UCDIR_MBAR_TIMEOUT_NS 2000000000ull
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint64_t t0;
@@ -41,7 +45,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 1023u) == 0) {
       uint64_t t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (t - t0 > 2000000000ull) {
+      if (t - t0 > UCDIR_MBAR_TIMEOUT_NS) {
         printf("ucdir tc: mbarrier timeout (block %d thread %d, barrier @%u parity %u)\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
         __trap();
       }

@@ -56,6 +56,20 @@ class _NullGuard:
 _NULL_GUARD = _NullGuard()
 
 
+_NVTX = os.environ.get("UCDIR_NVTX", "0") == "1"
+"""UCDIR_NVTX=1: NVTX ranges around the host-visible phases (bind / guidance maps, a denoising step, the tile all-gather) here and
+around every op inside libucdir_b200.so (c_abi.cu) -- for nsys / `ncu --nvtx` captures.  Off by default (push/pop cost)."""
+
+
+class _Range:
+    def __init__(self, name): self.name = name
+    def __enter__(self):
+        if _NVTX: torch.cuda.nvtx.range_push(self.name)
+    def __exit__(self, *a):
+        if _NVTX: torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _on_device(fn):
     """Method decorator: run with self.dev as the current CUDA device (see _device_guard)."""
     import functools
@@ -1346,7 +1360,7 @@ class Session:
             return
         self.guide.copy_(guide)
         self._guide_ref, self._guide_ver = guide, guide._version
-        with _device_guard(self.dev):
+        with _device_guard(self.dev), _Range("ucdir bind: guidance maps"):
             if len(self.static_ops):
                 _run_ops(self.static_ops.array(), len(self.static_ops), self.stream())
         self._bound = True
@@ -1468,15 +1482,16 @@ class Session:
         """Run each parity once eagerly (one-time function attributes, lazy module loading), then capture."""
         graphs = []
         for body, tail in self.res_ops:
-            _run_ops(body.array(), len(body), self.stream())
+            if len(body):
+                _run_ops(body.array(), len(body), self.stream())
             _run_ops(tail.array(), 1, self.stream())
         torch.cuda.synchronize(self.dev)
         for body, tail in self.res_ops:
             if self.group is None:
                 both = OpList(); both.ops = body.ops + tail.ops
                 graphs.append((_lib.Graph(both.array(), len(both)), None))
-            else:
-                graphs.append((_lib.Graph(body.array(), len(body)), _lib.Graph(tail.array(), 1)))
+            else:                                # a rank can own no tiles at all (more ranks than tiles): empty body
+                graphs.append((_lib.Graph(body.array(), len(body)) if len(body) else None, _lib.Graph(tail.array(), 1)))
         self.graphs = graphs
 
     @_on_device
@@ -1498,25 +1513,32 @@ class Session:
         self.params.copy_(params_row)
         body, tail = self.res_ops[self.cur]
         st = self.stream()
+        if _NVTX:
+            torch.cuda.nvtx.range_push("ucdir p_sample step")
         if self.graphs is not None:
             gb, gt = self.graphs[self.cur]
-            gb.launch(st)
+            if gb is not None:
+                gb.launch(st)
             if self.group is not None:
                 self._all_gather()
                 gt.launch(st)
         else:
-            _run_ops(body.array(), len(body), st)
+            if len(body):
+                _run_ops(body.array(), len(body), st)
             if self.group is not None:
                 self._all_gather()
             _run_ops(tail.array(), 1, st)
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
         self.cur ^= 1
 
     def _all_gather(self):
         if self.time_collective:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        torch.distributed.all_gather_into_tensor(self.eps, self.eps[self.rank * self.per_rank:(self.rank + 1) * self.per_rank],
-                                                 group=self.group)
+        with _Range("ucdir tile all-gather"):
+            torch.distributed.all_gather_into_tensor(self.eps, self.eps[self.rank * self.per_rank:(self.rank + 1) * self.per_rank],
+                                                     group=self.group)
         if self.time_collective:
             e1.record()
             self.collective_events.append((e0, e1))
