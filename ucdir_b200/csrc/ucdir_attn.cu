@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) flash_attn_kernel(const __grid_
         if (elect_one()) {
           mbar_expect_tx(&full[slot], 2 * AT_SLOT);
           tma_load_3d(&mapV, &full[slot], ring + slot * AT_SLOT, j * AT_BN + c * AT_KC, half * AT_DH, img);
-          mbar_arrive(&full[slot + 1]);                 // keeps the second slot's phase in step; nobody waits on it
+          mbar_arrive(&full[slot + 1]);                 // keeps the second slot's phase in step (the MMA warp consumes it with the first)
         }
         __syncwarp();
         slot += 2;
@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) flash_attn_kernel(const __grid_
       const uint32_t tO = tmem_base + 256u;
       for (int c = 0; c < 2; ++c) {
         mbar_wait(&full[slot], phase);
-        tc_fence_after();
+        mbar_wait(&full[slot + 1], phase);              // the pair's second barrier (arrived by the producer at issue time): consumed
+        tc_fence_after();                               // here so that every completed phase has a waiter
         if (elect_one()) {
           const uint64_t ad = make_desc(smem_u32(sP + c * AT_SLOT), 128), bd = make_desc(smem_u32(ring + slot * AT_SLOT), 128);
 #pragma unroll
