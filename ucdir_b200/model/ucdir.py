@@ -138,10 +138,37 @@ class Downsample(nn.Module):
         self.conv = nn.Conv2d(dim, dim, 3, 2, 1)
 
 
+def dy3h_plan(in_channel, inner_channel, channel_mults, attn_res, res_blocks, image_size):
+    """The layer table of the denoiser: what the reference's constructor (model/ucdir.py:205-268) builds, as data.
+    Returns (downs, mid, ups, final_channels); entries are ("conv", cin, cout) | ("block", cin, cout, with_attn) | ("down", c) |
+    ("up", c).  Attention is keyed on the NOMINAL resolution (image_size halved per level), not on the actual input size."""
+    downs, ups, skip_channels = [("conv", in_channel, inner_channel)], [], [inner_channel]
+    c, res, last = inner_channel, image_size, len(channel_mults) - 1
+    for level, mult in enumerate(channel_mults):
+        for _ in range(res_blocks):
+            downs.append(("block", c, inner_channel * mult, res in attn_res))
+            c = inner_channel * mult
+            skip_channels.append(c)
+        if level != last:
+            downs.append(("down", c))
+            skip_channels.append(c)
+            res //= 2
+    mid = [("block", c, c, True), ("block", c, c, False)]
+    for level in range(last, -1, -1):
+        for _ in range(res_blocks + 1):
+            ups.append(("block", c + skip_channels.pop(), inner_channel * channel_mults[level], res in attn_res))
+            c = inner_channel * channel_mults[level]
+        if level:
+            ups.append(("up", c))
+            res *= 2
+    return downs, mid, ups, c
+
+
 class DY3h(nn.Module):
-    """Conditional denoiser UNet; constructor mirrors ucdir.py:204-268 line by line in
-    parameter-creation order.  forward/naiveforward keep the reference signatures
-    (ucdir.py:270-307) and run on the CUDA engine."""
+    """Conditional denoiser UNet (model/ucdir.py:204-307): a parameter container built from `dy3h_plan`, in the reference's
+    parameter-creation order (noise_level_mlp, downs, mid, ups, final_conv) so that seeded construction draws the reference's
+    weights and `state_dict()` carries its key names.  forward / naiveforward keep the reference signatures (ucdir.py:270-307) and
+    run on the CUDA engine."""
 
     def __init__(self, in_channel=6, out_channel=3, inner_channel=32, norm_groups=1, channel_mults=[1, 2, 4, 8, 8],
                  attn_res=[8], res_blocks=3, dropout=0, with_noise_level_emb=True, image_size=128,
@@ -152,54 +179,28 @@ class DY3h(nn.Module):
         self.cfg = dict(in_channel=in_channel, out_channel=out_channel, inner_channel=inner_channel,
                         channel_mults=list(channel_mults), attn_res=list(attn_res), res_blocks=res_blocks,
                         image_size=image_size)
-        noise_level_channel = inner_channel
         self.noise_level_mlp = nn.Sequential(PositionalEncoding(inner_channel),
                                              nn.Linear(inner_channel, inner_channel * 4), Swish(),
                                              nn.Linear(inner_channel * 4, inner_channel))
-        num_mults = len(channel_mults)
-        pre_channel = inner_channel
-        feat_channels = [pre_channel]
-        now_res = image_size
-        downs = [nn.Conv2d(in_channel, inner_channel, kernel_size=3, padding=1)]
-        for ind in range(num_mults):
-            is_last = ind == num_mults - 1
-            use_attn = now_res in attn_res
-            channel_mult = inner_channel * channel_mults[ind]
-            for _ in range(res_blocks):
-                downs.append(ResnetBlocWithAttn(pre_channel, channel_mult, nl_emb_dim=noise_level_channel,
-                                                norm_groups=norm_groups, dropout=dropout, with_attn=use_attn,
-                                                resname=resname))
-                feat_channels.append(channel_mult)
-                pre_channel = channel_mult
-            if not is_last:
-                downs.append(Downsample(pre_channel))
-                feat_channels.append(pre_channel)
-                now_res //= 2
-        self.downs = nn.ModuleList(downs)
-        self.mid = nn.ModuleList([
-            ResnetBlocWithAttn(pre_channel, pre_channel, nl_emb_dim=noise_level_channel, norm_groups=norm_groups,
-                               dropout=dropout, with_attn=True, resname=resname),
-            ResnetBlocWithAttn(pre_channel, pre_channel, nl_emb_dim=noise_level_channel, norm_groups=norm_groups,
-                               dropout=dropout, with_attn=False, resname=resname)])
-        ups = []
-        for ind in reversed(range(num_mults)):
-            is_last = ind < 1
-            use_attn = now_res in attn_res
-            channel_mult = inner_channel * channel_mults[ind]
-            for _ in range(res_blocks + 1):
-                ups.append(ResnetBlocWithAttn(pre_channel + feat_channels.pop(), channel_mult,
-                                              nl_emb_dim=noise_level_channel, norm_groups=norm_groups,
-                                              dropout=dropout, with_attn=use_attn, resname=resname))
-                pre_channel = channel_mult
-            if not is_last:
-                ups.append(Upsample(pre_channel))
-                now_res *= 2
-        self.ups = nn.ModuleList(ups)
-        self.prec = pre_channel
-        dim_out = out_channel if out_channel is not None else in_channel
-        self.final_conv = nn.Sequential(nn.GroupNorm(1, pre_channel), Swish(),
+        downs, mid, ups, self.prec = dy3h_plan(in_channel, inner_channel, channel_mults, attn_res, res_blocks, image_size)
+
+        def make(spec):
+            kind = spec[0]
+            if kind == "conv":
+                return nn.Conv2d(spec[1], spec[2], kernel_size=3, padding=1)
+            if kind == "down":
+                return Downsample(spec[1])
+            if kind == "up":
+                return Upsample(spec[1])
+            return ResnetBlocWithAttn(spec[1], spec[2], nl_emb_dim=inner_channel, norm_groups=norm_groups, dropout=dropout,
+                                      with_attn=spec[3], resname=resname)
+
+        self.downs = nn.ModuleList([make(sp) for sp in downs])
+        self.mid = nn.ModuleList([make(sp) for sp in mid])
+        self.ups = nn.ModuleList([make(sp) for sp in ups])
+        self.final_conv = nn.Sequential(nn.GroupNorm(1, self.prec), Swish(),
                                         nn.Dropout(dropout) if dropout != 0 else nn.Identity(),
-                                        nn.Conv2d(pre_channel, dim_out, 3, padding=1))
+                                        nn.Conv2d(self.prec, out_channel if out_channel is not None else in_channel, 3, padding=1))
         # Tile geometry of DY3h.forward (ucdir.py:298-300).  The reference hard-wires (1024, 64) and the
         # 1 Mpx trigger; they are semantic parameters, overridable but never changed silently.
         self.tile_skip = int(os.environ.get("UCDIR_TILE_SKIP", 1024))
@@ -250,38 +251,42 @@ class DY3h(nn.Module):
         return self.engine().forward(x, time, guide)
 
 
+PREDICTOR_WIDTHS = (32, 64, 128, 256, 512)
+
+
+def predictor_plan(in_channels=3, out_channels=3):
+    """Layer table of the initial predictor (model/ucdir.py:310-350), in parameter-creation order: two 3x3 convs per encoder level
+    with a 2x2 max-pool between levels, then per decoder level a 2x2 stride-2 transposed conv and two 3x3 convs on the concatenated
+    features, and a final 1x1 conv.  Entries: (attribute name, kind, cin, cout)."""
+    plan, c = [], in_channels
+    for lvl, wd in enumerate(PREDICTOR_WIDTHS, start=1):
+        plan += [("conv%d_1" % lvl, "conv3", c, wd), ("conv%d_2" % lvl, "conv3", wd, wd)]
+        if lvl < len(PREDICTOR_WIDTHS):
+            plan.append(("pool%d" % lvl, "pool", wd, wd))
+        c = wd
+    for lvl, wd in zip(range(6, 10), reversed(PREDICTOR_WIDTHS[:-1])):
+        plan += [("upv%d" % lvl, "convT", c, wd), ("conv%d_1" % lvl, "conv3", 2 * wd, wd), ("conv%d_2" % lvl, "conv3", wd, wd)]
+        c = wd
+    plan.append(("conv10_1", "conv1", c, out_channels))
+    return plan
+
+
 class UNetSeeInDark(nn.Module):
-    """Initial predictor; parameter container mirroring ucdir.py:310-350."""
+    """Initial predictor; parameter container built from `predictor_plan` (same attribute names and creation order as the
+    reference, model/ucdir.py:310-350)."""
 
     def __init__(self, in_channels=3, out_channels=3):
         super().__init__()
-        self.conv1_1 = nn.Conv2d(in_channels, 32, kernel_size=3, stride=1, padding=1)
-        self.conv1_2 = nn.Conv2d(32, 32, kernel_size=3, stride=1, padding=1)
-        self.pool1 = nn.MaxPool2d(kernel_size=2)
-        self.conv2_1 = nn.Conv2d(32, 64, kernel_size=3, stride=1, padding=1)
-        self.conv2_2 = nn.Conv2d(64, 64, kernel_size=3, stride=1, padding=1)
-        self.pool2 = nn.MaxPool2d(kernel_size=2)
-        self.conv3_1 = nn.Conv2d(64, 128, kernel_size=3, stride=1, padding=1)
-        self.conv3_2 = nn.Conv2d(128, 128, kernel_size=3, stride=1, padding=1)
-        self.pool3 = nn.MaxPool2d(kernel_size=2)
-        self.conv4_1 = nn.Conv2d(128, 256, kernel_size=3, stride=1, padding=1)
-        self.conv4_2 = nn.Conv2d(256, 256, kernel_size=3, stride=1, padding=1)
-        self.pool4 = nn.MaxPool2d(kernel_size=2)
-        self.conv5_1 = nn.Conv2d(256, 512, kernel_size=3, stride=1, padding=1)
-        self.conv5_2 = nn.Conv2d(512, 512, kernel_size=3, stride=1, padding=1)
-        self.upv6 = nn.ConvTranspose2d(512, 256, 2, stride=2)
-        self.conv6_1 = nn.Conv2d(512, 256, kernel_size=3, stride=1, padding=1)
-        self.conv6_2 = nn.Conv2d(256, 256, kernel_size=3, stride=1, padding=1)
-        self.upv7 = nn.ConvTranspose2d(256, 128, 2, stride=2)
-        self.conv7_1 = nn.Conv2d(256, 128, kernel_size=3, stride=1, padding=1)
-        self.conv7_2 = nn.Conv2d(128, 128, kernel_size=3, stride=1, padding=1)
-        self.upv8 = nn.ConvTranspose2d(128, 64, 2, stride=2)
-        self.conv8_1 = nn.Conv2d(128, 64, kernel_size=3, stride=1, padding=1)
-        self.conv8_2 = nn.Conv2d(64, 64, kernel_size=3, stride=1, padding=1)
-        self.upv9 = nn.ConvTranspose2d(64, 32, 2, stride=2)
-        self.conv9_1 = nn.Conv2d(64, 32, kernel_size=3, stride=1, padding=1)
-        self.conv9_2 = nn.Conv2d(32, 32, kernel_size=3, stride=1, padding=1)
-        self.conv10_1 = nn.Conv2d(32, out_channels, kernel_size=1, stride=1)
+        for name, kind, cin, cout in predictor_plan(in_channels, out_channels):
+            if kind == "conv3":
+                layer = nn.Conv2d(cin, cout, kernel_size=3, stride=1, padding=1)
+            elif kind == "conv1":
+                layer = nn.Conv2d(cin, cout, kernel_size=1, stride=1)
+            elif kind == "convT":
+                layer = nn.ConvTranspose2d(cin, cout, 2, stride=2)
+            else:
+                layer = nn.MaxPool2d(kernel_size=2)
+            setattr(self, name, layer)
         self._engine = None
 
     def engine(self):
