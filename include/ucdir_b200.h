@@ -176,7 +176,8 @@ enum ucdir_scatter_flt {
 
 /* ---- UCDIR_OP_MAXPOOL2: DST[B,H,W,C] = max 2x2 of SRC[B,2H,2W,C] (fp32 NHWC) -------------------------- */
 enum ucdir_pool_ptr { UCDIR_POOL_P_SRC = 0, UCDIR_POOL_P_DST = 1 };
-enum ucdir_pool_int { UCDIR_POOL_I_B = 0, UCDIR_POOL_I_H = 1, UCDIR_POOL_I_W = 2, UCDIR_POOL_I_C = 3 };
+enum ucdir_pool_int { UCDIR_POOL_I_B = 0, UCDIR_POOL_I_H = 1, UCDIR_POOL_I_W = 2, UCDIR_POOL_I_C = 3,
+                      UCDIR_POOL_I_SPLIT = 4 /* 1: (hi, lo) bf16 plane pairs [..][2*C] instead of fp32 (UCDIR_TC_I_SPLIT) */ };
 
 /* ---- UCDIR_OP_TC_CONV: bf16 tcgen05 / TMA implicit-GEMM convolution (ucdir_tc.cu) ---------------------------
  * Same reference lines as UCDIR_OP_CONV_F32.  Activations bf16 NHWC; weights bf16 [NTOT][K] K-major with
@@ -184,7 +185,7 @@ enum ucdir_pool_int { UCDIR_POOL_I_B = 0, UCDIR_POOL_I_H = 1, UCDIR_POOL_I_W = 2
  * Source pixel of output (y, x), tap (ty, tx): (y*STRIDE + ty + OY0, x*STRIDE + tx + OX0); outside the image = 0.
  * GN=1: GroupNorm(1,C) of the input is folded: weights carry gamma, the epilogue applies
  *   v = rstd*acc - mean*rstd*TG[cls][n] + TB[cls][n]  (cls = 3x3 border class when NCLS = 9, else 0);
- * GN=0: v = acc + TB[0][n] (TB = bias).  MODE / ACT / RES / DST_UP as in UCDIR_OP_CONV_F32 (RES, DST bf16;
+ * GN=0: v = acc + TB[0][n] (TB = bias).  MODE / ACT (0 none | 1 Swish | 2 LeakyReLU 0.2) / RES / DST_UP as in UCDIR_OP_CONV_F32 (RES, DST bf16;
  * DST_F32=1 stores fp32 and only columns < NCOL_VALID).  DST_STATS as in UCDIR_OP_CONV_F32. */
 enum ucdir_tc_ptr {
   UCDIR_TC_P_SRC0 = 0, UCDIR_TC_P_SRC1 = 1, UCDIR_TC_P_W = 2, UCDIR_TC_P_TB = 3, UCDIR_TC_P_TG = 4,

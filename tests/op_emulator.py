@@ -308,6 +308,14 @@ def emu_scatter(op, mem):
 
 def emu_maxpool(op, mem):
     B, H, W, Cc = _i(op, "UCDIR_POOL_I_B"), _i(op, "UCDIR_POOL_I_H"), _i(op, "UCDIR_POOL_I_W"), _i(op, "UCDIR_POOL_I_C")
+    if _i(op, "UCDIR_POOL_I_SPLIT"):                                # (hi, lo) bf16 plane pairs
+        bf = torch.bfloat16
+        s2 = mem.view(_p(op, "UCDIR_POOL_P_SRC"), (B, 2 * H, 2 * W, 2 * Cc), bf).float()
+        v = F.max_pool2d((s2[..., :Cc] + s2[..., Cc:]).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+        d2 = mem.view(_p(op, "UCDIR_POOL_P_DST"), (B, H, W, 2 * Cc), bf)
+        d2[..., :Cc] = v.to(bf)
+        d2[..., Cc:] = (v - v.to(bf).float()).to(bf)
+        return
     s = mem.view(_p(op, "UCDIR_POOL_P_SRC"), (B, 2 * H, 2 * W, Cc))
     d = mem.view(_p(op, "UCDIR_POOL_P_DST"), (B, H, W, Cc))
     d.copy_(F.max_pool2d(s.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1))
@@ -438,6 +446,8 @@ def emu_tc_conv(op, mem):
     else:
         if act == 1:
             v = swish(v)
+        elif act == 2:
+            v = torch.maximum(0.2 * v, v)
         rp = _p(op, "UCDIR_TC_P_RES")
         if rp and split:
             r2 = mem.view(rp, (B, H, W, 2 * resC), bf).float()

@@ -486,3 +486,20 @@ def test_reference_ddpm_methods_drive_our_module(emulated, sid_weights):
         want = O.ddpm_test(sd, lay, O.schedule_buffers(so), sr, [noise], continous=True)
     close(vis["SR"], want)
     assert torch.equal(vis["INF"], sr) and net.training
+
+
+def test_predictor_tensor_core_plan(emulated, golden, sid_weights):
+    """UNetSeeInDark on the tensor-core plan (split operands, channels padded to 64, LeakyReLU epilogue, ConvTranspose as four 1x1
+    phase GEMMs, max-pool on plane pairs) against the reference's golden output, fp32 tolerance; records valid for the C ABI."""
+    net, _ = sid_weights
+    eng = net.predictor.engine()
+    eng.set_mode("tc")
+    try:
+        g = golden("unet")
+        y = net.predictor(T(g["xp"]))
+        plan = next(iter(eng._plans.values()))
+        _lib.check_ops(plan[0].array(), len(plan[0]))
+        assert any(o.kind == _lib.C["UCDIR_OP_TC_CONV"] and o.i[_lib.C["UCDIR_TC_I_SPLIT"]] for o in plan[0].ops)
+        close(y, g["pred"], rtol=1e-4, atol=2e-5)
+    finally:
+        eng.set_mode("fp32")

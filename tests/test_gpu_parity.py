@@ -265,3 +265,24 @@ def test_tensor2img_kernel_bit_exact(golden):
     assert np.array_equal(tensor2img(x, crop=int(g["crop"])), g["img_crop"])
     with pytest.raises(Exception):
         tensor2img(T(g["x"]))                                  # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("shape", [(1, 40, 56), (2, 72, 88), (1, 130, 250)])
+def test_predictor_tensor_core_plan(sid_weights, sd, golden, shape):
+    """UNetSeeInDark on the split-operand tensor-core plan (what the samplers use whenever the denoiser runs on the tensor cores):
+    the reference's golden vector and ragged / batched shapes against the oracle, fp32 tolerance."""
+    net, _ = sid_weights
+    net = net.to("cuda")
+    eng = net.predictor.engine()
+    eng.set_mode("tc")
+    try:
+        if shape == (1, 40, 56):
+            g = golden("unet")
+            close(net.predictor(T(g["xp"]).cuda()), g["pred"], what="predictor tc plan, golden 40x56")
+        b, h, w = shape
+        x = torch.rand(b, 3, h, w, generator=torch.Generator().manual_seed(h + w)) * 2 - 1
+        with torch.no_grad():
+            want = O.predictor_forward(sd, "predictor.", x)
+        close(net.predictor(x.cuda()), want, what="predictor tc plan %s" % (shape,))
+    finally:
+        eng.set_mode("fp32")

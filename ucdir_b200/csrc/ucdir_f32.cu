@@ -550,9 +550,58 @@ __global__ void maxpool2_kernel(const float4* __restrict__ src, float4* __restri
   dst[idx] = o;
 }
 
+// MaxPool 2x2 on (hi, lo) bf16 plane pairs [B][2H][2W][2C] -> [B][H][W][2C] (fp32_tc predictor): the maximum of the four hi + lo
+// values, re-split.  One thread per output pixel and 8 channels.
+__global__ void __launch_bounds__(256) maxpool2_split_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int H, int W, int C) {
+  const int c8 = C / 8;
+  const size_t total = (size_t)B * H * W * c8;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c8) * 8; size_t t = idx / c8;
+    const int x = (int)(t % W); t /= W;
+    const int y = (int)(t % H); const int b = (int)(t / H);
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const __nv_bfloat16* s = src + ((((size_t)b * 2 * H + 2 * y + dy) * (2 * W)) + 2 * x + dx) * 2 * C + c;
+        const uint4 uh = __ldg(reinterpret_cast<const uint4*>(s)), ul = __ldg(reinterpret_cast<const uint4*>(s + C));
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&uh);
+        const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&ul);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 fh = __bfloat1622float2(h2[k]), fl = __bfloat1622float2(l2[k]);
+          m[2 * k] = fmaxf(m[2 * k], fh.x + fl.x); m[2 * k + 1] = fmaxf(m[2 * k + 1], fh.y + fl.y);
+        }
+      }
+    __align__(16) __nv_bfloat162 oh[4];
+    __align__(16) __nv_bfloat162 ol[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      oh[k] = __floats2bfloat162_rn(m[2 * k], m[2 * k + 1]);
+      const float2 r = __bfloat1622float2(oh[k]);
+      ol[k] = __floats2bfloat162_rn(m[2 * k] - r.x, m[2 * k + 1] - r.y);
+    }
+    __nv_bfloat16* d = dst + (((size_t)b * H + y) * W + x) * 2 * C + c;
+    *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(oh);
+    *reinterpret_cast<uint4*>(d + C) = *reinterpret_cast<const uint4*>(ol);
+  }
+}
+
 int launch_maxpool2(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   int B = op.i[UCDIR_POOL_I_B], H = op.i[UCDIR_POOL_I_H], W = op.i[UCDIR_POOL_I_W], C = op.i[UCDIR_POOL_I_C];
   if (!op.p[0] || !op.p[1] || B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 4) { set_error("maxpool2: bad args"); return -1; }
+  if (op.i[UCDIR_POOL_I_SPLIT]) {
+    if (C % 8) { set_error("maxpool2: split planes need C %% 8 == 0"); return -1; }
+    if (dry) return 0;
+    const size_t total8 = (size_t)B * H * W * (C / 8);
+    const unsigned g = (unsigned)((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
+    maxpool2_split_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)op.p[0], (__nv_bfloat16*)op.p[1], B, H, W, C);
+    ++g_launches;
+    return 0;
+  }
   if (dry) return 0;
   size_t total = (size_t)B * H * W * (C / 4);
   maxpool2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float4*)op.p[0], (float4*)op.p[1], B, H, W, C / 4);

@@ -557,6 +557,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           if (p.act == 1) {
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = SPLIT ? swish_f(v[j]) : swish_fast(v[j]);
+          } else if (p.act == 2) {              // LeakyReLU(0.2) = max(0.2 x, x), model/ucdir.py:414-416 (predictor)
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = fmaxf(0.2f * v[j], v[j]);
           }
           if (EPI != EPI_F32 && p.res) {
 #pragma unroll

@@ -1553,11 +1553,29 @@ class Session:
 # ======================================================================================
 # predictor engine (UNetSeeInDark, model/ucdir.py:310-416)
 # ======================================================================================
+def _pad_c(c: int) -> int:
+    """channel count of a predictor tensor on the tensor-core path: multiples of 64 (32-channel levels carry 32 zero channels)."""
+    return _round_up(max(c, 64), 64)
+
+
 class PredictorEngine:
+    """UNetSeeInDark (model/ucdir.py:310-416), once per image.  Two plans: "fp32" = SIMT FFMA kernels; "tc" = the tensor-core path
+    with split (hi + lo bf16) operands -- fp32-class accuracy (the predictor's output is ADDED to the sampler's result,
+    model/diffusion.py:478, so it is never run with plain bf16 operands), LeakyReLU in the conv epilogue, ConvTranspose2d(2, 2) as
+    four 1x1 phase GEMMs, max-pool on plane pairs.  The sampler picks "tc" whenever the denoiser runs on the tensor cores."""
+
     def __init__(self, module):
         self.m = module
         self.ws: Optional[WeightStore] = None
         self._plans: Dict[tuple, tuple] = {}
+        self.mode = "fp32" if os.environ.get("UCDIR_PRECISION", "fp32") == "fp32" else "tc"
+
+    def set_mode(self, mode: str):
+        if mode not in ("fp32", "tc"):
+            raise ValueError("predictor mode must be fp32 or tc")
+        if mode != self.mode:
+            self.mode = mode
+            self.invalidate_weights()
 
     def invalidate_weights(self):
         self.ws = None
@@ -1578,6 +1596,10 @@ class PredictorEngine:
         self._packed_version = ver
         self._plans.clear()
         ws = WeightStore(dev)
+        if self.mode == "tc":
+            self._pack_tc(ws)
+            self.ws = ws
+            return
         for name, layer in self.m.named_children():
             if isinstance(layer, torch.nn.ConvTranspose2d):
                 for py in range(2):
@@ -1589,11 +1611,138 @@ class PredictorEngine:
                 ws.put(name + ".b", layer.bias.float())
         self.ws = ws
 
+    # ---- tensor-core plan (split operands) ------------------------------------------------------------------------------
+    def _pack_tc(self, ws: WeightStore):
+        from .model.ucdir import predictor_plan
+        cin_layout = {}                               # conv name -> list of (real channels, padded channels) per source
+        c_prev, enc = (3, 16), []
+        for name, kind, cin, cout in predictor_plan():
+            if kind == "conv3" or kind == "conv1":
+                if name.endswith("_1") and int(name[4:].split("_")[0]) in (6, 7, 8, 9):      # torch.cat([up, skip], 1)
+                    srcs = [(cout, _pad_c(cout)), (cout, _pad_c(cout))]
+                else:
+                    srcs = [c_prev]
+                cin_layout[name] = srcs
+                c_prev = (cout, _pad_c(cout))
+            elif kind == "convT":
+                cin_layout[name] = [c_prev]
+                c_prev = (cout, _pad_c(cout))
+        for name, kind, cin, cout in predictor_plan():
+            layer = getattr(self.m, name)
+            if kind == "pool":
+                continue
+            srcs = cin_layout[name]
+            cip = sum(pp for _, pp in srcs)
+            if kind == "convT":                       # [Cin][Cout][2][2] -> four 1x1 GEMMs [Cout][Cin]
+                cop = _pad_c(cout)
+                for py in range(2):
+                    for px in range(2):
+                        wp = torch.zeros(cop, cip, 1, 1, device=layer.weight.device)
+                        wp[:cout, :cin, 0, 0] = layer.weight[:, :, py, px].t().float()
+                        bp = torch.zeros(cop, device=layer.weight.device); bp[:cout] = layer.bias.float()
+                        w_, tb_, _ = pack_tc_dense(wp, bp, _tc_nt(cop), split=True)
+                        ws.put("%s.p%d%d.tcw" % (name, py, px), w_); ws.put("%s.p%d%d.tb" % (name, py, px), tb_)
+                continue
+            last = kind == "conv1"
+            cop = 16 if last else _pad_c(cout)
+            ks = layer.kernel_size[0]
+            wp = torch.zeros(cop, cip, ks, ks, device=layer.weight.device)
+            off_real = off_pad = 0
+            for real, padded in srcs:
+                wp[:cout, off_pad:off_pad + real] = layer.weight[:, off_real:off_real + real].float()
+                off_real += real; off_pad += padded
+            bp = torch.zeros(cop, device=layer.weight.device); bp[:cout] = layer.bias.float()
+            w_, tb_, _ = pack_tc_dense(wp, bp, 16 if last else _tc_nt(cop), split=True, c0=srcs[0][1])
+            ws.put(name + ".tcw", w_); ws.put(name + ".tb", tb_)
+
+    def _plan_tc(self, B, h, w):
+        from .model.ucdir import PREDICTOR_WIDTHS
+        dev = self.device()
+        ws = self.ws
+        geo = geometry_direct(B, h, w)                            # model/ucdir.py:352-358: same pad rule
+        TH, TW = geo.TH, geo.TW
+        pool = Pool(dev)
+        x_img = torch.empty((B, 3, h, w), dtype=F32, device=dev)
+        x_tiles = torch.empty((B, TH, TW, 32), dtype=BF16, device=dev)         # (hi, lo) planes of 16 channels (3 valid)
+        tab = torch.from_numpy(geo.table()).to(dev)
+        out_tiles = torch.empty((B, TH, TW, 4), dtype=F32, device=dev)
+        dummy_stats = torch.zeros((1, B, 2), dtype=torch.float64, device=dev)
+        bld = _Builder(pool, B, dummy_stats, elem=2, split=True)
+        ol = bld.ops
+        ol.add("UCDIR_OP_GATHER_TILES",
+               {"UCDIR_GATHER_P_SRC_A": x_img.data_ptr(), "UCDIR_GATHER_P_TAB": tab.data_ptr(), "UCDIR_GATHER_P_DST": x_tiles.data_ptr()},
+               {"UCDIR_GATHER_I_BT": B, "UCDIR_GATHER_I_TH": TH, "UCDIR_GATHER_I_TW": TW, "UCDIR_GATHER_I_IMG_H": h,
+                "UCDIR_GATHER_I_IMG_W": w, "UCDIR_GATHER_I_PD": 0, "UCDIR_GATHER_I_CA": 3, "UCDIR_GATHER_I_CB": 0,
+                "UCDIR_GATHER_I_CD": 16, "UCDIR_GATHER_I_OUT_BF16": 2})
+
+        def conv(name, x: Act, cout, skip: Optional[Act] = None, kc=64) -> Act:
+            cop = _pad_c(cout)
+            y = bld.new(cop, x.H, x.W, with_stats=False)
+            _tc_op(ol, split=1, src0=x, src1=skip, w=ws.ptr(name + ".tcw"), tb=ws.ptr(name + ".tb"), kc=kc, act=2, dst=y, ntot=cop, B=B,
+                   nt=_tc_nt(cop))
+            return y
+
+        def pool2(x: Act) -> Act:
+            y = bld.new(x.C, x.H // 2, x.W // 2, with_stats=False)
+            ol.add("UCDIR_OP_MAXPOOL2", {"UCDIR_POOL_P_SRC": x.ptr, "UCDIR_POOL_P_DST": y.ptr},
+                   {"UCDIR_POOL_I_B": B, "UCDIR_POOL_I_H": y.H, "UCDIR_POOL_I_W": y.W, "UCDIR_POOL_I_C": x.C, "UCDIR_POOL_I_SPLIT": 1})
+            return y
+
+        def upconv(name, x: Act, cout) -> Act:
+            cop = _pad_c(cout)
+            y = bld.new(cop, x.H * 2, x.W * 2, with_stats=False)
+            for py in range(2):
+                for px in range(2):
+                    _tc_op(ol, split=1, src0=x, w=ws.ptr("%s.p%d%d.tcw" % (name, py, px)), tb=ws.ptr("%s.p%d%d.tb" % (name, py, px)), nty=1,
+                           ntx=1, oy0=0, ox0=0, dst=y, ntot=cop, B=B, nt=_tc_nt(cop), dst_up=1, dst_py=py, dst_px=px)
+            return y
+
+        x = Act(x_tiles, 16, TH, TW, 0, keep=True, split=True)
+        enc = []
+        for lvl, c in enumerate(PREDICTOR_WIDTHS, start=1):
+            a = conv("conv%d_1" % lvl, x, c, kc=16 if lvl == 1 else 64)
+            if lvl > 1:
+                bld.release(x)
+            x = conv("conv%d_2" % lvl, a, c)
+            bld.release(a)
+            if lvl < len(PREDICTOR_WIDTHS):
+                x.keep = True
+                enc.append(x)
+                x = pool2(x)
+        for lvl, c in zip(range(6, 10), reversed(PREDICTOR_WIDTHS[:-1])):
+            u = upconv("upv%d" % lvl, x, c)
+            bld.release(x)
+            skip = enc.pop()
+            skip.keep = False
+            a = conv("conv%d_1" % lvl, u, c, skip=skip)           # torch.cat([up, conv_k], 1) as a dual-source K loop
+            bld.release(u); bld.release(skip)
+            x = conv("conv%d_2" % lvl, a, c)
+            bld.release(a)
+        dst = Act(out_tiles, 4, TH, TW, 0, keep=True)
+        _tc_op(ol, split=1, src0=x, w=ws.ptr("conv10_1.tcw"), tb=ws.ptr("conv10_1.tb"), nty=1, ntx=1, oy0=0, ox0=0, dst=dst, ntot=16, B=B,
+               nt=16, dst_f32=1, ncol_valid=3)
+        bld.release(x)
+        owner_y = torch.from_numpy(geo.owner_y).to(dev); owner_x = torch.from_numpy(geo.owner_x).to(dev)
+        z = torch.zeros(1, dtype=torch.int32, device=dev)
+        idx_scatter = ol.add("UCDIR_OP_SCATTER",
+                             {"UCDIR_SCATTER_P_EPS": out_tiles.data_ptr(), "UCDIR_SCATTER_P_OWNER_Y": owner_y.data_ptr(),
+                              "UCDIR_SCATTER_P_OWNER_X": owner_x.data_ptr(), "UCDIR_SCATTER_P_Y0": z.data_ptr(),
+                              "UCDIR_SCATTER_P_X0": z.data_ptr()},
+                             {"UCDIR_SCATTER_I_BIMG": B, "UCDIR_SCATTER_I_IMG_H": h, "UCDIR_SCATTER_I_IMG_W": w,
+                              "UCDIR_SCATTER_I_NTY": 1, "UCDIR_SCATTER_I_NTX": 1, "UCDIR_SCATTER_I_TH": TH,
+                              "UCDIR_SCATTER_I_TW": TW, "UCDIR_SCATTER_I_PD": 0, "UCDIR_SCATTER_I_CE": 4,
+                              "UCDIR_SCATTER_I_MODE": 0, "UCDIR_SCATTER_I_C": 3})
+        return (ol, x_img, idx_scatter, (pool, x_tiles, tab, out_tiles, owner_y, owner_x, z, dummy_stats))
+
     def _plan(self, B, h, w):
-        key = (B, h, w)
+        key = (B, h, w, self.mode)
         if key in self._plans:
             return self._plans[key]
         self._plans.clear()
+        if self.mode == "tc":
+            plan = self._plan_tc(B, h, w)
+            self._plans[key] = plan
+            return plan
         dev = self.device()
         ws = self.ws
         geo = geometry_direct(B, h, w)                            # model/ucdir.py:352-358: same pad rule

@@ -185,6 +185,12 @@ class GaussianDiffusion(nn.Module):
         """fp32 value of sqrt_alphas_cumprod_prev[t+1] (model/diffusion.py:162-163)."""
         return float(np.float32(self.sqrt_alphas_cumprod_prev[t + 1]))
 
+    def _initial_prediction(self, x_in):
+        """`self.predictor(x_in)` (model/diffusion.py:475) on the kernels that match the denoiser's precision mode: tensor cores with
+        split operands (fp32-class accuracy: this output is added to the final image) unless the denoiser runs the SIMT debug path."""
+        self.predictor.engine().set_mode("fp32" if self.denoise_fn.engine().precision == "fp32" else "tc")
+        return self.predictor(x_in)
+
     def _guide_of(self, kwargs):
         g = (kwargs or {}).get("guide")
         if g is None:
@@ -374,7 +380,7 @@ class ResiGaussianGuideDY(GaussianDiffusion):
     def super_resolution(self, x_in, continous=False):
         """model/diffusion.py:473-478.  Like the reference, `+ initx` broadcasts over the snapshot rows,
         which is only shape-valid for batch 1 when continous."""
-        initx = self.predictor(x_in)
+        initx = self._initial_prediction(x_in)
         self.pre_initx = initx
         return self.p_sample_loop(x_in, continous, kwargs={"guide": initx}) + initx
 
@@ -390,7 +396,7 @@ class ResiGaussianGuideDY_de(GaussianDiffusion):
     @torch.no_grad()
     def super_resolution(self, x_in, continous=False):
         """model/diffusion.py:518-523."""
-        initx = self.predictor(x_in)
+        initx = self._initial_prediction(x_in)
         self.pre_initx = initx
         return self.p_sample_loop(x_in, continous, kwargs={"guide": x_in}) + initx
 
@@ -401,7 +407,7 @@ class ResiGaussianGuideDY_initxloss(ResiGaussianGuideDY):
 
     @torch.no_grad()
     def super_resolution(self, x_in, continous=False):
-        initx = self.predictor(x_in)
+        initx = self._initial_prediction(x_in)
         return self.p_sample_loop(x_in, continous, kwargs={"guide": initx}) + initx
 
 
@@ -418,7 +424,7 @@ class _GuidelessResidual(GaussianDiffusion):
 
     @torch.no_grad()
     def super_resolution(self, x_in, continous=False):
-        initx = self.predictor(x_in)
+        initx = self._initial_prediction(x_in)
         return self.p_sample_loop(x_in, continous) + initx           # -> TypeError: guide (as in the reference)
 
 
@@ -436,6 +442,6 @@ class NoDiffusion(_GuidelessResidual):
 
     @torch.no_grad()
     def super_resolution(self, x_in, continous=False):
-        initx = self.predictor(x_in)
+        initx = self._initial_prediction(x_in)
         self._guide_of(None)                                          # raises
         return initx
