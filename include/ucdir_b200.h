@@ -242,6 +242,9 @@ enum ucdir_tc_int {
   UCDIR_TC_I_DST_CROP = 50,                      /* fused final conv only: DST is [B][H - 2*CROP][W - 2*CROP][DST_C] and receives only the interior of every
                                                   * sample -- the part of a tile that is stitched (utils/util.py:144-145) and, sharded, all-gathered; replaces a
                                                   * separate UCDIR_OP_CROP_TILES pass */
+  UCDIR_TC_I_PHASES = 51,                        /* 4: nearest-2x upsample + conv3x3 (model/ucdir.py:53-60) as ONE launch: the four 2x2-tap phase convolutions
+                                                  * are an extra work-item dimension; W = the phases' weight blocks stacked along N ([4*NTOT][K], phase = py*2 + px),
+                                                  * OY0 = OX0 = -1, DST_UP = 1, DST_PY = DST_PX = 0 */
   UCDIR_TC_I_HALO = 43                           /* 1: halo schedule where it applies (grouped mix convs, C = 64 / 128 / 256): one 10 x 18 pixel TMA box per
                                                   * 8 x 16 pixel tile serves all nine taps, weights stay resident in shared memory (ucdir_mix.cu); 3x3 convs with 64 / 128 output
                                                   * channels: super tiles (ucdir_dhalo.cu) */

@@ -328,6 +328,17 @@ def emu_memset(op, mem):
 
 def emu_tc_conv(op, mem):
     """UCDIR_OP_TC_CONV restated: bf16 operands, fp32 accumulation, epilogue exactly as documented in the header."""
+    if _i(op, "UCDIR_TC_I_PHASES") == 4:                         # fused upsample phases = the four single-phase records
+        ntot, kc = _i(op, "UCDIR_TC_I_NTOT"), _i(op, "UCDIR_TC_I_KC")
+        ktot = 4 * (_i(op, "UCDIR_TC_I_C0") + _i(op, "UCDIR_TC_I_C1")) * (3 if _i(op, "UCDIR_TC_I_SPLIT") else 1)
+        for ph in range(4):
+            sub = _lib.Op.from_buffer_copy(op)
+            sub.i[K["UCDIR_TC_I_PHASES"]] = 0
+            sub.p[K["UCDIR_TC_P_W"]] = _p(op, "UCDIR_TC_P_W") + ph * ntot * ktot * 2
+            sub.i[K["UCDIR_TC_I_OY0"]], sub.i[K["UCDIR_TC_I_OX0"]] = (ph >> 1) - 1, (ph & 1) - 1
+            sub.i[K["UCDIR_TC_I_DST_PY"]], sub.i[K["UCDIR_TC_I_DST_PX"]] = ph >> 1, ph & 1
+            emu_tc_conv(sub, mem)
+        return
     g = lambda n: _i(op, "UCDIR_TC_I_" + n)
     B, H, W, sH, sW = g("B"), g("H"), g("W"), g("SRC_H"), g("SRC_W")
     C0, C1, Ntot = g("C0"), g("C1"), g("NTOT")

@@ -434,3 +434,35 @@ def test_tc_flash_attention_16k_tokens_vs_materialised_path():
     a, b = o1.float().cpu(), o2.float().cpu()
     assert torch.isfinite(a).all()
     assert_close(a, b, "flash vs materialised attention, 16384 tokens", rtol=2e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 8, 12, 128), (5, 8, 8, 512), (3, 32, 32, 256)])
+def test_tc_upsample_fused_phases(B, H, W, C):
+    """UCDIR_TC_I_PHASES = 4: the four phase convolutions of nearest-2x + conv3x3 in ONE launch (phase = extra work-item dimension,
+    weight blocks stacked along N) against the interpreter and against torch's upsample + conv on the same bf16 input; statistics of
+    the output accumulate over all four phases."""
+    g = torch.Generator().manual_seed(C + H)
+    x = rnd(g, B, H, W, C).to(BF)
+    w = rnd(g, C, C, 3, 3, scale=1.0 / np.sqrt(9 * C))
+    bias = rnd(g, C, scale=0.1)
+    nt = E._tc_nt(C)
+    blocks = []
+    for py in range(2):
+        for px in range(2):
+            wp, tb = E.pack_tc_up_phase(w, bias, py, px, nt)
+            blocks.append(wp)
+    c = Case().add("x", x).add("dst", torch.zeros(B, 2 * H, 2 * W, C, dtype=BF)).add("dstats", torch.zeros(B, 2, dtype=torch.float64))
+    c.add("w", torch.cat(blocks, 0)).add("tb", tb)
+
+    def build(t):
+        ol = E.OpList()
+        E._tc_op(ol, src0=act(t["x"], C, H, W), w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), nty=2, ntx=2, oy0=-1, ox0=-1,
+                 dst=act(t["dst"], C, 2 * H, 2 * W, t["dstats"]), ntot=C, B=B, nt=nt, dst_up=1, phases=4)
+        return ol
+    _lib.check_ops(build(c.on("cpu")).array(), 1)
+    host, dev = run_both(c, build)
+    assert_close(dev["dst"], host["dst"], "fused phases vs interpreter")
+    assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
+    xn = torch.nn.functional.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    want = torch.nn.functional.conv2d(xn, w, bias, padding=1).permute(0, 2, 3, 1)
+    assert_close(dev["dst"], want, "fused phases vs upsample+conv", rtol=3e-2, atol=3e-2)

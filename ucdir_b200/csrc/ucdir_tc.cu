@@ -57,6 +57,9 @@ struct TcParams {
   int a0_lo, a1_lo;            // channel offset of the lo plane inside a pixel row of src0 / src1
   int b_lo;                    // batched weights: K offset of the lo plane inside a weight row
   int dst_lo, res_lo, t_lo;    // element offset of the lo plane inside a dst / residual / dst2 row
+  // fused upsample phases (UCDIR_TC_I_PHASES = 4): the four output parities of nearest-2x + conv3x3 in one launch; the phase is an
+  // extra, slowest work-item dimension folded into the image-tile index (tiles_n = phases * tiles_n_real)
+  int phases, tiles_n_real;
 };
 
 // Which activation slab chunk j of a filter tap reads (map 0 / 1, channel coordinate) and, for batched weights, the K
@@ -219,8 +222,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     int stage = 0; uint32_t phase = 0;
     int cur_ns = -1; uint32_t bfree_phase = 0;
     for (int li = 0; li < n_items; ++li) {
-      const int x0 = cur.tx_i * p.bw * p.stride + p.ox0, y0 = cur.ty_i * p.bh * p.stride + p.oy0, n0 = cur.tn_i * p.bn;
+      int tn = cur.tn_i, ph = 0;
+      if (p.phases > 1) { ph = tn / p.tiles_n_real; tn -= ph * p.tiles_n_real; }
+      const int x0 = cur.tx_i * p.bw * p.stride + p.ox0 + (ph & 1), y0 = cur.ty_i * p.bh * p.stride + p.oy0 + (ph >> 1), n0 = tn * p.bn;
       const int ncol0 = cur.ns * NT;
+      const int brow0 = ncol0 + ph * p.Ntot;           // weight rows: the phases' blocks are stacked along N
       const int cgrp0 = p.groups > 1 ? ((ncol0 / p.Ng) * p.Cg) / p.cg_eff * p.cg_eff : 0;
       if (BSTAT && cur.ns != cur_ns) {
         // new N sub-tile: (re)load its whole weight block once; every following item streams activations only
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           tma_load_4d(use1 ? &mapA1 : &mapA0, &full[stage], sa, coff, x0 + tx, y0 + ty, n0);
           if (!BSTAT) {
             if (p.w_batched) tma_load_3d(&mapB, &full[stage], sa + S::A_BYTES, kbx, ncol0, n0);
-            else tma_load_2d(&mapB, &full[stage], sa + S::A_BYTES, kbx, ncol0);
+            else tma_load_2d(&mapB, &full[stage], sa + S::A_BYTES, kbx, brow0);
           }
         }
         __syncwarp();
@@ -375,7 +381,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     for (int li = 0; li < n_items; ++li) {
       const int ncol0 = cur.ns * NT;
       if (new_m) {                                    // per-pixel state changes only with the M tile
-        const int im0 = cur.tn_i * p.bn;
+        int tn = cur.tn_i, ph = 0;
+        if (p.phases > 1) { ph = tn / p.tiles_n_real; tn -= ph * p.tiles_n_real; }
+        const int im0 = tn * p.bn;
         if (p.dst_stats && p.bn == 1 && im0 != stat_img) {
           if (stat_img >= 0) {
             const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
@@ -396,7 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           if (p.ncls == 9) cls = (y == 0 ? 0 : (y == p.H - 1 ? 2 : 1)) * 3 + (x == 0 ? 0 : (x == p.W - 1 ? 2 : 1));
         }
         pix_in = ((size_t)img * p.H + y) * p.W + x;
-        pix_out = p.dstUp ? ((size_t)img * 2 * p.H + 2 * y + p.dstPy) * (2 * p.W) + 2 * x + p.dstPx : pix_in;
+        pix_out = p.dstUp ? ((size_t)img * 2 * p.H + 2 * y + p.dstPy + (ph >> 1)) * (2 * p.W) + 2 * x + p.dstPx + (ph & 1) : pix_in;
         res_row = p.res ? p.res + pix_in * p.resC : nullptr;
         dst_row = reinterpret_cast<uint8_t*>(p.dst) + (pix_out * p.dstC + p.dstCoff) * (EPI == EPI_F32 ? 4 : 2);
         if (MIX) {
@@ -835,7 +843,14 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   const int tiles_n = (p.B + p.bn - 1) / p.bn;
   const long mt = (long)p.tiles_x * p.tiles_y * tiles_n;
   if (mt > 0x7fffffffL) { set_error("tc_conv: too many M tiles"); return -2; }
-  p.m_tiles = (int)mt; p.tiles_n = tiles_n;
+  p.phases = op.i[UCDIR_TC_I_PHASES] > 1 ? op.i[UCDIR_TC_I_PHASES] : 1;
+  p.tiles_n_real = tiles_n;
+  if (p.phases > 1) {
+    if (p.phases != 4 || !p.dstUp || p.nty != 2 || p.ntx != 2 || p.stride != 1 || p.groups != 1 || p.w_batched || p.dst2 || p.mode == 1 ||
+        op.i[UCDIR_TC_I_DST_PY] || op.i[UCDIR_TC_I_DST_PX] || mt * 4 > 0x7fffffffL) {
+      set_error("tc_conv: PHASES = 4 needs a dense 2x2-tap stride-1 conv with DST_UP = 1 and DST_PY = DST_PX = 0"); return -2; }
+  }
+  p.m_tiles = (int)(mt * p.phases); p.tiles_n = tiles_n * p.phases;
   if (op.i[UCDIR_TC_I_SRC_GN_SWISH] && !tc_final_halo_applies(op)) {
     set_error("tc_conv: SRC_GN_SWISH needs a 3x3 stride-1 conv of <= 128 channels (multiple of 64) with GN = 0, NT = NTOT = 16, DST_F32 = 1, SRC_GAMMA / SRC_BETA / STATS0");
     return -2;
@@ -862,7 +877,7 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
     for (int c = 0; c < 3; ++c) {
       const int nt = cand[c];
       if (nt > NT || p.Ntot % nt || (plain_t && (nt < 128 || p.t_col0 % nt))) continue;
-      const long long it = (long long)mt * (p.Ntot / nt);
+      const long long it = (long long)p.m_tiles * (p.Ntot / nt);
       const long long per_cta = (it + n_sm - 1) / n_sm;
       const double est = (double)per_cta * cyc[c] + 400.0 * (double)per_cta;      // + per-item epilogue / pipeline refill
       if (est < best * 0.97) { best = est; best_nt = nt; }
@@ -884,9 +899,9 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   else a1 = a0;
   const int Ktot = p.nty * p.ntx * p.nchunk * KB;
   if (p.w_batched) rc = make_w_map(&bm, w, split ? p.b_lo + p.n0 * KB : C0, op.i[UCDIR_TC_I_W_ROWS] ? op.i[UCDIR_TC_I_W_ROWS] : p.Ntot, KB, NT, w_rowstride, p.B, w_batchstride);
-  else rc = make_w_map(&bm, w, Ktot, p.Ntot, KB, NT, Ktot, 0, 0);
+  else rc = make_w_map(&bm, w, Ktot, p.Ntot * p.phases, KB, NT, Ktot, 0, 0);
   if (rc) return rc;
-  const long long items = (long long)mt * (p.Ntot / NT);
+  const long long items = (long long)p.m_tiles * (p.Ntot / NT);
   dim3 grid((unsigned)(items < n_sm ? items : n_sm), 1, 1);      // persistent: one CTA per SM
   p.ctab = (!split && p.mode == 1 && p.gn && p.ncls == 9 && p.bn == 1 && p.Ntot <= 1024 && KC == 32 && KB == 16 && op.i[UCDIR_TC_I_NO_CTAB] == 0 &&
             op.i[UCDIR_TC_I_BSTAT] == 0 && op.i[UCDIR_TC_I_SPS3] == 0) ? 1 : 0;

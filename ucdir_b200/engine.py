@@ -469,7 +469,7 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
            w_batched: int = 0, w_rowstride: int = 0, w_batchstride: int = 0, alpha: float = 0.0, dst2: int = 0, t_col0: int = 0,
            t_ld: int = 0, w_rows: int = 0, row3: Optional[int] = None, halo: Optional[int] = None, src_gn_swish: int = 0,
            src_gamma: int = 0, src_beta: int = 0, w2: int = 0, tb2: int = 0, dst_res: Optional[Act] = None,
-           split: int = 0, src_lo_off: int = 0, w_lo_off: int = 0, dst_crop: int = 0):
+           split: int = 0, src_lo_off: int = 0, w_lo_off: int = 0, dst_crop: int = 0, phases: int = 0):
     H, W = (dst.H // 2, dst.W // 2) if dst_up else (dst.H, dst.W)
     p = {"UCDIR_TC_P_SRC0": src0.ptr, "UCDIR_TC_P_W": w, "UCDIR_TC_P_TB": tb, "UCDIR_TC_P_DST": dst.ptr}
     if src1 is not None: p["UCDIR_TC_P_SRC1"] = src1.ptr
@@ -498,6 +498,7 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
         i["UCDIR_TC_I_SRC_LO_OFF"], i["UCDIR_TC_I_W_LO_OFF"] = src_lo_off, w_lo_off
     if dst2: p["UCDIR_TC_P_DST2"] = dst2
     if dst_crop: i["UCDIR_TC_I_DST_CROP"] = dst_crop
+    if phases: i["UCDIR_TC_I_PHASES"] = phases
     if src_gn_swish:
         p["UCDIR_TC_P_SRC_GAMMA"], p["UCDIR_TC_P_SRC_BETA"], p["UCDIR_TC_P_STATS0"] = src_gamma, src_beta, src0.stats
         i["UCDIR_TC_I_SRC_GN_SWISH"] = 1
@@ -515,6 +516,8 @@ where its preconditions hold).  On unless UCDIR_TC_ROW3=0."""
 _TC_FUSE_RES = 0 if os.environ.get("UCDIR_TC_FUSE_RES", "1") == "0" else 1
 """Fuse a block's 1x1 res_conv into its conv1 launch where the halo schedule applies (csrc/ucdir_dhalo.cu, RES).  On unless
 UCDIR_TC_FUSE_RES=0."""
+_TC_FUSE_PHASES = 0 if os.environ.get("UCDIR_TC_FUSE_PHASES", "1") == "0" else 1
+"""One launch for the four phase convolutions of an Upsample layer (UCDIR_TC_I_PHASES).  UCDIR_TC_FUSE_PHASES=0: four launches."""
 _TC_FLASH = 0 if os.environ.get("UCDIR_TC_FLASH", "1") == "0" else 1
 """Fused attention core (csrc/ucdir_attn.cu: QK^T -> online softmax -> PV in one kernel, scores / probabilities never in HBM) for
 the 512-channel attention layers of the bf16 path.  UCDIR_TC_FLASH=0 keeps the three-launch form (score GEMM, softmax, PV GEMM)."""
@@ -910,10 +913,13 @@ class UNetEngine:
                 elif isinstance(layer, U.Downsample):
                     put3(name, pack_tc_dense(layer.conv.weight, layer.conv.bias, _tc_nt(layer.conv.out_channels), **sp))
                 elif isinstance(layer, U.Upsample):
+                    blocks = []
                     for py in range(2):
                         for px in range(2):
                             w, tb = pack_tc_up_phase(layer.conv.weight, layer.conv.bias, py, px, _tc_nt(layer.conv.out_channels), **sp)
                             ws.put("%s.p%d%d.tcw" % (name, py, px), w); ws.put("%s.p%d%d.tb" % (name, py, px), tb)
+                            blocks.append(w)
+                    ws.put(name + ".ph.tcw", torch.cat(blocks, dim=0))       # the four phases stacked along N: one launch (PHASES = 4)
         fc = m.final_conv
         put3("final", pack_tc_dense(fc[3].weight, fc[3].bias, 16, **sp))
         ws.put("zeros", torch.zeros(65536, dtype=F32, device=ws.device))    # bias table of the attention GEMMs
@@ -1091,11 +1097,15 @@ class UNetEngine:
             name = "ups.%d" % k
             if isinstance(layer, U.Upsample):
                 y = bld.new(x.C, x.H * 2, x.W * 2)
-                for py in range(2):
-                    for px in range(2):
-                        _tc_op(ol, split=sp, src0=x, w=ws.ptr("%s.p%d%d.tcw" % (name, py, px)), tb=ws.ptr("%s.p%d%d.tb" % (name, py, px)),
-                               nty=2, ntx=2, oy0=py - 1, ox0=px - 1, dst=y, ntot=x.C, B=BT, nt=_tc_nt(x.C), dst_up=1,
-                               dst_py=py, dst_px=px)
+                if _TC_FUSE_PHASES:
+                    _tc_op(ol, split=sp, src0=x, w=ws.ptr(name + ".ph.tcw"), tb=ws.ptr(name + ".p00.tb"), nty=2, ntx=2, oy0=-1, ox0=-1,
+                           dst=y, ntot=x.C, B=BT, nt=_tc_nt(x.C), dst_up=1, phases=4)
+                else:
+                    for py in range(2):
+                        for px in range(2):
+                            _tc_op(ol, split=sp, src0=x, w=ws.ptr("%s.p%d%d.tcw" % (name, py, px)), tb=ws.ptr("%s.p%d%d.tb" % (name, py, px)),
+                                   nty=2, ntx=2, oy0=py - 1, ox0=px - 1, dst=y, ntot=x.C, B=BT, nt=_tc_nt(x.C), dst_up=1,
+                                   dst_py=py, dst_px=px)
                 bld.release(x)
                 x = y
             else:
