@@ -7,6 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# The library's default precision is "fp32_tc" (tensor cores, fp32 tolerance).  Tests that do not pick a mode themselves run the
+# SIMT "fp32" graph -- the independent arithmetic the tensor-core modes are also compared with; the tensor-core modes are selected
+# explicitly (set_precision / parametrised fixtures).
+os.environ.setdefault("UCDIR_PRECISION", "fp32")
 
 
 def pytest_configure(config):

@@ -19,7 +19,9 @@ def _net(name, sid_weights):
     torch.manual_seed(1234)
     net = define_G({"model": dict(ucdir_b200.SID_MODEL_OPT, diffusion_name=name)})
     assert all(torch.equal(v, sd[k]) for k, v in net.state_dict().items())
-    return net.to("cuda")
+    net = net.to("cuda")
+    net.denoise_fn.engine().set_precision("fp32_tc")          # the library's default mode (tests/conftest.py pins the SIMT one otherwise)
+    return net
 
 
 def _images(n, h=40, w=48, seed=31):

@@ -585,7 +585,7 @@ class UNetEngine:
         self._geo_cache: Dict[tuple, Geometry] = {}
         self._params: Optional[list] = None
         self._packed_version = -1
-        self.precision = os.environ.get("UCDIR_PRECISION", "fp32")    # see PRECISIONS
+        self.precision = os.environ.get("UCDIR_PRECISION", "fp32_tc")    # see PRECISIONS; default = the tensor-core mode that meets the reference's fp32 tolerance
         if self.precision not in PRECISIONS:
             raise ValueError("UCDIR_PRECISION must be one of %s" % (PRECISIONS,))
         self.shard_mode = os.environ.get("UCDIR_SHARD", "none")       # "none" | "tiles" | "batch" 
@@ -1578,7 +1578,7 @@ class PredictorEngine:
         self.m = module
         self.ws: Optional[WeightStore] = None
         self._plans: Dict[tuple, tuple] = {}
-        self.mode = "fp32" if os.environ.get("UCDIR_PRECISION", "fp32") == "fp32" else "tc"
+        self.mode = "fp32" if os.environ.get("UCDIR_PRECISION", "fp32_tc") == "fp32" else "tc"
 
     def set_mode(self, mode: str):
         if mode not in ("fp32", "tc"):
