@@ -536,17 +536,24 @@ def _tile_forwards(O, sd, lay, sched, x6, gd, t, chunk=1):
             O.unet_naiveforward(sd, "denoise_fn.", lay, xb, torch.full((xb.shape[0], 1), lvl, device=xb.device), gd[k:k + chunk])
 
 
-def cpu_baseline(args, sample_tiles):
+def cpu_baseline(args, sample_tiles, budget_s=15.0):
+    """The oracle port on all host cores, a bounded sample of the step's tile forwards (about `budget_s` seconds of CPU work; the
+    whole step when it fits)."""
     torch.set_num_threads(os.cpu_count() or 1)
     O, sd, lay, sched = _ref_setup(args.workload)
     geo = _tile_geometry(args.workload)
     n_tiles = geo.n_tiles
-    sample_tiles = min(sample_tiles, n_tiles)
     g = torch.Generator().manual_seed(INPUT_SEED)
+    x6 = torch.rand(1, 6, geo.TH, geo.TW, generator=g) * 2 - 1
+    gd = torch.rand(1, 3, geo.TH, geo.TW, generator=g) * 2 - 1
+    t0 = time.perf_counter()
+    _tile_forwards(O, sd, lay, sched, x6, gd, 10)                  # warm-up (thread pool, allocator) + cost probe
+    t_probe = time.perf_counter() - t0
+    if sample_tiles <= 0:
+        sample_tiles = int(budget_s / max(t_probe, 1e-3))
+    sample_tiles = max(1, min(sample_tiles, n_tiles))
     x6 = torch.rand(sample_tiles, 6, geo.TH, geo.TW, generator=g) * 2 - 1
     gd = torch.rand(sample_tiles, 3, geo.TH, geo.TW, generator=g) * 2 - 1
-    if geo.TH * geo.TW <= 512 * 512:
-        _tile_forwards(O, sd, lay, sched, x6[:1], gd[:1], 10)      # warm-up (thread pool, allocator)
     t0 = time.perf_counter()
     _tile_forwards(O, sd, lay, sched, x6, gd, 10)
     dt = time.perf_counter() - t0
@@ -727,9 +734,6 @@ def main():
     elif args.impl == "torch_gpu":
         run_torch_gpu(args)
     else:
-        if args.cpu_tiles <= 0:
-            wl = WORKLOADS[args.workload]
-            args.cpu_tiles = 4 if (wl["force"] and wl["skip"] <= 256) or wl["side"] <= 256 else 1
         run_ours(args)
 
 

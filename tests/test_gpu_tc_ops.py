@@ -100,6 +100,25 @@ def dense_case(seed, B, H, W, C0, C1, Cout, ks, gn, act_, res, stride=1, row3=0,
                  res=act(t["res"], Cout, H, W) if res else None, dst=act(t["dst"], Cout, H, W, t["dstats"]), ntot=Cout, B=B, nt=nt,
                  row3=row3, halo=halo, kc=kc)
         return ol
+
+    def torch_ref():
+        """The same layer through torch.nn.functional in the reference's own form (GroupNorm(1, C) -> conv -> Swish -> + residual,
+        model/ucdir.py:109-111) on the same bf16 inputs, fp32 weights: independent of the op interpreter and of the weight packer."""
+        F = torch.nn.functional
+        x = c.t["x0"].float()
+        if C1:
+            x = torch.cat([x, c.t["x1"].float()], dim=-1)
+        x = x.permute(0, 3, 1, 2)
+        if gn:
+            x = F.group_norm(x, 1, gamma, beta, eps=1e-5)
+        y = F.conv2d(x, w, bias, stride=stride, padding=ks // 2)
+        if act_ == 1:
+            y = y * torch.sigmoid(y)
+        y = y.permute(0, 2, 3, 1)
+        if res:
+            y = y + c.t["res"].float()
+        return y
+    build.torch_ref = torch_ref
     return c, build
 
 
@@ -118,6 +137,7 @@ def test_tc_dense(cfg):
     host, dev = run_both(c, build)
     assert_close(dev["dst"], host["dst"], "dst")
     assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
+    assert_close(dev["dst"], build.torch_ref(), "dst vs torch.nn.functional", rtol=3e-2, atol=3e-2)
 
 
 @pytest.mark.parametrize("cfg", [
@@ -142,6 +162,7 @@ def test_tc_dense_halo(cfg):
     host, dev = run_both(c, build)
     assert_close(dev["dst"], host["dst"], "dst")
     assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
+    assert_close(dev["dst"], build.torch_ref(), "dst vs torch.nn.functional", rtol=3e-2, atol=3e-2)
     if cfg.get("fuse_res"):
         assert float(host["dres"].abs().max()) > 0.1
         assert_close(dev["dres"], host["dres"], "fused res_conv")
@@ -202,6 +223,15 @@ def test_tc_grouped_mix(C, B, H, W, halo):
     host, dev = run_both(c, build)
     assert_close(dev["dst"], host["dst"], "mix dst")
     assert_close(dev["dstats"], host["dstats"], "stats", rtol=2e-3, atol=2e-3)
+    # the integration module through torch.nn.functional in the reference's own form (model/ucdir.py:112,135-140): independent
+    # of the op interpreter and of the weight packer
+    F = torch.nn.functional
+    h = F.group_norm(c.t["h1"].float().permute(0, 3, 1, 2), 1, gamma, beta, eps=1e-5)
+    hset = F.conv2d(h, w, bias, padding=1, groups=8).view(B, C, 8, H, W)
+    att_sp = c.t["att"].permute(0, 3, 1, 2) * c.t["attw"].view(B, 8, 1, 1)
+    hh = torch.sum(hset * att_sp.unsqueeze(1), dim=2)
+    want = (hh * torch.sigmoid(hh)).permute(0, 2, 3, 1) + c.t["res"].float()
+    assert_close(dev["dst"], want, "mix dst vs torch.nn.functional", rtol=3e-2, atol=3e-2)
 
 
 def test_tc_upsample_phases_equal_upsample_then_conv():
