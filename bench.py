@@ -546,8 +546,9 @@ def cpu_baseline(args, sample_tiles, budget_s=15.0):
     g = torch.Generator().manual_seed(INPUT_SEED)
     x6 = torch.rand(1, 6, geo.TH, geo.TW, generator=g) * 2 - 1
     gd = torch.rand(1, 3, geo.TH, geo.TW, generator=g) * 2 - 1
+    _tile_forwards(O, sd, lay, sched, x6, gd, 10)                  # warm-up (thread pool, allocator)
     t0 = time.perf_counter()
-    _tile_forwards(O, sd, lay, sched, x6, gd, 10)                  # warm-up (thread pool, allocator) + cost probe
+    _tile_forwards(O, sd, lay, sched, x6, gd, 10)                  # cost probe
     t_probe = time.perf_counter() - t0
     if sample_tiles <= 0:
         sample_tiles = int(budget_s / max(t_probe, 1e-3))
