@@ -17,10 +17,13 @@ run() {  # N, workload, steps, output tag
   fi
   echo "$4 N=$1 rc=$?"; tail -1 $O/$4_$1.err | cut -c1-200; python -c "import json; d=json.load(open('$O/$4_$1.json')); print('   value', d['value'], 'e2e', d['e2e']['value'], 'ms/step', d['ms_per_step'], 'frac', d['roofline']['frac'], 'frac_of_step', d['roofline']['frac_of_step'], d['collective'])"
 }
+# SKIP1=1: leave the single-GPU runs to a 1-GPU visit (an 8-GPU box is charged 8x while one GPU works)
 for N in 1 2 4 8; do
-  if [ $N -le $NG ]; then run $N c3_1024_tile128 ${STEPS:-20} scale; fi
+  if [ $N -le $NG ] && ! { [ $N -eq 1 ] && [ "${SKIP1:-0}" = "1" ]; }; then run $N c3_1024_tile128 ${STEPS:-20} scale; fi
 done
-run 1 c5_sid_512_b32 5 c5; run $NG c5_sid_512_b32 5 c5
-run 1 c2_256_b8 10 c2; run $NG c2_256_b8 10 c2
+[ "${SKIP1:-0}" = "1" ] || run 1 c5_sid_512_b32 5 c5
+run $NG c5_sid_512_b32 5 c5
+[ "${SKIP1:-0}" = "1" ] || run 1 c2_256_b8 10 c2
+run $NG c2_256_b8 10 c2
 grep -h "NVLS\|Connected all" $O/nccl_scale_$NG.*.log 2>/dev/null | head -3
 rm -f $O/nccl_*.log
