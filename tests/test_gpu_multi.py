@@ -81,3 +81,43 @@ def test_sharded_equals_unsharded_nccl():
            "--master-port", "29611", path]
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-4000:]
+
+
+SECOND_DEVICE = r'''
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.environ["UCDIR_ROOT"])
+import ucdir_b200
+from ucdir_b200.model.networks import define_G
+# one process, two GPUs: the current device stays cuda:0 while the modules live on cuda:0 and cuda:1 (ADVICE r1: function attributes
+# and the SM count are per device; the library launches on the CURRENT device with a stream handle of the module's device)
+assert torch.cuda.current_device() == 0
+outs = []
+for dev in ("cuda:0", "cuda:1"):
+    for precision in ("bf16", "fp32_tc"):
+        torch.manual_seed(1234)
+        net = define_G({"model": ucdir_b200.SID_MODEL_OPT}).to(dev)
+        net.denoise_fn.engine().set_precision(precision)
+        net.set_new_noise_schedule(dict(schedule="linear", n_timestep=2, linear_start=1e-6, linear_end=0.4), torch.device(dev))
+        g = torch.Generator().manual_seed(1)
+        x = (torch.rand(1, 3, 72, 88, generator=g) * 2 - 1).to(dev)
+        ng = torch.Generator().manual_seed(2)
+        net._noise_source = lambda shape: torch.randn(shape, generator=ng)
+        out = net.super_resolution(x, False)
+        assert out.device == torch.device(dev) and torch.isfinite(out).all()
+        assert torch.cuda.current_device() == 0
+        outs.append((dev, precision, out.cpu()))
+for k in range(2):
+    a, b = outs[k][2], outs[k + 2][2]
+    err = (a - b).abs().max().item()
+    print(outs[k][1], "cuda:0 vs cuda:1 max abs diff", err)
+    assert err <= (2e-2 if outs[k][1] == "bf16" else 1e-5), err
+print("second device ok")
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_module_on_a_second_device_of_the_same_process():
+    env = dict(os.environ, UCDIR_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-c", SECOND_DEVICE], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "second device ok" in r.stdout, r.stdout[-4000:]
