@@ -28,6 +28,14 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+// Timing probes (wrong results, never part of the product build; UCDIR_NVCC_EXTRA=-DUCDIR_MIX_PROBE=n): 2 = MMAs with half the
+// columns (half the B-operand bytes and tensor work: what cta_group::2 would leave per CTA), 3 = epilogue without its TMEM reads.
+// Round-2 result: probe 2 changes the C = 64 / 128 launches by -4 % / -5 % only -- these kernels are not MMA bound.
+#ifndef UCDIR_MIX_PROBE
+#define UCDIR_MIX_PROBE 1
+#endif
+#define UCDIR_MIX_PROBE_NDIV (UCDIR_MIX_PROBE == 2 ? 2 : 1)
+
 namespace ucdir {
 
 struct MixParams {
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(S::NSUB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((S::NSUB / UCDIR_MIX_PROBE_NDIV) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       UnitCursor cur; cur.init(u0, p.m_tiles, p.tiles_x, p.tiles_y);
       int stage = 0; uint32_t phase = 0;
       int slot = 0; uint32_t sph = 0;
@@ -328,14 +336,19 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
         // 16 columns (two output channels) per step; the TMEM load of step k+1 is in flight during the math of step k
         uint32_t rbuf[2][16];
         float4 cbuf[2][4];                                  // additive terms of step k / k+1 (read ahead of the TMEM wait)
-        tmem_ld16(taddr, rbuf[0]);
+#if UCDIR_MIX_PROBE == 3           // timing probe only: the epilogue without its TMEM reads (math, table reads, stores and barriers stay)
+#define MX_TMEM_LD16(addr, dst) do { _Pragma("unroll") for (int z_ = 0; z_ < 16; ++z_) (dst)[z_] = __float_as_uint((float)(lane + z_)); } while (0)
+#else
+#define MX_TMEM_LD16(addr, dst) tmem_ld16(addr, dst)
+#endif
+        MX_TMEM_LD16(taddr, rbuf[0]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) cbuf[0][j] = ct[j];
         tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (k < 3) {
-            tmem_ld16(taddr + 16 * (k + 1), rbuf[(k + 1) & 1]);
+            MX_TMEM_LD16(taddr + 16 * (k + 1), rbuf[(k + 1) & 1]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) cbuf[(k + 1) & 1][j] = ct[4 * (k + 1) + j];
           }
