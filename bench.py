@@ -209,7 +209,10 @@ def dump_op_profile(path, step_ops, prof, steps, K):
             r.update(B=g("B"), H=g("H"), W=g("W"), C0=g("C0"), C1=g("C1"), N=g("NTOT"), taps=g("NTY") * g("NTX"), stride=g("STRIDE"),
                      groups=g("GROUPS"), KC=g("KC"), NT=g("NT"), mode=g("MODE"), gn=g("GN"), split=g("SPLIT"))
             cin = (g("C0") + g("C1")) // g("GROUPS")
-            r["gflop"] = round(2e-9 * g("B") * g("H") * g("W") * g("NTY") * g("NTX") * cin * g("NTOT"), 2)
+            phases = max(g("PHASES"), 1)                      # fused upsample: four 2x2-tap phase convolutions in one launch
+            r["gflop"] = round(2e-9 * g("B") * g("H") * g("W") * g("NTY") * g("NTX") * cin * g("NTOT") * phases, 2)
+            if phases > 1:
+                r["phases"] = phases
         elif "UCDIR_OP_TC_ATTN" in K and kind == K["UCDIR_OP_TC_ATTN"] and "UCDIR_ATTN_I_N" in K:
             g = lambda n: int(o.i[K["UCDIR_ATTN_I_" + n]])
             r.update(B=g("B"), N=g("N"), C=g("C"))
