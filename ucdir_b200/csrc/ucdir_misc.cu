@@ -184,10 +184,25 @@ __global__ void __launch_bounds__(256) gather_tiles_kernel(const float* __restri
   for (int c = 0; c < CB; ++c) v[CA + c] = __ldg(srcB + ((size_t)img * CB + c) * plane + sp);
   if (BF16 == 2) {               // (hi, lo) plane pairs for the fp32-tolerance tensor-core mode: [hi: CD | lo: CD] per pixel
     __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dstv) + idx * 2 * CD;
-    for (int c = 0; c < CD; ++c) {
-      const __nv_bfloat16 hi = __float2bfloat16(v[c]);
-      d[c] = hi;
-      d[CD + c] = __float2bfloat16(v[c] - __bfloat162float(hi));
+    if (CD == 16) {               // 64 bytes per pixel: four 16-byte stores
+      __align__(16) __nv_bfloat162 oh[8];
+      __align__(16) __nv_bfloat162 ol[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        oh[c] = __floats2bfloat162_rn(v[2 * c], v[2 * c + 1]);
+        const float2 r = __bfloat1622float2(oh[c]);
+        ol[c] = __floats2bfloat162_rn(v[2 * c] - r.x, v[2 * c + 1] - r.y);
+      }
+      reinterpret_cast<uint4*>(d)[0] = reinterpret_cast<const uint4*>(oh)[0];
+      reinterpret_cast<uint4*>(d)[1] = reinterpret_cast<const uint4*>(oh)[1];
+      reinterpret_cast<uint4*>(d)[2] = reinterpret_cast<const uint4*>(ol)[0];
+      reinterpret_cast<uint4*>(d)[3] = reinterpret_cast<const uint4*>(ol)[1];
+    } else {
+      for (int c = 0; c < CD; ++c) {
+        const __nv_bfloat16 hi = __float2bfloat16(v[c]);
+        d[c] = hi;
+        d[CD + c] = __float2bfloat16(v[c] - __bfloat162float(hi));
+      }
     }
   } else if (BF16) {
     __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dstv) + idx * CD;
