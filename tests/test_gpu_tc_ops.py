@@ -234,6 +234,60 @@ def test_tc_grouped_mix(C, B, H, W, halo):
     assert_close(dev["dst"], want, "mix dst vs torch.nn.functional", rtol=3e-2, atol=3e-2)
 
 
+def split_planes(t32):
+    """fp32 [..., C] -> bf16 [..., 2C] = [hi | lo] (UCDIR_TC_I_SPLIT activation layout)."""
+    hi, lo = E.split_hi_lo(t32)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def join_planes(t, C):
+    return t[..., :C].float() + t[..., C:2 * C].float()
+
+
+@pytest.mark.parametrize("halo", [0, 1], ids=["streamed", "halo"])
+@pytest.mark.parametrize("C,B,H,W", [(64, 2, 16, 16), (128, 1, 24, 16), (64, 1, 128, 128), (128, 3, 64, 64), (64, 2, 36, 20), (128, 2, 18, 18)])
+def test_tc_grouped_mix_split(C, B, H, W, halo):
+    """fp32_tc form of the integration-module conv: (hi, lo) plane pairs, three passes per tap, fp32 epilogue.  halo=1 is
+    mix_halo_kernel<CG, SPLIT> (hi and lo halo boxes in a three-stage ring, both weight planes resident); both schedules are held
+    to the fp32-class tolerance against torch.nn.functional in the reference's own form (model/ucdir.py:112,135-140)."""
+    g = torch.Generator().manual_seed(7 * C + H)
+    c = Case()
+    h1 = torch.nn.functional.silu(rnd(g, B, H, W, C))
+    c.add("h1", split_planes(h1))
+    w = rnd(g, 8 * C, C // 8, 3, 3, scale=1.0 / np.sqrt(C // 8 * 9))
+    bias = rnd(g, 8 * C, scale=0.1)
+    gamma, beta = 1 + 0.3 * rnd(g, C), 0.2 * rnd(g, C)
+    kc, kb, nt, nsplit = E.tc_mix_tiling(C)
+    wp, tb, tg = E.pack_tc_grouped(w, bias, 8, kb, gamma, beta, split=True)
+    h1v = join_planes(c.t["h1"], C)                       # the value the kernels see (16 mantissa bits)
+    c.add("w", wp).add("tb", tb).add("tg", tg).add("s0", stats_of(h1v))
+    res = rnd(g, B, H, W, C)
+    c.add("att", rnd(g, B, H, W, 8)).add("attw", rnd(g, B, 8)).add("res", split_planes(res))
+    c.add("dst", torch.zeros(B, H, W, 2 * C, dtype=BF)).add("dstats", torch.zeros(B, 2, dtype=torch.float64))
+
+    def sact(t, stats=None):
+        return E.Act(t, C, H, W, stats.data_ptr() if stats is not None else 0, True, True)
+
+    def build(t):
+        ol = E.OpList()
+        E._tc_op(ol, split=1, src0=sact(t["h1"], t["s0"]), w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), tg=t["tg"].data_ptr(),
+                 gn=1, ncls=9, groups=8, kc=kc, kb=kb, nsplit=nsplit, nt=nt, mode=1, att=t["att"].data_ptr(), attw=t["attw"].data_ptr(),
+                 attw_stride=8, res=sact(t["res"]), dst=sact(t["dst"], t["dstats"]), ntot=8 * C, B=B, halo=halo)
+        return ol
+    assert _lib.tc_schedule(build(c.on("cpu")).array()[0]) == halo
+    host, dev = run_both(c, build)
+    got = join_planes(dev["dst"], C)
+    assert_close(got, join_planes(host["dst"], C), "split mix dst vs interpreter", rtol=1e-3, atol=1e-4)
+    assert_close(dev["dstats"], host["dstats"], "stats", rtol=1e-5, atol=1e-5)
+    F = torch.nn.functional
+    h = F.group_norm(h1v.permute(0, 3, 1, 2), 1, gamma, beta, eps=1e-5)
+    hset = F.conv2d(h, w, bias, padding=1, groups=8).view(B, C, 8, H, W)
+    att_sp = c.t["att"].permute(0, 3, 1, 2) * c.t["attw"].view(B, 8, 1, 1)
+    hh = torch.sum(hset * att_sp.unsqueeze(1), dim=2)
+    want = (hh * torch.sigmoid(hh)).permute(0, 2, 3, 1) + join_planes(c.t["res"], C)
+    assert_close(got, want, "split mix dst vs torch.nn.functional", rtol=1e-3, atol=1e-4)
+
+
 def test_tc_upsample_phases_equal_upsample_then_conv():
     """Four 2x2-tap phase convolutions == nearest-2x + conv3x3 (model/ucdir.py:53-60), checked against torch."""
     g = torch.Generator().manual_seed(9)

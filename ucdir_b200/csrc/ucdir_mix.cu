@@ -29,7 +29,8 @@
 #include "tc_ptx.cuh"
 
 // Timing probes (wrong results, never part of the product build; UCDIR_NVCC_EXTRA=-DUCDIR_MIX_PROBE=n): 2 = MMAs with half the
-// columns (half the B-operand bytes and tensor work: what cta_group::2 would leave per CTA), 3 = epilogue without its TMEM reads.
+// columns (half the B-operand bytes and tensor work: what cta_group::2 would leave per CTA), 3 = epilogue without its TMEM reads,
+// 4 = no epilogue work at all (the MMA side alone).
 // Round-2 result: probe 2 changes the C = 64 / 128 launches by -4 % / -5 % only -- these kernels are not MMA bound.
 #ifndef UCDIR_MIX_PROBE
 #define UCDIR_MIX_PROBE 1
@@ -46,6 +47,7 @@ struct MixParams {
   int B, H, W, Ntot;
   int tiles_x, tiles_y, m_tiles, n_units;
   int resC, dstC, attwStride;
+  int a_lo, res_lo, dst_lo;      // SPLIT: element offset of the lo plane inside a source / residual / destination pixel row
   double gn_count; float eps;
 };
 
@@ -53,7 +55,6 @@ constexpr int MX_TW = 8, MX_TH = 16;                       // M tile: 8 x 16 out
 constexpr int MX_BW = MX_TW + 2, MX_BH = MX_TH + 2;        // halo box
 constexpr int MX_A_BYTES = MX_BW * MX_BH * 128;            // 23040: 180 pixel rows of 64 bf16 channels
 constexpr int MX_A_STAGE = (MX_A_BYTES + 1023) & ~1023;    // 23552
-constexpr int MX_ASTAGES = 2;
 constexpr int MX_WRES = 147456;                            // resident weight block of one column set
 constexpr int MX_EPI_WARPS = 16, MX_FIRST_EPI_WARP = 4;
 constexpr int MX_THREADS = 32 * (MX_FIRST_EPI_WARP + MX_EPI_WARPS);
@@ -61,8 +62,14 @@ constexpr int MX_THREADS = 32 * (MX_FIRST_EPI_WARP + MX_EPI_WARPS);
 // warpgroups can grow to 104 (8 x 512) -- the pool only holds what the CTA released (checked on the host before launch)
 constexpr int MX_REGS_LOW = 40, MX_REGS_HIGH = 104;
 
-template <int CG>
+// SPLIT (fp32_tc): activations are (hi, lo) bf16 plane pairs and the weights [W_hi | W_hi | W_lo] per tap; an item
+// is three passes over the nine taps -- lo box x W_hi, hi box x W_hi, hi box x W_lo -- into one fp32 accumulator.  Both weight
+// planes stay resident, so a column set is ONE 256-column item (2 x 72 KB), the hi and lo boxes of a tile travel as two stages of
+// a three-deep ring (the lo box is consumed first: while the 18 hi MMAs run, the next tile's lo box is already resident and its
+// hi box is in flight), and the epilogue works in fp32 (exact Swish, residual = hi + lo, (hi, lo) stores).
+template <int CG, bool SPLIT = false>
 struct MixCfg {
+  static_assert(!(SPLIT && CG == 32), "SPLIT: both weight planes of a C = 256 item exceed shared memory");
   static constexpr int C = 8 * CG;                         // channels; columns per group NG = 8C / 8 = C
   static constexpr int NG = C;
   // MMAs per tap and 256-column item.  C = 64: groups 2j and 2j+1 live in the same 32-byte K slice of the pixel row (their
@@ -72,15 +79,18 @@ struct MixCfg {
   static constexpr int NSUB = 256 / NSPLIT;                // columns per MMA
   static constexpr int KB = CG < 16 ? 16 : CG;             // K elements per tap and group (C = 64: 8 real + 8 foreign, zero weights)
   static constexpr int KSTEPS = KB / 16;
-  static constexpr int IPB = CG == 32 ? 1 : 2;             // items that share one halo box (= one 64-channel chunk)
+  static constexpr int IPB = (CG == 32 || SPLIT) ? 1 : 2;  // items that share one halo box (= one 64-channel chunk)
   static constexpr int SETCOLS = 256 * IPB;
-  static constexpr int BSLAB = 256 * KB * 2;               // one tap's weight slab of one item
-  static_assert(IPB * 9 * BSLAB == MX_WRES, "resident weight block");
+  static constexpr int BSLAB = 256 * KB * 2;               // one tap's weight slab of one item (and plane)
+  static constexpr int NPL = SPLIT ? 2 : 1;                // resident weight planes: slab index = item * 9 + tap, SPLIT: tap * 2 + plane
+  static constexpr int NBOX = SPLIT ? 2 : 1;               // halo boxes per unit (SPLIT: lo plane, then hi plane)
+  static constexpr int ASTAGES = SPLIT ? 3 : 2;
+  static_assert(IPB * 9 * NPL * BSLAB == MX_WRES, "resident weight block");
   static constexpr int CTAB_BYTES = 9 * SETCOLS * 4;
-  static constexpr int OFF_W = MX_ASTAGES * MX_A_STAGE;
+  static constexpr int OFF_W = ASTAGES * MX_A_STAGE;
   static constexpr int OFF_CTAB = OFF_W + MX_WRES;
-  static constexpr int OFF_RES = OFF_CTAB + CTAB_BYTES;   // residual staging: [epilogue warp][2][32 lanes] x 16 bytes (cp.async)
-  static constexpr int OFF_BARS = OFF_RES + MX_EPI_WARPS * 2 * 32 * 16;
+  static constexpr int OFF_RES = OFF_CTAB + CTAB_BYTES;   // residual staging: [epilogue warp][2][32 lanes] x 16 bytes (cp.async); SPLIT: none
+  static constexpr int OFF_BARS = OFF_RES + (SPLIT ? 0 : MX_EPI_WARPS * 2 * 32 * 16);
   static constexpr int TOTAL = OFF_BARS + 128 + 1024 /* align slack */;
   static_assert(TOTAL <= 227 * 1024, "shared memory");
   static_assert(OFF_W % 1024 == 0, "weight block alignment");
@@ -110,10 +120,11 @@ struct UnitCursor {
   }
 };
 
-template <int CG>
+template <int CG, bool SPLIT>
 __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                  const __grid_constant__ CUtensorMap mapB, const MixParams p) {
-  using S = MixCfg<CG>;
+  using S = MixCfg<CG, SPLIT>;
+  constexpr int MX_ASTAGES = S::ASTAGES;
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer arithmetic on the __shared__ array (no integer round trip) so table reads compile to LDS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -162,22 +173,31 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
           if (elect_one()) {
             mbar_expect_tx(bfull, (uint32_t)MX_WRES);
 #pragma unroll 1
-            for (int i = 0; i < S::IPB * 9; ++i) {
-              const int item = i / 9, tap = i - item * 9;
-              tma_load_2d(&mapB, bfull, wres + i * S::BSLAB, tap * S::KB, cur.set * S::SETCOLS + item * 256);
+            for (int i = 0; i < S::IPB * 9 * S::NPL; ++i) {
+              if (SPLIT) {                                   // packed row per tap: [W_hi | W_hi | W_lo]; resident: [tap][W_hi, W_lo]
+                const int tap = i >> 1, plane = i & 1;
+                tma_load_2d(&mapB, bfull, wres + i * S::BSLAB, (tap * 3 + plane * 2) * S::KB, cur.set * S::SETCOLS);
+              } else {
+                const int item = i / 9, tap = i - item * 9;
+                tma_load_2d(&mapB, bfull, wres + i * S::BSLAB, tap * S::KB, cur.set * S::SETCOLS + item * 256);
+              }
             }
           }
           __syncwarp();
           cur_set = cur.set;
         }
-        mbar_wait(&a_empty[stage], phase ^ 1);
-        if (elect_one()) {
-          const int chunk = ((cur.set * S::SETCOLS) / S::NG * CG) >> 6;          // 64-channel chunk that holds the set's groups
-          mbar_expect_tx(&a_full[stage], (uint32_t)MX_A_BYTES);
-          tma_load_4d(&mapA, &a_full[stage], smem + stage * MX_A_STAGE, chunk * 64, cur.tx * MX_TW - 1, cur.ty * MX_TH - 1, cur.img);
+#pragma unroll
+        for (int b = 0; b < S::NBOX; ++b) {                  // SPLIT: the lo box first (it is consumed first)
+          mbar_wait(&a_empty[stage], phase ^ 1);
+          if (elect_one()) {
+            const int chunk = ((cur.set * S::SETCOLS) / S::NG * CG) >> 6;          // 64-channel chunk that holds the set's groups
+            mbar_expect_tx(&a_full[stage], (uint32_t)MX_A_BYTES);
+            tma_load_4d(&mapA, &a_full[stage], smem + stage * MX_A_STAGE, chunk * 64 + ((SPLIT && b == 0) ? p.a_lo : 0), cur.tx * MX_TW - 1,
+                        cur.ty * MX_TH - 1, cur.img);
+          }
+          __syncwarp();
+          if (++stage == MX_ASTAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == MX_ASTAGES) { stage = 0; phase ^= 1; }
         cur.next(p.tiles_x, p.tiles_y, p.B);
       }
     } else if (warp == 1) {
@@ -192,46 +212,90 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
         const int set = cur.set;
         cur.next(p.tiles_x, p.tiles_y, p.B);
         const bool last_of_set = (cur.set != set) && (u + 1 < u1);
-        mbar_wait(&a_full[stage], phase);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * MX_A_STAGE);
+        if constexpr (!SPLIT) {
+          mbar_wait(&a_full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * MX_A_STAGE);
 #pragma unroll
-        for (int item = 0; item < S::IPB; ++item) {
+          for (int item = 0; item < S::IPB; ++item) {
+            mbar_wait(&tmem_empty[slot], sph ^ 1);           // the epilogue has drained this accumulator
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t tacc = tmem_base + (uint32_t)(slot * 256);
+              const int g0 = (set * S::SETCOLS + item * 256) / S::NG;            // first group of the item
+              constexpr int GPS = S::NSUB / S::NG;                                // groups per MMA
+              constexpr uint32_t a_hi = desc_hi(MX_BW * 128, 2u), b_hi = desc_hi(8 * S::KB * 2, S::KB * 2 == 64 ? 4u : 6u);
+              // the 32-byte K slice of the 128-byte pixel row that holds the first group of split sp, as a descriptor offset
+              uint32_t a_lo0[S::NSPLIT];
+#pragma unroll
+              for (int sp = 0; sp < S::NSPLIT; ++sp) a_lo0[sp] = desc_lo(a_base) + (uint32_t)(((((g0 + sp * GPS) * CG * 2) & 127) & ~31) >> 4);
+              uint32_t b_lo = desc_lo(smem_u32(wres + item * 9 * S::BSLAB));
+#pragma unroll 1                                            // one 32-bit add per descriptor and tap: warpgroup 0 runs on 40 registers
+              for (int tap = 0; tap < 9; ++tap) {
+                const int ty = tap / 3, tx = tap - ty * 3;
+                const uint32_t a_tap = (uint32_t)(((ty * MX_BW + tx) * 128) >> 4);
+#pragma unroll
+                for (int sp = 0; sp < S::NSPLIT; ++sp) {
+#pragma unroll
+                  for (int k = 0; k < S::KSTEPS; ++k)
+                    umma_bf16_lohi(tacc + (uint32_t)(sp * S::NSUB), a_lo0[sp] + a_tap + (uint32_t)(k * 2), a_hi,
+                                   b_lo + (uint32_t)((sp * S::NSUB * S::KB * 2) >> 4) + (uint32_t)(k * 2), b_hi, idesc, (tap | k) != 0);
+                }
+                b_lo += (uint32_t)(S::BSLAB >> 4);
+              }
+              umma_commit(&tmem_full[slot]);                 // accumulator of this item complete
+              if (item == S::IPB - 1) {
+                umma_commit(&a_empty[stage]);                // halo box may be overwritten
+                if (last_of_set) umma_commit(bfree);         // ... and so may the weight block
+              }
+            }
+            __syncwarp();
+            if (++slot == 2) { slot = 0; sph ^= 1; }
+          }
+          if (++stage == MX_ASTAGES) { stage = 0; phase ^= 1; }
+        } else {
+          // three passes into one accumulator: lo box x W_hi (frees the lo stage early), hi box x W_hi, hi box x W_lo
           mbar_wait(&tmem_empty[slot], sph ^ 1);           // the epilogue has drained this accumulator
           tc_fence_after();
-          if (elect_one()) {
-            const uint32_t tacc = tmem_base + (uint32_t)(slot * 256);
-            const int g0 = (set * S::SETCOLS + item * 256) / S::NG;            // first group of the item
-            constexpr int GPS = S::NSUB / S::NG;                                // groups per MMA
-            constexpr uint32_t a_hi = desc_hi(MX_BW * 128, 2u), b_hi = desc_hi(8 * S::KB * 2, S::KB * 2 == 64 ? 4u : 6u);
-            // the 32-byte K slice of the 128-byte pixel row that holds the first group of split sp, as a descriptor offset
-            uint32_t a_lo0[S::NSPLIT];
+          const uint32_t tacc = tmem_base + (uint32_t)(slot * 256);
+          const int g0 = (set * S::SETCOLS) / S::NG;       // first group of the item
+          constexpr int GPS = S::NSUB / S::NG;
+          constexpr uint32_t a_hi = desc_hi(MX_BW * 128, 2u), b_hi = desc_hi(8 * S::KB * 2, S::KB * 2 == 64 ? 4u : 6u);
+          const uint32_t w_lo0 = desc_lo(smem_u32(wres));
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {           // pass 0: lo box; passes 1, 2: hi box (the next stage)
+            if (pass < 2) { mbar_wait(&a_full[stage], phase); tc_fence_after(); }
+            if (elect_one()) {
+              const uint32_t a_base = smem_u32(smem + stage * MX_A_STAGE);
+              uint32_t a_lo0[S::NSPLIT];
 #pragma unroll
-            for (int sp = 0; sp < S::NSPLIT; ++sp) a_lo0[sp] = desc_lo(a_base) + (uint32_t)(((((g0 + sp * GPS) * CG * 2) & 127) & ~31) >> 4);
-            uint32_t b_lo = desc_lo(smem_u32(wres + item * 9 * S::BSLAB));
-#pragma unroll 1                                            // one 32-bit add per descriptor and tap: warpgroup 0 runs on 40 registers
-            for (int tap = 0; tap < 9; ++tap) {
-              const int ty = tap / 3, tx = tap - ty * 3;
-              const uint32_t a_tap = (uint32_t)(((ty * MX_BW + tx) * 128) >> 4);
+              for (int sp = 0; sp < S::NSPLIT; ++sp) a_lo0[sp] = desc_lo(a_base) + (uint32_t)(((((g0 + sp * GPS) * CG * 2) & 127) & ~31) >> 4);
+              uint32_t b_lo = w_lo0 + (pass == 2 ? (uint32_t)(S::BSLAB >> 4) : 0u);       // weight plane: W_hi, W_hi, W_lo
+#pragma unroll 1
+              for (int tap = 0; tap < 9; ++tap) {
+                const int ty = tap / 3, tx = tap - ty * 3;
+                const uint32_t a_tap = (uint32_t)(((ty * MX_BW + tx) * 128) >> 4);
 #pragma unroll
-              for (int sp = 0; sp < S::NSPLIT; ++sp) {
+                for (int sp = 0; sp < S::NSPLIT; ++sp) {
 #pragma unroll
-                for (int k = 0; k < S::KSTEPS; ++k)
-                  umma_bf16_lohi(tacc + (uint32_t)(sp * S::NSUB), a_lo0[sp] + a_tap + (uint32_t)(k * 2), a_hi,
-                                 b_lo + (uint32_t)((sp * S::NSUB * S::KB * 2) >> 4) + (uint32_t)(k * 2), b_hi, idesc, (tap | k) != 0);
+                  for (int k = 0; k < S::KSTEPS; ++k)
+                    umma_bf16_lohi(tacc + (uint32_t)(sp * S::NSUB), a_lo0[sp] + a_tap + (uint32_t)(k * 2), a_hi,
+                                   b_lo + (uint32_t)((sp * S::NSUB * S::KB * 2) >> 4) + (uint32_t)(k * 2), b_hi, idesc, (pass | tap | k) != 0);
+                }
+                b_lo += (uint32_t)((2 * S::BSLAB) >> 4);
               }
-              b_lo += (uint32_t)(S::BSLAB >> 4);
+              if (pass == 0) umma_commit(&a_empty[stage]);   // lo box may be overwritten
+              if (pass == 2) {
+                umma_commit(&tmem_full[slot]);               // accumulator complete
+                umma_commit(&a_empty[stage]);                // hi box may be overwritten
+                if (last_of_set) umma_commit(bfree);         // ... and so may the weight block
+              }
             }
-            umma_commit(&tmem_full[slot]);                 // accumulator of this item complete
-            if (item == S::IPB - 1) {
-              umma_commit(&a_empty[stage]);                // halo box may be overwritten
-              if (last_of_set) umma_commit(bfree);         // ... and so may the weight block
-            }
+            __syncwarp();
+            if (pass != 1) { if (++stage == MX_ASTAGES) { stage = 0; phase ^= 1; } }
           }
-          __syncwarp();
           if (++slot == 2) { slot = 0; sph ^= 1; }
         }
-        if (++stage == MX_ASTAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -272,7 +336,7 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
       cp_async_commit();
     };
     fetch_unit();
-    request_res(0, n_pix, cur.set, 0);
+    if constexpr (!SPLIT) request_res(0, n_pix, cur.set, 0);
     int rbuf_i = 0;                                          // staging buffer that holds the current item's residual
     for (int left = u1 - u0; left > 0; --left) {
       const int img = cur.img, set = cur.set;
@@ -299,7 +363,7 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
         if (img != tab_img) {
           const float* wp = p.attw + (size_t)img * p.attwStride;
 #pragma unroll
-          for (int s = 0; s < 8; ++s) w8[s] = 0.5f * __ldg(wp + s);     // 1/2: the Swish below works on x / 2
+          for (int s = 0; s < 8; ++s) w8[s] = (SPLIT ? 1.0f : 0.5f) * __ldg(wp + s);     // 1/2: the bf16 Swish below works on x / 2
         }
         tab_img = img; tab_set = set;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * MX_EPI_WARPS) : "memory");
@@ -315,70 +379,61 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
       const bool more = left > 1;
       if (more) fetch_unit();                                // ... and those of the next unit are requested now
       const float2 rs2 = make_float2(rstd, rstd);
-#pragma unroll
-      for (int item = 0; item < S::IPB; ++item) {
-        const int lcol = item * 256 + stripe * 64;          // first column of the stripe within the set
-        const int ch0 = (set * S::SETCOLS + lcol) >> 3;     // its first output channel
-        // request the residual of the next item (an empty group keeps the group count uniform at the very end)
-        if (item + 1 < S::IPB) request_res(rbuf_i ^ 1, pix, set, item + 1);
-        else if (more) request_res(rbuf_i ^ 1, n_pix, cur.set, 0);
-        else cp_async_commit();
+      if constexpr (SPLIT) {
+        // fp32-tolerance epilogue (one 256-column item per unit): the MMA side needs three passes per item, so this side has
+        // slack -- plain loads for the residual planes, exact Swish (swish_f), (hi, lo) stores, statistics of the fp32 values
+        const int lcol = stripe * 64;
+        const int ch0 = (set * S::SETCOLS + lcol) >> 3;
+        uint4 res_h = make_uint4(0u, 0u, 0u, 0u), res_l = res_h;
+        if (valid) {
+          const __nv_bfloat16* rp = p.res + (size_t)pix * p.resC + ch0;
+          res_h = __ldg(reinterpret_cast<const uint4*>(rp));
+          res_l = __ldg(reinterpret_cast<const uint4*>(rp + p.res_lo));
+        }
         mbar_wait(&tmem_full[slot], sph);
         tc_fence_after();
+#if UCDIR_MIX_PROBE == 4             // timing probe only: the MMA side alone (the epilogue hands every accumulator straight back)
+        { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[slot]); if (++slot == 2) { slot = 0; sph ^= 1; } continue; }
+#endif
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + stripe * 64);
         const float4* ct = reinterpret_cast<const float4*>(ctab + cls * S::SETCOLS + lcol);
-        cp_async_wait1();                                   // everything but the request just made has landed
-        const uint4 res_cur = *reinterpret_cast<const uint4*>(smem + S::OFF_RES + ((warp - MX_FIRST_EPI_WARP) * 64 + rbuf_i * 32 + lane) * 16);
-        rbuf_i ^= 1;
-        const __nv_bfloat162* rr = reinterpret_cast<const __nv_bfloat162*>(&res_cur);
+        const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&res_h);
+        const __nv_bfloat162* rl = reinterpret_cast<const __nv_bfloat162*>(&res_l);
         __align__(16) __nv_bfloat162 o[4];
+        __align__(16) __nv_bfloat162 ol[4];
         float2 st1 = make_float2(0.f, 0.f), st2 = make_float2(0.f, 0.f);
-        // 16 columns (two output channels) per step; the TMEM load of step k+1 is in flight during the math of step k
         uint32_t rbuf[2][16];
-        float4 cbuf[2][4];                                  // additive terms of step k / k+1 (read ahead of the TMEM wait)
-#if UCDIR_MIX_PROBE == 3           // timing probe only: the epilogue without its TMEM reads (math, table reads, stores and barriers stay)
-#define MX_TMEM_LD16(addr, dst) do { _Pragma("unroll") for (int z_ = 0; z_ < 16; ++z_) (dst)[z_] = __float_as_uint((float)(lane + z_)); } while (0)
-#else
-#define MX_TMEM_LD16(addr, dst) tmem_ld16(addr, dst)
-#endif
-        MX_TMEM_LD16(taddr, rbuf[0]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cbuf[0][j] = ct[j];
+        tmem_ld16(taddr, rbuf[0]);
         tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (k < 3) {
-            MX_TMEM_LD16(taddr + 16 * (k + 1), rbuf[(k + 1) & 1]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) cbuf[(k + 1) & 1][j] = ct[4 * (k + 1) + j];
-          }
+          if (k < 3) tmem_ld16(taddr + 16 * (k + 1), rbuf[(k + 1) & 1]);
           if (valid) {
             const uint32_t* rv = rbuf[k & 1];
             float hh[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const float4 ca = cbuf[k & 1][2 * e], cb = cbuf[k & 1][2 * e + 1];
+              const float4 ca = ct[4 * k + 2 * e], cb = ct[4 * k + 2 * e + 1];
               const float2 v0 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 0]), __uint_as_float(rv[e * 8 + 1])), rs2, make_float2(ca.x, ca.y));
               const float2 v1 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 2]), __uint_as_float(rv[e * 8 + 3])), rs2, make_float2(ca.z, ca.w));
               const float2 v2 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 4]), __uint_as_float(rv[e * 8 + 5])), rs2, make_float2(cb.x, cb.y));
               const float2 v3 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 6]), __uint_as_float(rv[e * 8 + 7])), rs2, make_float2(cb.z, cb.w));
-              // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
               float2 h2 = __fmul2_rn(v0, aw2[0]);
               h2 = __ffma2_rn(v1, aw2[1], h2);
               float2 g2 = __fmul2_rn(v2, aw2[2]);
               g2 = __ffma2_rn(v3, aw2[3], g2);
               hh[e] = (h2.x + g2.x) + (h2.y + g2.y);
             }
-            const float2 rf = __bfloat1622float2(rr[k]);
-            const float2 tv = make_float2(swish_half(hh[0]) + rf.x, swish_half(hh[1]) + rf.y);
+            const float2 rf = __bfloat1622float2(rh[k]), rg = __bfloat1622float2(rl[k]);
+            const float2 tv = make_float2(swish_f(hh[0]) + (rf.x + rg.x), swish_f(hh[1]) + (rf.y + rg.y));
             o[k] = __floats2bfloat162_rn(tv.x, tv.y);
-            // statistics from the fp32 values (their bf16 rounding is zero-mean noise of relative size 2^-9)
+            const float2 of = __bfloat1622float2(o[k]);
+            ol[k] = __floats2bfloat162_rn(tv.x - of.x, tv.y - of.y);
             st1 = __fadd2_rn(st1, tv);
             st2 = __ffma2_rn(tv, tv, st2);
           }
           if (k < 3) tmem_ld_wait();
           if (k == 2) {
-            // every accumulator value of this stripe is in registers: hand the slot back to the MMA issuer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[slot]);
@@ -386,8 +441,89 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
         }
         if (++slot == 2) { slot = 0; sph ^= 1; }
         if (valid) {
-          *reinterpret_cast<uint4*>(p.dst + (size_t)pix * p.dstC + ch0) = *reinterpret_cast<const uint4*>(o);
+          __nv_bfloat16* d = p.dst + (size_t)pix * p.dstC + ch0;
+          *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(o);
+          *reinterpret_cast<uint4*>(d + p.dst_lo) = *reinterpret_cast<const uint4*>(ol);
           s1 += st1.x + st1.y; s2 += st2.x + st2.y;
+        }
+      } else {
+#pragma unroll
+        for (int item = 0; item < S::IPB; ++item) {
+          const int lcol = item * 256 + stripe * 64;          // first column of the stripe within the set
+          const int ch0 = (set * S::SETCOLS + lcol) >> 3;     // its first output channel
+          // request the residual of the next item (an empty group keeps the group count uniform at the very end)
+          if (item + 1 < S::IPB) request_res(rbuf_i ^ 1, pix, set, item + 1);
+          else if (more) request_res(rbuf_i ^ 1, n_pix, cur.set, 0);
+          else cp_async_commit();
+          mbar_wait(&tmem_full[slot], sph);
+          tc_fence_after();
+#if UCDIR_MIX_PROBE == 4             // timing probe only: the MMA side alone (the epilogue hands every accumulator straight back)
+          { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[slot]); if (++slot == 2) { slot = 0; sph ^= 1; } continue; }
+#endif
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + stripe * 64);
+          const float4* ct = reinterpret_cast<const float4*>(ctab + cls * S::SETCOLS + lcol);
+          cp_async_wait1();                                   // everything but the request just made has landed
+          const uint4 res_cur = *reinterpret_cast<const uint4*>(smem + S::OFF_RES + ((warp - MX_FIRST_EPI_WARP) * 64 + rbuf_i * 32 + lane) * 16);
+          rbuf_i ^= 1;
+          const __nv_bfloat162* rr = reinterpret_cast<const __nv_bfloat162*>(&res_cur);
+          __align__(16) __nv_bfloat162 o[4];
+          float2 st1 = make_float2(0.f, 0.f), st2 = make_float2(0.f, 0.f);
+          // 16 columns (two output channels) per step; the TMEM load of step k+1 is in flight during the math of step k
+          uint32_t rbuf[2][16];
+          float4 cbuf[2][4];                                  // additive terms of step k / k+1 (read ahead of the TMEM wait)
+#if UCDIR_MIX_PROBE == 3           // timing probe only: the epilogue without its TMEM reads (math, table reads, stores and barriers stay)
+#define MX_TMEM_LD16(addr, dst) do { _Pragma("unroll") for (int z_ = 0; z_ < 16; ++z_) (dst)[z_] = __float_as_uint((float)(lane + z_)); } while (0)
+#else
+#define MX_TMEM_LD16(addr, dst) tmem_ld16(addr, dst)
+#endif
+          MX_TMEM_LD16(taddr, rbuf[0]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cbuf[0][j] = ct[j];
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < 3) {
+              MX_TMEM_LD16(taddr + 16 * (k + 1), rbuf[(k + 1) & 1]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) cbuf[(k + 1) & 1][j] = ct[4 * (k + 1) + j];
+            }
+            if (valid) {
+              const uint32_t* rv = rbuf[k & 1];
+              float hh[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float4 ca = cbuf[k & 1][2 * e], cb = cbuf[k & 1][2 * e + 1];
+                const float2 v0 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 0]), __uint_as_float(rv[e * 8 + 1])), rs2, make_float2(ca.x, ca.y));
+                const float2 v1 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 2]), __uint_as_float(rv[e * 8 + 3])), rs2, make_float2(ca.z, ca.w));
+                const float2 v2 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 4]), __uint_as_float(rv[e * 8 + 5])), rs2, make_float2(cb.x, cb.y));
+                const float2 v3 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 6]), __uint_as_float(rv[e * 8 + 7])), rs2, make_float2(cb.z, cb.w));
+                // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
+                float2 h2 = __fmul2_rn(v0, aw2[0]);
+                h2 = __ffma2_rn(v1, aw2[1], h2);
+                float2 g2 = __fmul2_rn(v2, aw2[2]);
+                g2 = __ffma2_rn(v3, aw2[3], g2);
+                hh[e] = (h2.x + g2.x) + (h2.y + g2.y);
+              }
+              const float2 rf = __bfloat1622float2(rr[k]);
+              const float2 tv = make_float2(swish_half(hh[0]) + rf.x, swish_half(hh[1]) + rf.y);
+              o[k] = __floats2bfloat162_rn(tv.x, tv.y);
+              // statistics from the fp32 values (their bf16 rounding is zero-mean noise of relative size 2^-9)
+              st1 = __fadd2_rn(st1, tv);
+              st2 = __ffma2_rn(tv, tv, st2);
+            }
+            if (k < 3) tmem_ld_wait();
+            if (k == 2) {
+              // every accumulator value of this stripe is in registers: hand the slot back to the MMA issuer
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+            }
+          }
+          if (++slot == 2) { slot = 0; sph ^= 1; }
+          if (valid) {
+            *reinterpret_cast<uint4*>(p.dst + (size_t)pix * p.dstC + ch0) = *reinterpret_cast<const uint4*>(o);
+            s1 += st1.x + st1.y; s2 += st2.x + st2.y;
+          }
         }
       }
     }
@@ -409,14 +545,14 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 static const bool g_mix_pdl = []() { const char* e = getenv("UCDIR_PDL"); return !(e && e[0] == '0'); }();
 
-template <int CG>
+template <int CG, bool SPLIT = false>
 static int launch_mix_inst(const CUtensorMap& a, const CUtensorMap& b, const MixParams& p, int grid, cudaStream_t st) {
-  using S = MixCfg<CG>;
+  using S = MixCfg<CG, SPLIT>;
   static bool attr_dev[UCDIR_MAX_DEV] = {};
   bool& attr = attr_dev[cur_dev()];
   if (!attr) {
-    if (int rc = check_reg_pool((const void*)mix_halo_kernel<CG>, "tc_mix_halo", 32 * MX_FIRST_EPI_WARP, MX_REGS_LOW, 32 * MX_EPI_WARPS, MX_REGS_HIGH)) return rc;
-    if (cudaFuncSetAttribute(mix_halo_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+    if (int rc = check_reg_pool((const void*)mix_halo_kernel<CG, SPLIT>, "tc_mix_halo", 32 * MX_FIRST_EPI_WARP, MX_REGS_LOW, 32 * MX_EPI_WARPS, MX_REGS_HIGH)) return rc;
+    if (cudaFuncSetAttribute(mix_halo_kernel<CG, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
       set_error("tc_mix_halo: cannot opt in to %d bytes of shared memory: %s", S::TOTAL, cudaGetErrorString(cudaGetLastError())); return -3; }
     attr = true;
   }
@@ -426,7 +562,7 @@ static int launch_mix_inst(const CUtensorMap& a, const CUtensorMap& b, const Mix
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = g_mix_pdl ? 1 : 0;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, mix_halo_kernel<CG>, a, b, p) != cudaSuccess) {
+  if (cudaLaunchKernelEx(&cfg, mix_halo_kernel<CG, SPLIT>, a, b, p) != cudaSuccess) {
     set_error("tc_mix_halo: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
   return 0;
 }
@@ -435,12 +571,16 @@ static int launch_mix_inst(const CUtensorMap& a, const CUtensorMap& b, const Mix
 bool tc_mix_halo_applies(const ucdir_op_t& op) {
   const int C = op.i[UCDIR_TC_I_C0], H = op.i[UCDIR_TC_I_H], W = op.i[UCDIR_TC_I_W];
   const int KB = op.i[UCDIR_TC_I_KB] ? op.i[UCDIR_TC_I_KB] : op.i[UCDIR_TC_I_KC];
-  return op.i[UCDIR_TC_I_HALO] == 1 && op.i[UCDIR_TC_I_SPLIT] == 0 && op.i[UCDIR_TC_I_MODE] == 1 && op.i[UCDIR_TC_I_GROUPS] == 8 && (C == 64 || C == 128 || C == 256) &&
+  const bool split = op.i[UCDIR_TC_I_SPLIT] != 0;
+  // SPLIT (fp32_tc): C = 64 / 128 (both weight planes of a C = 256 item do not fit), default plane layout [hi: C | lo: C]
+  if (split && (C == 256 || (op.i[UCDIR_TC_I_SRC_LO_OFF] != 0 && op.i[UCDIR_TC_I_SRC_LO_OFF] != C) || op.i[UCDIR_TC_I_W_LO_OFF] != 0)) return false;
+  const int cs = split ? 2 * C : C;
+  return op.i[UCDIR_TC_I_HALO] == 1 && op.i[UCDIR_TC_I_MODE] == 1 && op.i[UCDIR_TC_I_GROUPS] == 8 && (C == 64 || C == 128 || C == 256) &&
          op.i[UCDIR_TC_I_C1] == 0 && op.i[UCDIR_TC_I_NTOT] == 8 * C && op.i[UCDIR_TC_I_GN] == 1 && op.i[UCDIR_TC_I_NCLS] == 9 &&
          op.i[UCDIR_TC_I_NTY] == 3 && op.i[UCDIR_TC_I_NTX] == 3 && op.i[UCDIR_TC_I_OY0] == -1 && op.i[UCDIR_TC_I_OX0] == -1 &&
          op.i[UCDIR_TC_I_STRIDE] == 1 && KB == (C / 8 < 16 ? 16 : C / 8) && H >= 2 && W >= 2 && op.i[UCDIR_TC_I_SRC_H] == H &&
          op.i[UCDIR_TC_I_SRC_W] == W && !op.i[UCDIR_TC_I_DST_F32] && !op.i[UCDIR_TC_I_DST_UP] && !op.i[UCDIR_TC_I_W_BATCHED] &&
-         !op.p[UCDIR_TC_P_DST2] && op.i[UCDIR_TC_I_DST_COFF] == 0 && (op.i[UCDIR_TC_I_SRC_CSTRIDE] == 0 || op.i[UCDIR_TC_I_SRC_CSTRIDE] == C) &&
+         !op.p[UCDIR_TC_P_DST2] && op.i[UCDIR_TC_I_DST_COFF] == 0 && (op.i[UCDIR_TC_I_SRC_CSTRIDE] == 0 || op.i[UCDIR_TC_I_SRC_CSTRIDE] == cs) &&
          op.i[UCDIR_TC_I_DST_C] % 8 == 0 && op.i[UCDIR_TC_I_RES_C] % 8 == 0 && op.p[UCDIR_TC_P_TG] && op.p[UCDIR_TC_P_STATS0];
 }
 
@@ -453,11 +593,16 @@ int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st) {
   p.B = op.i[UCDIR_TC_I_B]; p.H = op.i[UCDIR_TC_I_H]; p.W = op.i[UCDIR_TC_I_W]; p.Ntot = op.i[UCDIR_TC_I_NTOT];
   const int C = op.i[UCDIR_TC_I_C0], CG = C / 8, KB = CG < 16 ? 16 : CG;
   p.resC = op.i[UCDIR_TC_I_RES_C]; p.dstC = op.i[UCDIR_TC_I_DST_C]; p.attwStride = op.i[UCDIR_TC_I_ATTW_STRIDE];
+  const bool split = op.i[UCDIR_TC_I_SPLIT] != 0;
+  p.a_lo = p.res_lo = p.dst_lo = 0;
+  if (split) {                                               // (hi, lo) plane pairs: rows are twice as long, lo plane after the hi plane
+    p.a_lo = C; p.res_lo = p.resC; p.resC *= 2; p.dst_lo = p.dstC; p.dstC *= 2;
+  }
   p.eps = op.f[UCDIR_TC_F_EPS];
   p.gn_count = (double)C * p.H * p.W;
   p.tiles_x = (p.W + MX_TW - 1) / MX_TW; p.tiles_y = (p.H + MX_TH - 1) / MX_TH;
   const long long mt = (long long)p.tiles_x * p.tiles_y * p.B;
-  const int setcols = CG == 32 ? 256 : 512;
+  const int setcols = (CG == 32 || split) ? 256 : 512;
   const long long units = mt * (p.Ntot / setcols);
   if (units > 0x7fffffffLL || (long long)p.B * p.H * p.W > 0x7fffffffLL) { set_error("tc_mix_halo: too many units / pixels"); return -2; }
   p.m_tiles = (int)mt; p.n_units = (int)units;
@@ -465,8 +610,9 @@ int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st) {
   if (!enc) { set_error("tc_mix_halo: cuTensorMapEncodeTiled unavailable"); return -3; }
   CUtensorMap ma, mb;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * p.W, (cuuint64_t)C * 2 * p.W * p.H};
+    const cuuint64_t cs = split ? 2 * C : C;                 // channels per pixel row (both planes)
+    cuuint64_t dims[4] = {cs, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+    cuuint64_t strides[3] = {cs * 2, cs * 2 * p.W, cs * 2 * p.W * p.H};
     cuuint32_t box[4] = {64, MX_BW, MX_BH, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.p[UCDIR_TC_P_SRC0]), dims, strides, box, es,
@@ -474,7 +620,7 @@ int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st) {
     if (r != CUDA_SUCCESS) { set_error("tc_mix_halo: cuTensorMapEncodeTiled(activation C=%d W=%d H=%d B=%d) failed: %d", C, p.W, p.H, p.B, (int)r); return -3; }
   }
   {
-    const int Ktot = 9 * KB;
+    const int Ktot = 9 * KB * (split ? 3 : 1);               // SPLIT: [W_hi | W_hi | W_lo] per tap
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p.Ntot};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
     cuuint32_t box[2] = {(cuuint32_t)KB, 256};
@@ -487,7 +633,8 @@ int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st) {
   const int n_sm = sm_count();
   const int grid = units < n_sm ? (int)units : n_sm;       // persistent: one CTA per SM
   int rc;
-  if (CG == 8) rc = launch_mix_inst<8>(ma, mb, p, grid, st);
+  if (split) rc = CG == 8 ? launch_mix_inst<8, true>(ma, mb, p, grid, st) : launch_mix_inst<16, true>(ma, mb, p, grid, st);
+  else if (CG == 8) rc = launch_mix_inst<8>(ma, mb, p, grid, st);
   else if (CG == 16) rc = launch_mix_inst<16>(ma, mb, p, grid, st);
   else rc = launch_mix_inst<32>(ma, mb, p, grid, st);
   if (rc) return rc;

@@ -493,8 +493,8 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
          "UCDIR_TC_I_W_BATCHSTRIDE_LO": w_batchstride & 0x7FFFFFFF, "UCDIR_TC_I_W_BATCHSTRIDE_HI": w_batchstride >> 31,
          "UCDIR_TC_I_T_COL0": t_col0, "UCDIR_TC_I_T_LD": t_ld, "UCDIR_TC_I_W_ROWS": w_rows,
          "UCDIR_TC_I_ROW3": _TC_ROW3 if row3 is None else row3, "UCDIR_TC_I_HALO": _TC_HALO if halo is None else halo}
-    if split:
-        i["UCDIR_TC_I_SPLIT"], i["UCDIR_TC_I_HALO"] = 1, 0
+    if split:                                # the halo request stays: the library applies it where a split schedule exists
+        i["UCDIR_TC_I_SPLIT"] = 1
         i["UCDIR_TC_I_SRC_LO_OFF"], i["UCDIR_TC_I_W_LO_OFF"] = src_lo_off, w_lo_off
     if dst2: p["UCDIR_TC_P_DST2"] = dst2
     if dst_crop: i["UCDIR_TC_I_DST_CROP"] = dst_crop
