@@ -14,13 +14,19 @@
 //   for C = 256) resident in shared memory and walks the M tiles of its unit range; units are ordered set-major.
 //   L2 -> SM traffic per 128 pixels drops from 288 KB to the 23 KB halo box.
 // * 16 epilogue warps (four per TMEM lane quadrant); warp j of a quadrant owns the fixed 64-column stripe j of every
-//   256-column item = 8 output channels.  TMEM is read 16 columns at a time, the load of step k+1 in flight during the math
-//   of step k;  out[c] = Swish(sum_s aw[s] * (rstd*acc[c*8+s] + cadd[cls][c*8+s])) + res[c], with the folded-GroupNorm
-//   additive table of the current (image, set) in shared memory (read one step ahead), the guidance row of the next tile
-//   prefetched into registers, the residual row of the next item staged by cp.async, Swish as h + h*tanh(h) (one MUFU op).
-// * measured (ncu, profiles/r01_ncu_halo_kernels.md): an M = 128, N = 128, K = 16 MMA from shared-memory operands takes
-//   ~125 cycles, not its 64 tensor cycles -- operand fetch (A 4 KB + B 4 KB) runs at ~64 B/clk per SM -- so the C = 64 item
-//   costs >= 18 x 125 = 2250 cycles; the epilogue was brought from ~3200 to ~2700 cycles per item to sit next to that.
+//   256-column item = 8 output channels.  TMEM is read 16 columns at a time, the load of step k+1 in flight during the math of
+//   step k;  out[c] = Swish(sum_s aw[s] * (rstd*acc[c*8+s] + cadd[cls][c*8+s])) + res[c] evaluated as
+//   Swish(sum_s (aw[s] rstd) acc[c*8+s] + D[c]), D[c] = sum_s aw[s] cadd[cls][c*8+s]: the D chain reads the folded-GroupNorm
+//   additive table of the current (image, set) from shared memory while the TMEM load is in flight; the guidance row of the next
+//   tile is prefetched into registers; Swish as h + h*tanh(h) (one MUFU op).
+// * residual in / output out as TMA boxes (round 2).  One pixel per lane means a per-thread global access touches 32 different
+//   128-byte lines per warp instruction; timing probes (profiles/r02_mix_probes.md) showed that these accesses -- not the
+//   arithmetic, the TMEM reads, the table reads or the MUFU ops, which all hide behind the MMA side -- were what the C = 64 / 128
+//   launches spent a third of their time on.  Now the residual tile of an item (32 channels x 8 x 16 pixels) lands in shared
+//   memory by TMA two items ahead, every epilogue thread swaps its 16-byte chunk for its outputs, and the tile leaves by a TMA
+//   store (warp 2 runs this: load -> [res_full] -> epilogue -> [out_done] -> store -> load of item n + 2); partial tiles are
+//   clipped by the TMA unit.
+// * measured (profiles/r02_mix_probes.md): the MMA side alone runs the C = 64 launch in 194 us (94 cycles per N = 128 MMA).
 //
 // Packed weights, TB / TG tables and every other operand are those of the streamed form (engine.py:pack_tc_grouped).
 #include <cuda.h>
@@ -36,6 +42,11 @@
 #define UCDIR_MIX_PROBE 1
 #endif
 #define UCDIR_MIX_PROBE_NDIV (UCDIR_MIX_PROBE == 2 ? 2 : 1)
+#if UCDIR_MIX_PROBE == 3           // the epilogue without its TMEM reads (math, table reads, stores and barriers stay)
+#define MX_TMEM_LD16(addr, dst) do { _Pragma("unroll") for (int z_ = 0; z_ < 16; ++z_) (dst)[z_] = __float_as_uint((float)(lane + z_)); } while (0)
+#else
+#define MX_TMEM_LD16(addr, dst) tmem_ld16(addr, dst)
+#endif
 
 namespace ucdir {
 
@@ -89,20 +100,17 @@ struct MixCfg {
   static constexpr int CTAB_BYTES = 9 * SETCOLS * 4;
   static constexpr int OFF_W = ASTAGES * MX_A_STAGE;
   static constexpr int OFF_CTAB = OFF_W + MX_WRES;
-  static constexpr int OFF_RES = OFF_CTAB + CTAB_BYTES;   // residual staging: [epilogue warp][2][32 lanes] x 16 bytes (cp.async); SPLIT: none
-  static constexpr int OFF_BARS = OFF_RES + (SPLIT ? 0 : MX_EPI_WARPS * 2 * 32 * 16);
-  static constexpr int TOTAL = OFF_BARS + 128 + 1024 /* align slack */;
+  // bf16: two item tiles [128 pixels][32 channels] (64-byte rows, 64B swizzle): the residual of an item lands here by TMA, every
+  // epilogue thread replaces its 16-byte chunk by its output, and the tile leaves by a TMA store.  SPLIT: none (no room).  (A third
+  // tile -- paid for by a 5-class table -- was measured and buys nothing: the load of item n + 2 is not what the epilogue waits for.)
+  static constexpr int OFF_RES = OFF_CTAB + CTAB_BYTES;
+  static constexpr int IO_TILE = 128 * 64, IO_TILES = 2;
+  static constexpr int OFF_BARS = OFF_RES + (SPLIT ? 0 : IO_TILES * IO_TILE);
+  static_assert(SPLIT || OFF_RES % 1024 == 0, "I/O tile alignment (swizzle atom)");
+  static constexpr int TOTAL = OFF_BARS + 256 + 1024 /* align slack */;
   static_assert(TOTAL <= 227 * 1024, "shared memory");
   static_assert(OFF_W % 1024 == 0, "weight block alignment");
 };
-
-// 16-byte asynchronous global -> shared copy (completion is tracked per thread by cp.async groups, not by the register
-// scoreboards a prefetch into registers shares with every other load in flight)
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // unit = (column set, M tile), set-major; M tile = (image, tile row, tile column), column fastest
 struct UnitCursor {
@@ -122,7 +130,9 @@ struct UnitCursor {
 
 template <int CG, bool SPLIT>
 __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                 const __grid_constant__ CUtensorMap mapB, const MixParams p) {
+                                                                 const __grid_constant__ CUtensorMap mapB,
+                                                                 const __grid_constant__ CUtensorMap mapR,
+                                                                 const __grid_constant__ CUtensorMap mapD, const MixParams p) {
   using S = MixCfg<CG, SPLIT>;
   constexpr int MX_ASTAGES = S::ASTAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -136,7 +146,9 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* bfull = tmem_empty + 2;
   uint64_t* bfree = bfull + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfree + 1);
+  uint64_t* res_full = bfree + 1;                                     // [IO_TILES] residual tile of an item has landed (TMA)
+  uint64_t* out_done = res_full + S::IO_TILES;                                  // [IO_TILES] every epilogue warp has written its outputs into the tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_done + S::IO_TILES);
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -147,6 +159,8 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
     for (int s = 0; s < MX_ASTAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int j = 0; j < 2; ++j) { mbar_init(&tmem_full[j], 1); mbar_init(&tmem_empty[j], MX_EPI_WARPS); }
     mbar_init(bfull, 1); mbar_init(bfree, 1);
+    for (int j = 0; j < S::IO_TILES; ++j) { mbar_init(&res_full[j], 1); mbar_init(&out_done[j], MX_EPI_WARPS); }
+    if (!SPLIT) { prefetch_tmap(&mapR); prefetch_tmap(&mapD); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -298,6 +312,41 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
         }
       }
     }
+    else if (warp == 2 && !SPLIT) {
+      // ===================== tile I/O (bf16): residual tiles in, output tiles out, both as TMA boxes =====================
+      // Item n of this CTA uses tile n % IO_TILES:  load residual(n) -> [res_full] -> the epilogue threads swap their 16-byte chunks for
+      // outputs -> [out_done] -> store(n) -> (source read) -> load residual(n + IO_TILES).  One elected lane issues everything, so the
+      // bulk async groups it waits on are its own.
+      const int n_items = (u1 - u0) * S::IPB;
+      if (n_items > 0 && elect_one()) {
+        UnitCursor cl; cl.init(u0, p.m_tiles, p.tiles_x, p.tiles_y);      // cursor of the next item to load
+        UnitCursor cs = cl;                                               // cursor of the next item to store
+        int il = 0, is = 0;                                               // item of the unit (0 .. IPB-1) of either cursor
+        int tl = 0;                                                       // tile of the next load
+        auto chan0 = [&](const UnitCursor& c, int item) { return (c.set * S::SETCOLS + item * 256) >> 3; };
+        auto load_next = [&]() {
+          mbar_expect_tx(&res_full[tl], (uint32_t)S::IO_TILE);
+          tma_load_4d(&mapR, &res_full[tl], smem + S::OFF_RES + tl * S::IO_TILE, chan0(cl, il), cl.tx * MX_TW, cl.ty * MX_TH, cl.img);
+          if (++tl == S::IO_TILES) tl = 0;
+          if (++il == S::IPB) { il = 0; cl.next(p.tiles_x, p.tiles_y, p.B); }
+        };
+        for (int n = 0; n < S::IO_TILES && n < n_items; ++n) load_next();
+        int ts = 0; uint32_t tph = 0;
+        for (int n = 0; n < n_items; ++n) {
+          mbar_wait(&out_done[ts], tph);
+          tma_store_4d(&mapD, smem + S::OFF_RES + ts * S::IO_TILE, chan0(cs, is), cs.tx * MX_TW, cs.ty * MX_TH, cs.img);
+          bulk_commit();
+          if (++is == S::IPB) { is = 0; cs.next(p.tiles_x, p.tiles_y, p.B); }
+          if (++ts == S::IO_TILES) { ts = 0; tph ^= 1; }
+          if (n + S::IO_TILES < n_items) {
+            bulk_wait_read0();                               // the store has read the tile: it may be overwritten
+            load_next();
+          }
+        }
+        bulk_wait0();                                        // every output tile is in global memory before the CTA retires
+      }
+      __syncwarp();
+    }
   } else {
     // ===================== epilogue =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MX_REGS_HIGH));
@@ -315,9 +364,8 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
 #pragma unroll
     for (int s = 0; s < 8; ++s) w8[s] = 0.f;
     int slot = 0; uint32_t sph = 0;
-    // Software pipeline: the guidance-map row of unit u+1 and the residual row of the next item are requested while the
-    // current item is processed (they stream from HBM; requested at the point of use they stalled every item for a full
-    // DRAM round trip -- 30% of all warp samples in the first ncu capture of this kernel).
+    // The guidance-map row of unit u+1 is requested while unit u is processed (requested at the point of use it stalled every
+    // unit for a full DRAM round trip -- 30% of all warp samples in the first ncu capture of this kernel).
     bool n_valid = false; uint32_t n_pix = 0; int n_cls = 0;
     float4 n_att0 = make_float4(0.f, 0.f, 0.f, 0.f), n_att1 = n_att0;
     auto fetch_unit = [&]() {
@@ -328,16 +376,11 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
       n_att0 = __ldg(reinterpret_cast<const float4*>(p.att + (size_t)n_pix * 8));
       n_att1 = __ldg(reinterpret_cast<const float4*>(p.att + (size_t)n_pix * 8 + 4));
     };
-    // The residual row of the NEXT item travels global -> shared by cp.async into this thread's own 16-byte slot (double
-    // buffered); the thread reads it back after cp.async.wait_group, so no cross-thread synchronisation is involved.
-    const uint32_t res_slot = smem_u32(smem + S::OFF_RES) + (uint32_t)(((warp - MX_FIRST_EPI_WARP) * 64 + lane) * 16);
-    auto request_res = [&](int buf, uint32_t pix, int set, int item) {
-      cp_async16(res_slot + (uint32_t)(buf * 512), p.res + (size_t)pix * p.resC + ((set * S::SETCOLS + item * 256 + stripe * 64) >> 3));
-      cp_async_commit();
-    };
+    // bf16: this thread's 16-byte chunk of an item tile [128 pixels][4 chunks], 64B swizzle (chunk ^= (row >> 1) & 3): the residual
+    // of its 8 channels is read from it and their outputs are written back to it (tile I/O warp above)
+    const uint32_t io_chunk = (uint32_t)(S::OFF_RES + r * 64 + ((stripe ^ ((r >> 1) & 3)) << 4));
+    int io_t = 0; uint32_t io_ph = 0;                        // I/O tile of the current item and the phase of its barriers
     fetch_unit();
-    if constexpr (!SPLIT) request_res(0, n_pix, cur.set, 0);
-    int rbuf_i = 0;                                          // staging buffer that holds the current item's residual
     for (int left = u1 - u0; left > 0; --left) {
       const int img = cur.img, set = cur.set;
       if (img != stat_img) {
@@ -372,159 +415,119 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
       const bool valid = n_valid;
       const uint32_t pix = n_pix;
       const int cls = n_cls;
-      float2 aw2[4];
+      // out[c] = Swish(sum_s aw[s] (rstd acc[c*8+s] + cadd[cls][c*8+s])) + res[c]  (model/ucdir.py:136-140 on the folded GroupNorm)
+      //        = Swish(sum_s (aw[s] rstd) acc[c*8+s] + D[c]),  D[c] = sum_s aw[s] cadd[cls][c*8+s]:
+      // the D chain does not depend on the accumulator (it runs while the TMEM load is in flight, the table values never wait in
+      // registers) and the accumulator chain continues from D[c]: 8 packed FMAs + 1 add per output
+      float2 aw2[4], awr2[4];
       aw2[0] = make_float2(n_att0.x * w8[0], n_att0.y * w8[1]); aw2[1] = make_float2(n_att0.z * w8[2], n_att0.w * w8[3]);
       aw2[2] = make_float2(n_att1.x * w8[4], n_att1.y * w8[5]); aw2[3] = make_float2(n_att1.z * w8[6], n_att1.w * w8[7]);
-      cur.next(p.tiles_x, p.tiles_y, p.B);
-      const bool more = left > 1;
-      if (more) fetch_unit();                                // ... and those of the next unit are requested now
       const float2 rs2 = make_float2(rstd, rstd);
-      if constexpr (SPLIT) {
-        // fp32-tolerance epilogue (one 256-column item per unit): the MMA side needs three passes per item, so this side has
-        // slack -- plain loads for the residual planes, exact Swish (swish_f), (hi, lo) stores, statistics of the fp32 values
-        const int lcol = stripe * 64;
-        const int ch0 = (set * S::SETCOLS + lcol) >> 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) awr2[j] = __fmul2_rn(aw2[j], rs2);
+      cur.next(p.tiles_x, p.tiles_y, p.B);
+      if (left > 1) fetch_unit();                            // ... and those of the next unit are requested now
+#pragma unroll
+      for (int item = 0; item < S::IPB; ++item) {
+        const int lcol = item * 256 + stripe * 64;           // first column of the stripe within the set
+        const int ch0 = (set * S::SETCOLS + lcol) >> 3;      // its first output channel
         uint4 res_h = make_uint4(0u, 0u, 0u, 0u), res_l = res_h;
-        if (valid) {
-          const __nv_bfloat16* rp = p.res + (size_t)pix * p.resC + ch0;
+        if (SPLIT && valid) {                                // fp32_tc: plain loads of the two residual planes (the MMA side needs three
+          const __nv_bfloat16* rp = p.res + (size_t)pix * p.resC + ch0;            // passes per item, this side has the slack)
           res_h = __ldg(reinterpret_cast<const uint4*>(rp));
           res_l = __ldg(reinterpret_cast<const uint4*>(rp + p.res_lo));
         }
         mbar_wait(&tmem_full[slot], sph);
         tc_fence_after();
 #if UCDIR_MIX_PROBE == 4             // timing probe only: the MMA side alone (the epilogue hands every accumulator straight back)
-        { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[slot]); if (++slot == 2) { slot = 0; sph ^= 1; } continue; }
+        { tc_fence_before(); __syncwarp(); if (lane == 0) { mbar_arrive(&tmem_empty[slot]); if (!SPLIT) mbar_arrive(&out_done[io_t]); }
+          if (++io_t == S::IO_TILES) { io_t = 0; io_ph ^= 1; } if (++slot == 2) { slot = 0; sph ^= 1; } continue; }
 #endif
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + stripe * 64);
+        uint32_t rbuf[2][16];
+        MX_TMEM_LD16(taddr, rbuf[0]);
+        float2 d2[8];
         const float4* ct = reinterpret_cast<const float4*>(ctab + cls * S::SETCOLS + lcol);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 ca = ct[2 * c], cb = ct[2 * c + 1];
+          float2 d = __fmul2_rn(make_float2(ca.x, ca.y), aw2[0]);
+          d = __ffma2_rn(make_float2(ca.z, ca.w), aw2[1], d);
+          d = __ffma2_rn(make_float2(cb.x, cb.y), aw2[2], d);
+          d2[c] = __ffma2_rn(make_float2(cb.z, cb.w), aw2[3], d);
+        }
+        uint8_t* io_ptr = smem + io_chunk + io_t * S::IO_TILE;
+        if (!SPLIT) {                                        // residual tile of this item (TMA, requested two items ago)
+          mbar_wait(&res_full[io_t], io_ph);
+          res_h = *reinterpret_cast<const uint4*>(io_ptr);
+        }
         const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&res_h);
         const __nv_bfloat162* rl = reinterpret_cast<const __nv_bfloat162*>(&res_l);
-        __align__(16) __nv_bfloat162 o[4];
-        __align__(16) __nv_bfloat162 ol[4];
+        uint32_t o[4], ol[4];
         float2 st1 = make_float2(0.f, 0.f), st2 = make_float2(0.f, 0.f);
-        uint32_t rbuf[2][16];
-        tmem_ld16(taddr, rbuf[0]);
         tmem_ld_wait();
+        // 16 columns (two output channels) per step; the TMEM load of step k+1 is in flight during the math of step k.  Rows of a
+        // partial tile that lie outside the image compute on zero accumulators and are masked where results leave the thread.
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (k < 3) tmem_ld16(taddr + 16 * (k + 1), rbuf[(k + 1) & 1]);
-          if (valid) {
-            const uint32_t* rv = rbuf[k & 1];
-            float hh[2];
+          if (k < 3) MX_TMEM_LD16(taddr + 16 * (k + 1), rbuf[(k + 1) & 1]);
+          const uint32_t* rv = rbuf[k & 1];
+          float hh[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float4 ca = ct[4 * k + 2 * e], cb = ct[4 * k + 2 * e + 1];
-              const float2 v0 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 0]), __uint_as_float(rv[e * 8 + 1])), rs2, make_float2(ca.x, ca.y));
-              const float2 v1 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 2]), __uint_as_float(rv[e * 8 + 3])), rs2, make_float2(ca.z, ca.w));
-              const float2 v2 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 4]), __uint_as_float(rv[e * 8 + 5])), rs2, make_float2(cb.x, cb.y));
-              const float2 v3 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 6]), __uint_as_float(rv[e * 8 + 7])), rs2, make_float2(cb.z, cb.w));
-              float2 h2 = __fmul2_rn(v0, aw2[0]);
-              h2 = __ffma2_rn(v1, aw2[1], h2);
-              float2 g2 = __fmul2_rn(v2, aw2[2]);
-              g2 = __ffma2_rn(v3, aw2[3], g2);
-              hh[e] = (h2.x + g2.x) + (h2.y + g2.y);
-            }
-            const float2 rf = __bfloat1622float2(rh[k]), rg = __bfloat1622float2(rl[k]);
-            const float2 tv = make_float2(swish_f(hh[0]) + (rf.x + rg.x), swish_f(hh[1]) + (rf.y + rg.y));
-            o[k] = __floats2bfloat162_rn(tv.x, tv.y);
-            const float2 of = __bfloat1622float2(o[k]);
-            ol[k] = __floats2bfloat162_rn(tv.x - of.x, tv.y - of.y);
-            st1 = __fadd2_rn(st1, tv);
-            st2 = __ffma2_rn(tv, tv, st2);
+          for (int e = 0; e < 2; ++e) {
+            float2 h2 = d2[2 * k + e];
+            h2 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 0]), __uint_as_float(rv[e * 8 + 1])), awr2[0], h2);
+            h2 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 2]), __uint_as_float(rv[e * 8 + 3])), awr2[1], h2);
+            h2 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 4]), __uint_as_float(rv[e * 8 + 5])), awr2[2], h2);
+            h2 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 6]), __uint_as_float(rv[e * 8 + 7])), awr2[3], h2);
+            hh[e] = h2.x + h2.y;
           }
+          float2 rf = __bfloat1622float2(rh[k]);
+          float2 tv;
+          if (SPLIT) {
+            // fp32_tc: Swish from ex2.approx + rcp.approx (relative error ~3e-7 against a tolerance of rtol 1e-3 / atol 1e-4 and
+            // operands of 16 mantissa bits), residual = hi + lo, the result stored as a (hi, lo) pair
+            const float2 rg = __bfloat1622float2(rl[k]);
+            tv = make_float2(swish_fast(hh[0]) + (rf.x + rg.x), swish_fast(hh[1]) + (rf.y + rg.y));
+            const __nv_bfloat162 oh = __floats2bfloat162_rn(tv.x, tv.y);
+            const float2 of = __bfloat1622float2(oh);
+            const __nv_bfloat162 olo = __floats2bfloat162_rn(tv.x - of.x, tv.y - of.y);
+            o[k] = *reinterpret_cast<const uint32_t*>(&oh);
+            ol[k] = *reinterpret_cast<const uint32_t*>(&olo);
+          } else {
+            // Swish = h + h tanh(h), h = x / 2 (the 1/2 is folded into attw): one MUFU op
+            tv = make_float2(swish_half(hh[0]) + rf.x, swish_half(hh[1]) + rf.y);
+            const __nv_bfloat162 oh = __floats2bfloat162_rn(tv.x, tv.y);
+            o[k] = *reinterpret_cast<const uint32_t*>(&oh);
+          }
+          // statistics from the fp32 values (their bf16 rounding is zero-mean noise of relative size 2^-9)
+          st1 = __fadd2_rn(st1, tv);
+          st2 = __ffma2_rn(tv, tv, st2);
           if (k < 3) tmem_ld_wait();
           if (k == 2) {
+            // every accumulator value of this stripe is in registers: hand the slot back to the MMA issuer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[slot]);
           }
         }
         if (++slot == 2) { slot = 0; sph ^= 1; }
-        if (valid) {
-          __nv_bfloat16* d = p.dst + (size_t)pix * p.dstC + ch0;
-          *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(o);
-          *reinterpret_cast<uint4*>(d + p.dst_lo) = *reinterpret_cast<const uint4*>(ol);
-          s1 += st1.x + st1.y; s2 += st2.x + st2.y;
-        }
-      } else {
-#pragma unroll
-        for (int item = 0; item < S::IPB; ++item) {
-          const int lcol = item * 256 + stripe * 64;          // first column of the stripe within the set
-          const int ch0 = (set * S::SETCOLS + lcol) >> 3;     // its first output channel
-          // request the residual of the next item (an empty group keeps the group count uniform at the very end)
-          if (item + 1 < S::IPB) request_res(rbuf_i ^ 1, pix, set, item + 1);
-          else if (more) request_res(rbuf_i ^ 1, n_pix, cur.set, 0);
-          else cp_async_commit();
-          mbar_wait(&tmem_full[slot], sph);
-          tc_fence_after();
-#if UCDIR_MIX_PROBE == 4             // timing probe only: the MMA side alone (the epilogue hands every accumulator straight back)
-          { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[slot]); if (++slot == 2) { slot = 0; sph ^= 1; } continue; }
-#endif
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + stripe * 64);
-          const float4* ct = reinterpret_cast<const float4*>(ctab + cls * S::SETCOLS + lcol);
-          cp_async_wait1();                                   // everything but the request just made has landed
-          const uint4 res_cur = *reinterpret_cast<const uint4*>(smem + S::OFF_RES + ((warp - MX_FIRST_EPI_WARP) * 64 + rbuf_i * 32 + lane) * 16);
-          rbuf_i ^= 1;
-          const __nv_bfloat162* rr = reinterpret_cast<const __nv_bfloat162*>(&res_cur);
-          __align__(16) __nv_bfloat162 o[4];
-          float2 st1 = make_float2(0.f, 0.f), st2 = make_float2(0.f, 0.f);
-          // 16 columns (two output channels) per step; the TMEM load of step k+1 is in flight during the math of step k
-          uint32_t rbuf[2][16];
-          float4 cbuf[2][4];                                  // additive terms of step k / k+1 (read ahead of the TMEM wait)
-#if UCDIR_MIX_PROBE == 3           // timing probe only: the epilogue without its TMEM reads (math, table reads, stores and barriers stay)
-#define MX_TMEM_LD16(addr, dst) do { _Pragma("unroll") for (int z_ = 0; z_ < 16; ++z_) (dst)[z_] = __float_as_uint((float)(lane + z_)); } while (0)
-#else
-#define MX_TMEM_LD16(addr, dst) tmem_ld16(addr, dst)
-#endif
-          MX_TMEM_LD16(taddr, rbuf[0]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) cbuf[0][j] = ct[j];
-          tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (k < 3) {
-              MX_TMEM_LD16(taddr + 16 * (k + 1), rbuf[(k + 1) & 1]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) cbuf[(k + 1) & 1][j] = ct[4 * (k + 1) + j];
-            }
-            if (valid) {
-              const uint32_t* rv = rbuf[k & 1];
-              float hh[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float4 ca = cbuf[k & 1][2 * e], cb = cbuf[k & 1][2 * e + 1];
-                const float2 v0 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 0]), __uint_as_float(rv[e * 8 + 1])), rs2, make_float2(ca.x, ca.y));
-                const float2 v1 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 2]), __uint_as_float(rv[e * 8 + 3])), rs2, make_float2(ca.z, ca.w));
-                const float2 v2 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 4]), __uint_as_float(rv[e * 8 + 5])), rs2, make_float2(cb.x, cb.y));
-                const float2 v3 = __ffma2_rn(make_float2(__uint_as_float(rv[e * 8 + 6]), __uint_as_float(rv[e * 8 + 7])), rs2, make_float2(cb.z, cb.w));
-                // integration-module mix: 8 adjacent columns (c*8+s) -> channel c   (model/ucdir.py:136-140)
-                float2 h2 = __fmul2_rn(v0, aw2[0]);
-                h2 = __ffma2_rn(v1, aw2[1], h2);
-                float2 g2 = __fmul2_rn(v2, aw2[2]);
-                g2 = __ffma2_rn(v3, aw2[3], g2);
-                hh[e] = (h2.x + g2.x) + (h2.y + g2.y);
-              }
-              const float2 rf = __bfloat1622float2(rr[k]);
-              const float2 tv = make_float2(swish_half(hh[0]) + rf.x, swish_half(hh[1]) + rf.y);
-              o[k] = __floats2bfloat162_rn(tv.x, tv.y);
-              // statistics from the fp32 values (their bf16 rounding is zero-mean noise of relative size 2^-9)
-              st1 = __fadd2_rn(st1, tv);
-              st2 = __ffma2_rn(tv, tv, st2);
-            }
-            if (k < 3) tmem_ld_wait();
-            if (k == 2) {
-              // every accumulator value of this stripe is in registers: hand the slot back to the MMA issuer
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty[slot]);
-            }
-          }
-          if (++slot == 2) { slot = 0; sph ^= 1; }
+        if (SPLIT) {
           if (valid) {
-            *reinterpret_cast<uint4*>(p.dst + (size_t)pix * p.dstC + ch0) = *reinterpret_cast<const uint4*>(o);
-            s1 += st1.x + st1.y; s2 += st2.x + st2.y;
+            __nv_bfloat16* d = p.dst + (size_t)pix * p.dstC + ch0;
+            *reinterpret_cast<uint4*>(d) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(d + p.dst_lo) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
           }
+        } else {
+          // outputs replace the residual chunk; once all 16 warps have arrived the I/O warp stores the tile (rows outside the image
+          // are clipped by the TMA store)
+          *reinterpret_cast<uint4*>(io_ptr) = make_uint4(o[0], o[1], o[2], o[3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&out_done[io_t]);
+          if (++io_t == S::IO_TILES) { io_t = 0; io_ph ^= 1; }
         }
+        if (valid) { s1 += st1.x + st1.y; s2 += st2.x + st2.y; }
       }
     }
     if (p.dst_stats && stat_img >= 0) {
@@ -546,7 +549,8 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
 static const bool g_mix_pdl = []() { const char* e = getenv("UCDIR_PDL"); return !(e && e[0] == '0'); }();
 
 template <int CG, bool SPLIT = false>
-static int launch_mix_inst(const CUtensorMap& a, const CUtensorMap& b, const MixParams& p, int grid, cudaStream_t st) {
+static int launch_mix_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& r, const CUtensorMap& d, const MixParams& p, int grid,
+                           cudaStream_t st) {
   using S = MixCfg<CG, SPLIT>;
   static bool attr_dev[UCDIR_MAX_DEV] = {};
   bool& attr = attr_dev[cur_dev()];
@@ -562,7 +566,7 @@ static int launch_mix_inst(const CUtensorMap& a, const CUtensorMap& b, const Mix
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = g_mix_pdl ? 1 : 0;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, mix_halo_kernel<CG, SPLIT>, a, b, p) != cudaSuccess) {
+  if (cudaLaunchKernelEx(&cfg, mix_halo_kernel<CG, SPLIT>, a, b, r, d, p) != cudaSuccess) {
     set_error("tc_mix_halo: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return -3; }
   return 0;
 }
@@ -630,13 +634,28 @@ int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tc_mix_halo: cuTensorMapEncodeTiled(weights K=%d N=%d) failed: %d", Ktot, p.Ntot, (int)r); return -3; }
   }
+  // bf16: residual tiles in / output tiles out as TMA boxes of 32 channels x 8 x 16 pixels (64-byte rows, 64B swizzle; ucdir_mix.cu: tile I/O)
+  CUtensorMap mr = ma, md = ma;
+  if (!split) {
+    for (int k = 0; k < 2; ++k) {
+      const int pitch = k == 0 ? p.resC : p.dstC;
+      void* base = k == 0 ? const_cast<__nv_bfloat16*>(p.res) : p.dst;
+      cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+      cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 2 * p.W, (cuuint64_t)pitch * 2 * p.W * p.H};
+      cuuint32_t box[4] = {32, MX_TW, MX_TH, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = enc(k == 0 ? &mr : &md, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("tc_mix_halo: cuTensorMapEncodeTiled(%s C=%d pitch=%d) failed: %d", k == 0 ? "residual" : "destination", C, pitch, (int)r); return -3; }
+    }
+  }
   const int n_sm = sm_count();
   const int grid = units < n_sm ? (int)units : n_sm;       // persistent: one CTA per SM
   int rc;
-  if (split) rc = CG == 8 ? launch_mix_inst<8, true>(ma, mb, p, grid, st) : launch_mix_inst<16, true>(ma, mb, p, grid, st);
-  else if (CG == 8) rc = launch_mix_inst<8>(ma, mb, p, grid, st);
-  else if (CG == 16) rc = launch_mix_inst<16>(ma, mb, p, grid, st);
-  else rc = launch_mix_inst<32>(ma, mb, p, grid, st);
+  if (split) rc = CG == 8 ? launch_mix_inst<8, true>(ma, mb, mr, md, p, grid, st) : launch_mix_inst<16, true>(ma, mb, mr, md, p, grid, st);
+  else if (CG == 8) rc = launch_mix_inst<8>(ma, mb, mr, md, p, grid, st);
+  else if (CG == 16) rc = launch_mix_inst<16>(ma, mb, mr, md, p, grid, st);
+  else rc = launch_mix_inst<32>(ma, mb, mr, md, p, grid, st);
   if (rc) return rc;
   ++g_launches;
   return 0;
