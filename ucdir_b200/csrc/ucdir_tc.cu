@@ -60,6 +60,7 @@ struct TcParams {
   // fused upsample phases (UCDIR_TC_I_PHASES = 4): the four output parities of nearest-2x + conv3x3 in one launch; the phase is an
   // extra, slowest work-item dimension folded into the image-tile index (tiles_n = phases * tiles_n_real)
   int phases, tiles_n_real;
+  int io32;                    // bf16 destination (and residual) rows are 32-byte aligned per 16 columns: 256-bit stores / loads
 };
 
 // Which activation slab chunk j of a filter tap reads (map 0 / 1, channel coordinate) and, for batched weights, the K
@@ -494,12 +495,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             res_mix = res_next; res_mix_lo = res_next_lo;
           } else if (EPI != EPI_F32 && p.res) {
             const uint4* rp = reinterpret_cast<const uint4*>(res_row + ncol0 + c0);
+            if (CH % 16 == 0 && p.io32) {
 #pragma unroll
-            for (int j = 0; j < CH / 8; ++j) res_pl[j] = __ldg(rp + j);
+              for (int j = 0; j < CH / 8; j += 2) ld_global_nc_v8(rp + j, reinterpret_cast<uint32_t*>(&res_pl[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) res_pl[j] = __ldg(rp + j);
+            }
             if (SPLIT) {
               const uint4* rl = reinterpret_cast<const uint4*>(res_row + p.res_lo + ncol0 + c0);
+              if (CH % 16 == 0 && p.io32) {
 #pragma unroll
-              for (int j = 0; j < CH / 8; ++j) res_pl_lo[j] = __ldg(rl + j);
+                for (int j = 0; j < CH / 8; j += 2) ld_global_nc_v8(rl + j, reinterpret_cast<uint32_t*>(&res_pl_lo[j]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < CH / 8; ++j) res_pl_lo[j] = __ldg(rl + j);
+              }
             }
           }
         }
@@ -608,24 +619,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             }
           } else {
             __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst_row) + nb;
+            constexpr int SW = (CH % 16 == 0 && !SPLIT) ? 16 : 8;   // columns per store: 256-bit where the rows allow it (p.io32; SPLIT: register bound)
 #pragma unroll
-            for (int j = 0; j < CH; j += 8) {
-              __align__(16) __nv_bfloat162 o2[4];
-              __align__(16) __nv_bfloat162 l2[4];
+            for (int j = 0; j < CH; j += SW) {
+              uint32_t o2[SW / 2], l2[SW / 2];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                o2[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-                const float2 f = __bfloat1622float2(o2[e]);
+              for (int e = 0; e < SW / 2; ++e) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+                o2[e] = *reinterpret_cast<const uint32_t*>(&h);
+                const float2 f = __bfloat1622float2(h);
                 if (SPLIT) {
                   const float a = v[j + 2 * e], b = v[j + 2 * e + 1];
-                  l2[e] = __floats2bfloat162_rn(a - f.x, b - f.y);
+                  const __nv_bfloat162 l = __floats2bfloat162_rn(a - f.x, b - f.y);
+                  l2[e] = *reinterpret_cast<const uint32_t*>(&l);
                   t1s += a + b; t2s += a * a + b * b;
                 } else {
                   t1s += f.x + f.y; t2s += f.x * f.x + f.y * f.y;
                 }
               }
-              *reinterpret_cast<uint4*>(d + j) = *reinterpret_cast<const uint4*>(o2);
-              if (SPLIT) *reinterpret_cast<uint4*>(d + p.dst_lo + j) = *reinterpret_cast<const uint4*>(l2);
+              if (SW == 16 && p.io32) {
+                st_global_v8(d + j, o2);
+                if (SPLIT) st_global_v8(d + p.dst_lo + j, l2);
+              } else {
+#pragma unroll
+                for (int e = 0; e < SW / 8; ++e) {
+                  *reinterpret_cast<uint4*>(d + j + 8 * e) = make_uint4(o2[4 * e], o2[4 * e + 1], o2[4 * e + 2], o2[4 * e + 3]);
+                  if (SPLIT) *reinterpret_cast<uint4*>(d + p.dst_lo + j + 8 * e) = make_uint4(l2[4 * e], l2[4 * e + 1], l2[4 * e + 2], l2[4 * e + 3]);
+                }
+              }
             }
           }
         }
@@ -824,6 +845,9 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
     if (p.res) { p.res_lo = p.resC; p.resC *= 2; }
     if (p.dst2) { p.t_lo = p.t_ld; p.t_ld *= 2; }
   }
+  // 256-bit stores / residual loads: every 16-column step of a destination / residual row (and of its lo plane) starts on a 32-byte boundary
+  p.io32 = (!p.dst_f32 && p.dstC % 16 == 0 && p.dstCoff % 16 == 0 && p.dst_lo % 16 == 0 && (reinterpret_cast<uintptr_t>(p.dst) & 31) == 0 &&
+            (!p.res || (p.resC % 16 == 0 && p.res_lo % 16 == 0 && (reinterpret_cast<uintptr_t>(p.res) & 31) == 0))) ? 1 : 0;
   if (p.Ntot % NT) { set_error("tc_conv: Ntot=%d not a multiple of NT=%d", p.Ntot, NT); return -2; }
   if (p.gn) {
     if (!p.tg || !p.stats0 || (C1 > 0 && !p.stats1)) { set_error("tc_conv: GroupNorm fold needs tg and stats"); return -1; }
