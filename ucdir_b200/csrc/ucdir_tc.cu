@@ -364,6 +364,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     const int box = p.bw * p.bh;
     const int nn = r / box, rr = r - nn * box;
     const int yy = rr / p.bw, xx = rr - yy * p.bw;
+    // GroupNorm statistics of the stored tensor: when every lane of a warp works on the same image (one image per tile, or whole
+    // 32-row groups per image) the per-thread sums live in registers across items and are reduced when the tile's images change
+    // (the <= 8x8-pixel levels stack two images per tile: a warp reduction in double per item was 10 % of those launches)
+    const bool wu_stats = p.bn == 1 || (box & 31) == 0;
     constexpr int CH = NT < 32 ? 16 : 32;
     ItemCursor cur; cur.template init<BSTAT>(it0, n_sub, p.m_tiles, p.tiles_x, p.tiles_y);
     bool new_m = true;
@@ -385,10 +389,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         int tn = cur.tn_i, ph = 0;
         if (p.phases > 1) { ph = tn / p.tiles_n_real; tn -= ph * p.tiles_n_real; }
         const int im0 = tn * p.bn;
-        if (p.dst_stats && p.bn == 1 && im0 != stat_img) {
+        if (p.dst_stats && wu_stats && im0 != stat_img) {
           if (stat_img >= 0) {
             const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
-            if (lane == 0) { atomicAdd(p.dst_stats + 2 * stat_img, d1); atomicAdd(p.dst_stats + 2 * stat_img + 1, d2); }
+            if (lane == 0 && stat_img + nn < p.B) { atomicAdd(p.dst_stats + 2 * (stat_img + nn), d1); atomicAdd(p.dst_stats + 2 * (stat_img + nn) + 1, d2); }
           }
           stat_img = im0; s1 = 0.f; s2 = 0.f;
         }
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             for (int s = 0; s < 8; s += 2) h2 = __ffma2_rn(make_float2(v[c * 8 + s], v[c * 8 + s + 1]), make_float2(aw[s], aw[s + 1]), h2);
             const float h = h2.x + h2.y;
             if (SPLIT) {
-              const float t = swish_f(h) + (__bfloat162float(rres[c]) + __bfloat162float(rres_lo[c]));
+              const float t = swish_fast(h) + (__bfloat162float(rres[c]) + __bfloat162float(rres_lo[c]));   // ex2 / rcp.approx: ~3e-7 relative
               o[c] = __float2bfloat16(t);
               ol[c] = __float2bfloat16(t - __bfloat162float(o[c]));
               t1s += t; t2s += t * t;
@@ -575,7 +579,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           const int nb = ncol0 + c0;
           if (p.act == 1) {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = SPLIT ? swish_f(v[j]) : swish_fast(v[j]);
+            for (int j = 0; j < CH; ++j) v[j] = swish_fast(v[j]);   // ex2.approx + rcp.approx (~3e-7 relative: ample for SPLIT's 1e-3 / 1e-4 too)
           } else if (p.act == 2) {              // LeakyReLU(0.2) = max(0.2 x, x), model/ucdir.py:414-416 (predictor)
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = fmaxf(0.2f * v[j], v[j]);
@@ -658,19 +662,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       if (lane == 0) mbar_arrive(&tmem_empty[slot]);
       if (++slot == NSLOT) { slot = 0; sph ^= 1; }
       if (p.dst_stats) {
-        if (p.bn == 1) { s1 += t1s; s2 += t2s; }      // flushed when the image changes / at the end
-        else if ((box & 31) == 0) {                   // several images per tile, but one image per warp: reduce in the warp
-          const double d1 = warp_sum_d((double)t1s), d2 = warp_sum_d((double)t2s);
-          const int wimg = __shfl_sync(0xffffffffu, img, 0);
-          const bool wvalid = __shfl_sync(0xffffffffu, (int)valid, 0) != 0;
-          if (lane == 0 && wvalid) { atomicAdd(p.dst_stats + 2 * wimg, d1); atomicAdd(p.dst_stats + 2 * wimg + 1, d2); }
-        } else if (valid) { atomicAdd(p.dst_stats + 2 * img, (double)t1s); atomicAdd(p.dst_stats + 2 * img + 1, (double)t2s); }
+        if (wu_stats) { s1 += t1s; s2 += t2s; }       // flushed when the tile's images change / at the end
+        else if (valid) { atomicAdd(p.dst_stats + 2 * img, (double)t1s); atomicAdd(p.dst_stats + 2 * img + 1, (double)t2s); }
       }
       new_m = cur.template next<BSTAT>(n_sub, p.tiles_x, p.tiles_y, p.tiles_n);
     }
-    if (p.dst_stats && p.bn == 1 && stat_img >= 0) {
+    if (p.dst_stats && wu_stats && stat_img >= 0) {
       const double d1 = warp_sum_d((double)s1), d2 = warp_sum_d((double)s2);
-      if (lane == 0) { atomicAdd(p.dst_stats + 2 * stat_img, d1); atomicAdd(p.dst_stats + 2 * stat_img + 1, d2); }
+      if (lane == 0 && stat_img + nn < p.B) { atomicAdd(p.dst_stats + 2 * (stat_img + nn), d1); atomicAdd(p.dst_stats + 2 * (stat_img + nn) + 1, d2); }
     }
     tc_fence_before();
   }
