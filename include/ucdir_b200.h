@@ -247,7 +247,7 @@ enum ucdir_tc_int {
                                                   * OY0 = OX0 = -1, DST_UP = 1, DST_PY = DST_PX = 0 */
   UCDIR_TC_I_HALO = 43                           /* 1: halo schedule where it applies (grouped mix convs, C = 64 / 128 / 256): one 10 x 18 pixel TMA box per
                                                   * 8 x 16 pixel tile serves all nine taps, weights stay resident in shared memory (ucdir_mix.cu); 3x3 convs with 64 / 128 output
-                                                  * channels: super tiles (ucdir_dhalo.cu).  With SPLIT = 1: the grouped mix convs with C = 64 / 128 (hi and lo boxes, both
+                                                  * channels: super tiles (ucdir_dhalo.cu).  With SPLIT = 1: the grouped mix convs with C = 64 / 128 / 256 (hi and lo boxes, both
                                                   * weight planes resident); every other SPLIT op runs the streamed schedule */
 };
 enum ucdir_tc_flt { UCDIR_TC_F_EPS = 0, UCDIR_TC_F_ALPHA = 1 /* 0 = 1.0 */ };

@@ -245,7 +245,8 @@ def join_planes(t, C):
 
 
 @pytest.mark.parametrize("halo", [0, 1], ids=["streamed", "halo"])
-@pytest.mark.parametrize("C,B,H,W", [(64, 2, 16, 16), (128, 1, 24, 16), (64, 1, 128, 128), (128, 3, 64, 64), (64, 2, 36, 20), (128, 2, 18, 18)])
+@pytest.mark.parametrize("C,B,H,W", [(64, 2, 16, 16), (128, 1, 24, 16), (64, 1, 128, 128), (128, 3, 64, 64), (64, 2, 36, 20), (128, 2, 18, 18),
+                                     (256, 3, 32, 32), (256, 1, 18, 18), (256, 3, 8, 8)])
 def test_tc_grouped_mix_split(C, B, H, W, halo):
     """fp32_tc form of the integration-module conv: (hi, lo) plane pairs, three passes per tap, fp32 epilogue.  halo=1 is
     mix_halo_kernel<CG, SPLIT> (hi and lo halo boxes in a three-stage ring, both weight planes resident); both schedules are held

@@ -80,19 +80,22 @@ constexpr int MX_REGS_LOW = 40, MX_REGS_HIGH = 104;
 // hi box is in flight), and the epilogue works in fp32 (exact Swish, residual = hi + lo, (hi, lo) stores).
 template <int CG, bool SPLIT = false>
 struct MixCfg {
-  static_assert(!(SPLIT && CG == 32), "SPLIT: both weight planes of a C = 256 item exceed shared memory");
   static constexpr int C = 8 * CG;                         // channels; columns per group NG = 8C / 8 = C
   static constexpr int NG = C;
   // MMAs per tap and 256-column item.  C = 64: groups 2j and 2j+1 live in the same 32-byte K slice of the pixel row (their
   // weight rows carry zeros for the other group's 8 channels), so ONE N = 128 MMA serves both -- the A slice is read from
   // shared memory once instead of twice (at N = 64 the operand reads, 6 KB per 32 tensor cycles, exceed the 128 B/clk port).
-  static constexpr int NSPLIT = CG == 8 ? 2 : 256 / NG;    // 2 / 2 / 1
-  static constexpr int NSUB = 256 / NSPLIT;                // columns per MMA
+  // columns of an item (one accumulator slot).  SPLIT, C = 256: both weight planes of a 256-column item exceed shared memory, so an
+  // item is half a group (128 columns, N = 128 MMAs; the two upper epilogue stripes idle -- this mode is MMA bound)
+  static constexpr int ICOLS = (SPLIT && CG == 32) ? 128 : 256;
+  static constexpr int NSPLIT = CG == 8 ? 2 : (ICOLS > NG ? ICOLS / NG : 1);    // 2 / 2 / 1
+  static constexpr int NSUB = ICOLS / NSPLIT;              // columns per MMA
   static constexpr int KB = CG < 16 ? 16 : CG;             // K elements per tap and group (C = 64: 8 real + 8 foreign, zero weights)
   static constexpr int KSTEPS = KB / 16;
   static constexpr int IPB = (CG == 32 || SPLIT) ? 1 : 2;  // items that share one halo box (= one 64-channel chunk)
-  static constexpr int SETCOLS = 256 * IPB;
-  static constexpr int BSLAB = 256 * KB * 2;               // one tap's weight slab of one item (and plane)
+  static constexpr int SETCOLS = ICOLS * IPB;
+  static constexpr int BSLAB = ICOLS * KB * 2;             // one tap's weight slab of one item (and plane)
+  static constexpr int EPI_ACTIVE = 4 * (ICOLS / 64);      // epilogue warps with a stripe inside the item
   static constexpr int NPL = SPLIT ? 2 : 1;                // resident weight planes: slab index = item * 9 + tap, SPLIT: tap * 2 + plane
   static constexpr int NBOX = SPLIT ? 2 : 1;               // halo boxes per unit (SPLIT: lo plane, then hi plane)
   static constexpr int ASTAGES = SPLIT ? 3 : 2;
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
   if (threadIdx.x == 0) {
     prefetch_tmap(&mapA); prefetch_tmap(&mapB);
     for (int s = 0; s < MX_ASTAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int j = 0; j < 2; ++j) { mbar_init(&tmem_full[j], 1); mbar_init(&tmem_empty[j], MX_EPI_WARPS); }
+    for (int j = 0; j < 2; ++j) { mbar_init(&tmem_full[j], 1); mbar_init(&tmem_empty[j], S::EPI_ACTIVE); }
     mbar_init(bfull, 1); mbar_init(bfree, 1);
     for (int j = 0; j < S::IO_TILES; ++j) { mbar_init(&res_full[j], 1); mbar_init(&out_done[j], MX_EPI_WARPS); }
     if (!SPLIT) { prefetch_tmap(&mapR); prefetch_tmap(&mapD); }
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
                 tma_load_2d(&mapB, bfull, wres + i * S::BSLAB, (tap * 3 + plane * 2) * S::KB, cur.set * S::SETCOLS);
               } else {
                 const int item = i / 9, tap = i - item * 9;
-                tma_load_2d(&mapB, bfull, wres + i * S::BSLAB, tap * S::KB, cur.set * S::SETCOLS + item * 256);
+                tma_load_2d(&mapB, bfull, wres + i * S::BSLAB, tap * S::KB, cur.set * S::SETCOLS + item * S::ICOLS);
               }
             }
           }
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
             tc_fence_after();
             if (elect_one()) {
               const uint32_t tacc = tmem_base + (uint32_t)(slot * 256);
-              const int g0 = (set * S::SETCOLS + item * 256) / S::NG;            // first group of the item
+              const int g0 = (set * S::SETCOLS + item * S::ICOLS) / S::NG;        // first group of the item
               constexpr int GPS = S::NSUB / S::NG;                                // groups per MMA
               constexpr uint32_t a_hi = desc_hi(MX_BW * 128, 2u), b_hi = desc_hi(8 * S::KB * 2, S::KB * 2 == 64 ? 4u : 6u);
               // the 32-byte K slice of the 128-byte pixel row that holds the first group of split sp, as a descriptor offset
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
         UnitCursor cs = cl;                                               // cursor of the next item to store
         int il = 0, is = 0;                                               // item of the unit (0 .. IPB-1) of either cursor
         int tl = 0;                                                       // tile of the next load
-        auto chan0 = [&](const UnitCursor& c, int item) { return (c.set * S::SETCOLS + item * 256) >> 3; };
+        auto chan0 = [&](const UnitCursor& c, int item) { return (c.set * S::SETCOLS + item * S::ICOLS) >> 3; };
         auto load_next = [&]() {
           mbar_expect_tx(&res_full[tl], (uint32_t)S::IO_TILE);
           tma_load_4d(&mapR, &res_full[tl], smem + S::OFF_RES + tl * S::IO_TILE, chan0(cl, il), cl.tx * MX_TW, cl.ty * MX_TH, cl.img);
@@ -429,7 +432,8 @@ __global__ void __launch_bounds__(MX_THREADS, 1) mix_halo_kernel(const __grid_co
       if (left > 1) fetch_unit();                            // ... and those of the next unit are requested now
 #pragma unroll
       for (int item = 0; item < S::IPB; ++item) {
-        const int lcol = item * 256 + stripe * 64;           // first column of the stripe within the set
+        if (stripe * 64 >= S::ICOLS) continue;               // (SPLIT, C = 256: 128-column items -- this warp's stripe does not exist)
+        const int lcol = item * S::ICOLS + stripe * 64;      // first column of the stripe within the set
         const int ch0 = (set * S::SETCOLS + lcol) >> 3;      // its first output channel
         uint4 res_h = make_uint4(0u, 0u, 0u, 0u), res_l = res_h;
         if (SPLIT && valid) {                                // fp32_tc: plain loads of the two residual planes (the MMA side needs three
@@ -576,8 +580,8 @@ bool tc_mix_halo_applies(const ucdir_op_t& op) {
   const int C = op.i[UCDIR_TC_I_C0], H = op.i[UCDIR_TC_I_H], W = op.i[UCDIR_TC_I_W];
   const int KB = op.i[UCDIR_TC_I_KB] ? op.i[UCDIR_TC_I_KB] : op.i[UCDIR_TC_I_KC];
   const bool split = op.i[UCDIR_TC_I_SPLIT] != 0;
-  // SPLIT (fp32_tc): C = 64 / 128 (both weight planes of a C = 256 item do not fit), default plane layout [hi: C | lo: C]
-  if (split && (C == 256 || (op.i[UCDIR_TC_I_SRC_LO_OFF] != 0 && op.i[UCDIR_TC_I_SRC_LO_OFF] != C) || op.i[UCDIR_TC_I_W_LO_OFF] != 0)) return false;
+  // SPLIT (fp32_tc): default plane layout [hi: C | lo: C]
+  if (split && ((op.i[UCDIR_TC_I_SRC_LO_OFF] != 0 && op.i[UCDIR_TC_I_SRC_LO_OFF] != C) || op.i[UCDIR_TC_I_W_LO_OFF] != 0)) return false;
   const int cs = split ? 2 * C : C;
   return op.i[UCDIR_TC_I_HALO] == 1 && op.i[UCDIR_TC_I_MODE] == 1 && op.i[UCDIR_TC_I_GROUPS] == 8 && (C == 64 || C == 128 || C == 256) &&
          op.i[UCDIR_TC_I_C1] == 0 && op.i[UCDIR_TC_I_NTOT] == 8 * C && op.i[UCDIR_TC_I_GN] == 1 && op.i[UCDIR_TC_I_NCLS] == 9 &&
@@ -606,7 +610,7 @@ int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st) {
   p.gn_count = (double)C * p.H * p.W;
   p.tiles_x = (p.W + MX_TW - 1) / MX_TW; p.tiles_y = (p.H + MX_TH - 1) / MX_TH;
   const long long mt = (long long)p.tiles_x * p.tiles_y * p.B;
-  const int setcols = (CG == 32 || split) ? 256 : 512;
+  const int setcols = split ? (CG == 32 ? 128 : 256) : (CG == 32 ? 256 : 512);
   const long long units = mt * (p.Ntot / setcols);
   if (units > 0x7fffffffLL || (long long)p.B * p.H * p.W > 0x7fffffffLL) { set_error("tc_mix_halo: too many units / pixels"); return -2; }
   p.m_tiles = (int)mt; p.n_units = (int)units;
@@ -627,7 +631,7 @@ int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st) {
     const int Ktot = 9 * KB * (split ? 3 : 1);               // SPLIT: [W_hi | W_hi | W_lo] per tap
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p.Ntot};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KB, 256};
+    cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)((split && CG == 32) ? 128 : 256)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.p[UCDIR_TC_P_W]), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
@@ -652,7 +656,8 @@ int launch_tc_mix_halo(const ucdir_op_t& op, cudaStream_t st) {
   const int n_sm = sm_count();
   const int grid = units < n_sm ? (int)units : n_sm;       // persistent: one CTA per SM
   int rc;
-  if (split) rc = CG == 8 ? launch_mix_inst<8, true>(ma, mb, mr, md, p, grid, st) : launch_mix_inst<16, true>(ma, mb, mr, md, p, grid, st);
+  if (split) rc = CG == 8 ? launch_mix_inst<8, true>(ma, mb, mr, md, p, grid, st)
+                : (CG == 16 ? launch_mix_inst<16, true>(ma, mb, mr, md, p, grid, st) : launch_mix_inst<32, true>(ma, mb, mr, md, p, grid, st));
   else if (CG == 8) rc = launch_mix_inst<8>(ma, mb, mr, md, p, grid, st);
   else if (CG == 16) rc = launch_mix_inst<16>(ma, mb, mr, md, p, grid, st);
   else rc = launch_mix_inst<32>(ma, mb, mr, md, p, grid, st);
