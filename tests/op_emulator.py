@@ -414,11 +414,20 @@ def emu_tc_conv(op, mem):
                 rows = slice(gi * Ng, (gi + 1) * Ng)
                 acc[..., rows] += patch[..., cb:cb + cg_eff] @ wp[rows, ty * ntx + tx].t()
     if g("RES_FUSED"):                                           # the block's 1x1 res_conv of the same (un-normalised) input
-        w2 = mem.view(_p(op, "UCDIR_TC_P_W2"), (Ntot, Cin), bf).float()
         b2 = mem.view(_p(op, "UCDIR_TC_P_TB2"), (Ntot,))
         rC = g("DST_RES_C")
-        dres = mem.view(_p(op, "UCDIR_TC_P_DST_RES"), (B, H, W, rC), bf)
-        dres[..., :Ntot] = (x @ w2.t() + b2.view(1, 1, 1, -1)).to(bf)
+        if split:                                                # weights [s0 hi | s0 hi | s1 hi | s1 hi | s0 lo | s1 lo], (hi, lo) output planes
+            w23 = mem.view(_p(op, "UCDIR_TC_P_W2"), (Ntot, 3 * Cin), bf).float()
+            h0, _, h1, _, l0, l1 = torch.split(w23, [C0, C0, C1, C1, C0, C1], dim=-1)
+            w2 = torch.cat([h0 + l0, h1 + l1], dim=-1)
+            r32 = x @ w2.t() + b2.view(1, 1, 1, -1)
+            dres = mem.view(_p(op, "UCDIR_TC_P_DST_RES"), (B, H, W, 2 * rC), bf)
+            dres[..., :Ntot] = r32.to(bf)
+            dres[..., rC:rC + Ntot] = (r32 - r32.to(bf).float()).to(bf)
+        else:
+            w2 = mem.view(_p(op, "UCDIR_TC_P_W2"), (Ntot, Cin), bf).float()
+            dres = mem.view(_p(op, "UCDIR_TC_P_DST_RES"), (B, H, W, rC), bf)
+            dres[..., :Ntot] = (x @ w2.t() + b2.view(1, 1, 1, -1)).to(bf)
     tb = mem.view(_p(op, "UCDIR_TC_P_TB"), (ncls if gn else 1, Ntot))
     if gn:
         s0 = mem.view(_p(op, "UCDIR_TC_P_STATS0"), (B, 2), torch.float64).clone()

@@ -448,11 +448,13 @@ def test_fp32_tc_graph_meets_fp32_tolerance(emulated, golden, sid_weights):
         sess = next(iter(eng._sessions.values()))
         _lib.check_ops(sess.step_ops.array(), len(sess.step_ops))
         tc = [o for o in sess.step_ops.ops if o.kind == _lib.C["UCDIR_OP_TC_CONV"]]
-        # split records run the streamed kernel, except the integration-module convs with C = 64 / 128 / 256 (halo mix kernel, SPLIT form)
+        # split records run the streamed kernel, except the integration-module convs with C = 64 / 128 / 256 (halo mix kernel, SPLIT form), the in-conv and conv1 + res_conv (halo dense kernel)
         I = lambda o, k: o.i[_lib.C["UCDIR_TC_I_" + k]]
         assert tc and all(I(o, "SPLIT") == 1 for o in tc)
         for o in tc:
             want = 1 if (I(o, "MODE") == 1 and I(o, "C0") in (64, 128, 256) and I(o, "H") >= 2 and I(o, "W") >= 2) else 0
+            if I(o, "MODE") == 0 and I(o, "NTY") == 3 and (I(o, "KC") == 16 or I(o, "RES_FUSED")):
+                want = 2                                         # the in-conv and conv1 + fused res_conv: halo dense kernel, SPLIT form
             assert _lib.tc_schedule(o) == want, (I(o, "MODE"), I(o, "C0"), _lib.tc_schedule(o))
         assert any(_lib.tc_schedule(o) == 1 for o in tc)
         close(eps, g["eps"])

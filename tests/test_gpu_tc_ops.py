@@ -289,6 +289,78 @@ def test_tc_grouped_mix_split(C, B, H, W, halo):
     assert_close(got, want, "split mix dst vs torch.nn.functional", rtol=1e-3, atol=1e-4)
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(seed=41, B=2, H=40, W=72, C0=16, C1=0, Cout=64, gn=False, act_=0, kc=16),          # the in-conv
+    dict(seed=42, B=1, H=128, W=128, C0=16, C1=0, Cout=64, gn=False, act_=0, kc=16),
+    dict(seed=43, B=2, H=40, W=72, C0=64, C1=64, Cout=64, fuse_res=True),                     # + fused 1x1 res_conv, concat input
+    dict(seed=44, B=1, H=64, W=64, C0=128, C1=64, Cout=64, fuse_res=True),
+    dict(seed=45, B=2, H=32, W=48, C0=256, C1=128, Cout=128, fuse_res=True),
+    dict(seed=46, B=2, H=24, W=20, C0=64, C1=0, Cout=128, fuse_res=True),
+], ids=lambda c: "C%d+%d_%d_%dx%dx%d%s" % (c["C0"], c["C1"], c["Cout"], c["B"], c["H"], c["W"], "_res" if c.get("fuse_res") else ""))
+def test_tc_dense_halo_split(cfg):
+    """fp32_tc form of csrc/ucdir_dhalo.cu: (hi, lo) plane pairs, per channel chunk a lo box (x W_hi) and a hi box (x W_hi, x W_lo);
+    used for the 16-channel in-conv and for conv1 with the block's 1x1 res_conv riding along.  fp32-class tolerance against the op
+    interpreter and against torch.nn.functional in the reference's form (model/ucdir.py:109-111,120)."""
+    cfg = dict(dict(ks=3, gn=True, act_=1, kc=64, fuse_res=False), **cfg)
+    g = torch.Generator().manual_seed(cfg["seed"])
+    B, H, W, C0, C1, Cout, gn, act_, kc, fuse = (cfg[k] for k in ("B", "H", "W", "C0", "C1", "Cout", "gn", "act_", "kc", "fuse_res"))
+    Cin = C0 + C1
+    c = Case()
+    x0 = rnd(g, B, H, W, C0) + 0.3
+    c.add("x0", split_planes(x0))
+    x0v = join_planes(c.t["x0"], C0)
+    xv = x0v
+    if C1:
+        x1 = rnd(g, B, H, W, C1) * 0.7 - 0.2
+        c.add("x1", split_planes(x1))
+        xv = torch.cat([x0v, join_planes(c.t["x1"], C1)], dim=-1)
+    w = rnd(g, Cout, Cin, 3, 3, scale=1.0 / np.sqrt(Cin * 9))
+    bias = rnd(g, Cout, scale=0.1)
+    gamma = 1 + 0.3 * rnd(g, Cin) if gn else None
+    beta = 0.2 * rnd(g, Cin) if gn else None
+    nt = E._tc_nt(Cout)
+    wp, tb, tg = E.pack_tc_dense(w, bias, nt, gamma, beta, split=True, c0=C0)
+    c.add("w", wp).add("tb", tb)
+    if tg is not None:
+        c.add("tg", tg)
+    if gn:
+        c.add("s0", stats_of(x0v))
+        if C1:
+            c.add("s1", stats_of(join_planes(c.t["x1"], C1)))
+    c.add("dst", torch.zeros(B, H, W, 2 * Cout, dtype=BF)).add("dstats", torch.zeros(B, 2, dtype=torch.float64))
+    if fuse:
+        w2 = rnd(g, Cout, Cin, 1, 1, scale=1.0 / np.sqrt(Cin))
+        b2 = rnd(g, Cout, scale=0.1)
+        w2p, tb2, _ = E.pack_tc_dense(w2, b2, nt, split=True, c0=C0)
+        c.add("w2", w2p).add("tb2", tb2).add("dres", torch.zeros(B, H, W, 2 * Cout, dtype=BF))
+
+    def sact(t, C, stats=None):
+        return E.Act(t, C, H, W, stats.data_ptr() if stats is not None else 0, True, True)
+
+    def build(t):
+        ol = E.OpList()
+        extra = dict(w2=t["w2"].data_ptr(), tb2=t["tb2"].data_ptr(), dst_res=sact(t["dres"], Cout)) if fuse else {}
+        E._tc_op(ol, **extra, split=1, src0=sact(t["x0"], C0, t.get("s0")), src1=sact(t["x1"], C1, t.get("s1")) if C1 else None,
+                 w=t["w"].data_ptr(), tb=t["tb"].data_ptr(), tg=t["tg"].data_ptr() if "tg" in t else 0, gn=1 if gn else 0,
+                 ncls=9 if gn else 1, act=act_, dst=sact(t["dst"], Cout, t["dstats"]), ntot=Cout, B=B, nt=nt, halo=1, kc=kc)
+        return ol
+    assert _lib.tc_schedule(build(c.on("cpu")).array()[0]) == 2
+    host, dev = run_both(c, build)
+    got = join_planes(dev["dst"], Cout)
+    assert_close(got, join_planes(host["dst"], Cout), "split dense dst vs interpreter", rtol=1e-3, atol=1e-4)
+    assert_close(dev["dstats"], host["dstats"], "stats", rtol=1e-4, atol=1e-4)      # per-thread fp32 partial sums, double across threads
+    F = torch.nn.functional
+    xn = xv.permute(0, 3, 1, 2)
+    y = F.conv2d(F.group_norm(xn, 1, gamma, beta, eps=1e-5) if gn else xn, w, bias, padding=1)
+    if act_ == 1:
+        y = y * torch.sigmoid(y)
+    assert_close(got, y.permute(0, 2, 3, 1), "split dense dst vs torch.nn.functional", rtol=1e-3, atol=1e-4)
+    if fuse:
+        want = F.conv2d(xn, w2, b2).permute(0, 2, 3, 1)
+        assert_close(join_planes(dev["dres"], Cout), want, "fused res_conv vs torch.nn.functional", rtol=1e-3, atol=1e-4)
+        assert_close(join_planes(dev["dres"], Cout), join_planes(host["dres"], Cout), "fused res_conv vs interpreter", rtol=1e-3, atol=1e-4)
+
+
 def test_tc_upsample_phases_equal_upsample_then_conv():
     """Four 2x2-tap phase convolutions == nearest-2x + conv3x3 (model/ucdir.py:53-60), checked against torch."""
     g = torch.Generator().manual_seed(9)

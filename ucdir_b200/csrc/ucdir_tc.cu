@@ -832,8 +832,8 @@ int launch_tc_conv(const ucdir_op_t& op, cudaStream_t st, bool dry) {
   // fp32-tolerance mode: (hi, lo) plane pairs, three K passes per tap
   p.a0_lo = p.a1_lo = p.b_lo = p.dst_lo = p.res_lo = p.t_lo = 0;
   if (split) {
-    if (op.i[UCDIR_TC_I_SRC_GN_SWISH] || op.i[UCDIR_TC_I_RES_FUSED] || op.i[UCDIR_TC_I_BSTAT] || op.i[UCDIR_TC_I_SPS3]) {
-      set_error("tc_conv: SPLIT runs on the streamed kernel only (no SRC_GN_SWISH / RES_FUSED / BSTAT / SPS3)"); return -2; }
+    if (op.i[UCDIR_TC_I_SRC_GN_SWISH] || op.i[UCDIR_TC_I_BSTAT] || op.i[UCDIR_TC_I_SPS3]) {
+      set_error("tc_conv: SPLIT has no SRC_GN_SWISH / BSTAT / SPS3 form"); return -2; }
     p.a0_lo = op.i[UCDIR_TC_I_SRC_LO_OFF] ? op.i[UCDIR_TC_I_SRC_LO_OFF] : (p.groups > 1 ? Cin : C0);
     p.a1_lo = C1;
     p.b_lo = op.i[UCDIR_TC_I_W_LO_OFF];

@@ -947,7 +947,8 @@ class UNetEngine:
             h1 = bld.new(cout, x.H, x.W)
             has_res = ws.has(name + ".res.tcw")
             # the halo schedule computes the 1x1 res_conv from the activation box conv1 already holds in shared memory
-            fuse_res = (has_res and not split and _TC_HALO and _TC_FUSE_RES and cout in (64, 128) and x.C % 64 == 0 and
+            # (fp32_tc too: the split form of the halo kernel visits the hi and lo boxes of every chunk)
+            fuse_res = (has_res and _TC_HALO and _TC_FUSE_RES and cout in (64, 128) and x.C % 64 == 0 and
                         (skip is None or skip.C % 64 == 0))
             res = bld.new(cout, x.H, x.W, with_stats=False) if has_res else None
             _tc_op(ol, split=sp, src0=x, src1=skip, w=ws.ptr(name + ".conv1.tcw"), tb=ws.ptr(name + ".conv1.tb"),
