@@ -53,7 +53,7 @@ if os.path.exists(lc):
 
 summ = []
 top = None
-WHAT = {"mix_halo_kernel<8>": ("downs.1 spdyconv + integration mix, C=64, 121 tiles x 128x128 (the single most expensive launch of the step; 5 such launches per step)",
+WHAT = {"mix_halo_kernel<8, 0>": ("downs.1 spdyconv + integration mix, C=64, 121 tiles x 128x128 (the single most expensive launch of the step; 5 such launches per step)",
                                824705024, "per pixel: h1 in (64 bf16) + guidance map (8 fp32) + residual (64 bf16) + out (64 bf16); weights 0.15 MB")}
 for rep in ("prof_halo.ncu-rep", "prof_tc.ncu-rep", "prof_attn.ncu-rep"):
     path = os.path.join(G, rep)

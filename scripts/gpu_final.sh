@@ -24,7 +24,7 @@ echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -c 4000 --csv --log-file $O/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu --no-eager --no-parity-mode > $O/ncu_bench.log 2>&1; echo "rc=$?"
 echo "== ncu full: mix halo + dense halo + streamed conv"
 timeout 500 ncu --set full --clock-control none --import-source on -k "regex:(mix_halo|dense_halo)_kernel" -s 1 -c 2 -o $O/prof_halo -f python bench.py --steps 1 --warmup 3 --no-cpu --no-eager --no-parity-mode > $O/ncu_halo.log 2>&1; echo "rc=$?"
-timeout 500 ncu --set full --clock-control none --import-source on -k "regex:tc_conv_kernel" -s 12 -c 3 -o $O/prof_tc -f python bench.py --steps 1 --warmup 3 --no-cpu --no-eager --no-parity-mode > $O/ncu_tc.log 2>&1; echo "rc=$?"
+timeout 500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:tc_conv_kernel<\(int\)64, \(int\)64, \(int\)256, \(int\)1, \(int\)[01]," -s 10 -c 3 -o $O/prof_tc -f python bench.py --steps 1 --warmup 3 --no-cpu --no-eager --no-parity-mode > $O/ncu_tc.log 2>&1; echo "rc=$?"
 echo "== ncu full: flash attention at 16384 tokens (reference tiling)"
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:flash_attn_kernel" -c 1 -o $O/prof_attn -f python bench.py --workload c3_1152_ref_tiling --steps 1 --warmup 3 --no-cpu --no-eager --no-parity-mode > $O/ncu_attn.log 2>&1; echo "rc=$?"
 ls -la $O/*.ncu-rep
