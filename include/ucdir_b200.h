@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define UCDIR_ABI_VERSION 13
+#define UCDIR_ABI_VERSION 14
 
 #define UCDIR_OP_NPTR 16
 #define UCDIR_OP_NINT 56
@@ -46,11 +46,19 @@ extern "C" {
 
 typedef struct ucdir_op {
   int32_t kind;                 /* enum ucdir_op_kind */
-  int32_t flags;                /* reserved, 0 */
+  int32_t flags;                /* UCDIR_OP_FLAG_* (0 = none) */
   void*   p[UCDIR_OP_NPTR];     /* device pointers, meaning per kind (enums below) */
   int32_t i[UCDIR_OP_NINT];     /* integers, meaning per kind */
   float   f[UCDIR_OP_NFLT];     /* floats, meaning per kind */
 } ucdir_op_t;
+
+/* Op flags.  An op list is a sequential program; the flags only tell ucdir_graph_capture which ops need not wait for each other:
+ * a BRANCH op is captured on a side stream forked from the main stream just before it (it depends on everything before it, nothing
+ * after it depends on it) until the next op flagged JOIN, which waits for the side stream as well.  ucdir_run_ops ignores the flags and
+ * runs the list in order.  The caller guarantees that no op between a BRANCH op and its JOIN reads what the BRANCH op writes or writes
+ * what it reads (engine.py: a block's 1x1 res_conv beside its conv1, joined at the integration conv that reads both). */
+#define UCDIR_OP_FLAG_BRANCH 1
+#define UCDIR_OP_FLAG_JOIN 2
 
 enum ucdir_op_kind {
   UCDIR_OP_CONV_F32 = 1,

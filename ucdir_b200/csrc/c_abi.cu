@@ -132,16 +132,34 @@ int ucdir_graph_capture(const ucdir_op_t* ops, int n_ops, void** graph_out) {
   if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     ucdir::set_error("graph_capture: begin: %s", cudaGetErrorString(cudaGetLastError())); cudaStreamDestroy(cs); return -3; }
   int rc = 0;
+  // UCDIR_OP_FLAG_BRANCH / JOIN: a side stream forked from (and joined back into) the capturing stream turns the flagged ops into
+  // parallel branches of the graph (UCDIR_GRAPH_BRANCH=0: capture the list strictly in order)
+  static const bool branches = []() { const char* e = getenv("UCDIR_GRAPH_BRANCH"); return !(e && e[0] == '0'); }();
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool pending = false;
+  auto join = [&]() { if (pending) { cudaEventRecord(ev_join, side); cudaStreamWaitEvent(cs, ev_join, 0); pending = false; } };
   for (int k = 0; k < n_ops && !rc; ++k) {
     ucdir::NvtxOp range(ops[k], k);
-    rc = ucdir::dispatch(ops[k], cs, false);
+    if (ops[k].flags & UCDIR_OP_FLAG_JOIN) join();
+    cudaStream_t target = cs;
+    if (branches && (ops[k].flags & UCDIR_OP_FLAG_BRANCH)) {
+      if (!side && (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)) {
+        ucdir::set_error("graph_capture: side stream: %s", cudaGetErrorString(cudaGetLastError())); rc = -3; break; }
+      join();                                         // one branch at a time
+      cudaEventRecord(ev_fork, cs); cudaStreamWaitEvent(side, ev_fork, 0);
+      target = side; pending = true;
+    }
+    rc = ucdir::dispatch(ops[k], target, false);
     if (rc) { char tmp[400]; snprintf(tmp, sizeof(tmp), "%s", ucdir::g_err); ucdir::set_error("graph_capture: op %d (kind %d): %s", k, ops[k].kind, tmp); }
   }
+  join();
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(cs, &g);
   const long long kernels = ucdir::g_launches - before;
   ucdir::g_launches = before;                       // nothing ran yet; launches are counted per replay
   cudaStreamDestroy(cs);
+  if (side) { cudaStreamDestroy(side); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
   if (rc) { if (g) cudaGraphDestroy(g); return rc; }
   if (e != cudaSuccess || !g) { ucdir::set_error("graph_capture: end: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return -3; }
   cudaGraphExec_t ex = nullptr;

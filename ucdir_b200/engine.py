@@ -276,8 +276,10 @@ class OpList:
         self.ops: List[_lib.Op] = []
         self._arr = None
 
-    def add(self, kind, p=None, i=None, f=None) -> int:
-        self.ops.append(_lib.make_op(kind, p, i, f))
+    def add(self, kind, p=None, i=None, f=None, flags: int = 0) -> int:
+        op = _lib.make_op(kind, p, i, f)
+        op.flags = flags
+        self.ops.append(op)
         self._arr = None
         return len(self.ops) - 1
 
@@ -469,7 +471,7 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
            w_batched: int = 0, w_rowstride: int = 0, w_batchstride: int = 0, alpha: float = 0.0, dst2: int = 0, t_col0: int = 0,
            t_ld: int = 0, w_rows: int = 0, row3: Optional[int] = None, halo: Optional[int] = None, src_gn_swish: int = 0,
            src_gamma: int = 0, src_beta: int = 0, w2: int = 0, tb2: int = 0, dst_res: Optional[Act] = None,
-           split: int = 0, src_lo_off: int = 0, w_lo_off: int = 0, dst_crop: int = 0, phases: int = 0):
+           split: int = 0, src_lo_off: int = 0, w_lo_off: int = 0, dst_crop: int = 0, phases: int = 0, flags: int = 0):
     H, W = (dst.H // 2, dst.W // 2) if dst_up else (dst.H, dst.W)
     p = {"UCDIR_TC_P_SRC0": src0.ptr, "UCDIR_TC_P_W": w, "UCDIR_TC_P_TB": tb, "UCDIR_TC_P_DST": dst.ptr}
     if src1 is not None: p["UCDIR_TC_P_SRC1"] = src1.ptr
@@ -505,7 +507,7 @@ def _tc_op(ol: OpList, *, src0: Act, w: int, tb: int, dst: Act, ntot: int, B: in
     if dst_res is not None:                  # fused 1x1 res_conv of the same input (halo schedule only)
         p["UCDIR_TC_P_W2"], p["UCDIR_TC_P_TB2"], p["UCDIR_TC_P_DST_RES"] = w2, tb2, dst_res.ptr
         i["UCDIR_TC_I_RES_FUSED"], i["UCDIR_TC_I_DST_RES_C"] = 1, dst_res.C
-    ol.add("UCDIR_OP_TC_CONV", p, i, {"UCDIR_TC_F_EPS": eps, "UCDIR_TC_F_ALPHA": alpha})
+    ol.add("UCDIR_OP_TC_CONV", p, i, {"UCDIR_TC_F_EPS": eps, "UCDIR_TC_F_ALPHA": alpha}, flags=flags)
 
 
 _TC_ROW3 = 0 if os.environ.get("UCDIR_TC_ROW3", "1") == "0" else 1
@@ -951,13 +953,17 @@ class UNetEngine:
             fuse_res = (has_res and _TC_HALO and _TC_FUSE_RES and cout in (64, 128) and x.C % 64 == 0 and
                         (skip is None or skip.C % 64 == 0))
             res = bld.new(cout, x.H, x.W, with_stats=False) if has_res else None
+            # a separate 1x1 res_conv reads the same input as conv1 and is first read by the integration conv: it is emitted as a
+            # BRANCH of the step graph (captured on a forked stream, joined at the integration conv) -- at the coarse levels of a small
+            # tile batch neither kernel fills the GPU
+            branch = has_res and not fuse_res
+            if branch:
+                _tc_op(ol, split=sp, src0=x, src1=skip, w=ws.ptr(name + ".res.tcw"), tb=ws.ptr(name + ".res.tb"), nty=1, ntx=1, oy0=0,
+                       ox0=0, dst=res, ntot=cout, B=BT, nt=nt, flags=_lib.C["UCDIR_OP_FLAG_BRANCH"])
             _tc_op(ol, split=sp, src0=x, src1=skip, w=ws.ptr(name + ".conv1.tcw"), tb=ws.ptr(name + ".conv1.tb"),
                    tg=ws.ptr(name + ".conv1.tg"), gn=1, ncls=9, act=1, dst=h1, ntot=cout, B=BT, nt=nt,
                    **(dict(w2=ws.ptr(name + ".res.tcw"), tb2=ws.ptr(name + ".res.tb"), dst_res=res) if fuse_res else {}))
             if has_res:
-                if not fuse_res:
-                    _tc_op(ol, split=sp, src0=x, src1=skip, w=ws.ptr(name + ".res.tcw"), tb=ws.ptr(name + ".res.tb"), nty=1, ntx=1, oy0=0,
-                           ox0=0, dst=res, ntot=cout, B=BT, nt=nt)
                 own_res = True
             else:
                 if skip is not None:
@@ -967,7 +973,8 @@ class UNetEngine:
             kc, kb, mnt, nsplit = tc_mix_tiling(cout)
             _tc_op(ol, split=sp, src0=h1, w=ws.ptr(name + ".spdy.tcw"), tb=ws.ptr(name + ".spdy.tb"), tg=ws.ptr(name + ".spdy.tg"),
                    gn=1, ncls=9, groups=rb.nset, kc=kc, kb=kb, nsplit=nsplit, nt=mnt, mode=1, att=gmaps[k].data_ptr(),
-                   attw=attw.data_ptr() + k * 8 * 4, attw_stride=attw_stride, res=res, dst=out, ntot=cout * rb.nset, B=BT)
+                   attw=attw.data_ptr() + k * 8 * 4, attw_stride=attw_stride, res=res, dst=out, ntot=cout * rb.nset, B=BT,
+                   flags=_lib.C["UCDIR_OP_FLAG_JOIN"] if branch else 0)
             bld.release(h1)
             if own_res:
                 bld.release(res)
