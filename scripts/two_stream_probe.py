@@ -1,5 +1,6 @@
 """Probe: do two independent half-batches on two CUDA streams hide the per-launch fixed cost (pipeline fill / drain of ~135
-dependent launches per step)?  16 tiles in one session vs 2 x 8 tiles in two sessions, sequential and concurrent."""
+dependent launches per step)?  16 tiles in one session vs 2 x 8 tiles in two sessions, sequential and concurrent (default), or any
+image size: `python scripts/two_stream_probe.py 1024 1024` = the 121-tile step against two half images on two streams."""
 import os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -36,10 +37,11 @@ def timeit(fn, n=30):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 
-full = make(384, 384)
+FH, FW = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (384, 384)     # e.g. 1024 1024: the 121-tile step
+full = make(FH, FW)
 print("tiles", full.geo.n_tiles)
 t_full = timeit(lambda: full.step_resident(table[10]))
-a, b = make(384, 192), make(384, 192)
+a, b = make(FH, FW // 2), make(FH, FW // 2)
 print("half tiles", a.geo.n_tiles)
 t_seq = timeit(lambda: (a.step_resident(table[10]), b.step_resident(table[10])))
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
@@ -50,4 +52,5 @@ def conc():
     with torch.cuda.stream(s2): b.step_resident(table[10])
     cur.wait_stream(s1); cur.wait_stream(s2)
 t_conc = timeit(conc)
-print("PDL=%s: 16 tiles one graph %.3f ms | 2 x 8 tiles sequential %.3f ms | 2 x 8 tiles on two streams %.3f ms" % (pdl, t_full, t_seq, t_conc))
+print("PDL=%s: %d tiles one graph %.3f ms (%.4f ms/tile) | 2 x %d tiles sequential %.3f ms | on two streams %.3f ms (%.4f ms/tile)" % (
+    pdl, full.geo.n_tiles, t_full, t_full / full.geo.n_tiles, a.geo.n_tiles, t_seq, t_conc, t_conc / (2 * a.geo.n_tiles)))
