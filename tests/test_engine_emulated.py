@@ -434,6 +434,41 @@ def test_product_schedule_buffers_bit_exact(golden, sid_weights):
     assert other._step_scalars(1) == net._step_scalars(1)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32_tc"])
+def test_graph_branches_bracket_the_res_conv(emulated, golden, sid_weights, precision):
+    """UCDIR_OP_FLAG_BRANCH / JOIN (step graph with branches, include/ucdir_b200.h): every BRANCH op is a block's separate 1x1
+    res_conv, directly followed by the conv1 that reads the same input(s) and writes something else, and the next flagged op is
+    the JOIN on the integration conv that reads the res_conv's output as its residual -- nothing in between touches it."""
+    net, _ = sid_weights
+    unet = net.denoise_fn
+    eng = unet.engine()
+    eng.set_precision(precision)
+    try:
+        g = golden("unet")
+        unet(T(g["x6"]), T(g["level"]), T(g["guide"]))
+        sess = next(iter(eng._sessions.values()))
+        ops = sess.step_ops.ops
+        P = lambda o, k: o.p[_lib.C["UCDIR_TC_P_" + k]]
+        I = lambda o, k: o.i[_lib.C["UCDIR_TC_I_" + k]]
+        BR, JN = _lib.C["UCDIR_OP_FLAG_BRANCH"], _lib.C["UCDIR_OP_FLAG_JOIN"]
+        branches = [k for k, o in enumerate(ops) if o.flags & BR]
+        assert branches, "no branch in the step graph"
+        for k in branches:
+            rc, c1 = ops[k], ops[k + 1]
+            assert rc.kind == c1.kind == _lib.C["UCDIR_OP_TC_CONV"]
+            assert I(rc, "NTY") == 1 and I(rc, "NTX") == 1 and I(rc, "MODE") == 0 and not I(rc, "GN")          # the 1x1 res_conv
+            assert I(c1, "NTY") == 3 and c1.flags == 0 and not I(c1, "RES_FUSED")
+            assert P(c1, "SRC0") == P(rc, "SRC0") and P(c1, "SRC1") == P(rc, "SRC1")                            # same input(s)
+            assert P(c1, "DST") != P(rc, "DST") and P(rc, "DST") not in (P(c1, "SRC0"), P(c1, "SRC1"))
+            mix = ops[k + 2]
+            assert (mix.flags & JN) and I(mix, "MODE") == 1 and P(mix, "RES") == P(rc, "DST") and P(mix, "SRC0") == P(c1, "DST")
+        # a JOIN without a BRANCH before it does not occur, and blocks with a fused res_conv carry no flags
+        assert sum(1 for o in ops if o.flags & JN) == len(branches)
+        assert all(o.flags == 0 for o in ops if o.kind == _lib.C["UCDIR_OP_TC_CONV"] and I(o, "RES_FUSED"))
+    finally:
+        eng.set_precision("fp32")
+
+
 def test_fp32_tc_graph_meets_fp32_tolerance(emulated, golden, sid_weights):
     """precision "fp32_tc": split-operand (hi + lo bf16 pairs) tensor-core graph -- three K passes per tap, plane-pair
     activations, exact epilogue math -- executed by the CPU interpreter must meet the reference's fp32 tolerance
