@@ -70,9 +70,12 @@ def main():
     ap.add_argument("--split", action="store_true")
     ap.add_argument("--out", default="")
     ap.add_argument("--tiles", type=int, default=121)
+    ap.add_argument("--shapes", default="", help="C:S pairs instead of the default halo shapes, e.g. 512:16,512:8 (the streamed C = 512 levels)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     shapes = [(64, 128), (128, 64)] + ([] if a.split else [(256, 32)])
+    if a.shapes:
+        shapes = [tuple(int(v) for v in t.split(":")) for t in a.shapes.split(",")]
     libs = []
     for path in a.libs:
         lib = ctypes.CDLL(os.path.abspath(path))
