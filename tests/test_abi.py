@@ -69,6 +69,44 @@ def test_tc_schedule_routing():
     assert dense(64, 64, 0) == 0 and dense(256, 256, 1) == 0 and dense(64, 64, 1, ks=1) == 0
     assert dense(64, 64, 1, gn=0) == 2 and dense(64, 64, 1, stride=2) == 0
 
+    # fp32_tc (SPLIT) records: the halo mix kernel has a split form for C = 64 / 128 / 256, the halo dense kernel for the 16-channel
+    # in-conv and for conv1 with the fused res_conv; every other split record runs the streamed kernel
+    def sact(C, H, W):
+        return E.Act(torch.zeros(1), C, H, W, 1, True, True)
+
+    def mix_split(C):
+        ol = E.OpList()
+        kc, kb, nt, nsplit = E.tc_mix_tiling(C)
+        E._tc_op(ol, split=1, src0=sact(C, 32, 32), w=1, tb=1, tg=1, gn=1, ncls=9, groups=8, kc=kc, kb=kb, nsplit=nsplit, nt=nt, mode=1, att=1,
+                 attw=1, attw_stride=8, res=sact(C, 32, 32), dst=sact(C, 32, 32), ntot=8 * C, B=2, halo=1)
+        return _lib.tc_schedule(ol.array()[0])
+
+    def dense_split(C0, Cout, kc=64, fused=False, gn=1):
+        ol = E.OpList()
+        extra = dict(w2=1, tb2=1, dst_res=sact(Cout, 32, 32)) if fused else {}
+        E._tc_op(ol, split=1, **extra, src0=sact(C0, 32, 32), w=1, tb=1, tg=1 if gn else 0, gn=gn, ncls=9 if gn else 1, act=1, dst=sact(Cout, 32, 32),
+                 ntot=Cout, B=2, nt=E._tc_nt(Cout), halo=1, kc=kc)
+        _lib.check_ops(ol.array(), 1)
+        return _lib.tc_schedule(ol.array()[0])
+
+    assert [mix_split(C) for C in (64, 128, 256, 512)] == [1, 1, 1, 0]
+    assert dense_split(16, 64, kc=16, gn=0) == 2 and dense_split(128, 64, fused=True) == 2 and dense_split(64, 128, fused=True) == 2
+    assert dense_split(128, 64) == 0 and dense_split(256, 256) == 0
+
+
+def test_op_flags_are_part_of_the_record():
+    """UCDIR_OP_FLAG_BRANCH / JOIN (ABI 14): carried in ucdir_op_t.flags, accepted by the argument checker, named in the header."""
+    import torch
+    from ucdir_b200 import engine as E
+    assert _lib.C["UCDIR_OP_FLAG_BRANCH"] == 1 and _lib.C["UCDIR_OP_FLAG_JOIN"] == 2 and _lib.C["UCDIR_ABI_VERSION"] >= 14
+    a = lambda C: E.Act(torch.zeros(1), C, 32, 32, 1, True)
+    ol = E.OpList()
+    E._tc_op(ol, src0=a(256), w=1, tb=1, nty=1, ntx=1, oy0=0, ox0=0, dst=a(256), ntot=256, B=2, nt=256, flags=_lib.C["UCDIR_OP_FLAG_BRANCH"])
+    E._tc_op(ol, src0=a(256), w=1, tb=1, tg=1, gn=1, ncls=9, act=1, dst=a(256), ntot=256, B=2, nt=256)
+    arr = ol.array()
+    assert arr[0].flags == 1 and arr[1].flags == 0
+    _lib.check_ops(arr, 2)
+
 
 def test_c_abi_weight_packers_match_the_engine(tmp_path):
     """ucdir_pack_* (host-side C++, csrc/ucdir_pack.cu) against the torch packers the engine uses (engine.pack_tc_* / pack_conv_f32):
